@@ -1,0 +1,274 @@
+/*
+ * afs_b200.h -- C ABI of the B200-native area-function-to-speech hot path.
+ *
+ * This is the drop-in boundary for the acoustic back end of
+ * Simon-Stone/AreaFunctionSynthesis (VocalTractLab classes).  The reference has
+ * no FFI of its own; the boundary is the public C++
+ * class API used by its two callers, restated here as batched, POD-only entry
+ * points.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference repository root, src/Backend/...).
+ *
+ * Conventions
+ *   - plain pointers and sizes only, no C++/torch types;
+ *   - every function returns an afs_status (0 = success); nothing prints,
+ *     nothing throws;
+ *   - all buffers are caller-owned; "_device" variants take device pointers
+ *     and a cudaStream_t passed as void* and are asynchronous on that stream;
+ *   - there is NO CPU fallback: without a CUDA device afs_create fails with
+ *     AFS_ERR_NO_DEVICE and every compute entry point fails with
+ *     AFS_ERR_BAD_CONTEXT.
+ */
+#ifndef AFS_B200_H
+#define AFS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFS_VERSION 100 /* 0.1.0 */
+
+/* ---- tube topology (Tube.h:53-79) ---------------------------------------- */
+#define AFS_NUM_TRACHEA_SECTIONS 23
+#define AFS_NUM_GLOTTIS_SECTIONS 2
+#define AFS_NUM_PHARYNX_SECTIONS 16
+#define AFS_NUM_MOUTH_SECTIONS 24
+#define AFS_NUM_PM_SECTIONS 40 /* pharynx + mouth: the dynamic part */
+#define AFS_NUM_NOSE_SECTIONS 19
+#define AFS_NUM_FOSSA_SECTIONS 5
+#define AFS_NUM_SINUS_SECTIONS 4
+#define AFS_NUM_SECTIONS 93
+#define AFS_NUM_CURRENTS 97 /* TdsModel.h:37 */
+
+#define AFS_FIRST_TRACHEA_SECTION 0
+#define AFS_LOWER_GLOTTIS_SECTION 23
+#define AFS_UPPER_GLOTTIS_SECTION 24
+#define AFS_FIRST_PHARYNX_SECTION 25
+#define AFS_FIRST_MOUTH_SECTION 41
+#define AFS_FIRST_NOSE_SECTION 65
+#define AFS_FIRST_FOSSA_SECTION 84
+#define AFS_FIRST_SINUS_SECTION 89
+
+/* Tube::Articulator (Tube.h:23-31) */
+enum afs_articulator {
+  AFS_VOCAL_FOLDS = 0,
+  AFS_TONGUE = 1,
+  AFS_LOWER_INCISORS = 2,
+  AFS_LOWER_LIP = 3,
+  AFS_OTHER_ARTICULATOR = 4
+};
+
+/* TlModel::SpectrumType (TlModel.h:40-43) */
+enum afs_spectrum_type {
+  AFS_INPUT_IMPEDANCE = 0,
+  AFS_OUTPUT_IMPEDANCE = 1,
+  AFS_FLOW_SOURCE_TF = 2,
+  AFS_PRESSURE_SOURCE_TF = 3,
+  AFS_RADIATION = 4
+};
+
+/* TlModel::RadiationType (TlModel.h:31-38) */
+enum afs_radiation_type {
+  AFS_NO_RADIATION = 0,
+  AFS_PISTONINSPHERE_RADIATION = 1,
+  AFS_PISTONINWALL_RADIATION = 2,
+  AFS_PARALLEL_RADIATION = 3
+};
+
+/* TdsModel::GlottisLossOptions / SolverType (TdsModel.h:60-73) */
+enum afs_glottis_loss { AFS_STANDARD_ENTRANCE_LOSS = 0, AFS_ENTRANCE_LOSS_VAN_DEN_BERG = 1 };
+
+typedef enum afs_status {
+  AFS_OK = 0,
+  AFS_ERR_NO_DEVICE = 1,      /* no CUDA device / driver: there is no CPU fallback */
+  AFS_ERR_BAD_CONTEXT = 2,
+  AFS_ERR_BAD_ARGUMENT = 3,
+  AFS_ERR_UNSUPPORTED = 4,    /* option of the reference not implemented on the device path */
+  AFS_ERR_CUDA = 5,           /* a CUDA call failed; see afs_last_cuda_error */
+  AFS_ERR_OUT_OF_MEMORY = 6
+} afs_status;
+
+/*
+ * One control frame of the area function: the part of a reference `Tube`
+ * that changes during speech (Tube.h:33-51, 100-118; written by
+ * Tube::setPharynxMouthGeometry Tube.cpp:323, setVelumOpening :402,
+ * setGlottisGeometry :358, setAspirationStrength :425).  The static cavities
+ * (trachea, nose, sinuses, piriform fossa) are those of Tube::Tube()
+ * (Tube.cpp:46-260) with the default lengths (Tube.cpp:29-32).
+ *
+ * A `Tube` cannot cross a C ABI (it holds pointers into itself, SURVEY.md
+ * App. D), hence this POD.  1184 bytes.
+ */
+typedef struct afs_tube_frame {
+  double area_cm2[AFS_NUM_PM_SECTIONS];
+  double length_cm[AFS_NUM_PM_SECTIONS];
+  double laterality[AFS_NUM_PM_SECTIONS];
+  double incisor_pos_cm;       /* Tube::teethPosition_cm */
+  double velum_area_cm2;       /* argument of Tube::setVelumOpening */
+  double aspiration_dB;        /* Tube::aspirationStrength_dB (TL ignores it) */
+  double glottis_area_cm2[2];  /* TL only: TDS takes these from the glottis model */
+  double glottis_length_cm[2]; /* TL only */
+  double reserved;             /* keeps the int block 8-byte aligned; must be 0 */
+  int32_t articulator[AFS_NUM_PM_SECTIONS]; /* enum afs_articulator */
+} afs_tube_frame;
+
+/* TriangularGlottis control parameters (TriangularGlottis.h:27-38, defaults
+ * TriangularGlottis.cpp:17-26): f0 Hz, pressure dPa, lower/upper rest
+ * displacement cm, arytenoid area cm^2, aspiration strength dB. */
+#define AFS_NUM_GLOTTIS_CONTROL 6
+/* TriangularGlottis static parameters (TriangularGlottis.h:40-61, defaults
+ * TriangularGlottis.cpp:38-56). */
+#define AFS_NUM_GLOTTIS_STATIC 16
+
+/* TlModel::Options (TlModel.h:47-59); defaults of TlModel::TlModel()
+ * (TlModel.cpp:30-39) via afs_tl_options_default. */
+typedef struct afs_tl_options {
+  int32_t radiation; /* enum afs_radiation_type */
+  int32_t boundary_layer;
+  int32_t heat_conduction;
+  int32_t soft_walls;
+  int32_t hagen_resistance;
+  int32_t inner_length_corrections;
+  int32_t lumped_elements; /* 0 (wave propagation with cosh/sinh) is AFS_ERR_UNSUPPORTED */
+  int32_t paranasal_sinuses;
+  int32_t piriform_fossa;
+  int32_t static_pressure_drops;
+  /* TlModel keeps the lung pressure as hidden state (TlModel.cpp:253-260,
+   * SURVEY.md App. D); here it is explicit.  Default 0. */
+  double lung_pressure_dPa;
+} afs_tl_options;
+
+/* TdsModel::Options (TdsModel.h:75-87); defaults of TdsModel::TdsModel()
+ * (TdsModel.cpp:35-44) via afs_tds_options_default, except that the default
+ * here is generate_noise_sources = 0 (the parity-gated configuration). */
+typedef struct afs_tds_options {
+  int32_t turbulence_losses;
+  int32_t soft_walls;
+  int32_t generate_noise_sources;
+  int32_t radiation_from_skin;
+  int32_t piriform_fossa;
+  int32_t inner_length_corrections;
+  int32_t transvelar_coupling;   /* 1 is AFS_ERR_UNSUPPORTED */
+  int32_t glottis_loss_option;   /* enum afs_glottis_loss; VARIABLE_ENTRANCE_LOSS unsupported */
+  double flow_separation_area_ratio;
+  /* TriangularGlottis static parameters; afs_tds_options_default fills the
+   * reference defaults. */
+  double glottis_static[AFS_NUM_GLOTTIS_STATIC];
+} afs_tds_options;
+
+typedef struct afs_ctx afs_ctx; /* opaque: one CUDA device, scratch buffers, one stream */
+
+/* ---- life cycle ----------------------------------------------------------- */
+int afs_version(void);
+const char *afs_status_string(int status);
+/* Replaces `new TdsModel()` / `new TlModel()` (Data.cpp:78-88,
+ * Synthesizer.cpp:48): binds one CUDA device. */
+int afs_create(afs_ctx **ctx, int device_ordinal);
+int afs_destroy(afs_ctx *ctx);
+/* Text of the last CUDA error seen by this context ("" if none). */
+const char *afs_last_cuda_error(const afs_ctx *ctx);
+/* Number of kernel launches issued by this context so far (bench.py's
+ * `gpu_launches` claim is counted here, not guessed). */
+int64_t afs_launch_count(const afs_ctx *ctx);
+
+void afs_tl_options_default(afs_tl_options *opts);   /* TlModel.cpp:30-47 */
+void afs_tds_options_default(afs_tds_options *opts); /* TdsModel.cpp:35-44 */
+/* A frame equal to a freshly constructed reference Tube (Tube.cpp:46-73,
+ * 265-315): 40 sections of 4 cm^2 x 0.4 cm, velum 0, glottis 0.1 cm^2. */
+void afs_tube_frame_default(afs_tube_frame *frame);
+
+/* ---- TlModel: transfer-function sweep ------------------------------------- */
+/*
+ * Replaces TlModel::getSpectrum (TlModel.cpp:123-197) incl.
+ * prepareCalculations (:484-676) and getFlowSourceTF / getPressureSourceTF /
+ * getInputImpedance / getOutputImpedance (:987-1469) for a batch of tubes.
+ * The reference derives the bin grid from its compile-time SAMPLING_RATE and
+ * caps it at MAX_NUM_FREQ = 1024 (TlModel.h:89, TlModel.cpp:125-148); here
+ * (f0_hz, num_freq) are arguments: bin i is at i*f0_hz, i = 0..num_freq-1.
+ * Output: re/im [n_tubes][num_freq] (the non-negative-frequency half of the
+ * reference's ComplexSignal; Dsp.cpp:128-138 mirrors it).
+ * Host buffers; H2D/D2H copies happen inside the call.
+ */
+int afs_tl_sweep(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes,
+                 const afs_tube_frame *tubes, int spectrum_type, int section,
+                 double f0_hz, int num_freq, double *re, double *im);
+/* Same, device-resident tubes and outputs, asynchronous on `stream`. */
+int afs_tl_sweep_device(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes,
+                        const afs_tube_frame *d_tubes, int spectrum_type,
+                        int section, double f0_hz, int num_freq, double *d_re,
+                        double *d_im, void *stream);
+
+/*
+ * Replaces TlModel::getFormants (TlModel.cpp:280-461) for a batch of tubes:
+ * FLOW_SOURCE_TF at FIRST_PHARYNX_SECTION on the grid f0 = sampling_rate /
+ * spectrum_length (reference: 22050 / 2048), peak picking between 150 Hz and
+ * 7 kHz with parabolic interpolation and -3 dB bandwidths.
+ * Outputs per tube: formant_hz/bandwidth_hz [n_tubes][max_formants],
+ * num_formants [n_tubes], flags [n_tubes] (bit0 frictionNoise, bit1
+ * isClosure, bit2 isNasal).
+ */
+int afs_tl_formants(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes,
+                    const afs_tube_frame *tubes, double sampling_rate_hz,
+                    int spectrum_length, int max_formants, double *formant_hz,
+                    double *bandwidth_hz, int32_t *num_formants, int32_t *flags);
+
+/* ---- TdsModel + TriangularGlottis + driver loop ---------------------------- */
+/*
+ * Replaces, for a batch of independent utterances ("tracts"), the per-sample
+ * loop of Synthesizer::synthesizeSignalTds (Synthesizer.cpp:515-639): for
+ * every audio sample Tube::interpolate (Tube.cpp:438-505), glottis parameter
+ * lerp + TriangularGlottis::calcGeometry/incTime (TriangularGlottis.cpp:154-
+ * 397), TdsModel::setTube/setPressureSource/proceedTimeStep (TdsModel.cpp:
+ * 552-711: prepareTimeStep :718, calcMatrix :1785, linear solve :2231,
+ * updateVariables :2046), flow differentiation and the Chebyshev-8 output
+ * low-pass (Synthesizer.cpp:52,614-627).
+ *
+ * Control frames: tract b has n_frames frames tubes[b*n_frames + k] and
+ * glottis[(b*n_frames + k)*6 ...].  Frame 0 primes the driver (the reference's
+ * first call only stores prevTube, Synthesizer.cpp:522-532); frame k >= 1
+ * produces frame_len[k-1] output samples interpolating linearly from frame
+ * k-1 to frame k (ratio i/N, right end excluded), exactly like one reference
+ * call synthesizeSignalTds(tube_k, glottis_k, frame_len[k-1], out).
+ * The simulation runs at fs_tds_hz = sr_factor * output rate (reference:
+ * TDS_SAMPLING_RATE = TDS_SR_FACTOR * SAMPLING_RATE, Constants.h:22-26).
+ *
+ * Outputs: audio [n_tracts][n_out], n_out = sum(frame_len) (range ~[-1,1]);
+ * flow (nullable) [n_tracts][n_out*sr_factor], the radiated flow returned by
+ * TdsModel::proceedTimeStep per simulation step; status (nullable)
+ * [n_tracts]: bit0 = non-finite value seen (the reference prints and carries
+ * on, TdsModel.cpp:2267).
+ * seeds (nullable) [n_tracts]: per-tract srand() seeds, used only with
+ * generate_noise_sources.
+ */
+int afs_tds_synthesize(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts,
+                       int n_frames, const int32_t *frame_len,
+                       const afs_tube_frame *tubes, const double *glottis,
+                       double fs_tds_hz, int sr_factor, const uint32_t *seeds,
+                       double *audio, double *flow, uint32_t *status);
+/* Same with device-resident tubes/glottis/outputs (frame_len stays on the
+ * host), asynchronous on `stream`. */
+int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts,
+                              int n_tracts, int n_frames,
+                              const int32_t *frame_len,
+                              const afs_tube_frame *d_tubes,
+                              const double *d_glottis, double fs_tds_hz,
+                              int sr_factor, const uint32_t *d_seeds,
+                              double *d_audio, double *d_flow,
+                              uint32_t *d_status, void *stream);
+
+/* ---- host-side helpers of the boundary (no device work) -------------------- */
+/* IirFilter::createChebyshev low-pass (IirFilter.cpp:286-432): recursion
+ * coefficients a[0..num_poles], b[0..num_poles] (b[0] = 0) for
+ * y[n] = sum a_i x[n-i] + sum b_i y[n-i].  num_poles even, <= 16. */
+int afs_chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double *b);
+/* OneDimAreaFunction::calculateOneDimTubeFunction (OneDimAreaFunction.cpp:
+ * 23-138): 16 parameters (Llar, Alar, powLar, xp, Ap, powP, xc, Ac, powC, xa,
+ * Aa, powA, xin, Ain, Lvt, Alip) -> the 40 pharynx/mouth sections of `frame`
+ * (other fields untouched). Input generator for benches; host code. */
+int afs_area_function_to_frame(const double params[16], afs_tube_frame *frame);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFS_B200_H */

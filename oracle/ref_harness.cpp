@@ -1,0 +1,262 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// extern "C" wrapper around the UNMODIFIED reference classes (compiled from
+// /root/reference/src/Backend where they lie, see oracle/Makefile) so that
+// tests and bench.py's cpu_baseline leg can run the real reference.
+// The driver loop below restates Synthesizer::synthesizeSignalTds
+// (Synthesizer.cpp:515-639) because Synthesizer itself needs wxWidgets and
+// PortAudio; everything it calls is the reference's own code.
+#include "../include/afs_b200.h"
+
+#include "TdsModel.h"
+#include "TlModel.h"
+#include "TriangularGlottis.h"
+#include "OneDimAreaFunction.h"
+#include "IirFilter.h"
+#include "Tube.h"
+
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+static void frame_to_tube(const afs_tube_frame *f, Tube *t) {
+  Tube::Articulator art[Tube::NUM_PHARYNX_MOUTH_SECTIONS];
+  for (int i = 0; i < Tube::NUM_PHARYNX_MOUTH_SECTIONS; i++) art[i] = (Tube::Articulator)f->articulator[i];
+  t->setPharynxMouthGeometry(f->length_cm, f->area_cm2, art, f->laterality, f->incisor_pos_cm);
+  t->setGlottisGeometry(f->glottis_length_cm, f->glottis_area_cm2);
+  t->setVelumOpening(f->velum_area_cm2);
+  t->setAspirationStrength(f->aspiration_dB);
+}
+
+extern "C" {
+
+int ref_sampling_rate() { return SAMPLING_RATE; }
+int ref_tds_sr_factor() { return TDS_SR_FACTOR; }
+
+// OneDimAreaFunction::setParameters + calculateOneDimTubeFunction -> frame
+void ref_area_function_to_frame(const double *params16, afs_tube_frame *frame) {
+  OneDimAreaFunction af;
+  OneDimAreaFunction::Param p[OneDimAreaFunction::NUM_AF_PARAMS];
+  af.getParameters(p);
+  for (int i = 0; i < OneDimAreaFunction::NUM_AF_PARAMS; i++) p[i].x = params16[i];
+  af.setParameters(p);
+  Tube t;
+  af.calculateOneDimTubeFunction(&t);
+  for (int i = 0; i < Tube::NUM_PHARYNX_MOUTH_SECTIONS; i++) {
+    // NB: Tube clamps the area to MIN_AREA_CM2 on the way in (Tube.cpp:337).
+    frame->area_cm2[i] = t.pharynxMouthSection[i].area_cm2;
+    frame->length_cm[i] = t.pharynxMouthSection[i].length_cm;
+    frame->laterality[i] = t.pharynxMouthSection[i].laterality;
+    frame->articulator[i] = (int)t.pharynxMouthSection[i].articulator;
+  }
+  frame->incisor_pos_cm = t.teethPosition_cm;
+}
+
+// Dump all 93 sections of the Tube a frame expands to (area,length,volume,pos,Mw,Bw,Kw).
+void ref_frame_sections(const afs_tube_frame *frame, double *out93x7) {
+  Tube t;
+  frame_to_tube(frame, &t);
+  for (int i = 0; i < Tube::NUM_SECTIONS; i++) {
+    Tube::Section *s = t.section[i];
+    double *o = out93x7 + 7 * i;
+    o[0] = s->area_cm2; o[1] = s->length_cm; o[2] = s->volume_cm3; o[3] = s->pos_cm;
+    o[4] = s->wallMass_cgs; o[5] = s->wallResistance_cgs; o[6] = s->wallStiffness_cgs;
+  }
+}
+
+static void set_tl_options(TlModel *tl, const afs_tl_options *o) {
+  tl->options.radiation = (TlModel::RadiationType)o->radiation;
+  tl->options.boundaryLayer = o->boundary_layer;
+  tl->options.heatConduction = o->heat_conduction;
+  tl->options.softWalls = o->soft_walls;
+  tl->options.hagenResistance = o->hagen_resistance;
+  tl->options.innerLengthCorrections = o->inner_length_corrections;
+  tl->options.lumpedElements = o->lumped_elements;
+  tl->options.paranasalSinuses = o->paranasal_sinuses;
+  tl->options.piriformFossa = o->piriform_fossa;
+  tl->options.staticPressureDrops = o->static_pressure_drops;
+  tl->setLungPressure(o->lung_pressure_dPa);
+}
+
+// TlModel::getSpectrum on a fresh TlModel per tube (a reused
+// object carries hidden lung-pressure state).  spectrum_length picks the grid:
+// f0 = SAMPLING_RATE / spectrum_length; returns numFreq written per tube.
+int ref_tl_spectrum(const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
+                    int type, int section, int spectrum_length, int max_bins,
+                    double *re, double *im, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  std::vector<int> nf(n_threads, 0);
+  auto work = [&](int tid) {
+    TlModel *tl = new TlModel();  // 6 MB object: heap
+    ComplexSignal s;
+    for (int b = tid; b < n_tubes; b += n_threads) {
+      set_tl_options(tl, opts);
+      frame_to_tube(&tubes[b], &tl->tube);
+      tl->getSpectrum((TlModel::SpectrumType)type, &s, spectrum_length, section);
+      int n = 0;
+      // numFreq is private; recover it as in TlModel.cpp:131-143.
+      double f0 = (double)SAMPLING_RATE / (double)spectrum_length;
+      n = (int)(10100.0 / f0);
+      if (n > 2048) n = 2048;  // MAX_NUM_FREQ of the patched build
+      if (n >= spectrum_length / 2) n = spectrum_length / 2 - 1;
+      if (n > max_bins) n = max_bins;
+      for (int i = 0; i < n; i++) {
+        re[(size_t)b * max_bins + i] = s.re[i];
+        im[(size_t)b * max_bins + i] = s.im[i];
+      }
+      nf[tid] = n;
+    }
+    delete tl;
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto &t : th) t.join();
+  return nf[0];
+}
+
+// TlModel::getFormants on a fresh TlModel per tube.
+void ref_tl_formants(const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
+                     int max_formants, double *freq, double *bw, int32_t *num, int32_t *flags) {
+  TlModel *tl = new TlModel();
+  for (int b = 0; b < n_tubes; b++) {
+    delete tl;
+    tl = new TlModel();
+    set_tl_options(tl, opts);
+    frame_to_tube(&tubes[b], &tl->tube);
+    int n = 0;
+    bool friction = false, closure = false, nasal = false;
+    tl->getFormants(freq + (size_t)b * max_formants, bw + (size_t)b * max_formants, n, max_formants,
+                    friction, closure, nasal);
+    num[b] = n;
+    flags[b] = (friction ? 1 : 0) | (closure ? 2 : 0) | (nasal ? 4 : 0);
+  }
+  delete tl;
+}
+
+// One utterance through the reference TdsModel + TriangularGlottis, driver
+// loop restated from Synthesizer.cpp:515-639 (outputFlow[] starts at 0; the
+// reference leaves it uninitialised).  Not thread safe when noise is on
+// (libc rand()).
+static void tds_one(const afs_tds_options *o, int n_frames, const int32_t *frame_len,
+                    const afs_tube_frame *frames, const double *glottis, unsigned seed,
+                    double *audio, double *flow, double *state_dump, int dump_step) {
+  TdsModel *tds = new TdsModel();
+  TriangularGlottis *gl = new TriangularGlottis();
+  tds->options.turbulenceLosses = o->turbulence_losses;
+  tds->options.softWalls = o->soft_walls;
+  tds->options.generateNoiseSources = o->generate_noise_sources;
+  tds->options.radiationFromSkin = o->radiation_from_skin;
+  tds->options.piriformFossa = o->piriform_fossa;
+  tds->options.innerLengthCorrections = o->inner_length_corrections;
+  tds->options.transvelarCoupling = o->transvelar_coupling;
+  tds->options.glottisLossOption = o->glottis_loss_option;
+  tds->options.flowSeparationAreaRatio = o->flow_separation_area_ratio;
+  for (int i = 0; i < AFS_NUM_GLOTTIS_STATIC; i++) gl->staticParam[i].x = o->glottis_static[i];
+  tds->resetMotion();
+  gl->resetMotion();
+  if (o->generate_noise_sources) srand(seed);
+
+  IirFilter outputPressureFilter;
+  outputPressureFilter.createChebyshev(7000.0 / (double)TDS_SAMPLING_RATE, false, 8);
+  outputPressureFilter.resetBuffers();
+  double prevFlow = 0.0;
+
+  Tube tube, prevTube, newTube;
+  frame_to_tube(&frames[0], &prevTube);
+  const double *prevG = glottis;
+  long outPos = 0, flowPos = 0;
+  double length_cm[2], area_cm2[2], pressure_dPa[4];
+
+  for (int k = 1; k < n_frames; k++) {
+    frame_to_tube(&frames[k], &newTube);
+    const double *newG = glottis + (size_t)k * AFS_NUM_GLOTTIS_CONTROL;
+    int numNewSamples = frame_len[k - 1] * TDS_SR_FACTOR;
+    if (numNewSamples < 1) numNewSamples = 1;
+    for (int i = 0; i < numNewSamples; i++) {
+      double ratio = (double)i / (double)numNewSamples;
+      double ratio1 = 1.0 - ratio;
+      tube.interpolate(&prevTube, &newTube, ratio);
+      for (int j = 0; j < AFS_NUM_GLOTTIS_CONTROL; j++) gl->controlParam[j].x = ratio1 * prevG[j] + ratio * newG[j];
+      gl->calcGeometry();
+      gl->getTubeData(length_cm, area_cm2);
+      tube.setGlottisGeometry(length_cm, area_cm2);
+      tube.setAspirationStrength(gl->getAspirationStrength_dB());
+      tds->setTube(&tube, tds->getSampleIndex() != 0);
+      tds->setFlowSource(0.0, -1);
+      tds->setPressureSource(gl->controlParam[Glottis::PRESSURE].x, Tube::FIRST_TRACHEA_SECTION);
+      pressure_dPa[0] = tds->getSectionPressure(Tube::LAST_TRACHEA_SECTION);
+      pressure_dPa[1] = tds->getSectionPressure(Tube::LOWER_GLOTTIS_SECTION);
+      pressure_dPa[2] = tds->getSectionPressure(Tube::UPPER_GLOTTIS_SECTION);
+      pressure_dPa[3] = tds->getSectionPressure(Tube::FIRST_PHARYNX_SECTION);
+      gl->incTime(1.0 / (double)TDS_SAMPLING_RATE, pressure_dPa);
+      double u = tds->proceedTimeStep();
+      int pos = tds->getSampleIndex();
+      if (flow) flow[flowPos] = u;
+      flowPos++;
+      if (state_dump && pos == dump_step) {
+        // [0..92] pressure, [93..185] pressureRate, [186..278] wallCurrent,
+        // [279..375] current magnitude, [376..472] magnitudeRate
+        for (int s = 0; s < 93; s++) {
+          state_dump[s] = tds->tubeSection[s].pressure;
+          state_dump[93 + s] = tds->tubeSection[s].pressureRate;
+          state_dump[186 + s] = tds->tubeSection[s].wallCurrent;
+        }
+        for (int c = 0; c < 97; c++) {
+          state_dump[279 + c] = tds->branchCurrent[c].magnitude;
+          state_dump[376 + c] = tds->branchCurrent[c].magnitudeRate;
+        }
+      }
+      double outP = (u - prevFlow) / tds->timeStep;
+      prevFlow = u;
+      double filt = outputPressureFilter.getOutputSample(outP);
+      if ((pos % TDS_SR_FACTOR) == 0) {
+        double s = filt * 0.004;
+        audio[i / TDS_SR_FACTOR + outPos] = s / SHRT_MAX;
+      }
+    }
+    outPos += frame_len[k - 1];
+    prevTube = newTube;
+    prevG = newG;
+  }
+  delete tds;
+  delete gl;
+}
+
+// Batch of utterances; n_threads > 1 only legal with noise off.
+void ref_tds_synthesize(const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
+                        const afs_tube_frame *tubes, const double *glottis, const uint32_t *seeds,
+                        double *audio, double *flow, int n_threads) {
+  long n_out = 0;
+  for (int k = 0; k + 1 < n_frames; k++) n_out += frame_len[k];
+  if (n_threads < 1 || opts->generate_noise_sources) n_threads = 1;
+  auto work = [&](int tid) {
+    for (int b = tid; b < n_tracts; b += n_threads) {
+      tds_one(opts, n_frames, frame_len, tubes + (size_t)b * n_frames,
+              glottis + (size_t)b * n_frames * AFS_NUM_GLOTTIS_CONTROL, seeds ? seeds[b] : 1u,
+              audio + (size_t)b * n_out, flow ? flow + (size_t)b * n_out * TDS_SR_FACTOR : nullptr, nullptr, 0);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto &t : th) t.join();
+}
+
+// Single utterance with a state dump after simulation step `dump_step` (1-based).
+void ref_tds_state_after(const afs_tds_options *opts, int n_frames, const int32_t *frame_len,
+                         const afs_tube_frame *tubes, const double *glottis, int dump_step,
+                         double *audio, double *flow, double *state473) {
+  tds_one(opts, n_frames, frame_len, tubes, glottis, 1u, audio, flow, state473, dump_step);
+}
+
+// IirFilter::createChebyshev (low-pass) coefficients.
+void ref_chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double *b) {
+  IirFilter f;
+  f.createChebyshev(cutoff_ratio, false, num_poles);
+  for (int i = 0; i <= num_poles; i++) { a[i] = f.a[i]; b[i] = f.b[i]; }
+}
+
+}  // extern "C"
