@@ -171,3 +171,39 @@ def load_default_params(path="/root/reference/Default.params"):
                 names.append(parts[0].strip())
                 rows.append([float(x) for x in parts[1:17]])
     return names, np.array(rows)
+
+
+class Oracle:
+    """The plain-C restatement (oracle/afs_oracle.c)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "liboracle.so")
+        src = os.path.join(HERE, "afs_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build("oracle")
+        self.lib = C.CDLL(path)
+
+    def expand_frame(self, frame):
+        dt = np.dtype([("v", "<f8", (8,)), ("articulator", "<i4"), ("_pad", "<i4")])
+        out = np.zeros(93, dtype=dt)
+        self.lib.orc_expand_frame(_ptr(frame), _ptr(out))
+        return out  # v = pos, area, length, volume, Mw, Bw, Kw, laterality
+
+    def tl_spectrum(self, frames, f0_hz, num_freq, opts=None, type_=2, section=25):
+        opts = opts or tl_options_default()
+        n = len(frames)
+        re = np.zeros((n, num_freq)); im = np.zeros((n, num_freq))
+        rc = self.lib.orc_tl_spectrum(C.byref(opts), n, _ptr(np.ascontiguousarray(frames)), type_, section,
+                                      C.c_double(f0_hz), num_freq, _ptr(re), _ptr(im))
+        assert rc == 0, rc
+        return re, im
+
+    def tl_formants(self, frames, opts=None, sampling_rate=22050.0, spectrum_length=2048, max_formants=8):
+        opts = opts or tl_options_default()
+        n = len(frames)
+        f = np.zeros((n, max_formants)); bw = np.zeros((n, max_formants))
+        num = np.zeros(n, dtype=np.int32); flags = np.zeros(n, dtype=np.int32)
+        rc = self.lib.orc_tl_formants(C.byref(opts), n, _ptr(np.ascontiguousarray(frames)), C.c_double(sampling_rate),
+                                      spectrum_length, max_formants, _ptr(f), _ptr(bw), _ptr(num), _ptr(flags))
+        assert rc == 0, rc
+        return f, bw, num, flags
