@@ -1,0 +1,23 @@
+"""areafunctionsynthesis_b200 -- B200-native area-function-to-speech hot path.
+
+Thin ctypes layer over the C ABI (include/afs_b200.h, libafs_b200.so).  The
+product is the CUDA library; Python is only test/bench plumbing.  There is no
+CPU fallback: creating a `Context` without the built library or without a CUDA
+device raises.
+"""
+from .api import (  # noqa: F401
+    FRAME_DTYPE,
+    AfsError,
+    Context,
+    TdsOptions,
+    TlOptions,
+    area_function_to_frames,
+    chebyshev_lowpass,
+    default_frames,
+    library_path,
+    load_library,
+    tds_options_default,
+    tl_options_default,
+)
+
+__version__ = "0.1.0"

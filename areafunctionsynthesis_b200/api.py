@@ -1,0 +1,232 @@
+"""ctypes bindings of include/afs_b200.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NUM_PM = 40
+NUM_GLOTTIS_CONTROL = 6
+
+# afs_tube_frame (include/afs_b200.h)
+FRAME_DTYPE = np.dtype(
+    [
+        ("area_cm2", "<f8", (NUM_PM,)),
+        ("length_cm", "<f8", (NUM_PM,)),
+        ("laterality", "<f8", (NUM_PM,)),
+        ("incisor_pos_cm", "<f8"),
+        ("velum_area_cm2", "<f8"),
+        ("aspiration_dB", "<f8"),
+        ("glottis_area_cm2", "<f8", (2,)),
+        ("glottis_length_cm", "<f8", (2,)),
+        ("reserved", "<f8"),
+        ("articulator", "<i4", (NUM_PM,)),
+    ]
+)
+assert FRAME_DTYPE.itemsize == 1184
+
+SPECTRUM_TYPES = {"input_impedance": 0, "output_impedance": 1, "flow_source_tf": 2, "pressure_source_tf": 3,
+                  "radiation": 4}
+FIRST_PHARYNX_SECTION = 25
+
+
+class AfsError(RuntimeError):
+    pass
+
+
+class TlOptions(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "radiation", "boundary_layer", "heat_conduction", "soft_walls", "hagen_resistance",
+        "inner_length_corrections", "lumped_elements", "paranasal_sinuses", "piriform_fossa",
+        "static_pressure_drops")] + [("lung_pressure_dPa", C.c_double)]
+
+
+class TdsOptions(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "turbulence_losses", "soft_walls", "generate_noise_sources", "radiation_from_skin",
+        "piriform_fossa", "inner_length_corrections", "transvelar_coupling", "glottis_loss_option")] + [
+        ("flow_separation_area_ratio", C.c_double), ("glottis_static", C.c_double * 16)]
+
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(HERE, "libafs_b200.so")
+
+
+def load_library():
+    """Load libafs_b200.so; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise AfsError(f"{path} is missing: build it with `python -m areafunctionsynthesis_b200.build` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.afs_status_string.restype = C.c_char_p
+    lib.afs_last_cuda_error.restype = C.c_char_p
+    lib.afs_last_cuda_error.argtypes = [C.c_void_p]
+    lib.afs_launch_count.restype = C.c_int64
+    lib.afs_launch_count.argtypes = [C.c_void_p]
+    lib.afs_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.afs_destroy.argtypes = [C.c_void_p]
+    vp, dbl, i32 = C.c_void_p, C.c_double, C.c_int
+    lib.afs_tl_sweep.argtypes = [vp, vp, i32, vp, i32, i32, dbl, i32, vp, vp]
+    lib.afs_tl_sweep_device.argtypes = [vp, vp, i32, vp, i32, i32, dbl, i32, vp, vp, vp]
+    lib.afs_tl_formants.argtypes = [vp, vp, i32, vp, dbl, i32, i32, vp, vp, vp, vp]
+    lib.afs_tds_synthesize.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp]
+    lib.afs_tds_synthesize_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
+    lib.afs_chebyshev_lowpass.argtypes = [dbl, i32, vp, vp]
+    lib.afs_area_function_to_frame.argtypes = [vp, vp]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return C.c_void_p(a.data_ptr())
+    return a
+
+
+def _check(lib, rc, ctx=None):
+    if rc != 0:
+        msg = lib.afs_status_string(rc).decode()
+        if ctx is not None:
+            extra = lib.afs_last_cuda_error(ctx).decode()
+            if extra:
+                msg += f" [{extra}]"
+        raise AfsError(f"afs status {rc}: {msg}")
+
+
+def tl_options_default():
+    o = TlOptions()
+    load_library().afs_tl_options_default(C.byref(o))
+    return o
+
+
+def tds_options_default():
+    o = TdsOptions()
+    load_library().afs_tds_options_default(C.byref(o))
+    return o
+
+
+def default_frames(n):
+    lib = load_library()
+    f = np.zeros(n, dtype=FRAME_DTYPE)
+    if n:
+        lib.afs_tube_frame_default(_ptr(f[:1]))
+        f[:] = f[0]
+    return f
+
+
+def area_function_to_frames(params, frames=None):
+    """OneDimAreaFunction parameters [N,16] -> frames (pharynx/mouth part filled)."""
+    lib = load_library()
+    p = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+    out = default_frames(len(p)) if frames is None else frames
+    for i in range(len(p)):
+        _check(lib, lib.afs_area_function_to_frame(_ptr(p[i]), _ptr(out[i:i + 1])))
+    return out
+
+
+def chebyshev_lowpass(cutoff_ratio, poles):
+    lib = load_library()
+    a = np.zeros(poles + 1)
+    b = np.zeros(poles + 1)
+    _check(lib, lib.afs_chebyshev_lowpass(cutoff_ratio, poles, _ptr(a), _ptr(b)))
+    return a, b
+
+
+class Context:
+    """One CUDA device (afs_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib, self.lib.afs_create(C.byref(h), int(device)))
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.afs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self.lib.afs_launch_count(self.h))
+
+    # ---- TL ----------------------------------------------------------------
+    def tl_sweep(self, frames, f0_hz, num_freq, spectrum_type="flow_source_tf", section=FIRST_PHARYNX_SECTION,
+                 opts=None):
+        """Host buffers in/out (H2D + kernel + D2H).  Returns (re, im) [n, num_freq]."""
+        opts = opts or tl_options_default()
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        n = len(frames)
+        re = np.empty((n, num_freq))
+        im = np.empty((n, num_freq))
+        t = SPECTRUM_TYPES[spectrum_type] if isinstance(spectrum_type, str) else int(spectrum_type)
+        _check(self.lib, self.lib.afs_tl_sweep(self.h, C.byref(opts), n, _ptr(frames), t, int(section),
+                                               float(f0_hz), int(num_freq), _ptr(re), _ptr(im)), self.h)
+        return re, im
+
+    def tl_sweep_device(self, d_frames, n, f0_hz, num_freq, d_re, d_im, stream, spectrum_type=2,
+                        section=FIRST_PHARYNX_SECTION, opts=None):
+        """Device-resident variant: d_* are torch CUDA tensors (or raw pointers); async on `stream`."""
+        opts = opts or tl_options_default()
+        _check(self.lib, self.lib.afs_tl_sweep_device(self.h, C.byref(opts), int(n), _ptr(d_frames),
+                                                      int(spectrum_type), int(section), float(f0_hz), int(num_freq),
+                                                      _ptr(d_re), _ptr(d_im), C.c_void_p(stream)), self.h)
+
+    def tl_formants(self, frames, sampling_rate_hz=22050.0, spectrum_length=2048, max_formants=8, opts=None):
+        opts = opts or tl_options_default()
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        n = len(frames)
+        f = np.zeros((n, max_formants)); bw = np.zeros((n, max_formants))
+        num = np.zeros(n, dtype=np.int32); flags = np.zeros(n, dtype=np.int32)
+        _check(self.lib, self.lib.afs_tl_formants(self.h, C.byref(opts), n, _ptr(frames), float(sampling_rate_hz),
+                                                  int(spectrum_length), int(max_formants), _ptr(f), _ptr(bw),
+                                                  _ptr(num), _ptr(flags)), self.h)
+        return f, bw, num, flags
+
+    # ---- TDS ---------------------------------------------------------------
+    def tds_synthesize(self, frames, glottis, frame_len, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None,
+                       want_flow=False):
+        """frames [B, F] FRAME_DTYPE, glottis [B, F, 6], frame_len [F-1] output samples per interval.
+        Host buffers (H2D + kernel + D2H).  Returns (audio [B, n_out], flow or None, status [B])."""
+        opts = opts or tds_options_default()
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        B, F = frames.shape
+        glottis = np.ascontiguousarray(glottis, dtype=np.float64).reshape(B, F, NUM_GLOTTIS_CONTROL)
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.int32)
+        assert frame_len.shape == (F - 1,)
+        n_out = int(frame_len.sum())
+        audio = np.empty((B, n_out))
+        flow = np.empty((B, n_out * sr_factor)) if want_flow else None
+        status = np.zeros(B, dtype=np.uint32)
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
+        _check(self.lib, self.lib.afs_tds_synthesize(self.h, C.byref(opts), B, F, _ptr(frame_len), _ptr(frames),
+                                                     _ptr(glottis), float(fs_tds_hz), int(sr_factor), _ptr(s),
+                                                     _ptr(audio), _ptr(flow), _ptr(status)), self.h)
+        return audio, flow, status
+
+    def tds_synthesize_device(self, d_frames, d_glottis, n_tracts, n_frames, frame_len, d_audio, stream,
+                              fs_tds_hz=44100.0, sr_factor=2, opts=None, d_seeds=None, d_flow=None, d_status=None):
+        opts = opts or tds_options_default()
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.int32)
+        _check(self.lib, self.lib.afs_tds_synthesize_device(
+            self.h, C.byref(opts), int(n_tracts), int(n_frames), _ptr(frame_len), _ptr(d_frames), _ptr(d_glottis),
+            float(fs_tds_hz), int(sr_factor), _ptr(d_seeds), _ptr(d_audio), _ptr(d_flow), _ptr(d_status),
+            C.c_void_p(stream)), self.h)

@@ -1,0 +1,44 @@
+// afs_internal.h -- launch-parameter structs and launcher prototypes shared by
+// the C-ABI layer (afs_api.cu) and the kernel translation units.
+#pragma once
+#include <vector>
+
+#include "afs_common.cuh"
+
+namespace afs {
+
+// ---- TL -------------------------------------------------------------------
+struct TlParams {
+  afs_tl_options o;
+  int n_tubes, type, section, num_freq;
+  double f0;
+  double rs_factor, cp_factor, gp_factor;  // TlModel.cpp:14-19, evaluated on the host with libm
+  double sinus_gp[4];                      // 4 pi (3V/4pi)^(2/3) / 65000 per sinus (TlModel.cpp:858,863), host libm pow
+};
+struct FormantParams {
+  int n_tubes, num_freq, max_formants;
+  double f0;
+};
+cudaError_t launch_tl_sweep(const TlParams &p, const afs_tube_frame *d_tubes, double *d_re, double *d_im,
+                            cudaStream_t stream);
+cudaError_t launch_formant_pick(const FormantParams &p, const afs_tube_frame *d_tubes, const double *d_re,
+                                const double *d_im, double *d_freq, double *d_bw, int32_t *d_num, int32_t *d_flags,
+                                cudaStream_t stream);
+
+// ---- TDS ------------------------------------------------------------------
+struct TdsParams;  // tds_kernels.cu
+struct TdsLaunch {
+  std::vector<int32_t> step_bounds;  // [n_frames]: first simulation step of every frame interval, then the total
+  std::vector<unsigned char> params; // opaque TdsParams blob
+  int n_tracts = 0, n_frames = 0;
+};
+int tds_prepare_launch(const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
+                       double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L);
+cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
+                       const double *d_glottis, double *d_audio, double *d_flow, uint32_t *d_status,
+                       cudaStream_t stream);
+
+// ---- host helpers (afs_host.cpp) -------------------------------------------
+void chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double *b);
+
+}  // namespace afs

@@ -1,0 +1,78 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/afs_b200.h
+declares, refuses to compute without a device, and its host helpers match the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import areafunctionsynthesis_b200 as afs
+from conftest import ROOT, load_golden
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "afs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(afs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree_and_exports_the_header():
+    from areafunctionsynthesis_b200.build import build_library
+    build_library()
+    lib = afs.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/afs_b200.h but not exported"
+    assert lib.afs_version() == 100
+
+
+def test_struct_layouts_match_the_header():
+    assert afs.FRAME_DTYPE.itemsize == 1184
+    assert C.sizeof(afs.TlOptions) == 48
+    assert C.sizeof(afs.TdsOptions) == 8 * 4 + 8 + 16 * 8
+    o = afs.tl_options_default()
+    assert (o.radiation, o.boundary_layer, o.soft_walls, o.lumped_elements, o.paranasal_sinuses,
+            o.piriform_fossa, o.static_pressure_drops, o.lung_pressure_dPa) == (3, 1, 1, 1, 1, 0, 1, 0.0)
+    t = afs.tds_options_default()
+    assert (t.turbulence_losses, t.soft_walls, t.generate_noise_sources, t.radiation_from_skin, t.piriform_fossa,
+            t.inner_length_corrections) == (1, 1, 0, 1, 0, 1)
+    assert t.glottis_static[14] == 129.0 and t.glottis_static[15] == 125.51
+    f = afs.default_frames(2)
+    assert np.all(f["area_cm2"] == 4.0) and np.all(f["articulator"] == 4) and np.all(f["glottis_area_cm2"] == 0.1)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(afs.AfsError, match="no CUDA device"):
+        afs.Context(0)
+    lib = afs.load_library()
+    # compute entry points refuse a null context instead of computing on the host
+    rc = lib.afs_tl_sweep(None, None, 1, None, 2, 25, 10.0, 16, None, None)
+    assert rc == 2  # AFS_ERR_BAD_CONTEXT
+
+
+def test_chebyshev_designer_matches_reference():
+    g = load_golden("chebyshev.npz")
+    a, b = afs.chebyshev_lowpass(7000.0 / 44100.0, 8)
+    assert np.array_equal(a, g["a44"]) and np.array_equal(b, g["b44"])
+    a, b = afs.chebyshev_lowpass(7000.0 / 22050.0, 8)
+    assert np.array_equal(a, g["a22"]) and np.array_equal(b, g["b22"])
+
+
+def test_area_function_rasteriser_matches_reference(shapes):
+    n = len(shapes["names"])
+    mine = afs.area_function_to_frames(shapes["params"])
+    ref = shapes["frames"][:n]
+    for k in ("area_cm2", "length_cm", "articulator", "incisor_pos_cm", "laterality"):
+        assert np.array_equal(mine[k], ref[k]), k
+
+
+def test_bad_arguments_are_reported_not_printed():
+    lib = afs.load_library()
+    assert lib.afs_chebyshev_lowpass(0.2, 7, None, None) == 3
+    assert lib.afs_area_function_to_frame(None, None) == 3
+    assert b"bad argument" in lib.afs_status_string(3)

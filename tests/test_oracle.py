@@ -1,0 +1,77 @@
+"""CPU tests: the oracle restatement (oracle/afs_oracle.c) against the reference's outputs.
+
+The reference has no golden vectors of its own; the fixtures under tests/golden/ were produced by
+the unmodified reference compiled from /root/reference (tools/make_golden.py).  Where the compiled
+reference is available (build container, or oracle/_ref shipped to the GPU box) it is also run live.
+"""
+import numpy as np
+import pytest
+
+from conftest import have_ref, load_golden
+
+F0_938 = 22050.0 / 2048
+F0_2048 = 22050.0 / 8192
+
+
+def test_frame_expansion_matches_reference_tube(oracle, shapes):
+    if not have_ref():
+        pytest.skip("compiled reference not available")
+    from oracle.pyoracle import Ref
+    r = Ref(22)
+    for i in (0, 7, 60, 101):
+        sec = r.frame_sections(shapes["frames"][i:i + 1])
+        e = oracle.expand_frame(shapes["frames"][i:i + 1])["v"]
+        assert np.array_equal(sec[:, 0], e[:, 1]) and np.array_equal(sec[:, 1], e[:, 2])
+        assert np.array_equal(sec[:, 2], e[:, 3]) and np.array_equal(sec[:, 3], e[:, 0])
+        assert np.array_equal(sec[:, 4:7], e[:, 4:7])
+
+
+def test_tl_spectra_bit_identical_to_golden(oracle, shapes):
+    g = load_golden("tl_reference.npz")
+    fr = shapes["frames"]
+    re, im = oracle.tl_spectrum(fr[g["sel938"]], F0_938, 938)
+    assert np.array_equal(re, g["re938"]) and np.array_equal(im, g["im938"])
+    re, im = oracle.tl_spectrum(fr[g["sel2048"]], F0_2048, 2048)
+    assert np.array_equal(re, g["re2048"]) and np.array_equal(im, g["im2048"])
+
+
+def test_tl_bin0_aliases_bin1(oracle, shapes):
+    re, im = oracle.tl_spectrum(shapes["frames"][:1], F0_2048, 2048)
+    assert re[0, 0] == re[0, 1] and im[0, 0] == im[0, 1]
+    # SURVEY section 4 anchor for /a/
+    assert re[0, 0] == 1.0003095278623926 and abs(im[0, 0] - -0.0025227522178727) < 1e-15
+
+
+def test_tl_other_spectrum_types_and_options(oracle, shapes):
+    from oracle.pyoracle import tl_options_default
+    g = load_golden("tl_reference.npz")
+    n = len(shapes["names"])
+    fr = shapes["frames"][[0, n + 30]]
+    for t, sec in ((0, 30), (1, 30), (3, 30), (3, -1), (2, 50), (0, 70), (4, 0)):
+        re, im = oracle.tl_spectrum(fr, F0_938, 938, type_=t, section=sec)
+        assert np.array_equal(re, g[f"t{t}_s{sec}_re"]) and np.array_equal(im, g[f"t{t}_s{sec}_im"]), (t, sec)
+    o = tl_options_default()
+    o.piriform_fossa = 1; o.inner_length_corrections = 1; o.lung_pressure_dPa = 8000.0
+    o.hagen_resistance = 1; o.heat_conduction = 1
+    re, im = oracle.tl_spectrum(shapes["frames"][[0, 5, n + 30]], F0_938, 938, opts=o)
+    assert np.array_equal(re, g["re_opts"]) and np.array_equal(im, g["im_opts"])
+
+
+def test_formants_bit_identical_to_golden(oracle, shapes):
+    g = load_golden("tl_reference.npz")
+    f, bw, num, flags = oracle.tl_formants(shapes["frames"])
+    assert np.array_equal(num, g["num_formants"]) and np.array_equal(flags, g["flags"])
+    assert np.array_equal(f, g["formant_hz"]) and np.array_equal(bw, g["bandwidth_hz"])
+    # SURVEY section 4 anchors: /a/ oral
+    np.testing.assert_allclose(f[0, :3], [705.947857, 1246.117959, 2679.313681], atol=1e-6)
+
+
+def test_tl_live_reference_random_tubes(oracle):
+    if not have_ref():
+        pytest.skip("compiled reference not available")
+    from conftest import random_frames
+    from oracle.pyoracle import Ref
+    fr = random_frames(24, seed=11)
+    re, im = Ref(22).tl_spectrum(fr, 8192)
+    re2, im2 = oracle.tl_spectrum(fr, F0_2048, 2048)
+    assert np.array_equal(re, re2) and np.array_equal(im, im2)
