@@ -52,7 +52,7 @@ int scratch(afs_ctx *ctx, int slot, size_t bytes, void **out) {
 }
 
 int fill_tl_params(const afs_tl_options *o, int n_tubes, int type, int section, double f0, int num_freq, TlParams *p) {
-  if (!o || n_tubes < 0 || num_freq < 1 || !(f0 > 0.0)) return AFS_ERR_BAD_ARGUMENT;
+  if (!o || n_tubes < 0 || num_freq < 2 || !(f0 > 0.0)) return AFS_ERR_BAD_ARGUMENT;  // bin 0 aliases bin 1
   if (type < AFS_INPUT_IMPEDANCE || type > AFS_RADIATION) return AFS_ERR_BAD_ARGUMENT;
   if (section < -1 || section >= AFS_NUM_SECTIONS) return AFS_ERR_BAD_ARGUMENT;
   if (!o->lumped_elements) return AFS_ERR_UNSUPPORTED;

@@ -185,7 +185,8 @@ void afs_tube_frame_default(afs_tube_frame *frame);
  * getInputImpedance / getOutputImpedance (:987-1469) for a batch of tubes.
  * The reference derives the bin grid from its compile-time SAMPLING_RATE and
  * caps it at MAX_NUM_FREQ = 1024 (TlModel.h:89, TlModel.cpp:125-148); here
- * (f0_hz, num_freq) are arguments: bin i is at i*f0_hz, i = 0..num_freq-1.
+ * (f0_hz, num_freq) are arguments: bin i is at i*f0_hz, i = 0..num_freq-1,
+ * num_freq >= 2 (bin 0 reports the value of bin 1, TlModel.cpp:992,1293).
  * Output: re/im [n_tubes][num_freq] (the non-negative-frequency half of the
  * reference's ComplexSignal; Dsp.cpp:128-138 mirrors it).
  * Host buffers; H2D/D2H copies happen inside the call.

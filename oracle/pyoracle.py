@@ -207,3 +207,27 @@ class Oracle:
                                       spectrum_length, max_formants, _ptr(f), _ptr(bw), _ptr(num), _ptr(flags))
         assert rc == 0, rc
         return f, bw, num, flags
+
+    def tds_synthesize(self, frames, glottis, frame_len, fs_tds_hz=44100.0, sr_factor=2, opts=None, want_flow=True,
+                       dump_step=0):
+        opts = opts or tds_options_default()
+        frames = np.ascontiguousarray(frames)
+        B, F = frames.shape
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.int32)
+        n_out = int(frame_len.sum())
+        audio = np.zeros((B, n_out))
+        flow = np.zeros((B, n_out * sr_factor)) if want_flow else None
+        st = np.zeros(473) if dump_step else None
+        g = np.ascontiguousarray(glottis, dtype=np.float64)
+        rc = self.lib.orc_tds_synthesize(C.byref(opts), B, F, _ptr(frame_len), _ptr(frames), _ptr(g),
+                                         C.c_double(fs_tds_hz), sr_factor, None, _ptr(audio), _ptr(flow), _ptr(st),
+                                         dump_step)
+        assert rc == 0, rc
+        if dump_step:
+            return audio, flow, st
+        return audio, flow
+
+    def chebyshev_lowpass(self, cutoff_ratio, poles):
+        a = np.zeros(poles + 1); b = np.zeros(poles + 1)
+        self.lib.orc_chebyshev_lowpass(C.c_double(cutoff_ratio), poles, _ptr(a), _ptr(b))
+        return a, b

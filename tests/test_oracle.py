@@ -75,3 +75,54 @@ def test_tl_live_reference_random_tubes(oracle):
     re, im = Ref(22).tl_spectrum(fr, 8192)
     re2, im2 = oracle.tl_spectrum(fr, F0_2048, 2048)
     assert np.array_equal(re, re2) and np.array_equal(im, im2)
+
+
+# ---------------------------------------------------------------------------------------------
+# TDS restatement vs reference fixtures (bit-identical flow and audio, noise sources off)
+# ---------------------------------------------------------------------------------------------
+def test_tds_static_vowel_bit_identical(oracle):
+    g = load_golden("tds_reference.npz")
+    a, u = oracle.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 44100.0, 2)
+    assert np.array_equal(u, g["static_flow44"]) and np.array_equal(a, g["static_audio44"])
+    a, u = oracle.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 22050.0, 1)
+    assert np.array_equal(u, g["static_flow22"]) and np.array_equal(a, g["static_audio22"])
+
+
+def test_tds_transition_velum_and_options_bit_identical(oracle):
+    from oracle.pyoracle import tds_options_default
+    g = load_golden("tds_reference.npz")
+    a, u = oracle.tds_synthesize(g["trans_frames"], g["trans_glottis"], g["trans_len"], 44100.0, 2)
+    assert np.array_equal(u, g["trans_flow44"]) and np.array_equal(a, g["trans_audio44"])
+    o = tds_options_default()
+    o.piriform_fossa = 1; o.glottis_loss_option = 1
+    a, u = oracle.tds_synthesize(g["nasal_frames"], g["static_glottis"], [1102], 44100.0, 2, opts=o)
+    assert np.array_equal(u, g["nasal_flow44"]) and np.array_equal(a, g["nasal_audio44"])
+
+
+def test_tds_state_dump_matches_reference(oracle):
+    g = load_golden("tds_reference.npz")
+    for step in (1, 2, 500):
+        _, _, st = oracle.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 44100.0, 2, dump_step=step)
+        assert np.array_equal(st, g[f"static_state_{step}"]), step
+
+
+def test_tds_live_reference_random_transitions(oracle, shapes):
+    if not have_ref():
+        pytest.skip("compiled reference not available")
+    from oracle.pyoracle import Ref
+    rng = np.random.default_rng(3)
+    n = len(shapes["names"])
+    idx = rng.integers(0, n, size=(3, 2))
+    fr = shapes["frames"][idx]  # [3 tracts, 2 frames], incl. consonant closures
+    fr["velum_area_cm2"] = rng.random((3, 2)) * 0.6
+    gl = np.tile(np.array([120.0, 8000.0, 0.01, 0.01, 0.0, -40.0]), (3, 2, 1))
+    gl[:, :, 0] = rng.uniform(90, 220, size=(3, 2))
+    a, u = oracle.tds_synthesize(fr, gl, [1500], 44100.0, 2)
+    ar, ur = Ref(44).tds_synthesize(fr, gl, [1500])
+    assert np.array_equal(u, ur) and np.array_equal(a, ar)
+
+
+def test_chebyshev_restatement(oracle):
+    g = load_golden("chebyshev.npz")
+    a, b = oracle.chebyshev_lowpass(7000.0 / 44100.0, 8)
+    assert np.array_equal(a, g["a44"]) and np.array_equal(b, g["b44"])
