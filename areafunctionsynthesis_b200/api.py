@@ -78,6 +78,7 @@ def load_library():
     lib.afs_tl_formants.argtypes = [vp, vp, i32, vp, dbl, i32, i32, vp, vp, vp, vp]
     lib.afs_tds_synthesize.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp]
     lib.afs_tds_synthesize_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
+    lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
     lib.afs_chebyshev_lowpass.argtypes = [dbl, i32, vp, vp]
     lib.afs_area_function_to_frame.argtypes = [vp, vp]
     _lib = lib
@@ -202,6 +203,11 @@ class Context:
         return f, bw, num, flags
 
     # ---- TDS ---------------------------------------------------------------
+    def set_state_dump(self, step, out473=None):
+        """Diagnostics: dump tract 0's state after simulation step `step` (1-based) on the next calls."""
+        self._dump = out473 if step else None
+        _check(self.lib, self.lib.afs_tds_set_state_dump(self.h, int(step), _ptr(self._dump)), self.h)
+
     def tds_synthesize(self, frames, glottis, frame_len, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None,
                        want_flow=False):
         """frames [B, F] FRAME_DTYPE, glottis [B, F, 6], frame_len [F-1] output samples per interval.

@@ -21,7 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # per-file device flags
 UNITS = {
     "tl_kernels.cu": ["-fmad=false"],
-    "tds_kernels.cu": ["-fmad=false"],
+    "tds_kernels.cu": [],
     "afs_api.cu": [],
     "afs_host.cpp": [],
 }

@@ -21,6 +21,8 @@ struct afs_ctx {
   void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int sm_count = 0;
+  int dump_step = 0;          // diagnostics, see afs_tds_set_state_dump
+  double *dump_host = nullptr;
 };
 
 namespace {
@@ -253,7 +255,7 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   if (opts->glottis_loss_option != AFS_STANDARD_ENTRANCE_LOSS &&
       opts->glottis_loss_option != AFS_ENTRANCE_LOSS_VAN_DEN_BERG)
     return AFS_ERR_UNSUPPORTED;
-  if (opts->generate_noise_sources) return AFS_ERR_UNSUPPORTED;  // TODO(noise): glibc-compatible per-tract rand()
+  if (opts->generate_noise_sources) return AFS_ERR_UNSUPPORTED;  // noise sources: not on the device path yet
   for (int k = 0; k + 1 < n_frames; k++) if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT;
   if (n_tracts == 0) return AFS_OK;
   if (!d_tubes || !d_glottis || !d_audio) return AFS_ERR_BAD_ARGUMENT;
@@ -267,8 +269,25 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   if ((rc = scratch(ctx, 7, sizeof(int32_t) * (size_t)(n_frames + 1), &d_bounds))) return rc;
   CU(cudaMemcpyAsync(d_bounds, L.step_bounds.data(), sizeof(int32_t) * (size_t)n_frames, cudaMemcpyHostToDevice,
                      (cudaStream_t)stream));
-  CU(launch_tds(L, (const int32_t *)d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, (cudaStream_t)stream));
+  void *d_dump = nullptr;
+  if (ctx->dump_step > 0 && ctx->dump_host) {
+    if ((rc = scratch(ctx, 6, 473 * sizeof(double), &d_dump))) return rc;
+    CU(cudaMemsetAsync(d_dump, 0, 473 * sizeof(double), (cudaStream_t)stream));
+  }
+  CU(launch_tds(L, (const int32_t *)d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, (double *)d_dump,
+                ctx->dump_step, (cudaStream_t)stream));
   ctx->launches++;
+  if (d_dump) {
+    CU(cudaMemcpyAsync(ctx->dump_host, d_dump, 473 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  return AFS_OK;
+}
+
+int afs_tds_set_state_dump(afs_ctx *ctx, int step, double *host_out473) {
+  if (!ctx) return AFS_ERR_BAD_CONTEXT;
+  ctx->dump_step = step;
+  ctx->dump_host = host_out473;
   return AFS_OK;
 }
 

@@ -36,7 +36,8 @@ int tds_prepare_launch(const afs_tds_options *opts, int n_tracts, int n_frames, 
                        double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L);
 cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, double *d_audio, double *d_flow, uint32_t *d_status,
-                       cudaStream_t stream);
+                       double *d_dump, int dump_step, cudaStream_t stream);
+size_t tds_smem_bytes();
 
 // ---- host helpers (afs_host.cpp) -------------------------------------------
 void chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double *b);

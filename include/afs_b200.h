@@ -258,6 +258,13 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts,
                               double *d_audio, double *d_flow,
                               uint32_t *d_status, void *stream);
 
+/* Diagnostics: the next afs_tds_synthesize* calls copy the recurrent state of
+ * tract 0 right after simulation step `step` (1-based; 0 disables) into
+ * host_out473: [0..92] section pressure, [93..185] pressure rate, [186..278]
+ * wall current, [279..375] branch current, [376..472] branch-current rate
+ * (TdsModel.h:141-143,166-167,184). */
+int afs_tds_set_state_dump(afs_ctx *ctx, int step, double *host_out473);
+
 /* ---- host-side helpers of the boundary (no device work) -------------------- */
 /* IirFilter::createChebyshev low-pass (IirFilter.cpp:286-432): recursion
  * coefficients a[0..num_poles], b[0..num_poles] (b[0] = 0) for

@@ -1,0 +1,155 @@
+"""GPU parity tests of K1 tds_batch_kernel through the C ABI.
+
+Bar (BASELINE.json north_star): audio within 1e-6 relative max-abs of the reference in FP64, noise
+sources off.  The kernel reorders arithmetic (zero-fill elimination order, FMA, folded wall terms), so
+it is not bit-identical; the per-step state check below keeps that honest at the 1e-9 level before the
+self-oscillating glottis has had time to amplify rounding noise.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, random_frames
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6  # relative max-abs, as stated by the north star
+G0 = np.array([120.0, 8000.0, 0.01, 0.01, 0.0, -40.0])
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def test_state_after_single_steps_matches_reference(ctx):
+    g = load_golden("tds_reference.npz")
+    for step, tol in ((1, 1e-12), (2, 1e-12), (500, 1e-9)):
+        st = np.zeros(473)
+        ctx.set_state_dump(step, st)
+        ctx.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 44100.0, 2)
+        ctx.set_state_dump(0)
+        ref = g[f"static_state_{step}"]
+        for name, sl in (("pressure", slice(0, 93)), ("pressureRate", slice(93, 186)), ("wallCurrent", slice(186, 279)),
+                         ("current", slice(279, 376)), ("currentRate", slice(376, 473))):
+            scale = np.max(np.abs(ref[sl])) + 1e-300
+            err = np.max(np.abs(st[sl] - ref[sl])) / scale
+            assert err <= tol, (step, name, err)
+
+
+def test_golden_static_vowel(ctx):
+    g = load_golden("tds_reference.npz")
+    a, u, status = ctx.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 44100.0, 2, want_flow=True)
+    assert status[0] == 0
+    assert rel_err(u, g["static_flow44"]) <= TOL
+    assert rel_err(a, g["static_audio44"]) <= TOL
+    a, u, _ = ctx.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 22050.0, 1, want_flow=True)
+    assert rel_err(u, g["static_flow22"]) <= TOL and rel_err(a, g["static_audio22"]) <= TOL
+
+
+def test_golden_transition_and_options(ctx):
+    import areafunctionsynthesis_b200 as afs
+    g = load_golden("tds_reference.npz")
+    a, u, _ = ctx.tds_synthesize(g["trans_frames"], g["trans_glottis"], g["trans_len"], 44100.0, 2, want_flow=True)
+    assert rel_err(u, g["trans_flow44"]) <= TOL and rel_err(a, g["trans_audio44"]) <= TOL
+    o = afs.tds_options_default()
+    o.piriform_fossa = 1; o.glottis_loss_option = 1
+    a, u, _ = ctx.tds_synthesize(g["nasal_frames"], g["static_glottis"], [1102], 44100.0, 2, opts=o, want_flow=True)
+    assert rel_err(u, g["nasal_flow44"]) <= TOL and rel_err(a, g["nasal_audio44"]) <= TOL
+
+
+def _vowel_transitions(shapes, n, seed, nasal=False, dur=2205):
+    vowels = ["a:", "e:", "i:", "o:", "u:", "E:", "2:", "y:", "I", "E", "a", "O", "9", "Y", "U", "@"]
+    idx = [shapes["names"].index(v) for v in vowels]
+    rng = np.random.default_rng(seed)
+    pick = np.array([rng.choice(idx, size=2, replace=False) for _ in range(n)])
+    fr = shapes["frames"][pick].copy()
+    fr["velum_area_cm2"] = rng.random((n, 2)) if nasal else 0.0
+    gl = np.tile(G0, (n, 2, 1))
+    gl[:, :, 0] = rng.uniform(90, 220, size=(n, 2))
+    return fr, gl, [dur]
+
+
+def test_batch_of_vowel_transitions_against_oracle(ctx, oracle, shapes):
+    """SURVEY 8d config C3 at a size the oracle finishes in seconds: 40 oral vowel-to-vowel transitions
+    (more tracts than one CTA holds), 0.1 s each at 44.1 kHz."""
+    fr, gl, fl = _vowel_transitions(shapes, 40, 20260002)
+    a, u, status = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, want_flow=True)
+    ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2)
+    assert not status.any()
+    for b in range(len(fr)):
+        assert rel_err(u[b], uo[b]) <= TOL, b
+        assert rel_err(a[b], ao[b]) <= TOL, b
+
+
+def test_nasal_and_fossa_against_oracle(ctx, oracle, shapes):
+    """SURVEY 8d config C4 flavour: velum open U[0,1] cm^2 per endpoint, piriform fossa on."""
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    fr, gl, fl = _vowel_transitions(shapes, 12, 20260003, nasal=True)
+    o = afs.tds_options_default(); o.piriform_fossa = 1
+    oo = oracle_opts(); oo.piriform_fossa = 1
+    a, u, _ = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=o, want_flow=True)
+    ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=oo)
+    for b in range(len(fr)):
+        assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, b
+
+
+def test_consonant_closures_and_random_area_functions(ctx, oracle, shapes):
+    """Closures (areas clamped to 0.001 cm^2) and random parametric tubes."""
+    n = len(shapes["names"])
+    rng = np.random.default_rng(7)
+    pick = rng.integers(0, n, size=(8, 3))
+    fr = shapes["frames"][pick].copy()
+    gl = np.tile(G0, (8, 3, 1))
+    a, u, _ = ctx.tds_synthesize(fr, gl, [700, 401], 44100.0, 2, want_flow=True)
+    ao, uo = oracle.tds_synthesize(fr, gl, [700, 401], 44100.0, 2)
+    for b in range(8):
+        assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, b
+    rf = random_frames(16, seed=99).reshape(8, 2)
+    gl = np.tile(G0, (8, 2, 1))
+    a, u, _ = ctx.tds_synthesize(rf, gl, [1000], 44100.0, 2, want_flow=True)
+    ao, uo = oracle.tds_synthesize(rf, gl, [1000], 44100.0, 2)
+    for b in range(8):
+        assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, b
+
+
+def test_edge_cases(ctx, oracle, shapes):
+    import areafunctionsynthesis_b200 as afs
+    fr, gl, _ = _vowel_transitions(shapes, 3, 5)
+    # empty batch
+    a, u, st = ctx.tds_synthesize(fr[:0], gl[:0], [10], 44100.0, 2)
+    assert a.shape == (0, 10)
+    # one-sample frames, odd lengths, sr_factor 1 and 3
+    for srf, fl in ((1, [1]), (2, [1, 1]), (3, [7]), (2, [333])):
+        F = len(fl) + 1
+        frr = np.concatenate([fr, fr], axis=1)[:, :F]
+        gll = np.concatenate([gl, gl], axis=1)[:, :F]
+        a, u, _ = ctx.tds_synthesize(frr, gll, fl, 22050.0 * srf, srf, want_flow=True)
+        ao, uo = oracle.tds_synthesize(frr, gll, fl, 22050.0 * srf, srf)
+        assert rel_err(u, uo) <= TOL and np.allclose(a, ao, rtol=0, atol=TOL * np.max(np.abs(ao)) + 1e-30), (srf, fl)
+    # options the device path does not implement are errors, not silently different audio
+    o = afs.tds_options_default(); o.transvelar_coupling = 1
+    with pytest.raises(afs.AfsError, match="not supported"):
+        ctx.tds_synthesize(fr, gl, [10], 44100.0, 2, opts=o)
+    # other option switches
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    for name in ("turbulence_losses", "soft_walls", "radiation_from_skin", "inner_length_corrections"):
+        o = afs.tds_options_default(); setattr(o, name, 0)
+        oo = oracle_opts(); setattr(oo, name, 0)
+        a, u, _ = ctx.tds_synthesize(fr, gl, [600], 44100.0, 2, opts=o, want_flow=True)
+        ao, uo = oracle.tds_synthesize(fr, gl, [600], 44100.0, 2, opts=oo)
+        assert rel_err(u, uo) <= TOL and rel_err(a, ao) <= TOL, name
+
+
+def test_full_length_utterances_permutation_property(ctx, oracle, shapes):
+    """1 s utterances (44100 steps): a handful against the oracle, plus the size-independent property that a
+    tract's audio does not depend on which lane / CTA / batch it was computed in."""
+    fr, gl, _ = _vowel_transitions(shapes, 96, 20260002)
+    a, _, status = ctx.tds_synthesize(fr, gl, [22050], 44100.0, 2)
+    assert not status.any() and np.isfinite(a).all()
+    sel = [0, 37, 95]
+    ao, _ = oracle.tds_synthesize(fr[sel], gl[sel], [22050], 44100.0, 2, want_flow=False)
+    for k, b in enumerate(sel):
+        assert rel_err(a[b], ao[k]) <= TOL, b
+    perm = np.random.default_rng(0).permutation(96)[:40]
+    a2, _, _ = ctx.tds_synthesize(fr[perm], gl[perm], [22050], 44100.0, 2)
+    assert np.array_equal(a[perm], a2)
