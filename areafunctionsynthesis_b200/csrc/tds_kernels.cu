@@ -70,7 +70,7 @@ struct TdsParams {
 struct TdsSmem {
   // per-tract exchange, [item][lane]
   double D[NS][LANES];
-  double E[ND][LANES], L[ND][LANES], R[ND][LANES], invr[ND][LANES], area[ND][LANES], alpha[ND][LANES];
+  double E[ND][LANES], L[ND][LANES], R[ND][LANES], invr[ND][LANES], alpha[ND][LANES];  // invr = 1/sqrt(area/pi)
   double diag[NC][LANES];
   double sol[2][NC][LANES];
   double urb[16][LANES];          // current rates of the 16 sibling (branch / radiation) currents
@@ -84,7 +84,7 @@ struct TdsSmem {
   double chebX[8][LANES], chebY[8][LANES];   // output low-pass history
   double prevFlow[LANES];
   // static sections (same for all tracts)
-  double cE[NS], cL[NS], cR[NS], cAlpha[NS], cInvr[NS], cArea[NS];
+  double cE[NS], cL[NS], cR[NS], cAlpha[NS], cInvr[NS];
 };
 
 __device__ __forceinline__ int static_section_of(int t) {  // t = 0..46
@@ -133,7 +133,8 @@ struct SecAccess {
   __device__ __forceinline__ double R(int s) const { return is_dyn(s) ? S.R[s - DYN0][lane] : S.cR[s]; }
   __device__ __forceinline__ double alpha(int s) const { return is_dyn(s) ? S.alpha[s - DYN0][lane] : S.cAlpha[s]; }
   __device__ __forceinline__ double invr(int s) const { return is_dyn(s) ? S.invr[s - DYN0][lane] : S.cInvr[s]; }
-  __device__ __forceinline__ double area(int s) const { return is_dyn(s) ? S.area[s - DYN0][lane] : S.cArea[s]; }
+  // 1/area from the published 1/radius (areas are only ever needed as reciprocals or compared)
+  __device__ __forceinline__ double inva(int s) const { const double q = invr(s); return q * q * (1.0 / kPi); }
 };
 
 // Recurrent state of one owned section + its in-flowing current (registers).
@@ -198,7 +199,7 @@ __device__ __forceinline__ void phase1_dynamic(const TdsParams &P, TdsSmem &S, i
   }
   const double E = P.dtth / (C + alpha);
   const double D = st.p + P.dtth1 * st.pr - E * beta;  // no monopole / flow source (TdsModel.cpp:988-1008)
-  S.E[d][lane] = E; S.L[d][lane] = L; S.R[d][lane] = R; S.invr[d][lane] = invr; S.area[d][lane] = area;
+  S.E[d][lane] = E; S.L[d][lane] = L; S.R[d][lane] = R; S.invr[d][lane] = invr;
   S.alpha[d][lane] = alpha;
   S.D[s][lane] = D;
 }
@@ -241,9 +242,8 @@ __device__ __forceinline__ void phase2_row(const TdsParams &P, TdsSmem &S, const
       if (i > PHAR0 && i <= MOUTH_LAST) {  // junctions inside pharynx+mouth (A >= 25, B <= 64)
         const double ia = X.invr(A), ib = X.invr(B);
         if (P.ilc) L_AB += (8.0 * kRho / (3.0 * kPi * kPi)) * fabs(ia - ib);  // Sondhi (TdsModel.cpp:1745-1778)
-        if (P.turbulence) {  // Bernoulli loss wide -> narrow (TdsModel.cpp:850-877)
-          const double aA = X.area(A), aB = X.area(B);
-          if (((aB < aA) && (uB > 0)) || ((aB > aA) && (uB < 0))) {
+        if (P.turbulence) {  // Bernoulli loss wide -> narrow (TdsModel.cpp:850-877); area_B < area_A <=> ib > ia
+          if (((ib > ia) && (uB > 0)) || ((ib < ia) && (uB < 0))) {
             const double qa = ia * ia * (1.0 / kPi), qb = ib * ib * (1.0 / kPi);  // 1/area
             R_A -= uB * (0.5 * kRho) * (qa * qa);
             R_B += uB * (0.5 * kRho) * (qb * qb);
@@ -251,14 +251,14 @@ __device__ __forceinline__ void phase2_row(const TdsParams &P, TdsSmem &S, const
         }
       } else if (i == GLOT_LO) {  // glottal entrance loss (TdsModel.cpp:900-920)
         if (uB > 0) {
-          const double aT = X.area(B), aS = X.area(A);
-          R_B += P.k_ent * 0.5 * kRho * fabs(uB) * (1.0 / (aT * aT) - 1.0 / (aS * aS));
+          const double qT = X.inva(B), qS = X.inva(A);
+          R_B += P.k_ent * 0.5 * kRho * fabs(uB) * (qT * qT - qS * qS);
         }
       } else if (i == GLOT_UP) {  // lower -> upper glottis section (TdsModel.cpp:930-950)
-        const double aS = X.area(A), aT = X.area(B);
-        const double target = (aT < P.fsar * aS) ? 1.0 : 0.0;
+        const double qS = X.inva(A), qT = X.inva(B);
+        const double target = (qT * P.fsar > qS) ? 1.0 : 0.0;  // area_T < fsar * area_S
         gbf = 0.8 * gbf + (1.0 - 0.8) * target;
-        if (uB > 0) R_A += gbf * fabs(uB) * 0.5 * kRho * (1.0 / (aT * aT) - 1.0 / (aS * aS));
+        if (uB > 0) R_A += gbf * fabs(uB) * 0.5 * kRho * (qT * qT - qS * qS);
       }
       const double R_AB = R_A + R_B;
       const double G = L_AB * P.idt + R_AB;
@@ -677,10 +677,10 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       if (surface < kMinArea) surface = kMinArea;
       const double C = q.volume / (kRho * kC * kC);
       const double alpha = P.soft_walls ? surface * P.kalpha[wall_type(s)] : 0.0;
-      S.cL[s] = L; S.cR[s] = R; S.cInvr[s] = invr; S.cArea[s] = q.area; S.cAlpha[s] = alpha;
+      S.cL[s] = L; S.cR[s] = R; S.cInvr[s] = invr; S.cAlpha[s] = alpha;
       S.cE[s] = P.dtth / (C + alpha);
     } else {
-      S.cL[s] = S.cR[s] = S.cInvr[s] = S.cArea[s] = S.cAlpha[s] = S.cE[s] = 0.0;
+      S.cL[s] = S.cR[s] = S.cInvr[s] = S.cAlpha[s] = S.cE[s] = 0.0;
     }
   }
   for (int i = warp; i < NC; i += NWS) { S.sol[0][i][lane] = 0.0; S.sol[1][i][lane] = 0.0; S.diag[i][lane] = 1.0; }
@@ -906,6 +906,7 @@ cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tu
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
+  static_assert(sizeof(TdsSmem) <= 227 * 1024, "TdsSmem exceeds the 227 KB a CTA can have on sm_100a");
   cudaError_t e = cudaFuncSetAttribute(tds_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(TdsSmem));  // per device; cheap
   if (e != cudaSuccess) return e;
