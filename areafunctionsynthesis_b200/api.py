@@ -79,6 +79,7 @@ def load_library():
     lib.afs_tds_synthesize.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp]
     lib.afs_tds_synthesize_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
     lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
+    lib.afs_probe_fp64_tflops.argtypes = [vp, vp]
     lib.afs_chebyshev_lowpass.argtypes = [dbl, i32, vp, vp]
     lib.afs_area_function_to_frame.argtypes = [vp, vp]
     _lib = lib
@@ -164,6 +165,11 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def probe_fp64_tflops(self):
+        out = C.c_double()
+        _check(self.lib, self.lib.afs_probe_fp64_tflops(self.h, C.byref(out)), self.h)
+        return out.value
 
     @property
     def launch_count(self):

@@ -22,6 +22,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = {
     "tl_kernels.cu": ["-fmad=false"],
     "tds_kernels.cu": [],
+    "probe_kernels.cu": [],
     "afs_api.cu": [],
     "afs_host.cpp": [],
 }

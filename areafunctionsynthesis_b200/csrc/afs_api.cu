@@ -152,6 +152,34 @@ void afs_tube_frame_default(afs_tube_frame *f) {
   f->glottis_length_cm[0] = f->glottis_length_cm[1] = 0.3;
 }
 
+int afs_probe_fp64_tflops(afs_ctx *ctx, double *tflops) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!tflops) return AFS_ERR_BAD_ARGUMENT;
+  void *d_out;
+  if ((rc = scratch(ctx, 6, 473 * sizeof(double), &d_out))) return rc;
+  const int ctas = ctx->sm_count * 8, iters = 1 << 15;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {  // first rep is the warm-up
+    CU(cudaEventRecord(e0, ctx->stream));
+    CU(launch_fp64_probe((double *)d_out, ctas, iters, ctx->stream));
+    ctx->launches++;
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)ctas;
+  *tflops = flops / ((double)best * 1e-3) / 1e12;
+  return AFS_OK;
+}
+
 // ---------------------------------------------------------------------------
 // TL
 // ---------------------------------------------------------------------------

@@ -39,6 +39,9 @@ cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tu
                        double *d_dump, int dump_step, cudaStream_t stream);
 size_t tds_smem_bytes();
 
+// ---- probes ------------------------------------------------------------------
+cudaError_t launch_fp64_probe(double *d_out, int ctas, int iters, cudaStream_t stream);
+
 // ---- host helpers (afs_host.cpp) -------------------------------------------
 void chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double *b);
 

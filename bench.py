@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the area-function-to-speech hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): TDS simulated audio-seconds per wall-second at batch 4096 (headline) and TL
+transfer functions per second at 2048 bins (reported in the same JSON line under "tl").
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  TDS  4096 independent utterances per GPU, each a 1 s vowel-to-vowel transition simulated at 44.1 kHz
+       with the nasal branch open (velum U[0,1] cm^2 per endpoint) and the subglottal tract (always
+       part of the 93-section network) -- BASELINE config 4 ("workload": "tds_nasal_subglottal_b4096").
+       N > 1: every rank gets its own 4096 utterances (weak scaling, no data-path collective; a small
+       NCCL all_gather of per-utterance checksums after the timed region collects the outputs' digest).
+  TL   4096 random parametric area functions x 2048 bins -- BASELINE config 2.
+
+`value` is device-resident throughput (inputs already in HBM), timed with CUDA events on the launching
+stream; `e2e` is the same metric through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed
+region).  `roofline` is against the FP64 FMA peak measured live by afs_probe_fp64_tflops (both kernels are
+FP64-pipe bound scalar recurrences) with W_tds = 1.0e4 flop per tract-step and W_tl = 8.0e3
+flop per (area function, bin).  `cpu_baseline` times the compiled reference (oracle/_ref) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_TDS = 1.0e4  # algorithmic FP64 flop per tract-step
+W_TL = 8.0e3   # algorithmic FP64 flop per (area function, bin)
+B_TDS = 4096
+T_SEC = 1.0  # overridden by --utt-seconds (profiling only)
+FS = 44100.0
+SR_FACTOR = 2
+B_TL, K_TL = 4096, 2048
+F0_TL = 22050.0 / 8192
+VOWELS = ["a:", "e:", "i:", "o:", "u:", "E:", "2:", "y:", "I", "E", "a", "O", "9", "Y", "U", "@"]
+
+
+def make_tds_batch(n, seed):
+    """Vowel-to-vowel transitions between the 16 vowel shapes of Default.params (frames stored as a
+    fixture under tests/golden/), velum U[0,1] cm^2 per endpoint, F0 U[90,220] Hz gliding, P = 8000 dPa."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "default_shapes.npz"))
+    names = [str(x) for x in g["names"]]
+    idx = np.array([names.index(v) for v in VOWELS])
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, len(idx), size=n)
+    b = (a + 1 + rng.integers(0, len(idx) - 1, size=n)) % len(idx)
+    fr = g["frames"][np.stack([idx[a], idx[b]], axis=1)].copy()
+    fr["velum_area_cm2"] = rng.random((n, 2))
+    gl = np.tile(np.array([120.0, 8000.0, 0.01, 0.01, 0.0, -40.0]), (n, 2, 1))
+    gl[:, :, 0] = rng.uniform(90.0, 220.0, size=(n, 2))
+    return fr, gl
+
+
+def make_tl_batch(n, seed):
+    import areafunctionsynthesis_b200 as afs
+    rng = np.random.default_rng(seed)
+    lo = np.array([-0.2, 0.67, 0.015, 1.92, 1.82, 0.37, 6.36, 0.087, 0.31, 10.97, 0.092, 0.0, 16.33, 1.05, 16.53, 0.107])
+    hi = np.array([2.63, 2.05, 5.22, 6.43, 11.55, 6.96, 16.44, 2.50, 5.21, 18.82, 14.33, 9.33, 20.45, 6.12, 21.52, 4.40])
+    p = lo + (hi - lo) * rng.random((n, 16))
+    p[:, [0, 3, 6, 9, 12, 14]] = np.sort(p[:, [0, 3, 6, 9, 12, 14]], axis=1)
+    p[:, 0] = np.maximum(p[:, 0], 0.0)
+    f = afs.area_function_to_frames(p)
+    f["glottis_area_cm2"] = 0.0
+    f["velum_area_cm2"] = np.where(rng.random(n) < 0.5, rng.random(n), 0.0)
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref), all host threads
+# ---------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(n_threads, utt_seconds, n_utts=None, seed=20260003):
+    """Times the compiled reference on `n_utts` utterances of `utt_seconds` each over `n_threads` threads."""
+    from oracle.pyoracle import Oracle, Ref
+    fr, gl = make_tds_batch(n_utts or n_threads, seed)
+    n_out = int(round(utt_seconds * FS / SR_FACTOR))
+    try:
+        ref = Ref(44)
+        kind = "reference"
+        t0 = time.perf_counter()
+        ref.tds_synthesize(fr, gl, [n_out], want_flow=False, threads=n_threads)
+        dt = time.perf_counter() - t0
+        cores = n_threads
+    except (FileNotFoundError, OSError):
+        orc = Oracle()  # scalar restatement, one thread
+        kind, cores = "port", 1
+        fr, gl = fr[:1], gl[:1]
+        t0 = time.perf_counter()
+        orc.tds_synthesize(fr, gl, [n_out], FS, SR_FACTOR, want_flow=False)
+        dt = time.perf_counter() - t0
+    audio_s = len(fr) * n_out * SR_FACTOR / FS
+    return audio_s / dt, kind, cores, dt, len(fr)
+
+
+def cpu_reference_tl(n_threads, n_tubes):
+    from oracle.pyoracle import Oracle, Ref
+    f = make_tl_batch(n_tubes, 20260001)
+    try:
+        ref = Ref(22)
+        t0 = time.perf_counter()
+        ref.tl_spectrum(f, 8192, threads=n_threads)
+        return n_tubes / (time.perf_counter() - t0), "reference", n_threads
+    except (FileNotFoundError, OSError):
+        orc = Oracle()
+        t0 = time.perf_counter()
+        orc.tl_spectrum(f[:8], F0_TL, K_TL)
+        return 8 / (time.perf_counter() - t0), "port", 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    utt = 0.25  # seconds of audio per utterance per step: bounded sample of the 1 s workload
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, kind, cores, dt, n = cpu_reference(threads, utt)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([d for _, d in vals]) * 1e3)
+    sample = f"{n} utterances x {utt} s @44.1 kHz per step, one per thread ({kind})"
+    line = {"impl": "reference", "metric": "tds_audio_seconds_per_second", "value": value,
+            "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "tds_nasal_subglottal_b4096", "batch_per_gpu": B_TDS, "utterance_s": T_SEC,
+                       "fs_tds_hz": FS, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import areafunctionsynthesis_b200 as afs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = afs.Context(local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps, warmup):
+        """W untimed warm-up steps, then K steps, each bracketed by CUDA events on the launching stream; L2 is
+        flushed (256 MiB write, untimed) between steps.  Returns total ms (max over ranks)."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        tot = 0.0
+        for _ in range(steps):
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(tot)
+
+    # ---------------- TDS: headline --------------------------------------------------------------
+    n_out = int(round(T_SEC * FS / SR_FACTOR))
+    total_steps = n_out * SR_FACTOR
+    fr, gl = make_tds_batch(B_TDS, 20260003 + rank)
+    frame_len = np.array([n_out], dtype=np.int32)
+    d_fr = torch.from_numpy(fr.view(np.uint8).reshape(B_TDS, -1)).to(dev)
+    d_gl = torch.from_numpy(gl).to(dev)
+    d_audio = torch.empty(B_TDS, n_out, dtype=torch.float64, device=dev)
+    d_status = torch.zeros(B_TDS, dtype=torch.int32, device=dev)
+
+    def tds_dev():
+        ctx.tds_synthesize_device(d_fr, d_gl, B_TDS, 2, frame_len, d_audio, stream, FS, SR_FACTOR, d_status=d_status)
+
+    fp64_peak = ctx.probe_fp64_tflops()
+    sampler = ClockSampler(local)
+    l0 = ctx.launch_count
+    for _ in range(args.warmup):
+        tds_dev()
+    barrier()
+    l0 = ctx.launch_count
+    sampler.start()
+    ms_total = timed(tds_dev, args.steps, 0)
+    clocks = sampler.stop()
+    launches = ctx.launch_count - l0
+    ms_step = ms_total / args.steps
+    audio_s_per_step = world * B_TDS * T_SEC
+    value = audio_s_per_step / (ms_step * 1e-3)
+    assert int(d_status.sum().item()) == 0, "non-finite values in the TDS batch"
+    tds_tflops = W_TDS * B_TDS * total_steps / (ms_step * 1e-3) / 1e12  # this rank's kernel
+
+    # e2e: pinned host buffers -> C-ABI host call (H2D + kernel + D2H)
+    h_fr = torch.from_numpy(fr.view(np.uint8).reshape(B_TDS, -1).copy()).pin_memory()
+    h_gl = torch.from_numpy(gl.copy()).pin_memory()
+    h_audio = torch.empty(B_TDS, n_out, dtype=torch.float64).pin_memory()
+    h_status = torch.zeros(B_TDS, dtype=torch.int32).pin_memory()
+    opts = afs.tds_options_default()
+
+    def tds_host():
+        rc = ctx.lib.afs_tds_synthesize(ctx.h, afs.api.C.byref(opts), B_TDS, 2, frame_len.ctypes.data,
+                                        h_fr.data_ptr(), h_gl.data_ptr(), FS, SR_FACTOR, None, h_audio.data_ptr(), None,
+                                        h_status.data_ptr())
+        assert rc == 0, rc
+
+    tds_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tds_host()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    e2e_value = audio_s_per_step / e2e_s
+    assert torch.equal(h_audio, d_audio.cpu()), "host-path audio differs from the device-resident path"
+
+    # digest of every rank's output, gathered over NCCL after the timed region
+    digest = d_audio.abs().mean(dim=1)
+    if world > 1:
+        gathered = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        digest = torch.cat(gathered)
+    digest_mean = float(digest.mean().item())
+
+    # ---------------- TL: second metric -----------------------------------------------------------
+    f_tl = make_tl_batch(B_TL, 20260001 + rank)
+    d_ftl = torch.from_numpy(f_tl.view(np.uint8).reshape(B_TL, -1)).to(dev)
+    d_re = torch.empty(B_TL, K_TL, dtype=torch.float64, device=dev)
+    d_im = torch.empty_like(d_re)
+
+    def tl_dev():
+        ctx.tl_sweep_device(d_ftl, B_TL, F0_TL, K_TL, d_re, d_im, stream)
+
+    tl_steps = max(args.steps, 5)
+    tl_ms = timed(tl_dev, tl_steps, 3) / tl_steps
+    tl_value = world * B_TL / (tl_ms * 1e-3)
+    tl_tflops = W_TL * B_TL * K_TL / (tl_ms * 1e-3) / 1e12
+    h_re = np.empty((B_TL, K_TL)); h_im = np.empty((B_TL, K_TL))
+    ctx.tl_sweep(f_tl, F0_TL, K_TL)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        h_re, h_im = ctx.tl_sweep(f_tl, F0_TL, K_TL)
+    barrier()
+    tl_e2e = world * B_TL / max_over_ranks((time.perf_counter() - t0) / 3)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------------------------------------
+    cpu = None
+    tl_cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        v, kind, cores, dt, n = cpu_reference(threads, 1.0, n_utts=min(4 * threads, 512))
+        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind,
+               "sample": f"{n} utterances x 1.0 s @44.1 kHz of the same workload over {cores} threads, {dt:.1f} s wall"}
+        tv, tkind, tcores = cpu_reference_tl(threads, 4 * threads)
+        tl_cpu = {"value": tv, "unit": "spectra/s", "cores": tcores, "kind": tkind,
+                  "sample": f"{4 * threads} area functions x 2048 bins"}
+
+    peaks = load_peaks()
+    line = {
+        "metric": "tds_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "tds_nasal_subglottal_b4096", "batch_per_gpu": B_TDS, "utterance_s": T_SEC,
+                   "fs_tds_hz": FS, "sr_factor": SR_FACTOR, "control_frames": 2, "noise_sources": False,
+                   "parallelism": f"independent utterances sharded over {world} GPU(s), no data-path collective",
+                   "l2": "flushed between timed steps (256 MiB write, untimed)"},
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h_fr.numel() + h_gl.numel() * 8),
+                "d2h_bytes_per_step": int(h_audio.numel() * 8 + h_status.numel() * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": tds_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": tds_tflops / fp64_peak, "traffic": None,
+                     "kernel": "tds_batch_kernel", "flop_per_tract_step": W_TDS,
+                     "peak_source": "afs_probe_fp64_tflops, measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                     "hbm_gbs_algorithmic": B_TDS * n_out * 8 / (ms_step * 1e-3) / 1e9,
+                     "hbm_gbs_peak_measured": peaks.get("hbm_gbs")},
+        "cpu_baseline": cpu,
+        "output_digest": digest_mean,
+        "tl": {"metric": "tl_spectra_per_second_2048_bins", "value": tl_value, "unit": "spectra/s", "ms_per_step": tl_ms,
+               "config": {"workload": "tl_sweep_4096x2048", "area_functions_per_gpu": B_TL, "bins": K_TL},
+               "e2e": {"value": tl_e2e, "unit": "spectra/s", "h2d_bytes_per_step": int(f_tl.nbytes),
+                       "d2h_bytes_per_step": int(2 * B_TL * K_TL * 8)},
+               "roofline": {"bound": "fp64", "achieved": tl_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": tl_tflops / fp64_peak, "kernel": "tl_sweep_kernel", "flop_per_bin": W_TL,
+                            "hbm_gbs_algorithmic": B_TL * K_TL * 16 / (tl_ms * 1e-3) / 1e9},
+               "cpu_baseline": tl_cpu},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--utt-seconds", type=float, default=1.0, help="utterance length; != 1.0 is for profiling only")
+    args = ap.parse_args()
+    global T_SEC
+    T_SEC = args.utt_seconds
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -265,6 +265,11 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts,
  * (TdsModel.h:141-143,166-167,184). */
 int afs_tds_set_state_dump(afs_ctx *ctx, int step, double *host_out473);
 
+/* Measures the FP64 FMA peak of the bound device (independent DFMA chains,
+ * best of 4), in TFLOP/s: the roofline denominator of both kernels
+ * (MEASURED_PEAKS.json has no FP64 figure). */
+int afs_probe_fp64_tflops(afs_ctx *ctx, double *tflops);
+
 /* ---- host-side helpers of the boundary (no device work) -------------------- */
 /* IirFilter::createChebyshev low-pass (IirFilter.cpp:286-432): recursion
  * coefficients a[0..num_poles], b[0..num_poles] (b[0] = 0) for
