@@ -1,0 +1,206 @@
+// afs_b200.hpp -- header-only C++17 facade over the C ABI (afs_b200.h) that keeps
+// the reference's class vocabulary for the hot path, so that callers written
+// against the VocalTractLab backend classes of Simon-Stone/AreaFunctionSynthesis
+// (`Tube`, `TlModel`, `Synthesizer::synthesizeSignalTds`) can switch with
+// mechanical edits.  Batched: every object drives a whole batch of tubes /
+// utterances on one B200.  Errors surface as afs::Error (the reference prints
+// and carries on, TdsModel.cpp:259,1832,2267).
+//
+// Reference interfaces mirrored (paths under src/Backend/):
+//   afs::Tube            Tube.h:14-170        setPharynxMouthGeometry, setGlottisGeometry, setGlottisArea,
+//                                             setVelumOpening, setAspirationStrength, interpolate
+//   afs::TlModel         TlModel.h:24-131     public `options`, `tube`; getSpectrum, getFormants
+//   afs::TdsSynthesizer  Synthesizer.h:161    synthesizeSignalTds(newTube, newGlottisParams, numNewSamples, out)
+//                        + TdsModel.h:257-280 options, resetMotion
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "afs_b200.h"
+
+namespace afs {
+
+struct Error : std::runtime_error {
+  int status;
+  Error(int s, const std::string &what) : std::runtime_error(what), status(s) {}
+};
+inline void check(int status, const afs_ctx *ctx = nullptr) {
+  if (status == AFS_OK) return;
+  std::string msg = afs_status_string(status);
+  if (ctx && afs_last_cuda_error(ctx)[0]) msg += std::string(" [") + afs_last_cuda_error(ctx) + "]";
+  throw Error(status, msg);
+}
+
+// One CUDA device.  Replaces `new TdsModel()` / `new TlModel()` (Data.cpp:78-88, Synthesizer.cpp:48).
+class Device {
+ public:
+  explicit Device(int ordinal = 0) { check(afs_create(&ctx_, ordinal)); }
+  ~Device() { afs_destroy(ctx_); }
+  Device(const Device &) = delete;
+  Device &operator=(const Device &) = delete;
+  afs_ctx *ctx() const { return ctx_; }
+
+ private:
+  afs_ctx *ctx_ = nullptr;
+};
+
+// The dynamic part of the reference Tube as a value type (a reference Tube holds pointers into itself and cannot
+// be copied).  Same setter names and argument meaning as Tube.h.
+class Tube {
+ public:
+  enum Articulator { VOCAL_FOLDS, TONGUE, LOWER_INCISORS, LOWER_LIP, OTHER_ARTICULATOR, NUM_ARTICULATORS };
+  static constexpr int NUM_PHARYNX_MOUTH_SECTIONS = AFS_NUM_PM_SECTIONS;
+  static constexpr int NUM_GLOTTIS_SECTIONS = AFS_NUM_GLOTTIS_SECTIONS;
+  static constexpr int FIRST_PHARYNX_SECTION = AFS_FIRST_PHARYNX_SECTION;
+  static constexpr double MIN_AREA_CM2 = 0.1e-2;
+
+  afs_tube_frame frame;
+
+  Tube() { afs_tube_frame_default(&frame); }
+  void setPharynxMouthGeometry(const double *length_cm, const double *area_cm2, const Articulator *articulator,
+                               const double *laterality, double incisorPos_cm) {
+    for (int i = 0; i < NUM_PHARYNX_MOUTH_SECTIONS; i++) {
+      frame.length_cm[i] = length_cm[i];
+      frame.area_cm2[i] = area_cm2[i] < MIN_AREA_CM2 ? MIN_AREA_CM2 : area_cm2[i];  // Tube.cpp:337
+      frame.articulator[i] = (int32_t)articulator[i];
+      frame.laterality[i] = laterality[i];
+    }
+    frame.incisor_pos_cm = incisorPos_cm;
+  }
+  void setGlottisGeometry(const double *length_cm, const double *area_cm2) {
+    for (int i = 0; i < 2; i++) { frame.glottis_length_cm[i] = length_cm[i]; frame.glottis_area_cm2[i] = area_cm2[i]; }
+  }
+  void setGlottisArea(double area_cm2) {  // Tube.cpp:388-394
+    const double l[2] = {0.3, 0.3}, a[2] = {area_cm2, area_cm2};
+    setGlottisGeometry(l, a);
+  }
+  void setVelumOpening(double area_cm2) { frame.velum_area_cm2 = area_cm2; }
+  void setAspirationStrength(double dB) { frame.aspiration_dB = dB; }
+  double getVelumOpening_cm2() const { return frame.velum_area_cm2 < MIN_AREA_CM2 ? MIN_AREA_CM2 : frame.velum_area_cm2; }
+  // Tube::interpolate (Tube.cpp:438-505) for the fields a frame carries.
+  void interpolate(const Tube *left, const Tube *right, double ratio) {
+    const double r1 = 1.0 - ratio;
+    for (int i = 0; i < NUM_PHARYNX_MOUTH_SECTIONS; i++) {
+      const double a = r1 * left->frame.area_cm2[i] + ratio * right->frame.area_cm2[i];
+      frame.area_cm2[i] = a < MIN_AREA_CM2 ? MIN_AREA_CM2 : a;
+      frame.length_cm[i] = r1 * left->frame.length_cm[i] + ratio * right->frame.length_cm[i];
+      frame.articulator[i] = left->frame.articulator[i];
+      frame.laterality[i] = r1 * left->frame.laterality[i] + ratio * right->frame.laterality[i];
+    }
+    frame.incisor_pos_cm = r1 * left->frame.incisor_pos_cm + ratio * right->frame.incisor_pos_cm;
+    frame.velum_area_cm2 = r1 * left->getVelumOpening_cm2() + ratio * right->getVelumOpening_cm2();
+    frame.aspiration_dB = r1 * left->frame.aspiration_dB + ratio * right->frame.aspiration_dB;
+  }
+};
+
+// OneDimAreaFunction::setParameters + calculateOneDimTubeFunction (OneDimAreaFunction.cpp:75-138, 356-368).
+inline void calculateOneDimTubeFunction(const double params[16], Tube *tube) {
+  check(afs_area_function_to_frame(params, &tube->frame));
+}
+
+struct ComplexSpectrum {  // the non-negative-frequency half of the reference's ComplexSignal (Signal.h:61-92)
+  int numFreq = 0;
+  std::vector<double> re, im;  // [n_tubes][numFreq]
+};
+
+// Batched TlModel.  `options` and `tubes` are public like TlModel::options / TlModel::tube.
+class TlModel {
+ public:
+  enum SpectrumType { INPUT_IMPEDANCE, OUTPUT_IMPEDANCE, FLOW_SOURCE_TF, PRESSURE_SOURCE_TF, RADIATION };
+  afs_tl_options options;
+  std::vector<Tube> tubes;
+
+  explicit TlModel(Device &dev) : dev_(dev) { afs_tl_options_default(&options); }
+  void setLungPressure(double lungPressure_dPa) { options.lung_pressure_dPa = lungPressure_dPa; }
+
+  // TlModel::getSpectrum (TlModel.cpp:123-197) for every tube; the bin grid is explicit: bin i at i*f0_hz.
+  void getSpectrum(SpectrumType type, ComplexSpectrum *spectrum, double f0_hz, int numFreq, int section) {
+    std::vector<afs_tube_frame> f(tubes.size());
+    for (size_t i = 0; i < tubes.size(); i++) f[i] = tubes[i].frame;
+    spectrum->numFreq = numFreq;
+    spectrum->re.assign(tubes.size() * (size_t)numFreq, 0.0);
+    spectrum->im.assign(tubes.size() * (size_t)numFreq, 0.0);
+    check(afs_tl_sweep(dev_.ctx(), &options, (int)f.size(), f.data(), (int)type, section, f0_hz, numFreq,
+                       spectrum->re.data(), spectrum->im.data()), dev_.ctx());
+  }
+  // Reference grid: spectrumLength points at `samplingRate` (reference: 22050), numFreq as in TlModel.cpp:125-148
+  // without the MAX_NUM_FREQ cap.
+  void getSpectrum(SpectrumType type, ComplexSpectrum *spectrum, int spectrumLength, int section,
+                   double samplingRate = 22050.0) {
+    const double f0 = samplingRate / (double)spectrumLength;
+    int n = (int)(10100.0 / f0);
+    if (n >= spectrumLength / 2) n = spectrumLength / 2 - 1;
+    getSpectrum(type, spectrum, f0, n, section);
+  }
+  // TlModel::getFormants (TlModel.cpp:280-461) for every tube.
+  void getFormants(std::vector<double> *formantFreq, std::vector<double> *formantBW, std::vector<int32_t> *numFormants,
+                   int MAX_FORMANTS, std::vector<int32_t> *flags /* bit0 friction, bit1 closure, bit2 nasal */) {
+    std::vector<afs_tube_frame> f(tubes.size());
+    for (size_t i = 0; i < tubes.size(); i++) f[i] = tubes[i].frame;
+    formantFreq->assign(f.size() * (size_t)MAX_FORMANTS, 0.0);
+    formantBW->assign(f.size() * (size_t)MAX_FORMANTS, 0.0);
+    numFormants->assign(f.size(), 0);
+    flags->assign(f.size(), 0);
+    check(afs_tl_formants(dev_.ctx(), &options, (int)f.size(), f.data(), 22050.0, 2048, MAX_FORMANTS,
+                          formantFreq->data(), formantBW->data(), numFormants->data(), flags->data()), dev_.ctx());
+  }
+
+ private:
+  Device &dev_;
+};
+
+// Batched replacement of the Synthesizer's TDS driver: the caller queues control frames exactly like successive
+// calls of Synthesizer::synthesizeSignalTds(newTube, newGlottisParams, numNewSamples, out) (Synthesizer.cpp:515-639)
+// -- the first call primes -- and flush() runs the whole batch of utterances in one kernel launch.
+class TdsSynthesizer {
+ public:
+  afs_tds_options options;  // TdsModel::options + TriangularGlottis static parameters
+  double samplingRate = 22050.0;
+  int tdsSrFactor = 2;  // TDS_SR_FACTOR (Constants.h:25): simulation at 44.1 kHz
+
+  TdsSynthesizer(Device &dev, int numUtterances) : dev_(dev), n_(numUtterances) { afs_tds_options_default(&options); }
+  void resetMotion() { tubes_.clear(); glottis_.clear(); frameLen_.clear(); frames_ = 0; }
+
+  // One control frame for ALL utterances: newTubes[n], newGlottisParams[n][6].  The first call primes (returns
+  // without producing samples, Synthesizer.cpp:522-532); later calls append numNewSamples output samples.
+  void synthesizeSignalTds(const Tube *newTubes, const double *newGlottisParams, int numNewSamples) {
+    for (int b = 0; b < n_; b++) tubes_.push_back(newTubes[b].frame);
+    glottis_.insert(glottis_.end(), newGlottisParams, newGlottisParams + (size_t)n_ * AFS_NUM_GLOTTIS_CONTROL);
+    if (frames_ > 0) frameLen_.push_back(numNewSamples < 1 ? 1 : numNewSamples);
+    frames_++;
+  }
+  // Runs the queued frames; audio[n][sum(numNewSamples)] in [-1, 1]; flow (optional) per simulation step.
+  void flush(std::vector<double> *audio, std::vector<double> *flow = nullptr, std::vector<uint32_t> *status = nullptr) {
+    if (frames_ < 2) throw Error(AFS_ERR_BAD_ARGUMENT, "need at least two control frames");
+    size_t n_out = 0;
+    for (int v : frameLen_) n_out += (size_t)v;
+    // queue order is frame-major; the ABI wants [utterance][frame]
+    std::vector<afs_tube_frame> t((size_t)n_ * frames_);
+    std::vector<double> g((size_t)n_ * frames_ * AFS_NUM_GLOTTIS_CONTROL);
+    for (int k = 0; k < frames_; k++)
+      for (int b = 0; b < n_; b++) {
+        t[(size_t)b * frames_ + k] = tubes_[(size_t)k * n_ + b];
+        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
+          g[((size_t)b * frames_ + k) * AFS_NUM_GLOTTIS_CONTROL + c] = glottis_[((size_t)k * n_ + b) * AFS_NUM_GLOTTIS_CONTROL + c];
+      }
+    audio->assign((size_t)n_ * n_out, 0.0);
+    if (flow) flow->assign((size_t)n_ * n_out * tdsSrFactor, 0.0);
+    if (status) status->assign((size_t)n_, 0u);
+    check(afs_tds_synthesize(dev_.ctx(), &options, n_, frames_, frameLen_.data(), t.data(), g.data(),
+                             samplingRate * tdsSrFactor, tdsSrFactor, nullptr, audio->data(),
+                             flow ? flow->data() : nullptr, status ? status->data() : nullptr), dev_.ctx());
+    resetMotion();
+  }
+
+ private:
+  Device &dev_;
+  int n_;
+  int frames_ = 0;
+  std::vector<afs_tube_frame> tubes_;
+  std::vector<double> glottis_;
+  std::vector<int32_t> frameLen_;
+};
+
+}  // namespace afs

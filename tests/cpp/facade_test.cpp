@@ -1,0 +1,45 @@
+// Compiles against include/afs_b200.hpp and links libafs_b200.so: a reference-style caller.
+// Without a CUDA device it must fail loudly (no CPU fallback); with one it prints formants and audio
+// statistics that tests/test_facade.py compares with the ctypes path.
+#include <cmath>
+#include <cstdio>
+
+#include "afs_b200.hpp"
+
+int main() {
+  try {
+    afs::Device dev(0);
+    // --- TlModel-style use (Data::getVowelFormants, Data.cpp:149-196) ---
+    const double a_params[16] = {2.066256, 1.143496, 0.117848, 2.693147, 5.744530, 6.962660, 8.276990, 0.940841,
+                                 1.252275, 14.184641, 6.665092, 0.243414, 16.520416, 2.830321, 16.529516, 2.968984};
+    afs::TlModel tl(dev);
+    tl.tubes.resize(2);
+    afs::calculateOneDimTubeFunction(a_params, &tl.tubes[0]);
+    tl.tubes[0].setGlottisArea(0.0);
+    tl.tubes[1] = tl.tubes[0];
+    tl.tubes[1].setVelumOpening(0.5);
+    std::vector<double> f, bw;
+    std::vector<int32_t> n, flags;
+    tl.getFormants(&f, &bw, &n, 8, &flags);
+    std::printf("formants %d %.6f %.6f %.6f nasal %d %.6f\n", n[0], f[0], f[1], f[2], flags[1] & 4 ? 1 : 0, f[8]);
+    afs::ComplexSpectrum s;
+    tl.getSpectrum(afs::TlModel::FLOW_SOURCE_TF, &s, 2048, afs::Tube::FIRST_PHARYNX_SECTION);
+    std::printf("spectrum %d %.16g %.16g\n", s.numFreq, s.re[0], s.im[0]);
+    // --- Synthesizer-style use (Synthesizer.cpp:515-639): prime, then one 50 ms frame ---
+    afs::TdsSynthesizer syn(dev, 2);
+    afs::Tube tubes[2] = {tl.tubes[0], tl.tubes[1]};
+    const double g[12] = {120, 8000, 0.01, 0.01, 0, -40, 150, 8000, 0.01, 0.01, 0, -40};
+    syn.synthesizeSignalTds(tubes, g, 1102);
+    syn.synthesizeSignalTds(tubes, g, 1102);
+    std::vector<double> audio;
+    std::vector<uint32_t> status;
+    syn.flush(&audio, nullptr, &status);
+    double e = 0;
+    for (double v : audio) e += v * v;
+    std::printf("audio %zu %.12e status %u\n", audio.size(), e, status[0] | status[1]);
+  } catch (const afs::Error &err) {
+    std::printf("error %d %s\n", err.status, err.what());
+    return err.status == AFS_ERR_NO_DEVICE ? 0 : 2;
+  }
+  return 0;
+}

@@ -1,0 +1,50 @@
+"""The C++ facade (include/afs_b200.hpp) compiled as a reference-style caller against libafs_b200.so."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+EXE = os.path.join(ROOT, "tests", "cpp", "facade_test")
+
+
+def build_exe():
+    from areafunctionsynthesis_b200.build import build_library
+    build_library()
+    lib_dir = os.path.join(ROOT, "areafunctionsynthesis_b200")
+    src = os.path.join(ROOT, "tests", "cpp", "facade_test.cpp")
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(lib_dir, "libafs_b200.so"))):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-L", lib_dir,
+                        "-lafs_b200", f"-Wl,-rpath,{lib_dir}", "-o", EXE], check=True)
+    return EXE
+
+
+def test_facade_compiles_and_refuses_to_run_without_a_device():
+    import torch
+    exe = build_exe()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if not torch.cuda.is_available():
+        assert r.stdout.startswith("error 1 "), r.stdout  # AFS_ERR_NO_DEVICE: no CPU fallback
+
+
+@pytest.mark.gpu
+def test_facade_matches_ctypes_path(ctx, shapes):
+    exe = build_exe()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = dict((ln.split()[0], ln.split()[1:]) for ln in r.stdout.strip().splitlines())
+    fr = shapes["frames"][[0, 0]].copy()
+    fr["velum_area_cm2"][1] = 0.5
+    f, bw, num, flags = ctx.tl_formants(fr)
+    assert int(lines["formants"][0]) == num[0]
+    np.testing.assert_allclose([float(x) for x in lines["formants"][1:4]], f[0, :3], atol=1e-6)
+    assert int(lines["formants"][5]) == 1 and abs(float(lines["formants"][6]) - f[1, 0]) < 1e-6
+    re, im = ctx.tl_sweep(fr[:1], 22050.0 / 2048, 938)
+    assert int(lines["spectrum"][0]) == 938 and float(lines["spectrum"][1]) == re[0, 0]
+    gl = np.array([[[120, 8000, 0.01, 0.01, 0, -40]] * 2, [[150, 8000, 0.01, 0.01, 0, -40]] * 2], dtype=float)
+    a, _, st = ctx.tds_synthesize(np.stack([fr, fr], axis=1), gl, [1102], 44100.0, 2)
+    assert int(lines["audio"][0]) == a.size and int(lines["audio"][3]) == 0
+    assert abs(float(lines["audio"][1]) - float((a ** 2).sum())) <= 1e-9 * float((a ** 2).sum())
