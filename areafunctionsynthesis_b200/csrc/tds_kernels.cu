@@ -79,6 +79,7 @@ struct TdsSmem {
   double gctl[2][AFS_NUM_GLOTTIS_CONTROL][LANES];
   double glLen[2][2][LANES], glArea[2][2][LANES];  // glottis geometry, double buffered by step parity
   double p4[4][LANES];            // pressures of sections 22..25 after the last update
+  double noseCoup[AFS_NUM_NOSE_SECTIONS][LANES];  // solver: couplings along the nose chain (sinus junctions modified)
   double gx[4][LANES];            // glottis: x0, x1 (current), xp0, xp1 (previous) relative displacements
   double toneX[4][LANES], toneY[4][LANES];   // skin-radiation filter history
   double chebX[8][LANES], chebY[8][LANES];   // output low-pass history
@@ -148,11 +149,46 @@ __device__ __forceinline__ double wall_beta(const TdsParams &P, int wt, const Se
   return P.kalpha[wt] * (st.wc * P.c1[wt] + st.wcr * P.c2[wt] + st.wcr2 * P.c3[wt]);
 }
 
+// ---- fast FP64 reciprocal / sqrt (branch-free) -----------------------------------
+// IEEE division / sqrt compile to ~20-instruction sequences with a slow-path CALL that fences the
+// scheduler; all operands here are positive, normal and well inside the range, so MUFU seed + two
+// Newton steps (error <= ~1 ulp) is enough for the 1e-6 parity bar and lets independent sections
+// interleave.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+__device__ __forceinline__ double fast_div(double a, double b) {
+  const double y = fast_rcp(b);
+  const double q = a * y;
+  return fma(fma(-b, q, a), y, q);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+__device__ __forceinline__ double fast_sqrt(double x) {  // x > 0
+  const double y = fast_rsqrt(x);
+  const double sq = x * y;
+  return fma(fma(-sq, sq, x), 0.5 * y, sq);
+}
+
 // Network elements of a non-sinus section (TdsModel.cpp:759-793).
 __device__ __forceinline__ void section_elements(double area, double length, bool glottal, double &L, double &R,
                                                  double &invr, double &circ) {
-  const double inva = 1.0 / area;
-  const double r = sqrt(area * (1.0 / kPi));
+  const double inva = fast_rcp(area);
+  const double r = fast_sqrt(area * (1.0 / kPi));
   invr = r * kPi * inva;
   circ = 2.0 * kPi * r;  // 2*sqrt(area*pi)
   L = (kRho * 0.5 * length) * inva;
@@ -197,7 +233,7 @@ __device__ __forceinline__ void phase1_dynamic(const TdsParams &P, TdsSmem &S, i
     alpha = surface * P.kalpha[0];
     beta = wall_beta(P, 0, st);
   }
-  const double E = P.dtth / (C + alpha);
+  const double E = P.dtth * fast_rcp(C + alpha);
   const double D = st.p + P.dtth1 * st.pr - E * beta;  // no monopole / flow source (TdsModel.cpp:988-1008)
   S.E[d][lane] = E; S.L[d][lane] = L; S.R[d][lane] = R; S.invr[d][lane] = invr;
   S.alpha[d][lane] = alpha;
@@ -297,67 +333,81 @@ __device__ __forceinline__ void phase2_radiation(const TdsParams &P, TdsSmem &S,
 }
 
 // ---- phase 3: the linear solve ------------------------------------------------
-// Negated system (SPD).  Couplings: two currents meeting in section s are
-// coupled by -E_s (in/out) or by +E_s + G_s (two outs of a branching section),
-// G_s = L_s/(dt theta) + R_s.  Elimination stores 1/pivot in diag[] and the
-// reduced right-hand side in sol[]; back substitution overwrites sol[] with
-// the currents.
+// Negated system (SPD).  Couplings: two currents meeting in section s are coupled by -E_s (in/out) or
+// by +E_s + G_s (two outs of a branching section), G_s = L_s/(dt theta) + R_s.
+//
+// Chains are eliminated in three passes so that no division sits on a loop-carried dependence:
+//   1. pivots as a ratio p/q:  p' = d_next*p - o^2*q,  q' = p   (2 dependent FMAs per node; the
+//      reciprocal pivots w_k = q/p are computed off the critical path and stored in diag[]);
+//   2. reduced right-hand sides r'_next = r_next - (o w_k) r'_k      (1 FMA per node);
+//   3. back substitution u_k = w_k r'_k - (o w_k) u_next             (1 FMA per node).
+// (p, q) are rescaled by an exact power of two every 4 nodes.
+enum Coupling { C_STAT, C_DYN, C_NOSE };
+
 struct Solver {
   TdsSmem &S;
-  const SecAccess &X;
   int lane, cur;
   double idt;
   __device__ __forceinline__ double &d(int i) { return S.diag[i][lane]; }
   __device__ __forceinline__ double &r(int i) { return S.sol[cur][i][lane]; }
-
-  // eliminate a chain first..last (ascending if step=+1), each node k coupled to k+step by -E(link(k)).
-  // Returns with d(last+step), r(last+step) updated.  link section of (k, k+1) is k.
-  __device__ __forceinline__ void chain_up(int first, int last) {  // eliminates first..last, updates last+1
-    double dk = d(first), rk = r(first);
-    for (int k = first; k <= last; k++) {
-      const double w = 1.0 / dk;
-      d(k) = w;
-      const double e = X.E(k);
-      const double t = e * w;
-      dk = d(k + 1) - t * e;
-      rk = r(k + 1) + t * rk;
-      r(k + 1) = rk;
-    }
-    d(last + 1) = dk;
+  // coupling between the currents on both sides of link section ls
+  template <int C>
+  __device__ __forceinline__ double coup(int ls) const {
+    if (C == C_STAT) return -S.cE[ls];
+    if (C == C_DYN) return -S.E[ls - DYN0][lane];
+    return S.noseCoup[ls - NOSE0][lane];
   }
-  __device__ __forceinline__ void chain_up_back(int first, int last) {  // solves last..first given u(last+1)
-    double un = r(last + 1);
-    for (int k = last; k >= first; k--) {
-      un = (r(k) + X.E(k) * un) * d(k);
+  __device__ __forceinline__ double E(int s) const { return is_dyn(s) ? S.E[s - DYN0][lane] : S.cE[s]; }
+  __device__ __forceinline__ double G(int s) const {
+    return is_dyn(s) ? S.L[s - DYN0][lane] * idt + S.R[s - DYN0][lane] : S.cL[s] * idt + S.cR[s];
+  }
+  static __device__ __forceinline__ void rescale(double &p, double &q) {
+    const int e = (__double2hiint(p) >> 20) & 0x7ff;
+    const double sc = __hiloint2double((2046 - e) << 20, 0);
+    p *= sc; q *= sc;
+  }
+  // pass 1 over `count` nodes starting at `first`, direction DIR (+1: link section k, -1: link section k-1).
+  template <int C, int DIR>
+  __device__ __forceinline__ void pivots(int first, int count, double &p, double &q) {
+#pragma unroll 4
+    for (int j = 0; j < count; j++) {
+      const int k = first + DIR * j;
+      const double o = coup<C>(DIR > 0 ? k : k - 1);
+      const double dn = d(k + DIR);
+      d(k) = q * fast_rcp(p);  // w_k, off the critical path
+      const double pn = fma(dn, p, -(o * o) * q);
+      q = p; p = pn;
+      if ((j & 3) == 3) rescale(p, q);
+    }
+  }
+  // pass 2: reduced right-hand sides; rk enters as r'(first), leaves as r'(first + DIR*count)
+  template <int C, int DIR>
+  __device__ __forceinline__ void forward(int first, int count, double &rk) {
+#pragma unroll 4
+    for (int j = 0; j < count; j++) {
+      const int k = first + DIR * j;
+      const double t = coup<C>(DIR > 0 ? k : k - 1) * d(k);
+      rk = fma(-t, rk, r(k + DIR));
+      r(k + DIR) = rk;
+    }
+  }
+  // pass 3: un enters as u(first + DIR*count) ... walks back to `first`
+  template <int C, int DIR>
+  __device__ __forceinline__ void backward(int first, int count, double &un) {
+#pragma unroll 4
+    for (int j = count - 1; j >= 0; j--) {
+      const int k = first + DIR * j;
+      const double w = d(k);
+      const double t = coup<C>(DIR > 0 ? k : k - 1) * w;
+      un = fma(-t, un, w * r(k));
       r(k) = un;
-    }
-  }
-  // descending chain: eliminates first..last (first > last), node k coupled to k-1 through section k-1
-  __device__ __forceinline__ void chain_down(int first, int last, double dk, double rk) {
-    for (int k = first; k >= last; k--) {
-      const double w = 1.0 / dk;
-      d(k) = w;
-      r(k) = rk;
-      const double e = X.E(k - 1);
-      const double t = e * w;
-      dk = d(k - 1) - t * e;
-      rk = r(k - 1) + t * rk;
-    }
-    d(last - 1) = dk;
-    r(last - 1) = rk;
-  }
-  __device__ __forceinline__ void chain_down_back(int first, int last) {  // solves last..first given u(last-1)
-    double up = r(last - 1);
-    for (int k = last; k <= first; k++) {
-      up = (r(k) + X.E(k - 1) * up) * d(k);
-      r(k) = up;
     }
   }
   // Eliminate leaf current c hanging (as second out) on branching section s whose in-current is a and
   // whose other out-current is b: clique {a, b, c}.  Returns the modified coupling o(a,b).
   __device__ __forceinline__ double elim_leaf(int c, int s, int a, int b, double &e_out, double &g_out) {
-    const double e = X.E(s), g = e + X.L(s) * idt + X.R(s);
-    const double w = 1.0 / d(c);
+    const double e = E(s), g = e + G(s);
+    const double w = fast_rcp(d(c));
     d(c) = w;
     const double rc = r(c);
     d(a) -= e * e * w;
@@ -367,121 +417,123 @@ struct Solver {
     e_out = e; g_out = g;
     return -e + e * g * w;
   }
+  // Eliminate node c coupled to a single remaining neighbour a by o.
+  __device__ __forceinline__ void elim_single(int c, int a, double o) {
+    const double w = fast_rcp(d(c));
+    d(c) = w;
+    const double t = o * w;
+    d(a) -= t * o;
+    r(a) -= t * r(c);
+  }
 };
 
-// Nose chain with modified couplings at the four sinus junctions.
-// Order: sinuses 89..92 (leaves), radiation 96, 95, then 83 -> 66; leaves d(65), r(65) reduced.
-__device__ void solve_nose_forward(Solver &Z, double oN[4], double &o8395) {
+// Nose: sinuses 89..92 (leaves), radiation 96, 95, then 83 -> 66; leaves d(65), r(65) reduced.
+__device__ void solve_nose_forward(Solver &Z, double &o8395) {
   double e, g;
-  oN[0] = Z.elim_leaf(89, 73, 73, 74, e, g);
-  oN[1] = Z.elim_leaf(90, 74, 74, 75, e, g);
-  oN[2] = Z.elim_leaf(91, 76, 76, 77, e, g);
-  oN[3] = Z.elim_leaf(92, 77, 77, 78, e, g);
+  for (int j = 0; j < AFS_NUM_NOSE_SECTIONS; j++) Z.S.noseCoup[j][Z.lane] = -Z.E(NOSE0 + j);
+  Z.S.noseCoup[73 - NOSE0][Z.lane] = Z.elim_leaf(89, 73, 73, 74, e, g);
+  Z.S.noseCoup[74 - NOSE0][Z.lane] = Z.elim_leaf(90, 74, 74, 75, e, g);
+  Z.S.noseCoup[76 - NOSE0][Z.lane] = Z.elim_leaf(91, 76, 76, 77, e, g);
+  Z.S.noseCoup[77 - NOSE0][Z.lane] = Z.elim_leaf(92, 77, 77, 78, e, g);
   o8395 = Z.elim_leaf(96, 83, 83, 95, e, g);  // clique {83, 95, 96}
-  {  // eliminate 95 (coupled to 83 by o8395)
-    const double w = 1.0 / Z.d(95);
-    Z.d(95) = w;
-    const double t = o8395 * w;
-    Z.d(83) -= t * o8395;
-    Z.r(83) -= t * Z.r(95);
-  }
-  double dk = Z.d(83), rk = Z.r(83);
-  for (int k = 83; k >= 66; k--) {
-    const double w = 1.0 / dk;
-    Z.d(k) = w;
-    Z.r(k) = rk;
-    const int ls = k - 1;  // link section
-    const double o = ls == 73 ? oN[0] : ls == 74 ? oN[1] : ls == 76 ? oN[2] : ls == 77 ? oN[3] : -Z.X.E(ls);
-    const double t = o * w;
-    dk = Z.d(k - 1) - t * o;
-    rk = Z.r(k - 1) - t * rk;
-  }
-  Z.d(65) = dk;
-  Z.r(65) = rk;
+  Z.elim_single(95, 83, o8395);
+  double p = Z.d(83), q = 1.0, rk = Z.r(83);
+  Z.pivots<C_NOSE, -1>(83, 18, p, q);   // nodes 83..66, links 82..65
+  Z.d(65) = p * fast_rcp(q);
+  Z.forward<C_NOSE, -1>(83, 18, rk);
 }
-__device__ void solve_nose_back(Solver &Z, const double oN[4], double o8395) {
-  double up = Z.r(65);
-  for (int k = 66; k <= 83; k++) {
-    const int ls = k - 1;
-    const double o = ls == 73 ? oN[0] : ls == 74 ? oN[1] : ls == 76 ? oN[2] : ls == 77 ? oN[3] : -Z.X.E(ls);
-    up = (Z.r(k) - o * up) * Z.d(k);
-    Z.r(k) = up;
-  }
-  const double u83 = up;
+__device__ void solve_nose_back(Solver &Z, double o8395) {
+  double un = Z.r(65);
+  Z.backward<C_NOSE, -1>(83, 18, un);
+  const double u83 = Z.r(83);
   const double u95 = (Z.r(95) - o8395 * u83) * Z.d(95);
   Z.r(95) = u95;
   {
-    const double e = Z.X.E(83), g = e + Z.X.L(83) * Z.idt + Z.X.R(83);
+    const double e = Z.E(83), g = e + Z.G(83);
     Z.r(96) = (Z.r(96) + e * u83 - g * u95) * Z.d(96);
   }
   const int sN[4] = {73, 74, 76, 77};
 #pragma unroll
   for (int m = 0; m < 4; m++) {
     const int s = sN[m];
-    const double e = Z.X.E(s), g = e + Z.X.L(s) * Z.idt + Z.X.R(s);
+    const double e = Z.E(s), g = e + Z.G(s);
     Z.r(89 + m) = (Z.r(89 + m) + e * Z.r(s) - g * Z.r(s + 1)) * Z.d(89 + m);
   }
 }
 
-// Mouth chain: radiation 94, 93, then 64 -> 42; leaves d(41), r(41) reduced.
+// Mouth: radiation 94, 93, then 64 -> 42; leaves d(41), r(41) reduced.
 __device__ void solve_mouth_forward(Solver &Z, double &o6493) {
   double e, g;
   o6493 = Z.elim_leaf(94, 64, 64, 93, e, g);
-  {
-    const double w = 1.0 / Z.d(93);
-    Z.d(93) = w;
-    const double t = o6493 * w;
-    Z.d(64) -= t * o6493;
-    Z.r(64) -= t * Z.r(93);
-  }
-  Z.chain_down(64, 42, Z.d(64), Z.r(64));
+  Z.elim_single(93, 64, o6493);
+  double p = Z.d(64), q = 1.0, rk = Z.r(64);
+  Z.pivots<C_DYN, -1>(64, 23, p, q);    // nodes 64..42, links 63..41
+  Z.d(41) = p * fast_rcp(q);
+  Z.forward<C_DYN, -1>(64, 23, rk);
 }
 __device__ void solve_mouth_back(Solver &Z, double o6493) {
-  Z.chain_down_back(64, 42);
+  double un = Z.r(41);
+  Z.backward<C_DYN, -1>(64, 23, un);
   const double u64 = Z.r(64);
   const double u93 = (Z.r(93) - o6493 * u64) * Z.d(93);
   Z.r(93) = u93;
-  const double e = Z.X.E(64), g = e + Z.X.L(64) * Z.idt + Z.X.R(64);
+  const double e = Z.E(64), g = e + Z.G(64);
   Z.r(94) = (Z.r(94) + e * u64 - g * u93) * Z.d(94);
 }
 
-// Trachea + pharynx chain incl. the piriform fossa: fossa 88 -> 85, trachea 0 -> 27, junction {28, 29, 84},
-// pharynx 29 -> 39; leaves d(40), r(40) reduced.
+// Trunk: fossa 88 -> 85, trachea+glottis+pharynx 0 -> 27, junction {28, 29, 84}, pharynx 29 -> 39;
+// leaves d(40), r(40) reduced.
 __device__ void solve_trunk_forward(Solver &Z, double &o2829, double &e28, double &g28) {
-  Z.chain_down(88, 85, Z.d(88), Z.r(88));
-  Z.chain_up(0, 27);
-  o2829 = Z.elim_leaf(84, 28, 28, 29, e28, g28);
-  {
-    const double w = 1.0 / Z.d(28);
-    Z.d(28) = w;
-    const double t = o2829 * w;
-    Z.d(29) -= t * o2829;
-    Z.r(29) -= t * Z.r(28);
+  {  // fossa: nodes 88..85, links 87..84 (static)
+    double p = Z.d(88), q = 1.0, rk = Z.r(88);
+    Z.pivots<C_STAT, -1>(88, 4, p, q);
+    Z.d(84) = p * fast_rcp(q);
+    Z.forward<C_STAT, -1>(88, 4, rk);
   }
-  Z.chain_up(29, 39);
+  {  // nodes 0..22 over static links 0..22, then 23..27 over dynamic links 23..27
+    double p = Z.d(0), q = 1.0, rk = Z.r(0);
+    Z.pivots<C_STAT, +1>(0, 23, p, q);
+    Z.pivots<C_DYN, +1>(23, 5, p, q);
+    Z.d(28) = p * fast_rcp(q);
+    Z.forward<C_STAT, +1>(0, 23, rk);
+    Z.forward<C_DYN, +1>(23, 5, rk);
+  }
+  o2829 = Z.elim_leaf(84, 28, 28, 29, e28, g28);
+  Z.elim_single(28, 29, o2829);
+  {
+    double p = Z.d(29), q = 1.0, rk = Z.r(29);
+    Z.pivots<C_DYN, +1>(29, 11, p, q);  // nodes 29..39, links 29..39
+    Z.d(40) = p * fast_rcp(q);
+    Z.forward<C_DYN, +1>(29, 11, rk);
+  }
 }
 __device__ void solve_trunk_back(Solver &Z, double o2829, double e28, double g28) {
-  Z.chain_up_back(29, 39);
+  double un = Z.r(40);
+  Z.backward<C_DYN, +1>(29, 11, un);
   const double u29 = Z.r(29);
   const double u28 = (Z.r(28) - o2829 * u29) * Z.d(28);
   Z.r(28) = u28;
-  Z.r(84) = (Z.r(84) + e28 * u28 - g28 * u29) * Z.d(84);
-  Z.chain_up_back(0, 27);
-  Z.chain_down_back(88, 85);
+  const double u84 = (Z.r(84) + e28 * u28 - g28 * u29) * Z.d(84);
+  Z.r(84) = u84;
+  un = u28;
+  Z.backward<C_DYN, +1>(23, 5, un);
+  Z.backward<C_STAT, +1>(0, 23, un);
+  un = u84;
+  Z.backward<C_STAT, -1>(88, 4, un);
 }
 // Junction at the velum: clique {40, 41, 65} through section 40.
 __device__ void solve_velum_junction(Solver &Z) {
-  const double e = Z.X.E(40), g = e + Z.X.L(40) * Z.idt + Z.X.R(40);
-  const double w65 = 1.0 / Z.d(65);
+  const double e = Z.E(40), g = e + Z.G(40);
+  const double w65 = fast_rcp(Z.d(65));
   double d40 = Z.d(40) - e * e * w65;
-  double d41 = Z.d(41) - g * g * w65;
+  const double d41 = Z.d(41) - g * g * w65;
   const double o = -e + e * g * w65;
   double r40 = Z.r(40) + e * w65 * Z.r(65);
-  double r41 = Z.r(41) - g * w65 * Z.r(65);
-  const double w41 = 1.0 / d41;
+  const double r41 = Z.r(41) - g * w65 * Z.r(65);
+  const double w41 = fast_rcp(d41);
   d40 -= o * o * w41;
   r40 -= o * w41 * r41;
-  const double u40 = r40 / d40;
+  const double u40 = fast_div(r40, d40);
   const double u41 = (r41 - o * u40) * w41;
   const double u65 = (Z.r(65) + e * u40 - g * u41) * w65;
   Z.r(40) = u40; Z.r(41) = u41; Z.r(65) = u65;
@@ -540,24 +592,28 @@ __device__ __forceinline__ void glottis_open_close(double cordLength, double res
   } else if ((back <= 0.0) && (front <= 0.0)) {
   } else {
     if (fabs(rest) < 0.000000001) rest = 0.000000001;
-    const double zApex = cordLength * (1.0 + rel / rest);
+    const double zApex = cordLength * (1.0 + fast_div(rel, rest));
     if ((zApex >= 0.0) && (zApex <= cordLength)) {
       if (back > 0.0) { ol = zApex; mw = back; cl = cordLength - zApex; mz = 0.5 * (zApex + cordLength); }
       else { ol = cordLength - zApex; mw = front; cl = zApex; mz = 0.5 * zApex; }
     }
   }
 }
-__device__ __forceinline__ void glottis_dims(const TdsParams &P, const double ctl[AFS_NUM_GLOTTIS_CONTROL],
-                                             const GlottisState &g, GlottisDims &D) {
+// tension Q, cord length, thicknesses (getTensionParameter / getLengthAndThickness)
+__device__ __forceinline__ void glottis_tension(const TdsParams &P, double f0, GlottisDims &D) {
   double f0DivQ = P.gs[S_F0_DIV_Q];
   if (f0DivQ < 0.000001) f0DivQ = 0.000001;
-  double Q = 1.0 + (ctl[G_F0] - P.gs[S_NATURAL_F0]) / f0DivQ;
+  double Q = 1.0 + fast_div(f0 - P.gs[S_NATURAL_F0], f0DivQ);
   if (Q < 0.05) Q = 0.05;
-  const double factor = sqrt(Q);
+  const double rs = fast_rsqrt(Q);  // 1/sqrt(Q)
   D.Q = Q;
-  D.cordLength = P.gs[S_REST_LENGTH] * factor;
-  D.th0 = P.gs[S_REST_THICK1] / factor;
-  D.th1 = P.gs[S_REST_THICK2] / factor;
+  D.cordLength = P.gs[S_REST_LENGTH] * (Q * rs);
+  D.th0 = P.gs[S_REST_THICK1] * rs;
+  D.th1 = P.gs[S_REST_THICK2] * rs;
+}
+__device__ __forceinline__ void glottis_dims(const TdsParams &P, const double ctl[AFS_NUM_GLOTTIS_CONTROL],
+                                             const GlottisState &g, GlottisDims &D) {
+  glottis_tension(P, ctl[G_F0], D);
   glottis_open_close(D.cordLength, ctl[G_REST1], g.x0, D.ol0, D.cl0, D.mw0, D.mz0);
   glottis_open_close(D.cordLength, ctl[G_REST2], g.x1, D.ol1, D.cl1, D.mw1, D.mz1);
 }
@@ -567,19 +623,21 @@ __device__ __forceinline__ void glottis_inc_time(const TdsParams &P, const doubl
   GlottisDims D;
   glottis_dims(P, ctl, g, D);
   const double T = P.dt, Q = D.Q;
-  const double m0 = P.gs[S_MASS1] / Q, m1 = P.gs[S_MASS2] / Q;
-  const double al0 = D.cl0 / D.cordLength, al1 = D.cl1 / D.cordLength;
+  const double iQ = fast_rcp(Q), iLen = fast_rcp(D.cordLength);
+  const double m0 = P.gs[S_MASS1] * iQ, m1 = P.gs[S_MASS2] * iQ;
+  const double al0 = D.cl0 * iLen, al1 = D.cl1 * iLen;
   const double k0 = P.gs[S_K1] * Q, k1 = P.gs[S_K2] * Q;
   const double ck0 = P.gs[S_CK1] * Q, ck1 = P.gs[S_CK2] * Q;
   const double kc = P.gs[S_KC] * Q * Q;
   const double dr0 = P.gs[S_DAMP1] + al0 * 1.0, dr1 = P.gs[S_DAMP2] + al1 * 1.0;
-  const double r0 = 2.0 * dr0 * sqrt(m0 * k0), r1 = 2.0 * dr1 * sqrt(m1 * k1);
+  // mass*spring = MASS*K (Q cancels): sqrt of a launch constant
+  const double r0 = 2.0 * dr0 * fast_sqrt(m0 * k0), r1 = 2.0 * dr1 * fast_sqrt(m1 * k1);
   double f0 = p[1] * D.ol0 * D.th0, f1 = p[2] * D.ol1 * D.th1;
   f0 += 0.5 * 0.5 * (p[0] + p[1]) * P.gs[S_INLET] * D.cordLength;
   f1 += 0.5 * 0.5 * (p[3] + p[2]) * P.gs[S_OUTLET] * D.cordLength;
   const double rest0 = ctl[G_REST1], rest1 = ctl[G_REST2];
-  const double rs0 = (rest0 >= 0.0) ? rest0 * (1.0 - D.mz0 / D.cordLength) : rest0;
-  const double rs1 = (rest1 >= 0.0) ? rest1 * (1.0 - D.mz1 / D.cordLength) : rest1;
+  const double rs0 = (rest0 >= 0.0) ? rest0 * (1.0 - D.mz0 * iLen) : rest0;
+  const double rs1 = (rest1 >= 0.0) ? rest1 * (1.0 - D.mz1 * iLen) : rest1;
   const double A = m0 + r0 * T + T * T * (k0 + ck0 * al0) + kc * T * T;
   const double B = -kc * T * T;
   const double C = -kc * T * T;
@@ -588,8 +646,9 @@ __device__ __forceinline__ void glottis_inc_time(const TdsParams &P, const doubl
   const double F = f1 * T * T + 2.0 * m1 * g.x1 - m1 * g.xp1 + r1 * T * g.x1 - T * T * ck1 * al1 * rs1;
   double det = A * Dd - B * C;
   if (fabs(det) < 0.000000001) det = 0.000000001;
-  const double n0 = (E * Dd - B * F) / det;
-  const double n1 = (A * F - E * C) / det;
+  const double idet = fast_rcp(det);
+  const double n0 = (E * Dd - B * F) * idet;
+  const double n1 = (A * F - E * C) * idet;
   g.xp0 = g.x0; g.xp1 = g.x1;
   g.x0 = n0; g.x1 = n1;
 }
@@ -702,6 +761,12 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
   uint32_t bad = 0;
 
   int interval = -1, i0 = 0, i1 = 0;  // current control interval [i0, i1)
+#ifdef AFS_TDS_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define AFS_TICK(k) do { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } while (0)
+#else
+#define AFS_TICK(k) do { } while (0)
+#endif
 
   for (int n = 0; n < P.total_steps; n++) {
     const int cur = n & 1, prev = cur ^ 1;
@@ -741,6 +806,7 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
     const double ratio = (double)(n - i0) / (double)(i1 - i0);
     const double ratio1 = 1.0 - ratio;
 
+    AFS_TICK(0);
     // ======================= phase 1: elements, E, D ==========================
 #pragma unroll
     for (int k = 0; k < KD; k++) {
@@ -752,7 +818,9 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       const int t = k * NWS + warp;
       if (t < NSTAT) phase1_static(P, S, lane, static_section_of(t), sta[k]);
     }
+    AFS_TICK(1);
     __syncthreads();
+    AFS_TICK(2);
 
     // ======================= phase 2: matrix rows =============================
     {
@@ -770,15 +838,17 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       if (warp == NWS - 2) phase2_radiation(P, S, X, lane, MOUTH_LAST, 93, urR, urL, prev, cur);
       if (warp == NWS - 1) phase2_radiation(P, S, X, lane, NOSE_LAST, 95, urR, urL, prev, cur);
     }
+    AFS_TICK(3);
     __syncthreads();
+    AFS_TICK(4);
 
     // ======================= phase 3: solve (+ glottis, + output) =============
     {
-      Solver Z{S, X, lane, cur, P.idt};
-      double oN[4], oA = 0.0, e28 = 0.0, g28 = 0.0;
+      Solver Z{S, lane, cur, P.idt};
+      double oA = 0.0, e28 = 0.0, g28 = 0.0;
       if (warp == 0) solve_trunk_forward(Z, oA, e28, g28);
       else if (warp == 1) solve_mouth_forward(Z, oA);
-      else if (warp == 2) solve_nose_forward(Z, oN, oA);
+      else if (warp == 2) solve_nose_forward(Z, oA);
       else if (warp == W_GLOTTIS) {
         // incTime for this step (pressures of the previous step), then the geometry step n+1 will use
         double ctl[AFS_NUM_GLOTTIS_CONTROL], p[4], len[2], ar[2];
@@ -795,14 +865,16 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       } else if (warp == W_OUTPUT && n > 0) {
         emit_output(P, S, lane, prev, n, active, tract, n_out, audio, flow, bad);
       }
+      AFS_TICK(7);
       __syncthreads();
       if (warp == 0) solve_velum_junction(Z);
       __syncthreads();
       if (warp == 0) solve_trunk_back(Z, oA, e28, g28);
       else if (warp == 1) solve_mouth_back(Z, oA);
-      else if (warp == 2) solve_nose_back(Z, oN, oA);
+      else if (warp == 2) solve_nose_back(Z, oA);
     }
     __syncthreads();
+    AFS_TICK(5);
 
     // ======================= phase 4: update ==================================
 #pragma unroll
@@ -820,6 +892,7 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       urR = (S.sol[cur][iR][lane] - S.sol[prev][iR][lane]) * P.idt - P.th * urR;
       urL = (S.sol[cur][iR + 1][lane] - S.sol[prev][iR + 1][lane]) * P.idt - P.th * urL;
     }
+    AFS_TICK(6);
     if (dump && P.dump_step == n + 1) {  // diagnostics: state of tract 0 after step n+1
       if (blockIdx.x == 0 && lane == 0) {
 #define AFS_DUMP(sec, st)                                                                  \
@@ -847,6 +920,9 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
     }
     __syncthreads();
   }
+#ifdef AFS_TDS_TIMING
+  if (dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) dump[warp * 8 + k] = (double)tacc[k];
+#endif
   // epilogue: output of the last step
   if (warp == W_OUTPUT) {
     if (P.total_steps > 0)

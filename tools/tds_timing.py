@@ -1,0 +1,19 @@
+"""Per-phase clock64 breakdown of tds_batch_kernel (needs a build with AFS_TDS_TIMING=1)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import areafunctionsynthesis_b200 as afs
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)) + "/..")
+from bench import make_tds_batch
+B, T = 4096, 2205
+ctx = afs.Context(0)
+fr, gl = make_tds_batch(B, 1)
+buf = np.zeros(473); ctx.set_state_dump(10**9, buf)
+a, _, _ = ctx.tds_synthesize(fr, gl, [T // 2 + 1], 44100.0, 2)
+steps = (T // 2 + 1) * 2
+names = ["loop+stage+bar", "P1 compute", "P1 barrier", "P2 compute", "P2 barrier", "P3 rest(bar,junction,back)", "P4 compute", "P3 fwd/glottis/output"]
+t = buf[:128].reshape(16, 8) / steps
+print("cycles per step, per warp (lane 0 of CTA 0):")
+print("warp " + " ".join(f"{n[:12]:>12s}" for n in names) + "        total")
+for w in range(16):
+    print(f"{w:4d} " + " ".join(f"{v:12.0f}" for v in t[w]) + f" {t[w].sum():12.0f}")
