@@ -79,7 +79,9 @@ struct TdsSmem {
   double gctl[2][AFS_NUM_GLOTTIS_CONTROL][LANES];
   double glLen[2][2][LANES], glArea[2][2][LANES];  // glottis geometry, double buffered by step parity
   double p4[4][LANES];            // pressures of sections 22..25 after the last update
-  double noseCoup[AFS_NUM_NOSE_SECTIONS][LANES];  // solver: couplings along the nose chain (sinus junctions modified)
+  double side[9][3][LANES];       // solver: per-segment contributions to the left separator + new coupling (dd_a, dr_a, c_ab)
+  double leaf[9][LANES];          // solver: fossa (dd28, dr28, dd29, dr29, o2829), mouth / nose radiation (dd, dr)
+  double g3[3][LANES];            // G = L/(dt theta)+R of the dynamic branching sections 28, 40, 64
   double gx[4][LANES];            // glottis: x0, x1 (current), xp0, xp1 (previous) relative displacements
   double toneX[4][LANES], toneY[4][LANES];   // skin-radiation filter history
   double chebX[8][LANES], chebY[8][LANES];   // output low-pass history
@@ -238,6 +240,7 @@ __device__ __forceinline__ void phase1_dynamic(const TdsParams &P, TdsSmem &S, i
   S.E[d][lane] = E; S.L[d][lane] = L; S.R[d][lane] = R; S.invr[d][lane] = invr;
   S.alpha[d][lane] = alpha;
   S.D[s][lane] = D;
+  if (s == 28 || s == 40 || s == 64) S.g3[s == 28 ? 0 : s == 40 ? 1 : 2][lane] = L * P.idt + R;
 }
 
 __device__ __forceinline__ void phase1_static(const TdsParams &P, TdsSmem &S, int lane, int s, const SecState &st) {
@@ -332,17 +335,20 @@ __device__ __forceinline__ void phase2_radiation(const TdsParams &P, TdsSmem &S,
   }
 }
 
-// ---- phase 3: the linear solve ------------------------------------------------
+// ---- phase 3: the linear solve (parallel partition) ------------------------------
 // Negated system (SPD).  Couplings: two currents meeting in section s are coupled by -E_s (in/out) or
-// by +E_s + G_s (two outs of a branching section), G_s = L_s/(dt theta) + R_s.
-//
-// Chains are eliminated in three passes so that no division sits on a loop-carried dependence:
-//   1. pivots as a ratio p/q:  p' = d_next*p - o^2*q,  q' = p   (2 dependent FMAs per node; the
-//      reciprocal pivots w_k = q/p are computed off the critical path and stored in diag[]);
-//   2. reduced right-hand sides r'_next = r_next - (o w_k) r'_k      (1 FMA per node);
-//   3. back substitution u_k = w_k r'_k - (o w_k) u_next             (1 FMA per node).
-// (p, q) are rescaled by an exact power of two every 4 nodes.
-enum Coupling { C_STAT, C_DYN, C_NOSE };
+// by +E_s + G_s (two outs of a branching section), G_s = L_s/(dt theta) + R_s.  The graph is a tree of
+// 3-cliques, so elimination from the leaves has no fill.  A single warp can only issue one FP64
+// instruction every ~3 cycles (measured), so the 97 unknowns are cut into SEGMENTS that different
+// warps eliminate concurrently (one tract per lane in every warp):
+//   3a  each segment warp eliminates its interior nodes towards its two separator nodes (the coupling
+//       to the left separator travels along as a "spike" f); leaf cliques (sinuses, radiation pairs,
+//       piriform fossa) are folded in by the warp that owns their neighbours or by a leaf warp;
+//   3b  the reduced system over the 11 separators 9,19,28,29,40 | 41,53,64 | 65,75,83 (three short
+//       chains meeting in the velum clique {40,41,65}) is solved by three warps + one junction step;
+//   3c  every segment warp back-substitutes its interior.
+// Per interior node i the forward pass stores T = o_i/d'_i (in diag[]), G = r'_i/d'_i (in sol[]) and
+// H = f_i/d'_i (scratch aliased on the L/R/invr exchange arrays, dead after phase 2).
 
 struct Solver {
   TdsSmem &S;
@@ -350,62 +356,19 @@ struct Solver {
   double idt;
   __device__ __forceinline__ double &d(int i) { return S.diag[i][lane]; }
   __device__ __forceinline__ double &r(int i) { return S.sol[cur][i][lane]; }
-  // coupling between the currents on both sides of link section ls
-  template <int C>
-  __device__ __forceinline__ double coup(int ls) const {
-    if (C == C_STAT) return -S.cE[ls];
-    if (C == C_DYN) return -S.E[ls - DYN0][lane];
-    return S.noseCoup[ls - NOSE0][lane];
-  }
+  __device__ __forceinline__ double &H(int i) { return (&S.L[0])[i][lane]; }  // L,R,invr are contiguous: 138 >= 97 items
+  // side slot of a segment warp: warps 0,1,2 -> 0..2, 5..10 -> 3..8
+  __device__ __forceinline__ double &side(int w, int k) { return S.side[w < 3 ? w : w - 2][k][lane]; }
+  __device__ __forceinline__ double &leaf(int k) { return S.leaf[k][lane]; }
   __device__ __forceinline__ double E(int s) const { return is_dyn(s) ? S.E[s - DYN0][lane] : S.cE[s]; }
+  // G_s of the branching sections: static ones from the table, dynamic ones (28, 40, 64) published in phase 1
   __device__ __forceinline__ double G(int s) const {
-    return is_dyn(s) ? S.L[s - DYN0][lane] * idt + S.R[s - DYN0][lane] : S.cL[s] * idt + S.cR[s];
+    return s == 28 ? S.g3[0][lane] : s == 40 ? S.g3[1][lane] : s == 64 ? S.g3[2][lane] : S.cL[s] * idt + S.cR[s];
   }
-  static __device__ __forceinline__ void rescale(double &p, double &q) {
-    const int e = (__double2hiint(p) >> 20) & 0x7ff;
-    const double sc = __hiloint2double((2046 - e) << 20, 0);
-    p *= sc; q *= sc;
-  }
-  // pass 1 over `count` nodes starting at `first`, direction DIR (+1: link section k, -1: link section k-1).
-  template <int C, int DIR>
-  __device__ __forceinline__ void pivots(int first, int count, double &p, double &q) {
-#pragma unroll 4
-    for (int j = 0; j < count; j++) {
-      const int k = first + DIR * j;
-      const double o = coup<C>(DIR > 0 ? k : k - 1);
-      const double dn = d(k + DIR);
-      d(k) = q * fast_rcp(p);  // w_k, off the critical path
-      const double pn = fma(dn, p, -(o * o) * q);
-      q = p; p = pn;
-      if ((j & 3) == 3) rescale(p, q);
-    }
-  }
-  // pass 2: reduced right-hand sides; rk enters as r'(first), leaves as r'(first + DIR*count)
-  template <int C, int DIR>
-  __device__ __forceinline__ void forward(int first, int count, double &rk) {
-#pragma unroll 4
-    for (int j = 0; j < count; j++) {
-      const int k = first + DIR * j;
-      const double t = coup<C>(DIR > 0 ? k : k - 1) * d(k);
-      rk = fma(-t, rk, r(k + DIR));
-      r(k + DIR) = rk;
-    }
-  }
-  // pass 3: un enters as u(first + DIR*count) ... walks back to `first`
-  template <int C, int DIR>
-  __device__ __forceinline__ void backward(int first, int count, double &un) {
-#pragma unroll 4
-    for (int j = count - 1; j >= 0; j--) {
-      const int k = first + DIR * j;
-      const double w = d(k);
-      const double t = coup<C>(DIR > 0 ? k : k - 1) * w;
-      un = fma(-t, un, w * r(k));
-      r(k) = un;
-    }
-  }
-  // Eliminate leaf current c hanging (as second out) on branching section s whose in-current is a and
-  // whose other out-current is b: clique {a, b, c}.  Returns the modified coupling o(a,b).
-  __device__ __forceinline__ double elim_leaf(int c, int s, int a, int b, double &e_out, double &g_out) {
+
+  // Eliminate leaf current c (second out of branching section s) into its clique partners a (in-current of s)
+  // and b (other out-current), both updated IN PLACE.  Returns the modified coupling o(a,b).
+  __device__ __forceinline__ double leaf_in_place(int c, int s, int a, int b) {
     const double e = E(s), g = e + G(s);
     const double w = fast_rcp(d(c));
     d(c) = w;
@@ -414,115 +377,142 @@ struct Solver {
     d(b) -= g * g * w;
     r(a) += e * w * rc;
     r(b) -= g * w * rc;
-    e_out = e; g_out = g;
     return -e + e * g * w;
   }
-  // Eliminate node c coupled to a single remaining neighbour a by o.
-  __device__ __forceinline__ void elim_single(int c, int a, double o) {
-    const double w = fast_rcp(d(c));
-    d(c) = w;
-    const double t = o * w;
-    d(a) -= t * o;
-    r(a) -= t * r(c);
+  __device__ __forceinline__ void leaf_back(int c, int s, int a, int b) {
+    const double e = E(s), g = e + G(s);
+    r(c) = (r(c) + e * r(a) - g * r(b)) * d(c);
   }
+
+  // 3a: eliminate `count` interior nodes first, first+dir, ... towards separator b = first + dir*count; a (or -1)
+  // is the separator on the other side.  Link sections ov0s / ov1s carry modified couplings ov0 / ov1.
+  __device__ __forceinline__ void seg_forward(int w_id, int a, int first, int count, int dir, int ov0s, double ov0,
+                                              int ov1s, double ov1) {
+    double f = 0.0;
+    if (a >= 0) { const int ls = dir > 0 ? a : a - 1; f = ls == ov0s ? ov0 : ls == ov1s ? ov1 : -E(ls); }
+    double dc = d(first), rc = r(first), dda = 0.0, dra = 0.0;
+    int i = first;
+#pragma unroll 2
+    for (int j = 0; j < count; j++, i += dir) {
+      const int ls = dir > 0 ? i : i - 1;
+      const double o = ls == ov0s ? ov0 : ls == ov1s ? ov1 : -E(ls);
+      const double dn = d(i + dir), rn = r(i + dir);
+      const double w = fast_rcp(dc);
+      const double t = o * w, h = f * w;
+      d(i) = t; r(i) = rc * w; H(i) = h;
+      dda = fma(h, f, dda); dra = fma(h, rc, dra);
+      dc = fma(-t, o, dn);
+      rc = fma(-t, rc, rn);
+      f = -t * f;
+    }
+    d(i) = dc; r(i) = rc;  // separator b, in place (only this warp touches it in 3a)
+    side(w_id, 0) = dda; side(w_id, 1) = dra; side(w_id, 2) = f;
+  }
+  // 3c: u_i = G_i - H_i u_a - T_i u_next, walking back from b
+  __device__ __forceinline__ void seg_back(int a, int first, int count, int dir) {
+    const double ua = a >= 0 ? r(a) : 0.0;
+    int i = first + dir * (count - 1);
+    double un = r(i + dir);
+#pragma unroll 2
+    for (int j = 0; j < count; j++, i -= dir) {
+      un = fma(-d(i), un, fma(-H(i), ua, r(i)));
+      r(i) = un;
+    }
+  }
+  // 3b helpers on separators (in place): eliminate x into y over coupling c / recover x from y
+  __device__ __forceinline__ void elim_into(int x, int y, double c) {
+    const double w = fast_rcp(d(x));
+    d(x) = w;
+    const double t = c * w;
+    d(y) -= t * c;
+    r(y) -= t * r(x);
+  }
+  __device__ __forceinline__ void back_from(int x, int y, double c) { r(x) = (r(x) - c * r(y)) * d(x); }
 };
 
-// Nose: sinuses 89..92 (leaves), radiation 96, 95, then 83 -> 66; leaves d(65), r(65) reduced.
-__device__ void solve_nose_forward(Solver &Z, double &o8395) {
-  double e, g;
-  for (int j = 0; j < AFS_NUM_NOSE_SECTIONS; j++) Z.S.noseCoup[j][Z.lane] = -Z.E(NOSE0 + j);
-  Z.S.noseCoup[73 - NOSE0][Z.lane] = Z.elim_leaf(89, 73, 73, 74, e, g);
-  Z.S.noseCoup[74 - NOSE0][Z.lane] = Z.elim_leaf(90, 74, 74, 75, e, g);
-  Z.S.noseCoup[76 - NOSE0][Z.lane] = Z.elim_leaf(91, 76, 76, 77, e, g);
-  Z.S.noseCoup[77 - NOSE0][Z.lane] = Z.elim_leaf(92, 77, 77, 78, e, g);
-  o8395 = Z.elim_leaf(96, 83, 83, 95, e, g);  // clique {83, 95, 96}
-  Z.elim_single(95, 83, o8395);
-  double p = Z.d(83), q = 1.0, rk = Z.r(83);
-  Z.pivots<C_NOSE, -1>(83, 18, p, q);   // nodes 83..66, links 82..65
-  Z.d(65) = p * fast_rcp(q);
-  Z.forward<C_NOSE, -1>(83, 18, rk);
-}
-__device__ void solve_nose_back(Solver &Z, double o8395) {
-  double un = Z.r(65);
-  Z.backward<C_NOSE, -1>(83, 18, un);
-  const double u83 = Z.r(83);
-  const double u95 = (Z.r(95) - o8395 * u83) * Z.d(95);
-  Z.r(95) = u95;
-  {
-    const double e = Z.E(83), g = e + Z.G(83);
-    Z.r(96) = (Z.r(96) + e * u83 - g * u95) * Z.d(96);
-  }
-  const int sN[4] = {73, 74, 76, 77};
-#pragma unroll
-  for (int m = 0; m < 4; m++) {
-    const int s = sN[m];
-    const double e = Z.E(s), g = e + Z.G(s);
-    Z.r(89 + m) = (Z.r(89 + m) + e * Z.r(s) - g * Z.r(s + 1)) * Z.d(89 + m);
+// warp roles in phase 3 (warps W_GLOTTIS = 3 and W_OUTPUT = 4 run the glottis and the output filters)
+enum { R_T0 = 0, R_T1 = 1, R_T2 = 2, R_T4 = 5, R_M1 = 6, R_M2 = 7, R_N1 = 8, R_N2 = 9, R_FOSSA = 10, R_RADM = 11,
+       R_RADN = 12, R_RED_T = 13, R_RED_M = 14, R_RED_N = 15 };
+
+__device__ __forceinline__ void solve_3a(Solver &Z, int warp, double &k0, double &k1) {
+  switch (warp) {
+    case R_T0: Z.seg_forward(warp, -1, 0, 9, +1, -1, 0.0, -1, 0.0); break;    // 0..8   -> 9
+    case R_T1: Z.seg_forward(warp, 9, 10, 9, +1, -1, 0.0, -1, 0.0); break;    // 10..18 -> 19
+    case R_T2: Z.seg_forward(warp, 19, 20, 8, +1, -1, 0.0, -1, 0.0); break;   // 20..27 -> 28
+    case R_T4: Z.seg_forward(warp, 29, 30, 10, +1, -1, 0.0, -1, 0.0); break;  // 30..39 -> 40
+    case R_M1: Z.seg_forward(warp, 41, 42, 11, +1, -1, 0.0, -1, 0.0); break;  // 42..52 -> 53
+    case R_M2: Z.seg_forward(warp, 53, 54, 10, +1, -1, 0.0, -1, 0.0); break;  // 54..63 -> 64
+    case R_N1:  // sinuses 89 (on 73: {73,74}) and 90 (on 74: {74,75}), then 66..74 -> 75
+      k0 = Z.leaf_in_place(89, 73, 73, 74);
+      k1 = Z.leaf_in_place(90, 74, 74, 75);
+      Z.seg_forward(warp, 65, 66, 9, +1, 73, k0, 74, k1);
+      break;
+    case R_N2:  // sinuses 91 (on 76: {76,77}) and 92 (on 77: {77,78}), then 76..82 -> 83
+      k0 = Z.leaf_in_place(91, 76, 76, 77);
+      k1 = Z.leaf_in_place(92, 77, 77, 78);
+      Z.seg_forward(warp, 75, 76, 7, +1, 76, k0, 77, k1);
+      break;
+    case R_FOSSA: {  // fossa chain 88..85 -> 84, then 84 out of the clique {28, 29, 84}
+      Z.seg_forward(warp, -1, 88, 4, -1, -1, 0.0, -1, 0.0);
+      const double e = Z.E(28), g = e + Z.G(28);
+      const double w = fast_rcp(Z.d(84));
+      Z.d(84) = w;
+      const double rc = Z.r(84);
+      Z.leaf(0) = e * e * w;       // dd28
+      Z.leaf(1) = -e * w * rc;     // dr28
+      Z.leaf(2) = g * g * w;       // dd29
+      Z.leaf(3) = g * w * rc;      // dr29
+      Z.leaf(4) = -e + e * g * w;  // o(28,29)
+      break;
+    }
+    case R_RADM:
+    case R_RADN: {  // radiation pair: iL = iR+1 out of {s_in, iR, iL}, then iR; contributions to the separator
+      const int sec = warp == R_RADM ? MOUTH_LAST : NOSE_LAST, iR = warp == R_RADM ? 93 : 95, iL = iR + 1;
+      const double e = Z.E(sec), g = e + Z.G(sec);
+      const double wL = fast_rcp(Z.d(iL));
+      Z.d(iL) = wL;
+      const double rL = Z.r(iL);
+      double dds = e * e * wL, drs = -e * wL * rL;
+      const double dR = Z.d(iR) - g * g * wL, rR = Z.r(iR) - g * wL * rL;
+      const double o = -e + e * g * wL;
+      const double wR = fast_rcp(dR);
+      Z.d(iR) = wR; Z.r(iR) = rR;
+      dds += o * o * wR; drs += o * wR * rR;
+      Z.leaf(warp == R_RADM ? 5 : 7) = dds; Z.leaf(warp == R_RADM ? 6 : 8) = drs;
+      k0 = o;
+      break;
+    }
+    default: break;
   }
 }
 
-// Mouth: radiation 94, 93, then 64 -> 42; leaves d(41), r(41) reduced.
-__device__ void solve_mouth_forward(Solver &Z, double &o6493) {
-  double e, g;
-  o6493 = Z.elim_leaf(94, 64, 64, 93, e, g);
-  Z.elim_single(93, 64, o6493);
-  double p = Z.d(64), q = 1.0, rk = Z.r(64);
-  Z.pivots<C_DYN, -1>(64, 23, p, q);    // nodes 64..42, links 63..41
-  Z.d(41) = p * fast_rcp(q);
-  Z.forward<C_DYN, -1>(64, 23, rk);
-}
-__device__ void solve_mouth_back(Solver &Z, double o6493) {
-  double un = Z.r(41);
-  Z.backward<C_DYN, -1>(64, 23, un);
-  const double u64 = Z.r(64);
-  const double u93 = (Z.r(93) - o6493 * u64) * Z.d(93);
-  Z.r(93) = u93;
-  const double e = Z.E(64), g = e + Z.G(64);
-  Z.r(94) = (Z.r(94) + e * u64 - g * u93) * Z.d(94);
-}
-
-// Trunk: fossa 88 -> 85, trachea+glottis+pharynx 0 -> 27, junction {28, 29, 84}, pharynx 29 -> 39;
-// leaves d(40), r(40) reduced.
-__device__ void solve_trunk_forward(Solver &Z, double &o2829, double &e28, double &g28) {
-  {  // fossa: nodes 88..85, links 87..84 (static)
-    double p = Z.d(88), q = 1.0, rk = Z.r(88);
-    Z.pivots<C_STAT, -1>(88, 4, p, q);
-    Z.d(84) = p * fast_rcp(q);
-    Z.forward<C_STAT, -1>(88, 4, rk);
+// 3b: reduced system.  Forward: three separator chains; junction; back.
+__device__ __forceinline__ void solve_3b_forward(Solver &Z, int warp) {
+  if (warp == R_RED_T) {
+    Z.d(9) -= Z.side(R_T1, 0); Z.r(9) -= Z.side(R_T1, 1);
+    Z.d(19) -= Z.side(R_T2, 0); Z.r(19) -= Z.side(R_T2, 1);
+    Z.d(28) -= Z.leaf(0); Z.r(28) -= Z.leaf(1);
+    Z.d(29) -= Z.leaf(2) + Z.side(R_T4, 0); Z.r(29) -= Z.leaf(3) + Z.side(R_T4, 1);
+    Z.elim_into(9, 19, Z.side(R_T1, 2));
+    Z.elim_into(19, 28, Z.side(R_T2, 2));
+    Z.elim_into(28, 29, Z.leaf(4));
+    Z.elim_into(29, 40, Z.side(R_T4, 2));
+  } else if (warp == R_RED_M) {
+    Z.d(41) -= Z.side(R_M1, 0); Z.r(41) -= Z.side(R_M1, 1);
+    Z.d(53) -= Z.side(R_M2, 0); Z.r(53) -= Z.side(R_M2, 1);
+    Z.d(64) -= Z.leaf(5); Z.r(64) -= Z.leaf(6);
+    Z.elim_into(64, 53, Z.side(R_M2, 2));
+    Z.elim_into(53, 41, Z.side(R_M1, 2));
+  } else if (warp == R_RED_N) {
+    Z.d(65) -= Z.side(R_N1, 0); Z.r(65) -= Z.side(R_N1, 1);
+    Z.d(75) -= Z.side(R_N2, 0); Z.r(75) -= Z.side(R_N2, 1);
+    Z.d(83) -= Z.leaf(7); Z.r(83) -= Z.leaf(8);
+    Z.elim_into(83, 75, Z.side(R_N2, 2));
+    Z.elim_into(75, 65, Z.side(R_N1, 2));
   }
-  {  // nodes 0..22 over static links 0..22, then 23..27 over dynamic links 23..27
-    double p = Z.d(0), q = 1.0, rk = Z.r(0);
-    Z.pivots<C_STAT, +1>(0, 23, p, q);
-    Z.pivots<C_DYN, +1>(23, 5, p, q);
-    Z.d(28) = p * fast_rcp(q);
-    Z.forward<C_STAT, +1>(0, 23, rk);
-    Z.forward<C_DYN, +1>(23, 5, rk);
-  }
-  o2829 = Z.elim_leaf(84, 28, 28, 29, e28, g28);
-  Z.elim_single(28, 29, o2829);
-  {
-    double p = Z.d(29), q = 1.0, rk = Z.r(29);
-    Z.pivots<C_DYN, +1>(29, 11, p, q);  // nodes 29..39, links 29..39
-    Z.d(40) = p * fast_rcp(q);
-    Z.forward<C_DYN, +1>(29, 11, rk);
-  }
-}
-__device__ void solve_trunk_back(Solver &Z, double o2829, double e28, double g28) {
-  double un = Z.r(40);
-  Z.backward<C_DYN, +1>(29, 11, un);
-  const double u29 = Z.r(29);
-  const double u28 = (Z.r(28) - o2829 * u29) * Z.d(28);
-  Z.r(28) = u28;
-  const double u84 = (Z.r(84) + e28 * u28 - g28 * u29) * Z.d(84);
-  Z.r(84) = u84;
-  un = u28;
-  Z.backward<C_DYN, +1>(23, 5, un);
-  Z.backward<C_STAT, +1>(0, 23, un);
-  un = u84;
-  Z.backward<C_STAT, -1>(88, 4, un);
 }
 // Junction at the velum: clique {40, 41, 65} through section 40.
-__device__ void solve_velum_junction(Solver &Z) {
+__device__ __forceinline__ void solve_velum_junction(Solver &Z) {
   const double e = Z.E(40), g = e + Z.G(40);
   const double w65 = fast_rcp(Z.d(65));
   double d40 = Z.d(40) - e * e * w65;
@@ -537,6 +527,44 @@ __device__ void solve_velum_junction(Solver &Z) {
   const double u41 = (r41 - o * u40) * w41;
   const double u65 = (Z.r(65) + e * u40 - g * u41) * w65;
   Z.r(40) = u40; Z.r(41) = u41; Z.r(65) = u65;
+}
+__device__ __forceinline__ void solve_3b_back(Solver &Z, int warp) {
+  if (warp == R_RED_T) {
+    Z.back_from(29, 40, Z.side(R_T4, 2));
+    Z.back_from(28, 29, Z.leaf(4));
+    Z.back_from(19, 28, Z.side(R_T2, 2));
+    Z.back_from(9, 19, Z.side(R_T1, 2));
+  } else if (warp == R_RED_M) {
+    Z.back_from(53, 41, Z.side(R_M1, 2));
+    Z.back_from(64, 53, Z.side(R_M2, 2));
+  } else if (warp == R_RED_N) {
+    Z.back_from(75, 65, Z.side(R_N1, 2));
+    Z.back_from(83, 75, Z.side(R_N2, 2));
+  }
+}
+__device__ __forceinline__ void solve_3c(Solver &Z, int warp, double k0) {
+  switch (warp) {
+    case R_T0: Z.seg_back(-1, 0, 9, +1); break;
+    case R_T1: Z.seg_back(9, 10, 9, +1); break;
+    case R_T2: Z.seg_back(19, 20, 8, +1); break;
+    case R_T4: Z.seg_back(29, 30, 10, +1); break;
+    case R_M1: Z.seg_back(41, 42, 11, +1); break;
+    case R_M2: Z.seg_back(53, 54, 10, +1); break;
+    case R_N1: Z.seg_back(65, 66, 9, +1); Z.leaf_back(89, 73, 73, 74); Z.leaf_back(90, 74, 74, 75); break;
+    case R_N2: Z.seg_back(75, 76, 7, +1); Z.leaf_back(91, 76, 76, 77); Z.leaf_back(92, 77, 77, 78); break;
+    case R_FOSSA: Z.leaf_back(84, 28, 28, 29); Z.seg_back(-1, 88, 4, -1); break;
+    case R_RADM:
+    case R_RADN: {
+      const int sec = warp == R_RADM ? MOUTH_LAST : NOSE_LAST, iR = warp == R_RADM ? 93 : 95, iL = iR + 1;
+      const double e = Z.E(sec), g = e + Z.G(sec);
+      const double us = Z.r(sec);  // current into the radiating section carries the section's index
+      const double uR = (Z.r(iR) - k0 * us) * Z.d(iR);
+      Z.r(iR) = uR;
+      Z.r(iL) = (Z.r(iL) + e * us - g * uR) * Z.d(iL);
+      break;
+    }
+    default: break;
+  }
 }
 
 // ---- phase 4: update of the recurrent state ------------------------------------
@@ -845,11 +873,8 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
     // ======================= phase 3: solve (+ glottis, + output) =============
     {
       Solver Z{S, lane, cur, P.idt};
-      double oA = 0.0, e28 = 0.0, g28 = 0.0;
-      if (warp == 0) solve_trunk_forward(Z, oA, e28, g28);
-      else if (warp == 1) solve_mouth_forward(Z, oA);
-      else if (warp == 2) solve_nose_forward(Z, oA);
-      else if (warp == W_GLOTTIS) {
+      double k0 = 0.0, k1 = 0.0;
+      if (warp == W_GLOTTIS) {
         // incTime for this step (pressures of the previous step), then the geometry step n+1 will use
         double ctl[AFS_NUM_GLOTTIS_CONTROL], p[4], len[2], ar[2];
         GlottisState G{S.gx[0][lane], S.gx[1][lane], S.gx[2][lane], S.gx[3][lane]};
@@ -862,16 +887,20 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
         S.gx[0][lane] = G.x0; S.gx[1][lane] = G.x1; S.gx[2][lane] = G.xp0; S.gx[3][lane] = G.xp1;
         S.glLen[prev][0][lane] = len[0]; S.glLen[prev][1][lane] = len[1];
         S.glArea[prev][0][lane] = ar[0]; S.glArea[prev][1][lane] = ar[1];
-      } else if (warp == W_OUTPUT && n > 0) {
-        emit_output(P, S, lane, prev, n, active, tract, n_out, audio, flow, bad);
+      } else if (warp == W_OUTPUT) {
+        if (n > 0) emit_output(P, S, lane, prev, n, active, tract, n_out, audio, flow, bad);
+      } else {
+        solve_3a(Z, warp, k0, k1);
       }
       AFS_TICK(7);
       __syncthreads();
-      if (warp == 0) solve_velum_junction(Z);
+      solve_3b_forward(Z, warp);
       __syncthreads();
-      if (warp == 0) solve_trunk_back(Z, oA, e28, g28);
-      else if (warp == 1) solve_mouth_back(Z, oA);
-      else if (warp == 2) solve_nose_back(Z, oA);
+      if (warp == R_RED_T) solve_velum_junction(Z);
+      __syncthreads();
+      solve_3b_back(Z, warp);
+      __syncthreads();
+      solve_3c(Z, warp, k0);
     }
     __syncthreads();
     AFS_TICK(5);
