@@ -79,10 +79,11 @@ struct TdsSmem {
   double gctl[2][AFS_NUM_GLOTTIS_CONTROL][LANES];
   double glLen[2][2][LANES], glArea[2][2][LANES];  // glottis geometry, double buffered by step parity
   double p4[4][LANES];            // pressures of sections 22..25 after the last update
-  double side[9][3][LANES];       // solver: per-segment contributions to the left separator + new coupling (dd_a, dr_a, c_ab)
+  double side[7][3][LANES];       // solver: per-segment contributions to the left separator + new coupling (dd_a, dr_a, c_ab)
   double leaf[9][LANES];          // solver: fossa (dd28, dr28, dd29, dr29, o2829), mouth / nose radiation (dd, dr)
   double g3[3][LANES];            // G = L/(dt theta)+R of the dynamic branching sections 28, 40, 64
   double gx[4][LANES];            // glottis: x0, x1 (current), xp0, xp1 (previous) relative displacements
+  double gdim[10][LANES];         // glottis: cached dimensions for the current displacement (Q, length, th, ol, cl, mz)
   double toneX[4][LANES], toneY[4][LANES];   // skin-radiation filter history
   double chebX[8][LANES], chebY[8][LANES];   // output low-pass history
   double prevFlow[LANES];
@@ -357,8 +358,8 @@ struct Solver {
   __device__ __forceinline__ double &d(int i) { return S.diag[i][lane]; }
   __device__ __forceinline__ double &r(int i) { return S.sol[cur][i][lane]; }
   __device__ __forceinline__ double &H(int i) { return (&S.L[0])[i][lane]; }  // L,R,invr are contiguous: 138 >= 97 items
-  // side slot of a segment warp: warps 0,1,2 -> 0..2, 5..10 -> 3..8
-  __device__ __forceinline__ double &side(int w, int k) { return S.side[w < 3 ? w : w - 2][k][lane]; }
+  // side slot of a two-sided segment warp: warps 1,2 -> 0,1; 5..9 -> 2..6
+  __device__ __forceinline__ double &side(int w, int k) { return S.side[w < 3 ? w - 1 : w - 3][k][lane]; }
   __device__ __forceinline__ double &leaf(int k) { return S.leaf[k][lane]; }
   __device__ __forceinline__ double E(int s) const { return is_dyn(s) ? S.E[s - DYN0][lane] : S.cE[s]; }
   // G_s of the branching sections: static ones from the table, dynamic ones (28, 40, 64) published in phase 1
@@ -406,7 +407,7 @@ struct Solver {
       f = -t * f;
     }
     d(i) = dc; r(i) = rc;  // separator b, in place (only this warp touches it in 3a)
-    side(w_id, 0) = dda; side(w_id, 1) = dra; side(w_id, 2) = f;
+    if (a >= 0) { side(w_id, 0) = dda; side(w_id, 1) = dra; side(w_id, 2) = f; }
   }
   // 3c: u_i = G_i - H_i u_a - T_i u_next, walking back from b
   __device__ __forceinline__ void seg_back(int a, int first, int count, int dir) {
@@ -646,10 +647,10 @@ __device__ __forceinline__ void glottis_dims(const TdsParams &P, const double ct
   glottis_open_close(D.cordLength, ctl[G_REST2], g.x1, D.ol1, D.cl1, D.mw1, D.mz1);
 }
 // TriangularGlottis::incTime
+// `D` are the dimensions for the CURRENT displacement and control values: exactly what the geometry call of the
+// previous step computed (same inputs), so they are cached instead of recomputed.
 __device__ __forceinline__ void glottis_inc_time(const TdsParams &P, const double ctl[AFS_NUM_GLOTTIS_CONTROL],
-                                                 GlottisState &g, const double p[4]) {
-  GlottisDims D;
-  glottis_dims(P, ctl, g, D);
+                                                 GlottisState &g, const double p[4], const GlottisDims &D) {
   const double T = P.dt, Q = D.Q;
   const double iQ = fast_rcp(Q), iLen = fast_rcp(D.cordLength);
   const double m0 = P.gs[S_MASS1] * iQ, m1 = P.gs[S_MASS2] * iQ;
@@ -682,8 +683,7 @@ __device__ __forceinline__ void glottis_inc_time(const TdsParams &P, const doubl
 }
 // TriangularGlottis::calcGeometry + getTubeData -> the two glottal tube sections
 __device__ __forceinline__ void glottis_geometry(const TdsParams &P, const double ctl[AFS_NUM_GLOTTIS_CONTROL],
-                                                 const GlottisState &g, double len[2], double area[2]) {
-  GlottisDims D;
+                                                 const GlottisState &g, double len[2], double area[2], GlottisDims &D) {
   glottis_dims(P, ctl, g, D);
   double chink = ctl[G_ARY];
   if (chink < 0.0) chink = 0.0;
@@ -825,7 +825,11 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
         double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
         for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
         const GlottisState G{0.0, 0.0, 0.0, 0.0};
-        glottis_geometry(P, ctl, G, len, ar);
+        GlottisDims GD;
+        glottis_geometry(P, ctl, G, len, ar, GD);
+        S.gdim[0][lane] = GD.Q; S.gdim[1][lane] = GD.cordLength; S.gdim[2][lane] = GD.th0; S.gdim[3][lane] = GD.th1;
+        S.gdim[4][lane] = GD.ol0; S.gdim[5][lane] = GD.ol1; S.gdim[6][lane] = GD.cl0; S.gdim[7][lane] = GD.cl1;
+        S.gdim[8][lane] = GD.mz0; S.gdim[9][lane] = GD.mz1;
         S.glLen[0][0][lane] = len[0]; S.glLen[0][1][lane] = len[1];
         S.glArea[0][0][lane] = ar[0]; S.glArea[0][1][lane] = ar[1];
       }
@@ -880,10 +884,17 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
         GlottisState G{S.gx[0][lane], S.gx[1][lane], S.gx[2][lane], S.gx[3][lane]};
         for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = ratio1 * S.gctl[0][c][lane] + ratio * S.gctl[1][c][lane];
         for (int c = 0; c < 4; c++) p[c] = S.p4[c][lane];
-        glottis_inc_time(P, ctl, G, p);
+        GlottisDims GD;
+        GD.Q = S.gdim[0][lane]; GD.cordLength = S.gdim[1][lane]; GD.th0 = S.gdim[2][lane]; GD.th1 = S.gdim[3][lane];
+        GD.ol0 = S.gdim[4][lane]; GD.ol1 = S.gdim[5][lane]; GD.cl0 = S.gdim[6][lane]; GD.cl1 = S.gdim[7][lane];
+        GD.mz0 = S.gdim[8][lane]; GD.mz1 = S.gdim[9][lane]; GD.mw0 = 0.0; GD.mw1 = 0.0;
+        glottis_inc_time(P, ctl, G, p, GD);
         const double rn = (double)(n + 1 - i0) / (double)(i1 - i0), rn1 = 1.0 - rn;
         for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = rn1 * S.gctl[0][c][lane] + rn * S.gctl[1][c][lane];
-        glottis_geometry(P, ctl, G, len, ar);
+        glottis_geometry(P, ctl, G, len, ar, GD);
+        S.gdim[0][lane] = GD.Q; S.gdim[1][lane] = GD.cordLength; S.gdim[2][lane] = GD.th0; S.gdim[3][lane] = GD.th1;
+        S.gdim[4][lane] = GD.ol0; S.gdim[5][lane] = GD.ol1; S.gdim[6][lane] = GD.cl0; S.gdim[7][lane] = GD.cl1;
+        S.gdim[8][lane] = GD.mz0; S.gdim[9][lane] = GD.mz1;
         S.gx[0][lane] = G.x0; S.gx[1][lane] = G.x1; S.gx[2][lane] = G.xp0; S.gx[3][lane] = G.xp1;
         S.glLen[prev][0][lane] = len[0]; S.glLen[prev][1][lane] = len[1];
         S.glArea[prev][0][lane] = ar[0]; S.glArea[prev][1][lane] = ar[1];
