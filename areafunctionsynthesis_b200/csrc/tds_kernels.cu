@@ -14,28 +14,28 @@
 //   * one CTA = up to 32 independent tracts; LANE = TRACT everywhere, so every
 //     warp instruction does useful work for 32 tracts and all branches on the
 //     section type are warp-uniform (no divergence);
-//   * NWS "section warps" each own a fixed set of tube sections (3 dynamic + 3
-//     static) together with the branch current flowing INTO each owned section;
-//     the recurrent state (pressure, its rate, three wall-current terms, the
-//     current's rate) never leaves the owner's REGISTERS for the whole
-//     utterance;
-//   * everything that crosses sections (E, D, L, R, areas, matrix rows, the
-//     solution vector) is exchanged through SHARED MEMORY in [item][lane]
-//     layout (256 B per item: conflict-free);
-//   * the per-step 97x97 SPD system is a tree of 3-cliques; it is solved by
-//     zero-fill elimination from the leaves (three chains: trachea+pharynx,
-//     mouth, nose, worked concurrently by three warps, one tract per lane) and
-//     a 3x3 junction at the velum -- 104 off-diagonals instead of the
-//     reference's 313-entry envelope;
-//   * one extra warp runs the glottis model and the output filters;
+//   * 16 warps each own 3 "dynamic" slots (sections 23..68 whose geometry
+//     changes every sample, blocked 3 per warp, + sections 69 and 84 whose
+//     upstream neighbour is dynamic) and 3 static slots, together with the
+//     branch current flowing INTO each owned section; the recurrent state (p,
+//     p', three wall-current terms, the current's history term c) never leaves
+//     the owner's REGISTERS for the whole utterance;
+//   * everything that crosses sections (E, D, L, R, 1/r, alpha, matrix rows,
+//     the solution) is exchanged through SHARED MEMORY in [item][lane] layout
+//     (256 B per item: conflict-free); all per-slot addressing comes from a
+//     small uint16 offset table built once, so the phases are straight-line
+//     code with uniform-offset LDS/STS and no per-access index arithmetic;
+//   * per step: phase 2 rows -> phase 3 solve (parallel partition over 12
+//     warps + 3-warp reduced system) || glottis || output filters -> fused
+//     phase 4 (state update) + phase 1 of the next step (elements, E, D);
 //   * the two control frames of the current interval are staged in shared
-//     memory (area/length of the 40 pharynx-mouth sections, velum, glottis
-//     parameters); audio and flow are the only per-step HBM traffic (8-16 B
-//     per tract-step).
+//     memory; audio and flow are the only per-step HBM traffic.
 // FP64 throughout.  Algebraically simplified w.r.t. the reference (wall
-// admittance alpha = surface * const, no per-section divisions except 1/area
-// and E), FMA contraction on; parity gate 1e-6 relative max-abs on audio.
+// admittance alpha = surface * const, one rcp + one sqrt + one rcp per dynamic
+// section instead of ~15 div/sqrt, branch-free MUFU+Newton rcp/sqrt), FMA
+// contraction on; parity gate 1e-6 relative max-abs on audio.
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 
 #include "afs_internal.h"
@@ -43,14 +43,17 @@
 namespace afs {
 
 constexpr int LANES = 32;
-constexpr int NWS = 16;                       // section warps
-constexpr int TDS_THREADS = NWS * 32;         // glottis + output filters run on warps idle during the solve
-constexpr int W_GLOTTIS = 3, W_OUTPUT = 4;    // (warps 0..2 solve)
-constexpr int ND = 46;                        // dynamic sections 23..68
+constexpr int NWS = 16;                       // warps per CTA
+constexpr int TDS_THREADS = NWS * 32;
+constexpr int W_GLOTTIS = 3, W_OUTPUT = 4;    // warps that run the glottis / output filters during phase 3
+constexpr int ND = 46;                        // truly dynamic sections 23..68
 constexpr int DYN0 = 23, DYN_LAST = 68;
-constexpr int NSTAT = 47;
-constexpr int KD = (ND + NWS - 1) / NWS;      // dynamic slots per warp (3)
-constexpr int KS = (NSTAT + NWS - 1) / NWS;   // static slots per warp (3)
+constexpr int NDX = 49;                       // per-lane exchange records: 0..45 sections 23..68, 46 = 69, 47 = 84, 48 = copy of 22
+constexpr int DX_69 = 46, DX_84 = 47, DX_22 = 48;
+constexpr int KD = 3, KS = 3;                 // dynamic / static slots per warp
+constexpr int NSTAT = 45;                     // sections owned by static slots (all but 23..69 and 84)
+constexpr int NCX = NC + 1;                   // + one always-zero dummy current (index 97)
+constexpr int NSX = NS + 1;                   // + one all-zero dummy section (index 93): "no source section"
 constexpr double kTheta = 0.515;              // TdsModel.cpp:15
 constexpr double kTheta1 = 1.0 - kTheta;
 
@@ -66,44 +69,69 @@ struct TdsParams {
   double gs[AFS_NUM_GLOTTIS_STATIC];
 };
 
+// Static section record (same for all tracts).  R1 = resistance seen by the out-flowing current, R0 by the
+// in-flowing one (they differ only for the decoupled piriform fossa entrance, TdsModel.cpp:883-889).
+struct SRec { double E, L, R1, invr, alpha, R0; };
+
+// Per (warp, slot) byte offsets, built once in the prologue.  All offsets are relative to array bases and fit 16 bits.
+struct SlotTab {
+  uint16_t sec256;   // section (= in-flowing current) index * 256: D[], diag[], sol[]
+  uint16_t own;      // dynamic slots: record index * 256 into E/L/R/invr/alpha; static slots: section * sizeof(SRec)
+  uint16_t aRec;     // source section A: dynamic slots -> record index * 256; static slots -> section * sizeof(SRec)
+  uint16_t aD256;    // A * 256 into D[] (dummy section 93 = zero when there is no source section)
+  uint16_t out0, out1;      // out-flowing currents * 256 into sol[] (dummy current 97 = zero)
+  uint16_t urbOwn, urbSib;  // slots * 256 in urb[]: where to publish the own history term / read the sibling's
+  uint16_t p4off;    // slot * 256 in p4[] (4 = sink)
+  uint16_t wall;     // wall-constant set * 24 in wallc[] (3 = no walls: glottis)
+  uint16_t flags;
+  uint16_t pad;
+};
+enum { FL_JUNCTION = 1, FL_GLO = 2, FL_GUP = 4, FL_ROW0 = 8, FL_VALID = 16, FL_G3 = 32 };
+
 // ---- shared memory layout ---------------------------------------------------
 struct TdsSmem {
   // per-tract exchange, [item][lane]
-  double D[NS][LANES];
-  double E[ND][LANES], L[ND][LANES], R[ND][LANES], invr[ND][LANES], alpha[ND][LANES];  // invr = 1/sqrt(area/pi)
+  double D[NSX][LANES];
+  double E[NDX][LANES];
+  double L[NDX][LANES], R[NDX][LANES], invr[NDX][LANES];  // contiguous: reused as solver scratch in phase 3
+  double alpha[NDX][LANES];
   double diag[NC][LANES];
-  double sol[2][NC][LANES];
-  double urb[16][LANES];          // current rates of the 16 sibling (branch / radiation) currents
+  double sol[2][NCX][LANES];
+  double urb[18][LANES];          // history terms c of the 16 sibling (branch / radiation) currents, 16 = sink, 17 = zero
   double fA[2][AFS_NUM_PM_SECTIONS][LANES], fLen[2][AFS_NUM_PM_SECTIONS][LANES];  // control frames of the interval
   double velum[2][LANES];
   double gctl[2][AFS_NUM_GLOTTIS_CONTROL][LANES];
   double glLen[2][2][LANES], glArea[2][2][LANES];  // glottis geometry, double buffered by step parity
-  double p4[4][LANES];            // pressures of sections 22..25 after the last update
-  double side[7][3][LANES];       // solver: per-segment contributions to the left separator + new coupling (dd_a, dr_a, c_ab)
-  double leaf[9][LANES];          // solver: fossa (dd28, dr28, dd29, dr29, o2829), mouth / nose radiation (dd, dr)
+  double p4[5][LANES];            // pressures of sections 22..25 after the last update, 4 = sink
   double g3[3][LANES];            // G = L/(dt theta)+R of the dynamic branching sections 28, 40, 64
   double gx[4][LANES];            // glottis: x0, x1 (current), xp0, xp1 (previous) relative displacements
-  double gdim[10][LANES];         // glottis: cached dimensions for the current displacement (Q, length, th, ol, cl, mz)
+  double gdim[10][LANES];         // glottis: cached dimensions for the current displacement
   double toneX[4][LANES], toneY[4][LANES];   // skin-radiation filter history
   double chebX[8][LANES], chebY[8][LANES];   // output low-pass history
   double prevFlow[LANES];
-  // static sections (same for all tracts)
-  double cE[NS], cL[NS], cR[NS], cAlpha[NS], cInvr[NS];
+  // same for all tracts
+  SRec srec[NSX];
+  double wallc[4][3];             // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = zeros
+  SlotTab slot[NWS][KD + KS];
 };
 
-__device__ __forceinline__ int static_section_of(int t) {  // t = 0..46
-  return t < 23 ? t : t < 38 ? 69 + (t - 23) : t < 43 ? FOSSA0 + (t - 38) : SINUS0 + (t - 43);
-}
 __device__ __forceinline__ int wall_type(int s) { return s <= TRACHEA_LAST ? 1 : s >= SINUS0 ? 2 : 0; }
 __device__ __forceinline__ bool is_dyn(int s) { return s >= DYN0 && s <= DYN_LAST; }
-// source section of current i (TdsModel.cpp:93-131)
+// section owned by dynamic slot index dx = 3*warp + k / static slot index t = 3*warp + k (t < 45)
+__device__ __forceinline__ int dyn_slot_section(int dx) { return dx < ND ? DYN0 + dx : dx == DX_69 ? 69 : FOSSA0; }
+__device__ __forceinline__ int stat_slot_section(int t) {
+  return t < 23 ? t : t < 37 ? 70 + (t - 23) : t < 41 ? 85 + (t - 37) : SINUS0 + (t - 41);
+}
+// record index of a section in the per-lane exchange arrays (-1: none)
+__device__ __forceinline__ int dyn_record_of(int s) {
+  return is_dyn(s) ? s - DYN0 : s == 69 ? DX_69 : s == FOSSA0 ? DX_84 : s == TRACHEA_LAST ? DX_22 : -1;
+}
+// source section of current i (TdsModel.cpp:93-131); 93 (dummy) for the current out of the lungs
 __device__ __forceinline__ int src_of(int i) {
-  if (i == 0) return -1;
+  if (i == 0) return NS;
   if (i == NOSE0) return PHAR_LAST;
   if (i == FOSSA0) return PHAR0 + FOSSA_COUPLING;
   if (i >= SINUS0 && i <= SINUS_LAST) return i == 89 ? 73 : i == 90 ? 74 : i == 91 ? 76 : 77;
-  if (i == 93 || i == 94) return MOUTH_LAST;
-  if (i == 95 || i == 96) return NOSE_LAST;
   return i - 1;
 }
 // sibling current at a branching source section, -1 if none
@@ -118,7 +146,7 @@ __device__ __forceinline__ int sibling_of(int i) {
     default: return -1;
   }
 }
-// slot in the small sibling-rate table
+// slot in the small sibling table urb[]
 __device__ __forceinline__ int urb_slot(int i) {
   switch (i) {
     case 29: return 0; case 84: return 1; case 41: return 2; case 65: return 3;
@@ -128,29 +156,26 @@ __device__ __forceinline__ int urb_slot(int i) {
     default: return -1;
   }
 }
-
-struct SecAccess {
-  TdsSmem &S;
-  int lane;
-  __device__ __forceinline__ double E(int s) const { return is_dyn(s) ? S.E[s - DYN0][lane] : S.cE[s]; }
-  __device__ __forceinline__ double L(int s) const { return is_dyn(s) ? S.L[s - DYN0][lane] : S.cL[s]; }
-  __device__ __forceinline__ double R(int s) const { return is_dyn(s) ? S.R[s - DYN0][lane] : S.cR[s]; }
-  __device__ __forceinline__ double alpha(int s) const { return is_dyn(s) ? S.alpha[s - DYN0][lane] : S.cAlpha[s]; }
-  __device__ __forceinline__ double invr(int s) const { return is_dyn(s) ? S.invr[s - DYN0][lane] : S.cInvr[s]; }
-  // 1/area from the published 1/radius (areas are only ever needed as reciprocals or compared)
-  __device__ __forceinline__ double inva(int s) const { const double q = invr(s); return q * q * (1.0 / kPi); }
-};
+// out-flowing currents of a section (dummy 97 where there is none)
+__device__ __forceinline__ void outs_of(int s, int &o0, int &o1) {
+  o0 = s + 1; o1 = NC;
+  if (s == 28) o1 = 84;
+  else if (s == 40) o1 = 65;
+  else if (s == 64) { o0 = 93; o1 = 94; }
+  else if (s == 83) { o0 = 95; o1 = 96; }
+  else if (s == 73) o1 = 89;
+  else if (s == 74) o1 = 90;
+  else if (s == 76) o1 = 91;
+  else if (s == 77) o1 = 92;
+  else if (s == FOSSA_LAST || s >= SINUS0) o0 = NC;
+}
 
 // Recurrent state of one owned section + its in-flowing current (registers).
+// c = u/(dt theta) + (theta1/theta) u' is all that the next step needs of the current's history:
+// H = -L c (TdsModel.cpp:2020) and u'_new = u_new/(dt theta) - c (TdsModel.cpp:2070).
 struct SecState {
-  double p, pr, wc, wcr, wcr2, ur;
+  double p, pr, wc, wcr, wcr2, c;
 };
-
-// beta of TdsModel.cpp:826-831 with Lw = Mw/surface, Rw = Bw/surface folded:
-// beta = kalpha * (wc*c1 + wcr*c2 + wcr2*c3), independent of the geometry.
-__device__ __forceinline__ double wall_beta(const TdsParams &P, int wt, const SecState &st) {
-  return P.kalpha[wt] * (st.wc * P.c1[wt] + st.wcr * P.c2[wt] + st.wcr2 * P.c3[wt]);
-}
 
 // ---- fast FP64 reciprocal / sqrt (branch-free) -----------------------------------
 // IEEE division / sqrt compile to ~20-instruction sequences with a slow-path CALL that fences the
@@ -205,82 +230,105 @@ __device__ __forceinline__ void section_elements(double area, double length, boo
   }
 }
 
-// ---- phase 1: per-section elements, E and D ----------------------------------
-__device__ __forceinline__ void phase1_dynamic(const TdsParams &P, TdsSmem &S, int lane, int s, const SecState &st,
-                                               double ratio, double ratio1, int parity) {
-  double area, length;
-  const int d = s - DYN0;
-  if (s >= PHAR0 && s <= MOUTH_LAST) {  // Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350)
-    const int j = s - PHAR0;
-    area = ratio1 * S.fA[0][j][lane] + ratio * S.fA[1][j][lane];
-    length = ratio1 * S.fLen[0][j][lane] + ratio * S.fLen[1][j][lane];
-  } else if (s < PHAR0) {  // glottis sections from the glottis model (Synthesizer.cpp:576-579)
-    area = S.glArea[parity][s - GLOT_LO][lane];
-    length = S.glLen[parity][s - GLOT_LO][lane];
-  } else {  // velum port: Tube::setVelumOpening (Tube.cpp:402-416)
-    const int j = s - NOSE0;
-    const double v = ratio1 * S.velum[0][lane] + ratio * S.velum[1][lane];
-    area = v + ((double)(j * j) * (4.24 - v)) / 16.0;
-    length = (11.4 / 11.4) * 0.6;
-  }
-  if (area < kMinArea) area = kMinArea;
-  const double volume = area * length;
-  double L, R, invr, circ;
-  const bool glottal = s < PHAR0;
-  section_elements(area, length, glottal, L, R, invr, circ);
-  const double C = volume * (1.0 / (kRho * kC * kC));
-  double alpha = 0.0, beta = 0.0;
-  if (P.soft_walls && !glottal) {  // TdsModel.cpp:805-832
-    double surface = circ * length;
-    if (surface < kMinArea) surface = kMinArea;
-    alpha = surface * P.kalpha[0];
-    beta = wall_beta(P, 0, st);
-  }
-  const double E = P.dtth * fast_rcp(C + alpha);
-  const double D = st.p + P.dtth1 * st.pr - E * beta;  // no monopole / flow source (TdsModel.cpp:988-1008)
-  S.E[d][lane] = E; S.L[d][lane] = L; S.R[d][lane] = R; S.invr[d][lane] = invr;
-  S.alpha[d][lane] = alpha;
-  S.D[s][lane] = D;
-  if (s == 28 || s == 40 || s == 64) S.g3[s == 28 ? 0 : s == 40 ? 1 : 2][lane] = L * P.idt + R;
+
+// raw shared-memory access with byte offsets
+__device__ __forceinline__ double lds(const char *base, int off) { return *reinterpret_cast<const double *>(base + off); }
+__device__ __forceinline__ void sts(char *base, int off, double v) { *reinterpret_cast<double *>(base + off) = v; }
+#define OFF(member) ((int)offsetof(TdsSmem, member))
+constexpr int ITEM = LANES * 8;  // bytes per [item] row
+
+// beta of TdsModel.cpp:826-831 with Lw = Mw/surface, Rw = Bw/surface folded in:
+// beta = kalpha*(c1 wc + c2 wc' + c3 wc''), independent of the geometry.  w points at {kalpha c1, kalpha c2, kalpha c3}.
+__device__ __forceinline__ double wall_beta(const char *sm, int wallOff, const SecState &st) {
+  const double *w = reinterpret_cast<const double *>(sm + OFF(wallc) + wallOff);
+  return fma(st.wc, w[0], fma(st.wcr, w[1], st.wcr2 * w[2]));
 }
 
-__device__ __forceinline__ void phase1_static(const TdsParams &P, TdsSmem &S, int lane, int s, const SecState &st) {
-  const double beta = P.soft_walls ? wall_beta(P, wall_type(s), st) : 0.0;
-  S.D[s][lane] = st.p + P.dtth1 * st.pr - S.cE[s] * beta;
+// ---- phase 1: per-section elements, E and D ----------------------------------
+// Dynamic slot dx (uniform).  lane8 = lane*8.
+__device__ __forceinline__ void phase1_dyn(const TdsParams &P, char *sm, int lane8, int dx, const SlotTab &T,
+                                           const SecState &st, double ratio, double ratio1, int parity) {
+  double E;
+  const int own = T.own + lane8;
+  const double beta = wall_beta(sm, T.wall, st);
+  if (dx < ND) {
+    double area, length;
+    if (dx >= 2 && dx < 42) {  // pharynx / mouth: Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350)
+      const int j = (dx - 2) * ITEM + lane8;
+      area = ratio1 * lds(sm, OFF(fA[0]) + j) + ratio * lds(sm, OFF(fA[1]) + j);
+      length = ratio1 * lds(sm, OFF(fLen[0]) + j) + ratio * lds(sm, OFF(fLen[1]) + j);
+    } else if (dx < 2) {  // glottis sections from the glottis model (Synthesizer.cpp:576-579)
+      area = lds(sm, OFF(glArea) + (parity * 2 + dx) * ITEM + lane8);
+      length = lds(sm, OFF(glLen) + (parity * 2 + dx) * ITEM + lane8);
+    } else {  // velum port: Tube::setVelumOpening (Tube.cpp:402-416)
+      const int j = dx - 42;
+      const double v = ratio1 * lds(sm, OFF(velum[0]) + lane8) + ratio * lds(sm, OFF(velum[1]) + lane8);
+      area = v + ((double)(j * j) * (4.24 - v)) / 16.0;
+      length = (11.4 / 11.4) * 0.6;
+    }
+    if (area < kMinArea) area = kMinArea;
+    const double volume = area * length;
+    double L, R, invr, circ;
+    const bool glottal = dx < 2;
+    section_elements(area, length, glottal, L, R, invr, circ);
+    const double C = volume * (1.0 / (kRho * kC * kC));
+    double alpha = 0.0;
+    if (P.soft_walls && !glottal) {  // TdsModel.cpp:805-832
+      double surface = circ * length;
+      if (surface < kMinArea) surface = kMinArea;
+      alpha = surface * P.kalpha[0];
+    }
+    E = P.dtth * fast_rcp(C + alpha);
+    sts(sm, OFF(E) + own, E); sts(sm, OFF(L) + own, L); sts(sm, OFF(R) + own, R); sts(sm, OFF(invr) + own, invr);
+    sts(sm, OFF(alpha) + own, alpha);
+    if (T.flags & FL_G3) sts(sm, OFF(g3) + (dx == 5 ? 0 : dx == 17 ? 1 : 2) * ITEM + lane8, L * P.idt + R);
+  } else {  // sections 69 and 84: static geometry; E/alpha copies are permanent, but L, R, 1/r live in the arrays the
+            // solver reuses as scratch, so they are refreshed every step
+    E = lds(sm, OFF(E) + own);
+    const SRec *r = reinterpret_cast<const SRec *>(sm + OFF(srec) + (dx == DX_69 ? 69 : FOSSA0) * (int)sizeof(SRec));
+    sts(sm, OFF(L) + own, r->L); sts(sm, OFF(R) + own, dx == DX_84 ? r->R0 : r->R1); sts(sm, OFF(invr) + own, r->invr);
+  }
+  if (dx == 0) {  // per-lane copy of static section 22, the source section of row 23 (same reason)
+    const SRec *r = reinterpret_cast<const SRec *>(sm + OFF(srec) + TRACHEA_LAST * (int)sizeof(SRec));
+    const int o = DX_22 * ITEM + lane8;
+    sts(sm, OFF(L) + o, r->L); sts(sm, OFF(R) + o, r->R1); sts(sm, OFF(invr) + o, r->invr);
+  }
+  sts(sm, OFF(D) + T.sec256 + lane8, st.p + P.dtth1 * st.pr - E * beta);  // TdsModel.cpp:988-1008, no flow sources
+}
+
+__device__ __forceinline__ void phase1_stat(const TdsParams &P, char *sm, int lane8, const SlotTab &T, const SecState &st) {
+  const double beta = wall_beta(sm, T.wall, st);
+  const double E = lds(sm, OFF(srec) + T.own);
+  sts(sm, OFF(D) + T.sec256 + lane8, st.p + P.dtth1 * st.pr - E * beta);
 }
 
 // ---- phase 2: one matrix row (negated: SPD) per owned current -----------------
-// Row of current i flowing into section B = i (TdsModel.cpp:1916-2034).
-__device__ __forceinline__ void phase2_row(const TdsParams &P, TdsSmem &S, const SecAccess &X, int lane, int i,
-                                           const SecState &st, int prev, int cur, double psrc, double &gbf) {
-  const int B = i, A = src_of(i);
-  const double uB = S.sol[prev][i][lane], urB = st.ur;
-  const double E_B = X.E(B), D_B = S.D[B][lane], L_B = X.L(B);
-  double R_B = X.R(B);
-  if (B == FOSSA0 && !P.fossa)  // TdsModel.cpp:883-889
-    R_B = 8.0 * kMu * (3.0 / 5.0) * kPi / (kMinArea * kMinArea);
-  double diag, rhs;
-  if (A < 0) {  // current 0: from the lung pressure source into the first trachea section
-    const double L_AB = L_B, R_AB = R_B;
-    const double G = L_AB * P.idt + R_AB;
-    const double H = -urB * L_AB * P.th - (L_AB * uB) * P.idt - psrc;
-    diag = E_B + G;
-    rhs = -(H + D_B);
+// Row of the current flowing from section A into the owned section B (TdsModel.cpp:1916-2034):
+//   diag = E_B + E_A + L_AB/(dt theta) + R_AB,   rhs = L_AB c + L_A c_sibling + [p_lung] - D_B + D_A
+// with c the history term of SecState.  The same formula covers plain, bifurcation and "no source section" rows
+// (dummy zero records); junction inductance / Bernoulli and the glottal losses are added under uniform flags.
+template <bool DYN>
+__device__ __forceinline__ void phase2_row(const TdsParams &P, char *sm, int lane8, const SlotTab &T, const SecState &st,
+                                           int prevOff, int curOff, double psrc, double &gbf) {
+  double E_B, L_B, R_B, E_A, L_A, R_A, ia = 0.0, ib = 0.0;
+  if (DYN) {
+    const int own = T.own + lane8, a = T.aRec + lane8;
+    E_B = lds(sm, OFF(E) + own); L_B = lds(sm, OFF(L) + own); R_B = lds(sm, OFF(R) + own); ib = lds(sm, OFF(invr) + own);
+    E_A = lds(sm, OFF(E) + a); L_A = lds(sm, OFF(L) + a); R_A = lds(sm, OFF(R) + a); ia = lds(sm, OFF(invr) + a);
   } else {
-    const double E_A = X.E(A), D_A = S.D[A][lane], L_A = X.L(A);
-    double R_A = X.R(A);
-    const int sib = sibling_of(i);
-    if (sib >= 0) {  // bifurcation (TdsModel.cpp:1961-1993)
-      const double uD = S.sol[prev][sib][lane], urD = S.urb[urb_slot(sib)][lane];
-      const double L_AB = L_A + L_B, R_AB = R_A + R_B;
-      const double F = L_AB * P.idt + R_AB;
-      const double H = -P.idt * (L_AB * uB + L_A * uD) - P.th * (L_AB * urB + L_A * urD);
-      diag = E_B + E_A + F;
-      rhs = -(H + D_B - D_A);
-    } else {
-      double L_AB = L_A + L_B;
-      if (i > PHAR0 && i <= MOUTH_LAST) {  // junctions inside pharynx+mouth (A >= 25, B <= 64)
-        const double ia = X.invr(A), ib = X.invr(B);
+    const SRec *b = reinterpret_cast<const SRec *>(sm + OFF(srec) + T.own);
+    const SRec *a = reinterpret_cast<const SRec *>(sm + OFF(srec) + T.aRec);
+    E_B = b->E; L_B = b->L; R_B = b->R0;
+    E_A = a->E; L_A = a->L; R_A = a->R1;
+  }
+  const double D_B = lds(sm, OFF(D) + T.sec256 + lane8), D_A = lds(sm, OFF(D) + T.aD256 + lane8);
+  const double c_sib = lds(sm, OFF(urb) + T.urbSib + lane8);
+  double L_AB = L_A + L_B;
+  if (DYN) {
+    const int fl = T.flags;
+    if (fl & (FL_JUNCTION | FL_GLO | FL_GUP)) {
+      const double uB = lds(sm, OFF(sol) + prevOff + T.sec256 + lane8);
+      if (fl & FL_JUNCTION) {
         if (P.ilc) L_AB += (8.0 * kRho / (3.0 * kPi * kPi)) * fabs(ia - ib);  // Sondhi (TdsModel.cpp:1745-1778)
         if (P.turbulence) {  // Bernoulli loss wide -> narrow (TdsModel.cpp:850-877); area_B < area_A <=> ib > ia
           if (((ib > ia) && (uB > 0)) || ((ib < ia) && (uB < 0))) {
@@ -289,51 +337,68 @@ __device__ __forceinline__ void phase2_row(const TdsParams &P, TdsSmem &S, const
             R_B += uB * (0.5 * kRho) * (qb * qb);
           }
         }
-      } else if (i == GLOT_LO) {  // glottal entrance loss (TdsModel.cpp:900-920)
+      } else if (fl & FL_GLO) {  // glottal entrance loss (TdsModel.cpp:900-920)
         if (uB > 0) {
-          const double qT = X.inva(B), qS = X.inva(A);
+          const double qT = ib * ib * (1.0 / kPi), qS = ia * ia * (1.0 / kPi);
           R_B += P.k_ent * 0.5 * kRho * fabs(uB) * (qT * qT - qS * qS);
         }
-      } else if (i == GLOT_UP) {  // lower -> upper glottis section (TdsModel.cpp:930-950)
-        const double qS = X.inva(A), qT = X.inva(B);
+      } else {  // lower -> upper glottis section (TdsModel.cpp:930-950)
+        const double qS = ia * ia * (1.0 / kPi), qT = ib * ib * (1.0 / kPi);
         const double target = (qT * P.fsar > qS) ? 1.0 : 0.0;  // area_T < fsar * area_S
         gbf = 0.8 * gbf + (1.0 - 0.8) * target;
         if (uB > 0) R_A += gbf * fabs(uB) * 0.5 * kRho * (qT * qT - qS * qS);
       }
-      const double R_AB = R_A + R_B;
-      const double G = L_AB * P.idt + R_AB;
-      const double H = -urB * L_AB * P.th - (L_AB * uB) * P.idt;
-      diag = E_B + G + E_A;
-      rhs = -(H + D_B - D_A);
     }
   }
-  S.diag[i][lane] = diag;
-  S.sol[cur][i][lane] = rhs;
+  const double diag = E_B + E_A + fma(L_AB, P.idt, R_A + R_B);
+  double rhs = fma(L_AB, st.c, fma(L_A, c_sib, D_A - D_B));
+  if (!DYN) { if (T.flags & FL_ROW0) rhs += psrc; }
+  sts(sm, OFF(diag) + T.sec256 + lane8, diag);
+  sts(sm, OFF(sol) + curOff + T.sec256 + lane8, rhs);
 }
 
 // Rows of the two parallel radiation currents out of section A (TdsModel.cpp:1841-1911):
 // iR through the radiation resistance, iL = iR + 1 through the radiation inductance.
-__device__ __forceinline__ void phase2_radiation(const TdsParams &P, TdsSmem &S, const SecAccess &X, int lane, int A,
-                                                 int iR, double urR, double urL, int prev, int cur) {
+__device__ __forceinline__ void phase2_radiation(const TdsParams &P, TdsSmem &S, int lane, int A, int iR, double cR,
+                                                 double cL, int cur) {
   const int iL = iR + 1;
-  const double uR = S.sol[prev][iR][lane], uL = S.sol[prev][iL][lane];
-  const double E_A = X.E(A), D_A = S.D[A][lane], L_A = X.L(A), R_A = X.R(A);
-  const double invr = X.invr(A);
+  double E_A, L_A, R_A, invr;
+  if (A == MOUTH_LAST) { const int d = MOUTH_LAST - DYN0; E_A = S.E[d][lane]; L_A = S.L[d][lane]; R_A = S.R[d][lane]; invr = S.invr[d][lane]; }
+  else { E_A = S.srec[A].E; L_A = S.srec[A].L; R_A = S.srec[A].R1; invr = S.srec[A].invr; }
+  const double D_A = S.D[A][lane];
   const double R_rad = (128.0 * kRho * kC / (9.0 * kPi * kPi)) * (invr * invr * (1.0 / kPi));
   const double L_rad = (8.0 * kRho / (3.0 * kPi * kPi)) * invr;
-  {
-    const double F = L_A * P.idt + R_A + R_rad;
-    const double H = -(L_A * P.idt) * (uR + uL) - (L_A * P.th) * (urR + urL);
-    S.diag[iR][lane] = E_A + F;
-    S.sol[cur][iR][lane] = -(H - D_A);
-  }
-  {
-    const double L_AB = L_A + L_rad;
-    const double G = L_AB * P.idt + R_A;
-    const double H = -P.idt * (L_A * uR + L_AB * uL) - P.th * (L_A * urR + L_AB * urL);
-    S.diag[iL][lane] = E_A + G;
-    S.sol[cur][iL][lane] = -(H - D_A);
-  }
+  const double L_AB = L_A + L_rad;
+  S.diag[iR][lane] = E_A + L_A * P.idt + R_A + R_rad;
+  S.sol[cur][iR][lane] = L_A * (cR + cL) + D_A;
+  S.diag[iL][lane] = E_A + L_AB * P.idt + R_A;
+  S.sol[cur][iL][lane] = fma(L_A, cR, L_AB * cL) + D_A;
+}
+
+// ---- phase 4: update of the recurrent state (TdsModel.cpp:2046-2098) -------------
+template <bool DYN>
+__device__ __forceinline__ void phase4_update(const TdsParams &P, char *sm, int lane8, const SlotTab &T, SecState &st,
+                                              int curOff) {
+  const int solc = OFF(sol) + curOff + lane8;
+  const double u_new = lds(sm, solc + T.sec256);
+  const double out = lds(sm, solc + T.out0) + lds(sm, solc + T.out1);
+  double E, alpha;
+  if (DYN) { E = lds(sm, OFF(E) + T.own + lane8); alpha = lds(sm, OFF(alpha) + T.own + lane8); }
+  else { const SRec *b = reinterpret_cast<const SRec *>(sm + OFF(srec) + T.own); E = b->E; alpha = b->alpha; }
+  const double D = lds(sm, OFF(D) + T.sec256 + lane8);
+  const double beta = wall_beta(sm, T.wall, st);
+  // current: u' = (u_new - u_old)/(dt theta) - (theta1/theta) u'_old = u_new/(dt theta) - c
+  const double ur_new = fma(u_new, P.idt, -st.c);
+  st.c = fma(ur_new, P.th, u_new * P.idt);
+  sts(sm, OFF(urb) + T.urbOwn + lane8, st.c);
+  // section
+  const double p_new = fma(E, u_new - out, D);
+  const double pr_new = (p_new - st.p) * P.idt - st.pr * P.th;
+  const double wc_new = fma(pr_new, alpha, beta);
+  const double wcr_new = (wc_new - st.wc) * P.idt - st.wcr * P.th;
+  const double wcr2_new = (wcr_new - st.wcr) * P.idt - st.wcr2 * P.th;
+  st.p = p_new; st.pr = pr_new; st.wc = wc_new; st.wcr = wcr_new; st.wcr2 = wcr2_new;
+  sts(sm, OFF(p4) + T.p4off + lane8, p_new);
 }
 
 // ---- phase 3: the linear solve (parallel partition) ------------------------------
@@ -357,14 +422,16 @@ struct Solver {
   double idt;
   __device__ __forceinline__ double &d(int i) { return S.diag[i][lane]; }
   __device__ __forceinline__ double &r(int i) { return S.sol[cur][i][lane]; }
-  __device__ __forceinline__ double &H(int i) { return (&S.L[0])[i][lane]; }  // L,R,invr are contiguous: 138 >= 97 items
+  // scratch aliased on the L/R/invr exchange arrays (3*NDX = 147 contiguous items, dead between phase 2 and
+  // the next phase 1): items 0..96 = H per node, 100..120 = side slots, 124..132 = leaf slots
+  __device__ __forceinline__ double &H(int i) { return (&S.L[0])[i][lane]; }
   // side slot of a two-sided segment warp: warps 1,2 -> 0,1; 5..9 -> 2..6
-  __device__ __forceinline__ double &side(int w, int k) { return S.side[w < 3 ? w - 1 : w - 3][k][lane]; }
-  __device__ __forceinline__ double &leaf(int k) { return S.leaf[k][lane]; }
-  __device__ __forceinline__ double E(int s) const { return is_dyn(s) ? S.E[s - DYN0][lane] : S.cE[s]; }
+  __device__ __forceinline__ double &side(int w, int k) { return (&S.L[0])[100 + 3 * (w < 3 ? w - 1 : w - 3) + k][lane]; }
+  __device__ __forceinline__ double &leaf(int k) { return (&S.L[0])[124 + k][lane]; }
+  __device__ __forceinline__ double E(int s) const { return is_dyn(s) ? S.E[s - DYN0][lane] : S.srec[s].E; }
   // G_s of the branching sections: static ones from the table, dynamic ones (28, 40, 64) published in phase 1
   __device__ __forceinline__ double G(int s) const {
-    return s == 28 ? S.g3[0][lane] : s == 40 ? S.g3[1][lane] : s == 64 ? S.g3[2][lane] : S.cL[s] * idt + S.cR[s];
+    return s == 28 ? S.g3[0][lane] : s == 40 ? S.g3[1][lane] : s == 64 ? S.g3[2][lane] : S.srec[s].L * idt + S.srec[s].R1;
   }
 
   // Eliminate leaf current c (second out of branching section s) into its clique partners a (in-current of s)
@@ -568,37 +635,6 @@ __device__ __forceinline__ void solve_3c(Solver &Z, int warp, double k0) {
   }
 }
 
-// ---- phase 4: update of the recurrent state ------------------------------------
-__device__ __forceinline__ void phase4_update(const TdsParams &P, TdsSmem &S, const SecAccess &X, int lane, int s,
-                                              SecState &st, int prev, int cur) {
-  // current s (TdsModel.cpp:2063-2072)
-  const double u_new = S.sol[cur][s][lane], u_old = S.sol[prev][s][lane];
-  st.ur = (u_new - u_old) * P.idt - P.th * st.ur;
-  const int us = urb_slot(s);
-  if (us >= 0) S.urb[us][lane] = st.ur;
-  // section s (TdsModel.cpp:2078-2096)
-  double out = 0.0;
-  if (s == 28) out = S.sol[cur][29][lane] + S.sol[cur][84][lane];
-  else if (s == 40) out = S.sol[cur][41][lane] + S.sol[cur][65][lane];
-  else if (s == 64) out = S.sol[cur][93][lane] + S.sol[cur][94][lane];
-  else if (s == 83) out = S.sol[cur][95][lane] + S.sol[cur][96][lane];
-  else if (s == 73 || s == 74 || s == 76 || s == 77)
-    out = S.sol[cur][s + 1][lane] + S.sol[cur][s == 73 ? 89 : s == 74 ? 90 : s == 76 ? 91 : 92][lane];
-  else if (s == FOSSA_LAST || s >= SINUS0) out = 0.0;
-  else out = S.sol[cur][s + 1][lane];
-  const double net = u_new - out;
-  const double alpha = X.alpha(s);
-  const bool walls = P.soft_walls && s != GLOT_LO && s != GLOT_UP;
-  const double beta = walls ? wall_beta(P, is_dyn(s) ? 0 : wall_type(s), st) : 0.0;
-  const double p_new = S.D[s][lane] + X.E(s) * net;
-  const double pr_new = (p_new - st.p) * P.idt - st.pr * P.th;
-  const double wc_new = pr_new * alpha + beta;
-  const double wcr_new = (wc_new - st.wc) * P.idt - st.wcr * P.th;
-  const double wcr2_new = (wcr_new - st.wcr) * P.idt - st.wcr2 * P.th;
-  st.p = p_new; st.pr = pr_new; st.wc = wc_new; st.wcr = wcr_new; st.wcr2 = wcr2_new;
-  if (s >= TRACHEA_LAST && s <= PHAR0) S.p4[s - TRACHEA_LAST][lane] = p_new;
-}
-
 // ---- glottis (TriangularGlottis.cpp:154-576) -----------------------------------
 struct GlottisState {
   double x0, x1;    // current relative displacements (lower, upper)
@@ -732,24 +768,61 @@ __device__ __forceinline__ void emit_output(const TdsParams &P, TdsSmem &S, int 
   }
 }
 
+
+// Slot table entry for dynamic (isDyn) slot index q = 3*warp + k, or static slot index q.
+__device__ void build_slot(const TdsParams &P, bool isDyn, int q, SlotTab &T) {
+  T = SlotTab{};
+  const bool valid = isDyn ? true : q < NSTAT;
+  const int s = isDyn ? dyn_slot_section(q) : (valid ? stat_slot_section(q) : NS);
+  const int A = valid ? src_of(s) : NS;
+  int o0, o1;
+  outs_of(valid ? s : FOSSA_LAST, o0, o1);
+  const int sib = valid ? sibling_of(s) : -1;
+  T.sec256 = (uint16_t)(s * ITEM);
+  T.aD256 = (uint16_t)(A * ITEM);
+  T.out0 = (uint16_t)(o0 * ITEM); T.out1 = (uint16_t)(o1 * ITEM);
+  T.urbOwn = (uint16_t)((urb_slot(s) >= 0 && valid ? urb_slot(s) : 16) * ITEM);
+  T.urbSib = (uint16_t)((sib >= 0 ? urb_slot(sib) : 17) * ITEM);
+  T.p4off = (uint16_t)((valid && s >= TRACHEA_LAST && s <= PHAR0 ? s - TRACHEA_LAST : 4) * ITEM);
+  int fl = valid ? FL_VALID : 0;
+  if (isDyn) {
+    T.own = (uint16_t)(q * ITEM);
+    T.aRec = (uint16_t)(dyn_record_of(A) * ITEM);
+    T.wall = (uint16_t)((P.soft_walls && s != GLOT_LO && s != GLOT_UP ? 0 : 3) * 24);
+    if (s > PHAR0 && s <= MOUTH_LAST && sib < 0) fl |= FL_JUNCTION;
+    if (s == GLOT_LO) fl |= FL_GLO;
+    if (s == GLOT_UP) fl |= FL_GUP;
+    if (s == 28 || s == 40 || s == 64) fl |= FL_G3;
+  } else {
+    T.own = (uint16_t)(s * sizeof(SRec));
+    T.aRec = (uint16_t)(A * sizeof(SRec));
+    T.wall = (uint16_t)((P.soft_walls && valid ? wall_type(s) : 3) * 24);
+    if (s == 0) fl |= FL_ROW0;
+  }
+  T.flags = (uint16_t)fl;
+}
+
 __global__ void __launch_bounds__(TDS_THREADS, 1)
 tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const afs_tube_frame *__restrict__ tubes,
                  const double *__restrict__ glottis, double *__restrict__ audio, double *__restrict__ flow,
                  uint32_t *__restrict__ status, double *__restrict__ dump) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TdsSmem &S = *reinterpret_cast<TdsSmem *>(smem_raw);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  char *sm = reinterpret_cast<char *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane8 = lane * 8;
   const int tract_raw = blockIdx.x * P.lanes_per_cta + lane;
   const bool active = lane < P.lanes_per_cta && tract_raw < P.n_tracts;
   const int tract = tract_raw < P.n_tracts ? tract_raw : P.n_tracts - 1;
-  const SecAccess X{S, lane};
   const afs_tube_frame *my_frames = tubes + (size_t)tract * P.n_frames;
   const double *my_glottis = glottis + (size_t)tract * P.n_frames * AFS_NUM_GLOTTIS_CONTROL;
   const int n_out = P.total_steps / P.sr_factor;
 
-  // ---- prologue: static section tables, zero state ----------------------------
-  for (int s = threadIdx.x; s < NS; s += TDS_THREADS) {
-    if (!is_dyn(s)) {
+  // ---- prologue: static records, slot table, zero state ------------------------
+  for (int s = threadIdx.x; s < NSX; s += TDS_THREADS) {
+    SRec r{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (s < NS && !is_dyn(s)) {
       const StaticSection q = static_section(s);
       double L, R, invr, circ, surface;
       if (s >= SINUS0) {  // Helmholtz resonators (TdsModel.cpp:751-757, 808-811)
@@ -764,18 +837,38 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       if (surface < kMinArea) surface = kMinArea;
       const double C = q.volume / (kRho * kC * kC);
       const double alpha = P.soft_walls ? surface * P.kalpha[wall_type(s)] : 0.0;
-      S.cL[s] = L; S.cR[s] = R; S.cInvr[s] = invr; S.cAlpha[s] = alpha;
-      S.cE[s] = P.dtth / (C + alpha);
-    } else {
-      S.cL[s] = S.cR[s] = S.cInvr[s] = S.cAlpha[s] = S.cE[s] = 0.0;
+      r.L = L; r.R1 = R; r.R0 = R; r.invr = invr; r.alpha = alpha;
+      r.E = P.dtth / (C + alpha);
+      if (s == FOSSA0 && !P.fossa) r.R0 = 8.0 * kMu * q.length * kPi / (kMinArea * kMinArea);  // TdsModel.cpp:883-889
     }
+    S.srec[s] = r;
   }
-  for (int i = warp; i < NC; i += NWS) { S.sol[0][i][lane] = 0.0; S.sol[1][i][lane] = 0.0; S.diag[i][lane] = 1.0; }
+  if (threadIdx.x < 12) {
+    const int t = threadIdx.x / 3, j = threadIdx.x % 3;
+    double v = 0.0;
+    if (t < 3) v = P.kalpha[t] * (j == 0 ? P.c1[t] : j == 1 ? P.c2[t] : P.c3[t]);
+    S.wallc[t][j] = v;
+  }
+  if (lane < KD + KS) {
+    const int k = lane;
+    build_slot(P, k < KD, 3 * warp + (k < KD ? k : k - KD), S.slot[warp][k]);
+  }
+  for (int i = warp; i < NCX; i += NWS) { S.sol[0][i][lane] = 0.0; S.sol[1][i][lane] = 0.0; if (i < NC) S.diag[i][lane] = 1.0; }
+  for (int i = warp; i < NSX; i += NWS) S.D[i][lane] = 0.0;
   if (warp == 0) {
-    for (int i = 0; i < 16; i++) S.urb[i][lane] = 0.0;
-    for (int i = 0; i < 4; i++) { S.p4[i][lane] = 0.0; S.gx[i][lane] = 0.0; S.toneX[i][lane] = 0.0; S.toneY[i][lane] = 0.0; }
+    for (int i = 0; i < 18; i++) S.urb[i][lane] = 0.0;
+    for (int i = 0; i < 5; i++) S.p4[i][lane] = 0.0;
+    for (int i = 0; i < 4; i++) { S.gx[i][lane] = 0.0; S.toneX[i][lane] = 0.0; S.toneY[i][lane] = 0.0; }
     for (int i = 0; i < 8; i++) { S.chebX[i][lane] = 0.0; S.chebY[i][lane] = 0.0; }
     S.prevFlow[lane] = 0.0;
+  }
+  __syncthreads();
+  // per-lane copies of the static records a dynamic slot reads: 69, 84 (own) and 22 (source of 23)
+  if (warp < 3) {
+    const int s = warp == 0 ? 69 : warp == 1 ? FOSSA0 : TRACHEA_LAST, x = warp == 0 ? DX_69 : warp == 1 ? DX_84 : DX_22;
+    const SRec r = S.srec[s];
+    S.E[x][lane] = r.E; S.L[x][lane] = r.L; S.R[x][lane] = s == FOSSA0 ? r.R0 : r.R1; S.invr[x][lane] = r.invr;
+    S.alpha[x][lane] = r.alpha;
   }
 
   // ---- per-thread recurrent state (registers) ----------------------------------
@@ -784,11 +877,67 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
   for (int k = 0; k < KD; k++) dyn[k] = SecState{0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int k = 0; k < KS; k++) sta[k] = SecState{0, 0, 0, 0, 0, 0};
-  double urR = 0.0, urL = 0.0;  // radiation pair owned by warps NWS-2 (mouth) and NWS-1 (nose)
-  double gbf = 0.0;             // glottalBernoulliFactor (owner of section 24)
+  double cRad[4] = {0.0, 0.0, 0.0, 0.0};  // history terms of the radiation currents 93..96 (warp NWS-1)
+  double gbf = 0.0;                        // glottalBernoulliFactor (owner of section 24)
   uint32_t bad = 0;
+  const bool has_static = warp < NWS - 1;  // warp 15 owns 68, 69, 84 and the four radiation currents instead
 
   int interval = -1, i0 = 0, i1 = 0;  // current control interval [i0, i1)
+
+  // Stages the control frames of the next interval (all warps; surrounded by barriers by the caller).
+  auto stage_interval = [&]() {
+    interval++;
+    i0 = bounds[interval]; i1 = bounds[interval + 1];
+    for (int item = warp; item < 2 * AFS_NUM_PM_SECTIONS + 2; item += NWS) {
+      if (item < 2 * AFS_NUM_PM_SECTIONS) {
+        const int f = item / AFS_NUM_PM_SECTIONS, j = item % AFS_NUM_PM_SECTIONS;
+        const afs_tube_frame *fr = my_frames + interval + f;
+        double a = fr->area_cm2[j];
+        if (a < kMinArea) a = kMinArea;  // Tube::setPharynxMouthGeometry clamps on the way in
+        S.fA[f][j][lane] = a;
+        S.fLen[f][j][lane] = fr->length_cm[j];
+      } else {
+        const int f = item - 2 * AFS_NUM_PM_SECTIONS;
+        double v = my_frames[interval + f].velum_area_cm2;
+        if (v < kMinArea) v = kMinArea;  // Tube::getVelumOpening_cm2 returns the clamped nose[0] area
+        S.velum[f][lane] = v;
+        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
+          S.gctl[f][c][lane] = my_glottis[(size_t)(interval + f) * AFS_NUM_GLOTTIS_CONTROL + c];
+      }
+    }
+  };
+  // Phase 1 of step `step` for all owned sections.
+  auto phase1_all = [&](int step) {
+    const double ratio = (double)(step - i0) / (double)(i1 - i0);
+    const double ratio1 = 1.0 - ratio;
+#pragma unroll
+    for (int k = 0; k < KD; k++) phase1_dyn(P, sm, lane8, 3 * warp + k, S.slot[warp][k], dyn[k], ratio, ratio1, step & 1);
+    if (has_static) {
+#pragma unroll
+      for (int k = 0; k < KS; k++) phase1_stat(P, sm, lane8, S.slot[warp][KD + k], sta[k]);
+    }
+  };
+
+  if (P.total_steps > 0) {
+    __syncthreads();
+    stage_interval();
+    __syncthreads();
+    if (warp == W_GLOTTIS) {  // glottis geometry of step 0
+      double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
+      for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
+      const GlottisState G{0.0, 0.0, 0.0, 0.0};
+      GlottisDims GD;
+      glottis_geometry(P, ctl, G, len, ar, GD);
+      S.gdim[0][lane] = GD.Q; S.gdim[1][lane] = GD.cordLength; S.gdim[2][lane] = GD.th0; S.gdim[3][lane] = GD.th1;
+      S.gdim[4][lane] = GD.ol0; S.gdim[5][lane] = GD.ol1; S.gdim[6][lane] = GD.cl0; S.gdim[7][lane] = GD.cl1;
+      S.gdim[8][lane] = GD.mz0; S.gdim[9][lane] = GD.mz1;
+      S.glLen[0][0][lane] = len[0]; S.glLen[0][1][lane] = len[1];
+      S.glArea[0][0][lane] = ar[0]; S.glArea[0][1][lane] = ar[1];
+    }
+    __syncthreads();
+    phase1_all(0);
+    __syncthreads();
+  }
 #ifdef AFS_TDS_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #define AFS_TICK(k) do { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } while (0)
@@ -798,81 +947,25 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
 
   for (int n = 0; n < P.total_steps; n++) {
     const int cur = n & 1, prev = cur ^ 1;
-    // ---- control-frame staging (uniform across the CTA) ----------------------
-    if (n == i1) {
-      __syncthreads();
-      interval++;
-      i0 = bounds[interval]; i1 = bounds[interval + 1];
-      for (int item = warp; item < 2 * AFS_NUM_PM_SECTIONS + 2; item += NWS) {
-        if (item < 2 * AFS_NUM_PM_SECTIONS) {
-          const int f = item / AFS_NUM_PM_SECTIONS, j = item % AFS_NUM_PM_SECTIONS;
-          const afs_tube_frame *fr = my_frames + interval + f;
-          double a = fr->area_cm2[j];
-          if (a < kMinArea) a = kMinArea;  // Tube::setPharynxMouthGeometry clamps on the way in
-          S.fA[f][j][lane] = a;
-          S.fLen[f][j][lane] = fr->length_cm[j];
-        } else {
-          const int f = item - 2 * AFS_NUM_PM_SECTIONS;
-          double v = my_frames[interval + f].velum_area_cm2;
-          if (v < kMinArea) v = kMinArea;  // Tube::getVelumOpening_cm2 returns the clamped nose[0] area
-          S.velum[f][lane] = v;
-          for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
-            S.gctl[f][c][lane] = my_glottis[(size_t)(interval + f) * AFS_NUM_GLOTTIS_CONTROL + c];
-        }
-      }
-      __syncthreads();
-      if (n == 0 && warp == W_GLOTTIS) {  // glottis geometry of step 0
-        double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
-        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
-        const GlottisState G{0.0, 0.0, 0.0, 0.0};
-        GlottisDims GD;
-        glottis_geometry(P, ctl, G, len, ar, GD);
-        S.gdim[0][lane] = GD.Q; S.gdim[1][lane] = GD.cordLength; S.gdim[2][lane] = GD.th0; S.gdim[3][lane] = GD.th1;
-        S.gdim[4][lane] = GD.ol0; S.gdim[5][lane] = GD.ol1; S.gdim[6][lane] = GD.cl0; S.gdim[7][lane] = GD.cl1;
-        S.gdim[8][lane] = GD.mz0; S.gdim[9][lane] = GD.mz1;
-        S.glLen[0][0][lane] = len[0]; S.glLen[0][1][lane] = len[1];
-        S.glArea[0][0][lane] = ar[0]; S.glArea[0][1][lane] = ar[1];
-      }
-      __syncthreads();
-    }
-    const double ratio = (double)(n - i0) / (double)(i1 - i0);
-    const double ratio1 = 1.0 - ratio;
-
+    const int curOff = cur * NCX * ITEM, prevOff = prev * NCX * ITEM;
     AFS_TICK(0);
-    // ======================= phase 1: elements, E, D ==========================
+    // ======================= phase 2: matrix rows =============================
+    {
+      const double ratio = (double)(n - i0) / (double)(i1 - i0);
+      const double psrc = (1.0 - ratio) * S.gctl[0][G_PRESSURE][lane] + ratio * S.gctl[1][G_PRESSURE][lane];
 #pragma unroll
-    for (int k = 0; k < KD; k++) {
-      const int d = k * NWS + warp;
-      if (d < ND) phase1_dynamic(P, S, lane, DYN0 + d, dyn[k], ratio, ratio1, cur);
-    }
+      for (int k = 0; k < KD; k++) phase2_row<true>(P, sm, lane8, S.slot[warp][k], dyn[k], prevOff, curOff, psrc, gbf);
+      if (has_static) {
 #pragma unroll
-    for (int k = 0; k < KS; k++) {
-      const int t = k * NWS + warp;
-      if (t < NSTAT) phase1_static(P, S, lane, static_section_of(t), sta[k]);
+        for (int k = 0; k < KS; k++) phase2_row<false>(P, sm, lane8, S.slot[warp][KD + k], sta[k], prevOff, curOff, psrc, gbf);
+      } else {
+        phase2_radiation(P, S, lane, MOUTH_LAST, 93, cRad[0], cRad[1], cur);
+        phase2_radiation(P, S, lane, NOSE_LAST, 95, cRad[2], cRad[3], cur);
+      }
     }
     AFS_TICK(1);
     __syncthreads();
     AFS_TICK(2);
-
-    // ======================= phase 2: matrix rows =============================
-    {
-      const double psrc = ratio1 * S.gctl[0][G_PRESSURE][lane] + ratio * S.gctl[1][G_PRESSURE][lane];
-#pragma unroll
-      for (int k = 0; k < KD; k++) {
-        const int d = k * NWS + warp;
-        if (d < ND) phase2_row(P, S, X, lane, DYN0 + d, dyn[k], prev, cur, psrc, gbf);
-      }
-#pragma unroll
-      for (int k = 0; k < KS; k++) {
-        const int t = k * NWS + warp;
-        if (t < NSTAT) phase2_row(P, S, X, lane, static_section_of(t), sta[k], prev, cur, psrc, gbf);
-      }
-      if (warp == NWS - 2) phase2_radiation(P, S, X, lane, MOUTH_LAST, 93, urR, urL, prev, cur);
-      if (warp == NWS - 1) phase2_radiation(P, S, X, lane, NOSE_LAST, 95, urR, urL, prev, cur);
-    }
-    AFS_TICK(3);
-    __syncthreads();
-    AFS_TICK(4);
 
     // ======================= phase 3: solve (+ glottis, + output) =============
     {
@@ -880,6 +973,7 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       double k0 = 0.0, k1 = 0.0;
       if (warp == W_GLOTTIS) {
         // incTime for this step (pressures of the previous step), then the geometry step n+1 will use
+        const double ratio = (double)(n - i0) / (double)(i1 - i0), ratio1 = 1.0 - ratio;
         double ctl[AFS_NUM_GLOTTIS_CONTROL], p[4], len[2], ar[2];
         GlottisState G{S.gx[0][lane], S.gx[1][lane], S.gx[2][lane], S.gx[3][lane]};
         for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = ratio1 * S.gctl[0][c][lane] + ratio * S.gctl[1][c][lane];
@@ -903,7 +997,7 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       } else {
         solve_3a(Z, warp, k0, k1);
       }
-      AFS_TICK(7);
+      AFS_TICK(3);
       __syncthreads();
       solve_3b_forward(Z, warp);
       __syncthreads();
@@ -913,51 +1007,57 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
       __syncthreads();
       solve_3c(Z, warp, k0);
     }
+    AFS_TICK(4);
     __syncthreads();
     AFS_TICK(5);
 
-    // ======================= phase 4: update ==================================
+    // ======================= control frames of the next interval ==============
+    if (n + 1 == i1 && n + 1 < P.total_steps) {
+      stage_interval();
+      __syncthreads();
+    }
+
+    // ======================= phase 4 (update) fused with phase 1 of step n+1 ===
 #pragma unroll
-    for (int k = 0; k < KD; k++) {
-      const int d = k * NWS + warp;
-      if (d < ND) phase4_update(P, S, X, lane, DYN0 + d, dyn[k], prev, cur);
-    }
+    for (int k = 0; k < KD; k++) phase4_update<true>(P, sm, lane8, S.slot[warp][k], dyn[k], curOff);
+    if (has_static) {
 #pragma unroll
-    for (int k = 0; k < KS; k++) {
-      const int t = k * NWS + warp;
-      if (t < NSTAT) phase4_update(P, S, X, lane, static_section_of(t), sta[k], prev, cur);
+      for (int k = 0; k < KS; k++) phase4_update<false>(P, sm, lane8, S.slot[warp][KD + k], sta[k], curOff);
+    } else {  // radiation currents (TdsModel.cpp:2063-2072)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double u_new = S.sol[cur][93 + j][lane];
+        const double ur_new = fma(u_new, P.idt, -cRad[j]);
+        cRad[j] = fma(ur_new, P.th, u_new * P.idt);
+      }
     }
-    if (warp >= NWS - 2) {  // radiation currents (TdsModel.cpp:2063-2072)
-      const int iR = warp == NWS - 2 ? 93 : 95;
-      urR = (S.sol[cur][iR][lane] - S.sol[prev][iR][lane]) * P.idt - P.th * urR;
-      urL = (S.sol[cur][iR + 1][lane] - S.sol[prev][iR + 1][lane]) * P.idt - P.th * urL;
-    }
-    AFS_TICK(6);
     if (dump && P.dump_step == n + 1) {  // diagnostics: state of tract 0 after step n+1
       if (blockIdx.x == 0 && lane == 0) {
-#define AFS_DUMP(sec, st)                                                                  \
-  do {                                                                                     \
-    dump[(sec)] = (st).p; dump[93 + (sec)] = (st).pr; dump[186 + (sec)] = (st).wc;          \
-    dump[279 + (sec)] = S.sol[cur][(sec)][lane]; dump[376 + (sec)] = (st).ur;               \
+#define AFS_DUMP(T_, st)                                                                        \
+  do {                                                                                          \
+    if ((T_).flags & FL_VALID) {                                                                \
+      const int sec = (T_).sec256 / ITEM;                                                       \
+      const double u = S.sol[cur][sec][lane];                                                   \
+      dump[sec] = (st).p; dump[93 + sec] = (st).pr; dump[186 + sec] = (st).wc;                   \
+      dump[279 + sec] = u; dump[376 + sec] = (st).c / P.th - u * P.idt / P.th;                   \
+    }                                                                                           \
   } while (0)
 #pragma unroll
-        for (int k = 0; k < KD; k++) {
-          const int d = k * NWS + warp;
-          if (d < ND) AFS_DUMP(DYN0 + d, dyn[k]);
-        }
+        for (int k = 0; k < KD; k++) AFS_DUMP(S.slot[warp][k], dyn[k]);
 #pragma unroll
-        for (int k = 0; k < KS; k++) {
-          const int t = k * NWS + warp;
-          if (t < NSTAT) AFS_DUMP(static_section_of(t), sta[k]);
-        }
+        for (int k = 0; k < KS; k++) if (has_static) AFS_DUMP(S.slot[warp][KD + k], sta[k]);
 #undef AFS_DUMP
-        if (warp >= NWS - 2) {
-          const int iR = warp == NWS - 2 ? 93 : 95;
-          dump[279 + iR] = S.sol[cur][iR][lane]; dump[279 + iR + 1] = S.sol[cur][iR + 1][lane];
-          dump[376 + iR] = urR; dump[376 + iR + 1] = urL;
+        if (!has_static) {
+          for (int j = 0; j < 4; j++) {
+            const double u = S.sol[cur][93 + j][lane];
+            dump[279 + 93 + j] = u; dump[376 + 93 + j] = cRad[j] / P.th - u * P.idt / P.th;
+          }
         }
       }
     }
+    AFS_TICK(6);
+    if (n + 1 < P.total_steps) phase1_all(n + 1);
+    AFS_TICK(7);
     __syncthreads();
   }
 #ifdef AFS_TDS_TIMING
