@@ -64,6 +64,7 @@ struct TdsParams {
   double dt, idt, th, dtth, dtth1;  // 1/fs, 1/(dt*theta), theta1/theta, dt*theta, dt*theta1
   double fsar, k_ent;
   double kalpha[3], c1[3], c2[3], c3[3];  // wall constants: 0 standard, 1 trachea, 2 sinus
+  double kc[4][3];                        // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = no walls (zeros)
   double sinus_surface[4];
   double cheb_a[9], cheb_b[9];
   double gs[AFS_NUM_GLOTTIS_STATIC];
@@ -75,18 +76,18 @@ struct SRec { double E, L, R1, invr, alpha, R0; };
 
 // Per (warp, slot) byte offsets, built once in the prologue.  All offsets are relative to array bases and fit 16 bits.
 struct SlotTab {
-  uint16_t sec256;   // section (= in-flowing current) index * 256: D[], diag[], sol[]
-  uint16_t own;      // dynamic slots: record index * 256 into E/L/R/invr/alpha; static slots: section * sizeof(SRec)
-  uint16_t aRec;     // source section A: dynamic slots -> record index * 256; static slots -> section * sizeof(SRec)
-  uint16_t aD256;    // A * 256 into D[] (dummy section 93 = zero when there is no source section)
-  uint16_t out0, out1;      // out-flowing currents * 256 into sol[] (dummy current 97 = zero)
-  uint16_t urbOwn, urbSib;  // slots * 256 in urb[]: where to publish the own history term / read the sibling's
-  uint16_t p4off;    // slot * 256 in p4[] (4 = sink)
-  uint16_t wall;     // wall-constant set * 24 in wallc[] (3 = no walls: glottis)
   uint16_t flags;
-  uint16_t pad;
+  uint8_t sec;       // section (= in-flowing current) index: D[], diag[], sol[]
+  uint8_t own;       // dynamic slots: record index into E/L/R/invr/alpha; static slots: section (srec[])
+  uint8_t aRec;      // source section A: dynamic slots -> record index; static slots -> section (srec[])
+  uint8_t aSec;      // A as an index into D[] (dummy section 93 = zero when there is no source section)
+  uint8_t out0, out1;      // out-flowing currents (dummy current 97 = zero)
+  uint8_t urbOwn, urbSib;  // slots in urb[]: where to publish the own history term / read the sibling's
+  uint8_t p4;        // slot in p4[]
+  uint8_t wall;      // wall-constant set in wallc[] (3 = no walls: glottis)
 };
-enum { FL_JUNCTION = 1, FL_GLO = 2, FL_GUP = 4, FL_ROW0 = 8, FL_VALID = 16, FL_G3 = 32 };
+enum { FL_JUNCTION = 1, FL_GLO = 2, FL_GUP = 4, FL_ROW0 = 8, FL_VALID = 16, FL_G3 = 32, FL_OUT1 = 64, FL_SIB = 128,
+       FL_URB = 256, FL_P4 = 512, FL_WALL = 1024 };
 
 // ---- shared memory layout ---------------------------------------------------
 struct TdsSmem {
@@ -231,38 +232,33 @@ __device__ __forceinline__ void section_elements(double area, double length, boo
 }
 
 
-// raw shared-memory access with byte offsets
-__device__ __forceinline__ double lds(const char *base, int off) { return *reinterpret_cast<const double *>(base + off); }
-__device__ __forceinline__ void sts(char *base, int off, double v) { *reinterpret_cast<double *>(base + off) = v; }
-#define OFF(member) ((int)offsetof(TdsSmem, member))
 constexpr int ITEM = LANES * 8;  // bytes per [item] row
 
 // beta of TdsModel.cpp:826-831 with Lw = Mw/surface, Rw = Bw/surface folded in:
-// beta = kalpha*(c1 wc + c2 wc' + c3 wc''), independent of the geometry.  w points at {kalpha c1, kalpha c2, kalpha c3}.
-__device__ __forceinline__ double wall_beta(const char *sm, int wallOff, const SecState &st) {
-  const double *w = reinterpret_cast<const double *>(sm + OFF(wallc) + wallOff);
+// beta = kalpha*(c1 wc + c2 wc' + c3 wc''), independent of the geometry.
+__device__ __forceinline__ double wall_beta3(const double *w, const SecState &st) {
   return fma(st.wc, w[0], fma(st.wcr, w[1], st.wcr2 * w[2]));
 }
 
 // ---- phase 1: per-section elements, E and D ----------------------------------
-// Dynamic slot dx (uniform).  lane8 = lane*8.
-__device__ __forceinline__ void phase1_dyn(const TdsParams &P, char *sm, int lane8, int dx, const SlotTab &T,
+// Dynamic slot dx (uniform).
+__device__ __forceinline__ void phase1_dyn(const TdsParams &P, TdsSmem &S, int lane, int dx, const SlotTab &T,
                                            const SecState &st, double ratio, double ratio1, int parity) {
   double E;
-  const int own = T.own + lane8;
-  const double beta = wall_beta(sm, T.wall, st);
+  const int own = T.own;
+  const double beta = (T.flags & FL_WALL) ? wall_beta3(P.kc[0], st) : 0.0;  // dynamic slots: standard walls or none
   if (dx < ND) {
     double area, length;
     if (dx >= 2 && dx < 42) {  // pharynx / mouth: Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350)
-      const int j = (dx - 2) * ITEM + lane8;
-      area = ratio1 * lds(sm, OFF(fA[0]) + j) + ratio * lds(sm, OFF(fA[1]) + j);
-      length = ratio1 * lds(sm, OFF(fLen[0]) + j) + ratio * lds(sm, OFF(fLen[1]) + j);
+      const int j = dx - 2;
+      area = ratio1 * S.fA[0][j][lane] + ratio * S.fA[1][j][lane];
+      length = ratio1 * S.fLen[0][j][lane] + ratio * S.fLen[1][j][lane];
     } else if (dx < 2) {  // glottis sections from the glottis model (Synthesizer.cpp:576-579)
-      area = lds(sm, OFF(glArea) + (parity * 2 + dx) * ITEM + lane8);
-      length = lds(sm, OFF(glLen) + (parity * 2 + dx) * ITEM + lane8);
+      area = S.glArea[parity][dx][lane];
+      length = S.glLen[parity][dx][lane];
     } else {  // velum port: Tube::setVelumOpening (Tube.cpp:402-416)
       const int j = dx - 42;
-      const double v = ratio1 * lds(sm, OFF(velum[0]) + lane8) + ratio * lds(sm, OFF(velum[1]) + lane8);
+      const double v = ratio1 * S.velum[0][lane] + ratio * S.velum[1][lane];
       area = v + ((double)(j * j) * (4.24 - v)) / 16.0;
       length = (11.4 / 11.4) * 0.6;
     }
@@ -279,27 +275,24 @@ __device__ __forceinline__ void phase1_dyn(const TdsParams &P, char *sm, int lan
       alpha = surface * P.kalpha[0];
     }
     E = P.dtth * fast_rcp(C + alpha);
-    sts(sm, OFF(E) + own, E); sts(sm, OFF(L) + own, L); sts(sm, OFF(R) + own, R); sts(sm, OFF(invr) + own, invr);
-    sts(sm, OFF(alpha) + own, alpha);
-    if (T.flags & FL_G3) sts(sm, OFF(g3) + (dx == 5 ? 0 : dx == 17 ? 1 : 2) * ITEM + lane8, L * P.idt + R);
+    S.E[own][lane] = E; S.L[own][lane] = L; S.R[own][lane] = R; S.invr[own][lane] = invr; S.alpha[own][lane] = alpha;
+    if (T.flags & FL_G3) S.g3[dx == 5 ? 0 : dx == 17 ? 1 : 2][lane] = L * P.idt + R;
   } else {  // sections 69 and 84: static geometry; E/alpha copies are permanent, but L, R, 1/r live in the arrays the
             // solver reuses as scratch, so they are refreshed every step
-    E = lds(sm, OFF(E) + own);
-    const SRec *r = reinterpret_cast<const SRec *>(sm + OFF(srec) + (dx == DX_69 ? 69 : FOSSA0) * (int)sizeof(SRec));
-    sts(sm, OFF(L) + own, r->L); sts(sm, OFF(R) + own, dx == DX_84 ? r->R0 : r->R1); sts(sm, OFF(invr) + own, r->invr);
+    E = S.E[own][lane];
+    const SRec &r = S.srec[dx == DX_69 ? 69 : FOSSA0];
+    S.L[own][lane] = r.L; S.R[own][lane] = dx == DX_84 ? r.R0 : r.R1; S.invr[own][lane] = r.invr;
   }
   if (dx == 0) {  // per-lane copy of static section 22, the source section of row 23 (same reason)
-    const SRec *r = reinterpret_cast<const SRec *>(sm + OFF(srec) + TRACHEA_LAST * (int)sizeof(SRec));
-    const int o = DX_22 * ITEM + lane8;
-    sts(sm, OFF(L) + o, r->L); sts(sm, OFF(R) + o, r->R1); sts(sm, OFF(invr) + o, r->invr);
+    const SRec &r = S.srec[TRACHEA_LAST];
+    S.L[DX_22][lane] = r.L; S.R[DX_22][lane] = r.R1; S.invr[DX_22][lane] = r.invr;
   }
-  sts(sm, OFF(D) + T.sec256 + lane8, st.p + P.dtth1 * st.pr - E * beta);  // TdsModel.cpp:988-1008, no flow sources
+  S.D[T.sec][lane] = st.p + P.dtth1 * st.pr - E * beta;  // TdsModel.cpp:988-1008, no flow sources
 }
 
-__device__ __forceinline__ void phase1_stat(const TdsParams &P, char *sm, int lane8, const SlotTab &T, const SecState &st) {
-  const double beta = wall_beta(sm, T.wall, st);
-  const double E = lds(sm, OFF(srec) + T.own);
-  sts(sm, OFF(D) + T.sec256 + lane8, st.p + P.dtth1 * st.pr - E * beta);
+__device__ __forceinline__ void phase1_stat(const TdsParams &P, TdsSmem &S, int lane, const SlotTab &T, const SecState &st) {
+  const double beta = wall_beta3(S.wallc[T.wall], st);
+  S.D[T.sec][lane] = st.p + P.dtth1 * st.pr - S.srec[T.own].E * beta;
 }
 
 // ---- phase 2: one matrix row (negated: SPD) per owned current -----------------
@@ -308,26 +301,25 @@ __device__ __forceinline__ void phase1_stat(const TdsParams &P, char *sm, int la
 // with c the history term of SecState.  The same formula covers plain, bifurcation and "no source section" rows
 // (dummy zero records); junction inductance / Bernoulli and the glottal losses are added under uniform flags.
 template <bool DYN>
-__device__ __forceinline__ void phase2_row(const TdsParams &P, char *sm, int lane8, const SlotTab &T, const SecState &st,
-                                           int prevOff, int curOff, double psrc, double &gbf) {
+__device__ __forceinline__ void phase2_row(const TdsParams &P, TdsSmem &S, int lane, const SlotTab &T, const SecState &st,
+                                           int prev, int cur, double psrc, double &gbf) {
   double E_B, L_B, R_B, E_A, L_A, R_A, ia = 0.0, ib = 0.0;
+  const int fl = T.flags;
   if (DYN) {
-    const int own = T.own + lane8, a = T.aRec + lane8;
-    E_B = lds(sm, OFF(E) + own); L_B = lds(sm, OFF(L) + own); R_B = lds(sm, OFF(R) + own); ib = lds(sm, OFF(invr) + own);
-    E_A = lds(sm, OFF(E) + a); L_A = lds(sm, OFF(L) + a); R_A = lds(sm, OFF(R) + a); ia = lds(sm, OFF(invr) + a);
+    const int own = T.own, a = T.aRec;
+    E_B = S.E[own][lane]; L_B = S.L[own][lane]; R_B = S.R[own][lane]; ib = S.invr[own][lane];
+    E_A = S.E[a][lane]; L_A = S.L[a][lane]; R_A = S.R[a][lane]; ia = S.invr[a][lane];
   } else {
-    const SRec *b = reinterpret_cast<const SRec *>(sm + OFF(srec) + T.own);
-    const SRec *a = reinterpret_cast<const SRec *>(sm + OFF(srec) + T.aRec);
-    E_B = b->E; L_B = b->L; R_B = b->R0;
-    E_A = a->E; L_A = a->L; R_A = a->R1;
+    const SRec &b = S.srec[T.own], &a = S.srec[T.aRec];
+    E_B = b.E; L_B = b.L; R_B = b.R0;
+    E_A = a.E; L_A = a.L; R_A = a.R1;
   }
-  const double D_B = lds(sm, OFF(D) + T.sec256 + lane8), D_A = lds(sm, OFF(D) + T.aD256 + lane8);
-  const double c_sib = lds(sm, OFF(urb) + T.urbSib + lane8);
+  const double D_B = S.D[T.sec][lane], D_A = S.D[T.aSec][lane];
+  const double c_sib = (fl & FL_SIB) ? S.urb[T.urbSib][lane] : 0.0;
   double L_AB = L_A + L_B;
   if (DYN) {
-    const int fl = T.flags;
     if (fl & (FL_JUNCTION | FL_GLO | FL_GUP)) {
-      const double uB = lds(sm, OFF(sol) + prevOff + T.sec256 + lane8);
+      const double uB = S.sol[prev][T.sec][lane];
       if (fl & FL_JUNCTION) {
         if (P.ilc) L_AB += (8.0 * kRho / (3.0 * kPi * kPi)) * fabs(ia - ib);  // Sondhi (TdsModel.cpp:1745-1778)
         if (P.turbulence) {  // Bernoulli loss wide -> narrow (TdsModel.cpp:850-877); area_B < area_A <=> ib > ia
@@ -352,9 +344,9 @@ __device__ __forceinline__ void phase2_row(const TdsParams &P, char *sm, int lan
   }
   const double diag = E_B + E_A + fma(L_AB, P.idt, R_A + R_B);
   double rhs = fma(L_AB, st.c, fma(L_A, c_sib, D_A - D_B));
-  if (!DYN) { if (T.flags & FL_ROW0) rhs += psrc; }
-  sts(sm, OFF(diag) + T.sec256 + lane8, diag);
-  sts(sm, OFF(sol) + curOff + T.sec256 + lane8, rhs);
+  if (!DYN) { if (fl & FL_ROW0) rhs += psrc; }
+  S.diag[T.sec][lane] = diag;
+  S.sol[cur][T.sec][lane] = rhs;
 }
 
 // Rows of the two parallel radiation currents out of section A (TdsModel.cpp:1841-1911):
@@ -377,20 +369,26 @@ __device__ __forceinline__ void phase2_radiation(const TdsParams &P, TdsSmem &S,
 
 // ---- phase 4: update of the recurrent state (TdsModel.cpp:2046-2098) -------------
 template <bool DYN>
-__device__ __forceinline__ void phase4_update(const TdsParams &P, char *sm, int lane8, const SlotTab &T, SecState &st,
-                                              int curOff) {
-  const int solc = OFF(sol) + curOff + lane8;
-  const double u_new = lds(sm, solc + T.sec256);
-  const double out = lds(sm, solc + T.out0) + lds(sm, solc + T.out1);
-  double E, alpha;
-  if (DYN) { E = lds(sm, OFF(E) + T.own + lane8); alpha = lds(sm, OFF(alpha) + T.own + lane8); }
-  else { const SRec *b = reinterpret_cast<const SRec *>(sm + OFF(srec) + T.own); E = b->E; alpha = b->alpha; }
-  const double D = lds(sm, OFF(D) + T.sec256 + lane8);
-  const double beta = wall_beta(sm, T.wall, st);
+__device__ __forceinline__ void phase4_update(const TdsParams &P, TdsSmem &S, int lane, const SlotTab &T, SecState &st,
+                                              int cur) {
+  const int fl = T.flags;
+  const double u_new = S.sol[cur][T.sec][lane];
+  double out = S.sol[cur][T.out0][lane];  // (dummy zero current for dead ends)
+  if (fl & FL_OUT1) out += S.sol[cur][T.out1][lane];
+  double E, alpha, beta;
+  if (DYN) {
+    E = S.E[T.own][lane]; alpha = S.alpha[T.own][lane];
+    beta = (fl & FL_WALL) ? wall_beta3(P.kc[0], st) : 0.0;
+  } else {
+    const SRec &b = S.srec[T.own];
+    E = b.E; alpha = b.alpha;
+    beta = wall_beta3(S.wallc[T.wall], st);
+  }
+  const double D = S.D[T.sec][lane];
   // current: u' = (u_new - u_old)/(dt theta) - (theta1/theta) u'_old = u_new/(dt theta) - c
   const double ur_new = fma(u_new, P.idt, -st.c);
   st.c = fma(ur_new, P.th, u_new * P.idt);
-  sts(sm, OFF(urb) + T.urbOwn + lane8, st.c);
+  if (fl & FL_URB) S.urb[T.urbOwn][lane] = st.c;
   // section
   const double p_new = fma(E, u_new - out, D);
   const double pr_new = (p_new - st.p) * P.idt - st.pr * P.th;
@@ -398,7 +396,7 @@ __device__ __forceinline__ void phase4_update(const TdsParams &P, char *sm, int 
   const double wcr_new = (wc_new - st.wc) * P.idt - st.wcr * P.th;
   const double wcr2_new = (wcr_new - st.wcr) * P.idt - st.wcr2 * P.th;
   st.p = p_new; st.pr = pr_new; st.wc = wc_new; st.wcr = wcr_new; st.wcr2 = wcr2_new;
-  sts(sm, OFF(p4) + T.p4off + lane8, p_new);
+  if (fl & FL_P4) S.p4[T.p4][lane] = p_new;
 }
 
 // ---- phase 3: the linear solve (parallel partition) ------------------------------
@@ -771,35 +769,40 @@ __device__ __forceinline__ void emit_output(const TdsParams &P, TdsSmem &S, int 
 
 // Slot table entry for dynamic (isDyn) slot index q = 3*warp + k, or static slot index q.
 __device__ void build_slot(const TdsParams &P, bool isDyn, int q, SlotTab &T) {
-  T = SlotTab{};
   const bool valid = isDyn ? true : q < NSTAT;
   const int s = isDyn ? dyn_slot_section(q) : (valid ? stat_slot_section(q) : NS);
   const int A = valid ? src_of(s) : NS;
   int o0, o1;
   outs_of(valid ? s : FOSSA_LAST, o0, o1);
   const int sib = valid ? sibling_of(s) : -1;
-  T.sec256 = (uint16_t)(s * ITEM);
-  T.aD256 = (uint16_t)(A * ITEM);
-  T.out0 = (uint16_t)(o0 * ITEM); T.out1 = (uint16_t)(o1 * ITEM);
-  T.urbOwn = (uint16_t)((urb_slot(s) >= 0 && valid ? urb_slot(s) : 16) * ITEM);
-  T.urbSib = (uint16_t)((sib >= 0 ? urb_slot(sib) : 17) * ITEM);
-  T.p4off = (uint16_t)((valid && s >= TRACHEA_LAST && s <= PHAR0 ? s - TRACHEA_LAST : 4) * ITEM);
+  SlotTab t{};
+  t.sec = (uint8_t)s; t.aSec = (uint8_t)A;
+  t.out0 = (uint8_t)o0; t.out1 = (uint8_t)o1;
+  t.urbOwn = (uint8_t)(valid && urb_slot(s) >= 0 ? urb_slot(s) : 16);
+  t.urbSib = (uint8_t)(sib >= 0 ? urb_slot(sib) : 17);
+  t.p4 = (uint8_t)(valid && s >= TRACHEA_LAST && s <= PHAR0 ? s - TRACHEA_LAST : 4);
   int fl = valid ? FL_VALID : 0;
+  if (valid && o1 != NC) fl |= FL_OUT1;
+  if (sib >= 0) fl |= FL_SIB;
+  if (valid && urb_slot(s) >= 0) fl |= FL_URB;
+  if (valid && s >= TRACHEA_LAST && s <= PHAR0) fl |= FL_P4;
   if (isDyn) {
-    T.own = (uint16_t)(q * ITEM);
-    T.aRec = (uint16_t)(dyn_record_of(A) * ITEM);
-    T.wall = (uint16_t)((P.soft_walls && s != GLOT_LO && s != GLOT_UP ? 0 : 3) * 24);
+    t.own = (uint8_t)q;
+    t.aRec = (uint8_t)dyn_record_of(A);
+    t.wall = 0;
+    if (P.soft_walls && s != GLOT_LO && s != GLOT_UP) fl |= FL_WALL;
     if (s > PHAR0 && s <= MOUTH_LAST && sib < 0) fl |= FL_JUNCTION;
     if (s == GLOT_LO) fl |= FL_GLO;
     if (s == GLOT_UP) fl |= FL_GUP;
     if (s == 28 || s == 40 || s == 64) fl |= FL_G3;
   } else {
-    T.own = (uint16_t)(s * sizeof(SRec));
-    T.aRec = (uint16_t)(A * sizeof(SRec));
-    T.wall = (uint16_t)((P.soft_walls && valid ? wall_type(s) : 3) * 24);
+    t.own = (uint8_t)s;
+    t.aRec = (uint8_t)A;
+    t.wall = (uint8_t)(P.soft_walls && valid ? wall_type(s) : 3);
     if (s == 0) fl |= FL_ROW0;
   }
-  T.flags = (uint16_t)fl;
+  t.flags = (uint16_t)fl;
+  T = t;
 }
 
 __global__ void __launch_bounds__(TDS_THREADS, 1)
@@ -808,10 +811,8 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
                  uint32_t *__restrict__ status, double *__restrict__ dump) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TdsSmem &S = *reinterpret_cast<TdsSmem *>(smem_raw);
-  char *sm = reinterpret_cast<char *>(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
-  const int lane8 = lane * 8;
   const int tract_raw = blockIdx.x * P.lanes_per_cta + lane;
   const bool active = lane < P.lanes_per_cta && tract_raw < P.n_tracts;
   const int tract = tract_raw < P.n_tracts ? tract_raw : P.n_tracts - 1;
@@ -911,10 +912,10 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
     const double ratio = (double)(step - i0) / (double)(i1 - i0);
     const double ratio1 = 1.0 - ratio;
 #pragma unroll
-    for (int k = 0; k < KD; k++) phase1_dyn(P, sm, lane8, 3 * warp + k, S.slot[warp][k], dyn[k], ratio, ratio1, step & 1);
+    for (int k = 0; k < KD; k++) phase1_dyn(P, S, lane, 3 * warp + k, S.slot[warp][k], dyn[k], ratio, ratio1, step & 1);
     if (has_static) {
 #pragma unroll
-      for (int k = 0; k < KS; k++) phase1_stat(P, sm, lane8, S.slot[warp][KD + k], sta[k]);
+      for (int k = 0; k < KS; k++) phase1_stat(P, S, lane, S.slot[warp][KD + k], sta[k]);
     }
   };
 
@@ -947,17 +948,16 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
 
   for (int n = 0; n < P.total_steps; n++) {
     const int cur = n & 1, prev = cur ^ 1;
-    const int curOff = cur * NCX * ITEM, prevOff = prev * NCX * ITEM;
     AFS_TICK(0);
     // ======================= phase 2: matrix rows =============================
     {
       const double ratio = (double)(n - i0) / (double)(i1 - i0);
       const double psrc = (1.0 - ratio) * S.gctl[0][G_PRESSURE][lane] + ratio * S.gctl[1][G_PRESSURE][lane];
 #pragma unroll
-      for (int k = 0; k < KD; k++) phase2_row<true>(P, sm, lane8, S.slot[warp][k], dyn[k], prevOff, curOff, psrc, gbf);
+      for (int k = 0; k < KD; k++) phase2_row<true>(P, S, lane, S.slot[warp][k], dyn[k], prev, cur, psrc, gbf);
       if (has_static) {
 #pragma unroll
-        for (int k = 0; k < KS; k++) phase2_row<false>(P, sm, lane8, S.slot[warp][KD + k], sta[k], prevOff, curOff, psrc, gbf);
+        for (int k = 0; k < KS; k++) phase2_row<false>(P, S, lane, S.slot[warp][KD + k], sta[k], prev, cur, psrc, gbf);
       } else {
         phase2_radiation(P, S, lane, MOUTH_LAST, 93, cRad[0], cRad[1], cur);
         phase2_radiation(P, S, lane, NOSE_LAST, 95, cRad[2], cRad[3], cur);
@@ -1019,10 +1019,10 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
 
     // ======================= phase 4 (update) fused with phase 1 of step n+1 ===
 #pragma unroll
-    for (int k = 0; k < KD; k++) phase4_update<true>(P, sm, lane8, S.slot[warp][k], dyn[k], curOff);
+    for (int k = 0; k < KD; k++) phase4_update<true>(P, S, lane, S.slot[warp][k], dyn[k], cur);
     if (has_static) {
 #pragma unroll
-      for (int k = 0; k < KS; k++) phase4_update<false>(P, sm, lane8, S.slot[warp][KD + k], sta[k], curOff);
+      for (int k = 0; k < KS; k++) phase4_update<false>(P, S, lane, S.slot[warp][KD + k], sta[k], cur);
     } else {  // radiation currents (TdsModel.cpp:2063-2072)
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -1036,7 +1036,7 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
 #define AFS_DUMP(T_, st)                                                                        \
   do {                                                                                          \
     if ((T_).flags & FL_VALID) {                                                                \
-      const int sec = (T_).sec256 / ITEM;                                                       \
+      const int sec = (T_).sec;                                                       \
       const double u = S.sol[cur][sec][lane];                                                   \
       dump[sec] = (st).p; dump[93 + sec] = (st).pr; dump[186 + sec] = (st).wc;                   \
       dump[279 + sec] = u; dump[376 + sec] = (st).c / P.th - u * P.idt / P.th;                   \
@@ -1107,6 +1107,11 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   }
   static const double sinus_vol[4] = {11.3, 6.8, 33.0, 6.2};
   for (int i = 0; i < 4; i++) P.sinus_surface[i] = 4.0 * M_PI * pow((3.0 * sinus_vol[i]) / (4.0 * M_PI), 2.0 / 3.0);
+  for (int t = 0; t < 4; t++) {
+    P.kc[t][0] = t < 3 ? P.kalpha[t] * P.c1[t] : 0.0;
+    P.kc[t][1] = t < 3 ? P.kalpha[t] * P.c2[t] : 0.0;
+    P.kc[t][2] = t < 3 ? P.kalpha[t] * P.c3[t] : 0.0;
+  }
   chebyshev_lowpass(7000.0 / fs_tds_hz, 8, P.cheb_a, P.cheb_b);  // Synthesizer.cpp:52
   for (int i = 0; i < AFS_NUM_GLOTTIS_STATIC; i++) P.gs[i] = o->glottis_static[i];
   P.dump_step = 0;

@@ -11,7 +11,7 @@ fr, gl = make_tds_batch(B, 1)
 buf = np.zeros(473); ctx.set_state_dump(10**9, buf)
 a, _, _ = ctx.tds_synthesize(fr, gl, [T // 2 + 1], 44100.0, 2)
 steps = (T // 2 + 1) * 2
-names = ["loop+stage+bar", "P1 compute", "P1 barrier", "P2 compute", "P2 barrier", "P3 rest(bar,junction,back)", "P4 compute", "P3 fwd/glottis/output"]
+names = ["loop top", "P2 compute", "P2 barrier", "P3a seg/glot", "P3 b+c", "P3 end barrier", "P4 update", "P1 next+stage"]
 t = buf[:128].reshape(16, 8) / steps
 print("cycles per step, per warp (lane 0 of CTA 0):")
 print("warp " + " ".join(f"{n[:12]:>12s}" for n in names) + "        total")
