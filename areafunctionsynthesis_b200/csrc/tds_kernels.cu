@@ -68,6 +68,7 @@ struct TdsParams {
   double sinus_surface[4];
   double cheb_a[9], cheb_b[9];
   double gs[AFS_NUM_GLOTTIS_STATIC];
+  double g_sqrt_mk[2];  // sqrt(mass_i * spring_i): the tension Q cancels (TriangularGlottis.cpp:247-249)
 };
 
 // Static section record (same for all tracts).  R1 = resistance seen by the out-flowing current, R0 by the
@@ -552,29 +553,45 @@ __device__ __forceinline__ void solve_3a(Solver &Z, int warp, double &k0, double
   }
 }
 
-// 3b: reduced system.  Forward: three separator chains; junction; back.
+// 3b: reduced system.  Forward: three separator chains (one warp each), all operands loaded up front and the
+// eliminations done in registers; junction; back.
+__device__ __forceinline__ void red_elim(double &dx, double rx, double c, double &dy, double &ry) {  // x into y
+  const double w = fast_rcp(dx);
+  dx = w;
+  const double t = c * w;
+  dy = fma(-t, c, dy);
+  ry = fma(-t, rx, ry);
+}
 __device__ __forceinline__ void solve_3b_forward(Solver &Z, int warp) {
   if (warp == R_RED_T) {
-    Z.d(9) -= Z.side(R_T1, 0); Z.r(9) -= Z.side(R_T1, 1);
-    Z.d(19) -= Z.side(R_T2, 0); Z.r(19) -= Z.side(R_T2, 1);
-    Z.d(28) -= Z.leaf(0); Z.r(28) -= Z.leaf(1);
-    Z.d(29) -= Z.leaf(2) + Z.side(R_T4, 0); Z.r(29) -= Z.leaf(3) + Z.side(R_T4, 1);
-    Z.elim_into(9, 19, Z.side(R_T1, 2));
-    Z.elim_into(19, 28, Z.side(R_T2, 2));
-    Z.elim_into(28, 29, Z.leaf(4));
-    Z.elim_into(29, 40, Z.side(R_T4, 2));
+    const double c0 = Z.side(R_T1, 2), c1 = Z.side(R_T2, 2), c2 = Z.leaf(4), c3 = Z.side(R_T4, 2);
+    double d9 = Z.d(9) - Z.side(R_T1, 0), r9 = Z.r(9) - Z.side(R_T1, 1);
+    double d19 = Z.d(19) - Z.side(R_T2, 0), r19 = Z.r(19) - Z.side(R_T2, 1);
+    double d28 = Z.d(28) - Z.leaf(0), r28 = Z.r(28) - Z.leaf(1);
+    double d29 = Z.d(29) - (Z.leaf(2) + Z.side(R_T4, 0)), r29 = Z.r(29) - (Z.leaf(3) + Z.side(R_T4, 1));
+    double d40 = Z.d(40), r40 = Z.r(40);
+    red_elim(d9, r9, c0, d19, r19);
+    red_elim(d19, r19, c1, d28, r28);
+    red_elim(d28, r28, c2, d29, r29);
+    red_elim(d29, r29, c3, d40, r40);
+    Z.d(9) = d9; Z.r(9) = r9; Z.d(19) = d19; Z.r(19) = r19; Z.d(28) = d28; Z.r(28) = r28; Z.d(29) = d29; Z.r(29) = r29;
+    Z.d(40) = d40; Z.r(40) = r40;
   } else if (warp == R_RED_M) {
-    Z.d(41) -= Z.side(R_M1, 0); Z.r(41) -= Z.side(R_M1, 1);
-    Z.d(53) -= Z.side(R_M2, 0); Z.r(53) -= Z.side(R_M2, 1);
-    Z.d(64) -= Z.leaf(5); Z.r(64) -= Z.leaf(6);
-    Z.elim_into(64, 53, Z.side(R_M2, 2));
-    Z.elim_into(53, 41, Z.side(R_M1, 2));
+    const double c0 = Z.side(R_M2, 2), c1 = Z.side(R_M1, 2);
+    double d41 = Z.d(41) - Z.side(R_M1, 0), r41 = Z.r(41) - Z.side(R_M1, 1);
+    double d53 = Z.d(53) - Z.side(R_M2, 0), r53 = Z.r(53) - Z.side(R_M2, 1);
+    double d64 = Z.d(64) - Z.leaf(5), r64 = Z.r(64) - Z.leaf(6);
+    red_elim(d64, r64, c0, d53, r53);
+    red_elim(d53, r53, c1, d41, r41);
+    Z.d(64) = d64; Z.r(64) = r64; Z.d(53) = d53; Z.r(53) = r53; Z.d(41) = d41; Z.r(41) = r41;
   } else if (warp == R_RED_N) {
-    Z.d(65) -= Z.side(R_N1, 0); Z.r(65) -= Z.side(R_N1, 1);
-    Z.d(75) -= Z.side(R_N2, 0); Z.r(75) -= Z.side(R_N2, 1);
-    Z.d(83) -= Z.leaf(7); Z.r(83) -= Z.leaf(8);
-    Z.elim_into(83, 75, Z.side(R_N2, 2));
-    Z.elim_into(75, 65, Z.side(R_N1, 2));
+    const double c0 = Z.side(R_N2, 2), c1 = Z.side(R_N1, 2);
+    double d65 = Z.d(65) - Z.side(R_N1, 0), r65 = Z.r(65) - Z.side(R_N1, 1);
+    double d75 = Z.d(75) - Z.side(R_N2, 0), r75 = Z.r(75) - Z.side(R_N2, 1);
+    double d83 = Z.d(83) - Z.leaf(7), r83 = Z.r(83) - Z.leaf(8);
+    red_elim(d83, r83, c0, d75, r75);
+    red_elim(d75, r75, c1, d65, r65);
+    Z.d(83) = d83; Z.r(83) = r83; Z.d(75) = d75; Z.r(75) = r75; Z.d(65) = d65; Z.r(65) = r65;
   }
 }
 // Junction at the velum: clique {40, 41, 65} through section 40.
@@ -596,16 +613,26 @@ __device__ __forceinline__ void solve_velum_junction(Solver &Z) {
 }
 __device__ __forceinline__ void solve_3b_back(Solver &Z, int warp) {
   if (warp == R_RED_T) {
-    Z.back_from(29, 40, Z.side(R_T4, 2));
-    Z.back_from(28, 29, Z.leaf(4));
-    Z.back_from(19, 28, Z.side(R_T2, 2));
-    Z.back_from(9, 19, Z.side(R_T1, 2));
+    const double c0 = Z.side(R_T1, 2), c1 = Z.side(R_T2, 2), c2 = Z.leaf(4), c3 = Z.side(R_T4, 2);
+    const double w9 = Z.d(9), w19 = Z.d(19), w28 = Z.d(28), w29 = Z.d(29);
+    const double r9 = Z.r(9), r19 = Z.r(19), r28 = Z.r(28), r29 = Z.r(29), u40 = Z.r(40);
+    const double u29 = (r29 - c3 * u40) * w29;
+    const double u28 = (r28 - c2 * u29) * w28;
+    const double u19 = (r19 - c1 * u28) * w19;
+    const double u9 = (r9 - c0 * u19) * w9;
+    Z.r(29) = u29; Z.r(28) = u28; Z.r(19) = u19; Z.r(9) = u9;
   } else if (warp == R_RED_M) {
-    Z.back_from(53, 41, Z.side(R_M1, 2));
-    Z.back_from(64, 53, Z.side(R_M2, 2));
+    const double c0 = Z.side(R_M2, 2), c1 = Z.side(R_M1, 2);
+    const double w53 = Z.d(53), w64 = Z.d(64), r53 = Z.r(53), r64 = Z.r(64), u41 = Z.r(41);
+    const double u53 = (r53 - c1 * u41) * w53;
+    const double u64 = (r64 - c0 * u53) * w64;
+    Z.r(53) = u53; Z.r(64) = u64;
   } else if (warp == R_RED_N) {
-    Z.back_from(75, 65, Z.side(R_N1, 2));
-    Z.back_from(83, 75, Z.side(R_N2, 2));
+    const double c0 = Z.side(R_N2, 2), c1 = Z.side(R_N1, 2);
+    const double w75 = Z.d(75), w83 = Z.d(83), r75 = Z.r(75), r83 = Z.r(83), u65 = Z.r(65);
+    const double u75 = (r75 - c1 * u65) * w75;
+    const double u83 = (r83 - c0 * u75) * w83;
+    Z.r(75) = u75; Z.r(83) = u83;
   }
 }
 __device__ __forceinline__ void solve_3c(Solver &Z, int warp, double k0) {
@@ -694,7 +721,7 @@ __device__ __forceinline__ void glottis_inc_time(const TdsParams &P, const doubl
   const double kc = P.gs[S_KC] * Q * Q;
   const double dr0 = P.gs[S_DAMP1] + al0 * 1.0, dr1 = P.gs[S_DAMP2] + al1 * 1.0;
   // mass*spring = MASS*K (Q cancels): sqrt of a launch constant
-  const double r0 = 2.0 * dr0 * fast_sqrt(m0 * k0), r1 = 2.0 * dr1 * fast_sqrt(m1 * k1);
+  const double r0 = 2.0 * dr0 * P.g_sqrt_mk[0], r1 = 2.0 * dr1 * P.g_sqrt_mk[1];
   double f0 = p[1] * D.ol0 * D.th0, f1 = p[2] * D.ol1 * D.th1;
   f0 += 0.5 * 0.5 * (p[0] + p[1]) * P.gs[S_INLET] * D.cordLength;
   f1 += 0.5 * 0.5 * (p[3] + p[2]) * P.gs[S_OUTLET] * D.cordLength;
@@ -1114,6 +1141,8 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   }
   chebyshev_lowpass(7000.0 / fs_tds_hz, 8, P.cheb_a, P.cheb_b);  // Synthesizer.cpp:52
   for (int i = 0; i < AFS_NUM_GLOTTIS_STATIC; i++) P.gs[i] = o->glottis_static[i];
+  P.g_sqrt_mk[0] = sqrt(P.gs[S_MASS1] * P.gs[S_K1]);
+  P.g_sqrt_mk[1] = sqrt(P.gs[S_MASS2] * P.gs[S_K2]);
   P.dump_step = 0;
   L->params.resize(sizeof P);
   memcpy(L->params.data(), &P, sizeof P);
