@@ -209,7 +209,7 @@ class Oracle:
         return f, bw, num, flags
 
     def tds_synthesize(self, frames, glottis, frame_len, fs_tds_hz=44100.0, sr_factor=2, opts=None, want_flow=True,
-                       dump_step=0):
+                       dump_step=0, seeds=None):
         opts = opts or tds_options_default()
         frames = np.ascontiguousarray(frames)
         B, F = frames.shape
@@ -219,8 +219,9 @@ class Oracle:
         flow = np.zeros((B, n_out * sr_factor)) if want_flow else None
         st = np.zeros(473) if dump_step else None
         g = np.ascontiguousarray(glottis, dtype=np.float64)
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
         rc = self.lib.orc_tds_synthesize(C.byref(opts), B, F, _ptr(frame_len), _ptr(frames), _ptr(g),
-                                         C.c_double(fs_tds_hz), sr_factor, None, _ptr(audio), _ptr(flow), _ptr(st),
+                                         C.c_double(fs_tds_hz), sr_factor, _ptr(sd), _ptr(audio), _ptr(flow), _ptr(st),
                                          dump_step)
         assert rc == 0, rc
         if dump_step:

@@ -99,6 +99,19 @@ def test_tds_transition_velum_and_options_bit_identical(oracle):
     assert np.array_equal(u, g["nasal_flow44"]) and np.array_equal(a, g["nasal_audio44"])
 
 
+def test_tds_noise_sources_bit_identical(oracle):
+    """calcNoiseSources/calcNoiseSample (TdsModel.cpp:1188-1708) with the glibc rand() stream restated."""
+    from oracle.pyoracle import tds_options_default
+    g = load_golden("tds_reference.npz")
+    on = tds_options_default(noise=True)
+    a, u = oracle.tds_synthesize(g["noise_frames"], g["noise_glottis"], [3308], 44100.0, 2, opts=on,
+                                 seeds=g["noise_seeds"])
+    assert np.array_equal(u, g["noise_flow44"]) and np.array_equal(a, g["noise_audio44"])
+    # the fixture really exercises the sources: noise off gives a different waveform
+    a0, _ = oracle.tds_synthesize(g["noise_frames"], g["noise_glottis"], [3308], 44100.0, 2)
+    assert np.abs(a0 - a).max() > 1e-3 * np.abs(a).max()
+
+
 def test_tds_state_dump_matches_reference(oracle):
     g = load_golden("tds_reference.npz")
     for step in (1, 2, 500):

@@ -88,6 +88,15 @@ def main():
     for step in (1, 2, 500):
         _, _, st = r44.tds_state_after(fr[0], gl[0], [2205], step)
         tds[f"static_state_{step}"] = st
+    # (5) noise sources on (TdsModel.cpp:1188-1708; libc rand() seeded per utterance): /a/ -> /s/ (tongue
+    #     constriction + teeth source), /a/ -> /f/ (lip source), static /S/ with strong aspiration
+    on = tds_options_default(noise=True)
+    gn = np.array([[[120.0, 8000.0, 0.01, 0.01, 0.0, -40.0], [120.0, 8000.0, 0.03, 0.03, 0.05, -10.0]]] * 3)
+    frn3 = np.stack([np.stack([fa[0], frames[idx["s"]]]), np.stack([fa[0], frames[idx["f"]]]),
+                     np.stack([frames[idx["S"]], frames[idx["S"]]])])
+    seeds = np.array([1234, 99, 20260002], dtype=np.uint32)
+    ans, uns = r44.tds_synthesize(frn3, gn, [3308], opts=on, seeds=seeds)
+    tds.update(noise_frames=frn3, noise_glottis=gn, noise_seeds=seeds, noise_audio44=ans, noise_flow44=uns)
     np.savez_compressed(os.path.join(OUT, "tds_reference.npz"), **tds)
 
     # --- filter design
