@@ -10,30 +10,38 @@
 // (:687-705) and the driver's differentiator + Chebyshev-8 output filter
 // (Synthesizer.cpp:614-627).
 //
-// B200 mapping ("tract per lane, sections across warps"):
+// B200 mapping ("tract per lane, one chain segment per warp"):
 //   * one CTA = up to 32 independent tracts; LANE = TRACT everywhere, so every
-//     warp instruction does useful work for 32 tracts and all branches on the
-//     section type are warp-uniform (no divergence);
-//   * 16 warps each own 3 "dynamic" slots (sections 23..68 whose geometry
-//     changes every sample, blocked 3 per warp, + sections 69 and 84 whose
-//     upstream neighbour is dynamic) and 3 static slots, together with the
-//     branch current flowing INTO each owned section; the recurrent state (p,
-//     p', three wall-current terms, the current's history term c) never leaves
-//     the owner's REGISTERS for the whole utterance;
-//   * everything that crosses sections (E, D, L, R, 1/r, alpha, matrix rows,
-//     the solution) is exchanged through SHARED MEMORY in [item][lane] layout
-//     (256 B per item: conflict-free); all per-slot addressing comes from a
-//     small uint16 offset table built once, so the phases are straight-line
-//     code with uniform-offset LDS/STS and no per-access index arithmetic;
-//   * per step: phase 2 rows -> phase 3 solve (parallel partition over 12
-//     warps + 3-warp reduced system) || glottis || output filters -> fused
-//     phase 4 (state update) + phase 1 of the next step (elements, E, D);
-//   * the two control frames of the current interval are staged in shared
-//     memory; audio and flow are the only per-step HBM traffic.
+//     warp instruction does useful work for 32 tracts and every branch on the
+//     section type is warp-uniform;
+//   * the 97-current network (a tree of chains: trachea-glottis-pharynx,
+//     mouth, nose, piriform fossa; sinuses and radiation loads as leaves) is
+//     cut into 14 contiguous SEGMENTS, one per warp: 8 "dynamic" warps own six
+//     sections of 23..70 each (geometry changes every sample), 6 "static"
+//     warps own the trachea, the rigid part of the nose (+ sinuses), the fossa
+//     (+ both radiation loads).  A segment warp keeps its recurrent state (p,
+//     p', current history c, last solution u) in REGISTERS and does the state
+//     update, the network elements, its matrix rows AND the elimination of
+//     its segment without leaving registers;
+//   * only what crosses a segment boundary goes through SHARED MEMORY in
+//     [item][lane] layout (256 B rows, conflict-free): the record of the last
+//     section (for the neighbour's first row), the Schur-complement
+//     contribution to the separator currents, the separator solutions; plus
+//     the soft-wall state (touched once per step) and the control frames;
+//   * the linear system (negated: SPD, graph = tree of 3-cliques) is solved by
+//     parallel partition: every warp eliminates its interior currents towards
+//     its last current (the coupling to the left separator travels along as a
+//     "spike"), three warps then solve the reduced system over the 16
+//     separators (three chains meeting in the velum clique {40,41,65}), and
+//     every warp back-substitutes.  Segments whose sections are all static
+//     have CONSTANT pivots: their factors are computed once in the prologue
+//     and only the right-hand side is eliminated per step;
+//   * two auxiliary warps run the glottis model + output filters and (noise
+//     sources on) the noise-source logic concurrently with the solve.
 // FP64 throughout.  Algebraically simplified w.r.t. the reference (wall
 // admittance alpha = surface * const, one rcp + one sqrt + one rcp per dynamic
-// section instead of ~15 div/sqrt, branch-free MUFU+Newton rcp/sqrt), FMA
-// contraction on; parity gate 1e-6 relative max-abs on audio.
+// section instead of ~15 div/sqrt, branch-free MUFU+Newton rcp/sqrt, zero-fill
+// elimination order), FMA contraction on; parity gate 1e-6 relative max-abs.
 #include <cmath>
 #include <cstddef>
 #include <cstring>
@@ -43,26 +51,33 @@
 namespace afs {
 
 constexpr int LANES = 32;
-constexpr int NWS = 16;                       // warps per CTA
-constexpr int TDS_THREADS = NWS * 32;
-constexpr int W_GLOTTIS = 3, W_OUTPUT = 4;    // warps that run the glottis / output filters during phase 3
-constexpr int ND = 46;                        // truly dynamic sections 23..68
-constexpr int DYN0 = 23, DYN_LAST = 68;
-constexpr int NDX = 49;                       // per-lane exchange records: 0..45 sections 23..68, 46 = 69, 47 = 84, 48 = copy of 22
-constexpr int DX_69 = 46, DX_84 = 47, DX_22 = 48;
-constexpr int KD = 3, KS = 3;                 // dynamic / static slots per warp
-constexpr int NSTAT = 45;                     // sections owned by static slots (all but 23..69 and 84)
-constexpr int NCX = NC + 1;                   // + one always-zero dummy current (index 97)
-constexpr int NSX = NS + 1;                   // + one all-zero dummy section (index 93): "no source section"
+constexpr int NW = 16;                        // warps per CTA
+constexpr int TDS_THREADS = NW * 32;
+constexpr int KD = 6;                         // sections per dynamic-chain warp
+constexpr int NSX = NS + 1;                   // + one all-zero dummy section (index 93)
 constexpr double kTheta = 0.515;              // TdsModel.cpp:15
 constexpr double kTheta1 = 1.0 - kTheta;
+
+// Warp roles.  The id also fixes the SM sub-partition (id % 4); the order balances the FP64 work of the four.
+//   dynamic chains: GP 23..28 (glottis + pharynx), P1 29..34, P2 35..40, M0 41..46, M1 47..52, M2 53..58,
+//                   M3 59..64, NV 65..70 (velum port 65..68 + two rigid nose sections)
+//   static chains:  T0 0..7, T1 8..15, T2 16..22 (trachea), N1 71..75 (+ sinuses 89, 90), N2 76..83 (+ sinuses
+//                   91, 92), F 84..88 (piriform fossa; + the radiation currents 93..96)
+//   X1 glottis model + output filters, X2 noise sources
+enum { W_GP = 0, W_P1, W_P2, W_M0, W_M1, W_M2, W_M3, W_NV, W_T0, W_T1, W_N2, W_T2, W_X1, W_F, W_X2, W_N1 };
+// separators of the partition (last current of every segment + the first currents of the branches)
+enum { S7 = 0, S15, S22, S28, S29, S34, S40, S41, S46, S52, S58, S64, S65, S70, S75, S83, NSEP };
+// uext[]: solution of the first current of every warp's segment (index = warp id) + radiated flows + zero
+enum { UX_RADM = 16, UX_RADN = 17, UX_ZERO = 18, NUX = 19 };
 
 struct TdsParams {
   int n_tracts, n_frames, lanes_per_cta, total_steps, sr_factor;
   int turbulence, soft_walls, skin, fossa, ilc;
   int dump_step;
   double dt, idt, th, dtth, dtth1;  // 1/fs, 1/(dt*theta), theta1/theta, dt*theta, dt*theta1
+  double ith, fs;                   // theta/theta1, fs
   double fsar, k_ent;
+  double k_sondhi, k_bern;          // 8 rho/(3 pi^2) resp. rho/2, or 0 when the option is off
   double kalpha[3], c1[3], c2[3], c3[3];  // wall constants: 0 standard, 1 trachea, 2 sinus
   double kc[4][3];                        // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = no walls (zeros)
   double sinus_surface[4];
@@ -73,39 +88,34 @@ struct TdsParams {
 
 // Static section record (same for all tracts).  R1 = resistance seen by the out-flowing current, R0 by the
 // in-flowing one (they differ only for the decoupled piriform fossa entrance, TdsModel.cpp:883-889).
-struct SRec { double E, L, R1, invr, alpha, R0; };
+struct SRec { double E, L, R1, R0, invr, alpha; };
 
-// Per (warp, slot) byte offsets, built once in the prologue.  All offsets are relative to array bases and fit 16 bits.
-struct SlotTab {
-  uint16_t flags;
-  uint8_t sec;       // section (= in-flowing current) index: D[], diag[], sol[]
-  uint8_t own;       // dynamic slots: record index into E/L/R/invr/alpha; static slots: section (srec[])
-  uint8_t aRec;      // source section A: dynamic slots -> record index; static slots -> section (srec[])
-  uint8_t aSec;      // A as an index into D[] (dummy section 93 = zero when there is no source section)
-  uint8_t out0, out1;      // out-flowing currents (dummy current 97 = zero)
-  uint8_t urbOwn, urbSib;  // slots in urb[]: where to publish the own history term / read the sibling's
-  uint8_t p4;        // slot in p4[]
-  uint8_t wall;      // wall-constant set in wallc[] (3 = no walls: glottis)
+// Elimination constants of one static chain (computed once in the prologue).
+struct STab {
+  double T[8], W[8], H[8];     // per interior current: coupling/pivot, 1/pivot, spike/pivot
+  double DB, FF, DDA;          // pivot of the last current, coupling left separator <-> last current, Schur term
+  double le[2], lg[2], lw[2];  // sinus leaves: couplings e, g and 1/pivot
+  double WB, CA;               // fossa: 1/DB and the constant part subtracted from the pivot of current 84
 };
-enum { FL_JUNCTION = 1, FL_GLO = 2, FL_GUP = 4, FL_ROW0 = 8, FL_VALID = 16, FL_G3 = 32, FL_OUT1 = 64, FL_SIB = 128,
-       FL_URB = 256, FL_P4 = 512, FL_WALL = 1024 };
 
 // ---- shared memory layout ---------------------------------------------------
 struct TdsSmem {
-  // per-tract exchange, [item][lane]
-  double D[NSX][LANES];
-  double E[NDX][LANES];
-  double L[NDX][LANES], R[NDX][LANES], invr[NDX][LANES];  // contiguous: reused as solver scratch in phase 3
-  double alpha[NDX][LANES];
-  double diag[NC][LANES];
-  double sol[2][NCX][LANES];
-  double urb[18][LANES];          // history terms c of the 16 sibling (branch / radiation) currents, 16 = sink, 17 = zero
+  // per tract, [item][lane]
+  double Ed[8 * KD][LANES], Al[8 * KD][LANES];   // E and alpha of the dynamic sections (index 6*warp + slot)
+  double wall[NS][3][LANES];                     // wall current, its 1st and 2nd rate (TdsModel.h:184-186)
   double fA[2][AFS_NUM_PM_SECTIONS][LANES], fLen[2][AFS_NUM_PM_SECTIONS][LANES];  // control frames of the interval
   double velum[2][LANES];
   double gctl[2][AFS_NUM_GLOTTIS_CONTROL][LANES];
   double glLen[2][2][LANES], glArea[2][2][LANES];  // glottis geometry, double buffered by step parity
-  double p4[5][LANES];            // pressures of sections 22..25 after the last update, 4 = sink
-  double g3[3][LANES];            // G = L/(dt theta)+R of the dynamic branching sections 28, 40, 64
+  // boundary record of every segment = its LAST section, for the first row of the next segment
+  double bE[NW][LANES], bL[NW][LANES], bR[NW][LANES], bI[NW][LANES], bG[NW][LANES], bD[NW][LANES];
+  double csib[NW][LANES];                        // history term c of the segment's first current (sibling rows)
+  double sepD[NSEP][LANES], sepR[NSEP][LANES], redW[NSEP][LANES];
+  double sideDD[NW][LANES], sideDR[NW][LANES], sideF[NW][LANES];
+  double lf[5][LANES];                           // fossa current 84 folded into the clique {28, 29}
+  double radc[2][2][LANES];                      // radiation pairs folded into currents 64 / 83
+  double uext[NUX][LANES];
+  double p4[4][LANES];            // pressures of sections 22..25 after the last update
   double gx[4][LANES];            // glottis: x0, x1 (current), xp0, xp1 (previous) relative displacements
   double gdim[10][LANES];         // glottis: cached dimensions for the current displacement
   double toneX[4][LANES], toneY[4][LANES];   // skin-radiation filter history
@@ -114,70 +124,51 @@ struct TdsSmem {
   // same for all tracts
   SRec srec[NSX];
   double wallc[4][3];             // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = zeros
-  SlotTab slot[NWS][KD + KS];
+  STab stab[NW];
 };
 
 __device__ __forceinline__ int wall_type(int s) { return s <= TRACHEA_LAST ? 1 : s >= SINUS0 ? 2 : 0; }
-__device__ __forceinline__ bool is_dyn(int s) { return s >= DYN0 && s <= DYN_LAST; }
-// section owned by dynamic slot index dx = 3*warp + k / static slot index t = 3*warp + k (t < 45)
-__device__ __forceinline__ int dyn_slot_section(int dx) { return dx < ND ? DYN0 + dx : dx == DX_69 ? 69 : FOSSA0; }
-__device__ __forceinline__ int stat_slot_section(int t) {
-  return t < 23 ? t : t < 37 ? 70 + (t - 23) : t < 41 ? 85 + (t - 37) : SINUS0 + (t - 41);
-}
-// record index of a section in the per-lane exchange arrays (-1: none)
-__device__ __forceinline__ int dyn_record_of(int s) {
-  return is_dyn(s) ? s - DYN0 : s == 69 ? DX_69 : s == FOSSA0 ? DX_84 : s == TRACHEA_LAST ? DX_22 : -1;
-}
-// source section of current i (TdsModel.cpp:93-131); 93 (dummy) for the current out of the lungs
-__device__ __forceinline__ int src_of(int i) {
-  if (i == 0) return NS;
-  if (i == NOSE0) return PHAR_LAST;
-  if (i == FOSSA0) return PHAR0 + FOSSA_COUPLING;
-  if (i >= SINUS0 && i <= SINUS_LAST) return i == 89 ? 73 : i == 90 ? 74 : i == 91 ? 76 : 77;
-  return i - 1;
-}
-// sibling current at a branching source section, -1 if none
-__device__ __forceinline__ int sibling_of(int i) {
-  switch (i) {
-    case 29: return 84; case 84: return 29;
-    case 41: return 65; case 65: return 41;
-    case 74: return 89; case 89: return 74;
-    case 75: return 90; case 90: return 75;
-    case 77: return 91; case 91: return 77;
-    case 78: return 92; case 92: return 78;
-    default: return -1;
-  }
-}
-// slot in the small sibling table urb[]
-__device__ __forceinline__ int urb_slot(int i) {
-  switch (i) {
-    case 29: return 0; case 84: return 1; case 41: return 2; case 65: return 3;
-    case 74: return 4; case 89: return 5; case 75: return 6; case 90: return 7;
-    case 77: return 8; case 91: return 9; case 78: return 10; case 92: return 11;
-    case 93: return 12; case 94: return 13; case 95: return 14; case 96: return 15;
-    default: return -1;
-  }
-}
-// out-flowing currents of a section (dummy 97 where there is none)
-__device__ __forceinline__ void outs_of(int s, int &o0, int &o1) {
-  o0 = s + 1; o1 = NC;
-  if (s == 28) o1 = 84;
-  else if (s == 40) o1 = 65;
-  else if (s == 64) { o0 = 93; o1 = 94; }
-  else if (s == 83) { o0 = 95; o1 = 96; }
-  else if (s == 73) o1 = 89;
-  else if (s == 74) o1 = 90;
-  else if (s == 76) o1 = 91;
-  else if (s == 77) o1 = 92;
-  else if (s == FOSSA_LAST || s >= SINUS0) o0 = NC;
-}
+__device__ __forceinline__ bool is_dyn(int s) { return s >= GLOT_LO && s <= 68; }
 
-// Recurrent state of one owned section + its in-flowing current (registers).
-// c = u/(dt theta) + (theta1/theta) u' is all that the next step needs of the current's history:
-// H = -L c (TdsModel.cpp:2020) and u'_new = u_new/(dt theta) - c (TdsModel.cpp:2070).
-struct SecState {
-  double p, pr, wc, wcr, wcr2, c;
-};
+// first current / section of a warp's segment, its length
+__device__ __forceinline__ int seg_first(int w) {
+  return w < 8 ? 23 + KD * w : w == W_T0 ? 0 : w == W_T1 ? 8 : w == W_T2 ? 16 : w == W_N1 ? 71 : w == W_N2 ? 76 : FOSSA0;
+}
+// warp that owns the source section of the segment's first current (-1: none)
+__device__ __forceinline__ int seg_prev(int w) {
+  switch (w) {
+    case W_GP: return W_T2; case W_P1: return W_GP; case W_P2: return W_P1; case W_M0: return W_P2;
+    case W_M1: return W_M0; case W_M2: return W_M1; case W_M3: return W_M2; case W_NV: return W_P2;
+    case W_T1: return W_T0; case W_T2: return W_T1; case W_N1: return W_NV; case W_N2: return W_N1;
+    case W_F: return W_GP; default: return -1;
+  }
+}
+// where the currents flowing OUT of the segment's last section are published
+__device__ __forceinline__ int seg_out0(int w) {
+  switch (w) {
+    case W_GP: return W_P1; case W_P1: return W_P2; case W_P2: return W_M0; case W_M0: return W_M1;
+    case W_M1: return W_M2; case W_M2: return W_M3; case W_M3: return UX_RADM; case W_NV: return W_N1;
+    case W_T0: return W_T1; case W_T1: return W_T2; case W_T2: return W_GP; case W_N1: return W_N2;
+    case W_N2: return UX_RADN; default: return UX_ZERO;
+  }
+}
+__device__ __forceinline__ int seg_out1(int w) { return w == W_GP ? W_F : w == W_P2 ? W_NV : UX_ZERO; }
+// separator ids: last current of the segment / separator on its left
+__device__ __forceinline__ int seg_b(int w) {
+  switch (w) {
+    case W_GP: return S28; case W_P1: return S34; case W_P2: return S40; case W_M0: return S46;
+    case W_M1: return S52; case W_M2: return S58; case W_M3: return S64; case W_NV: return S70;
+    case W_T0: return S7; case W_T1: return S15; case W_T2: return S22; case W_N1: return S75;
+    default: return S83;  // W_N2
+  }
+}
+__device__ __forceinline__ int seg_a(int w) {
+  switch (w) {
+    case W_GP: return S22; case W_P1: return S29; case W_P2: return S34; case W_M0: return S41;
+    case W_M1: return S46; case W_M2: return S52; case W_M3: return S58; case W_NV: return S65;
+    case W_T1: return S7; case W_T2: return S15; case W_N1: return S70; default: return S75;  // W_N2
+  }
+}
 
 // ---- fast FP64 reciprocal / sqrt (branch-free) -----------------------------------
 // IEEE division / sqrt compile to ~20-instruction sequences with a slow-path CALL that fences the
@@ -223,338 +214,547 @@ __device__ __forceinline__ void section_elements(double area, double length, boo
   circ = 2.0 * kPi * r;  // 2*sqrt(area*pi)
   L = (kRho * 0.5 * length) * inva;
   const double rmin = glottal ? 0.8 : 1.6;
-  if (r < rmin) {  // elliptical duct, major half-axis rmin (TdsModel.cpp:772-788)
-    const double a = rmin, b = area * (1.0 / (kPi * rmin));
-    const double t = kPi * inva;
-    R = (2.0 * kMu * length) * (a * a + b * b) * (t * t * inva);  // 1/(pi a^3 b^3) = pi^2 / area^3
-  } else {
-    R = (4.0 * kMu * kPi * length) * (inva * inva);
-  }
+  // elliptical duct with major half-axis rmin when r < rmin (TdsModel.cpp:772-788), else circular (a = b = r):
+  // R = 2 mu l (a^2 + b^2) / (pi a^3 b^3) with a b = area / pi
+  const double a = fmax(r, rmin), b = r < rmin ? area * (glottal ? 1.0 / (kPi * 0.8) : 1.0 / (kPi * 1.6)) : r;
+  const double t = kPi * inva;
+  R = (2.0 * kMu * length) * fma(a, a, b * b) * (t * t * inva);  // 1/(pi a^3 b^3) = pi^2 / area^3
 }
-
-
-constexpr int ITEM = LANES * 8;  // bytes per [item] row
 
 // beta of TdsModel.cpp:826-831 with Lw = Mw/surface, Rw = Bw/surface folded in:
 // beta = kalpha*(c1 wc + c2 wc' + c3 wc''), independent of the geometry.
-__device__ __forceinline__ double wall_beta3(const double *w, const SecState &st) {
-  return fma(st.wc, w[0], fma(st.wcr, w[1], st.wcr2 * w[2]));
+__device__ __forceinline__ double wall_beta3(const double *w, double wc, double wcr, double wcr2) {
+  return fma(wc, w[0], fma(wcr, w[1], wcr2 * w[2]));
 }
 
-// ---- phase 1: per-section elements, E and D ----------------------------------
-// Dynamic slot dx (uniform).
-__device__ __forceinline__ void phase1_dyn(const TdsParams &P, TdsSmem &S, int lane, int dx, const SlotTab &T,
-                                           const SecState &st, double ratio, double ratio1, int parity) {
-  double E;
-  const int own = T.own;
-  const double beta = (T.flags & FL_WALL) ? wall_beta3(P.kc[0], st) : 0.0;  // dynamic slots: standard walls or none
-  if (dx < ND) {
-    double area, length;
-    if (dx >= 2 && dx < 42) {  // pharynx / mouth: Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350)
-      const int j = dx - 2;
-      area = ratio1 * S.fA[0][j][lane] + ratio * S.fA[1][j][lane];
-      length = ratio1 * S.fLen[0][j][lane] + ratio * S.fLen[1][j][lane];
-    } else if (dx < 2) {  // glottis sections from the glottis model (Synthesizer.cpp:576-579)
-      area = S.glArea[parity][dx][lane];
-      length = S.glLen[parity][dx][lane];
-    } else {  // velum port: Tube::setVelumOpening (Tube.cpp:402-416)
-      const int j = dx - 42;
-      const double v = ratio1 * S.velum[0][lane] + ratio * S.velum[1][lane];
-      area = v + ((double)(j * j) * (4.24 - v)) / 16.0;
-      length = (11.4 / 11.4) * 0.6;
-    }
-    if (area < kMinArea) area = kMinArea;
-    const double volume = area * length;
-    double L, R, invr, circ;
-    const bool glottal = dx < 2;
-    section_elements(area, length, glottal, L, R, invr, circ);
-    const double C = volume * (1.0 / (kRho * kC * kC));
-    double alpha = 0.0;
-    if (P.soft_walls && !glottal) {  // TdsModel.cpp:805-832
-      double surface = circ * length;
-      if (surface < kMinArea) surface = kMinArea;
-      alpha = surface * P.kalpha[0];
-    }
-    E = P.dtth * fast_rcp(C + alpha);
-    S.E[own][lane] = E; S.L[own][lane] = L; S.R[own][lane] = R; S.invr[own][lane] = invr; S.alpha[own][lane] = alpha;
-    if (T.flags & FL_G3) S.g3[dx == 5 ? 0 : dx == 17 ? 1 : 2][lane] = L * P.idt + R;
-  } else {  // sections 69 and 84: static geometry; E/alpha copies are permanent, but L, R, 1/r live in the arrays the
-            // solver reuses as scratch, so they are refreshed every step
-    E = S.E[own][lane];
-    const SRec &r = S.srec[dx == DX_69 ? 69 : FOSSA0];
-    S.L[own][lane] = r.L; S.R[own][lane] = dx == DX_84 ? r.R0 : r.R1; S.invr[own][lane] = r.invr;
-  }
-  if (dx == 0) {  // per-lane copy of static section 22, the source section of row 23 (same reason)
-    const SRec &r = S.srec[TRACHEA_LAST];
-    S.L[DX_22][lane] = r.L; S.R[DX_22][lane] = r.R1; S.invr[DX_22][lane] = r.invr;
-  }
-  S.D[T.sec][lane] = st.p + P.dtth1 * st.pr - E * beta;  // TdsModel.cpp:988-1008, no flow sources
-}
-
-__device__ __forceinline__ void phase1_stat(const TdsParams &P, TdsSmem &S, int lane, const SlotTab &T, const SecState &st) {
-  const double beta = wall_beta3(S.wallc[T.wall], st);
-  S.D[T.sec][lane] = st.p + P.dtth1 * st.pr - S.srec[T.own].E * beta;
-}
-
-// ---- phase 2: one matrix row (negated: SPD) per owned current -----------------
-// Row of the current flowing from section A into the owned section B (TdsModel.cpp:1916-2034):
-//   diag = E_B + E_A + L_AB/(dt theta) + R_AB,   rhs = L_AB c + L_A c_sibling + [p_lung] - D_B + D_A
-// with c the history term of SecState.  The same formula covers plain, bifurcation and "no source section" rows
-// (dummy zero records); junction inductance / Bernoulli and the glottal losses are added under uniform flags.
-template <bool DYN>
-__device__ __forceinline__ void phase2_row(const TdsParams &P, TdsSmem &S, int lane, const SlotTab &T, const SecState &st,
-                                           int prev, int cur, double psrc, double &gbf) {
-  double E_B, L_B, R_B, E_A, L_A, R_A, ia = 0.0, ib = 0.0;
-  const int fl = T.flags;
-  if (DYN) {
-    const int own = T.own, a = T.aRec;
-    E_B = S.E[own][lane]; L_B = S.L[own][lane]; R_B = S.R[own][lane]; ib = S.invr[own][lane];
-    E_A = S.E[a][lane]; L_A = S.L[a][lane]; R_A = S.R[a][lane]; ia = S.invr[a][lane];
-  } else {
-    const SRec &b = S.srec[T.own], &a = S.srec[T.aRec];
-    E_B = b.E; L_B = b.L; R_B = b.R0;
-    E_A = a.E; L_A = a.L; R_A = a.R1;
-  }
-  const double D_B = S.D[T.sec][lane], D_A = S.D[T.aSec][lane];
-  const double c_sib = (fl & FL_SIB) ? S.urb[T.urbSib][lane] : 0.0;
+// ---- one matrix row (negated: SPD) of a dynamic segment ---------------------------
+// Row of the current flowing from section A into section B (TdsModel.cpp:1916-2034):
+//   diag = E_B + E_A + L_AB/(dt theta) + R_AB,   rhs = L_AB c + L_A c_sibling - D_B + D_A
+// with c = u/(dt theta) + (theta1/theta) u' the history term of the current (H = -L c, TdsModel.cpp:2020).
+// Junction inductance / Bernoulli loss (TdsModel.cpp:1745-1778, 850-877) and the glottal losses (:900-950) are
+// added under warp-uniform flags; uB is the previous solution of this current.
+enum { RF_JUNCTION = 1, RF_GLO = 2, RF_GUP = 4 };
+__device__ __forceinline__ void row_dyn(const TdsParams &P, int fl, double E_A, double L_A, double R_A, double ia,
+                                        double D_A, double E_B, double L_B, double R_B, double ib, double D_B, double c,
+                                        double c_sib, double uB, double &gbf, double &diag, double &rhs) {
   double L_AB = L_A + L_B;
-  if (DYN) {
-    if (fl & (FL_JUNCTION | FL_GLO | FL_GUP)) {
-      const double uB = S.sol[prev][T.sec][lane];
-      if (fl & FL_JUNCTION) {
-        if (P.ilc) L_AB += (8.0 * kRho / (3.0 * kPi * kPi)) * fabs(ia - ib);  // Sondhi (TdsModel.cpp:1745-1778)
-        if (P.turbulence) {  // Bernoulli loss wide -> narrow (TdsModel.cpp:850-877); area_B < area_A <=> ib > ia
-          if (((ib > ia) && (uB > 0)) || ((ib < ia) && (uB < 0))) {
-            const double qa = ia * ia * (1.0 / kPi), qb = ib * ib * (1.0 / kPi);  // 1/area
-            R_A -= uB * (0.5 * kRho) * (qa * qa);
-            R_B += uB * (0.5 * kRho) * (qb * qb);
-          }
-        }
-      } else if (fl & FL_GLO) {  // glottal entrance loss (TdsModel.cpp:900-920)
-        if (uB > 0) {
-          const double qT = ib * ib * (1.0 / kPi), qS = ia * ia * (1.0 / kPi);
-          R_B += P.k_ent * 0.5 * kRho * fabs(uB) * (qT * qT - qS * qS);
-        }
-      } else {  // lower -> upper glottis section (TdsModel.cpp:930-950)
-        const double qS = ia * ia * (1.0 / kPi), qT = ib * ib * (1.0 / kPi);
-        const double target = (qT * P.fsar > qS) ? 1.0 : 0.0;  // area_T < fsar * area_S
-        gbf = 0.8 * gbf + (1.0 - 0.8) * target;
-        if (uB > 0) R_A += gbf * fabs(uB) * 0.5 * kRho * (qT * qT - qS * qS);
-      }
-    }
+  if (fl & RF_JUNCTION) {
+    L_AB = fma(P.k_sondhi, fabs(ia - ib), L_AB);  // Sondhi (TdsModel.cpp:1745-1778); 0 when the option is off
+    // Bernoulli loss wide -> narrow (TdsModel.cpp:850-877); area_B < area_A <=> ib > ia
+    const bool on = ((ib > ia) && (uB > 0)) || ((ib < ia) && (uB < 0));
+    const double qa = ia * ia * (1.0 / kPi), qb = ib * ib * (1.0 / kPi);  // 1/area
+    const double ku = on ? uB * P.k_bern : 0.0;                            // u rho/2, 0 when the option is off
+    R_A = fma(-ku, qa * qa, R_A);
+    R_B = fma(ku, qb * qb, R_B);
+  } else if (fl & RF_GLO) {  // glottal entrance loss (TdsModel.cpp:900-920)
+    const double qT = ib * ib * (1.0 / kPi), qS = ia * ia * (1.0 / kPi);
+    const double ku = uB > 0 ? P.k_ent * 0.5 * kRho * uB : 0.0;
+    R_B = fma(ku, qT * qT - qS * qS, R_B);
+  } else if (fl & RF_GUP) {  // lower -> upper glottis section (TdsModel.cpp:930-950)
+    const double qS = ia * ia * (1.0 / kPi), qT = ib * ib * (1.0 / kPi);
+    const double target = (qT * P.fsar > qS) ? 1.0 : 0.0;  // area_T < fsar * area_S
+    gbf = 0.8 * gbf + (1.0 - 0.8) * target;
+    const double ku = uB > 0 ? gbf * uB * (0.5 * kRho) : 0.0;
+    R_A = fma(ku, qT * qT - qS * qS, R_A);
   }
-  const double diag = E_B + E_A + fma(L_AB, P.idt, R_A + R_B);
-  double rhs = fma(L_AB, st.c, fma(L_A, c_sib, D_A - D_B));
-  if (!DYN) { if (fl & FL_ROW0) rhs += psrc; }
-  S.diag[T.sec][lane] = diag;
-  S.sol[cur][T.sec][lane] = rhs;
+  diag = E_B + E_A + fma(L_AB, P.idt, R_A + R_B);
+  rhs = fma(L_AB, c, fma(L_A, c_sib, D_A - D_B));
+}
+__device__ __forceinline__ int row_flags(int sec) {
+  if (sec == GLOT_LO) return RF_GLO;
+  if (sec == GLOT_UP) return RF_GUP;
+  if (sec > PHAR0 && sec <= MOUTH_LAST && sec != 29 && sec != MOUTH0) return RF_JUNCTION;
+  return 0;
 }
 
-// Rows of the two parallel radiation currents out of section A (TdsModel.cpp:1841-1911):
-// iR through the radiation resistance, iL = iR + 1 through the radiation inductance.
-__device__ __forceinline__ void phase2_radiation(const TdsParams &P, TdsSmem &S, int lane, int A, int iR, double cR,
-                                                 double cL, int cur) {
-  const int iL = iR + 1;
-  double E_A, L_A, R_A, invr;
-  if (A == MOUTH_LAST) { const int d = MOUTH_LAST - DYN0; E_A = S.E[d][lane]; L_A = S.L[d][lane]; R_A = S.R[d][lane]; invr = S.invr[d][lane]; }
-  else { E_A = S.srec[A].E; L_A = S.srec[A].L; R_A = S.srec[A].R1; invr = S.srec[A].invr; }
-  const double D_A = S.D[A][lane];
+// ==================================================================================
+// Dynamic chain warp
+// ==================================================================================
+// Registers of a dynamic segment.  x: last solution u -> rhs -> G = rhs'/pivot -> new solution;
+// y: diag -> T = coupling/pivot; h: spike/pivot.
+struct DRegs {
+  double p[KD], pr[KD], c[KD], x[KD], y[KD], h[KD];
+  double L0, R0, I0, D0;  // record of the first section (its row is assembled after the barrier)
+  double gbf;             // glottalBernoulliFactor (TdsModel.h:241), used by the owner of section 24
+};
+
+struct StepCtx {
+  int n;            // loop iteration: update with the solution of step n-1, rows of step n
+  bool upd, rows;
+  double ratio, ratio1;
+  bool dumping;
+};
+
+__device__ __forceinline__ void dump_section(const TdsParams &P, double *dump, int sec, double p, double pr, double wc,
+                                             double u, double c) {
+  dump[sec] = p; dump[93 + sec] = pr; dump[186 + sec] = wc;
+  dump[279 + sec] = u; dump[376 + sec] = (c - u * P.idt) * P.ith;
+}
+
+// Pass A: state update with the solution of the previous step (TdsModel.cpp:2046-2098), then elements, E, D
+// (:718-1010) and the rows of all currents but the first (:1785-2039) of the new step.
+// V selects the code: 0 = GP (2 glottal + 4 pharynx sections), 1 = pharynx/mouth only, 2 = NV (velum port + 2 rigid
+// nose sections): the kind of every slot is a compile-time constant, the body is branch-free straight-line code
+// (update and rows both on, no state dump); V = -1: generic version with run-time kinds, used for the first and the
+// last iteration and when a state dump is requested.
+enum { GEOM_PM = 0, GEOM_GLOTTIS = 1, GEOM_VELUM = 2, GEOM_RIGID = 3 };
+template <int V>
+__device__ __forceinline__ int slot_geom(int k, int sec) {
+  if (V == 0) return k < 2 ? GEOM_GLOTTIS : GEOM_PM;
+  if (V == 1) return GEOM_PM;
+  if (V == 2) return k < 4 ? GEOM_VELUM : GEOM_RIGID;
+  return sec <= GLOT_UP ? GEOM_GLOTTIS : sec <= MOUTH_LAST ? GEOM_PM : sec <= 68 ? GEOM_VELUM : GEOM_RIGID;
+}
+template <int V>
+__device__ __forceinline__ int slot_row_flags(int k, int sec) {
+  if (V == 0) return k == 1 ? RF_GUP : k >= 3 ? RF_JUNCTION : 0;  // rows 24 | 26, 27, 28 (row 25: plain; row 23 later)
+  if (V == 1) return RF_JUNCTION;                                  // (k >= 1)
+  if (V == 2) return 0;
+  return row_flags(sec);
+}
+template <int V>
+__device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st,
+                                             const StepCtx &X, double *dump) {
+  constexpr bool FAST = V >= 0;
+  const bool upd = FAST ? true : X.upd, rows = FAST ? true : X.rows;
+  const int n0 = 23 + KD * w;
+  double outLast = 0.0;
+  if (upd) outLast = S.uext[seg_out0(w)][lane] + S.uext[seg_out1(w)][lane];
+  double pE = 0.0, pL = 0.0, pR = 0.0, pI = 0.0, pD = 0.0;  // record of the previous slot
+#pragma unroll
+  for (int k = 0; k < KD; k++) {
+    double p_ = st.p[k], pr_ = st.pr[k], c_ = st.c[k];
+    const double u_ = st.x[k], un_ = (k < KD - 1) ? st.x[k + 1] : outLast;
+    double x_ = u_, y_ = 0.0;
+    const int sec = n0 + k, rec = KD * w + k;
+    const int geom = slot_geom<V>(k, sec);
+    const bool wall = geom != GEOM_GLOTTIS;  // (soft walls off: kalpha = kc = 0, the wall state stays 0)
+    double wc = 0.0, wcr = 0.0, wcr2 = 0.0;
+    if (wall) { wc = S.wall[sec][0][lane]; wcr = S.wall[sec][1][lane]; wcr2 = S.wall[sec][2][lane]; }
+    if (upd) {
+      const double u = u_, out = un_;
+      const double E_old = S.Ed[rec][lane], al_old = S.Al[rec][lane];
+      const double beta_old = wall ? wall_beta3(P.kc[0], wc, wcr, wcr2) : 0.0;
+      const double D_old = fma(-E_old, beta_old, fma(P.dtth1, pr_, p_));
+      // current: u' = (u_new - u_old)/(dt theta) - (theta1/theta) u'_old = u_new/(dt theta) - c
+      const double ur = fma(u, P.idt, -c_);
+      c_ = fma(ur, P.th, u * P.idt);
+      const double p_new = fma(E_old, u - out, D_old);
+      const double pr_new = (p_new - p_) * P.idt - pr_ * P.th;
+      p_ = p_new; pr_ = pr_new;
+      if (wall) {
+        const double wc_new = fma(pr_new, al_old, beta_old);
+        const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
+        const double wcr2_new = (wcr_new - wcr) * P.idt - wcr2 * P.th;
+        wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
+        S.wall[sec][0][lane] = wc; S.wall[sec][1][lane] = wcr; S.wall[sec][2][lane] = wcr2;
+      }
+      if (V == 0 ? k < 3 : (V < 0 && sec <= PHAR0)) S.p4[sec - TRACHEA_LAST][lane] = p_new;  // sections 23, 24, 25
+    }
+    if (rows) {
+      double area, length;
+      if (geom == GEOM_PM) {  // Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350)
+        const int j = sec - PHAR0;
+        area = X.ratio1 * S.fA[0][j][lane] + X.ratio * S.fA[1][j][lane];
+        length = X.ratio1 * S.fLen[0][j][lane] + X.ratio * S.fLen[1][j][lane];
+      } else if (geom == GEOM_GLOTTIS) {  // glottis sections from the glottis model (Synthesizer.cpp:576-579)
+        area = S.glArea[X.n & 1][sec - GLOT_LO][lane];
+        length = S.glLen[X.n & 1][sec - GLOT_LO][lane];
+      } else if (geom == GEOM_VELUM) {  // velum port: Tube::setVelumOpening (Tube.cpp:402-416)
+        const int j = sec - NOSE0;
+        const double v = X.ratio1 * S.velum[0][lane] + X.ratio * S.velum[1][lane];
+        area = v + ((double)(j * j) * (4.24 - v)) / 16.0;
+        length = (11.4 / 11.4) * 0.6;
+      } else {  // rigid nose sections 69, 70 (Tube.cpp:155-157)
+        area = sec == 69 ? 4.24 : 3.26;
+        length = (11.4 / 11.4) * 0.6;
+      }
+      area = fmax(area, kMinArea);
+      double L, R, invr, circ;
+      section_elements(area, length, geom == GEOM_GLOTTIS, L, R, invr, circ);
+      const double C = (area * length) * (1.0 / (kRho * kC * kC));
+      double alpha = 0.0;
+      if (wall) alpha = fmax(circ * length, kMinArea) * P.kalpha[0];  // TdsModel.cpp:805-832
+      const double E = P.dtth * fast_rcp(C + alpha);
+      const double beta = wall ? wall_beta3(P.kc[0], wc, wcr, wcr2) : 0.0;
+      const double D = fma(-E, beta, fma(P.dtth1, pr_, p_));  // TdsModel.cpp:988-1008, no flow sources
+      S.Ed[rec][lane] = E; S.Al[rec][lane] = alpha;
+      if (k == 0) {
+        st.L0 = L; st.R0 = R; st.I0 = invr; st.D0 = D;
+        S.csib[w][lane] = c_;
+      } else {
+        row_dyn(P, slot_row_flags<V>(k, sec), pE, pL, pR, pI, pD, E, L, R, invr, D, c_, 0.0, u_, st.gbf, y_, x_);
+      }
+      if (k == KD - 1) {
+        S.bE[w][lane] = E; S.bL[w][lane] = L; S.bR[w][lane] = R; S.bI[w][lane] = invr; S.bD[w][lane] = D;
+        S.bG[w][lane] = fma(L, P.idt, R);
+      }
+      pE = E; pL = L; pR = R; pI = invr; pD = D;
+    }
+    st.p[k] = p_; st.pr[k] = pr_; st.c[k] = c_; st.x[k] = x_; st.y[k] = y_;
+  }
+}
+
+// After the barrier: the first row (its source section belongs to another warp), then elimination of the
+// interior currents towards the last one.  `aown`: the first current is itself a separator (branch heads 29, 41, 65).
+__device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st) {
+  const int pw = seg_prev(w), n0 = 23 + KD * w;
+  const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
+  const double E_A = S.bE[pw][lane], E_0 = S.Ed[KD * w][lane];
+  {
+    const double c_sib = w == W_P1 ? S.csib[W_F][lane] : w == W_M0 ? S.csib[W_NV][lane] : w == W_NV ? S.csib[W_M0][lane] : 0.0;
+    double diag, rhs;
+    row_dyn(P, row_flags(n0), E_A, S.bL[pw][lane], S.bR[pw][lane], S.bI[pw][lane], S.bD[pw][lane], E_0, st.L0, st.R0,
+            st.I0, st.D0, st.c[0], c_sib, st.x[0], st.gbf, diag, rhs);
+    st.y[0] = diag; st.x[0] = rhs;
+  }
+  double f = aown ? -E_0 : -E_A;
+  double dc = aown ? st.y[1] : st.y[0], rc = aown ? st.x[1] : st.x[0];
+  double dda = 0.0, dra = 0.0;
+#pragma unroll
+  for (int k = 0; k < KD - 1; k++) {
+    if (k == 0 && aown) continue;
+    const double o = -S.Ed[KD * w + k][lane];
+    const double dn = st.y[k + 1], rn = st.x[k + 1];
+    const double wv = fast_rcp(dc);
+    const double t = o * wv, h = f * wv;
+    st.y[k] = t; st.x[k] = rc * wv; st.h[k] = h;
+    dda = fma(h, f, dda); dra = fma(h, rc, dra);
+    dc = fma(-t, o, dn);
+    rc = fma(-t, rc, rn);
+    f = -t * f;
+  }
+  const int b = seg_b(w), a = seg_a(w);
+  S.sepD[b][lane] = dc; S.sepR[b][lane] = rc;
+  S.sideF[w][lane] = f;
+  if (aown) { S.sepD[a][lane] = st.y[0] - dda; S.sepR[a][lane] = st.x[0] - dra; }
+  else { S.sideDD[w][lane] = dda; S.sideDR[w][lane] = dra; }
+}
+
+__device__ __forceinline__ void dwarp_back(TdsSmem &S, const int lane, const int w, DRegs &st) {
+  const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
+  const double ub = S.sepR[seg_b(w)][lane], ua = S.sepR[seg_a(w)][lane];
+  st.x[KD - 1] = ub;
+  double un = ub;
+#pragma unroll
+  for (int k = KD - 2; k >= 0; k--) {
+    if (k == 0 && aown) { st.x[0] = ua; continue; }
+    un = fma(-st.y[k], un, fma(-st.h[k], ua, st.x[k]));
+    st.x[k] = un;
+  }
+  S.uext[w][lane] = st.x[0];
+}
+
+// ==================================================================================
+// Static chain warp: ONE instantiation shared by T0, T1, T2, N1, N2 and F (the hot loop has to stay small: the
+// instruction cache is the scarce resource once 16 warps run different code).  Up to KS chain sections, right-
+// aligned in the slot frame (valid slots ks..KS-1, slot k = section base + k), optionally two sinus leaves hanging
+// on the chain slots j0 and j0+1; `fossa`: the piriform fossa 84..88, whose first current 84 is a branch head with a
+// dynamic row and is folded into the clique {28, 29} locally.
+// ==================================================================================
+constexpr int KS = 8;
+struct SCfg {
+  int base, ks, leaf0;  // section of slot 0 (may be virtual), first valid slot (0, 1 or 3), first leaf section
+  bool leaves, n2;      // sinus leaves present; they hang on slots 0, 1 (N2) instead of 5, 6 (N1)
+  bool fossa, head;     // head: the segment starts at the lungs (no source section)
+};
+__device__ __forceinline__ SCfg scfg_of(int w) {
+  SCfg c;
+  c.ks = w == W_T2 ? 1 : (w == W_N1 || w == W_F) ? 3 : 0;
+  c.base = (w == W_T0 ? 0 : w == W_T1 ? 8 : w == W_T2 ? 16 : w == W_N1 ? 71 : w == W_N2 ? 76 : FOSSA0) - c.ks;
+  c.leaves = w == W_N1 || w == W_N2;
+  c.n2 = w != W_N1;  // (warps without leaves: zero leaf constants, any position)
+  c.leaf0 = w == W_N1 ? 89 : 91;
+  c.fossa = w == W_F;
+  c.head = w == W_T0;
+  return c;
+}
+struct SRegs {
+  double p[KS], pr[KS], c[KS], x[KS];
+  double lp[2], lpr[2], lc[2], lx[2];  // sinus leaves
+  double D0;                           // D of the first section (its row is assembled after the barrier)
+  double w84, e28, g28;                // fossa: factors kept between elimination and back substitution
+};
+// value of the first valid slot (ks is 0, 1 or 3)
+__device__ __forceinline__ double first_of(const SCfg &c, const double (&a)[KS]) { return c.ks == 0 ? a[0] : c.ks == 1 ? a[1] : a[3]; }
+__device__ __forceinline__ void set_first(const SCfg &c, double (&a)[KS], double v) {
+  a[0] = c.ks == 0 ? v : a[0]; a[1] = c.ks == 1 ? v : a[1]; a[3] = c.ks == 3 ? v : a[3];
+}
+
+__device__ __forceinline__ double srec_diag(const SRec &A, const SRec &B, double idt) {
+  return B.E + A.E + (A.L + B.L) * idt + A.R1 + B.R0;
+}
+
+// Prologue: pivots of the static rows (lane-uniform arithmetic, every lane computes the same values).  Slots that
+// are not part of the chain keep T = W = H = 0, which makes the branch-free recurrences below skip them.
+__device__ __noinline__ void swarp_build(const TdsParams &P, TdsSmem &S, const int lane, const int w) {
+  const SCfg c = scfg_of(w);
+  const int n0 = c.base + c.ks, j0 = c.n2 ? 0 : 5;
+  const SRec zero{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double d[KS], o[KS];
+  STab T;
+  memset(&T, 0, sizeof T);
+  for (int k = c.ks; k < KS; k++) {
+    const int sec = c.base + k;
+    const SRec B = S.srec[sec];
+    const SRec A = sec == 0 ? zero : S.srec[sec - 1];
+    d[k] = srec_diag(A, B, P.idt);  // (fossa: d[ks] is not used, the row of current 84 is dynamic)
+    o[k] = -B.E;
+  }
+  if (c.leaves) {
+    for (int j = 0; j < 2; j++) {
+      const SRec A = S.srec[c.base + j0 + j], B = S.srec[c.leaf0 + j];
+      const double dl = srec_diag(A, B, P.idt);
+      const double e = A.E, g = e + A.L * P.idt + A.R1, wl = 1.0 / dl;
+      d[j0 + j] -= e * e * wl;
+      d[j0 + j + 1] -= g * g * wl;
+      o[j0 + j] = -e + e * g * wl;
+      T.le[j] = e; T.lg[j] = g; T.lw[j] = wl;
+    }
+  }
+  const int k0 = c.fossa ? c.ks + 1 : c.ks;
+  double f = c.head ? 0.0 : c.fossa ? o[c.ks] : -S.srec[n0 - 1].E;
+  double dc = d[k0], dda = 0.0;
+  for (int k = k0; k < KS - 1; k++) {
+    const double wv = 1.0 / dc;
+    const double t = o[k] * wv, h = f * wv;
+    T.T[k] = t; T.W[k] = wv; T.H[k] = h;
+    dda += h * f;
+    dc = d[k + 1] - t * o[k];
+    f = -t * f;
+  }
+  T.DB = dc; T.FF = f; T.DDA = dda;
+  if (c.fossa) { T.WB = 1.0 / dc; T.CA = dda + f * f * T.WB; }
+  if (lane == 0) S.stab[w] = T;
+  // boundary record of the last section and the constant separator data
+  const SRec last = S.srec[c.base + KS - 1];
+  S.bE[w][lane] = last.E; S.bL[w][lane] = last.L; S.bR[w][lane] = last.R1; S.bI[w][lane] = last.invr;
+  S.bG[w][lane] = last.L * P.idt + last.R1; S.bD[w][lane] = 0.0;
+  if (!c.fossa) {
+    S.sepD[seg_b(w)][lane] = dc;
+    S.sideDD[w][lane] = dda; S.sideF[w][lane] = f; S.sideDR[w][lane] = 0.0;
+  }
+}
+
+// One static section: update with the last solution (TdsModel.cpp:2046-2098), then D of the new step (:988-1008).
+__device__ __forceinline__ void static_section(const TdsParams &P, TdsSmem &S, const int lane, const StepCtx &X, int sec,
+                                               double &p, double &pr, double &c, double u, double out, double &Dnew) {
+  const SRec &r = S.srec[sec];
+  const double *wk = S.wallc[wall_type(sec)];
+  double wc = S.wall[sec][0][lane], wcr = S.wall[sec][1][lane], wcr2 = S.wall[sec][2][lane];
+  const double E = r.E;
+  if (X.upd) {
+    const double beta_old = wall_beta3(wk, wc, wcr, wcr2);
+    const double D_old = fma(-E, beta_old, fma(P.dtth1, pr, p));
+    const double ur = fma(u, P.idt, -c);
+    c = fma(ur, P.th, u * P.idt);
+    const double p_new = fma(E, u - out, D_old);
+    const double pr_new = (p_new - p) * P.idt - pr * P.th;
+    const double wc_new = fma(pr_new, r.alpha, beta_old);
+    const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
+    const double wcr2_new = (wcr_new - wcr) * P.idt - wcr2 * P.th;
+    p = p_new; pr = pr_new; wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
+    S.wall[sec][0][lane] = wc; S.wall[sec][1][lane] = wcr; S.wall[sec][2][lane] = wcr2;
+    if (sec == TRACHEA_LAST) S.p4[0][lane] = p_new;
+  }
+  Dnew = fma(-E, wall_beta3(wk, wc, wcr, wcr2), fma(P.dtth1, pr, p));
+}
+
+__device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, const SCfg &c,
+                                             SRegs &st, const StepCtx &X) {
+  double outLast = 0.0;
+  if (X.upd) outLast = S.uext[seg_out0(w)][lane];
+  const int j0 = c.n2 ? 0 : 5;
+  double dn[KS], dl[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < KS; k++) {
+    dn[k] = 0.0;
+    if (k < c.ks) continue;
+    double out = (k < KS - 1) ? st.x[k + 1] : outLast;
+    if (k == j0) out += st.lx[0];
+    if (k == j0 + 1) out += st.lx[1];
+    static_section(P, S, lane, X, c.base + k, st.p[k], st.pr[k], st.c[k], st.x[k], out, dn[k]);
+  }
+  if (c.leaves) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) static_section(P, S, lane, X, c.leaf0 + j, st.lp[j], st.lpr[j], st.lc[j], st.lx[j], 0.0, dl[j]);
+  }
+  if (X.rows) {
+    // rows of the static currents: constant pivots, only the right-hand side is assembled (the rows of the slots
+    // up to ks are placeholders: slot ks is rewritten after the barrier, the others are not part of the chain)
+    st.D0 = first_of(c, dn);
+#pragma unroll
+    for (int k = KS - 1; k >= 1; k--) {
+      const double LA = S.srec[c.base + k - 1].L, LAB = LA + S.srec[c.base + k].L;
+      double rhs = fma(LAB, st.c[k], dn[k - 1] - dn[k]);
+      if (k == j0 + 1) rhs = fma(LA, st.lc[0], rhs);
+      if (k == j0 + 2) rhs = fma(LA, st.lc[1], rhs);
+      st.x[k] = k > c.ks ? rhs : 0.0;
+    }
+    if (c.leaves) {
+      const double cj0 = c.n2 ? st.c[1] : st.c[6], cj1 = c.n2 ? st.c[2] : st.c[7];
+      const double dj0 = c.n2 ? dn[0] : dn[5], dj1 = c.n2 ? dn[1] : dn[6];
+      const double LA0 = S.srec[c.base + j0].L, LA1 = S.srec[c.base + j0 + 1].L;
+      st.lx[0] = fma(LA0 + S.srec[c.leaf0].L, st.lc[0], fma(LA0, cj0, dj0 - dl[0]));
+      st.lx[1] = fma(LA1 + S.srec[c.leaf0 + 1].L, st.lc[1], fma(LA1, cj1, dj1 - dl[1]));
+    }
+    S.bD[w][lane] = dn[KS - 1];
+    if (c.fossa) S.csib[w][lane] = st.c[3];
+  }
+}
+
+__device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w,
+                                                const SCfg &c, SRegs &st, double psrc) {
+  const int n0 = c.base + c.ks, pw = seg_prev(w);
+  const STab &C = S.stab[w];
+  double d84 = 0.0, r0;
+  {  // first row: the source section belongs to another warp (or is the lung pressure source)
+    const double c0 = first_of(c, st.c);
+    if (c.head) {
+      r0 = fma(S.srec[0].L, c0, psrc - st.D0);
+    } else {
+      const double L_A = S.bL[pw][lane], L_AB = L_A + S.srec[n0].L;
+      const double c_sib = c.fossa ? S.csib[W_P1][lane] : 0.0;
+      r0 = fma(L_AB, c0, fma(L_A, c_sib, S.bD[pw][lane] - st.D0));
+      if (c.fossa) d84 = S.srec[n0].E + S.bE[pw][lane] + fma(L_AB, P.idt, S.bR[pw][lane] + S.srec[n0].R0);
+    }
+    set_first(c, st.x, r0);
+  }
+  {  // sinus leaves into their clique partners (zero constants in the warps without leaves)
+    const double a0 = C.le[0] * C.lw[0] * st.lx[0], b0 = C.lg[0] * C.lw[0] * st.lx[0];
+    const double a1 = C.le[1] * C.lw[1] * st.lx[1], b1 = C.lg[1] * C.lw[1] * st.lx[1];
+    st.x[0] += c.n2 ? a0 : 0.0; st.x[1] += c.n2 ? a1 - b0 : 0.0; st.x[2] -= c.n2 ? b1 : 0.0;
+    st.x[5] += c.n2 ? 0.0 : a0; st.x[6] += c.n2 ? 0.0 : a1 - b0; st.x[7] -= c.n2 ? 0.0 : b1;
+  }
+  double rc = st.x[0], dra = 0.0;
+#pragma unroll
+  for (int k = 0; k < KS - 1; k++) {  // (T = W = H = 0 on the slots that are not interior currents)
+    const double g = rc * C.W[k];
+    dra = fma(C.H[k], rc, dra);
+    rc = fma(-C.T[k], rc, st.x[k + 1]);
+    st.x[k] = g;
+  }
+  st.x[KS - 1] = rc;
+  if (!c.fossa) {
+    S.sepR[seg_b(w)][lane] = rc;
+    S.sideDR[w][lane] = dra;
+  } else {
+    // current 88 into 84, then 84 out of the clique {28, 29, 84} (couplings through section 28)
+    const double r84 = r0 - dra - C.FF * C.WB * rc;
+    const double d84b = d84 - C.CA;
+    const double e = S.bE[pw][lane], g = e + S.bG[pw][lane];
+    const double wv = fast_rcp(d84b);
+    S.lf[0][lane] = e * e * wv;        // pivot of 28
+    S.lf[1][lane] = -e * wv * r84;     // rhs of 28
+    S.lf[2][lane] = g * g * wv;        // pivot of 29
+    S.lf[3][lane] = g * wv * r84;      // rhs of 29
+    S.lf[4][lane] = -e + e * g * wv;   // coupling 28 <-> 29
+    st.x[3] = r84; st.w84 = wv; st.e28 = e; st.g28 = g;
+  }
+}
+
+__device__ __forceinline__ void swarp_back(TdsSmem &S, const int lane, const int w, const SCfg &c, SRegs &st) {
+  const STab &C = S.stab[w];
+  double ua, ub;
+  if (c.fossa) {
+    const double u28 = S.sepR[S28][lane], u29 = S.sepR[S29][lane];
+    ua = (st.x[3] + st.e28 * u28 - st.g28 * u29) * st.w84;
+    ub = (st.x[KS - 1] - C.FF * ua) * C.WB;
+  } else {
+    ub = S.sepR[seg_b(w)][lane];
+    ua = c.head ? 0.0 : S.sepR[seg_a(w)][lane];
+  }
+  st.x[KS - 1] = ub;
+  double un = ub;
+#pragma unroll
+  for (int k = KS - 2; k >= 0; k--) {
+    un = fma(-C.T[k], un, fma(-C.H[k], ua, st.x[k]));
+    st.x[k] = un;
+  }
+  if (c.fossa) st.x[3] = ua;
+  {
+    const double xa0 = c.n2 ? st.x[0] : st.x[5], xm = c.n2 ? st.x[1] : st.x[6], xb1 = c.n2 ? st.x[2] : st.x[7];
+    st.lx[0] = (st.lx[0] + C.le[0] * xa0 - C.lg[0] * xm) * C.lw[0];
+    st.lx[1] = (st.lx[1] + C.le[1] * xm - C.lg[1] * xb1) * C.lw[1];
+  }
+  S.uext[w][lane] = first_of(c, st.x);
+}
+
+// State dump (diagnostics): the caller runs pass A in two halves around it so that x still holds the solution.
+__device__ __forceinline__ void swarp_dump(const TdsParams &P, TdsSmem &S, const int lane, const SCfg &c, const SRegs &st,
+                                           double *dump) {
+  if (lane != 0) return;
+#pragma unroll
+  for (int k = 0; k < KS; k++)
+    if (k >= c.ks) dump_section(P, dump, c.base + k, st.p[k], st.pr[k], S.wall[c.base + k][0][0], st.x[k], st.c[k]);
+  if (c.leaves)
+    for (int j = 0; j < 2; j++) dump_section(P, dump, c.leaf0 + j, st.lp[j], st.lpr[j], S.wall[c.leaf0 + j][0][0], st.lx[j], st.lc[j]);
+}
+__device__ __forceinline__ void dwarp_dump(const TdsParams &P, TdsSmem &S, const int lane, const int w, const DRegs &st,
+                                           double *dump) {
+  if (lane != 0) return;
+#pragma unroll
+  for (int k = 0; k < KD; k++) {
+    const int sec = 23 + KD * w + k;
+    dump_section(P, dump, sec, st.p[k], st.pr[k], S.wall[sec][0][0], st.x[k], st.c[k]);
+  }
+}
+
+// ==================================================================================
+// Radiation loads (warp X2): the two parallel radiation currents out of the mouth (93, 94) and the nostrils (95, 96)
+// ==================================================================================
+struct RadRegs {
+  double c[4], u[4];  // history terms and last solutions of the currents 93..96
+  double keep[2][7];  // factors kept between elimination and back substitution
+};
+// Rows + elimination of one radiation pair (TdsModel.cpp:1841-1911) hanging on the last section of warp pw:
+// iR through the radiation resistance, iL through the radiation inductance.  Contribution to the separator -> radc.
+__device__ __forceinline__ void radiation_eliminate(const TdsParams &P, TdsSmem &S, const int lane, int pw, int q,
+                                                    double cR, double cL, double (&keep)[7]) {
+  const double E_A = S.bE[pw][lane], L_A = S.bL[pw][lane], R_A = S.bR[pw][lane], invr = S.bI[pw][lane];
+  const double D_A = S.bD[pw][lane], G_A = S.bG[pw][lane];
   const double R_rad = (128.0 * kRho * kC / (9.0 * kPi * kPi)) * (invr * invr * (1.0 / kPi));
   const double L_rad = (8.0 * kRho / (3.0 * kPi * kPi)) * invr;
   const double L_AB = L_A + L_rad;
-  S.diag[iR][lane] = E_A + L_A * P.idt + R_A + R_rad;
-  S.sol[cur][iR][lane] = L_A * (cR + cL) + D_A;
-  S.diag[iL][lane] = E_A + L_AB * P.idt + R_A;
-  S.sol[cur][iL][lane] = fma(L_A, cR, L_AB * cL) + D_A;
+  const double dR = E_A + G_A + R_rad, rR = fma(L_A, cR + cL, D_A);
+  const double dL = E_A + fma(L_AB, P.idt, R_A), rL = fma(L_A, cR, L_AB * cL) + D_A;
+  const double e = E_A, g = e + G_A;
+  const double wL = fast_rcp(dL);
+  double dds = e * e * wL, drs = -e * wL * rL;
+  const double dR2 = dR - g * g * wL, rR2 = rR - g * wL * rL;
+  const double o = -e + e * g * wL;
+  const double wR = fast_rcp(dR2);
+  dds += o * o * wR; drs += o * wR * rR2;
+  S.radc[q][0][lane] = dds; S.radc[q][1][lane] = drs;
+  keep[0] = wL; keep[1] = rL; keep[2] = wR; keep[3] = rR2; keep[4] = o; keep[5] = e; keep[6] = g;
 }
-
-// ---- phase 4: update of the recurrent state (TdsModel.cpp:2046-2098) -------------
-template <bool DYN>
-__device__ __forceinline__ void phase4_update(const TdsParams &P, TdsSmem &S, int lane, const SlotTab &T, SecState &st,
-                                              int cur) {
-  const int fl = T.flags;
-  const double u_new = S.sol[cur][T.sec][lane];
-  double out = S.sol[cur][T.out0][lane];  // (dummy zero current for dead ends)
-  if (fl & FL_OUT1) out += S.sol[cur][T.out1][lane];
-  double E, alpha, beta;
-  if (DYN) {
-    E = S.E[T.own][lane]; alpha = S.alpha[T.own][lane];
-    beta = (fl & FL_WALL) ? wall_beta3(P.kc[0], st) : 0.0;
-  } else {
-    const SRec &b = S.srec[T.own];
-    E = b.E; alpha = b.alpha;
-    beta = wall_beta3(S.wallc[T.wall], st);
+__device__ __forceinline__ void radiation_update(const TdsParams &P, const int lane, RadRegs &rr, const StepCtx &X,
+                                                 double *dump) {  // TdsModel.cpp:2063-2072
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const double u = rr.u[j];
+    const double ur = fma(u, P.idt, -rr.c[j]);
+    rr.c[j] = fma(ur, P.th, u * P.idt);
   }
-  const double D = S.D[T.sec][lane];
-  // current: u' = (u_new - u_old)/(dt theta) - (theta1/theta) u'_old = u_new/(dt theta) - c
-  const double ur_new = fma(u_new, P.idt, -st.c);
-  st.c = fma(ur_new, P.th, u_new * P.idt);
-  if (fl & FL_URB) S.urb[T.urbOwn][lane] = st.c;
-  // section
-  const double p_new = fma(E, u_new - out, D);
-  const double pr_new = (p_new - st.p) * P.idt - st.pr * P.th;
-  const double wc_new = fma(pr_new, alpha, beta);
-  const double wcr_new = (wc_new - st.wc) * P.idt - st.wcr * P.th;
-  const double wcr2_new = (wcr_new - st.wcr) * P.idt - st.wcr2 * P.th;
-  st.p = p_new; st.pr = pr_new; st.wc = wc_new; st.wcr = wcr_new; st.wcr2 = wcr2_new;
-  if (fl & FL_P4) S.p4[T.p4][lane] = p_new;
+  if (X.dumping && lane == 0) {
+    for (int j = 0; j < 4; j++) { dump[279 + 93 + j] = rr.u[j]; dump[376 + 93 + j] = (rr.c[j] - rr.u[j] * P.idt) * P.ith; }
+  }
 }
-
-// ---- phase 3: the linear solve (parallel partition) ------------------------------
-// Negated system (SPD).  Couplings: two currents meeting in section s are coupled by -E_s (in/out) or
-// by +E_s + G_s (two outs of a branching section), G_s = L_s/(dt theta) + R_s.  The graph is a tree of
-// 3-cliques, so elimination from the leaves has no fill.  A single warp can only issue one FP64
-// instruction every ~3 cycles (measured), so the 97 unknowns are cut into SEGMENTS that different
-// warps eliminate concurrently (one tract per lane in every warp):
-//   3a  each segment warp eliminates its interior nodes towards its two separator nodes (the coupling
-//       to the left separator travels along as a "spike" f); leaf cliques (sinuses, radiation pairs,
-//       piriform fossa) are folded in by the warp that owns their neighbours or by a leaf warp;
-//   3b  the reduced system over the 11 separators 9,19,28,29,40 | 41,53,64 | 65,75,83 (three short
-//       chains meeting in the velum clique {40,41,65}) is solved by three warps + one junction step;
-//   3c  every segment warp back-substitutes its interior.
-// Per interior node i the forward pass stores T = o_i/d'_i (in diag[]), G = r'_i/d'_i (in sol[]) and
-// H = f_i/d'_i (scratch aliased on the L/R/invr exchange arrays, dead after phase 2).
-
-struct Solver {
-  TdsSmem &S;
-  int lane, cur;
-  double idt;
-  __device__ __forceinline__ double &d(int i) { return S.diag[i][lane]; }
-  __device__ __forceinline__ double &r(int i) { return S.sol[cur][i][lane]; }
-  // scratch aliased on the L/R/invr exchange arrays (3*NDX = 147 contiguous items, dead between phase 2 and
-  // the next phase 1): items 0..96 = H per node, 100..120 = side slots, 124..132 = leaf slots
-  __device__ __forceinline__ double &H(int i) { return (&S.L[0])[i][lane]; }
-  // side slot of a two-sided segment warp: warps 1,2 -> 0,1; 5..9 -> 2..6
-  __device__ __forceinline__ double &side(int w, int k) { return (&S.L[0])[100 + 3 * (w < 3 ? w - 1 : w - 3) + k][lane]; }
-  __device__ __forceinline__ double &leaf(int k) { return (&S.L[0])[124 + k][lane]; }
-  __device__ __forceinline__ double E(int s) const { return is_dyn(s) ? S.E[s - DYN0][lane] : S.srec[s].E; }
-  // G_s of the branching sections: static ones from the table, dynamic ones (28, 40, 64) published in phase 1
-  __device__ __forceinline__ double G(int s) const {
-    return s == 28 ? S.g3[0][lane] : s == 40 ? S.g3[1][lane] : s == 64 ? S.g3[2][lane] : S.srec[s].L * idt + S.srec[s].R1;
-  }
-
-  // Eliminate leaf current c (second out of branching section s) into its clique partners a (in-current of s)
-  // and b (other out-current), both updated IN PLACE.  Returns the modified coupling o(a,b).
-  __device__ __forceinline__ double leaf_in_place(int c, int s, int a, int b) {
-    const double e = E(s), g = e + G(s);
-    const double w = fast_rcp(d(c));
-    d(c) = w;
-    const double rc = r(c);
-    d(a) -= e * e * w;
-    d(b) -= g * g * w;
-    r(a) += e * w * rc;
-    r(b) -= g * w * rc;
-    return -e + e * g * w;
-  }
-  __device__ __forceinline__ void leaf_back(int c, int s, int a, int b) {
-    const double e = E(s), g = e + G(s);
-    r(c) = (r(c) + e * r(a) - g * r(b)) * d(c);
-  }
-
-  // 3a: eliminate `count` interior nodes first, first+dir, ... towards separator b = first + dir*count; a (or -1)
-  // is the separator on the other side.  Link sections ov0s / ov1s carry modified couplings ov0 / ov1.
-  __device__ __forceinline__ void seg_forward(int w_id, int a, int first, int count, int dir, int ov0s, double ov0,
-                                              int ov1s, double ov1) {
-    double f = 0.0;
-    if (a >= 0) { const int ls = dir > 0 ? a : a - 1; f = ls == ov0s ? ov0 : ls == ov1s ? ov1 : -E(ls); }
-    double dc = d(first), rc = r(first), dda = 0.0, dra = 0.0;
-    int i = first;
-#pragma unroll 2
-    for (int j = 0; j < count; j++, i += dir) {
-      const int ls = dir > 0 ? i : i - 1;
-      const double o = ls == ov0s ? ov0 : ls == ov1s ? ov1 : -E(ls);
-      const double dn = d(i + dir), rn = r(i + dir);
-      const double w = fast_rcp(dc);
-      const double t = o * w, h = f * w;
-      d(i) = t; r(i) = rc * w; H(i) = h;
-      dda = fma(h, f, dda); dra = fma(h, rc, dra);
-      dc = fma(-t, o, dn);
-      rc = fma(-t, rc, rn);
-      f = -t * f;
-    }
-    d(i) = dc; r(i) = rc;  // separator b, in place (only this warp touches it in 3a)
-    if (a >= 0) { side(w_id, 0) = dda; side(w_id, 1) = dra; side(w_id, 2) = f; }
-  }
-  // 3c: u_i = G_i - H_i u_a - T_i u_next, walking back from b
-  __device__ __forceinline__ void seg_back(int a, int first, int count, int dir) {
-    const double ua = a >= 0 ? r(a) : 0.0;
-    int i = first + dir * (count - 1);
-    double un = r(i + dir);
-#pragma unroll 2
-    for (int j = 0; j < count; j++, i -= dir) {
-      un = fma(-d(i), un, fma(-H(i), ua, r(i)));
-      r(i) = un;
-    }
-  }
-  // 3b helpers on separators (in place): eliminate x into y over coupling c / recover x from y
-  __device__ __forceinline__ void elim_into(int x, int y, double c) {
-    const double w = fast_rcp(d(x));
-    d(x) = w;
-    const double t = c * w;
-    d(y) -= t * c;
-    r(y) -= t * r(x);
-  }
-  __device__ __forceinline__ void back_from(int x, int y, double c) { r(x) = (r(x) - c * r(y)) * d(x); }
-};
-
-// warp roles in phase 3 (warps W_GLOTTIS = 3 and W_OUTPUT = 4 run the glottis and the output filters)
-enum { R_T0 = 0, R_T1 = 1, R_T2 = 2, R_T4 = 5, R_M1 = 6, R_M2 = 7, R_N1 = 8, R_N2 = 9, R_FOSSA = 10, R_RADM = 11,
-       R_RADN = 12, R_RED_T = 13, R_RED_M = 14, R_RED_N = 15 };
-
-__device__ __forceinline__ void solve_3a(Solver &Z, int warp, double &k0, double &k1) {
-  switch (warp) {
-    case R_T0: Z.seg_forward(warp, -1, 0, 9, +1, -1, 0.0, -1, 0.0); break;    // 0..8   -> 9
-    case R_T1: Z.seg_forward(warp, 9, 10, 9, +1, -1, 0.0, -1, 0.0); break;    // 10..18 -> 19
-    case R_T2: Z.seg_forward(warp, 19, 20, 8, +1, -1, 0.0, -1, 0.0); break;   // 20..27 -> 28
-    case R_T4: Z.seg_forward(warp, 29, 30, 10, +1, -1, 0.0, -1, 0.0); break;  // 30..39 -> 40
-    case R_M1: Z.seg_forward(warp, 41, 42, 11, +1, -1, 0.0, -1, 0.0); break;  // 42..52 -> 53
-    case R_M2: Z.seg_forward(warp, 53, 54, 10, +1, -1, 0.0, -1, 0.0); break;  // 54..63 -> 64
-    case R_N1:  // sinuses 89 (on 73: {73,74}) and 90 (on 74: {74,75}), then 66..74 -> 75
-      k0 = Z.leaf_in_place(89, 73, 73, 74);
-      k1 = Z.leaf_in_place(90, 74, 74, 75);
-      Z.seg_forward(warp, 65, 66, 9, +1, 73, k0, 74, k1);
-      break;
-    case R_N2:  // sinuses 91 (on 76: {76,77}) and 92 (on 77: {77,78}), then 76..82 -> 83
-      k0 = Z.leaf_in_place(91, 76, 76, 77);
-      k1 = Z.leaf_in_place(92, 77, 77, 78);
-      Z.seg_forward(warp, 75, 76, 7, +1, 76, k0, 77, k1);
-      break;
-    case R_FOSSA: {  // fossa chain 88..85 -> 84, then 84 out of the clique {28, 29, 84}
-      Z.seg_forward(warp, -1, 88, 4, -1, -1, 0.0, -1, 0.0);
-      const double e = Z.E(28), g = e + Z.G(28);
-      const double w = fast_rcp(Z.d(84));
-      Z.d(84) = w;
-      const double rc = Z.r(84);
-      Z.leaf(0) = e * e * w;       // dd28
-      Z.leaf(1) = -e * w * rc;     // dr28
-      Z.leaf(2) = g * g * w;       // dd29
-      Z.leaf(3) = g * w * rc;      // dr29
-      Z.leaf(4) = -e + e * g * w;  // o(28,29)
-      break;
-    }
-    case R_RADM:
-    case R_RADN: {  // radiation pair: iL = iR+1 out of {s_in, iR, iL}, then iR; contributions to the separator
-      const int sec = warp == R_RADM ? MOUTH_LAST : NOSE_LAST, iR = warp == R_RADM ? 93 : 95, iL = iR + 1;
-      const double e = Z.E(sec), g = e + Z.G(sec);
-      const double wL = fast_rcp(Z.d(iL));
-      Z.d(iL) = wL;
-      const double rL = Z.r(iL);
-      double dds = e * e * wL, drs = -e * wL * rL;
-      const double dR = Z.d(iR) - g * g * wL, rR = Z.r(iR) - g * wL * rL;
-      const double o = -e + e * g * wL;
-      const double wR = fast_rcp(dR);
-      Z.d(iR) = wR; Z.r(iR) = rR;
-      dds += o * o * wR; drs += o * wR * rR;
-      Z.leaf(warp == R_RADM ? 5 : 7) = dds; Z.leaf(warp == R_RADM ? 6 : 8) = drs;
-      k0 = o;
-      break;
-    }
-    default: break;
+__device__ __forceinline__ void radiation_back(TdsSmem &S, const int lane, RadRegs &rr) {
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const double *kp = rr.keep[q];
+    const double us = S.sepR[q == 0 ? S64 : S83][lane];
+    const double uR = (kp[3] - kp[4] * us) * kp[2];
+    const double uL = (kp[1] + kp[5] * us - kp[6] * uR) * kp[0];
+    rr.u[2 * q] = uR; rr.u[2 * q + 1] = uL;
+    S.uext[UX_RADM + q][lane] = uR + uL;
   }
 }
 
-// 3b: reduced system.  Forward: three separator chains (one warp each), all operands loaded up front and the
-// eliminations done in registers; junction; back.
+// ==================================================================================
+// Reduced system over the separators (three chains + the velum clique)
+// ==================================================================================
 __device__ __forceinline__ void red_elim(double &dx, double rx, double c, double &dy, double &ry) {  // x into y
   const double w = fast_rcp(dx);
   dx = w;
@@ -562,101 +762,101 @@ __device__ __forceinline__ void red_elim(double &dx, double rx, double c, double
   dy = fma(-t, c, dy);
   ry = fma(-t, rx, ry);
 }
-__device__ __forceinline__ void solve_3b_forward(Solver &Z, int warp) {
-  if (warp == R_RED_T) {
-    const double c0 = Z.side(R_T1, 2), c1 = Z.side(R_T2, 2), c2 = Z.leaf(4), c3 = Z.side(R_T4, 2);
-    double d9 = Z.d(9) - Z.side(R_T1, 0), r9 = Z.r(9) - Z.side(R_T1, 1);
-    double d19 = Z.d(19) - Z.side(R_T2, 0), r19 = Z.r(19) - Z.side(R_T2, 1);
-    double d28 = Z.d(28) - Z.leaf(0), r28 = Z.r(28) - Z.leaf(1);
-    double d29 = Z.d(29) - (Z.leaf(2) + Z.side(R_T4, 0)), r29 = Z.r(29) - (Z.leaf(3) + Z.side(R_T4, 1));
-    double d40 = Z.d(40), r40 = Z.r(40);
-    red_elim(d9, r9, c0, d19, r19);
-    red_elim(d19, r19, c1, d28, r28);
-    red_elim(d28, r28, c2, d29, r29);
-    red_elim(d29, r29, c3, d40, r40);
-    Z.d(9) = d9; Z.r(9) = r9; Z.d(19) = d19; Z.r(19) = r19; Z.d(28) = d28; Z.r(28) = r28; Z.d(29) = d29; Z.r(29) = r29;
-    Z.d(40) = d40; Z.r(40) = r40;
-  } else if (warp == R_RED_M) {
-    const double c0 = Z.side(R_M2, 2), c1 = Z.side(R_M1, 2);
-    double d41 = Z.d(41) - Z.side(R_M1, 0), r41 = Z.r(41) - Z.side(R_M1, 1);
-    double d53 = Z.d(53) - Z.side(R_M2, 0), r53 = Z.r(53) - Z.side(R_M2, 1);
-    double d64 = Z.d(64) - Z.leaf(5), r64 = Z.r(64) - Z.leaf(6);
-    red_elim(d64, r64, c0, d53, r53);
-    red_elim(d53, r53, c1, d41, r41);
-    Z.d(64) = d64; Z.r(64) = r64; Z.d(53) = d53; Z.r(53) = r53; Z.d(41) = d41; Z.r(41) = r41;
-  } else if (warp == R_RED_N) {
-    const double c0 = Z.side(R_N2, 2), c1 = Z.side(R_N1, 2);
-    double d65 = Z.d(65) - Z.side(R_N1, 0), r65 = Z.r(65) - Z.side(R_N1, 1);
-    double d75 = Z.d(75) - Z.side(R_N2, 0), r75 = Z.r(75) - Z.side(R_N2, 1);
-    double d83 = Z.d(83) - Z.leaf(7), r83 = Z.r(83) - Z.leaf(8);
+// forward: chain T (7,15,22,28,29,34 -> 40), chain M (64,58,52,46 -> 41), chain N (83,75,70 -> 65)
+__device__ __noinline__ void reduced_forward(TdsSmem &S, const int lane, const int chain) {
+  if (chain == 0) {
+    const double c0 = S.sideF[W_T1][lane], c1 = S.sideF[W_T2][lane], c2 = S.sideF[W_GP][lane], c3 = S.lf[4][lane];
+    const double c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane];
+    double d7 = S.sepD[S7][lane] - S.sideDD[W_T1][lane], r7 = S.sepR[S7][lane] - S.sideDR[W_T1][lane];
+    double d15 = S.sepD[S15][lane] - S.sideDD[W_T2][lane], r15 = S.sepR[S15][lane] - S.sideDR[W_T2][lane];
+    double d22 = S.sepD[S22][lane] - S.sideDD[W_GP][lane], r22 = S.sepR[S22][lane] - S.sideDR[W_GP][lane];
+    double d28 = S.sepD[S28][lane] - S.lf[0][lane], r28 = S.sepR[S28][lane] - S.lf[1][lane];
+    double d29 = S.sepD[S29][lane] - S.lf[2][lane], r29 = S.sepR[S29][lane] - S.lf[3][lane];
+    double d34 = S.sepD[S34][lane] - S.sideDD[W_P2][lane], r34 = S.sepR[S34][lane] - S.sideDR[W_P2][lane];
+    double d40 = S.sepD[S40][lane], r40 = S.sepR[S40][lane];
+    red_elim(d7, r7, c0, d15, r15);
+    red_elim(d15, r15, c1, d22, r22);
+    red_elim(d22, r22, c2, d28, r28);
+    red_elim(d28, r28, c3, d29, r29);
+    red_elim(d29, r29, c4, d34, r34);
+    red_elim(d34, r34, c5, d40, r40);
+    S.redW[S7][lane] = d7; S.sepR[S7][lane] = r7; S.redW[S15][lane] = d15; S.sepR[S15][lane] = r15;
+    S.redW[S22][lane] = d22; S.sepR[S22][lane] = r22; S.redW[S28][lane] = d28; S.sepR[S28][lane] = r28;
+    S.redW[S29][lane] = d29; S.sepR[S29][lane] = r29; S.redW[S34][lane] = d34; S.sepR[S34][lane] = r34;
+    S.redW[S40][lane] = d40; S.sepR[S40][lane] = r40;
+  } else if (chain == 1) {
+    const double c0 = S.sideF[W_M3][lane], c1 = S.sideF[W_M2][lane], c2 = S.sideF[W_M1][lane], c3 = S.sideF[W_M0][lane];
+    double d41 = S.sepD[S41][lane], r41 = S.sepR[S41][lane];
+    double d46 = S.sepD[S46][lane] - S.sideDD[W_M1][lane], r46 = S.sepR[S46][lane] - S.sideDR[W_M1][lane];
+    double d52 = S.sepD[S52][lane] - S.sideDD[W_M2][lane], r52 = S.sepR[S52][lane] - S.sideDR[W_M2][lane];
+    double d58 = S.sepD[S58][lane] - S.sideDD[W_M3][lane], r58 = S.sepR[S58][lane] - S.sideDR[W_M3][lane];
+    double d64 = S.sepD[S64][lane] - S.radc[0][0][lane], r64 = S.sepR[S64][lane] - S.radc[0][1][lane];
+    red_elim(d64, r64, c0, d58, r58);
+    red_elim(d58, r58, c1, d52, r52);
+    red_elim(d52, r52, c2, d46, r46);
+    red_elim(d46, r46, c3, d41, r41);
+    S.redW[S64][lane] = d64; S.sepR[S64][lane] = r64; S.redW[S58][lane] = d58; S.sepR[S58][lane] = r58;
+    S.redW[S52][lane] = d52; S.sepR[S52][lane] = r52; S.redW[S46][lane] = d46; S.sepR[S46][lane] = r46;
+    S.redW[S41][lane] = d41; S.sepR[S41][lane] = r41;
+  } else {
+    const double c0 = S.sideF[W_N2][lane], c1 = S.sideF[W_N1][lane], c2 = S.sideF[W_NV][lane];
+    double d65 = S.sepD[S65][lane], r65 = S.sepR[S65][lane];
+    double d70 = S.sepD[S70][lane] - S.sideDD[W_N1][lane], r70 = S.sepR[S70][lane] - S.sideDR[W_N1][lane];
+    double d75 = S.sepD[S75][lane] - S.sideDD[W_N2][lane], r75 = S.sepR[S75][lane] - S.sideDR[W_N2][lane];
+    double d83 = S.sepD[S83][lane] - S.radc[1][0][lane], r83 = S.sepR[S83][lane] - S.radc[1][1][lane];
     red_elim(d83, r83, c0, d75, r75);
-    red_elim(d75, r75, c1, d65, r65);
-    Z.d(83) = d83; Z.r(83) = r83; Z.d(75) = d75; Z.r(75) = r75; Z.d(65) = d65; Z.r(65) = r65;
+    red_elim(d75, r75, c1, d70, r70);
+    red_elim(d70, r70, c2, d65, r65);
+    S.redW[S83][lane] = d83; S.sepR[S83][lane] = r83; S.redW[S75][lane] = d75; S.sepR[S75][lane] = r75;
+    S.redW[S70][lane] = d70; S.sepR[S70][lane] = r70; S.redW[S65][lane] = d65; S.sepR[S65][lane] = r65;
   }
 }
-// Junction at the velum: clique {40, 41, 65} through section 40.
-__device__ __forceinline__ void solve_velum_junction(Solver &Z) {
-  const double e = Z.E(40), g = e + Z.G(40);
-  const double w65 = fast_rcp(Z.d(65));
-  double d40 = Z.d(40) - e * e * w65;
-  const double d41 = Z.d(41) - g * g * w65;
+// Junction at the velum: clique {40, 41, 65} through section 40 (last section of warp P2).
+__device__ __noinline__ void reduced_junction(TdsSmem &S, const int lane) {
+  const double e = S.bE[W_P2][lane], g = e + S.bG[W_P2][lane];
+  const double r65 = S.sepR[S65][lane], r41i = S.sepR[S41][lane];
+  const double w65 = fast_rcp(S.redW[S65][lane]);
+  double d40 = S.redW[S40][lane] - e * e * w65;
+  const double d41 = S.redW[S41][lane] - g * g * w65;
   const double o = -e + e * g * w65;
-  double r40 = Z.r(40) + e * w65 * Z.r(65);
-  const double r41 = Z.r(41) - g * w65 * Z.r(65);
+  double r40 = S.sepR[S40][lane] + e * w65 * r65;
+  const double r41 = r41i - g * w65 * r65;
   const double w41 = fast_rcp(d41);
   d40 -= o * o * w41;
   r40 -= o * w41 * r41;
   const double u40 = fast_div(r40, d40);
   const double u41 = (r41 - o * u40) * w41;
-  const double u65 = (Z.r(65) + e * u40 - g * u41) * w65;
-  Z.r(40) = u40; Z.r(41) = u41; Z.r(65) = u65;
+  const double u65 = (r65 + e * u40 - g * u41) * w65;
+  S.sepR[S40][lane] = u40; S.sepR[S41][lane] = u41; S.sepR[S65][lane] = u65;
 }
-__device__ __forceinline__ void solve_3b_back(Solver &Z, int warp) {
-  if (warp == R_RED_T) {
-    const double c0 = Z.side(R_T1, 2), c1 = Z.side(R_T2, 2), c2 = Z.leaf(4), c3 = Z.side(R_T4, 2);
-    const double w9 = Z.d(9), w19 = Z.d(19), w28 = Z.d(28), w29 = Z.d(29);
-    const double r9 = Z.r(9), r19 = Z.r(19), r28 = Z.r(28), r29 = Z.r(29), u40 = Z.r(40);
-    const double u29 = (r29 - c3 * u40) * w29;
-    const double u28 = (r28 - c2 * u29) * w28;
-    const double u19 = (r19 - c1 * u28) * w19;
-    const double u9 = (r9 - c0 * u19) * w9;
-    Z.r(29) = u29; Z.r(28) = u28; Z.r(19) = u19; Z.r(9) = u9;
-  } else if (warp == R_RED_M) {
-    const double c0 = Z.side(R_M2, 2), c1 = Z.side(R_M1, 2);
-    const double w53 = Z.d(53), w64 = Z.d(64), r53 = Z.r(53), r64 = Z.r(64), u41 = Z.r(41);
-    const double u53 = (r53 - c1 * u41) * w53;
-    const double u64 = (r64 - c0 * u53) * w64;
-    Z.r(53) = u53; Z.r(64) = u64;
-  } else if (warp == R_RED_N) {
-    const double c0 = Z.side(R_N2, 2), c1 = Z.side(R_N1, 2);
-    const double w75 = Z.d(75), w83 = Z.d(83), r75 = Z.r(75), r83 = Z.r(83), u65 = Z.r(65);
-    const double u75 = (r75 - c1 * u65) * w75;
-    const double u83 = (r83 - c0 * u75) * w83;
-    Z.r(75) = u75; Z.r(83) = u83;
-  }
-}
-__device__ __forceinline__ void solve_3c(Solver &Z, int warp, double k0) {
-  switch (warp) {
-    case R_T0: Z.seg_back(-1, 0, 9, +1); break;
-    case R_T1: Z.seg_back(9, 10, 9, +1); break;
-    case R_T2: Z.seg_back(19, 20, 8, +1); break;
-    case R_T4: Z.seg_back(29, 30, 10, +1); break;
-    case R_M1: Z.seg_back(41, 42, 11, +1); break;
-    case R_M2: Z.seg_back(53, 54, 10, +1); break;
-    case R_N1: Z.seg_back(65, 66, 9, +1); Z.leaf_back(89, 73, 73, 74); Z.leaf_back(90, 74, 74, 75); break;
-    case R_N2: Z.seg_back(75, 76, 7, +1); Z.leaf_back(91, 76, 76, 77); Z.leaf_back(92, 77, 77, 78); break;
-    case R_FOSSA: Z.leaf_back(84, 28, 28, 29); Z.seg_back(-1, 88, 4, -1); break;
-    case R_RADM:
-    case R_RADN: {
-      const int sec = warp == R_RADM ? MOUTH_LAST : NOSE_LAST, iR = warp == R_RADM ? 93 : 95, iL = iR + 1;
-      const double e = Z.E(sec), g = e + Z.G(sec);
-      const double us = Z.r(sec);  // current into the radiating section carries the section's index
-      const double uR = (Z.r(iR) - k0 * us) * Z.d(iR);
-      Z.r(iR) = uR;
-      Z.r(iL) = (Z.r(iL) + e * us - g * uR) * Z.d(iL);
-      break;
-    }
-    default: break;
+__device__ __noinline__ void reduced_back(TdsSmem &S, const int lane, const int chain) {
+  if (chain == 0) {
+    const double c0 = S.sideF[W_T1][lane], c1 = S.sideF[W_T2][lane], c2 = S.sideF[W_GP][lane], c3 = S.lf[4][lane];
+    const double c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane];
+    const double u40 = S.sepR[S40][lane];
+    const double u34 = (S.sepR[S34][lane] - c5 * u40) * S.redW[S34][lane];
+    const double u29 = (S.sepR[S29][lane] - c4 * u34) * S.redW[S29][lane];
+    const double u28 = (S.sepR[S28][lane] - c3 * u29) * S.redW[S28][lane];
+    const double u22 = (S.sepR[S22][lane] - c2 * u28) * S.redW[S22][lane];
+    const double u15 = (S.sepR[S15][lane] - c1 * u22) * S.redW[S15][lane];
+    const double u7 = (S.sepR[S7][lane] - c0 * u15) * S.redW[S7][lane];
+    S.sepR[S34][lane] = u34; S.sepR[S29][lane] = u29; S.sepR[S28][lane] = u28; S.sepR[S22][lane] = u22;
+    S.sepR[S15][lane] = u15; S.sepR[S7][lane] = u7;
+  } else if (chain == 1) {
+    const double c0 = S.sideF[W_M3][lane], c1 = S.sideF[W_M2][lane], c2 = S.sideF[W_M1][lane], c3 = S.sideF[W_M0][lane];
+    const double u41 = S.sepR[S41][lane];
+    const double u46 = (S.sepR[S46][lane] - c3 * u41) * S.redW[S46][lane];
+    const double u52 = (S.sepR[S52][lane] - c2 * u46) * S.redW[S52][lane];
+    const double u58 = (S.sepR[S58][lane] - c1 * u52) * S.redW[S58][lane];
+    const double u64 = (S.sepR[S64][lane] - c0 * u58) * S.redW[S64][lane];
+    S.sepR[S46][lane] = u46; S.sepR[S52][lane] = u52; S.sepR[S58][lane] = u58; S.sepR[S64][lane] = u64;
+  } else {
+    const double c0 = S.sideF[W_N2][lane], c1 = S.sideF[W_N1][lane], c2 = S.sideF[W_NV][lane];
+    const double u65 = S.sepR[S65][lane];
+    const double u70 = (S.sepR[S70][lane] - c2 * u65) * S.redW[S70][lane];
+    const double u75 = (S.sepR[S75][lane] - c1 * u70) * S.redW[S75][lane];
+    const double u83 = (S.sepR[S83][lane] - c0 * u75) * S.redW[S83][lane];
+    S.sepR[S70][lane] = u70; S.sepR[S75][lane] = u75; S.sepR[S83][lane] = u83;
   }
 }
 
@@ -753,6 +953,11 @@ __device__ __forceinline__ void glottis_geometry(const TdsParams &P, const doubl
   len[0] = D.th0;
   len[1] = D.th1;
 }
+__device__ __forceinline__ void glottis_store_dims(TdsSmem &S, int lane, const GlottisDims &GD) {
+  S.gdim[0][lane] = GD.Q; S.gdim[1][lane] = GD.cordLength; S.gdim[2][lane] = GD.th0; S.gdim[3][lane] = GD.th1;
+  S.gdim[4][lane] = GD.ol0; S.gdim[5][lane] = GD.ol1; S.gdim[6][lane] = GD.cl0; S.gdim[7][lane] = GD.cl1;
+  S.gdim[8][lane] = GD.mz0; S.gdim[9][lane] = GD.mz1;
+}
 
 // Direct-form IIR of IirFilter::getOutputSample (IirFilter.cpp:47-65); history x[i] = input i+1 samples
 // ago, kept in shared memory [i][lane].
@@ -774,80 +979,219 @@ __device__ __constant__ double c_tone_a[5] = {5.027640021717718e-007, -7.9955355
 __device__ __constant__ double c_tone_b[5] = {0.0, 3.986308869708467, -5.959669638387298, 3.960408461107104,
                                               -0.987047716233603};
 
-// ---- the kernel -----------------------------------------------------------------
-// Output of the step whose solution sits in sol[buf]: radiated flow (TdsModel.cpp:687-705), pressure
+// Output of the step whose radiated flows sit in uext[]: radiated flow (TdsModel.cpp:687-705), pressure
 // differentiator + Chebyshev low-pass + decimation (Synthesizer.cpp:614-627).  `n_done` = steps finished.
-__device__ __forceinline__ void emit_output(const TdsParams &P, TdsSmem &S, int lane, int buf, int n_done, bool active,
+__device__ __forceinline__ void emit_output(const TdsParams &P, TdsSmem &S, int lane, int n_done, bool active,
                                             int tract, int n_out, double *audio, double *flow, uint32_t &bad) {
-  double u = 0.0;
-  u += S.sol[buf][93][lane]; u += S.sol[buf][94][lane];
-  u += S.sol[buf][95][lane]; u += S.sol[buf][96][lane];
+  double u = S.uext[UX_RADM][lane] + S.uext[UX_RADN][lane];
   if (P.skin) u += iir_step<4>(c_tone_a, c_tone_b, S.toneX, S.toneY, lane, S.p4[3][lane]);
   if (!isfinite(u)) bad |= 1u;
-  const double outP = (u - S.prevFlow[lane]) / P.dt;
+  const double outP = (u - S.prevFlow[lane]) * P.fs;
   S.prevFlow[lane] = u;
   const double filt = iir_step<8>(P.cheb_a, P.cheb_b, S.chebX, S.chebY, lane, outP);
   if (active) {
     if (flow) flow[(size_t)tract * P.total_steps + (n_done - 1)] = u;
-    if ((n_done % P.sr_factor) == 0) audio[(size_t)tract * n_out + (n_done / P.sr_factor - 1)] = (filt * 0.004) / 32767;
+    if ((n_done % P.sr_factor) == 0) audio[(size_t)tract * n_out + (n_done / P.sr_factor - 1)] = filt * (0.004 / 32767);
   }
 }
 
+// ---- the kernel -----------------------------------------------------------------
+struct KArgs {
+  const int32_t *bounds;
+  const afs_tube_frame *tubes;
+  const double *glottis;
+  double *audio, *flow;
+  uint32_t *status;
+  double *dump;
+};
 
-// Slot table entry for dynamic (isDyn) slot index q = 3*warp + k, or static slot index q.
-__device__ void build_slot(const TdsParams &P, bool isDyn, int q, SlotTab &T) {
-  const bool valid = isDyn ? true : q < NSTAT;
-  const int s = isDyn ? dyn_slot_section(q) : (valid ? stat_slot_section(q) : NS);
-  const int A = valid ? src_of(s) : NS;
-  int o0, o1;
-  outs_of(valid ? s : FOSSA_LAST, o0, o1);
-  const int sib = valid ? sibling_of(s) : -1;
-  SlotTab t{};
-  t.sec = (uint8_t)s; t.aSec = (uint8_t)A;
-  t.out0 = (uint8_t)o0; t.out1 = (uint8_t)o1;
-  t.urbOwn = (uint8_t)(valid && urb_slot(s) >= 0 ? urb_slot(s) : 16);
-  t.urbSib = (uint8_t)(sib >= 0 ? urb_slot(sib) : 17);
-  t.p4 = (uint8_t)(valid && s >= TRACHEA_LAST && s <= PHAR0 ? s - TRACHEA_LAST : 4);
-  int fl = valid ? FL_VALID : 0;
-  if (valid && o1 != NC) fl |= FL_OUT1;
-  if (sib >= 0) fl |= FL_SIB;
-  if (valid && urb_slot(s) >= 0) fl |= FL_URB;
-  if (valid && s >= TRACHEA_LAST && s <= PHAR0) fl |= FL_P4;
-  if (isDyn) {
-    t.own = (uint8_t)q;
-    t.aRec = (uint8_t)dyn_record_of(A);
-    t.wall = 0;
-    if (P.soft_walls && s != GLOT_LO && s != GLOT_UP) fl |= FL_WALL;
-    if (s > PHAR0 && s <= MOUTH_LAST && sib < 0) fl |= FL_JUNCTION;
-    if (s == GLOT_LO) fl |= FL_GLO;
-    if (s == GLOT_UP) fl |= FL_GUP;
-    if (s == 28 || s == 40 || s == 64) fl |= FL_G3;
-  } else {
-    t.own = (uint8_t)s;
-    t.aRec = (uint8_t)A;
-    t.wall = (uint8_t)(P.soft_walls && valid ? wall_type(s) : 3);
-    if (s == 0) fl |= FL_ROW0;
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+#ifdef AFS_TDS_TIMING
+#define AFS_TICK(k) do { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } while (0)
+#else
+#define AFS_TICK(k) do { } while (0)
+#endif
+
+// Stages the control frames of interval `interval` (all warps; the caller puts barriers around it).
+__device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const int warp, const afs_tube_frame *my_frames,
+                                               const double *my_glottis, int interval) {
+  for (int item = warp; item < 2 * AFS_NUM_PM_SECTIONS + 2; item += NW) {
+    if (item < 2 * AFS_NUM_PM_SECTIONS) {
+      const int f = item / AFS_NUM_PM_SECTIONS, j = item % AFS_NUM_PM_SECTIONS;
+      const afs_tube_frame *fr = my_frames + interval + f;
+      double a = fr->area_cm2[j];
+      if (a < kMinArea) a = kMinArea;  // Tube::setPharynxMouthGeometry clamps on the way in
+      S.fA[f][j][lane] = a;
+      S.fLen[f][j][lane] = fr->length_cm[j];
+    } else {
+      const int f = item - 2 * AFS_NUM_PM_SECTIONS;
+      double v = my_frames[interval + f].velum_area_cm2;
+      if (v < kMinArea) v = kMinArea;  // Tube::getVelumOpening_cm2 returns the clamped nose[0] area
+      S.velum[f][lane] = v;
+      for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
+        S.gctl[f][c][lane] = my_glottis[(size_t)(interval + f) * AFS_NUM_GLOTTIS_CONTROL + c];
+    }
   }
-  t.flags = (uint16_t)fl;
-  T = t;
 }
 
-__global__ void __launch_bounds__(TDS_THREADS, 1)
-tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const afs_tube_frame *__restrict__ tubes,
-                 const double *__restrict__ glottis, double *__restrict__ audio, double *__restrict__ flow,
-                 uint32_t *__restrict__ status, double *__restrict__ dump) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TdsSmem &S = *reinterpret_cast<TdsSmem *>(smem_raw);
-  const int lane = threadIdx.x & 31;
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+// The time loop, one instantiation per warp role.  All roles execute the same sequence of CTA barriers.
+//   ROLE 0: dynamic chain, 1: static chain, 2: X1 (glottis + output), 3: X2 (radiation loads; noise sources)
+template <int ROLE, int V>
+__device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const KArgs &A, const int lane, const int warp) {
   const int tract_raw = blockIdx.x * P.lanes_per_cta + lane;
   const bool active = lane < P.lanes_per_cta && tract_raw < P.n_tracts;
   const int tract = tract_raw < P.n_tracts ? tract_raw : P.n_tracts - 1;
-  const afs_tube_frame *my_frames = tubes + (size_t)tract * P.n_frames;
-  const double *my_glottis = glottis + (size_t)tract * P.n_frames * AFS_NUM_GLOTTIS_CONTROL;
+  const afs_tube_frame *my_frames = A.tubes + (size_t)tract * P.n_frames;
+  const double *my_glottis = A.glottis + (size_t)tract * P.n_frames * AFS_NUM_GLOTTIS_CONTROL;
   const int n_out = P.total_steps / P.sr_factor;
+  const int T = P.total_steps;
+  uint32_t bad = 0;
 
-  // ---- prologue: static records, slot table, zero state ------------------------
+  DRegs dst;
+  SRegs sst;
+  RadRegs rr;
+  const SCfg scfg = scfg_of(warp);
+  if (ROLE == 0) {
+#pragma unroll
+    for (int k = 0; k < KD; k++) { dst.p[k] = dst.pr[k] = dst.c[k] = dst.x[k] = dst.y[k] = dst.h[k] = 0.0; }
+    dst.L0 = dst.R0 = dst.I0 = dst.D0 = 0.0; dst.gbf = 0.0;
+  }
+  if (ROLE == 1) {
+#pragma unroll
+    for (int k = 0; k < KS; k++) { sst.p[k] = sst.pr[k] = sst.c[k] = sst.x[k] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 2; j++) { sst.lp[j] = sst.lpr[j] = sst.lc[j] = sst.lx[j] = 0.0; }
+    sst.D0 = 0.0; sst.w84 = sst.e28 = sst.g28 = 0.0;
+    swarp_build(P, S, lane, warp);
+  }
+  if (ROLE == 3) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; }
+  }
+  cta_sync();  // static boundary records / pivots visible
+
+  int interval = 0, i0 = 0, i1 = 0;
+  if (T > 0) {
+    i0 = A.bounds[0]; i1 = A.bounds[1];
+    stage_interval(S, lane, warp, my_frames, my_glottis, 0);
+    cta_sync();
+    if (ROLE == 2) {  // glottis geometry of step 0
+      double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
+      for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
+      const GlottisState G{0.0, 0.0, 0.0, 0.0};
+      GlottisDims GD;
+      glottis_geometry(P, ctl, G, len, ar, GD);
+      glottis_store_dims(S, lane, GD);
+      S.glLen[0][0][lane] = len[0]; S.glLen[0][1][lane] = len[1];
+      S.glArea[0][0][lane] = ar[0]; S.glArea[0][1][lane] = ar[1];
+    }
+    cta_sync();
+  }
+#ifdef AFS_TDS_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
+
+  for (int n = 0; n <= T && T > 0; n++) {
+    StepCtx X;
+    X.n = n; X.upd = n > 0; X.rows = n < T;
+    if (X.rows && n == i1) {  // control frames of the next interval (every warp is past its last read of the old ones)
+      interval++;
+      i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
+      stage_interval(S, lane, warp, my_frames, my_glottis, interval);
+      cta_sync();
+    }
+    X.ratio = (double)(n - i0) / (double)(i1 - i0);
+    X.ratio1 = 1.0 - X.ratio;
+    X.dumping = A.dump != nullptr && P.dump_step == n && blockIdx.x == 0;
+    AFS_TICK(0);
+    // ============ pass A: update (step n-1), elements + rows (step n) ============
+    // (state dump requested for this step: update and rows in two separate passes, the dump in between)
+    for (int half = 0; half < (X.dumping ? 2 : 1); half++) {
+      StepCtx Y = X;
+      if (X.dumping) { Y.upd = X.upd && half == 0; Y.rows = X.rows && half == 1; }
+      if (ROLE == 0) dwarp_pass_a<-1>(P, S, lane, warp, dst, Y, A.dump);
+      if (ROLE == 1) swarp_pass_a(P, S, lane, warp, scfg, sst, Y);
+      if (ROLE == 3 && Y.upd) radiation_update(P, lane, rr, Y, A.dump);
+      if (X.dumping && half == 0) {
+        if (ROLE == 0) dwarp_dump(P, S, lane, warp, dst, A.dump);
+        if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
+      }
+    }
+    AFS_TICK(1);
+    cta_sync();
+    AFS_TICK(2);
+    if (ROLE == 2 && n > 0) emit_output(P, S, lane, n, active, tract, n_out, A.audio, A.flow, bad);
+    if (!X.rows) break;
+    // ============ first rows + elimination of the segments || glottis ============
+    if (ROLE == 0) dwarp_eliminate(P, S, lane, warp, dst);
+    if (ROLE == 1) {
+      const double psrc = X.ratio1 * S.gctl[0][G_PRESSURE][lane] + X.ratio * S.gctl[1][G_PRESSURE][lane];
+      swarp_eliminate(P, S, lane, warp, scfg, sst, psrc);
+    }
+    if (ROLE == 3) {
+      radiation_eliminate(P, S, lane, W_M3, 0, rr.c[0], rr.c[1], rr.keep[0]);
+      radiation_eliminate(P, S, lane, W_N2, 1, rr.c[2], rr.c[3], rr.keep[1]);
+    }
+    if (ROLE == 2) {
+      // incTime for this step (pressures of the previous step), then the geometry step n+1 will use
+      double ctl[AFS_NUM_GLOTTIS_CONTROL], p[4], len[2], ar[2];
+      GlottisState G{S.gx[0][lane], S.gx[1][lane], S.gx[2][lane], S.gx[3][lane]};
+      for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = X.ratio1 * S.gctl[0][c][lane] + X.ratio * S.gctl[1][c][lane];
+      for (int c = 0; c < 4; c++) p[c] = S.p4[c][lane];
+      GlottisDims GD;
+      GD.Q = S.gdim[0][lane]; GD.cordLength = S.gdim[1][lane]; GD.th0 = S.gdim[2][lane]; GD.th1 = S.gdim[3][lane];
+      GD.ol0 = S.gdim[4][lane]; GD.ol1 = S.gdim[5][lane]; GD.cl0 = S.gdim[6][lane]; GD.cl1 = S.gdim[7][lane];
+      GD.mz0 = S.gdim[8][lane]; GD.mz1 = S.gdim[9][lane]; GD.mw0 = 0.0; GD.mw1 = 0.0;
+      glottis_inc_time(P, ctl, G, p, GD);
+      const double rn = (double)(n + 1 - i0) / (double)(i1 - i0), rn1 = 1.0 - rn;
+      for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = rn1 * S.gctl[0][c][lane] + rn * S.gctl[1][c][lane];
+      glottis_geometry(P, ctl, G, len, ar, GD);
+      glottis_store_dims(S, lane, GD);
+      S.gx[0][lane] = G.x0; S.gx[1][lane] = G.x1; S.gx[2][lane] = G.xp0; S.gx[3][lane] = G.xp1;
+      const int par = (n + 1) & 1;
+      S.glLen[par][0][lane] = len[0]; S.glLen[par][1][lane] = len[1];
+      S.glArea[par][0][lane] = ar[0]; S.glArea[par][1][lane] = ar[1];
+    }
+    AFS_TICK(3);
+    cta_sync();
+    // ============ reduced system over the separators ============
+    if (warp == W_T0) reduced_forward(S, lane, 0);
+    if (warp == W_T1) reduced_forward(S, lane, 1);
+    if (warp == W_T2) reduced_forward(S, lane, 2);
+    cta_sync();
+    if (warp == W_T0) reduced_junction(S, lane);
+    cta_sync();
+    if (warp == W_T0) reduced_back(S, lane, 0);
+    if (warp == W_T1) reduced_back(S, lane, 1);
+    if (warp == W_T2) reduced_back(S, lane, 2);
+    AFS_TICK(4);
+    cta_sync();
+    AFS_TICK(5);
+    // ============ back substitution inside the segments ============
+    if (ROLE == 0) dwarp_back(S, lane, warp, dst);
+    if (ROLE == 1) swarp_back(S, lane, warp, scfg, sst);
+    if (ROLE == 3) radiation_back(S, lane, rr);
+    AFS_TICK(6);
+    cta_sync();
+    AFS_TICK(7);
+  }
+#ifdef AFS_TDS_TIMING
+  if (A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) A.dump[warp * 8 + k] = (double)tacc[k];
+#endif
+  if (ROLE == 2 && active && A.status) A.status[tract] = bad;
+}
+
+__global__ void __launch_bounds__(TDS_THREADS, 1)
+tds_batch_kernel(const TdsParams P, const KArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TdsSmem &S = *reinterpret_cast<TdsSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  const int pw_ = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+  // role id: the four warps of one SM sub-partition (physical id % 4) run the SAME code (instruction fetch locality)
+  const int warp = (pw_ & 3) * 4 + (pw_ >> 2);
+
+  // ---- prologue: static records, zero state ------------------------------------
   for (int s = threadIdx.x; s < NSX; s += TDS_THREADS) {
     SRec r{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (s < NS && !is_dyn(s)) {
@@ -877,226 +1221,32 @@ tds_batch_kernel(const TdsParams P, const int32_t *__restrict__ bounds, const af
     if (t < 3) v = P.kalpha[t] * (j == 0 ? P.c1[t] : j == 1 ? P.c2[t] : P.c3[t]);
     S.wallc[t][j] = v;
   }
-  if (lane < KD + KS) {
-    const int k = lane;
-    build_slot(P, k < KD, 3 * warp + (k < KD ? k : k - KD), S.slot[warp][k]);
+  for (int i = warp; i < NS * 3; i += NW) (&S.wall[0][0])[i][lane] = 0.0;
+  for (int i = warp; i < 8 * KD; i += NW) { S.Ed[i][lane] = 0.0; S.Al[i][lane] = 0.0; }
+  {
+    const int w = warp;
+    S.bE[w][lane] = 0.0; S.bL[w][lane] = 0.0; S.bR[w][lane] = 0.0; S.bI[w][lane] = 0.0; S.bG[w][lane] = 0.0;
+    S.bD[w][lane] = 0.0; S.csib[w][lane] = 0.0; S.sideDD[w][lane] = 0.0; S.sideDR[w][lane] = 0.0; S.sideF[w][lane] = 0.0;
+    S.sepD[w][lane] = 1.0; S.sepR[w][lane] = 0.0; S.redW[w][lane] = 1.0;  // NSEP == NW
   }
-  for (int i = warp; i < NCX; i += NWS) { S.sol[0][i][lane] = 0.0; S.sol[1][i][lane] = 0.0; if (i < NC) S.diag[i][lane] = 1.0; }
-  for (int i = warp; i < NSX; i += NWS) S.D[i][lane] = 0.0;
   if (warp == 0) {
-    for (int i = 0; i < 18; i++) S.urb[i][lane] = 0.0;
-    for (int i = 0; i < 5; i++) S.p4[i][lane] = 0.0;
+    for (int i = 0; i < NUX; i++) S.uext[i][lane] = 0.0;
+    for (int i = 0; i < 5; i++) S.lf[i][lane] = 0.0;
+    for (int i = 0; i < 4; i++) { S.p4[i][lane] = 0.0; (&S.radc[0][0])[i][lane] = 0.0; }
     for (int i = 0; i < 4; i++) { S.gx[i][lane] = 0.0; S.toneX[i][lane] = 0.0; S.toneY[i][lane] = 0.0; }
     for (int i = 0; i < 8; i++) { S.chebX[i][lane] = 0.0; S.chebY[i][lane] = 0.0; }
     S.prevFlow[lane] = 0.0;
   }
   __syncthreads();
-  // per-lane copies of the static records a dynamic slot reads: 69, 84 (own) and 22 (source of 23)
-  if (warp < 3) {
-    const int s = warp == 0 ? 69 : warp == 1 ? FOSSA0 : TRACHEA_LAST, x = warp == 0 ? DX_69 : warp == 1 ? DX_84 : DX_22;
-    const SRec r = S.srec[s];
-    S.E[x][lane] = r.E; S.L[x][lane] = r.L; S.R[x][lane] = s == FOSSA0 ? r.R0 : r.R1; S.invr[x][lane] = r.invr;
-    S.alpha[x][lane] = r.alpha;
-  }
 
-  // ---- per-thread recurrent state (registers) ----------------------------------
-  SecState dyn[KD], sta[KS];
-#pragma unroll
-  for (int k = 0; k < KD; k++) dyn[k] = SecState{0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int k = 0; k < KS; k++) sta[k] = SecState{0, 0, 0, 0, 0, 0};
-  double cRad[4] = {0.0, 0.0, 0.0, 0.0};  // history terms of the radiation currents 93..96 (warp NWS-1)
-  double gbf = 0.0;                        // glottalBernoulliFactor (owner of section 24)
-  uint32_t bad = 0;
-  const bool has_static = warp < NWS - 1;  // warp 15 owns 68, 69, 84 and the four radiation currents instead
-
-  int interval = -1, i0 = 0, i1 = 0;  // current control interval [i0, i1)
-
-  // Stages the control frames of the next interval (all warps; surrounded by barriers by the caller).
-  auto stage_interval = [&]() {
-    interval++;
-    i0 = bounds[interval]; i1 = bounds[interval + 1];
-    for (int item = warp; item < 2 * AFS_NUM_PM_SECTIONS + 2; item += NWS) {
-      if (item < 2 * AFS_NUM_PM_SECTIONS) {
-        const int f = item / AFS_NUM_PM_SECTIONS, j = item % AFS_NUM_PM_SECTIONS;
-        const afs_tube_frame *fr = my_frames + interval + f;
-        double a = fr->area_cm2[j];
-        if (a < kMinArea) a = kMinArea;  // Tube::setPharynxMouthGeometry clamps on the way in
-        S.fA[f][j][lane] = a;
-        S.fLen[f][j][lane] = fr->length_cm[j];
-      } else {
-        const int f = item - 2 * AFS_NUM_PM_SECTIONS;
-        double v = my_frames[interval + f].velum_area_cm2;
-        if (v < kMinArea) v = kMinArea;  // Tube::getVelumOpening_cm2 returns the clamped nose[0] area
-        S.velum[f][lane] = v;
-        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
-          S.gctl[f][c][lane] = my_glottis[(size_t)(interval + f) * AFS_NUM_GLOTTIS_CONTROL + c];
-      }
-    }
-  };
-  // Phase 1 of step `step` for all owned sections.
-  auto phase1_all = [&](int step) {
-    const double ratio = (double)(step - i0) / (double)(i1 - i0);
-    const double ratio1 = 1.0 - ratio;
-#pragma unroll
-    for (int k = 0; k < KD; k++) phase1_dyn(P, S, lane, 3 * warp + k, S.slot[warp][k], dyn[k], ratio, ratio1, step & 1);
-    if (has_static) {
-#pragma unroll
-      for (int k = 0; k < KS; k++) phase1_stat(P, S, lane, S.slot[warp][KD + k], sta[k]);
-    }
-  };
-
-  if (P.total_steps > 0) {
-    __syncthreads();
-    stage_interval();
-    __syncthreads();
-    if (warp == W_GLOTTIS) {  // glottis geometry of step 0
-      double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
-      for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
-      const GlottisState G{0.0, 0.0, 0.0, 0.0};
-      GlottisDims GD;
-      glottis_geometry(P, ctl, G, len, ar, GD);
-      S.gdim[0][lane] = GD.Q; S.gdim[1][lane] = GD.cordLength; S.gdim[2][lane] = GD.th0; S.gdim[3][lane] = GD.th1;
-      S.gdim[4][lane] = GD.ol0; S.gdim[5][lane] = GD.ol1; S.gdim[6][lane] = GD.cl0; S.gdim[7][lane] = GD.cl1;
-      S.gdim[8][lane] = GD.mz0; S.gdim[9][lane] = GD.mz1;
-      S.glLen[0][0][lane] = len[0]; S.glLen[0][1][lane] = len[1];
-      S.glArea[0][0][lane] = ar[0]; S.glArea[0][1][lane] = ar[1];
-    }
-    __syncthreads();
-    phase1_all(0);
-    __syncthreads();
-  }
-#ifdef AFS_TDS_TIMING
-  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
-#define AFS_TICK(k) do { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } while (0)
-#else
-#define AFS_TICK(k) do { } while (0)
-#endif
-
-  for (int n = 0; n < P.total_steps; n++) {
-    const int cur = n & 1, prev = cur ^ 1;
-    AFS_TICK(0);
-    // ======================= phase 2: matrix rows =============================
-    {
-      const double ratio = (double)(n - i0) / (double)(i1 - i0);
-      const double psrc = (1.0 - ratio) * S.gctl[0][G_PRESSURE][lane] + ratio * S.gctl[1][G_PRESSURE][lane];
-#pragma unroll
-      for (int k = 0; k < KD; k++) phase2_row<true>(P, S, lane, S.slot[warp][k], dyn[k], prev, cur, psrc, gbf);
-      if (has_static) {
-#pragma unroll
-        for (int k = 0; k < KS; k++) phase2_row<false>(P, S, lane, S.slot[warp][KD + k], sta[k], prev, cur, psrc, gbf);
-      } else {
-        phase2_radiation(P, S, lane, MOUTH_LAST, 93, cRad[0], cRad[1], cur);
-        phase2_radiation(P, S, lane, NOSE_LAST, 95, cRad[2], cRad[3], cur);
-      }
-    }
-    AFS_TICK(1);
-    __syncthreads();
-    AFS_TICK(2);
-
-    // ======================= phase 3: solve (+ glottis, + output) =============
-    {
-      Solver Z{S, lane, cur, P.idt};
-      double k0 = 0.0, k1 = 0.0;
-      if (warp == W_GLOTTIS) {
-        // incTime for this step (pressures of the previous step), then the geometry step n+1 will use
-        const double ratio = (double)(n - i0) / (double)(i1 - i0), ratio1 = 1.0 - ratio;
-        double ctl[AFS_NUM_GLOTTIS_CONTROL], p[4], len[2], ar[2];
-        GlottisState G{S.gx[0][lane], S.gx[1][lane], S.gx[2][lane], S.gx[3][lane]};
-        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = ratio1 * S.gctl[0][c][lane] + ratio * S.gctl[1][c][lane];
-        for (int c = 0; c < 4; c++) p[c] = S.p4[c][lane];
-        GlottisDims GD;
-        GD.Q = S.gdim[0][lane]; GD.cordLength = S.gdim[1][lane]; GD.th0 = S.gdim[2][lane]; GD.th1 = S.gdim[3][lane];
-        GD.ol0 = S.gdim[4][lane]; GD.ol1 = S.gdim[5][lane]; GD.cl0 = S.gdim[6][lane]; GD.cl1 = S.gdim[7][lane];
-        GD.mz0 = S.gdim[8][lane]; GD.mz1 = S.gdim[9][lane]; GD.mw0 = 0.0; GD.mw1 = 0.0;
-        glottis_inc_time(P, ctl, G, p, GD);
-        const double rn = (double)(n + 1 - i0) / (double)(i1 - i0), rn1 = 1.0 - rn;
-        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = rn1 * S.gctl[0][c][lane] + rn * S.gctl[1][c][lane];
-        glottis_geometry(P, ctl, G, len, ar, GD);
-        S.gdim[0][lane] = GD.Q; S.gdim[1][lane] = GD.cordLength; S.gdim[2][lane] = GD.th0; S.gdim[3][lane] = GD.th1;
-        S.gdim[4][lane] = GD.ol0; S.gdim[5][lane] = GD.ol1; S.gdim[6][lane] = GD.cl0; S.gdim[7][lane] = GD.cl1;
-        S.gdim[8][lane] = GD.mz0; S.gdim[9][lane] = GD.mz1;
-        S.gx[0][lane] = G.x0; S.gx[1][lane] = G.x1; S.gx[2][lane] = G.xp0; S.gx[3][lane] = G.xp1;
-        S.glLen[prev][0][lane] = len[0]; S.glLen[prev][1][lane] = len[1];
-        S.glArea[prev][0][lane] = ar[0]; S.glArea[prev][1][lane] = ar[1];
-      } else if (warp == W_OUTPUT) {
-        if (n > 0) emit_output(P, S, lane, prev, n, active, tract, n_out, audio, flow, bad);
-      } else {
-        solve_3a(Z, warp, k0, k1);
-      }
-      AFS_TICK(3);
-      __syncthreads();
-      solve_3b_forward(Z, warp);
-      __syncthreads();
-      if (warp == R_RED_T) solve_velum_junction(Z);
-      __syncthreads();
-      solve_3b_back(Z, warp);
-      __syncthreads();
-      solve_3c(Z, warp, k0);
-    }
-    AFS_TICK(4);
-    __syncthreads();
-    AFS_TICK(5);
-
-    // ======================= control frames of the next interval ==============
-    if (n + 1 == i1 && n + 1 < P.total_steps) {
-      stage_interval();
-      __syncthreads();
-    }
-
-    // ======================= phase 4 (update) fused with phase 1 of step n+1 ===
-#pragma unroll
-    for (int k = 0; k < KD; k++) phase4_update<true>(P, S, lane, S.slot[warp][k], dyn[k], cur);
-    if (has_static) {
-#pragma unroll
-      for (int k = 0; k < KS; k++) phase4_update<false>(P, S, lane, S.slot[warp][KD + k], sta[k], cur);
-    } else {  // radiation currents (TdsModel.cpp:2063-2072)
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const double u_new = S.sol[cur][93 + j][lane];
-        const double ur_new = fma(u_new, P.idt, -cRad[j]);
-        cRad[j] = fma(ur_new, P.th, u_new * P.idt);
-      }
-    }
-    if (dump && P.dump_step == n + 1) {  // diagnostics: state of tract 0 after step n+1
-      if (blockIdx.x == 0 && lane == 0) {
-#define AFS_DUMP(T_, st)                                                                        \
-  do {                                                                                          \
-    if ((T_).flags & FL_VALID) {                                                                \
-      const int sec = (T_).sec;                                                       \
-      const double u = S.sol[cur][sec][lane];                                                   \
-      dump[sec] = (st).p; dump[93 + sec] = (st).pr; dump[186 + sec] = (st).wc;                   \
-      dump[279 + sec] = u; dump[376 + sec] = (st).c / P.th - u * P.idt / P.th;                   \
-    }                                                                                           \
-  } while (0)
-#pragma unroll
-        for (int k = 0; k < KD; k++) AFS_DUMP(S.slot[warp][k], dyn[k]);
-#pragma unroll
-        for (int k = 0; k < KS; k++) if (has_static) AFS_DUMP(S.slot[warp][KD + k], sta[k]);
-#undef AFS_DUMP
-        if (!has_static) {
-          for (int j = 0; j < 4; j++) {
-            const double u = S.sol[cur][93 + j][lane];
-            dump[279 + 93 + j] = u; dump[376 + 93 + j] = cRad[j] / P.th - u * P.idt / P.th;
-          }
-        }
-      }
-    }
-    AFS_TICK(6);
-    if (n + 1 < P.total_steps) phase1_all(n + 1);
-    AFS_TICK(7);
-    __syncthreads();
-  }
-#ifdef AFS_TDS_TIMING
-  if (dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) dump[warp * 8 + k] = (double)tacc[k];
-#endif
-  // epilogue: output of the last step
-  if (warp == W_OUTPUT) {
-    if (P.total_steps > 0)
-      emit_output(P, S, lane, (P.total_steps - 1) & 1, P.total_steps, active, tract, n_out, audio, flow, bad);
-    if (active && status) status[tract] = bad;
+  switch (warp) {
+    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, 0>(P, S, A, lane, warp); break;
+    case W_X1: run_role<2, 0>(P, S, A, lane, warp); break;
+    case W_X2: run_role<3, 0>(P, S, A, lane, warp); break;
+    default: run_role<0, 0>(P, S, A, lane, warp); break;
   }
 }
+static_assert(NSEP == NW, "prologue zeroing assumes NSEP == NW");
 
 // ---- host side ------------------------------------------------------------------
 int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, const int32_t *frame_len,
@@ -1121,13 +1271,16 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   P.fossa = o->piriform_fossa; P.ilc = o->inner_length_corrections;
   P.fsar = o->flow_separation_area_ratio;
   P.k_ent = o->glottis_loss_option == AFS_ENTRANCE_LOSS_VAN_DEN_BERG ? 1.375 : 1.0;
+  P.k_sondhi = o->inner_length_corrections ? 8.0 * kRho / (3.0 * kPi * kPi) : 0.0;
+  P.k_bern = o->turbulence_losses ? 0.5 * kRho : 0.0;
   const double dt = 1.0 / fs_tds_hz;
   P.dt = dt; P.dtth = dt * kTheta; P.dtth1 = dt * kTheta1; P.idt = 1.0 / (dt * kTheta); P.th = kTheta1 / kTheta;
+  P.ith = kTheta / kTheta1; P.fs = fs_tds_hz;
   // wall types: standard (Tube.cpp:8-10), trachea (:103-105), sinus (:208-210)
   const double Mw[3] = {2.1, 0.25, 0.0}, Bw[3] = {800.0, 1000.0, 6500.0}, Kw[3] = {84500.0, 84500.0, 84500.0};
   for (int t = 0; t < 3; t++) {
     const double lq = Mw[t] / (dt * dt * kTheta * kTheta), rq = Bw[t] / (dt * kTheta);
-    P.kalpha[t] = 1.0 / (lq + rq + Kw[t]);
+    P.kalpha[t] = o->soft_walls ? 1.0 / (lq + rq + Kw[t]) : 0.0;  // rigid walls: alpha = beta = 0 without branches
     P.c1[t] = lq + rq;
     P.c2[t] = Mw[t] * (kTheta1 / kTheta + 1.0) / (dt * kTheta) + Bw[t] * (kTheta1 / kTheta);
     P.c3[t] = Mw[t] * (kTheta1 / kTheta);
@@ -1161,8 +1314,8 @@ cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tu
                                        (int)sizeof(TdsSmem));  // per device; cheap
   if (e != cudaSuccess) return e;
   const int ctas = (P.n_tracts + P.lanes_per_cta - 1) / P.lanes_per_cta;
-  tds_batch_kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, d_bounds, d_tubes, d_glottis, d_audio, d_flow,
-                                                                  d_status, d_dump);
+  KArgs A{d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, d_dump};
+  tds_batch_kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, A);
   return cudaGetLastError();
 }
 

@@ -3,7 +3,6 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import areafunctionsynthesis_b200 as afs
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)) + "/..")
 from bench import make_tds_batch
 B, T = 4096, 2205
 ctx = afs.Context(0)
@@ -11,9 +10,10 @@ fr, gl = make_tds_batch(B, 1)
 buf = np.zeros(473); ctx.set_state_dump(10**9, buf)
 a, _, _ = ctx.tds_synthesize(fr, gl, [T // 2 + 1], 44100.0, 2)
 steps = (T // 2 + 1) * 2
-names = ["loop top", "P2 compute", "P2 barrier", "P3a seg/glot", "P3 b+c", "P3 end barrier", "P4 update", "P1 next+stage"]
+names = ["top/stage", "passA", "B1 wait", "elim/aux", "reduced", "B5 wait", "back", "B6 wait"]
+roles = ["GP", "P1", "P2", "M0", "M1", "M2", "M3", "NV", "T0", "T1", "N2", "T2", "X1", "F", "X2", "N1"]
 t = buf[:128].reshape(16, 8) / steps
 print("cycles per step, per warp (lane 0 of CTA 0):")
-print("warp " + " ".join(f"{n[:12]:>12s}" for n in names) + "        total")
+print("warp " + " ".join(f"{n[:10]:>10s}" for n in names) + "      total")
 for w in range(16):
-    print(f"{w:4d} " + " ".join(f"{v:12.0f}" for v in t[w]) + f" {t[w].sum():12.0f}")
+    print(f"{roles[w]:>4s} " + " ".join(f"{v:10.0f}" for v in t[w]) + f" {t[w].sum():10.0f}")
