@@ -50,7 +50,10 @@
 
 namespace afs {
 
-constexpr int LANES = 32;
+constexpr int LANES = 28;                     // tracts per CTA = row length of the [item][lane] arrays (224 B).  4096
+                                              // utterances on 148 SMs are 27.7 per SM; hardware lanes 28..31 duplicate
+                                              // lane 27 (same addresses, same values), which keeps 12.5 % of the shared
+                                              // memory free for state
 constexpr int NW = 16;                        // warps per CTA
 constexpr int TDS_THREADS = NW * 32;
 constexpr int KD = 6;                         // sections per dynamic-chain warp
@@ -1038,9 +1041,10 @@ __device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const
 // The time loop, one instantiation per warp role.  All roles execute the same sequence of CTA barriers.
 //   ROLE 0: dynamic chain, 1: static chain, 2: X1 (glottis + output), 3: X2 (radiation loads; noise sources)
 template <int ROLE, int V>
-__device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const KArgs &A, const int lane, const int warp) {
+__device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const KArgs &A, const int lane, const int warp,
+                                         const bool hw_ok) {
   const int tract_raw = blockIdx.x * P.lanes_per_cta + lane;
-  const bool active = lane < P.lanes_per_cta && tract_raw < P.n_tracts;
+  const bool active = hw_ok && lane < P.lanes_per_cta && tract_raw < P.n_tracts;
   const int tract = tract_raw < P.n_tracts ? tract_raw : P.n_tracts - 1;
   const afs_tube_frame *my_frames = A.tubes + (size_t)tract * P.n_frames;
   const double *my_glottis = A.glottis + (size_t)tract * P.n_frames * AFS_NUM_GLOTTIS_CONTROL;
@@ -1189,7 +1193,8 @@ __global__ void __launch_bounds__(TDS_THREADS, 1)
 tds_batch_kernel(const TdsParams P, const KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TdsSmem &S = *reinterpret_cast<TdsSmem *>(smem_raw);
-  const int lane = threadIdx.x & 31;
+  const int hw_lane = threadIdx.x & 31;
+  const int lane = hw_lane < LANES ? hw_lane : LANES - 1;
   const int pw_ = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   // role id: the four warps of one SM sub-partition (physical id % 4) run the SAME code (instruction fetch locality)
   const int warp = (pw_ & 3) * 4 + (pw_ >> 2);
@@ -1243,10 +1248,10 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
   __syncthreads();
 
   switch (warp) {
-    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, 0>(P, S, A, lane, warp); break;
-    case W_X1: run_role<2, 0>(P, S, A, lane, warp); break;
-    case W_X2: run_role<3, 0>(P, S, A, lane, warp); break;
-    default: run_role<0, 0>(P, S, A, lane, warp); break;
+    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, 0>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_X1: run_role<2, 0>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_X2: run_role<3, 0>(P, S, A, lane, warp, hw_lane < LANES); break;
+    default: run_role<0, 0>(P, S, A, lane, warp, hw_lane < LANES); break;
   }
 }
 static_assert(NSEP == NW, "prologue zeroing assumes NSEP == NW");
