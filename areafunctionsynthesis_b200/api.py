@@ -112,9 +112,12 @@ def tl_options_default():
     return o
 
 
-def tds_options_default():
+def tds_options_default(noise=True):
+    """TdsModel::TdsModel() defaults (TdsModel.cpp:35-44); `noise=False` switches generateNoiseSources off."""
     o = TdsOptions()
     load_library().afs_tds_options_default(C.byref(o))
+    if not noise:
+        o.generate_noise_sources = 0
     return o
 
 

@@ -135,7 +135,7 @@ void afs_tds_options_default(afs_tds_options *o) {
   if (!o) return;
   static const double gs[AFS_NUM_GLOTTIS_STATIC] = {1.3, 0.24, 0.06, 0.12, 0.03, 0.1, 0.6, 80000.0, 8000.0,
                                                     240000.0, 24000.0, 25000.0, 0.05, 0.01, 129.0, 125.51};
-  o->turbulence_losses = 1; o->soft_walls = 1; o->generate_noise_sources = 0; o->radiation_from_skin = 1;
+  o->turbulence_losses = 1; o->soft_walls = 1; o->generate_noise_sources = 1; o->radiation_from_skin = 1;
   o->piriform_fossa = 0; o->inner_length_corrections = 1; o->transvelar_coupling = 0;
   o->glottis_loss_option = AFS_STANDARD_ENTRANCE_LOSS; o->flow_separation_area_ratio = 1.0;
   for (int i = 0; i < AFS_NUM_GLOTTIS_STATIC; i++) o->glottis_static[i] = gs[i];
@@ -283,11 +283,9 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   if (opts->glottis_loss_option != AFS_STANDARD_ENTRANCE_LOSS &&
       opts->glottis_loss_option != AFS_ENTRANCE_LOSS_VAN_DEN_BERG)
     return AFS_ERR_UNSUPPORTED;
-  if (opts->generate_noise_sources) return AFS_ERR_UNSUPPORTED;  // noise sources: not on the device path yet
   for (int k = 0; k + 1 < n_frames; k++) if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT;
   if (n_tracts == 0) return AFS_OK;
   if (!d_tubes || !d_glottis || !d_audio) return AFS_ERR_BAD_ARGUMENT;
-  (void)d_seeds;
 
   TdsLaunch L;
   rc = tds_prepare_launch(opts, n_tracts, n_frames, frame_len, fs_tds_hz, sr_factor, ctx->sm_count, &L);
@@ -302,8 +300,8 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
     if ((rc = scratch(ctx, 6, 473 * sizeof(double), &d_dump))) return rc;
     CU(cudaMemsetAsync(d_dump, 0, 473 * sizeof(double), (cudaStream_t)stream));
   }
-  CU(launch_tds(L, (const int32_t *)d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, (double *)d_dump,
-                ctx->dump_step, (cudaStream_t)stream));
+  CU(launch_tds(L, (const int32_t *)d_bounds, d_tubes, d_glottis, d_seeds, d_audio, d_flow, d_status,
+                (double *)d_dump, ctx->dump_step, (cudaStream_t)stream));
   ctx->launches++;
   if (d_dump) {
     CU(cudaMemcpyAsync(ctx->dump_host, d_dump, 473 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));

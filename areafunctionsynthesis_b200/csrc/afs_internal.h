@@ -35,8 +35,8 @@ struct TdsLaunch {
 int tds_prepare_launch(const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
                        double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L);
 cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
-                       const double *d_glottis, double *d_audio, double *d_flow, uint32_t *d_status,
-                       double *d_dump, int dump_step, cudaStream_t stream);
+                       const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
+                       uint32_t *d_status, double *d_dump, int dump_step, cudaStream_t stream);
 size_t tds_smem_bytes();
 
 // ---- probes ------------------------------------------------------------------

@@ -77,6 +77,8 @@ struct TdsParams {
   int n_tracts, n_frames, lanes_per_cta, total_steps, sr_factor;
   int turbulence, soft_walls, skin, fossa, ilc;
   int dump_step;
+  int noise;                        // generate_noise_sources (TdsModel.h:87)
+  double nz_F, nm_a, nm_1a;         // 1 - exp(-2 pi 40 dt) (TdsModel.cpp:1637), exp(-2 pi 500 dt) and 1 - that (:2052)
   double dt, idt, th, dtth, dtth1;  // 1/fs, 1/(dt*theta), theta1/theta, dt*theta, dt*theta1
   double ith, fs;                   // theta/theta1, fs
   double fsar, k_ent;
@@ -112,18 +114,20 @@ struct TdsSmem {
   double glLen[2][2][LANES], glArea[2][2][LANES];  // glottis geometry, double buffered by step parity
   // boundary record of every segment = its LAST section, for the first row of the next segment
   double bE[NW][LANES], bL[NW][LANES], bR[NW][LANES], bI[NW][LANES], bG[NW][LANES], bD[NW][LANES];
-  double csib[NW][LANES];                        // history term c of the segment's first current (sibling rows)
+  double csib[4][LANES];                         // history term c of the branch heads 29, 84, 41, 65 (sibling rows)
   double sepD[NSEP][LANES], sepR[NSEP][LANES], redW[NSEP][LANES];
   double sideDD[NW][LANES], sideDR[NW][LANES], sideF[NW][LANES];
   double lf[5][LANES];                           // fossa current 84 folded into the clique {28, 29}
   double radc[2][2][LANES];                      // radiation pairs folded into currents 64 / 83
   double uext[NUX][LANES];
   double p4[4][LANES];            // pressures of sections 22..25 after the last update
-  double gx[4][LANES];            // glottis: x0, x1 (current), xp0, xp1 (previous) relative displacements
-  double gdim[10][LANES];         // glottis: cached dimensions for the current displacement
-  double toneX[4][LANES], toneY[4][LANES];   // skin-radiation filter history
-  double chebX[8][LANES], chebY[8][LANES];   // output low-pass history
-  double prevFlow[LANES];
+  // noise sources (TdsModel.cpp:1188-1708; warp X2).  Index j = section - 25 for the dipole sources of the
+  // pharynx/mouth sections 25..64, 40 = lips; nmag: j = current - 25 for the currents 25..65, 41 = current 84.
+  double nmag[42][LANES];                        // noiseMagnitude (TdsModel.h:143) of the currents a constriction can feed
+  double namp[41][LANES], ncut[41][LANES], nout[41][LANES];  // currentAmp, cutoff, last filter output (TdsModel.h:101-112)
+  double inc[2][LANES];                          // incisor position of the two control frames
+  uint32_t rng[34][LANES];                       // glibc random() TYPE_3 ring (r[i] = r[i-3] + r[i-31])
+  unsigned char art[AFS_NUM_PM_SECTIONS][LANES]; // articulator of the LEFT control frame (Tube.cpp:452)
   // same for all tracts
   SRec srec[NSX];
   double wallc[4][3];             // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = zeros
@@ -155,6 +159,8 @@ __device__ __forceinline__ int seg_out0(int w) {
     case W_N2: return UX_RADN; default: return UX_ZERO;
   }
 }
+// slot in csib[] of a branch head's segment (P1: 29, F: 84, M0: 41, NV: 65), -1 otherwise
+__device__ __forceinline__ int csib_slot(int w) { return w == W_P1 ? 0 : w == W_F ? 1 : w == W_M0 ? 2 : w == W_NV ? 3 : -1; }
 __device__ __forceinline__ int seg_out1(int w) { return w == W_GP ? W_F : w == W_P2 ? W_NV : UX_ZERO; }
 // separator ids: last current of the segment / separator on its left
 __device__ __forceinline__ int seg_b(int w) {
@@ -239,7 +245,8 @@ __device__ __forceinline__ double wall_beta3(const double *w, double wc, double 
 enum { RF_JUNCTION = 1, RF_GLO = 2, RF_GUP = 4 };
 __device__ __forceinline__ void row_dyn(const TdsParams &P, int fl, double E_A, double L_A, double R_A, double ia,
                                         double D_A, double E_B, double L_B, double R_B, double ib, double D_B, double c,
-                                        double c_sib, double uB, double &gbf, double &diag, double &rhs) {
+                                        double c_sib, double uB, double areaA, double areaB, double &gbf, double &diag,
+                                        double &rhs) {
   double L_AB = L_A + L_B;
   if (fl & RF_JUNCTION) {
     L_AB = fma(P.k_sondhi, fabs(ia - ib), L_AB);  // Sondhi (TdsModel.cpp:1745-1778); 0 when the option is off
@@ -255,7 +262,8 @@ __device__ __forceinline__ void row_dyn(const TdsParams &P, int fl, double E_A, 
     R_B = fma(ku, qT * qT - qS * qS, R_B);
   } else if (fl & RF_GUP) {  // lower -> upper glottis section (TdsModel.cpp:930-950)
     const double qS = ia * ia * (1.0 / kPi), qT = ib * ib * (1.0 / kPi);
-    const double target = (qT * P.fsar > qS) ? 1.0 : 0.0;  // area_T < fsar * area_S
+    const double target = (areaB < P.fsar * areaA) ? 1.0 : 0.0;  // compared on the areas themselves, like the reference:
+                                                                 // the two glottal areas can be equal to the last bit
     gbf = 0.8 * gbf + (1.0 - 0.8) * target;
     const double ku = uB > 0 ? gbf * uB * (0.5 * kRho) : 0.0;
     R_A = fma(ku, qT * qT - qS * qS, R_A);
@@ -286,6 +294,18 @@ struct StepCtx {
   bool upd, rows;
   double ratio, ratio1;
   bool dumping;
+};
+
+// noise sources (warp X2), see noise_scan / noise_sources below
+struct NoiseCons {
+  int valid, nar, kind, up, teeth, lateral;  // nar: narrowest section as pharynx/mouth index, -1 = upper glottis
+  double downF;                              // kind: 0 vocal folds, 1 tongue, 2 lower lip
+};
+struct NoiseRegs {
+  unsigned long long nz;  // sources with a non-zero amplitude
+  int ri;                 // position in the random() ring
+  double lips;            // sample of the lips dipole source (enters all four radiation rows)
+  double nm93, nm94;      // noiseMagnitude of the mouth radiation currents
 };
 
 __device__ __forceinline__ void dump_section(const TdsParams &P, double *dump, int sec, double p, double pr, double wc,
@@ -323,7 +343,7 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
   const int n0 = 23 + KD * w;
   double outLast = 0.0;
   if (upd) outLast = S.uext[seg_out0(w)][lane] + S.uext[seg_out1(w)][lane];
-  double pE = 0.0, pL = 0.0, pR = 0.0, pI = 0.0, pD = 0.0;  // record of the previous slot
+  double pE = 0.0, pL = 0.0, pR = 0.0, pI = 0.0, pD = 0.0, pA = 0.0;  // record of the previous slot
 #pragma unroll
   for (int k = 0; k < KD; k++) {
     double p_ = st.p[k], pr_ = st.pr[k], c_ = st.c[k];
@@ -384,15 +404,15 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       S.Ed[rec][lane] = E; S.Al[rec][lane] = alpha;
       if (k == 0) {
         st.L0 = L; st.R0 = R; st.I0 = invr; st.D0 = D;
-        S.csib[w][lane] = c_;
+        if (csib_slot(w) >= 0) S.csib[csib_slot(w)][lane] = c_;
       } else {
-        row_dyn(P, slot_row_flags<V>(k, sec), pE, pL, pR, pI, pD, E, L, R, invr, D, c_, 0.0, u_, st.gbf, y_, x_);
+        row_dyn(P, slot_row_flags<V>(k, sec), pE, pL, pR, pI, pD, E, L, R, invr, D, c_, 0.0, u_, pA, area, st.gbf, y_, x_);
       }
       if (k == KD - 1) {
         S.bE[w][lane] = E; S.bL[w][lane] = L; S.bR[w][lane] = R; S.bI[w][lane] = invr; S.bD[w][lane] = D;
         S.bG[w][lane] = fma(L, P.idt, R);
       }
-      pE = E; pL = L; pR = R; pI = invr; pD = D;
+      pE = E; pL = L; pR = R; pI = invr; pD = D; pA = area;
     }
     st.p[k] = p_; st.pr[k] = pr_; st.c[k] = c_; st.x[k] = x_; st.y[k] = y_;
   }
@@ -405,11 +425,18 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
   const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
   const double E_A = S.bE[pw][lane], E_0 = S.Ed[KD * w][lane];
   {
-    const double c_sib = w == W_P1 ? S.csib[W_F][lane] : w == W_M0 ? S.csib[W_NV][lane] : w == W_NV ? S.csib[W_M0][lane] : 0.0;
+    const double c_sib = csib_slot(w) >= 0 ? S.csib[csib_slot(w) ^ 1][lane] : 0.0;  // 29 <-> 84, 41 <-> 65
     double diag, rhs;
     row_dyn(P, row_flags(n0), E_A, S.bL[pw][lane], S.bR[pw][lane], S.bI[pw][lane], S.bD[pw][lane], E_0, st.L0, st.R0,
-            st.I0, st.D0, st.c[0], c_sib, st.x[0], st.gbf, diag, rhs);
+            st.I0, st.D0, st.c[0], c_sib, st.x[0], 0.0, 0.0, st.gbf, diag, rhs);
     st.y[0] = diag; st.x[0] = rhs;
+  }
+  if (P.noise) {  // dipole sources of the pharynx/mouth sections: S = -sample (TdsModel.cpp:1936), sample = out * amp
+#pragma unroll
+    for (int k = 0; k < KD; k++) {
+      const int j = n0 + k - PHAR0;
+      if (j >= 0 && j < AFS_NUM_PM_SECTIONS) st.x[k] = fma(S.nout[j][lane], S.namp[j][lane], st.x[k]);
+    }
   }
   double f = aown ? -E_0 : -E_A;
   double dc = aown ? st.y[1] : st.y[0], rc = aown ? st.x[1] : st.x[0];
@@ -434,7 +461,7 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
   else { S.sideDD[w][lane] = dda; S.sideDR[w][lane] = dra; }
 }
 
-__device__ __forceinline__ void dwarp_back(TdsSmem &S, const int lane, const int w, DRegs &st) {
+__device__ __forceinline__ void dwarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st) {
   const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
   const double ub = S.sepR[seg_b(w)][lane], ua = S.sepR[seg_a(w)][lane];
   st.x[KD - 1] = ub;
@@ -446,6 +473,13 @@ __device__ __forceinline__ void dwarp_back(TdsSmem &S, const int lane, const int
     st.x[k] = un;
   }
   S.uext[w][lane] = st.x[0];
+  if (P.noise) {  // noiseMagnitude of the currents 25..65 (TdsModel.cpp:2052-2060)
+#pragma unroll
+    for (int k = 0; k < KD; k++) {
+      const int j = 23 + KD * w + k - PHAR0;
+      if (j >= 0 && j <= 40) S.nmag[j][lane] = fma(P.nm_a, S.nmag[j][lane], P.nm_1a * st.x[k]);
+    }
+  }
 }
 
 // ==================================================================================
@@ -602,7 +636,7 @@ __device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, con
       st.lx[1] = fma(LA1 + S.srec[c.leaf0 + 1].L, st.lc[1], fma(LA1, cj1, dj1 - dl[1]));
     }
     S.bD[w][lane] = dn[KS - 1];
-    if (c.fossa) S.csib[w][lane] = st.c[3];
+    if (c.fossa) S.csib[1][lane] = st.c[3];
   }
 }
 
@@ -617,7 +651,7 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
       r0 = fma(S.srec[0].L, c0, psrc - st.D0);
     } else {
       const double L_A = S.bL[pw][lane], L_AB = L_A + S.srec[n0].L;
-      const double c_sib = c.fossa ? S.csib[W_P1][lane] : 0.0;
+      const double c_sib = c.fossa ? S.csib[0][lane] : 0.0;
       r0 = fma(L_AB, c0, fma(L_A, c_sib, S.bD[pw][lane] - st.D0));
       if (c.fossa) d84 = S.srec[n0].E + S.bE[pw][lane] + fma(L_AB, P.idt, S.bR[pw][lane] + S.srec[n0].R0);
     }
@@ -656,7 +690,8 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
   }
 }
 
-__device__ __forceinline__ void swarp_back(TdsSmem &S, const int lane, const int w, const SCfg &c, SRegs &st) {
+__device__ __forceinline__ void swarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, const SCfg &c,
+                                           SRegs &st) {
   const STab &C = S.stab[w];
   double ua, ub;
   if (c.fossa) {
@@ -674,7 +709,10 @@ __device__ __forceinline__ void swarp_back(TdsSmem &S, const int lane, const int
     un = fma(-C.T[k], un, fma(-C.H[k], ua, st.x[k]));
     st.x[k] = un;
   }
-  if (c.fossa) st.x[3] = ua;
+  if (c.fossa) {
+    st.x[3] = ua;
+    if (P.noise) S.nmag[41][lane] = fma(P.nm_a, S.nmag[41][lane], P.nm_1a * ua);
+  }
   {
     const double xa0 = c.n2 ? st.x[0] : st.x[5], xm = c.n2 ? st.x[1] : st.x[6], xb1 = c.n2 ? st.x[2] : st.x[7];
     st.lx[0] = (st.lx[0] + C.le[0] * xa0 - C.lg[0] * xm) * C.lw[0];
@@ -713,14 +751,14 @@ struct RadRegs {
 // Rows + elimination of one radiation pair (TdsModel.cpp:1841-1911) hanging on the last section of warp pw:
 // iR through the radiation resistance, iL through the radiation inductance.  Contribution to the separator -> radc.
 __device__ __forceinline__ void radiation_eliminate(const TdsParams &P, TdsSmem &S, const int lane, int pw, int q,
-                                                    double cR, double cL, double (&keep)[7]) {
+                                                    double cR, double cL, double lips, double (&keep)[7]) {
   const double E_A = S.bE[pw][lane], L_A = S.bL[pw][lane], R_A = S.bR[pw][lane], invr = S.bI[pw][lane];
   const double D_A = S.bD[pw][lane], G_A = S.bG[pw][lane];
   const double R_rad = (128.0 * kRho * kC / (9.0 * kPi * kPi)) * (invr * invr * (1.0 / kPi));
   const double L_rad = (8.0 * kRho / (3.0 * kPi * kPi)) * invr;
   const double L_AB = L_A + L_rad;
-  const double dR = E_A + G_A + R_rad, rR = fma(L_A, cR + cL, D_A);
-  const double dL = E_A + fma(L_AB, P.idt, R_A), rL = fma(L_A, cR, L_AB * cL) + D_A;
+  const double dR = E_A + G_A + R_rad, rR = fma(L_A, cR + cL, D_A) + lips;  // S = -lipsDipole (TdsModel.cpp:1853)
+  const double dL = E_A + fma(L_AB, P.idt, R_A), rL = fma(L_A, cR, L_AB * cL) + D_A + lips;
   const double e = E_A, g = e + G_A;
   const double wL = fast_rcp(dL);
   double dds = e * e * wL, drs = -e * wL * rL;
@@ -731,14 +769,16 @@ __device__ __forceinline__ void radiation_eliminate(const TdsParams &P, TdsSmem 
   S.radc[q][0][lane] = dds; S.radc[q][1][lane] = drs;
   keep[0] = wL; keep[1] = rL; keep[2] = wR; keep[3] = rR2; keep[4] = o; keep[5] = e; keep[6] = g;
 }
-__device__ __forceinline__ void radiation_update(const TdsParams &P, const int lane, RadRegs &rr, const StepCtx &X,
-                                                 double *dump) {  // TdsModel.cpp:2063-2072
+__device__ __forceinline__ void radiation_update(const TdsParams &P, const int lane, RadRegs &rr, NoiseRegs &nr,
+                                                 const StepCtx &X, double *dump) {  // TdsModel.cpp:2063-2072
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const double u = rr.u[j];
     const double ur = fma(u, P.idt, -rr.c[j]);
     rr.c[j] = fma(ur, P.th, u * P.idt);
   }
+  nr.nm93 = fma(P.nm_a, nr.nm93, P.nm_1a * rr.u[0]);
+  nr.nm94 = fma(P.nm_a, nr.nm94, P.nm_1a * rr.u[1]);
   if (X.dumping && lane == 0) {
     for (int j = 0; j < 4; j++) { dump[279 + 93 + j] = rr.u[j]; dump[376 + 93 + j] = (rr.c[j] - rr.u[j] * P.idt) * P.ith; }
   }
@@ -752,6 +792,223 @@ __device__ __forceinline__ void radiation_back(TdsSmem &S, const int lane, RadRe
     const double uL = (kp[1] + kp[5] * us - kp[6] * uR) * kp[0];
     rr.u[2 * q] = uR; rr.u[2 * q + 1] = uL;
     S.uext[UX_RADM + q][lane] = uR + uL;
+  }
+}
+
+// ==================================================================================
+// Noise sources (warp X2): TdsModel::calcNoiseSources / calcNoiseSample (TdsModel.cpp:1188-1708)
+// ==================================================================================
+// Everything that DECIDES something (which sections form a constriction, where its obstacle is, how many random
+// numbers are drawn) repeats the reference's arithmetic operation by operation (explicit round-to-nearest
+// intrinsics: no FMA contraction, exact divisions), so that the discrete choices and the libc rand() stream are
+// the reference's; amplitudes are smooth functions of the state and follow it to rounding level.
+// glibc srand() (stdlib/random_r.c, TYPE_3): the reference draws from libc rand() (TdsModel.cpp:1690-1696); every
+// tract owns a private generator.
+__device__ __noinline__ void rng_seed(TdsSmem &S, const int lane, uint32_t seed, int &ri) {
+  if (seed == 0) seed = 1;
+  long long r = (int32_t)seed;
+  S.rng[0][lane] = (uint32_t)(int32_t)r;
+  for (int i = 1; i < 31; i++) {
+    const long long hi = r / 127773, lo = r % 127773;
+    long long word = 16807 * lo - 2836 * hi;
+    if (word < 0) word += 2147483647;
+    r = (int32_t)word;
+    S.rng[i][lane] = (uint32_t)(int32_t)r;
+  }
+  for (int i = 31; i < 34; i++) S.rng[i][lane] = S.rng[i - 31][lane];
+  for (int i = 34; i < 344; i++) S.rng[i % 34][lane] = S.rng[(i - 31) % 34][lane] + S.rng[(i - 3) % 34][lane];
+  ri = 310 % 34;  // the oldest value
+}
+__device__ __forceinline__ uint32_t rng_next(TdsSmem &S, const int lane, int &ri) {
+  int i3 = ri + 3, i31 = ri + 31;
+  if (i3 >= 34) i3 -= 34;
+  if (i31 >= 34) i31 -= 34;
+  const uint32_t v = S.rng[i3][lane] + S.rng[i31][lane];
+  S.rng[ri][lane] = v;
+  ri = ri == 33 ? 0 : ri + 1;
+  return v >> 1;
+}
+
+// Tube::interpolate (Tube.cpp:449-466) exactly as the reference rounds it
+__device__ __forceinline__ double nz_lerp(double r1, double a, double r, double b) { return __dadd_rn(__dmul_rn(r1, a), __dmul_rn(r, b)); }
+__device__ __forceinline__ double nz_area(const TdsSmem &S, const int lane, double r, double r1, int j) {
+  const double a = nz_lerp(r1, S.fA[0][j][lane], r, S.fA[1][j][lane]);
+  return a < kMinArea ? kMinArea : a;
+}
+__device__ __forceinline__ double nz_len(const TdsSmem &S, const int lane, double r, double r1, int j) {
+  return nz_lerp(r1, S.fLen[0][j][lane], r, S.fLen[1][j][lane]);
+}
+// widen a constriction around its narrowest section (TdsModel.cpp:1260-1275 and the copies below it)
+__device__ __forceinline__ void nz_expand(const TdsSmem &S, const int lane, double r, double r1, int idx, int artX,
+                                          double minA, int &first, int &last) {
+  const double maxA = __dadd_rn(minA, 0.2);
+  first = last = idx;
+  while ((nz_area(S, lane, r, r1, first) < maxA) && (S.art[first][lane] == artX) && (first > 0)) first--;
+  while ((nz_area(S, lane, r, r1, last) < maxA) && (S.art[last][lane] == artX) && (last < AFS_NUM_PM_SECTIONS - 1)) last++;
+  first++; last--;
+}
+
+// State-independent part: the constrictions of this sample and where their noise sources sit.
+__device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double r, const double r1,
+                                        const afs_tube_frame *fr0, const afs_tube_frame *fr1, NoiseCons (&C)[4]) {
+  constexpr int NPM = AFS_NUM_PM_SECTIONS;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { C[k].valid = 0; C[k].nar = -1; C[k].kind = 0; C[k].up = 0; C[k].teeth = 0; C[k].lateral = 0; C[k].downF = 0.0; }
+  // narrowest tongue and lip sections
+  double minT = 1000000.0, minL = 1000000.0;
+  int iT = -1, iL = -1;
+  for (int j = 0; j < NPM; j++) {
+    const double a = nz_area(S, lane, r, r1, j);
+    const int ar = S.art[j][lane];
+    if ((ar == AFS_TONGUE) && (a < minT)) { minT = a; iT = j; }
+    if ((ar == AFS_LOWER_LIP) && (a < minL)) { minL = a; iL = j; }
+  }
+  int f1 = 0, l1 = -1, f2 = 0, l2 = -1, fL = 0, lL = -1, n2 = -1;
+  bool t1 = false, t2 = false;
+  double a2 = 1000000.0;
+  if (minT < 1.0) { t1 = true; nz_expand(S, lane, r, r1, iT, AFS_TONGUE, minT, f1, l1); }
+  if (t1) {  // a second tongue constriction outside the first (TdsModel.cpp:1310-1372)
+    for (int j = 0; j < NPM; j++) {
+      const double a = nz_area(S, lane, r, r1, j);
+      if ((S.art[j][lane] == AFS_TONGUE) && (a < a2) && ((j < f1) || (j > l1))) { a2 = a; n2 = j; }
+    }
+    if (a2 < 1.0) {
+      nz_expand(S, lane, r, r1, n2, AFS_TONGUE, a2, f2, l2);
+      if ((f2 > l1 + 1) || (l2 < f1 - 1)) t2 = true;
+    }
+  }
+  const bool lipCand = minL < 1.0;
+  if (lipCand) nz_expand(S, lane, r, r1, iL, AFS_LOWER_LIP, minL, fL, lL);
+  // laterality of the tongue constrictions (rare: read from the control frames in global memory)
+  double lat1 = 0.0, lat2 = 0.0;
+  if (t1) for (int i = f1; i <= l1; i++) { const double v = nz_lerp(r1, fr0->laterality[i], r, fr1->laterality[i]); if (v > lat1) lat1 = v; }
+  if (t2) for (int i = f2; i <= l2; i++) { const double v = nz_lerp(r1, fr0->laterality[i], r, fr1->laterality[i]); if (v > lat2) lat2 = v; }
+  // positions (Tube.cpp:329-346): one sequential pass that picks up what the constrictions need
+  const double teeth = nz_lerp(r1, S.inc[0][lane], r, S.inc[1][lane]);
+  double pos = 0.0;
+  bool have15 = false, haveT = false;
+  int s15 = -1, sT = -1;
+  double p15 = 0.0, e15 = 1.0, pT = 0.0, eT = 1.0;
+  double pL1 = 0.0, eL1 = 0.0, pN1 = 0.0, eN1 = 1.0, pL2 = 0.0, eL2 = 0.0, pN2 = 0.0, eN2 = 1.0, pLL = 0.0, eLL = 1.0, pNL = 0.0;
+  for (int j = 0; j < NPM; j++) {
+    const double len = nz_len(S, lane, r, r1, j);
+    const double end = __dadd_rn(pos, len);
+    if (!have15 && (pos <= 1.5) && (end >= 1.5)) { have15 = true; s15 = j; p15 = pos; e15 = len; }
+    if (!haveT && (pos <= teeth) && (end >= teeth)) { haveT = true; sT = j; pT = pos; eT = len; }
+    if (j == l1) { pL1 = pos; eL1 = len; }
+    if (j == l1 + 1) { pN1 = pos; eN1 = len; }
+    if (j == l2) { pL2 = pos; eL2 = len; }
+    if (j == l2 + 1) { pN2 = pos; eN2 = len; }
+    if (j == lL) { pLL = pos; eLL = len; }
+    if (j == lL + 1) pNL = pos;
+    pos = end;
+  }
+  // constriction 0: the glottis, obstacle 1.5 cm downstream (TdsModel.cpp:1222-1229)
+  if (have15) {
+    C[0].valid = 1; C[0].nar = -1; C[0].kind = 0; C[0].up = s15;
+    C[0].downF = __ddiv_rn(__dsub_rn(1.5, p15), e15);
+  }
+  double minTongueAreaForTeeth = 1000000.0;
+  // tongue constrictions: the jet hits the teeth when they are closer than 2 cm, else the next section
+  auto tongue = [&](NoiseCons &c, int nar, double aNar, int last, double pL, double eL, double pN, double eN, double lat) {
+    const double jetPos = __dadd_rn(pL, eL);
+    double x, p, e;
+    int sec;
+    bool ok;
+    if (__dsub_rn(teeth, jetPos) < 2.0) {
+      x = teeth; sec = sT; p = pT; e = eT; ok = haveT;
+      minTongueAreaForTeeth = aNar;
+    } else {
+      x = __dadd_rn(pN, __dmul_rn(0.5, eN)); sec = last + 1; p = pN; e = eN; ok = true;  // (inside section last+1)
+    }
+    c.valid = ok ? 1 : 0; c.nar = nar; c.kind = 1; c.up = sec;
+    c.downF = __ddiv_rn(__dsub_rn(x, p), e);
+    c.teeth = fabs(__dsub_rn(x, teeth)) < 0.0001 ? 1 : 0;
+    c.lateral = lat > 0.1 ? 1 : 0;
+  };
+  if (t1) tongue(C[1], iT, minT, l1, pL1, eL1, pN1, eN1, lat1);
+  if (t2) tongue(C[2], n2, a2, l2, pL2, eL2, pN2, eN2, lat2);
+  // lip constriction (TdsModel.cpp:1380-1418): the obstacle is the downstream end of its last section
+  if (lipCand && (minL < minTongueAreaForTeeth)) {
+    C[3].valid = 1; C[3].nar = iL; C[3].kind = 2; C[3].up = lL;
+    C[3].downF = __ddiv_rn(__dsub_rn(pNL, pLL), eLL);
+  }
+}
+
+// State-dependent part: target amplitudes from the flow through the constrictions (TdsModel.cpp:1430-1612), then
+// one sample of every source that is not silent (TdsModel.cpp:1630-1708).
+__device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const int lane, NoiseRegs &N,
+                                           const NoiseCons (&C)[4], const double r, const double r1, const int par,
+                                           const double asp_dB) {
+  int tIdx[8];
+  double tAmp[8], tCut[8];
+  unsigned long long todo = N.nz;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    tIdx[2 * k] = -1; tIdx[2 * k + 1] = -1; tAmp[2 * k] = tAmp[2 * k + 1] = 0.0; tCut[2 * k] = tCut[2 * k + 1] = 0.0;
+    if (!C[k].valid) continue;
+    const int nar = C[k].nar;
+    double A, flow = 0.0;
+    if (nar < 0) {
+      A = S.glArea[par][1][lane];
+      flow += S.nmag[0][lane];
+    } else {
+      A = nz_area(S, lane, r, r1, nar);
+      if (nar == AFS_NUM_PM_SECTIONS - 1) { flow += N.nm93; flow += N.nm94; }
+      else {
+        flow += S.nmag[nar + 1][lane];
+        if (nar == 3) flow += S.nmag[41][lane];   // section 28: currents 29 and 84
+        if (nar == 15) flow += S.nmag[40][lane];  // section 40: currents 41 and 65
+      }
+    }
+    if (A < kMinArea) A = kMinArea;
+    if (A < 0.1) A = 0.1;
+    if (flow < 0.0) flow = 0.0;
+    const double v = flow / A;
+    double gain, cutoff = 6000.0;
+    if (C[k].kind == 2) gain = 2.0e-7;
+    else if (C[k].kind == 0) gain = 0.5e-7 * pow(10.0, asp_dB / 20.0);
+    else {
+      const double d = sqrt(4.0 * A / kPi);
+      cutoff = 0.15 * v / d;
+      gain = C[k].teeth ? 10.0e-7 : 5.0e-7;
+    }
+    double fullAmp = gain * fabs(v) * v * v * sqrt(A);
+    if (C[k].lateral) fullAmp = 0.0;
+    if (cutoff < 50.0) cutoff = 50.0;
+    if (cutoff > 2000.0) cutoff = 2000.0;
+    const int up = C[k].up, down = up < AFS_NUM_PM_SECTIONS - 1 ? up + 1 : AFS_NUM_PM_SECTIONS;
+    tIdx[2 * k] = up; tAmp[2 * k] = (1.0 - C[k].downF) * fullAmp; tCut[2 * k] = cutoff;
+    tIdx[2 * k + 1] = down; tAmp[2 * k + 1] = C[k].downF * fullAmp; tCut[2 * k + 1] = cutoff;
+    todo |= (1ull << up) | (1ull << down);
+  }
+  N.lips = 0.0;
+  while (todo) {
+    const int j = __ffsll((long long)todo) - 1;
+    todo &= todo - 1;
+    double tgt = 0.0, cut = S.ncut[j][lane];
+    bool hit = false;
+#pragma unroll
+    for (int e = 0; e < 8; e++) if (tIdx[e] == j) { tgt = tAmp[e]; cut = tCut[e]; hit = true; }  // the last one wins
+    if (hit) S.ncut[j][lane] = cut;
+    const double old = S.namp[j][lane];
+    double a = __dadd_rn(old, __dmul_rn(P.nz_F, __dsub_rn(tgt, old)));
+    double out = S.nout[j][lane];
+    if ((old >= 0.001) && (a < 0.001)) out = 0.0;
+    if (a >= 0.001) {
+      const double x = exp(-2.0 * kPi * (cut * P.dt));  // IirFilter::createSinglePoleLowpass (IirFilter.cpp:235-243)
+      uint32_t isum = 0;  // 12 x rand() summed in an int: wraps around like the reference's
+      for (int q = 0; q < 12; q++) isum += rng_next(S, lane, N.ri);
+      double in = (double)(int32_t)isum;
+      in = __ddiv_rn(in, 2147483647.0);
+      in = __dsub_rn(in, 6.0);
+      in = __ddiv_rn(in, 3.4641016151377543864);  // sqrt(12.0)
+      out = __dadd_rn(__dmul_rn(__dsub_rn(1.0, x), in), __dmul_rn(x, out));
+    }
+    if ((a < 1.0e-30) && (tgt == 0.0)) { a = 0.0; N.nz &= ~(1ull << j); }  // (the reference lets it decay for ever)
+    else N.nz |= 1ull << j;
+    S.namp[j][lane] = a; S.nout[j][lane] = out;
+    if (j == AFS_NUM_PM_SECTIONS) N.lips = out * a;
   }
 }
 
@@ -956,23 +1213,16 @@ __device__ __forceinline__ void glottis_geometry(const TdsParams &P, const doubl
   len[0] = D.th0;
   len[1] = D.th1;
 }
-__device__ __forceinline__ void glottis_store_dims(TdsSmem &S, int lane, const GlottisDims &GD) {
-  S.gdim[0][lane] = GD.Q; S.gdim[1][lane] = GD.cordLength; S.gdim[2][lane] = GD.th0; S.gdim[3][lane] = GD.th1;
-  S.gdim[4][lane] = GD.ol0; S.gdim[5][lane] = GD.ol1; S.gdim[6][lane] = GD.cl0; S.gdim[7][lane] = GD.cl1;
-  S.gdim[8][lane] = GD.mz0; S.gdim[9][lane] = GD.mz1;
-}
-
 // Direct-form IIR of IirFilter::getOutputSample (IirFilter.cpp:47-65); history x[i] = input i+1 samples
-// ago, kept in shared memory [i][lane].
+// ago, kept in the registers of warp X1.
 template <int ORDER>
-__device__ __forceinline__ double iir_step(const double *a, const double *b, double (*x)[LANES], double (*y)[LANES],
-                                           int lane, double in) {
+__device__ __forceinline__ double iir_step(const double *a, const double *b, double (&x)[ORDER], double (&y)[ORDER], double in) {
   double sum = a[0] * in;
 #pragma unroll
-  for (int i = 1; i <= ORDER; i++) { sum += a[i] * x[i - 1][lane]; sum += b[i] * y[i - 1][lane]; }
+  for (int i = 1; i <= ORDER; i++) { sum += a[i] * x[i - 1]; sum += b[i] * y[i - 1]; }
 #pragma unroll
-  for (int i = ORDER - 1; i > 0; i--) { x[i][lane] = x[i - 1][lane]; y[i][lane] = y[i - 1][lane]; }
-  x[0][lane] = in; y[0][lane] = sum;
+  for (int i = ORDER - 1; i > 0; i--) { x[i] = x[i - 1]; y[i] = y[i - 1]; }
+  x[0] = in; y[0] = sum;
   return sum;
 }
 
@@ -982,16 +1232,24 @@ __device__ __constant__ double c_tone_a[5] = {5.027640021717718e-007, -7.9955355
 __device__ __constant__ double c_tone_b[5] = {0.0, 3.986308869708467, -5.959669638387298, 3.960408461107104,
                                               -0.987047716233603};
 
+// Registers of warp X1: glottis state + cached dimensions, filter histories.
+struct X1Regs {
+  GlottisState G;
+  GlottisDims GD;
+  double toneX[4], toneY[4];  // skin-radiation filter history
+  double chebX[8], chebY[8];  // output low-pass history
+  double prevFlow;
+};
 // Output of the step whose radiated flows sit in uext[]: radiated flow (TdsModel.cpp:687-705), pressure
 // differentiator + Chebyshev low-pass + decimation (Synthesizer.cpp:614-627).  `n_done` = steps finished.
-__device__ __forceinline__ void emit_output(const TdsParams &P, TdsSmem &S, int lane, int n_done, bool active,
+__device__ __forceinline__ void emit_output(const TdsParams &P, TdsSmem &S, X1Regs &xr, int lane, int n_done, bool active,
                                             int tract, int n_out, double *audio, double *flow, uint32_t &bad) {
   double u = S.uext[UX_RADM][lane] + S.uext[UX_RADN][lane];
-  if (P.skin) u += iir_step<4>(c_tone_a, c_tone_b, S.toneX, S.toneY, lane, S.p4[3][lane]);
+  if (P.skin) u += iir_step<4>(c_tone_a, c_tone_b, xr.toneX, xr.toneY, S.p4[3][lane]);
   if (!isfinite(u)) bad |= 1u;
-  const double outP = (u - S.prevFlow[lane]) * P.fs;
-  S.prevFlow[lane] = u;
-  const double filt = iir_step<8>(P.cheb_a, P.cheb_b, S.chebX, S.chebY, lane, outP);
+  const double outP = (u - xr.prevFlow) * P.fs;
+  xr.prevFlow = u;
+  const double filt = iir_step<8>(P.cheb_a, P.cheb_b, xr.chebX, xr.chebY, outP);
   if (active) {
     if (flow) flow[(size_t)tract * P.total_steps + (n_done - 1)] = u;
     if ((n_done % P.sr_factor) == 0) audio[(size_t)tract * n_out + (n_done / P.sr_factor - 1)] = filt * (0.004 / 32767);
@@ -1006,6 +1264,7 @@ struct KArgs {
   double *audio, *flow;
   uint32_t *status;
   double *dump;
+  const uint32_t *seeds;
 };
 
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
@@ -1018,7 +1277,7 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "mem
 
 // Stages the control frames of interval `interval` (all warps; the caller puts barriers around it).
 __device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const int warp, const afs_tube_frame *my_frames,
-                                               const double *my_glottis, int interval) {
+                                               const double *my_glottis, int interval, bool noise) {
   for (int item = warp; item < 2 * AFS_NUM_PM_SECTIONS + 2; item += NW) {
     if (item < 2 * AFS_NUM_PM_SECTIONS) {
       const int f = item / AFS_NUM_PM_SECTIONS, j = item % AFS_NUM_PM_SECTIONS;
@@ -1027,11 +1286,13 @@ __device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const
       if (a < kMinArea) a = kMinArea;  // Tube::setPharynxMouthGeometry clamps on the way in
       S.fA[f][j][lane] = a;
       S.fLen[f][j][lane] = fr->length_cm[j];
+      if (noise && f == 0) S.art[j][lane] = (unsigned char)fr->articulator[j];
     } else {
       const int f = item - 2 * AFS_NUM_PM_SECTIONS;
       double v = my_frames[interval + f].velum_area_cm2;
       if (v < kMinArea) v = kMinArea;  // Tube::getVelumOpening_cm2 returns the clamped nose[0] area
       S.velum[f][lane] = v;
+      S.inc[f][lane] = my_frames[interval + f].incisor_pos_cm;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
         S.gctl[f][c][lane] = my_glottis[(size_t)(interval + f) * AFS_NUM_GLOTTIS_CONTROL + c];
     }
@@ -1055,6 +1316,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   DRegs dst;
   SRegs sst;
   RadRegs rr;
+  X1Regs xr;
+  NoiseRegs nr;
+  nr.nz = 0; nr.ri = 0; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0;
   const SCfg scfg = scfg_of(warp);
   if (ROLE == 0) {
 #pragma unroll
@@ -1072,6 +1336,15 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (ROLE == 3) {
 #pragma unroll
     for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; }
+    if (P.noise) rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ri);
+  }
+  if (ROLE == 2) {
+    xr.G = GlottisState{0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) { xr.toneX[i] = 0.0; xr.toneY[i] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { xr.chebX[i] = 0.0; xr.chebY[i] = 0.0; }
+    xr.prevFlow = 0.0;
   }
   cta_sync();  // static boundary records / pivots visible
 
@@ -1080,15 +1353,12 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (T > 0) {
     i0 = A.bounds[0]; i1 = A.bounds[1];
     inv_len = 1.0 / (double)(i1 - i0);
-    stage_interval(S, lane, warp, my_frames, my_glottis, 0);
+    stage_interval(S, lane, warp, my_frames, my_glottis, 0, P.noise != 0);
     cta_sync();
     if (ROLE == 2) {  // glottis geometry of step 0
       double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
-      const GlottisState G{0.0, 0.0, 0.0, 0.0};
-      GlottisDims GD;
-      glottis_geometry(P, ctl, G, len, ar, GD);
-      glottis_store_dims(S, lane, GD);
+      glottis_geometry(P, ctl, xr.G, len, ar, xr.GD);
       S.glLen[0][0][lane] = len[0]; S.glLen[0][1][lane] = len[1];
       S.glArea[0][0][lane] = ar[0]; S.glArea[0][1][lane] = ar[1];
     }
@@ -1105,7 +1375,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       interval++;
       i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
       inv_len = 1.0 / (double)(i1 - i0);
-      stage_interval(S, lane, warp, my_frames, my_glottis, interval);
+      stage_interval(S, lane, warp, my_frames, my_glottis, interval, P.noise != 0);
       cta_sync();
     }
     X.ratio = (double)(n - i0) * inv_len;  // (1 ulp from the reference's i / N; irrelevant at the 1e-6 bar)
@@ -1119,16 +1389,23 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       if (X.dumping) { Y.upd = X.upd && half == 0; Y.rows = X.rows && half == 1; }
       if (ROLE == 0) dwarp_pass_a<-1>(P, S, lane, warp, dst, Y, A.dump);
       if (ROLE == 1) swarp_pass_a(P, S, lane, warp, scfg, sst, Y);
-      if (ROLE == 3 && Y.upd) radiation_update(P, lane, rr, Y, A.dump);
+      if (ROLE == 3 && Y.upd) radiation_update(P, lane, rr, nr, Y, A.dump);
       if (X.dumping && half == 0) {
         if (ROLE == 0) dwarp_dump(P, S, lane, warp, dst, A.dump);
         if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
       }
     }
+    if (ROLE == 3 && P.noise && X.rows) {  // noise sources of step n (needs the update of the radiation currents above)
+      const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
+      NoiseCons cons[4];
+      noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, cons);
+      const double asp = nz_lerp(re1, S.gctl[0][G_ASP][lane], re, S.gctl[1][G_ASP][lane]);
+      noise_sources(P, S, lane, nr, cons, re, re1, n & 1, asp);
+    }
     AFS_TICK(1);
     cta_sync();
     AFS_TICK(2);
-    if (ROLE == 2 && n > 0) emit_output(P, S, lane, n, active, tract, n_out, A.audio, A.flow, bad);
+    if (ROLE == 2 && n > 0) emit_output(P, S, xr, lane, n, active, tract, n_out, A.audio, A.flow, bad);
     if (!X.rows) break;
     // ============ first rows + elimination of the segments || glottis ============
     if (ROLE == 0) dwarp_eliminate(P, S, lane, warp, dst);
@@ -1137,25 +1414,18 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       swarp_eliminate(P, S, lane, warp, scfg, sst, psrc);
     }
     if (ROLE == 3) {
-      radiation_eliminate(P, S, lane, W_M3, 0, rr.c[0], rr.c[1], rr.keep[0]);
-      radiation_eliminate(P, S, lane, W_N2, 1, rr.c[2], rr.c[3], rr.keep[1]);
+      radiation_eliminate(P, S, lane, W_M3, 0, rr.c[0], rr.c[1], nr.lips, rr.keep[0]);
+      radiation_eliminate(P, S, lane, W_N2, 1, rr.c[2], rr.c[3], nr.lips, rr.keep[1]);
     }
     if (ROLE == 2) {
       // incTime for this step (pressures of the previous step), then the geometry step n+1 will use
       double ctl[AFS_NUM_GLOTTIS_CONTROL], p[4], len[2], ar[2];
-      GlottisState G{S.gx[0][lane], S.gx[1][lane], S.gx[2][lane], S.gx[3][lane]};
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = X.ratio1 * S.gctl[0][c][lane] + X.ratio * S.gctl[1][c][lane];
       for (int c = 0; c < 4; c++) p[c] = S.p4[c][lane];
-      GlottisDims GD;
-      GD.Q = S.gdim[0][lane]; GD.cordLength = S.gdim[1][lane]; GD.th0 = S.gdim[2][lane]; GD.th1 = S.gdim[3][lane];
-      GD.ol0 = S.gdim[4][lane]; GD.ol1 = S.gdim[5][lane]; GD.cl0 = S.gdim[6][lane]; GD.cl1 = S.gdim[7][lane];
-      GD.mz0 = S.gdim[8][lane]; GD.mz1 = S.gdim[9][lane]; GD.mw0 = 0.0; GD.mw1 = 0.0;
-      glottis_inc_time(P, ctl, G, p, GD);
+      glottis_inc_time(P, ctl, xr.G, p, xr.GD);
       const double rn = (double)(n + 1 - i0) * inv_len, rn1 = 1.0 - rn;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = rn1 * S.gctl[0][c][lane] + rn * S.gctl[1][c][lane];
-      glottis_geometry(P, ctl, G, len, ar, GD);
-      glottis_store_dims(S, lane, GD);
-      S.gx[0][lane] = G.x0; S.gx[1][lane] = G.x1; S.gx[2][lane] = G.xp0; S.gx[3][lane] = G.xp1;
+      glottis_geometry(P, ctl, xr.G, len, ar, xr.GD);
       const int par = (n + 1) & 1;
       S.glLen[par][0][lane] = len[0]; S.glLen[par][1][lane] = len[1];
       S.glArea[par][0][lane] = ar[0]; S.glArea[par][1][lane] = ar[1];
@@ -1176,8 +1446,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     cta_sync();
     AFS_TICK(5);
     // ============ back substitution inside the segments ============
-    if (ROLE == 0) dwarp_back(S, lane, warp, dst);
-    if (ROLE == 1) swarp_back(S, lane, warp, scfg, sst);
+    if (ROLE == 0) dwarp_back(P, S, lane, warp, dst);
+    if (ROLE == 1) swarp_back(P, S, lane, warp, scfg, sst);
     if (ROLE == 3) radiation_back(S, lane, rr);
     AFS_TICK(6);
     cta_sync();
@@ -1231,19 +1501,20 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
   }
   for (int i = warp; i < NS * 3; i += NW) (&S.wall[0][0])[i][lane] = 0.0;
   for (int i = warp; i < 8 * KD; i += NW) { S.Ed[i][lane] = 0.0; S.Al[i][lane] = 0.0; }
+  for (int i = warp; i < 42; i += NW) {
+    S.nmag[i][lane] = 0.0;
+    if (i < 41) { S.namp[i][lane] = 0.0; S.ncut[i][lane] = 3000.0; S.nout[i][lane] = 0.0; }
+  }
   {
     const int w = warp;
     S.bE[w][lane] = 0.0; S.bL[w][lane] = 0.0; S.bR[w][lane] = 0.0; S.bI[w][lane] = 0.0; S.bG[w][lane] = 0.0;
-    S.bD[w][lane] = 0.0; S.csib[w][lane] = 0.0; S.sideDD[w][lane] = 0.0; S.sideDR[w][lane] = 0.0; S.sideF[w][lane] = 0.0;
+    S.bD[w][lane] = 0.0; S.csib[w & 3][lane] = 0.0; S.sideDD[w][lane] = 0.0; S.sideDR[w][lane] = 0.0; S.sideF[w][lane] = 0.0;
     S.sepD[w][lane] = 1.0; S.sepR[w][lane] = 0.0; S.redW[w][lane] = 1.0;  // NSEP == NW
   }
   if (warp == 0) {
     for (int i = 0; i < NUX; i++) S.uext[i][lane] = 0.0;
     for (int i = 0; i < 5; i++) S.lf[i][lane] = 0.0;
     for (int i = 0; i < 4; i++) { S.p4[i][lane] = 0.0; (&S.radc[0][0])[i][lane] = 0.0; }
-    for (int i = 0; i < 4; i++) { S.gx[i][lane] = 0.0; S.toneX[i][lane] = 0.0; S.toneY[i][lane] = 0.0; }
-    for (int i = 0; i < 8; i++) { S.chebX[i][lane] = 0.0; S.chebY[i][lane] = 0.0; }
-    S.prevFlow[lane] = 0.0;
   }
   __syncthreads();
 
@@ -1304,6 +1575,10 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   for (int i = 0; i < AFS_NUM_GLOTTIS_STATIC; i++) P.gs[i] = o->glottis_static[i];
   P.g_sqrt_mk[0] = sqrt(P.gs[S_MASS1] * P.gs[S_K1]);
   P.g_sqrt_mk[1] = sqrt(P.gs[S_MASS2] * P.gs[S_K2]);
+  P.noise = o->generate_noise_sources ? 1 : 0;
+  P.nz_F = 1.0 - exp(-2.0 * M_PI * 40.0 * dt);
+  P.nm_a = exp(-2.0 * M_PI * 500.0 * dt);
+  P.nm_1a = 1.0 - P.nm_a;
   P.dump_step = 0;
   L->params.resize(sizeof P);
   memcpy(L->params.data(), &P, sizeof P);
@@ -1312,8 +1587,8 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
 }
 
 cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
-                       const double *d_glottis, double *d_audio, double *d_flow, uint32_t *d_status,
-                       double *d_dump, int dump_step, cudaStream_t stream) {
+                       const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
+                       uint32_t *d_status, double *d_dump, int dump_step, cudaStream_t stream) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
@@ -1322,7 +1597,7 @@ cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tu
                                        (int)sizeof(TdsSmem));  // per device; cheap
   if (e != cudaSuccess) return e;
   const int ctas = (P.n_tracts + P.lanes_per_cta - 1) / P.lanes_per_cta;
-  KArgs A{d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, d_dump};
+  KArgs A{d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, d_dump, d_seeds};
   tds_batch_kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, A);
   return cudaGetLastError();
 }

@@ -257,8 +257,11 @@ def run_ours(args):
     d_audio = torch.empty(B_TDS, n_out, dtype=torch.float64, device=dev)
     d_status = torch.zeros(B_TDS, dtype=torch.int32, device=dev)
 
+    quiet = afs.tds_options_default(noise=False)  # headline: noise sources off (the multi-threaded reference arm needs that)
+
     def tds_dev():
-        ctx.tds_synthesize_device(d_fr, d_gl, B_TDS, 2, frame_len, d_audio, stream, FS, SR_FACTOR, d_status=d_status)
+        ctx.tds_synthesize_device(d_fr, d_gl, B_TDS, 2, frame_len, d_audio, stream, FS, SR_FACTOR, opts=quiet,
+                                  d_status=d_status)
 
     fp64_peak = ctx.probe_fp64_tflops()
     sampler = ClockSampler(local)
@@ -282,7 +285,7 @@ def run_ours(args):
     h_gl = torch.from_numpy(gl.copy()).pin_memory()
     h_audio = torch.empty(B_TDS, n_out, dtype=torch.float64).pin_memory()
     h_status = torch.zeros(B_TDS, dtype=torch.int32).pin_memory()
-    opts = afs.tds_options_default()
+    opts = quiet
 
     def tds_host():
         rc = ctx.lib.afs_tds_synthesize(ctx.h, afs.api.C.byref(opts), B_TDS, 2, frame_len.ctypes.data,
@@ -300,13 +303,36 @@ def run_ours(args):
     e2e_value = audio_s_per_step / e2e_s
     assert torch.equal(h_audio, d_audio.cpu()), "host-path audio differs from the device-resident path"
 
-    # digest of every rank's output, gathered over NCCL after the timed region
+    # the only collective of the path: one all-gather of the outputs, after the compute; timed separately
     digest = d_audio.abs().mean(dim=1)
+    gather_ms = 0.0
     if world > 1:
-        gathered = [torch.empty_like(digest) for _ in range(world)]
-        dist.all_gather(gathered, digest)
-        digest = torch.cat(gathered)
+        all_audio = torch.empty(world * B_TDS, n_out, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(all_audio, d_audio)  # warm-up (NCCL channel setup)
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(all_audio, d_audio)
+        e1.record()
+        e1.synchronize()
+        gather_ms = max_over_ranks(e0.elapsed_time(e1))
+        digest = all_audio.abs().mean(dim=1)
+        assert torch.equal(all_audio[rank * B_TDS:(rank + 1) * B_TDS], d_audio)
+        del all_audio
     digest_mean = float(digest.mean().item())
+
+    # same workload with the reference's default generateNoiseSources = true (per-utterance random() streams)
+    noisy = afs.tds_options_default(noise=True)
+    d_seeds = torch.arange(1, B_TDS + 1, dtype=torch.int32, device=dev) + 7919 * rank
+
+    def tds_noise_dev():
+        ctx.tds_synthesize_device(d_fr, d_gl, B_TDS, 2, frame_len, d_audio, stream, FS, SR_FACTOR, opts=noisy,
+                                  d_seeds=d_seeds, d_status=d_status)
+
+    noise_steps = max(1, min(args.steps, 2))
+    noise_ms = timed(tds_noise_dev, noise_steps, 1) / noise_steps
+    assert int(d_status.sum().item()) == 0, "non-finite values in the TDS batch (noise sources on)"
 
     # ---------------- TL: second metric -----------------------------------------------------------
     f_tl = make_tl_batch(B_TL, 20260001 + rank)
@@ -370,6 +396,11 @@ def run_ours(args):
                      "hbm_gbs_peak_measured": peaks.get("hbm_gbs")},
         "cpu_baseline": cpu,
         "output_digest": digest_mean,
+        "gather": {"collective": "all_gather of the audio [B, n_out] f64 over NCCL, after the compute", "ms": gather_ms,
+                   "bytes_per_rank": int(B_TDS * n_out * 8),
+                   "value_including_gather": audio_s_per_step / ((ms_step + gather_ms) * 1e-3)},
+        "noise_sources_on": {"value": audio_s_per_step / (noise_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": noise_ms,
+                             "steps": noise_steps},
         "tl": {"metric": "tl_spectra_per_second_2048_bins", "value": tl_value, "unit": "spectra/s", "ms_per_step": tl_ms,
                "config": {"workload": "tl_sweep_4096x2048", "area_functions_per_gpu": B_TL, "bins": K_TL},
                "e2e": {"value": tl_e2e, "unit": "spectra/s", "h2d_bytes_per_step": int(f_tl.nbytes),

@@ -140,8 +140,11 @@ typedef struct afs_tl_options {
 } afs_tl_options;
 
 /* TdsModel::Options (TdsModel.h:75-87); defaults of TdsModel::TdsModel()
- * (TdsModel.cpp:35-44) via afs_tds_options_default, except that the default
- * here is generate_noise_sources = 0 (the parity-gated configuration). */
+ * (TdsModel.cpp:35-44) via afs_tds_options_default.  With
+ * generate_noise_sources every tract draws from its own glibc-compatible
+ * random() stream (the reference shares libc rand(), TdsModel.cpp:1690-1696),
+ * seeded by `seeds[tract]` (1 when no seeds are given, like an unseeded
+ * process). */
 typedef struct afs_tds_options {
   int32_t turbulence_losses;
   int32_t soft_walls;

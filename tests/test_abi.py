@@ -37,7 +37,7 @@ def test_struct_layouts_match_the_header():
             o.piriform_fossa, o.static_pressure_drops, o.lung_pressure_dPa) == (3, 1, 1, 1, 1, 0, 1, 0.0)
     t = afs.tds_options_default()
     assert (t.turbulence_losses, t.soft_walls, t.generate_noise_sources, t.radiation_from_skin, t.piriform_fossa,
-            t.inner_length_corrections) == (1, 1, 0, 1, 0, 1)
+            t.inner_length_corrections) == (1, 1, 1, 1, 0, 1)  # TdsModel.cpp:35-44
     assert t.glottis_static[14] == 129.0 and t.glottis_static[15] == 125.51
     f = afs.default_frames(2)
     assert np.all(f["area_cm2"] == 4.0) and np.all(f["articulator"] == 4) and np.all(f["glottis_area_cm2"] == 0.1)

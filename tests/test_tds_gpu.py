@@ -1,7 +1,7 @@
 """GPU parity tests of K1 tds_batch_kernel through the C ABI.
 
 Bar (BASELINE.json north_star): audio within 1e-6 relative max-abs of the reference in FP64, noise
-sources off.  The kernel reorders arithmetic (zero-fill elimination order, FMA, folded wall terms), so
+sources off and on (per-tract glibc-compatible random() streams).  The kernel reorders arithmetic (zero-fill elimination order, FMA, folded wall terms), so
 it is not bit-identical; the per-step state check below keeps that honest at the 1e-9 level before the
 self-oscillating glottis has had time to amplify rounding noise.
 """
@@ -16,6 +16,14 @@ TOL = 1e-6  # relative max-abs, as stated by the north star
 G0 = np.array([120.0, 8000.0, 0.01, 0.01, 0.0, -40.0])
 
 
+def synth(ctx, *args, **kw):
+    """ctx.tds_synthesize with the noise sources off unless options are given (the oracle helper's default)."""
+    import areafunctionsynthesis_b200 as afs
+    if kw.get("opts") is None:
+        kw["opts"] = afs.tds_options_default(noise=False)
+    return ctx.tds_synthesize(*args, **kw)
+
+
 def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
 
@@ -25,7 +33,7 @@ def test_state_after_single_steps_matches_reference(ctx):
     for step, tol in ((1, 1e-12), (2, 1e-12), (500, 1e-9)):
         st = np.zeros(473)
         ctx.set_state_dump(step, st)
-        ctx.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 44100.0, 2)
+        synth(ctx, g["static_frames"], g["static_glottis"], [2205], 44100.0, 2)
         ctx.set_state_dump(0)
         ref = g[f"static_state_{step}"]
         for name, sl in (("pressure", slice(0, 93)), ("pressureRate", slice(93, 186)), ("wallCurrent", slice(186, 279)),
@@ -37,22 +45,22 @@ def test_state_after_single_steps_matches_reference(ctx):
 
 def test_golden_static_vowel(ctx):
     g = load_golden("tds_reference.npz")
-    a, u, status = ctx.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 44100.0, 2, want_flow=True)
+    a, u, status = synth(ctx, g["static_frames"], g["static_glottis"], [2205], 44100.0, 2, want_flow=True)
     assert status[0] == 0
     assert rel_err(u, g["static_flow44"]) <= TOL
     assert rel_err(a, g["static_audio44"]) <= TOL
-    a, u, _ = ctx.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 22050.0, 1, want_flow=True)
+    a, u, _ = synth(ctx, g["static_frames"], g["static_glottis"], [2205], 22050.0, 1, want_flow=True)
     assert rel_err(u, g["static_flow22"]) <= TOL and rel_err(a, g["static_audio22"]) <= TOL
 
 
 def test_golden_transition_and_options(ctx):
     import areafunctionsynthesis_b200 as afs
     g = load_golden("tds_reference.npz")
-    a, u, _ = ctx.tds_synthesize(g["trans_frames"], g["trans_glottis"], g["trans_len"], 44100.0, 2, want_flow=True)
+    a, u, _ = synth(ctx, g["trans_frames"], g["trans_glottis"], g["trans_len"], 44100.0, 2, want_flow=True)
     assert rel_err(u, g["trans_flow44"]) <= TOL and rel_err(a, g["trans_audio44"]) <= TOL
-    o = afs.tds_options_default()
+    o = afs.tds_options_default(noise=False)
     o.piriform_fossa = 1; o.glottis_loss_option = 1
-    a, u, _ = ctx.tds_synthesize(g["nasal_frames"], g["static_glottis"], [1102], 44100.0, 2, opts=o, want_flow=True)
+    a, u, _ = synth(ctx, g["nasal_frames"], g["static_glottis"], [1102], 44100.0, 2, opts=o, want_flow=True)
     assert rel_err(u, g["nasal_flow44"]) <= TOL and rel_err(a, g["nasal_audio44"]) <= TOL
 
 
@@ -72,7 +80,7 @@ def test_batch_of_vowel_transitions_against_oracle(ctx, oracle, shapes):
     """SURVEY 8d config C3 at a size the oracle finishes in seconds: 40 oral vowel-to-vowel transitions
     (more tracts than one CTA holds), 0.1 s each at 44.1 kHz."""
     fr, gl, fl = _vowel_transitions(shapes, 40, 20260002)
-    a, u, status = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, want_flow=True)
+    a, u, status = synth(ctx, fr, gl, fl, 44100.0, 2, want_flow=True)
     ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2)
     assert not status.any()
     for b in range(len(fr)):
@@ -85,9 +93,9 @@ def test_nasal_and_fossa_against_oracle(ctx, oracle, shapes):
     import areafunctionsynthesis_b200 as afs
     from oracle.pyoracle import tds_options_default as oracle_opts
     fr, gl, fl = _vowel_transitions(shapes, 12, 20260003, nasal=True)
-    o = afs.tds_options_default(); o.piriform_fossa = 1
+    o = afs.tds_options_default(noise=False); o.piriform_fossa = 1
     oo = oracle_opts(); oo.piriform_fossa = 1
-    a, u, _ = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=o, want_flow=True)
+    a, u, _ = synth(ctx, fr, gl, fl, 44100.0, 2, opts=o, want_flow=True)
     ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=oo)
     for b in range(len(fr)):
         assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, b
@@ -100,13 +108,13 @@ def test_consonant_closures_and_random_area_functions(ctx, oracle, shapes):
     pick = rng.integers(0, n, size=(8, 3))
     fr = shapes["frames"][pick].copy()
     gl = np.tile(G0, (8, 3, 1))
-    a, u, _ = ctx.tds_synthesize(fr, gl, [700, 401], 44100.0, 2, want_flow=True)
+    a, u, _ = synth(ctx, fr, gl, [700, 401], 44100.0, 2, want_flow=True)
     ao, uo = oracle.tds_synthesize(fr, gl, [700, 401], 44100.0, 2)
     for b in range(8):
         assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, b
     rf = random_frames(16, seed=99).reshape(8, 2)
     gl = np.tile(G0, (8, 2, 1))
-    a, u, _ = ctx.tds_synthesize(rf, gl, [1000], 44100.0, 2, want_flow=True)
+    a, u, _ = synth(ctx, rf, gl, [1000], 44100.0, 2, want_flow=True)
     ao, uo = oracle.tds_synthesize(rf, gl, [1000], 44100.0, 2)
     for b in range(8):
         assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, b
@@ -116,26 +124,26 @@ def test_edge_cases(ctx, oracle, shapes):
     import areafunctionsynthesis_b200 as afs
     fr, gl, _ = _vowel_transitions(shapes, 3, 5)
     # empty batch
-    a, u, st = ctx.tds_synthesize(fr[:0], gl[:0], [10], 44100.0, 2)
+    a, u, st = synth(ctx, fr[:0], gl[:0], [10], 44100.0, 2)
     assert a.shape == (0, 10)
     # one-sample frames, odd lengths, sr_factor 1 and 3
     for srf, fl in ((1, [1]), (2, [1, 1]), (3, [7]), (2, [333])):
         F = len(fl) + 1
         frr = np.concatenate([fr, fr], axis=1)[:, :F]
         gll = np.concatenate([gl, gl], axis=1)[:, :F]
-        a, u, _ = ctx.tds_synthesize(frr, gll, fl, 22050.0 * srf, srf, want_flow=True)
+        a, u, _ = synth(ctx, frr, gll, fl, 22050.0 * srf, srf, want_flow=True)
         ao, uo = oracle.tds_synthesize(frr, gll, fl, 22050.0 * srf, srf)
         assert rel_err(u, uo) <= TOL and np.allclose(a, ao, rtol=0, atol=TOL * np.max(np.abs(ao)) + 1e-30), (srf, fl)
     # options the device path does not implement are errors, not silently different audio
-    o = afs.tds_options_default(); o.transvelar_coupling = 1
+    o = afs.tds_options_default(noise=False); o.transvelar_coupling = 1
     with pytest.raises(afs.AfsError, match="not supported"):
-        ctx.tds_synthesize(fr, gl, [10], 44100.0, 2, opts=o)
+        synth(ctx, fr, gl, [10], 44100.0, 2, opts=o)
     # other option switches
     from oracle.pyoracle import tds_options_default as oracle_opts
     for name in ("turbulence_losses", "soft_walls", "radiation_from_skin", "inner_length_corrections"):
-        o = afs.tds_options_default(); setattr(o, name, 0)
+        o = afs.tds_options_default(noise=False); setattr(o, name, 0)
         oo = oracle_opts(); setattr(oo, name, 0)
-        a, u, _ = ctx.tds_synthesize(fr, gl, [600], 44100.0, 2, opts=o, want_flow=True)
+        a, u, _ = synth(ctx, fr, gl, [600], 44100.0, 2, opts=o, want_flow=True)
         ao, uo = oracle.tds_synthesize(fr, gl, [600], 44100.0, 2, opts=oo)
         assert rel_err(u, uo) <= TOL and rel_err(a, ao) <= TOL, name
 
@@ -144,12 +152,59 @@ def test_full_length_utterances_permutation_property(ctx, oracle, shapes):
     """1 s utterances (44100 steps): a handful against the oracle, plus the size-independent property that a
     tract's audio does not depend on which lane / CTA / batch it was computed in."""
     fr, gl, _ = _vowel_transitions(shapes, 96, 20260002)
-    a, _, status = ctx.tds_synthesize(fr, gl, [22050], 44100.0, 2)
+    a, _, status = synth(ctx, fr, gl, [22050], 44100.0, 2)
     assert not status.any() and np.isfinite(a).all()
     sel = [0, 37, 95]
     ao, _ = oracle.tds_synthesize(fr[sel], gl[sel], [22050], 44100.0, 2, want_flow=False)
     for k, b in enumerate(sel):
         assert rel_err(a[b], ao[k]) <= TOL, b
     perm = np.random.default_rng(0).permutation(96)[:40]
-    a2, _, _ = ctx.tds_synthesize(fr[perm], gl[perm], [22050], 44100.0, 2)
+    a2, _, _ = synth(ctx, fr[perm], gl[perm], [22050], 44100.0, 2)
+    assert np.array_equal(a[perm], a2)
+
+
+# ---------------------------------------------------------------------------------------------
+# noise sources (TdsModel::calcNoiseSources / calcNoiseSample, TdsModel.cpp:1188-1708)
+# ---------------------------------------------------------------------------------------------
+def test_noise_sources_golden(ctx):
+    """Reference output with generateNoiseSources = true and srand(seed): tongue/teeth, lip and glottal sources."""
+    import areafunctionsynthesis_b200 as afs
+    g = load_golden("tds_reference.npz")
+    a, u, st = ctx.tds_synthesize(g["noise_frames"], g["noise_glottis"], [3308], 44100.0, 2,
+                                  opts=afs.tds_options_default(noise=True), seeds=g["noise_seeds"], want_flow=True)
+    assert not st.any()
+    for b in range(3):
+        assert rel_err(u[b], g["noise_flow44"][b]) <= TOL and rel_err(a[b], g["noise_audio44"][b]) <= TOL, b
+    # the sources are really on: the noise-free run differs by far more than the tolerance
+    a0, _, _ = synth(ctx, g["noise_frames"], g["noise_glottis"], [3308], 44100.0, 2)
+    assert rel_err(a0, g["noise_audio44"]) > 1e-3
+
+
+def test_noise_sources_against_oracle(ctx, oracle, shapes):
+    """Vowel <-> consonant transitions (all 51 shapes), three control frames, per-tract seeds, nasal coupling; more
+    tracts than one CTA holds.  Also: the default seed is 1 and a tract's noise does not depend on its lane."""
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    n = len(shapes["names"])
+    rng = np.random.default_rng(20260004)
+    B = 36
+    fr = shapes["frames"][rng.integers(0, n, size=(B, 3))].copy()
+    fr["velum_area_cm2"] = np.where(rng.random((B, 3)) < 0.3, rng.random((B, 3)) * 0.5, 0.0)
+    gl = np.tile(G0, (B, 3, 1))
+    gl[:, :, 0] = rng.uniform(90, 220, size=(B, 3))
+    gl[:, :, 2:4] = rng.uniform(0.0, 0.04, size=(B, 3, 1))   # rest displacement: from pressed to breathy
+    gl[:, :, 5] = rng.uniform(-40.0, -10.0, size=(B, 3))     # aspiration strength
+    seeds = rng.integers(0, 2**32, size=B, dtype=np.uint64).astype(np.uint32)
+    fl = [900, 601]
+    on = afs.tds_options_default(noise=True)
+    a, u, st = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
+    ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=oracle_opts(noise=True), seeds=seeds)
+    assert not st.any()
+    for b in range(B):
+        assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, (b, rel_err(u[b], uo[b]))
+    a1, _, _ = ctx.tds_synthesize(fr[:2], gl[:2], fl, 44100.0, 2, opts=on)
+    ao1, _ = oracle.tds_synthesize(fr[:2], gl[:2], fl, 44100.0, 2, opts=oracle_opts(noise=True), want_flow=False)
+    assert rel_err(a1, ao1) <= TOL
+    perm = rng.permutation(B)[:20]
+    a2, _, _ = ctx.tds_synthesize(fr[perm], gl[perm], fl, 44100.0, 2, opts=on, seeds=seeds[perm])
     assert np.array_equal(a[perm], a2)
