@@ -406,13 +406,17 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
         st.L0 = L; st.R0 = R; st.I0 = invr; st.D0 = D;
         if (csib_slot(w) >= 0) S.csib[csib_slot(w)][lane] = c_;
       } else {
-        row_dyn(P, slot_row_flags<V>(k, sec), pE, pL, pR, pI, pD, E, L, R, invr, D, c_, 0.0, u_, pA, area, st.gbf, y_, x_);
+        // (the lower -> upper glottis row can only be slot 1, the entrance row only slot 0: keeps their code and the
+        //  registers they need out of the other slots)
+        const int fl = slot_row_flags<V>(k, sec) & (k == 1 ? (RF_JUNCTION | RF_GUP) : RF_JUNCTION);
+        row_dyn(P, fl, pE, pL, pR, pI, pD, E, L, R, invr, D, c_, 0.0, u_, k == 1 ? pA : 0.0, area, st.gbf, y_, x_);
       }
       if (k == KD - 1) {
         S.bE[w][lane] = E; S.bL[w][lane] = L; S.bR[w][lane] = R; S.bI[w][lane] = invr; S.bD[w][lane] = D;
         S.bG[w][lane] = fma(L, P.idt, R);
       }
-      pE = E; pL = L; pR = R; pI = invr; pD = D; pA = area;
+      pE = E; pL = L; pR = R; pI = invr; pD = D;
+      if (k == 0) pA = area;
     }
     st.p[k] = p_; st.pr[k] = pr_; st.c[k] = c_; st.x[k] = x_; st.y[k] = y_;
   }
@@ -420,6 +424,7 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
 
 // After the barrier: the first row (its source section belongs to another warp), then elimination of the
 // interior currents towards the last one.  `aown`: the first current is itself a separator (branch heads 29, 41, 65).
+template <bool NOISE>
 __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st) {
   const int pw = seg_prev(w), n0 = 23 + KD * w;
   const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
@@ -431,7 +436,7 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
             st.I0, st.D0, st.c[0], c_sib, st.x[0], 0.0, 0.0, st.gbf, diag, rhs);
     st.y[0] = diag; st.x[0] = rhs;
   }
-  if (P.noise) {  // dipole sources of the pharynx/mouth sections: S = -sample (TdsModel.cpp:1936), sample = out * amp
+  if (NOISE) {  // dipole sources of the pharynx/mouth sections: S = -sample (TdsModel.cpp:1936), sample = out * amp
 #pragma unroll
     for (int k = 0; k < KD; k++) {
       const int j = n0 + k - PHAR0;
@@ -461,6 +466,7 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
   else { S.sideDD[w][lane] = dda; S.sideDR[w][lane] = dra; }
 }
 
+template <bool NOISE>
 __device__ __forceinline__ void dwarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st) {
   const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
   const double ub = S.sepR[seg_b(w)][lane], ua = S.sepR[seg_a(w)][lane];
@@ -473,7 +479,7 @@ __device__ __forceinline__ void dwarp_back(const TdsParams &P, TdsSmem &S, const
     st.x[k] = un;
   }
   S.uext[w][lane] = st.x[0];
-  if (P.noise) {  // noiseMagnitude of the currents 25..65 (TdsModel.cpp:2052-2060)
+  if (NOISE) {  // noiseMagnitude of the currents 25..65 (TdsModel.cpp:2052-2060)
 #pragma unroll
     for (int k = 0; k < KD; k++) {
       const int j = 23 + KD * w + k - PHAR0;
@@ -690,6 +696,7 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
   }
 }
 
+template <bool NOISE>
 __device__ __forceinline__ void swarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, const SCfg &c,
                                            SRegs &st) {
   const STab &C = S.stab[w];
@@ -711,7 +718,7 @@ __device__ __forceinline__ void swarp_back(const TdsParams &P, TdsSmem &S, const
   }
   if (c.fossa) {
     st.x[3] = ua;
-    if (P.noise) S.nmag[41][lane] = fma(P.nm_a, S.nmag[41][lane], P.nm_1a * ua);
+    if (NOISE) S.nmag[41][lane] = fma(P.nm_a, S.nmag[41][lane], P.nm_1a * ua);
   }
   {
     const double xa0 = c.n2 ? st.x[0] : st.x[5], xm = c.n2 ? st.x[1] : st.x[6], xb1 = c.n2 ? st.x[2] : st.x[7];
@@ -829,6 +836,17 @@ __device__ __forceinline__ uint32_t rng_next(TdsSmem &S, const int lane, int &ri
   return v >> 1;
 }
 
+// exp(t) for -0.75 <= t <= 0 (cutoff <= 2000 Hz at fs >= 16.8 kHz), Taylor series to full double accuracy; libm exp else
+__device__ __forceinline__ double exp_small(double t) {
+  if (t < -0.75) return exp(t);
+  double y = 1.0 / 355687428096000.0;  // 1/17!
+  const double c[17] = {1.0 / 20922789888000.0, 1.0 / 1307674368000.0, 1.0 / 87178291200.0, 1.0 / 6227020800.0,
+                        1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                        1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+#pragma unroll
+  for (int i = 0; i < 17; i++) y = fma(y, t, c[i]);
+  return y;
+}
 // Tube::interpolate (Tube.cpp:449-466) exactly as the reference rounds it
 __device__ __forceinline__ double nz_lerp(double r1, double a, double r, double b) { return __dadd_rn(__dmul_rn(r1, a), __dmul_rn(r, b)); }
 __device__ __forceinline__ double nz_area(const TdsSmem &S, const int lane, double r, double r1, int j) {
@@ -902,11 +920,12 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
     if (j == lL) { pLL = pos; eLL = len; }
     if (j == lL + 1) pNL = pos;
     pos = end;
+    if (have15 && (haveT || !t1) && (j > l1) && (j > l2) && (j > lL)) break;  // (teeth position only matters with a tongue constriction)
   }
   // constriction 0: the glottis, obstacle 1.5 cm downstream (TdsModel.cpp:1222-1229)
   if (have15) {
     C[0].valid = 1; C[0].nar = -1; C[0].kind = 0; C[0].up = s15;
-    C[0].downF = __ddiv_rn(__dsub_rn(1.5, p15), e15);
+    C[0].downF = fast_div(__dsub_rn(1.5, p15), e15);
   }
   double minTongueAreaForTeeth = 1000000.0;
   // tongue constrictions: the jet hits the teeth when they are closer than 2 cm, else the next section
@@ -922,7 +941,7 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
       x = __dadd_rn(pN, __dmul_rn(0.5, eN)); sec = last + 1; p = pN; e = eN; ok = true;  // (inside section last+1)
     }
     c.valid = ok ? 1 : 0; c.nar = nar; c.kind = 1; c.up = sec;
-    c.downF = __ddiv_rn(__dsub_rn(x, p), e);
+    c.downF = fast_div(__dsub_rn(x, p), e);
     c.teeth = fabs(__dsub_rn(x, teeth)) < 0.0001 ? 1 : 0;
     c.lateral = lat > 0.1 ? 1 : 0;
   };
@@ -931,7 +950,7 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
   // lip constriction (TdsModel.cpp:1380-1418): the obstacle is the downstream end of its last section
   if (lipCand && (minL < minTongueAreaForTeeth)) {
     C[3].valid = 1; C[3].nar = iL; C[3].kind = 2; C[3].up = lL;
-    C[3].downF = __ddiv_rn(__dsub_rn(pNL, pLL), eLL);
+    C[3].downF = fast_div(__dsub_rn(pNL, pLL), eLL);
   }
 }
 
@@ -964,16 +983,16 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
     if (A < kMinArea) A = kMinArea;
     if (A < 0.1) A = 0.1;
     if (flow < 0.0) flow = 0.0;
-    const double v = flow / A;
+    const double v = fast_div(flow, A);
     double gain, cutoff = 6000.0;
     if (C[k].kind == 2) gain = 2.0e-7;
-    else if (C[k].kind == 0) gain = 0.5e-7 * pow(10.0, asp_dB / 20.0);
+    else if (C[k].kind == 0) gain = 0.5e-7 * exp(asp_dB * (2.302585092994045684 / 20.0));  // 10^(dB/20)
     else {
-      const double d = sqrt(4.0 * A / kPi);
-      cutoff = 0.15 * v / d;
+      const double id = fast_rsqrt(A * (4.0 / kPi));  // 1/d, d = sqrt(4 A / pi)
+      cutoff = 0.15 * v * id;
       gain = C[k].teeth ? 10.0e-7 : 5.0e-7;
     }
-    double fullAmp = gain * fabs(v) * v * v * sqrt(A);
+    double fullAmp = gain * fabs(v) * v * v * fast_sqrt(A);
     if (C[k].lateral) fullAmp = 0.0;
     if (cutoff < 50.0) cutoff = 50.0;
     if (cutoff > 2000.0) cutoff = 2000.0;
@@ -996,13 +1015,11 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
     double out = S.nout[j][lane];
     if ((old >= 0.001) && (a < 0.001)) out = 0.0;
     if (a >= 0.001) {
-      const double x = exp(-2.0 * kPi * (cut * P.dt));  // IirFilter::createSinglePoleLowpass (IirFilter.cpp:235-243)
+      const double x = exp_small(-2.0 * kPi * (cut * P.dt));  // IirFilter::createSinglePoleLowpass (IirFilter.cpp:235-243)
       uint32_t isum = 0;  // 12 x rand() summed in an int: wraps around like the reference's
       for (int q = 0; q < 12; q++) isum += rng_next(S, lane, N.ri);
       double in = (double)(int32_t)isum;
-      in = __ddiv_rn(in, 2147483647.0);
-      in = __dsub_rn(in, 6.0);
-      in = __ddiv_rn(in, 3.4641016151377543864);  // sqrt(12.0)
+      in = (in * (1.0 / 2147483647.0) - 6.0) * 0.28867513459481288225;  // / RAND_MAX, - 6, / sqrt(12)
       out = __dadd_rn(__dmul_rn(__dsub_rn(1.0, x), in), __dmul_rn(x, out));
     }
     if ((a < 1.0e-30) && (tgt == 0.0)) { a = 0.0; N.nz &= ~(1ull << j); }  // (the reference lets it decay for ever)
@@ -1301,7 +1318,7 @@ __device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const
 
 // The time loop, one instantiation per warp role.  All roles execute the same sequence of CTA barriers.
 //   ROLE 0: dynamic chain, 1: static chain, 2: X1 (glottis + output), 3: X2 (radiation loads; noise sources)
-template <int ROLE, int V>
+template <int ROLE, bool NOISE>
 __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const KArgs &A, const int lane, const int warp,
                                          const bool hw_ok) {
   const int tract_raw = blockIdx.x * P.lanes_per_cta + lane;
@@ -1336,7 +1353,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (ROLE == 3) {
 #pragma unroll
     for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; }
-    if (P.noise) rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ri);
+    if (NOISE) rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ri);
   }
   if (ROLE == 2) {
     xr.G = GlottisState{0.0, 0.0, 0.0, 0.0};
@@ -1353,7 +1370,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (T > 0) {
     i0 = A.bounds[0]; i1 = A.bounds[1];
     inv_len = 1.0 / (double)(i1 - i0);
-    stage_interval(S, lane, warp, my_frames, my_glottis, 0, P.noise != 0);
+    stage_interval(S, lane, warp, my_frames, my_glottis, 0, NOISE);
     cta_sync();
     if (ROLE == 2) {  // glottis geometry of step 0
       double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
@@ -1375,7 +1392,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       interval++;
       i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
       inv_len = 1.0 / (double)(i1 - i0);
-      stage_interval(S, lane, warp, my_frames, my_glottis, interval, P.noise != 0);
+      stage_interval(S, lane, warp, my_frames, my_glottis, interval, NOISE);
       cta_sync();
     }
     X.ratio = (double)(n - i0) * inv_len;  // (1 ulp from the reference's i / N; irrelevant at the 1e-6 bar)
@@ -1395,7 +1412,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
       }
     }
-    if (ROLE == 3 && P.noise && X.rows) {  // noise sources of step n (needs the update of the radiation currents above)
+    if (ROLE == 3 && NOISE && X.rows) {  // noise sources of step n (needs the update of the radiation currents above)
       const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
       NoiseCons cons[4];
       noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, cons);
@@ -1408,7 +1425,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     if (ROLE == 2 && n > 0) emit_output(P, S, xr, lane, n, active, tract, n_out, A.audio, A.flow, bad);
     if (!X.rows) break;
     // ============ first rows + elimination of the segments || glottis ============
-    if (ROLE == 0) dwarp_eliminate(P, S, lane, warp, dst);
+    if (ROLE == 0) dwarp_eliminate<NOISE>(P, S, lane, warp, dst);
     if (ROLE == 1) {
       const double psrc = X.ratio1 * S.gctl[0][G_PRESSURE][lane] + X.ratio * S.gctl[1][G_PRESSURE][lane];
       swarp_eliminate(P, S, lane, warp, scfg, sst, psrc);
@@ -1422,6 +1439,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       double ctl[AFS_NUM_GLOTTIS_CONTROL], p[4], len[2], ar[2];
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = X.ratio1 * S.gctl[0][c][lane] + X.ratio * S.gctl[1][c][lane];
       for (int c = 0; c < 4; c++) p[c] = S.p4[c][lane];
+      glottis_dims(P, ctl, xr.G, xr.GD);  // (recomputed rather than carried over from the last step: X1 is short of registers)
       glottis_inc_time(P, ctl, xr.G, p, xr.GD);
       const double rn = (double)(n + 1 - i0) * inv_len, rn1 = 1.0 - rn;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = rn1 * S.gctl[0][c][lane] + rn * S.gctl[1][c][lane];
@@ -1446,8 +1464,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     cta_sync();
     AFS_TICK(5);
     // ============ back substitution inside the segments ============
-    if (ROLE == 0) dwarp_back(P, S, lane, warp, dst);
-    if (ROLE == 1) swarp_back(P, S, lane, warp, scfg, sst);
+    if (ROLE == 0) dwarp_back<NOISE>(P, S, lane, warp, dst);
+    if (ROLE == 1) swarp_back<NOISE>(P, S, lane, warp, scfg, sst);
     if (ROLE == 3) radiation_back(S, lane, rr);
     AFS_TICK(6);
     cta_sync();
@@ -1459,6 +1477,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;
 }
 
+// NOISE = generate_noise_sources: a separate instantiation, so that the (large) noise-source code of warp X2 does not
+// sit in the instruction stream of the noise-free kernel.
+template <bool NOISE>
 __global__ void __launch_bounds__(TDS_THREADS, 1)
 tds_batch_kernel(const TdsParams P, const KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1519,10 +1540,10 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
   __syncthreads();
 
   switch (warp) {
-    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, 0>(P, S, A, lane, warp, hw_lane < LANES); break;
-    case W_X1: run_role<2, 0>(P, S, A, lane, warp, hw_lane < LANES); break;
-    case W_X2: run_role<3, 0>(P, S, A, lane, warp, hw_lane < LANES); break;
-    default: run_role<0, 0>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, NOISE>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_X1: run_role<2, NOISE>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_X2: run_role<3, NOISE>(P, S, A, lane, warp, hw_lane < LANES); break;
+    default: run_role<0, NOISE>(P, S, A, lane, warp, hw_lane < LANES); break;
   }
 }
 static_assert(NSEP == NW, "prologue zeroing assumes NSEP == NW");
@@ -1593,12 +1614,13 @@ cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tu
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
   static_assert(sizeof(TdsSmem) <= 227 * 1024, "TdsSmem exceeds the 227 KB a CTA can have on sm_100a");
-  cudaError_t e = cudaFuncSetAttribute(tds_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  auto kernel = P.noise ? tds_batch_kernel<true> : tds_batch_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(TdsSmem));  // per device; cheap
   if (e != cudaSuccess) return e;
   const int ctas = (P.n_tracts + P.lanes_per_cta - 1) / P.lanes_per_cta;
   KArgs A{d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, d_dump, d_seeds};
-  tds_batch_kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, A);
+  kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, A);
   return cudaGetLastError();
 }
 
