@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-EXTRA_DEFS = ["-DAFS_TDS_TIMING"] if os.environ.get("AFS_TDS_TIMING") else []
+EXTRA_DEFS = (["-DAFS_TDS_TIMING"] if os.environ.get("AFS_TDS_TIMING") else []) + os.environ.get("AFS_EXTRA_DEFS", "").split()
 COMMON = [*EXTRA_DEFS, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 # per-file device flags
 UNITS = {

@@ -1415,9 +1415,15 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     if (ROLE == 3 && NOISE && X.rows) {  // noise sources of step n (needs the update of the radiation currents above)
       const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
       NoiseCons cons[4];
+#ifndef AFS_NZ_SKIP_SCAN
       noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, cons);
+#else
+      for (int k = 0; k < 4; k++) { cons[k].valid = k == 0; cons[k].nar = -1; cons[k].kind = 0; cons[k].up = 3; cons[k].teeth = 0; cons[k].lateral = 0; cons[k].downF = 0.3; }
+#endif
       const double asp = nz_lerp(re1, S.gctl[0][G_ASP][lane], re, S.gctl[1][G_ASP][lane]);
+#ifndef AFS_NZ_SKIP_SRC
       noise_sources(P, S, lane, nr, cons, re, re1, n & 1, asp);
+#endif
     }
     AFS_TICK(1);
     cta_sync();
