@@ -247,27 +247,21 @@ __device__ __forceinline__ void row_dyn(const TdsParams &P, int fl, double E_A, 
                                         double D_A, double E_B, double L_B, double R_B, double ib, double D_B, double c,
                                         double c_sib, double uB, double areaA, double areaB, double &gbf, double &diag,
                                         double &rhs) {
-  double L_AB = L_A + L_B;
-  if (fl & RF_JUNCTION) {
-    L_AB = fma(P.k_sondhi, fabs(ia - ib), L_AB);  // Sondhi (TdsModel.cpp:1745-1778); 0 when the option is off
-    // Bernoulli loss wide -> narrow (TdsModel.cpp:850-877); area_B < area_A <=> ib > ia
-    const bool on = ((ib > ia) && (uB > 0)) || ((ib < ia) && (uB < 0));
-    const double qa = ia * ia * (1.0 / kPi), qb = ib * ib * (1.0 / kPi);  // 1/area
-    const double ku = on ? uB * P.k_bern : 0.0;                            // u rho/2, 0 when the option is off
-    R_A = fma(-ku, qa * qa, R_A);
-    R_B = fma(ku, qb * qb, R_B);
-  } else if (fl & RF_GLO) {  // glottal entrance loss (TdsModel.cpp:900-920)
-    const double qT = ib * ib * (1.0 / kPi), qS = ia * ia * (1.0 / kPi);
-    const double ku = uB > 0 ? P.k_ent * 0.5 * kRho * uB : 0.0;
-    R_B = fma(ku, qT * qT - qS * qS, R_B);
-  } else if (fl & RF_GUP) {  // lower -> upper glottis section (TdsModel.cpp:930-950)
-    const double qS = ia * ia * (1.0 / kPi), qT = ib * ib * (1.0 / kPi);
-    const double target = (areaB < P.fsar * areaA) ? 1.0 : 0.0;  // compared on the areas themselves, like the reference:
-                                                                 // the two glottal areas can be equal to the last bit
-    gbf = 0.8 * gbf + (1.0 - 0.8) * target;
-    const double ku = uB > 0 ? gbf * uB * (0.5 * kRho) : 0.0;
-    R_A = fma(ku, qT * qT - qS * qS, R_A);
-  }
+  // (branch-free: a flag only selects factors)
+  const bool junction = (fl & RF_JUNCTION) != 0, glo = (fl & RF_GLO) != 0, gup = (fl & RF_GUP) != 0;
+  const double qa = ia * ia * (1.0 / kPi), qb = ib * ib * (1.0 / kPi);  // 1/area_A, 1/area_B
+  // Sondhi junction inductance (TdsModel.cpp:1745-1778); 0 when the option is off
+  const double L_AB = fma(junction ? P.k_sondhi : 0.0, fabs(ia - ib), L_A + L_B);
+  // Bernoulli loss wide -> narrow (TdsModel.cpp:850-877); area_B < area_A <=> ib > ia
+  const bool on = junction && (((ib > ia) && (uB > 0)) || ((ib < ia) && (uB < 0)));
+  const double kb = on ? uB * P.k_bern : 0.0;  // u rho/2, 0 when the option is off
+  // glottal entrance loss (TdsModel.cpp:900-920) on R_B / lower -> upper glottis section (:930-950) on R_A
+  const double target = (areaB < P.fsar * areaA) ? 1.0 : 0.0;  // compared on the areas themselves, like the reference:
+  gbf = gup ? 0.8 * gbf + (1.0 - 0.8) * target : gbf;          // the two glottal areas can be equal to the last bit
+  const double up = uB > 0 ? uB * (0.5 * kRho) : 0.0;
+  const double dq = qb * qb - qa * qa;                          // 1/area_T^2 - 1/area_S^2
+  R_A = fma(-kb, qa * qa, fma(gup ? gbf * up : 0.0, dq, R_A));
+  R_B = fma(kb, qb * qb, fma(glo ? P.k_ent * up : 0.0, dq, R_B));
   diag = E_B + E_A + fma(L_AB, P.idt, R_A + R_B);
   rhs = fma(L_AB, c, fma(L_A, c_sib, D_A - D_B));
 }
@@ -316,48 +310,39 @@ __device__ __forceinline__ void dump_section(const TdsParams &P, double *dump, i
 
 // Pass A: state update with the solution of the previous step (TdsModel.cpp:2046-2098), then elements, E, D
 // (:718-1010) and the rows of all currents but the first (:1785-2039) of the new step.
-// V selects the code: 0 = GP (2 glottal + 4 pharynx sections), 1 = pharynx/mouth only, 2 = NV (velum port + 2 rigid
-// nose sections): the kind of every slot is a compile-time constant, the body is branch-free straight-line code
-// (update and rows both on, no state dump); V = -1: generic version with run-time kinds, used for the first and the
-// last iteration and when a state dump is requested.
-enum { GEOM_PM = 0, GEOM_GLOTTIS = 1, GEOM_VELUM = 2, GEOM_RIGID = 3 };
-template <int V>
-__device__ __forceinline__ int slot_geom(int k, int sec) {
-  if (V == 0) return k < 2 ? GEOM_GLOTTIS : GEOM_PM;
-  if (V == 1) return GEOM_PM;
-  if (V == 2) return k < 4 ? GEOM_VELUM : GEOM_RIGID;
-  return sec <= GLOT_UP ? GEOM_GLOTTIS : sec <= MOUTH_LAST ? GEOM_PM : sec <= 68 ? GEOM_VELUM : GEOM_RIGID;
-}
-template <int V>
-__device__ __forceinline__ int slot_row_flags(int k, int sec) {
-  if (V == 0) return k == 1 ? RF_GUP : k >= 3 ? RF_JUNCTION : 0;  // rows 24 | 26, 27, 28 (row 25: plain; row 23 later)
-  if (V == 1) return RF_JUNCTION;                                  // (k >= 1)
-  if (V == 2) return 0;
-  return row_flags(sec);
-}
-template <int V>
+// HOT = true is the loop body of all steps but the first and the last: update and rows both on, and the slot body is
+// BRANCH-FREE (the kind of a section only selects values), so that the update chain and the geometry chain of a slot
+// -- and neighbouring slots -- overlap: the kernel is bound by the latency of dependent FP64 operations, not by the
+// pipe.  HOT = false (first / last step, state dumps) takes the flags from X.
+template <bool HOT>
 __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st,
-                                             const StepCtx &X, double *dump) {
-  constexpr bool FAST = V >= 0;
-  const bool upd = FAST ? true : X.upd, rows = FAST ? true : X.rows;
+                                             const StepCtx &X) {
+  const bool upd = HOT ? true : X.upd, rows = HOT ? true : X.rows;
   const int n0 = 23 + KD * w;
   double outLast = 0.0;
   if (upd) outLast = S.uext[seg_out0(w)][lane] + S.uext[seg_out1(w)][lane];
   double pE = 0.0, pL = 0.0, pR = 0.0, pI = 0.0, pD = 0.0, pA = 0.0;  // record of the previous slot
+  const int par = X.n & 1;
+  double vel = 0.0;
+  if (rows) vel = X.ratio1 * S.velum[0][lane] + X.ratio * S.velum[1][lane];
 #pragma unroll
   for (int k = 0; k < KD; k++) {
     double p_ = st.p[k], pr_ = st.pr[k], c_ = st.c[k];
     const double u_ = st.x[k], un_ = (k < KD - 1) ? st.x[k + 1] : outLast;
     double x_ = u_, y_ = 0.0;
     const int sec = n0 + k, rec = KD * w + k;
-    const int geom = slot_geom<V>(k, sec);
-    const bool wall = geom != GEOM_GLOTTIS;  // (soft walls off: kalpha = kc = 0, the wall state stays 0)
-    double wc = 0.0, wcr = 0.0, wcr2 = 0.0;
-    if (wall) { wc = S.wall[sec][0][lane]; wcr = S.wall[sec][1][lane]; wcr2 = S.wall[sec][2][lane]; }
+    // kind of the section (warp-uniform): glottis only in slots 0, 1 (warp GP), velum port only in slots 0..3 (warp NV)
+    const bool glottal = k < 2 && sec <= GLOT_UP;
+    const bool velum = k < 4 && sec >= NOSE0;
+    const bool rigid = k >= 4 && sec > MOUTH_LAST;
+    // soft walls: none in the glottis (zero constants keep its wall state at 0; also when the option is off)
+    const double ka = glottal ? 0.0 : P.kalpha[0];
+    const double kc0 = glottal ? 0.0 : P.kc[0][0], kc1 = glottal ? 0.0 : P.kc[0][1], kc2 = glottal ? 0.0 : P.kc[0][2];
+    double wc = S.wall[sec][0][lane], wcr = S.wall[sec][1][lane], wcr2 = S.wall[sec][2][lane];
     if (upd) {
       const double u = u_, out = un_;
       const double E_old = S.Ed[rec][lane], al_old = S.Al[rec][lane];
-      const double beta_old = wall ? wall_beta3(P.kc[0], wc, wcr, wcr2) : 0.0;
+      const double beta_old = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
       const double D_old = fma(-E_old, beta_old, fma(P.dtth1, pr_, p_));
       // current: u' = (u_new - u_old)/(dt theta) - (theta1/theta) u'_old = u_new/(dt theta) - c
       const double ur = fma(u, P.idt, -c_);
@@ -365,41 +350,35 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       const double p_new = fma(E_old, u - out, D_old);
       const double pr_new = (p_new - p_) * P.idt - pr_ * P.th;
       p_ = p_new; pr_ = pr_new;
-      if (wall) {
-        const double wc_new = fma(pr_new, al_old, beta_old);
-        const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
-        const double wcr2_new = (wcr_new - wcr) * P.idt - wcr2 * P.th;
-        wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
-        S.wall[sec][0][lane] = wc; S.wall[sec][1][lane] = wcr; S.wall[sec][2][lane] = wcr2;
-      }
-      if (V == 0 ? k < 3 : (V < 0 && sec <= PHAR0)) S.p4[sec - TRACHEA_LAST][lane] = p_new;  // sections 23, 24, 25
+      const double wc_new = fma(pr_new, al_old, beta_old);
+      const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
+      const double wcr2_new = (wcr_new - wcr) * P.idt - wcr2 * P.th;
+      wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
+      S.wall[sec][0][lane] = wc; S.wall[sec][1][lane] = wcr; S.wall[sec][2][lane] = wcr2;
+      if (k < 3 && sec <= PHAR0) S.p4[sec - TRACHEA_LAST][lane] = p_new;  // sections 23, 24, 25
     }
     if (rows) {
-      double area, length;
-      if (geom == GEOM_PM) {  // Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350)
-        const int j = sec - PHAR0;
-        area = X.ratio1 * S.fA[0][j][lane] + X.ratio * S.fA[1][j][lane];
-        length = X.ratio1 * S.fLen[0][j][lane] + X.ratio * S.fLen[1][j][lane];
-      } else if (geom == GEOM_GLOTTIS) {  // glottis sections from the glottis model (Synthesizer.cpp:576-579)
-        area = S.glArea[X.n & 1][sec - GLOT_LO][lane];
-        length = S.glLen[X.n & 1][sec - GLOT_LO][lane];
-      } else if (geom == GEOM_VELUM) {  // velum port: Tube::setVelumOpening (Tube.cpp:402-416)
-        const int j = sec - NOSE0;
-        const double v = X.ratio1 * S.velum[0][lane] + X.ratio * S.velum[1][lane];
-        area = v + ((double)(j * j) * (4.24 - v)) / 16.0;
-        length = (11.4 / 11.4) * 0.6;
-      } else {  // rigid nose sections 69, 70 (Tube.cpp:155-157)
-        area = sec == 69 ? 4.24 : 3.26;
-        length = (11.4 / 11.4) * 0.6;
+      // Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350); the index is clamped for the other kinds
+      const int j = min(max(sec - PHAR0, 0), AFS_NUM_PM_SECTIONS - 1);
+      double area = X.ratio1 * S.fA[0][j][lane] + X.ratio * S.fA[1][j][lane];
+      double length = X.ratio1 * S.fLen[0][j][lane] + X.ratio * S.fLen[1][j][lane];
+      if (k < 2) {  // glottis sections from the glottis model (Synthesizer.cpp:576-579)
+        const double ga = S.glArea[par][k][lane], gl = S.glLen[par][k][lane];
+        area = glottal ? ga : area; length = glottal ? gl : length;
+      }
+      if (k < 4) {  // velum port: Tube::setVelumOpening (Tube.cpp:402-416)
+        const double va = vel + ((double)(k * k) * (4.24 - vel)) / 16.0;
+        area = velum ? va : area; length = velum ? (11.4 / 11.4) * 0.6 : length;
+      } else {      // rigid nose sections 69, 70 (Tube.cpp:155-157)
+        area = rigid ? (k == 4 ? 4.24 : 3.26) : area; length = rigid ? (11.4 / 11.4) * 0.6 : length;
       }
       area = fmax(area, kMinArea);
       double L, R, invr, circ;
-      section_elements(area, length, geom == GEOM_GLOTTIS, L, R, invr, circ);
+      section_elements(area, length, glottal, L, R, invr, circ);
       const double C = (area * length) * (1.0 / (kRho * kC * kC));
-      double alpha = 0.0;
-      if (wall) alpha = fmax(circ * length, kMinArea) * P.kalpha[0];  // TdsModel.cpp:805-832
+      const double alpha = fmax(circ * length, kMinArea) * ka;  // TdsModel.cpp:805-832
       const double E = P.dtth * fast_rcp(C + alpha);
-      const double beta = wall ? wall_beta3(P.kc[0], wc, wcr, wcr2) : 0.0;
+      const double beta = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
       const double D = fma(-E, beta, fma(P.dtth1, pr_, p_));  // TdsModel.cpp:988-1008, no flow sources
       S.Ed[rec][lane] = E; S.Al[rec][lane] = alpha;
       if (k == 0) {
@@ -408,7 +387,7 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       } else {
         // (the lower -> upper glottis row can only be slot 1, the entrance row only slot 0: keeps their code and the
         //  registers they need out of the other slots)
-        const int fl = slot_row_flags<V>(k, sec) & (k == 1 ? (RF_JUNCTION | RF_GUP) : RF_JUNCTION);
+        const int fl = row_flags(sec) & (k == 1 ? (RF_JUNCTION | RF_GUP) : RF_JUNCTION);
         row_dyn(P, fl, pE, pL, pR, pI, pD, E, L, R, invr, D, c_, 0.0, u_, k == 1 ? pA : 0.0, area, st.gbf, y_, x_);
       }
       if (k == KD - 1) {
@@ -1401,10 +1380,11 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(0);
     // ============ pass A: update (step n-1), elements + rows (step n) ============
     // (state dump requested for this step: update and rows in two separate passes, the dump in between)
-    for (int half = 0; half < (X.dumping ? 2 : 1); half++) {
+    if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true>(P, S, lane, warp, dst, X);
+    else for (int half = 0; half < (X.dumping ? 2 : 1); half++) {
       StepCtx Y = X;
       if (X.dumping) { Y.upd = X.upd && half == 0; Y.rows = X.rows && half == 1; }
-      if (ROLE == 0) dwarp_pass_a<-1>(P, S, lane, warp, dst, Y, A.dump);
+      if (ROLE == 0) dwarp_pass_a<false>(P, S, lane, warp, dst, Y);
       if (ROLE == 1) swarp_pass_a(P, S, lane, warp, scfg, sst, Y);
       if (ROLE == 3 && Y.upd) radiation_update(P, lane, rr, nr, Y, A.dump);
       if (X.dumping && half == 0) {
