@@ -179,6 +179,21 @@ __device__ __forceinline__ int seg_a(int w) {
   }
 }
 
+// The per-warp topology constants above, packed into ONE opaque register once per launch (otherwise the compiler
+// re-derives them with compare/branch chains in every step): out0:5 | out1:5 | b:4 | a:4 | prev:4 | csib+1:3.
+__device__ __forceinline__ unsigned wcfg_make(int w) {
+  unsigned v = (unsigned)seg_out0(w) | ((unsigned)seg_out1(w) << 5) | ((unsigned)seg_b(w) << 10) | ((unsigned)seg_a(w) << 14) |
+               (((unsigned)seg_prev(w) & 15u) << 18) | ((unsigned)(csib_slot(w) + 1) << 22);
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ int wc_out0(unsigned c) { return (int)(c & 31u); }
+__device__ __forceinline__ int wc_out1(unsigned c) { return (int)((c >> 5) & 31u); }
+__device__ __forceinline__ int wc_b(unsigned c) { return (int)((c >> 10) & 15u); }
+__device__ __forceinline__ int wc_a(unsigned c) { return (int)((c >> 14) & 15u); }
+__device__ __forceinline__ int wc_prev(unsigned c) { return (int)((c >> 18) & 15u); }
+__device__ __forceinline__ int wc_csib(unsigned c) { return (int)((c >> 22) & 7u) - 1; }
+
 // ---- fast FP64 reciprocal / sqrt (branch-free) -----------------------------------
 // IEEE division / sqrt compile to ~20-instruction sequences with a slow-path CALL that fences the
 // scheduler; all operands here are positive, normal and well inside the range, so MUFU seed + two
@@ -192,6 +207,18 @@ __device__ __forceinline__ double fast_rcp(double x) {
   e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   return y;
+}
+// One Newton step (relative error ~2e-14 after the 2^-23 seed): enough for the network ELEMENTS, whose rounding only
+// perturbs coefficients; the pivots of the solve keep two steps.
+__device__ __forceinline__ double fast_rcp1(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return fma(y, fma(-x, y, 1.0), y);
+}
+__device__ __forceinline__ double fast_rsqrt1(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return fma(y, fma(-0.5 * x * y, y, 0.5), y);
 }
 __device__ __forceinline__ double fast_div(double a, double b) {
   const double y = fast_rcp(b);
@@ -217,8 +244,9 @@ __device__ __forceinline__ double fast_sqrt(double x) {  // x > 0
 // Network elements of a non-sinus section (TdsModel.cpp:759-793).
 __device__ __forceinline__ void section_elements(double area, double length, bool glottal, double &L, double &R,
                                                  double &invr, double &circ) {
-  const double inva = fast_rcp(area);
-  const double r = fast_sqrt(area * (1.0 / kPi));
+  const double inva = fast_rcp1(area);
+  const double q = area * (1.0 / kPi);
+  const double r = q * fast_rsqrt1(q);
   invr = r * kPi * inva;
   circ = 2.0 * kPi * r;  // 2*sqrt(area*pi)
   L = (kRho * 0.5 * length) * inva;
@@ -315,12 +343,12 @@ __device__ __forceinline__ void dump_section(const TdsParams &P, double *dump, i
 // -- and neighbouring slots -- overlap: the kernel is bound by the latency of dependent FP64 operations, not by the
 // pipe.  HOT = false (first / last step, state dumps) takes the flags from X.
 template <bool HOT>
-__device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st,
-                                             const StepCtx &X) {
+__device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
+                                             DRegs &st, const StepCtx &X) {
   const bool upd = HOT ? true : X.upd, rows = HOT ? true : X.rows;
   const int n0 = 23 + KD * w;
   double outLast = 0.0;
-  if (upd) outLast = S.uext[seg_out0(w)][lane] + S.uext[seg_out1(w)][lane];
+  if (upd) outLast = S.uext[wc_out0(wc_)][lane] + S.uext[wc_out1(wc_)][lane];
   double pE = 0.0, pL = 0.0, pR = 0.0, pI = 0.0, pD = 0.0, pA = 0.0;  // record of the previous slot
   const int par = X.n & 1;
   double vel = 0.0;
@@ -377,13 +405,13 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       section_elements(area, length, glottal, L, R, invr, circ);
       const double C = (area * length) * (1.0 / (kRho * kC * kC));
       const double alpha = fmax(circ * length, kMinArea) * ka;  // TdsModel.cpp:805-832
-      const double E = P.dtth * fast_rcp(C + alpha);
+      const double E = P.dtth * fast_rcp1(C + alpha);
       const double beta = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
       const double D = fma(-E, beta, fma(P.dtth1, pr_, p_));  // TdsModel.cpp:988-1008, no flow sources
       S.Ed[rec][lane] = E; S.Al[rec][lane] = alpha;
       if (k == 0) {
         st.L0 = L; st.R0 = R; st.I0 = invr; st.D0 = D;
-        if (csib_slot(w) >= 0) S.csib[csib_slot(w)][lane] = c_;
+        if (wc_csib(wc_) >= 0) S.csib[wc_csib(wc_)][lane] = c_;
       } else {
         // (the lower -> upper glottis row can only be slot 1, the entrance row only slot 0: keeps their code and the
         //  registers they need out of the other slots)
@@ -404,12 +432,13 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
 // After the barrier: the first row (its source section belongs to another warp), then elimination of the
 // interior currents towards the last one.  `aown`: the first current is itself a separator (branch heads 29, 41, 65).
 template <bool NOISE>
-__device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st) {
-  const int pw = seg_prev(w), n0 = 23 + KD * w;
+__device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
+                                                DRegs &st) {
+  const int pw = wc_prev(wc_), n0 = 23 + KD * w;
   const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
   const double E_A = S.bE[pw][lane], E_0 = S.Ed[KD * w][lane];
   {
-    const double c_sib = csib_slot(w) >= 0 ? S.csib[csib_slot(w) ^ 1][lane] : 0.0;  // 29 <-> 84, 41 <-> 65
+    const double c_sib = wc_csib(wc_) >= 0 ? S.csib[wc_csib(wc_) ^ 1][lane] : 0.0;  // 29 <-> 84, 41 <-> 65
     double diag, rhs;
     row_dyn(P, row_flags(n0), E_A, S.bL[pw][lane], S.bR[pw][lane], S.bI[pw][lane], S.bD[pw][lane], E_0, st.L0, st.R0,
             st.I0, st.D0, st.c[0], c_sib, st.x[0], 0.0, 0.0, st.gbf, diag, rhs);
@@ -438,7 +467,7 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
     rc = fma(-t, rc, rn);
     f = -t * f;
   }
-  const int b = seg_b(w), a = seg_a(w);
+  const int b = wc_b(wc_), a = wc_a(wc_);
   S.sepD[b][lane] = dc; S.sepR[b][lane] = rc;
   S.sideF[w][lane] = f;
   if (aown) { S.sepD[a][lane] = st.y[0] - dda; S.sepR[a][lane] = st.x[0] - dra; }
@@ -446,9 +475,10 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
 }
 
 template <bool NOISE>
-__device__ __forceinline__ void dwarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st) {
+__device__ __forceinline__ void dwarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
+                                           DRegs &st) {
   const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
-  const double ub = S.sepR[seg_b(w)][lane], ua = S.sepR[seg_a(w)][lane];
+  const double ub = S.sepR[wc_b(wc_)][lane], ua = S.sepR[wc_a(wc_)][lane];
   st.x[KD - 1] = ub;
   double un = ub;
 #pragma unroll
@@ -489,6 +519,11 @@ __device__ __forceinline__ SCfg scfg_of(int w) {
   c.leaf0 = w == W_N1 ? 89 : 91;
   c.fossa = w == W_F;
   c.head = w == W_T0;
+  // (opaque to the optimiser: computed once per launch instead of once per step)
+  asm volatile("" : "+r"(c.base), "+r"(c.ks), "+r"(c.leaf0));
+  int fl = (c.leaves ? 1 : 0) | (c.n2 ? 2 : 0) | (c.fossa ? 4 : 0) | (c.head ? 8 : 0);
+  asm volatile("" : "+r"(fl));
+  c.leaves = fl & 1; c.n2 = fl & 2; c.fossa = fl & 4; c.head = fl & 8;
   return c;
 }
 struct SRegs {
@@ -582,10 +617,10 @@ __device__ __forceinline__ void static_section(const TdsParams &P, TdsSmem &S, c
   Dnew = fma(-E, wall_beta3(wk, wc, wcr, wcr2), fma(P.dtth1, pr, p));
 }
 
-__device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, const SCfg &c,
-                                             SRegs &st, const StepCtx &X) {
+__device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
+                                             const SCfg &c, SRegs &st, const StepCtx &X) {
   double outLast = 0.0;
-  if (X.upd) outLast = S.uext[seg_out0(w)][lane];
+  if (X.upd) outLast = S.uext[wc_out0(wc_)][lane];
   const int j0 = c.n2 ? 0 : 5;
   double dn[KS], dl[2] = {0.0, 0.0};
 #pragma unroll
@@ -625,9 +660,9 @@ __device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, con
   }
 }
 
-__device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w,
+__device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
                                                 const SCfg &c, SRegs &st, double psrc) {
-  const int n0 = c.base + c.ks, pw = seg_prev(w);
+  const int n0 = c.base + c.ks, pw = wc_prev(wc_);
   const STab &C = S.stab[w];
   double d84 = 0.0, r0;
   {  // first row: the source section belongs to another warp (or is the lung pressure source)
@@ -658,7 +693,7 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
   }
   st.x[KS - 1] = rc;
   if (!c.fossa) {
-    S.sepR[seg_b(w)][lane] = rc;
+    S.sepR[wc_b(wc_)][lane] = rc;
     S.sideDR[w][lane] = dra;
   } else {
     // current 88 into 84, then 84 out of the clique {28, 29, 84} (couplings through section 28)
@@ -676,8 +711,8 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
 }
 
 template <bool NOISE>
-__device__ __forceinline__ void swarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, const SCfg &c,
-                                           SRegs &st) {
+__device__ __forceinline__ void swarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
+                                           const SCfg &c, SRegs &st) {
   const STab &C = S.stab[w];
   double ua, ub;
   if (c.fossa) {
@@ -685,8 +720,8 @@ __device__ __forceinline__ void swarp_back(const TdsParams &P, TdsSmem &S, const
     ua = (st.x[3] + st.e28 * u28 - st.g28 * u29) * st.w84;
     ub = (st.x[KS - 1] - C.FF * ua) * C.WB;
   } else {
-    ub = S.sepR[seg_b(w)][lane];
-    ua = c.head ? 0.0 : S.sepR[seg_a(w)][lane];
+    ub = S.sepR[wc_b(wc_)][lane];
+    ua = c.head ? 0.0 : S.sepR[wc_a(wc_)][lane];
   }
   st.x[KS - 1] = ub;
   double un = ub;
@@ -1238,10 +1273,10 @@ struct X1Regs {
 };
 // Output of the step whose radiated flows sit in uext[]: radiated flow (TdsModel.cpp:687-705), pressure
 // differentiator + Chebyshev low-pass + decimation (Synthesizer.cpp:614-627).  `n_done` = steps finished.
-__device__ __forceinline__ void emit_output(const TdsParams &P, TdsSmem &S, X1Regs &xr, int lane, int n_done, bool active,
+__device__ __forceinline__ void emit_output(const TdsParams &P, X1Regs &xr, double u_rad, double p25, int n_done, bool active,
                                             int tract, int n_out, double *audio, double *flow, uint32_t &bad) {
-  double u = S.uext[UX_RADM][lane] + S.uext[UX_RADN][lane];
-  if (P.skin) u += iir_step<4>(c_tone_a, c_tone_b, xr.toneX, xr.toneY, S.p4[3][lane]);
+  double u = u_rad;
+  if (P.skin) u += iir_step<4>(c_tone_a, c_tone_b, xr.toneX, xr.toneY, p25);
   if (!isfinite(u)) bad |= 1u;
   const double outP = (u - xr.prevFlow) * P.fs;
   xr.prevFlow = u;
@@ -1264,6 +1299,10 @@ struct KArgs {
 };
 
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+// Named barriers of the solve phase.  Warp X1 (glottis model, output filters) only has to be back for the next pass A:
+// it ARRIVES at barrier 1 once it has read what the others will overwrite and takes no part in barrier 2.
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 #ifdef AFS_TDS_TIMING
 #define AFS_TICK(k) do { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } while (0)
@@ -1316,6 +1355,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   NoiseRegs nr;
   nr.nz = 0; nr.ri = 0; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0;
   const SCfg scfg = scfg_of(warp);
+  const unsigned wcfg = wcfg_make(warp);
   if (ROLE == 0) {
 #pragma unroll
     for (int k = 0; k < KD; k++) { dst.p[k] = dst.pr[k] = dst.c[k] = dst.x[k] = dst.y[k] = dst.h[k] = 0.0; }
@@ -1380,12 +1420,12 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(0);
     // ============ pass A: update (step n-1), elements + rows (step n) ============
     // (state dump requested for this step: update and rows in two separate passes, the dump in between)
-    if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true>(P, S, lane, warp, dst, X);
+    if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true>(P, S, lane, warp, wcfg, dst, X);
     else for (int half = 0; half < (X.dumping ? 2 : 1); half++) {
       StepCtx Y = X;
       if (X.dumping) { Y.upd = X.upd && half == 0; Y.rows = X.rows && half == 1; }
-      if (ROLE == 0) dwarp_pass_a<false>(P, S, lane, warp, dst, Y);
-      if (ROLE == 1) swarp_pass_a(P, S, lane, warp, scfg, sst, Y);
+      if (ROLE == 0) dwarp_pass_a<false>(P, S, lane, warp, wcfg, dst, Y);
+      if (ROLE == 1) swarp_pass_a(P, S, lane, warp, wcfg, scfg, sst, Y);
       if (ROLE == 3 && Y.upd) radiation_update(P, lane, rr, nr, Y, A.dump);
       if (X.dumping && half == 0) {
         if (ROLE == 0) dwarp_dump(P, S, lane, warp, dst, A.dump);
@@ -1408,13 +1448,19 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(1);
     cta_sync();
     AFS_TICK(2);
-    if (ROLE == 2 && n > 0) emit_output(P, S, xr, lane, n, active, tract, n_out, A.audio, A.flow, bad);
+    double x1p[4] = {0.0, 0.0, 0.0, 0.0};
+    if (ROLE == 2) {  // everything X1 reads from the other warps, then it is on its own until the end of the step
+      const double u_rad = S.uext[UX_RADM][lane] + S.uext[UX_RADN][lane];
+      for (int c = 0; c < 4; c++) x1p[c] = S.p4[c][lane];
+      if (X.rows) bar_arrive(1, TDS_THREADS);
+      if (n > 0) emit_output(P, xr, u_rad, x1p[3], n, active, tract, n_out, A.audio, A.flow, bad);
+    }
     if (!X.rows) break;
     // ============ first rows + elimination of the segments || glottis ============
-    if (ROLE == 0) dwarp_eliminate<NOISE>(P, S, lane, warp, dst);
+    if (ROLE == 0) dwarp_eliminate<NOISE>(P, S, lane, warp, wcfg, dst);
     if (ROLE == 1) {
       const double psrc = X.ratio1 * S.gctl[0][G_PRESSURE][lane] + X.ratio * S.gctl[1][G_PRESSURE][lane];
-      swarp_eliminate(P, S, lane, warp, scfg, sst, psrc);
+      swarp_eliminate(P, S, lane, warp, wcfg, scfg, sst, psrc);
     }
     if (ROLE == 3) {
       radiation_eliminate(P, S, lane, W_M3, 0, rr.c[0], rr.c[1], nr.lips, rr.keep[0]);
@@ -1422,9 +1468,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     }
     if (ROLE == 2) {
       // incTime for this step (pressures of the previous step), then the geometry step n+1 will use
-      double ctl[AFS_NUM_GLOTTIS_CONTROL], p[4], len[2], ar[2];
+      double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
+      const double (&p)[4] = x1p;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = X.ratio1 * S.gctl[0][c][lane] + X.ratio * S.gctl[1][c][lane];
-      for (int c = 0; c < 4; c++) p[c] = S.p4[c][lane];
       glottis_dims(P, ctl, xr.G, xr.GD);  // (recomputed rather than carried over from the last step: X1 is short of registers)
       glottis_inc_time(P, ctl, xr.G, p, xr.GD);
       const double rn = (double)(n + 1 - i0) * inv_len, rn1 = 1.0 - rn;
@@ -1435,23 +1481,25 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       S.glArea[par][0][lane] = ar[0]; S.glArea[par][1][lane] = ar[1];
     }
     AFS_TICK(3);
-    cta_sync();
-    // ============ reduced system over the separators ============
-    if (warp == W_T0) reduced_forward(S, lane, 0);
-    if (warp == W_T1) reduced_forward(S, lane, 1);
-    if (warp == W_T2) reduced_forward(S, lane, 2);
-    cta_sync();
-    if (warp == W_T0) reduced_junction(S, lane);
-    cta_sync();
-    if (warp == W_T0) reduced_back(S, lane, 0);
-    if (warp == W_T1) reduced_back(S, lane, 1);
-    if (warp == W_T2) reduced_back(S, lane, 2);
-    AFS_TICK(4);
-    cta_sync();
+    if (ROLE != 2) {
+      bar_sync(1, TDS_THREADS);
+      // ============ reduced system over the separators ============
+      if (warp == W_T0) reduced_forward(S, lane, 0);
+      if (warp == W_T1) reduced_forward(S, lane, 1);
+      if (warp == W_T2) reduced_forward(S, lane, 2);
+      bar_sync(2, TDS_THREADS - 32);
+      if (warp == W_T0) reduced_junction(S, lane);
+      bar_sync(2, TDS_THREADS - 32);
+      if (warp == W_T0) reduced_back(S, lane, 0);
+      if (warp == W_T1) reduced_back(S, lane, 1);
+      if (warp == W_T2) reduced_back(S, lane, 2);
+      AFS_TICK(4);
+      bar_sync(2, TDS_THREADS - 32);
+    }
     AFS_TICK(5);
     // ============ back substitution inside the segments ============
-    if (ROLE == 0) dwarp_back<NOISE>(P, S, lane, warp, dst);
-    if (ROLE == 1) swarp_back<NOISE>(P, S, lane, warp, scfg, sst);
+    if (ROLE == 0) dwarp_back<NOISE>(P, S, lane, warp, wcfg, dst);
+    if (ROLE == 1) swarp_back<NOISE>(P, S, lane, warp, wcfg, scfg, sst);
     if (ROLE == 3) radiation_back(S, lane, rr);
     AFS_TICK(6);
     cta_sync();

@@ -8,7 +8,8 @@ B, T = 4096, 2205
 ctx = afs.Context(0)
 fr, gl = make_tds_batch(B, 1)
 buf = np.zeros(473); ctx.set_state_dump(10**9, buf)
-a, _, _ = ctx.tds_synthesize(fr, gl, [T // 2 + 1], 44100.0, 2)
+noise = os.environ.get('NOISE', '0') == '1'
+a, _, _ = ctx.tds_synthesize(fr, gl, [T // 2 + 1], 44100.0, 2, opts=afs.tds_options_default(noise=noise))
 steps = (T // 2 + 1) * 2
 names = ["top/stage", "passA", "B1 wait", "elim/aux", "reduced", "B5 wait", "back", "B6 wait"]
 roles = ["GP", "P1", "P2", "M0", "M1", "M2", "M3", "NV", "T0", "T1", "N2", "T2", "X1", "F", "X2", "N1"]
