@@ -882,7 +882,8 @@ __device__ __forceinline__ void nz_expand(const TdsSmem &S, const int lane, doub
 
 // State-independent part: the constrictions of this sample and where their noise sources sit.
 __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double r, const double r1,
-                                        const afs_tube_frame *fr0, const afs_tube_frame *fr1, NoiseCons (&C)[4]) {
+                                        const afs_tube_frame *fr0, const afs_tube_frame *fr1, const unsigned long long latAlways,
+                                        const unsigned long long latMaybe, NoiseCons (&C)[4]) {
   constexpr int NPM = AFS_NUM_PM_SECTIONS;
 #pragma unroll
   for (int k = 0; k < 4; k++) { C[k].valid = 0; C[k].nar = -1; C[k].kind = 0; C[k].up = 0; C[k].teeth = 0; C[k].lateral = 0; C[k].downF = 0.0; }
@@ -911,10 +912,21 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
   }
   const bool lipCand = minL < 1.0;
   if (lipCand) nz_expand(S, lane, r, r1, iL, AFS_LOWER_LIP, minL, fL, lL);
-  // laterality of the tongue constrictions (rare: read from the control frames in global memory)
+  // laterality of the tongue constrictions: only `max > 0.1` matters (TdsModel.cpp:1545).  Sections whose two frame
+  // values are both clearly below (above) 0.1 can never (always) trip it; only the others are read from the control
+  // frames in global memory and interpolated like the reference does.
   double lat1 = 0.0, lat2 = 0.0;
-  if (t1) for (int i = f1; i <= l1; i++) { const double v = nz_lerp(r1, fr0->laterality[i], r, fr1->laterality[i]); if (v > lat1) lat1 = v; }
-  if (t2) for (int i = f2; i <= l2; i++) { const double v = nz_lerp(r1, fr0->laterality[i], r, fr1->laterality[i]); if (v > lat2) lat2 = v; }
+  auto range_lat = [&](int f, int l) {
+    double m = 0.0;
+    for (int i = f; i <= l; i++) {
+      const unsigned long long bit = 1ull << i;
+      if (latAlways & bit) m = 1.0;
+      else if (latMaybe & bit) { const double v = nz_lerp(r1, fr0->laterality[i], r, fr1->laterality[i]); if (v > m) m = v; }
+    }
+    return m;
+  };
+  if (t1) lat1 = range_lat(f1, l1);
+  if (t2) lat2 = range_lat(f2, l2);
   // positions (Tube.cpp:329-346): one sequential pass that picks up what the constrictions need
   const double teeth = nz_lerp(r1, S.inc[0][lane], r, S.inc[1][lane]);
   double pos = 0.0;
@@ -1386,9 +1398,19 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
 
   int interval = 0, i0 = 0, i1 = 0;
   double inv_len = 1.0;
+  unsigned long long latAlways = 0, latMaybe = 0;  // X2: laterality classes of the sections in this interval
+  auto lat_masks = [&](int iv) {
+    latAlways = 0; latMaybe = 0;
+    for (int j = 0; j < AFS_NUM_PM_SECTIONS; j++) {
+      const double a = my_frames[iv].laterality[j], b = my_frames[iv + 1].laterality[j];
+      if (a > 0.1000001 && b > 0.1000001) latAlways |= 1ull << j;
+      else if (!(a < 0.0999999 && b < 0.0999999)) latMaybe |= 1ull << j;
+    }
+  };
   if (T > 0) {
     i0 = A.bounds[0]; i1 = A.bounds[1];
     inv_len = 1.0 / (double)(i1 - i0);
+    if (ROLE == 3 && NOISE) lat_masks(0);
     stage_interval(S, lane, warp, my_frames, my_glottis, 0, NOISE);
     cta_sync();
     if (ROLE == 2) {  // glottis geometry of step 0
@@ -1411,6 +1433,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       interval++;
       i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
       inv_len = 1.0 / (double)(i1 - i0);
+      if (ROLE == 3 && NOISE) lat_masks(interval);
       stage_interval(S, lane, warp, my_frames, my_glottis, interval, NOISE);
       cta_sync();
     }
@@ -1436,7 +1459,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
       NoiseCons cons[4];
 #ifndef AFS_NZ_SKIP_SCAN
-      noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, cons);
+      noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, latAlways, latMaybe, cons);
 #else
       for (int k = 0; k < 4; k++) { cons[k].valid = k == 0; cons[k].nar = -1; cons[k].kind = 0; cons[k].up = 3; cons[k].teeth = 0; cons[k].lateral = 0; cons[k].downF = 0.3; }
 #endif
