@@ -128,6 +128,10 @@ struct TdsSmem {
   double inc[2][LANES];                          // incisor position of the two control frames
   uint32_t rng[34][LANES];                       // glibc random() TYPE_3 ring (r[i] = r[i-3] + r[i-31])
   unsigned char art[AFS_NUM_PM_SECTIONS][LANES]; // articulator of the LEFT control frame (Tube.cpp:452)
+  // constrictions of the NEXT step, found by warp X1 while the others solve (the scan does not depend on the state):
+  // packed {valid, kind, teeth, lateral, nar + 1, up} and the downstream factor, double buffered by step parity
+  uint32_t nzc_i[2][4][LANES];
+  double nzc_f[2][4][LANES];
   // same for all tracts
   SRec srec[NSX];
   double wallc[4][3];             // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = zeros
@@ -823,6 +827,24 @@ __device__ __forceinline__ void radiation_back(TdsSmem &S, const int lane, RadRe
 // numbers are drawn) repeats the reference's arithmetic operation by operation (explicit round-to-nearest
 // intrinsics: no FMA contraction, exact divisions), so that the discrete choices and the libc rand() stream are
 // the reference's; amplitudes are smooth functions of the state and follow it to rounding level.
+__device__ __forceinline__ void nzc_store(TdsSmem &S, const int lane, int buf, const NoiseCons (&C)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    S.nzc_i[buf][k][lane] = (uint32_t)(C[k].valid & 1) | ((uint32_t)(C[k].kind & 3) << 1) | ((uint32_t)(C[k].teeth & 1) << 3) |
+                            ((uint32_t)(C[k].lateral & 1) << 4) | ((uint32_t)(C[k].nar + 1) << 8) | ((uint32_t)C[k].up << 16);
+    S.nzc_f[buf][k][lane] = C[k].downF;
+  }
+}
+__device__ __forceinline__ void nzc_load(const TdsSmem &S, const int lane, int buf, NoiseCons (&C)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t v = S.nzc_i[buf][k][lane];
+    C[k].valid = v & 1; C[k].kind = (v >> 1) & 3; C[k].teeth = (v >> 3) & 1; C[k].lateral = (v >> 4) & 1;
+    C[k].nar = (int)((v >> 8) & 255) - 1; C[k].up = (int)(v >> 16);
+    C[k].downF = S.nzc_f[buf][k][lane];
+  }
+}
+
 // glibc srand() (stdlib/random_r.c, TYPE_3): the reference draws from libc rand() (TdsModel.cpp:1690-1696); every
 // tract owns a private generator.
 __device__ __noinline__ void rng_seed(TdsSmem &S, const int lane, uint32_t seed, int &ri) {
@@ -890,6 +912,7 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
   // narrowest tongue and lip sections
   double minT = 1000000.0, minL = 1000000.0;
   int iT = -1, iL = -1;
+#pragma unroll 4
   for (int j = 0; j < NPM; j++) {
     const double a = nz_area(S, lane, r, r1, j);
     const int ar = S.art[j][lane];
@@ -901,6 +924,7 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
   double a2 = 1000000.0;
   if (minT < 1.0) { t1 = true; nz_expand(S, lane, r, r1, iT, AFS_TONGUE, minT, f1, l1); }
   if (t1) {  // a second tongue constriction outside the first (TdsModel.cpp:1310-1372)
+#pragma unroll 4
     for (int j = 0; j < NPM; j++) {
       const double a = nz_area(S, lane, r, r1, j);
       if ((S.art[j][lane] == AFS_TONGUE) && (a < a2) && ((j < f1) || (j > l1))) { a2 = a; n2 = j; }
@@ -987,7 +1011,7 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
                                            const double asp_dB) {
   int tIdx[8];
   double tAmp[8], tCut[8];
-  unsigned long long todo = N.nz;
+  unsigned long long todo = N.nz, targeted = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     tIdx[2 * k] = -1; tIdx[2 * k + 1] = -1; tAmp[2 * k] = tAmp[2 * k + 1] = 0.0; tCut[2 * k] = tCut[2 * k + 1] = 0.0;
@@ -1025,16 +1049,19 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
     const int up = C[k].up, down = up < AFS_NUM_PM_SECTIONS - 1 ? up + 1 : AFS_NUM_PM_SECTIONS;
     tIdx[2 * k] = up; tAmp[2 * k] = (1.0 - C[k].downF) * fullAmp; tCut[2 * k] = cutoff;
     tIdx[2 * k + 1] = down; tAmp[2 * k + 1] = C[k].downF * fullAmp; tCut[2 * k + 1] = cutoff;
-    todo |= (1ull << up) | (1ull << down);
+    targeted |= (1ull << up) | (1ull << down);
   }
+  todo |= targeted;
   N.lips = 0.0;
   while (todo) {
     const int j = __ffsll((long long)todo) - 1;
     todo &= todo - 1;
     double tgt = 0.0, cut = S.ncut[j][lane];
     bool hit = false;
+    if ((targeted >> j) & 1ull) {
 #pragma unroll
-    for (int e = 0; e < 8; e++) if (tIdx[e] == j) { tgt = tAmp[e]; cut = tCut[e]; hit = true; }  // the last one wins
+      for (int e = 0; e < 8; e++) if (tIdx[e] == j) { tgt = tAmp[e]; cut = tCut[e]; hit = true; }  // the last one wins
+    }
     if (hit) S.ncut[j][lane] = cut;
     const double old = S.namp[j][lane];
     double a = __dadd_rn(old, __dmul_rn(P.nz_F, __dsub_rn(tgt, old)));
@@ -1048,7 +1075,8 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
       in = (in * (1.0 / 2147483647.0) - 6.0) * 0.28867513459481288225;  // / RAND_MAX, - 6, / sqrt(12)
       out = __dadd_rn(__dmul_rn(__dsub_rn(1.0, x), in), __dmul_rn(x, out));
     }
-    if ((a < 1.0e-30) && (tgt == 0.0)) { a = 0.0; N.nz &= ~(1ull << j); }  // (the reference lets it decay for ever)
+    if ((a < 1.0e-13) && (tgt == 0.0)) { a = 0.0; N.nz &= ~(1ull << j); }  // (the reference lets it decay for ever; a source
+                                                                           //  is silent below 1e-3)
     else N.nz |= 1ull << j;
     S.namp[j][lane] = a; S.nout[j][lane] = out;
     if (j == AFS_NUM_PM_SECTIONS) N.lips = out * a;
@@ -1410,7 +1438,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (T > 0) {
     i0 = A.bounds[0]; i1 = A.bounds[1];
     inv_len = 1.0 / (double)(i1 - i0);
-    if (ROLE == 3 && NOISE) lat_masks(0);
+    if ((ROLE == 3 || ROLE == 2) && NOISE) lat_masks(0);
     stage_interval(S, lane, warp, my_frames, my_glottis, 0, NOISE);
     cta_sync();
     if (ROLE == 2) {  // glottis geometry of step 0
@@ -1433,7 +1461,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       interval++;
       i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
       inv_len = 1.0 / (double)(i1 - i0);
-      if (ROLE == 3 && NOISE) lat_masks(interval);
+      if ((ROLE == 3 || ROLE == 2) && NOISE) lat_masks(interval);
       stage_interval(S, lane, warp, my_frames, my_glottis, interval, NOISE);
       cta_sync();
     }
@@ -1455,11 +1483,22 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
       }
     }
+    if (ROLE == 2 && NOISE && n + 1 < i1 && n + 1 < T) {
+      // constrictions of step n+1 for warp X2 (same control interval: its frames are staged); runs beside X2's source
+      // stage of step n, the two meet at the end-of-step barrier
+      const double re = __ddiv_rn((double)(n + 1 - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);
+      NoiseCons cons[4];
+      noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, latAlways, latMaybe, cons);
+      nzc_store(S, lane, (n + 1) & 1, cons);
+    }
     if (ROLE == 3 && NOISE && X.rows) {  // noise sources of step n (needs the update of the radiation currents above)
       const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
       NoiseCons cons[4];
 #ifndef AFS_NZ_SKIP_SCAN
-      noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, latAlways, latMaybe, cons);
+      // constrictions: found by X1 during the previous step, except on the first step of a control interval (the
+      // frames were not staged yet)
+      if (n == i0) noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, latAlways, latMaybe, cons);
+      else nzc_load(S, lane, n & 1, cons);
 #else
       for (int k = 0; k < 4; k++) { cons[k].valid = k == 0; cons[k].nar = -1; cons[k].kind = 0; cons[k].up = 3; cons[k].teeth = 0; cons[k].lateral = 0; cons[k].downF = 0.3; }
 #endif
