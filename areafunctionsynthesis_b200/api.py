@@ -82,6 +82,8 @@ def load_library():
     lib.afs_probe_fp64_tflops.argtypes = [vp, vp]
     lib.afs_chebyshev_lowpass.argtypes = [dbl, i32, vp, vp]
     lib.afs_area_function_to_frame.argtypes = [vp, vp]
+    lib.afs_area_functions_to_frames.argtypes = [vp, i32, vp, vp]
+    lib.afs_area_functions_to_frames_device.argtypes = [vp, i32, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -210,6 +212,18 @@ class Context:
                                                   int(spectrum_length), int(max_formants), _ptr(f), _ptr(bw),
                                                   _ptr(num), _ptr(flags)), self.h)
         return f, bw, num, flags
+
+    # ---- area-function rasteriser (K4) -------------------------------------
+    def area_functions_to_frames(self, params, frames=None):
+        """OneDimAreaFunction parameters [N,16] -> frames on the device (host buffers in and out)."""
+        p = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+        out = default_frames(len(p)) if frames is None else np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        _check(self.lib, self.lib.afs_area_functions_to_frames(self.h, len(p), _ptr(p), _ptr(out)), self.h)
+        return out
+
+    def area_functions_to_frames_device(self, d_params, d_frames, n, stream):
+        _check(self.lib, self.lib.afs_area_functions_to_frames_device(self.h, int(n), _ptr(d_params), _ptr(d_frames),
+                                                                      C.c_void_p(stream)), self.h)
 
     # ---- TDS ---------------------------------------------------------------
     def set_state_dump(self, step, out473=None):

@@ -24,6 +24,7 @@ UNITS = {
     "tl_kernels.cu": ["-fmad=false"],
     "tds_kernels.cu": [],
     "probe_kernels.cu": [],
+    "raster_kernels.cu": ["-fmad=false"],
     "afs_api.cu": [],
     "afs_host.cpp": [],
 }

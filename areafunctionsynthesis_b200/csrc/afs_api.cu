@@ -152,6 +152,40 @@ void afs_tube_frame_default(afs_tube_frame *f) {
   f->glottis_length_cm[0] = f->glottis_length_cm[1] = 0.3;
 }
 
+// ---------------------------------------------------------------------------
+// Area-function rasteriser (K4)
+// ---------------------------------------------------------------------------
+int afs_area_functions_to_frames_device(afs_ctx *ctx, int n, const double *d_params, afs_tube_frame *d_frames,
+                                        void *stream) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (n < 0) return AFS_ERR_BAD_ARGUMENT;
+  if (n == 0) return AFS_OK;
+  if (!d_params || !d_frames) return AFS_ERR_BAD_ARGUMENT;
+  CU(launch_area_function_raster(n, d_params, d_frames, (cudaStream_t)stream));
+  ctx->launches++;
+  return AFS_OK;
+}
+
+int afs_area_functions_to_frames(afs_ctx *ctx, int n, const double *params, afs_tube_frame *frames) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (n < 0) return AFS_ERR_BAD_ARGUMENT;
+  if (n == 0) return AFS_OK;
+  if (!params || !frames) return AFS_ERR_BAD_ARGUMENT;
+  void *d_p, *d_f;
+  const size_t pb = (size_t)n * 16 * sizeof(double), fb = (size_t)n * sizeof(afs_tube_frame);
+  if ((rc = scratch(ctx, 1, pb, &d_p))) return rc;
+  if ((rc = scratch(ctx, 0, fb, &d_f))) return rc;
+  CU(cudaMemcpyAsync(d_p, params, pb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_f, frames, fb, cudaMemcpyHostToDevice, ctx->stream));
+  rc = afs_area_functions_to_frames_device(ctx, n, (const double *)d_p, (afs_tube_frame *)d_f, ctx->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(frames, d_f, fb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return AFS_OK;
+}
+
 int afs_probe_fp64_tflops(afs_ctx *ctx, double *tflops) {
   int rc = bind(ctx);
   if (rc) return rc;

@@ -39,6 +39,9 @@ cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tu
                        uint32_t *d_status, double *d_dump, int dump_step, cudaStream_t stream);
 size_t tds_smem_bytes();
 
+// ---- area-function rasteriser -----------------------------------------------
+cudaError_t launch_area_function_raster(int n_sets, const double *d_params, afs_tube_frame *d_frames, cudaStream_t stream);
+
 // ---- probes ------------------------------------------------------------------
 cudaError_t launch_fp64_probe(double *d_out, int ctas, int iters, cudaStream_t stream);
 

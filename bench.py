@@ -356,6 +356,31 @@ def run_ours(args):
     barrier()
     tl_e2e = world * B_TL / max_over_ranks((time.perf_counter() - t0) / 3)
 
+    # ---------------- rasteriser: parameter sets -> frames on the device --------------
+    B_RA = 65536
+    rng = np.random.default_rng(20260004 + rank)
+    lo = np.array([-0.2, 0.67, 0.015, 1.92, 1.82, 0.37, 6.36, 0.087, 0.31, 10.97, 0.092, 0.0, 16.33, 1.05, 16.53, 0.107])
+    hi = np.array([2.63, 2.05, 5.22, 6.43, 11.55, 6.96, 16.44, 2.50, 5.21, 18.82, 14.33, 9.33, 20.45, 6.12, 21.52, 4.40])
+    pr = lo + (hi - lo) * rng.random((B_RA, 16))
+    pr[:, [0, 3, 6, 9, 12, 14]] = np.sort(pr[:, [0, 3, 6, 9, 12, 14]], axis=1)
+    pr[:, 0] = np.maximum(pr[:, 0], 0.0)
+    d_pr = torch.from_numpy(pr).to(dev)
+    d_fra = torch.from_numpy(afs.default_frames(B_RA).view(np.uint8).reshape(B_RA, -1)).to(dev)
+
+    def raster_dev():
+        ctx.area_functions_to_frames_device(d_pr, d_fra, B_RA, stream)
+
+    ra_ms = timed(raster_dev, 5, 3) / 5
+    ra_value = world * B_RA / (ra_ms * 1e-3)
+    ra_cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        host_fr = afs.area_function_to_frames(pr[:2048])
+        ra_cpu = 2048 / (time.perf_counter() - t0)
+        dev_fr = np.frombuffer(d_fra[:2048].cpu().numpy().tobytes(), dtype=afs.FRAME_DTYPE)
+        assert np.array_equal(dev_fr["articulator"], host_fr["articulator"])
+        assert np.max(np.abs(dev_fr["area_cm2"] - host_fr["area_cm2"]) / host_fr["area_cm2"]) <= 1e-12
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -399,6 +424,10 @@ def run_ours(args):
         "gather": {"collective": "all_gather of the audio [B, n_out] f64 over NCCL, after the compute", "ms": gather_ms,
                    "bytes_per_rank": int(B_TDS * n_out * 8),
                    "value_including_gather": audio_s_per_step / ((ms_step + gather_ms) * 1e-3)},
+        "raster": {"metric": "area_function_parameter_sets_per_second", "value": ra_value, "unit": "sets/s", "ms_per_step": ra_ms,
+                   "config": {"workload": "onedim_area_function_to_frames_65536", "sets_per_gpu": B_RA},
+                   "cpu_baseline": None if ra_cpu is None else {"value": ra_cpu, "unit": "sets/s", "cores": 1, "kind": "port",
+                                                                "sample": "2048 sets, host rasteriser of the C ABI (bit-identical to the reference on Default.params)"}},
         "noise_sources_on": {"value": audio_s_per_step / (noise_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": noise_ms,
                              "steps": noise_steps},
         "tl": {"metric": "tl_spectra_per_second_2048_bins", "value": tl_value, "unit": "spectra/s", "ms_per_step": tl_ms,

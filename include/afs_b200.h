@@ -283,6 +283,18 @@ int afs_chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double 
  * Aa, powA, xin, Ain, Lvt, Alip) -> the 40 pharynx/mouth sections of `frame`
  * (other fields untouched). Input generator for benches; host code. */
 int afs_area_function_to_frame(const double params[16], afs_tube_frame *frame);
+/* The same for a batch on the device (K4 area_function_raster_kernel; SURVEY.md
+ * 8f rank 1): params [n][16] -> frames [n].  Replaces n calls of
+ * OneDimAreaFunction::calculateOneDimTubeFunction (OneDimAreaFunction.cpp:75-138,
+ * as called from Data.cpp / the parametric-tract sweeps).  Sample positions,
+ * samples per section and articulator labels are the reference's exactly;
+ * areas agree to ~1e-15 relative (device pow/cos vs glibc).  Fills the 40
+ * pharynx/mouth sections, their articulators and the incisor position; the
+ * other fields of `frames` are left as they are (initialise them with
+ * afs_tube_frame_default).  The host variant copies frames in and out. */
+int afs_area_functions_to_frames(afs_ctx *ctx, int n, const double *params, afs_tube_frame *frames);
+int afs_area_functions_to_frames_device(afs_ctx *ctx, int n, const double *d_params, afs_tube_frame *d_frames,
+                                        void *stream);
 
 #ifdef __cplusplus
 }

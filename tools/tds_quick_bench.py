@@ -1,0 +1,20 @@
+"""Quick device-side timing of tds_batch_kernel on the bench batch (scratch tool, not the bench contract)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import areafunctionsynthesis_b200 as afs
+from bench import make_tds_batch
+B = int(os.environ.get("B", "4096")); T = int(os.environ.get("T", "4410"))
+ctx = afs.Context(0)
+fr, gl = make_tds_batch(B, 20260003)
+d_fr = torch.from_numpy(fr.view(np.uint8).reshape(B, -1)).cuda(); d_gl = torch.from_numpy(gl).cuda()
+d_a = torch.empty(B, T // 2, dtype=torch.float64, device="cuda")
+d_seeds = torch.arange(1, B + 1, dtype=torch.int32, device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+for noise in (False, True):
+    o = afs.tds_options_default(noise=noise)
+    ctx.tds_synthesize_device(d_fr, d_gl, B, 2, [T // 2], d_a, st, opts=o, d_seeds=d_seeds); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ctx.tds_synthesize_device(d_fr, d_gl, B, 2, [T // 2], d_a, st, opts=o, d_seeds=d_seeds); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"bench batch noise={noise} B={B} T={T}: {ms:.1f} ms -> {ms*1e3/T:.2f} us/step, {B*T/44100/(ms/1e3):.0f} audio-s/s")
