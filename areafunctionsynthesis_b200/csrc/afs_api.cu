@@ -313,10 +313,8 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   if (rc) return rc;
   if (!opts || n_tracts < 0 || n_frames < 2 || !frame_len || sr_factor < 1 || !(fs_tds_hz > 0))
     return AFS_ERR_BAD_ARGUMENT;
-  if (opts->transvelar_coupling) return AFS_ERR_UNSUPPORTED;
-  if (opts->glottis_loss_option != AFS_STANDARD_ENTRANCE_LOSS &&
-      opts->glottis_loss_option != AFS_ENTRANCE_LOSS_VAN_DEN_BERG)
-    return AFS_ERR_UNSUPPORTED;
+  if (opts->glottis_loss_option < AFS_STANDARD_ENTRANCE_LOSS || opts->glottis_loss_option > AFS_VARIABLE_ENTRANCE_LOSS)
+    return AFS_ERR_BAD_ARGUMENT;
   for (int k = 0; k + 1 < n_frames; k++) if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT;
   if (n_tracts == 0) return AFS_OK;
   if (!d_tubes || !d_glottis || !d_audio) return AFS_ERR_BAD_ARGUMENT;

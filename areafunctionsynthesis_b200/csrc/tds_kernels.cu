@@ -82,6 +82,8 @@ struct TdsParams {
   double dt, idt, th, dtth, dtth1;  // 1/fs, 1/(dt*theta), theta1/theta, dt*theta, dt*theta1
   double ith, fs;                   // theta/theta1, fs
   double fsar, k_ent;
+  int transvelar, var_loss;         // transvelarCoupling, glottisLossOption == VARIABLE_ENTRANCE_LOSS (TdsModel.h:75-87)
+  double tg_a[5], tg_b[5];          // 50 Hz Chebyshev low-pass of the transglottal pressure (TdsModel.cpp:474)
   double k_sondhi, k_bern;          // 8 rho/(3 pi^2) resp. rho/2, or 0 when the option is off
   double kalpha[3], c1[3], c2[3], c3[3];  // wall constants: 0 standard, 1 trachea, 2 sinus
   double kc[4][3];                        // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = no walls (zeros)
@@ -121,6 +123,10 @@ struct TdsSmem {
   double radc[2][2][LANES];                      // radiation pairs folded into currents 64 / 83
   double uext[NUX][LANES];
   double p4[4][LANES];            // pressures of sections 22..25 after the last update
+  // non-default options (warp X2 owns the filters): pressures below / above the velum (sections 43, 67), the history
+  // part of the two velum filters and of the transglottal-pressure filter (double buffered by step parity), the
+  // transvelar flow of the current step
+  double tvp[2][LANES], tvh[2][LANES], kenth[2][LANES], tvflow[LANES];
   // noise sources (TdsModel.cpp:1188-1708; warp X2).  Index j = section - 25 for the dipole sources of the
   // pharynx/mouth sections 25..64, 40 = lips; nmag: j = current - 25 for the currents 25..65, 41 = current 84.
   double nmag[42][LANES];                        // noiseMagnitude (TdsModel.h:143) of the currents a constriction can feed
@@ -268,6 +274,16 @@ __device__ __forceinline__ double wall_beta3(const double *w, double wc, double 
   return fma(wc, w[0], fma(wcr, w[1], wcr2 * w[2]));
 }
 
+// Filter for the sound radiated from the skin above the glottis (TdsModel.cpp:494-510, 544).
+__device__ __constant__ double c_tone_a[5] = {5.027640021717718e-007, -7.995535578908732e-007,
+                                              2.967895557191014e-007, 0.0, 0.0};
+__device__ __constant__ double c_tone_b[5] = {0.0, 3.986308869708467, -5.959669638387298, 3.960408461107104,
+                                              -0.987047716233603};
+
+// Second velum filter H2 of the transvelar coupling (TdsModel.cpp:512-527); H1 has the coefficients of the skin filter.
+__device__ __constant__ double c_tv2_a[5] = {6.589309727087047e-004, -0.001972281980771, 0.001968000742164,
+                                             -6.546497341015677e-004, 0.0};
+
 // ---- one matrix row (negated: SPD) of a dynamic segment ---------------------------
 // Row of the current flowing from section A into section B (TdsModel.cpp:1916-2034):
 //   diag = E_B + E_A + L_AB/(dt theta) + R_AB,   rhs = L_AB c + L_A c_sibling - D_B + D_A
@@ -277,8 +293,8 @@ __device__ __forceinline__ double wall_beta3(const double *w, double wc, double 
 enum { RF_JUNCTION = 1, RF_GLO = 2, RF_GUP = 4 };
 __device__ __forceinline__ void row_dyn(const TdsParams &P, int fl, double E_A, double L_A, double R_A, double ia,
                                         double D_A, double E_B, double L_B, double R_B, double ib, double D_B, double c,
-                                        double c_sib, double uB, double areaA, double areaB, double &gbf, double &diag,
-                                        double &rhs) {
+                                        double c_sib, double uB, double areaA, double areaB, double k_ent, double &gbf,
+                                        double &diag, double &rhs) {
   // (branch-free: a flag only selects factors)
   const bool junction = (fl & RF_JUNCTION) != 0, glo = (fl & RF_GLO) != 0, gup = (fl & RF_GUP) != 0;
   const double qa = ia * ia * (1.0 / kPi), qb = ib * ib * (1.0 / kPi);  // 1/area_A, 1/area_B
@@ -293,7 +309,7 @@ __device__ __forceinline__ void row_dyn(const TdsParams &P, int fl, double E_A, 
   const double up = uB > 0 ? uB * (0.5 * kRho) : 0.0;
   const double dq = qb * qb - qa * qa;                          // 1/area_T^2 - 1/area_S^2
   R_A = fma(-kb, qa * qa, fma(gup ? gbf * up : 0.0, dq, R_A));
-  R_B = fma(kb, qb * qb, fma(glo ? P.k_ent * up : 0.0, dq, R_B));
+  R_B = fma(kb, qb * qb, fma(glo ? k_ent * up : 0.0, dq, R_B));
   diag = E_B + E_A + fma(L_AB, P.idt, R_A + R_B);
   rhs = fma(L_AB, c, fma(L_A, c_sib, D_A - D_B));
 }
@@ -375,13 +391,15 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       const double u = u_, out = un_;
       const double E_old = S.Ed[rec][lane], al_old = S.Al[rec][lane];
       const double beta_old = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
-      const double D_old = fma(-E_old, beta_old, fma(P.dtth1, pr_, p_));
+      double D_old = fma(-E_old, beta_old, fma(P.dtth1, pr_, p_));
+      if (k == 2 && P.transvelar && w == W_NV) D_old = fma(E_old, S.tvflow[lane], D_old);  // source term of section 67
       // current: u' = (u_new - u_old)/(dt theta) - (theta1/theta) u'_old = u_new/(dt theta) - c
       const double ur = fma(u, P.idt, -c_);
       c_ = fma(ur, P.th, u * P.idt);
       const double p_new = fma(E_old, u - out, D_old);
       const double pr_new = (p_new - p_) * P.idt - pr_ * P.th;
       p_ = p_new; pr_ = pr_new;
+      if (k == 2 && P.transvelar && (w == W_M0 || w == W_NV)) S.tvp[w == W_NV ? 1 : 0][lane] = p_new;  // sections 43, 67
       const double wc_new = fma(pr_new, al_old, beta_old);
       const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
       const double wcr2_new = (wcr_new - wcr) * P.idt - wcr2 * P.th;
@@ -420,7 +438,7 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
         // (the lower -> upper glottis row can only be slot 1, the entrance row only slot 0: keeps their code and the
         //  registers they need out of the other slots)
         const int fl = row_flags(sec) & (k == 1 ? (RF_JUNCTION | RF_GUP) : RF_JUNCTION);
-        row_dyn(P, fl, pE, pL, pR, pI, pD, E, L, R, invr, D, c_, 0.0, u_, k == 1 ? pA : 0.0, area, st.gbf, y_, x_);
+        row_dyn(P, fl, pE, pL, pR, pI, pD, E, L, R, invr, D, c_, 0.0, u_, k == 1 ? pA : 0.0, area, 0.0, st.gbf, y_, x_);
       }
       if (k == KD - 1) {
         S.bE[w][lane] = E; S.bL[w][lane] = L; S.bR[w][lane] = R; S.bI[w][lane] = invr; S.bD[w][lane] = D;
@@ -433,20 +451,48 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
   }
 }
 
+// TdsModel::getGlottalEntranceLossCoeffFlucher2011 (TdsModel.cpp:1019-1092): entrance loss coefficient from the
+// low-pass filtered transglottal pressure and the width of the lower glottis section.
+__device__ __noinline__ double fulcher_k_ent(double pressure_dPa, double area_lower) {
+  double p = pressure_dPa / 979.7, D = area_lower / 1.25;
+  if (p < 0.001) p = 0.001;
+  if (D < 0.001) D = 0.001;
+  const double logD = log10(D);
+  const double a = pow(10.0, 0.7953 * logD * logD + 1.4741 * logD + 0.6529);
+  const double b = -0.7427 * logD * logD + -1.6209 * logD + -0.875;
+  double k = a * pow(p, b);
+  if (k < 0.6) k = 0.6;
+  if (k > 18.0) k = 18.0;
+  return k;
+}
+
 // After the barrier: the first row (its source section belongs to another warp), then elimination of the
 // interior currents towards the last one.  `aown`: the first current is itself a separator (branch heads 29, 41, 65).
 template <bool NOISE>
 __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
-                                                DRegs &st) {
+                                                DRegs &st, const int par) {
   const int pw = wc_prev(wc_), n0 = 23 + KD * w;
   const bool aown = (w == W_P1) || (w == W_M0) || (w == W_NV);
   const double E_A = S.bE[pw][lane], E_0 = S.Ed[KD * w][lane];
   {
     const double c_sib = wc_csib(wc_) >= 0 ? S.csib[wc_csib(wc_) ^ 1][lane] : 0.0;  // 29 <-> 84, 41 <-> 65
+    double k_ent = P.k_ent;
+    if (P.var_loss && w == W_GP) {  // (the filter's history part comes from warp X2, its newest input is p22 - p25)
+      const double filt = fma(P.tg_a[0], S.p4[0][lane] - S.p4[3][lane], S.kenth[par][lane]);
+      k_ent = fulcher_k_ent(filt, fmax(S.glArea[par][0][lane], kMinArea));
+    }
     double diag, rhs;
     row_dyn(P, row_flags(n0), E_A, S.bL[pw][lane], S.bR[pw][lane], S.bI[pw][lane], S.bD[pw][lane], E_0, st.L0, st.R0,
-            st.I0, st.D0, st.c[0], c_sib, st.x[0], 0.0, 0.0, st.gbf, diag, rhs);
+            st.I0, st.D0, st.c[0], c_sib, st.x[0], 0.0, 0.0, k_ent, st.gbf, diag, rhs);
     st.y[0] = diag; st.x[0] = rhs;
+  }
+  if (P.transvelar && w == W_NV) {
+    // extra flow into the nasal cavity through the velum (TdsModel.cpp:966-980, 996-999): a source in section 67
+    // (slot 2), i.e. D_67 += E_67 * flow, which enters the rows of the currents 67 and 68
+    const double tv = fma(c_tone_a[0], S.tvp[0][lane], fma(c_tv2_a[0], st.p[2], S.tvh[par][lane]));
+    const double dD = S.Ed[KD * w + 2][lane] * tv;
+    st.x[2] -= dD; st.x[3] += dD;
+    S.tvflow[lane] = tv;
   }
   if (NOISE) {  // dipole sources of the pharynx/mouth sections: S = -sample (TdsModel.cpp:1936), sample = out * amp
 #pragma unroll
@@ -769,6 +815,24 @@ __device__ __forceinline__ void dwarp_dump(const TdsParams &P, TdsSmem &S, const
 // ==================================================================================
 // Radiation loads (warp X2): the two parallel radiation currents out of the mouth (93, 94) and the nostrils (95, 96)
 // ==================================================================================
+// Filters of the non-default options (warp X2): x / y histories (index 0 = previous sample) of the two velum filters
+// (order 4, TdsModel.cpp:476-533) and of the 50 Hz Chebyshev filter of the transglottal pressure (:474).  Every
+// filter is split into a0 * x(n) -- evaluated where the value is needed, right after the barrier -- and the history
+// part, which X2 prepares one step ahead.
+struct OptRegs {
+  double x1[4], y1[4], x2[4], y2[4], xg[4], yg[4];
+};
+__device__ __forceinline__ double iir_history(const double *a, const double *b, const double (&x)[4], const double (&y)[4]) {
+  double h = 0.0;
+#pragma unroll
+  for (int i = 1; i <= 4; i++) { h = fma(a[i], x[i - 1], h); h = fma(b[i], y[i - 1], h); }
+  return h;
+}
+__device__ __forceinline__ void iir_push(double (&x)[4], double (&y)[4], double in, double out) {
+#pragma unroll
+  for (int i = 3; i > 0; i--) { x[i] = x[i - 1]; y[i] = y[i - 1]; }
+  x[0] = in; y[0] = out;
+}
 struct RadRegs {
   double c[4], u[4];  // history terms and last solutions of the currents 93..96
   double keep[2][7];  // factors kept between elimination and back substitution
@@ -1297,12 +1361,6 @@ __device__ __forceinline__ double iir_step(const double *a, const double *b, dou
   return sum;
 }
 
-// Filter for the sound radiated from the skin above the glottis (TdsModel.cpp:494-510, 544).
-__device__ __constant__ double c_tone_a[5] = {5.027640021717718e-007, -7.995535578908732e-007,
-                                              2.967895557191014e-007, 0.0, 0.0};
-__device__ __constant__ double c_tone_b[5] = {0.0, 3.986308869708467, -5.959669638387298, 3.960408461107104,
-                                              -0.987047716233603};
-
 // Registers of warp X1: glottis state + cached dimensions, filter histories.
 struct X1Regs {
   GlottisState G;
@@ -1391,6 +1449,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   DRegs dst;
   SRegs sst;
   RadRegs rr;
+  OptRegs orr;
   X1Regs xr;
   NoiseRegs nr;
   nr.nz = 0; nr.ri = 0; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0;
@@ -1411,7 +1470,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   }
   if (ROLE == 3) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; }
+    for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; orr.x1[j] = orr.y1[j] = orr.x2[j] = orr.y2[j] = orr.xg[j] = orr.yg[j] = 0.0; }
     if (NOISE) rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ri);
   }
   if (ROLE == 2) {
@@ -1519,10 +1578,30 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     }
     if (!X.rows) break;
     // ============ first rows + elimination of the segments || glottis ============
-    if (ROLE == 0) dwarp_eliminate<NOISE>(P, S, lane, warp, wcfg, dst);
+    if (ROLE == 0) dwarp_eliminate<NOISE>(P, S, lane, warp, wcfg, dst, n & 1);
     if (ROLE == 1) {
       const double psrc = X.ratio1 * S.gctl[0][G_PRESSURE][lane] + X.ratio * S.gctl[1][G_PRESSURE][lane];
       swarp_eliminate(P, S, lane, warp, wcfg, scfg, sst, psrc);
+    }
+    if (ROLE == 3 && (P.transvelar || P.var_loss)) {
+      // this step's filter outputs (same expression as their consumers use), then the history parts of the next step
+      const int par = n & 1;
+      if (P.transvelar) {
+        const double in1 = S.tvp[0][lane], in2 = S.tvp[1][lane];
+        const double h = S.tvh[par][lane];
+        // (split the sum of the two filters: y1 = a0 x1 + h1, y2 = a0' x2 + h2 with h = h1 + h2 kept separately)
+        const double h1 = iir_history(c_tone_a, c_tone_b, orr.x1, orr.y1), h2 = iir_history(c_tv2_a, c_tone_b, orr.x2, orr.y2);
+        (void)h;
+        iir_push(orr.x1, orr.y1, in1, fma(c_tone_a[0], in1, h1));
+        iir_push(orr.x2, orr.y2, in2, fma(c_tv2_a[0], in2, h2));
+        S.tvh[par ^ 1][lane] = iir_history(c_tone_a, c_tone_b, orr.x1, orr.y1) + iir_history(c_tv2_a, c_tone_b, orr.x2, orr.y2);
+      }
+      if (P.var_loss) {
+        const double in = S.p4[0][lane] - S.p4[3][lane];
+        const double hg = iir_history(P.tg_a, P.tg_b, orr.xg, orr.yg);
+        iir_push(orr.xg, orr.yg, in, fma(P.tg_a[0], in, hg));
+        S.kenth[par ^ 1][lane] = iir_history(P.tg_a, P.tg_b, orr.xg, orr.yg);
+      }
     }
     if (ROLE == 3) {
       radiation_eliminate(P, S, lane, W_M3, 0, rr.c[0], rr.c[1], nr.lips, rr.keep[0]);
@@ -1632,6 +1711,8 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
     for (int i = 0; i < NUX; i++) S.uext[i][lane] = 0.0;
     for (int i = 0; i < 5; i++) S.lf[i][lane] = 0.0;
     for (int i = 0; i < 4; i++) { S.p4[i][lane] = 0.0; (&S.radc[0][0])[i][lane] = 0.0; }
+    for (int i = 0; i < 2; i++) { S.tvp[i][lane] = 0.0; S.tvh[i][lane] = 0.0; S.kenth[i][lane] = 0.0; }
+    S.tvflow[lane] = 0.0;
   }
   __syncthreads();
 
@@ -1667,6 +1748,9 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   P.fossa = o->piriform_fossa; P.ilc = o->inner_length_corrections;
   P.fsar = o->flow_separation_area_ratio;
   P.k_ent = o->glottis_loss_option == AFS_ENTRANCE_LOSS_VAN_DEN_BERG ? 1.375 : 1.0;
+  P.transvelar = o->transvelar_coupling ? 1 : 0;
+  P.var_loss = o->glottis_loss_option == AFS_VARIABLE_ENTRANCE_LOSS ? 1 : 0;
+  chebyshev_lowpass(50.0 / fs_tds_hz, 4, P.tg_a, P.tg_b);
   P.k_sondhi = o->inner_length_corrections ? 8.0 * kRho / (3.0 * kPi * kPi) : 0.0;
   P.k_bern = o->turbulence_losses ? 0.5 * kRho : 0.0;
   const double dt = 1.0 / fs_tds_hz;

@@ -77,7 +77,7 @@ enum afs_radiation_type {
 };
 
 /* TdsModel::GlottisLossOptions / SolverType (TdsModel.h:60-73) */
-enum afs_glottis_loss { AFS_STANDARD_ENTRANCE_LOSS = 0, AFS_ENTRANCE_LOSS_VAN_DEN_BERG = 1 };
+enum afs_glottis_loss { AFS_STANDARD_ENTRANCE_LOSS = 0, AFS_ENTRANCE_LOSS_VAN_DEN_BERG = 1, AFS_VARIABLE_ENTRANCE_LOSS = 2 };
 
 typedef enum afs_status {
   AFS_OK = 0,
@@ -152,8 +152,8 @@ typedef struct afs_tds_options {
   int32_t radiation_from_skin;
   int32_t piriform_fossa;
   int32_t inner_length_corrections;
-  int32_t transvelar_coupling;   /* 1 is AFS_ERR_UNSUPPORTED */
-  int32_t glottis_loss_option;   /* enum afs_glottis_loss; VARIABLE_ENTRANCE_LOSS unsupported */
+  int32_t transvelar_coupling;   /* Dang et al. velum filters (TdsModel.cpp:476-533, 970-980) */
+  int32_t glottis_loss_option;   /* enum afs_glottis_loss (VARIABLE: Fulcher 2011, TdsModel.cpp:1019-1092) */
   double flow_separation_area_ratio;
   /* TriangularGlottis static parameters; afs_tds_options_default fills the
    * reference defaults. */

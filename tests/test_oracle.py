@@ -112,6 +112,15 @@ def test_tds_noise_sources_bit_identical(oracle):
     assert np.abs(a0 - a).max() > 1e-3 * np.abs(a).max()
 
 
+def test_tds_transvelar_and_variable_loss_bit_identical(oracle):
+    from oracle.pyoracle import tds_options_default
+    g = load_golden("tds_reference.npz")
+    o = tds_options_default()
+    o.transvelar_coupling = 1; o.glottis_loss_option = 2
+    a, u = oracle.tds_synthesize(g["opt_frames"], g["opt_glottis"], [2205], 44100.0, 2, opts=o)
+    assert np.array_equal(u, g["opt_flow44"]) and np.array_equal(a, g["opt_audio44"])
+
+
 def test_tds_state_dump_matches_reference(oracle):
     g = load_golden("tds_reference.npz")
     for step in (1, 2, 500):

@@ -134,9 +134,9 @@ def test_edge_cases(ctx, oracle, shapes):
         a, u, _ = synth(ctx, frr, gll, fl, 22050.0 * srf, srf, want_flow=True)
         ao, uo = oracle.tds_synthesize(frr, gll, fl, 22050.0 * srf, srf)
         assert rel_err(u, uo) <= TOL and np.allclose(a, ao, rtol=0, atol=TOL * np.max(np.abs(ao)) + 1e-30), (srf, fl)
-    # options the device path does not implement are errors, not silently different audio
-    o = afs.tds_options_default(noise=False); o.transvelar_coupling = 1
-    with pytest.raises(afs.AfsError, match="not supported"):
+    # an option value the reference does not have is an error, not silently different audio
+    o = afs.tds_options_default(noise=False); o.glottis_loss_option = 3
+    with pytest.raises(afs.AfsError):
         synth(ctx, fr, gl, [10], 44100.0, 2, opts=o)
     # other option switches
     from oracle.pyoracle import tds_options_default as oracle_opts
@@ -208,3 +208,33 @@ def test_noise_sources_against_oracle(ctx, oracle, shapes):
     perm = rng.permutation(B)[:20]
     a2, _, _ = ctx.tds_synthesize(fr[perm], gl[perm], fl, 44100.0, 2, opts=on, seeds=seeds[perm])
     assert np.array_equal(a[perm], a2)
+
+
+# ---------------------------------------------------------------------------------------------
+# non-default options of TdsModel::Options: transvelar coupling (TdsModel.cpp:476-533, 966-999) and the variable
+# glottal entrance loss of Fulcher et al. 2011 (TdsModel.cpp:1019-1092)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tv,loss,noise", [(1, 0, False), (0, 2, False), (1, 2, False), (1, 2, True), (0, 1, True)])
+def test_transvelar_coupling_and_variable_entrance_loss(ctx, oracle, shapes, tv, loss, noise):
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    n = len(shapes["names"])
+    rng = np.random.default_rng(20260005 + 10 * tv + loss)
+    B = 30  # more tracts than one CTA holds
+    fr = shapes["frames"][rng.integers(0, n, size=(B, 3))].copy()
+    fr["velum_area_cm2"] = np.where(rng.random((B, 3)) < 0.5, rng.random((B, 3)) * 0.5, 0.0)
+    gl = np.tile(G0, (B, 3, 1))
+    gl[:, :, 0] = rng.uniform(90, 220, size=(B, 3))
+    seeds = rng.integers(0, 2**32, size=B, dtype=np.uint64).astype(np.uint32)
+    o = afs.tds_options_default(noise=noise); o.transvelar_coupling = tv; o.glottis_loss_option = loss
+    oo = oracle_opts(noise=noise); oo.transvelar_coupling = tv; oo.glottis_loss_option = loss
+    fl = [700, 501]
+    a, u, st = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=o, seeds=seeds, want_flow=True)
+    ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=oo, seeds=seeds)
+    assert not st.any()
+    for b in range(B):
+        assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, (b, rel_err(u[b], uo[b]))
+    # the options really change the audio
+    a0, _ = oracle.tds_synthesize(fr[:4], gl[:4], fl, 44100.0, 2, opts=oracle_opts(noise=noise), seeds=seeds[:4], want_flow=False)
+    if tv or loss == 2:
+        assert rel_err(ao[:4], a0) > 1e-3

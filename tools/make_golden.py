@@ -97,6 +97,14 @@ def main():
     seeds = np.array([1234, 99, 20260002], dtype=np.uint32)
     ans, uns = r44.tds_synthesize(frn3, gn, [3308], opts=on, seeds=seeds)
     tds.update(noise_frames=frn3, noise_glottis=gn, noise_seeds=seeds, noise_audio44=ans, noise_flow44=uns)
+    # (6) non-default options: transvelar coupling + Fulcher variable entrance loss (TdsModel.cpp:476-533, 966-999,
+    #     1019-1092), nasalised /a/ -> /i/
+    oo = tds_options_default()
+    oo.transvelar_coupling = 1; oo.glottis_loss_option = 2
+    fo = np.stack([fa[0], fi[0]])[None].copy()
+    fo["velum_area_cm2"] = 0.3
+    ao_, uo_ = r44.tds_synthesize(fo, gl3[:, :2], [2205], opts=oo)
+    tds.update(opt_frames=fo, opt_glottis=gl3[:, :2], opt_audio44=ao_, opt_flow44=uo_)
     np.savez_compressed(os.path.join(OUT, "tds_reference.npz"), **tds)
 
     # --- filter design
