@@ -362,7 +362,7 @@ __device__ __forceinline__ void dump_section(const TdsParams &P, double *dump, i
 // BRANCH-FREE (the kind of a section only selects values), so that the update chain and the geometry chain of a slot
 // -- and neighbouring slots -- overlap: the kernel is bound by the latency of dependent FP64 operations, not by the
 // pipe.  HOT = false (first / last step, state dumps) takes the flags from X.
-template <bool HOT>
+template <bool HOT, bool OPT>
 __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
                                              DRegs &st, const StepCtx &X) {
   const bool upd = HOT ? true : X.upd, rows = HOT ? true : X.rows;
@@ -392,14 +392,14 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       const double E_old = S.Ed[rec][lane], al_old = S.Al[rec][lane];
       const double beta_old = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
       double D_old = fma(-E_old, beta_old, fma(P.dtth1, pr_, p_));
-      if (k == 2 && P.transvelar && w == W_NV) D_old = fma(E_old, S.tvflow[lane], D_old);  // source term of section 67
+      if (OPT && k == 2 && P.transvelar && w == W_NV) D_old = fma(E_old, S.tvflow[lane], D_old);  // source term of section 67
       // current: u' = (u_new - u_old)/(dt theta) - (theta1/theta) u'_old = u_new/(dt theta) - c
       const double ur = fma(u, P.idt, -c_);
       c_ = fma(ur, P.th, u * P.idt);
       const double p_new = fma(E_old, u - out, D_old);
       const double pr_new = (p_new - p_) * P.idt - pr_ * P.th;
       p_ = p_new; pr_ = pr_new;
-      if (k == 2 && P.transvelar && (w == W_M0 || w == W_NV)) S.tvp[w == W_NV ? 1 : 0][lane] = p_new;  // sections 43, 67
+      if (OPT && k == 2 && P.transvelar && (w == W_M0 || w == W_NV)) S.tvp[w == W_NV ? 1 : 0][lane] = p_new;  // sections 43, 67
       const double wc_new = fma(pr_new, al_old, beta_old);
       const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
       const double wcr2_new = (wcr_new - wcr) * P.idt - wcr2 * P.th;
@@ -468,7 +468,7 @@ __device__ __noinline__ double fulcher_k_ent(double pressure_dPa, double area_lo
 
 // After the barrier: the first row (its source section belongs to another warp), then elimination of the
 // interior currents towards the last one.  `aown`: the first current is itself a separator (branch heads 29, 41, 65).
-template <bool NOISE>
+template <bool NOISE, bool OPT>
 __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
                                                 DRegs &st, const int par) {
   const int pw = wc_prev(wc_), n0 = 23 + KD * w;
@@ -477,7 +477,7 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
   {
     const double c_sib = wc_csib(wc_) >= 0 ? S.csib[wc_csib(wc_) ^ 1][lane] : 0.0;  // 29 <-> 84, 41 <-> 65
     double k_ent = P.k_ent;
-    if (P.var_loss && w == W_GP) {  // (the filter's history part comes from warp X2, its newest input is p22 - p25)
+    if (OPT && P.var_loss && w == W_GP) {  // (the filter's history part comes from warp X2, its newest input is p22 - p25)
       const double filt = fma(P.tg_a[0], S.p4[0][lane] - S.p4[3][lane], S.kenth[par][lane]);
       k_ent = fulcher_k_ent(filt, fmax(S.glArea[par][0][lane], kMinArea));
     }
@@ -486,7 +486,7 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
             st.I0, st.D0, st.c[0], c_sib, st.x[0], 0.0, 0.0, k_ent, st.gbf, diag, rhs);
     st.y[0] = diag; st.x[0] = rhs;
   }
-  if (P.transvelar && w == W_NV) {
+  if (OPT && P.transvelar && w == W_NV) {
     // extra flow into the nasal cavity through the velum (TdsModel.cpp:966-980, 996-999): a source in section 67
     // (slot 2), i.e. D_67 += E_67 * flow, which enters the rows of the currents 67 and 68
     const double tv = fma(c_tone_a[0], S.tvp[0][lane], fma(c_tv2_a[0], st.p[2], S.tvh[par][lane]));
@@ -1434,7 +1434,7 @@ __device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const
 
 // The time loop, one instantiation per warp role.  All roles execute the same sequence of CTA barriers.
 //   ROLE 0: dynamic chain, 1: static chain, 2: X1 (glottis + output), 3: X2 (radiation loads; noise sources)
-template <int ROLE, bool NOISE>
+template <int ROLE, bool NOISE, bool OPT>
 __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const KArgs &A, const int lane, const int warp,
                                          const bool hw_ok) {
   const int tract_raw = blockIdx.x * P.lanes_per_cta + lane;
@@ -1530,11 +1530,11 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(0);
     // ============ pass A: update (step n-1), elements + rows (step n) ============
     // (state dump requested for this step: update and rows in two separate passes, the dump in between)
-    if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true>(P, S, lane, warp, wcfg, dst, X);
+    if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true, OPT>(P, S, lane, warp, wcfg, dst, X);
     else for (int half = 0; half < (X.dumping ? 2 : 1); half++) {
       StepCtx Y = X;
       if (X.dumping) { Y.upd = X.upd && half == 0; Y.rows = X.rows && half == 1; }
-      if (ROLE == 0) dwarp_pass_a<false>(P, S, lane, warp, wcfg, dst, Y);
+      if (ROLE == 0) dwarp_pass_a<false, OPT>(P, S, lane, warp, wcfg, dst, Y);
       if (ROLE == 1) swarp_pass_a(P, S, lane, warp, wcfg, scfg, sst, Y);
       if (ROLE == 3 && Y.upd) radiation_update(P, lane, rr, nr, Y, A.dump);
       if (X.dumping && half == 0) {
@@ -1578,12 +1578,12 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     }
     if (!X.rows) break;
     // ============ first rows + elimination of the segments || glottis ============
-    if (ROLE == 0) dwarp_eliminate<NOISE>(P, S, lane, warp, wcfg, dst, n & 1);
+    if (ROLE == 0) dwarp_eliminate<NOISE, OPT>(P, S, lane, warp, wcfg, dst, n & 1);
     if (ROLE == 1) {
       const double psrc = X.ratio1 * S.gctl[0][G_PRESSURE][lane] + X.ratio * S.gctl[1][G_PRESSURE][lane];
       swarp_eliminate(P, S, lane, warp, wcfg, scfg, sst, psrc);
     }
-    if (ROLE == 3 && (P.transvelar || P.var_loss)) {
+    if (ROLE == 3 && OPT && (P.transvelar || P.var_loss)) {
       // this step's filter outputs (same expression as their consumers use), then the history parts of the next step
       const int par = n & 1;
       if (P.transvelar) {
@@ -1652,9 +1652,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;
 }
 
-// NOISE = generate_noise_sources: a separate instantiation, so that the (large) noise-source code of warp X2 does not
+// OPT = transvelar coupling or variable entrance loss switched on; NOISE = generate_noise_sources: a separate instantiation, so that the (large) noise-source code of warp X2 does not
 // sit in the instruction stream of the noise-free kernel.
-template <bool NOISE>
+template <bool NOISE, bool OPT>
 __global__ void __launch_bounds__(TDS_THREADS, 1)
 tds_batch_kernel(const TdsParams P, const KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1717,10 +1717,10 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
   __syncthreads();
 
   switch (warp) {
-    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, NOISE>(P, S, A, lane, warp, hw_lane < LANES); break;
-    case W_X1: run_role<2, NOISE>(P, S, A, lane, warp, hw_lane < LANES); break;
-    case W_X2: run_role<3, NOISE>(P, S, A, lane, warp, hw_lane < LANES); break;
-    default: run_role<0, NOISE>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_X1: run_role<2, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_X2: run_role<3, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
+    default: run_role<0, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
   }
 }
 static_assert(NSEP == NW, "prologue zeroing assumes NSEP == NW");
@@ -1794,7 +1794,9 @@ cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tu
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
   static_assert(sizeof(TdsSmem) <= 227 * 1024, "TdsSmem exceeds the 227 KB a CTA can have on sm_100a");
-  auto kernel = P.noise ? tds_batch_kernel<true> : tds_batch_kernel<false>;
+  const bool opt = P.transvelar || P.var_loss;  // non-default options: separate instantiations, like the noise sources
+  auto kernel = P.noise ? (opt ? tds_batch_kernel<true, true> : tds_batch_kernel<true, false>)
+                        : (opt ? tds_batch_kernel<false, true> : tds_batch_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(TdsSmem));  // per device; cheap
   if (e != cudaSuccess) return e;
