@@ -57,7 +57,6 @@ int fill_tl_params(const afs_tl_options *o, int n_tubes, int type, int section, 
   if (!o || n_tubes < 0 || num_freq < 2 || !(f0 > 0.0)) return AFS_ERR_BAD_ARGUMENT;  // bin 0 aliases bin 1
   if (type < AFS_INPUT_IMPEDANCE || type > AFS_RADIATION) return AFS_ERR_BAD_ARGUMENT;
   if (section < -1 || section >= AFS_NUM_SECTIONS) return AFS_ERR_BAD_ARGUMENT;
-  if (!o->lumped_elements) return AFS_ERR_UNSUPPORTED;
   if (o->radiation < AFS_NO_RADIATION || o->radiation > AFS_PARALLEL_RADIATION) return AFS_ERR_BAD_ARGUMENT;
   p->o = *o;
   p->n_tubes = n_tubes; p->type = type; p->section = section; p->num_freq = num_freq; p->f0 = f0;

@@ -130,7 +130,7 @@ typedef struct afs_tl_options {
   int32_t soft_walls;
   int32_t hagen_resistance;
   int32_t inner_length_corrections;
-  int32_t lumped_elements; /* 0 (wave propagation with cosh/sinh) is AFS_ERR_UNSUPPORTED */
+  int32_t lumped_elements; /* 0: wave propagation with cosh/sinh (TlModel.cpp:896-929), 1e-9 parity instead of bitwise */
   int32_t paranasal_sinuses;
   int32_t piriform_fossa;
   int32_t static_pressure_drops;

@@ -80,6 +80,19 @@ def test_tl_live_reference_random_tubes(oracle):
 # ---------------------------------------------------------------------------------------------
 # TDS restatement vs reference fixtures (bit-identical flow and audio, noise sources off)
 # ---------------------------------------------------------------------------------------------
+def test_tl_wave_propagation_mode_live_reference(oracle, shapes):
+    """lumpedElements = false (TlModel.cpp:896-929): glibc csqrt/ccosh/csinh on both sides -> bit-identical."""
+    if not have_ref():
+        pytest.skip("compiled reference not available")
+    from oracle.pyoracle import Ref, tl_options_default
+    o = tl_options_default(); o.lumped_elements = 0; o.heat_conduction = 1
+    fr = shapes["frames"][[0, 5, 20, 60, 90]]
+    for t, sec in ((2, 25), (0, 30), (3, -1)):
+        re, im = oracle.tl_spectrum(fr, 22050.0 / 2048, 938, type_=t, section=sec, opts=o)
+        rr, ri = Ref(22).tl_spectrum(fr, 2048, type_=t, section=sec, opts=o)
+        assert np.array_equal(re, rr[:, :938]) and np.array_equal(im, ri[:, :938])
+
+
 def test_tds_static_vowel_bit_identical(oracle):
     g = load_golden("tds_reference.npz")
     a, u = oracle.tds_synthesize(g["static_frames"], g["static_glottis"], [2205], 44100.0, 2)
