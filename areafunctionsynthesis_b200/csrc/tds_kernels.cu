@@ -118,6 +118,7 @@ struct TdsSmem {
   double bE[NW][LANES], bL[NW][LANES], bR[NW][LANES], bI[NW][LANES], bG[NW][LANES], bD[NW][LANES];
   double csib[4][LANES];                         // history term c of the branch heads 29, 84, 41, 65 (sibling rows)
   double sepD[NSEP][LANES], sepR[NSEP][LANES], redW[NSEP][LANES];
+  double redC[2][LANES];                         // fill couplings 29 <-> 40 and 41 <-> 52 of the reduced system
   double sideDD[NW][LANES], sideDR[NW][LANES], sideF[NW][LANES];
   double lf[5][LANES];                           // fossa current 84 folded into the clique {28, 29}
   double radc[2][2][LANES];                      // radiation pairs folded into currents 64 / 83
@@ -141,6 +142,7 @@ struct TdsSmem {
   // same for all tracts
   SRec srec[NSX];
   double wallc[4][3];             // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = zeros
+  double rcn[8];                  // constant factors of the reduced system (reduced_constants)
   STab stab[NW];
 };
 
@@ -1157,42 +1159,77 @@ __device__ __forceinline__ void red_elim(double &dx, double rx, double c, double
   dy = fma(-t, c, dy);
   ry = fma(-t, rx, ry);
 }
-// forward: chain T (7,15,22,28,29,34 -> 40), chain M (64,58,52,46 -> 41), chain N (83,75,70 -> 65)
+// Constants of the trachea end of chain T (separators 7 and 15 have constant pivots): computed once per launch.
+//   rcn[0] = 1/d7', [1] = c(7,15)/d7', [2] = 1/d15', [3] = c(15,22)/d15', [4] = c(15,22)^2/d15' (comes off d22)
+__device__ __noinline__ void reduced_constants(TdsSmem &S, const int lane) {
+  const double c0 = S.sideF[W_T1][lane], c1 = S.sideF[W_T2][lane];
+  const double w7 = 1.0 / (S.sepD[S7][lane] - S.sideDD[W_T1][lane]);
+  const double t7 = c0 * w7;
+  const double w15 = 1.0 / (S.sepD[S15][lane] - S.sideDD[W_T2][lane] - t7 * c0);
+  const double t15 = c1 * w15;
+  if (lane == 0) { S.rcn[0] = w7; S.rcn[1] = t7; S.rcn[2] = w15; S.rcn[3] = t15; S.rcn[4] = t15 * c1; }
+}
+// forward: chain T (7,15,22,28,29,34 -> 40), chain M (64,58,52,46 -> 41), chain N (83,75,70 -> 65).  In the two long
+// chains two independent eliminations run interleaved in the same warp (22 -> 28 beside 34 -> {29, 40}; 64 -> 58 beside
+// 46 -> {41, 52}), which shortens the serial chain of reciprocals -- the reduced system is pure latency.
 __device__ __noinline__ void reduced_forward(TdsSmem &S, const int lane, const int chain) {
   if (chain == 0) {
-    const double c0 = S.sideF[W_T1][lane], c1 = S.sideF[W_T2][lane], c2 = S.sideF[W_GP][lane], c3 = S.lf[4][lane];
-    const double c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane];
-    double d7 = S.sepD[S7][lane] - S.sideDD[W_T1][lane], r7 = S.sepR[S7][lane] - S.sideDR[W_T1][lane];
-    double d15 = S.sepD[S15][lane] - S.sideDD[W_T2][lane], r15 = S.sepR[S15][lane] - S.sideDR[W_T2][lane];
-    double d22 = S.sepD[S22][lane] - S.sideDD[W_GP][lane], r22 = S.sepR[S22][lane] - S.sideDR[W_GP][lane];
+    const double c2 = S.sideF[W_GP][lane], c3 = S.lf[4][lane], c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane];
+    const double r7 = S.sepR[S7][lane] - S.sideDR[W_T1][lane];
+    const double r15 = fma(-S.rcn[1], r7, S.sepR[S15][lane] - S.sideDR[W_T2][lane]);
+    double d22 = S.sepD[S22][lane] - S.sideDD[W_GP][lane] - S.rcn[4];
+    const double r22 = fma(-S.rcn[3], r15, S.sepR[S22][lane] - S.sideDR[W_GP][lane]);
     double d28 = S.sepD[S28][lane] - S.lf[0][lane], r28 = S.sepR[S28][lane] - S.lf[1][lane];
     double d29 = S.sepD[S29][lane] - S.lf[2][lane], r29 = S.sepR[S29][lane] - S.lf[3][lane];
-    double d34 = S.sepD[S34][lane] - S.sideDD[W_P2][lane], r34 = S.sepR[S34][lane] - S.sideDR[W_P2][lane];
+    double d34 = S.sepD[S34][lane] - S.sideDD[W_P2][lane];
+    const double r34 = S.sepR[S34][lane] - S.sideDR[W_P2][lane];
     double d40 = S.sepD[S40][lane], r40 = S.sepR[S40][lane];
-    red_elim(d7, r7, c0, d15, r15);
-    red_elim(d15, r15, c1, d22, r22);
-    red_elim(d22, r22, c2, d28, r28);
-    red_elim(d28, r28, c3, d29, r29);
-    red_elim(d29, r29, c4, d34, r34);
-    red_elim(d34, r34, c5, d40, r40);
-    S.redW[S7][lane] = d7; S.sepR[S7][lane] = r7; S.redW[S15][lane] = d15; S.sepR[S15][lane] = r15;
-    S.redW[S22][lane] = d22; S.sepR[S22][lane] = r22; S.redW[S28][lane] = d28; S.sepR[S28][lane] = r28;
-    S.redW[S29][lane] = d29; S.sepR[S29][lane] = r29; S.redW[S34][lane] = d34; S.sepR[S34][lane] = r34;
+    // 22 -> 28  ||  34 -> {29, 40} (fill: coupling 29 <-> 40)
+    const double w22 = fast_rcp(d22), w34 = fast_rcp(d34);
+    const double t22 = c2 * w22, ta = c4 * w34, tb = c5 * w34;
+    d28 = fma(-t22, c2, d28); r28 = fma(-t22, r22, r28);
+    d29 = fma(-ta, c4, d29); r29 = fma(-ta, r34, r29);
+    d40 = fma(-tb, c5, d40); r40 = fma(-tb, r34, r40);
+    const double c6 = -ta * c5;
+    // 28 -> 29, 29 -> 40
+    const double w28 = fast_rcp(d28);
+    const double t28 = c3 * w28;
+    d29 = fma(-t28, c3, d29); r29 = fma(-t28, r28, r29);
+    const double w29 = fast_rcp(d29);
+    const double t29 = c6 * w29;
+    d40 = fma(-t29, c6, d40); r40 = fma(-t29, r29, r40);
+    S.sepR[S7][lane] = r7; S.sepR[S15][lane] = r15;
+    S.redW[S22][lane] = w22; S.sepR[S22][lane] = r22; S.redW[S28][lane] = w28; S.sepR[S28][lane] = r28;
+    S.redW[S29][lane] = w29; S.sepR[S29][lane] = r29; S.redW[S34][lane] = w34; S.sepR[S34][lane] = r34;
     S.redW[S40][lane] = d40; S.sepR[S40][lane] = r40;
+    S.redC[0][lane] = c6;
   } else if (chain == 1) {
     const double c0 = S.sideF[W_M3][lane], c1 = S.sideF[W_M2][lane], c2 = S.sideF[W_M1][lane], c3 = S.sideF[W_M0][lane];
     double d41 = S.sepD[S41][lane], r41 = S.sepR[S41][lane];
-    double d46 = S.sepD[S46][lane] - S.sideDD[W_M1][lane], r46 = S.sepR[S46][lane] - S.sideDR[W_M1][lane];
+    double d46 = S.sepD[S46][lane] - S.sideDD[W_M1][lane];
+    const double r46 = S.sepR[S46][lane] - S.sideDR[W_M1][lane];
     double d52 = S.sepD[S52][lane] - S.sideDD[W_M2][lane], r52 = S.sepR[S52][lane] - S.sideDR[W_M2][lane];
     double d58 = S.sepD[S58][lane] - S.sideDD[W_M3][lane], r58 = S.sepR[S58][lane] - S.sideDR[W_M3][lane];
-    double d64 = S.sepD[S64][lane] - S.radc[0][0][lane], r64 = S.sepR[S64][lane] - S.radc[0][1][lane];
-    red_elim(d64, r64, c0, d58, r58);
-    red_elim(d58, r58, c1, d52, r52);
-    red_elim(d52, r52, c2, d46, r46);
-    red_elim(d46, r46, c3, d41, r41);
-    S.redW[S64][lane] = d64; S.sepR[S64][lane] = r64; S.redW[S58][lane] = d58; S.sepR[S58][lane] = r58;
-    S.redW[S52][lane] = d52; S.sepR[S52][lane] = r52; S.redW[S46][lane] = d46; S.sepR[S46][lane] = r46;
+    double d64 = S.sepD[S64][lane] - S.radc[0][0][lane];
+    const double r64 = S.sepR[S64][lane] - S.radc[0][1][lane];
+    // 64 -> 58  ||  46 -> {41, 52} (fill: coupling 41 <-> 52)
+    const double w64 = fast_rcp(d64), w46 = fast_rcp(d46);
+    const double t64 = c0 * w64, ta = c3 * w46, tb = c2 * w46;
+    d58 = fma(-t64, c0, d58); r58 = fma(-t64, r64, r58);
+    d41 = fma(-ta, c3, d41); r41 = fma(-ta, r46, r41);
+    d52 = fma(-tb, c2, d52); r52 = fma(-tb, r46, r52);
+    const double c6 = -ta * c2;
+    // 58 -> 52, 52 -> 41
+    const double w58 = fast_rcp(d58);
+    const double t58 = c1 * w58;
+    d52 = fma(-t58, c1, d52); r52 = fma(-t58, r58, r52);
+    const double w52 = fast_rcp(d52);
+    const double t52 = c6 * w52;
+    d41 = fma(-t52, c6, d41); r41 = fma(-t52, r52, r41);
+    S.redW[S64][lane] = w64; S.sepR[S64][lane] = r64; S.redW[S58][lane] = w58; S.sepR[S58][lane] = r58;
+    S.redW[S52][lane] = w52; S.sepR[S52][lane] = r52; S.redW[S46][lane] = w46; S.sepR[S46][lane] = r46;
     S.redW[S41][lane] = d41; S.sepR[S41][lane] = r41;
+    S.redC[1][lane] = c6;
   } else {
     const double c0 = S.sideF[W_N2][lane], c1 = S.sideF[W_N1][lane], c2 = S.sideF[W_NV][lane];
     double d65 = S.sepD[S65][lane], r65 = S.sepR[S65][lane];
@@ -1227,21 +1264,22 @@ __device__ __noinline__ void reduced_junction(TdsSmem &S, const int lane) {
 __device__ __noinline__ void reduced_back(TdsSmem &S, const int lane, const int chain) {
   if (chain == 0) {
     const double c0 = S.sideF[W_T1][lane], c1 = S.sideF[W_T2][lane], c2 = S.sideF[W_GP][lane], c3 = S.lf[4][lane];
-    const double c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane];
+    const double c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane], c6 = S.redC[0][lane];
     const double u40 = S.sepR[S40][lane];
-    const double u34 = (S.sepR[S34][lane] - c5 * u40) * S.redW[S34][lane];
-    const double u29 = (S.sepR[S29][lane] - c4 * u34) * S.redW[S29][lane];
+    const double u29 = (S.sepR[S29][lane] - c6 * u40) * S.redW[S29][lane];
+    const double u34 = (S.sepR[S34][lane] - c4 * u29 - c5 * u40) * S.redW[S34][lane];
     const double u28 = (S.sepR[S28][lane] - c3 * u29) * S.redW[S28][lane];
     const double u22 = (S.sepR[S22][lane] - c2 * u28) * S.redW[S22][lane];
-    const double u15 = (S.sepR[S15][lane] - c1 * u22) * S.redW[S15][lane];
-    const double u7 = (S.sepR[S7][lane] - c0 * u15) * S.redW[S7][lane];
+    const double u15 = (S.sepR[S15][lane] - c1 * u22) * S.rcn[2];
+    const double u7 = (S.sepR[S7][lane] - c0 * u15) * S.rcn[0];
     S.sepR[S34][lane] = u34; S.sepR[S29][lane] = u29; S.sepR[S28][lane] = u28; S.sepR[S22][lane] = u22;
     S.sepR[S15][lane] = u15; S.sepR[S7][lane] = u7;
   } else if (chain == 1) {
     const double c0 = S.sideF[W_M3][lane], c1 = S.sideF[W_M2][lane], c2 = S.sideF[W_M1][lane], c3 = S.sideF[W_M0][lane];
+    const double c6 = S.redC[1][lane];
     const double u41 = S.sepR[S41][lane];
-    const double u46 = (S.sepR[S46][lane] - c3 * u41) * S.redW[S46][lane];
-    const double u52 = (S.sepR[S52][lane] - c2 * u46) * S.redW[S52][lane];
+    const double u52 = (S.sepR[S52][lane] - c6 * u41) * S.redW[S52][lane];
+    const double u46 = (S.sepR[S46][lane] - c3 * u41 - c2 * u52) * S.redW[S46][lane];
     const double u58 = (S.sepR[S58][lane] - c1 * u52) * S.redW[S58][lane];
     const double u64 = (S.sepR[S64][lane] - c0 * u58) * S.redW[S64][lane];
     S.sepR[S46][lane] = u46; S.sepR[S52][lane] = u52; S.sepR[S58][lane] = u58; S.sepR[S64][lane] = u64;
@@ -1482,6 +1520,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     xr.prevFlow = 0.0;
   }
   cta_sync();  // static boundary records / pivots visible
+  if (warp == W_T0) reduced_constants(S, lane);
 
   int interval = 0, i0 = 0, i1 = 0;
   double inv_len = 1.0;
