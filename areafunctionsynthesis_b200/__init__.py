@@ -7,6 +7,8 @@ device raises.
 """
 from .api import (  # noqa: F401
     FRAME_DTYPE,
+    TL_ARITHMETIC_FAST,
+    TL_ARITHMETIC_REFERENCE,
     AfsError,
     Context,
     TdsOptions,

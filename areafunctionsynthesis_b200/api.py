@@ -28,6 +28,7 @@ assert FRAME_DTYPE.itemsize == 1184
 SPECTRUM_TYPES = {"input_impedance": 0, "output_impedance": 1, "flow_source_tf": 2, "pressure_source_tf": 3,
                   "radiation": 4}
 FIRST_PHARYNX_SECTION = 25
+TL_ARITHMETIC_REFERENCE, TL_ARITHMETIC_FAST = 0, 1  # enum afs_tl_arithmetic
 
 
 class AfsError(RuntimeError):
@@ -38,7 +39,8 @@ class TlOptions(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "radiation", "boundary_layer", "heat_conduction", "soft_walls", "hagen_resistance",
         "inner_length_corrections", "lumped_elements", "paranasal_sinuses", "piriform_fossa",
-        "static_pressure_drops")] + [("lung_pressure_dPa", C.c_double)]
+        "static_pressure_drops")] + [("lung_pressure_dPa", C.c_double), ("arithmetic", C.c_int32),
+                                     ("reserved", C.c_int32)]
 
 
 class TdsOptions(C.Structure):

@@ -22,6 +22,7 @@ COMMON = [*EXTRA_DEFS, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", 
 # per-file device flags
 UNITS = {
     "tl_kernels.cu": ["-fmad=false"],
+    "tl_fast_kernels.cu": [],
     "tds_kernels.cu": [],
     "probe_kernels.cu": [],
     "raster_kernels.cu": ["-fmad=false"],

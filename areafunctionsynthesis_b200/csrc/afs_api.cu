@@ -58,6 +58,8 @@ int fill_tl_params(const afs_tl_options *o, int n_tubes, int type, int section, 
   if (type < AFS_INPUT_IMPEDANCE || type > AFS_RADIATION) return AFS_ERR_BAD_ARGUMENT;
   if (section < -1 || section >= AFS_NUM_SECTIONS) return AFS_ERR_BAD_ARGUMENT;
   if (o->radiation < AFS_NO_RADIATION || o->radiation > AFS_PARALLEL_RADIATION) return AFS_ERR_BAD_ARGUMENT;
+  if (o->arithmetic != AFS_TL_ARITHMETIC_REFERENCE && o->arithmetic != AFS_TL_ARITHMETIC_FAST) return AFS_ERR_BAD_ARGUMENT;
+  if (o->reserved != 0) return AFS_ERR_BAD_ARGUMENT;
   p->o = *o;
   p->n_tubes = n_tubes; p->type = type; p->section = section; p->num_freq = num_freq; p->f0 = f0;
   // TlModel.cpp:14-19 -- same expressions, host libm
@@ -128,6 +130,7 @@ void afs_tl_options_default(afs_tl_options *o) {
   o->boundary_layer = 1; o->heat_conduction = 0; o->soft_walls = 1; o->hagen_resistance = 0;
   o->inner_length_corrections = 0; o->lumped_elements = 1; o->paranasal_sinuses = 1; o->piriform_fossa = 0;
   o->static_pressure_drops = 1; o->lung_pressure_dPa = 0.0;
+  o->arithmetic = AFS_TL_ARITHMETIC_REFERENCE; o->reserved = 0;
 }
 
 void afs_tds_options_default(afs_tds_options *o) {
@@ -235,7 +238,10 @@ int afs_tl_sweep_device(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes, c
     }
     return AFS_OK;
   }
-  CU(launch_tl_sweep(p, d_tubes, d_re, d_im, (cudaStream_t)stream));
+  if (p.o.arithmetic == AFS_TL_ARITHMETIC_FAST && p.o.lumped_elements && spectrum_type != AFS_RADIATION)
+    CU(launch_tl_sweep_fast(p, d_tubes, d_re, d_im, (cudaStream_t)stream));
+  else
+    CU(launch_tl_sweep(p, d_tubes, d_re, d_im, (cudaStream_t)stream));
   ctx->launches++;
   return AFS_OK;
 }

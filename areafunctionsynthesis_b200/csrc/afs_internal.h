@@ -21,6 +21,8 @@ struct FormantParams {
 };
 cudaError_t launch_tl_sweep(const TlParams &p, const afs_tube_frame *d_tubes, double *d_re, double *d_im,
                             cudaStream_t stream);
+cudaError_t launch_tl_sweep_fast(const TlParams &p, const afs_tube_frame *d_tubes, double *d_re, double *d_im,
+                                 cudaStream_t stream);  // tl_fast_kernels.cu (afs_tl_options.arithmetic = FAST)
 cudaError_t launch_formant_pick(const FormantParams &p, const afs_tube_frame *d_tubes, const double *d_re,
                                 const double *d_im, double *d_freq, double *d_bw, int32_t *d_num, int32_t *d_flags,
                                 cudaStream_t stream);

@@ -76,6 +76,15 @@ enum afs_radiation_type {
   AFS_PARALLEL_RADIATION = 3
 };
 
+/* How the TL sweep evaluates the chain products of TlModel::prepareCalculations (TlModel.cpp:484-676).
+ *   REFERENCE: the reference's operations in the reference's order, no FMA contraction: spectra are
+ *              BIT-IDENTICAL to TlModel::getSpectrum.
+ *   FAST:      the same products as ladder recurrences (series/shunt updates, shared wall-admittance
+ *              reciprocals, FMA): ~6x fewer FP64 instructions, spectra within 1e-9 relative of the
+ *              reference (the north-star bar).  Wave-propagation mode (lumped_elements = 0) and the
+ *              RADIATION spectrum are always evaluated in REFERENCE arithmetic. */
+enum afs_tl_arithmetic { AFS_TL_ARITHMETIC_REFERENCE = 0, AFS_TL_ARITHMETIC_FAST = 1 };
+
 /* TdsModel::GlottisLossOptions / SolverType (TdsModel.h:60-73) */
 enum afs_glottis_loss { AFS_STANDARD_ENTRANCE_LOSS = 0, AFS_ENTRANCE_LOSS_VAN_DEN_BERG = 1, AFS_VARIABLE_ENTRANCE_LOSS = 2 };
 
@@ -137,6 +146,9 @@ typedef struct afs_tl_options {
   /* TlModel keeps the lung pressure as hidden state (TlModel.cpp:253-260,
    * SURVEY.md App. D); here it is explicit.  Default 0. */
   double lung_pressure_dPa;
+  /* enum afs_tl_arithmetic.  Default AFS_TL_ARITHMETIC_REFERENCE. */
+  int32_t arithmetic;
+  int32_t reserved; /* must be 0 */
 } afs_tl_options;
 
 /* TdsModel::Options (TdsModel.h:75-87); defaults of TdsModel::TdsModel()

@@ -38,7 +38,8 @@ class TlOptions(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "radiation", "boundary_layer", "heat_conduction", "soft_walls", "hagen_resistance",
         "inner_length_corrections", "lumped_elements", "paranasal_sinuses", "piriform_fossa",
-        "static_pressure_drops")] + [("lung_pressure_dPa", C.c_double)]
+        "static_pressure_drops")] + [("lung_pressure_dPa", C.c_double), ("arithmetic", C.c_int32),
+                                     ("reserved", C.c_int32)]
 
 
 class TdsOptions(C.Structure):

@@ -30,7 +30,7 @@ def test_library_is_built_in_tree_and_exports_the_header():
 
 def test_struct_layouts_match_the_header():
     assert afs.FRAME_DTYPE.itemsize == 1184
-    assert C.sizeof(afs.TlOptions) == 48
+    assert C.sizeof(afs.TlOptions) == 56
     assert C.sizeof(afs.TdsOptions) == 8 * 4 + 8 + 16 * 8
     o = afs.tl_options_default()
     assert (o.radiation, o.boundary_layer, o.soft_walls, o.lumped_elements, o.paranasal_sinuses,

@@ -108,6 +108,9 @@ def test_edge_cases(ctx, oracle, shapes):
     o = afs.tl_options_default(); o.radiation = 7
     with pytest.raises(afs.AfsError):
         ctx.tl_sweep(f, F0_938, 938, opts=o)
+    o = afs.tl_options_default(); o.arithmetic = 2
+    with pytest.raises(afs.AfsError):
+        ctx.tl_sweep(f, F0_938, 938, opts=o)
 
 
 def test_full_size_linearity_property(ctx):
@@ -153,3 +156,98 @@ def test_wave_propagation_mode(ctx, oracle, shapes):
     # the mode really is a different model
     rl, il = ctx.tl_sweep(fr, F0_2048, 2048)
     assert np.max(np.abs(np.hypot(re, im) - np.hypot(rl, il))) > 0
+
+
+# ---- afs_tl_options.arithmetic = FAST (K2f tl_sweep_fast_kernel) -------------------------------------------
+def _fast_opts(**kw):
+    import areafunctionsynthesis_b200 as afs
+    a, b = afs.tl_options_default(), afs.tl_options_default()
+    b.arithmetic = afs.TL_ARITHMETIC_FAST
+    for k, v in kw.items():
+        setattr(a, k, v); setattr(b, k, v)
+    return a, b
+
+
+def test_fast_arithmetic_against_reference_arithmetic(ctx, oracle, shapes):
+    """The ladder-recurrence kernel against the bit-identical one (== the oracle, checked here too).
+    Bar: |dH|/|H| <= 1e-9 for 99.9 % of all (area function, bin) points and <= 1e-8 everywhere; the points between
+    are those where the REFERENCE's own rounding noise exceeds 1e-9 (next test)."""
+    fr = np.concatenate([shapes["frames"], random_frames(96, seed=20260001)])
+    a, b = _fast_opts()
+    re, im = ctx.tl_sweep(fr, F0_2048, 2048, opts=a)
+    ro, io = oracle.tl_spectrum(fr, F0_2048, 2048)
+    assert np.array_equal(re, ro) and np.array_equal(im, io)
+    rf, jf = ctx.tl_sweep(fr, F0_2048, 2048, opts=b)
+    h, hf = re + 1j * im, rf + 1j * jf
+    rel = np.abs(hf - h) / np.abs(h)
+    assert np.quantile(rel, 0.999) <= 1e-9, np.quantile(rel, 0.999)
+    assert rel.max() <= 1e-8, rel.max()
+    # ragged bin counts, single tube, bin 0 aliasing bin 1
+    for nf in (2, 127, 129, 513, 1000):
+        r1, i1 = ctx.tl_sweep(fr[:3], 7.0, nf, opts=a)
+        r2, i2 = ctx.tl_sweep(fr[:3], 7.0, nf, opts=b)
+        assert np.max(np.abs((r2 + 1j * i2) - (r1 + 1j * i1)) / np.abs(r1 + 1j * i1)) <= 1e-8, nf
+        assert r2[0, 0] == r2[0, 1] and i2[0, 0] == i2[0, 1]
+
+
+def test_fast_arithmetic_against_extended_precision(ctx, oracle, shapes):
+    """Which arithmetic is nearer to the value the reference's formulas define?  tools/tl_truth.py evaluates them
+    with a 64-bit mantissa (x87 long double).  The fast kernel stays within 1e-11 of it; the reference arithmetic
+    (inverse(P[section]) * P[40] cancels, TlModel.cpp:1336) is up to ~1e-9 away -- so the distance between the two
+    kernels is the reference's rounding noise, not the fast kernel's."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from tl_truth import truth_flow_tf
+    n = len(shapes["names"])
+    fr = np.concatenate([shapes["frames"][[0, 4, 12, n + 0, n + 7]], random_frames(8, seed=20260001)[[1, 5]]])
+    a, b = _fast_opts()
+    re, im = ctx.tl_sweep(fr, F0_2048, 2048, opts=a)
+    rf, jf = ctx.tl_sweep(fr, F0_2048, 2048, opts=b)
+    bins = np.arange(2048)
+    worst_ref = worst_fast = 0.0
+    for i in range(len(fr)):
+        t = truth_flow_tf(oracle.expand_frame(fr[i:i + 1]), F0_2048, bins)
+        e_ref = float(np.max(np.abs((re[i] + 1j * im[i]) - t) / np.abs(t)))
+        e_fast = float(np.max(np.abs((rf[i] + 1j * jf[i]) - t) / np.abs(t)))
+        worst_ref, worst_fast = max(worst_ref, e_ref), max(worst_fast, e_fast)
+        assert e_fast <= 1e-11, (i, e_fast)
+    assert worst_fast < worst_ref
+
+
+def test_fast_arithmetic_types_sections_options(ctx, shapes):
+    """Every spectrum type / source section / lumped-element option through the fast kernel (generic and DIRECT
+    instantiations).  Transfer functions: 1e-8 pointwise; impedance spectra have poles and nulls where a pointwise
+    ratio is meaningless (the reference itself moves by 1e-7 there for a one-ulp change of an area):
+    1e-7 of the spectrum's scale."""
+    n = len(shapes["names"])
+    fr = np.concatenate([shapes["frames"][[0, 9, n + 30]], random_frames(13, seed=7)])
+    variants = (dict(), dict(piriform_fossa=1, inner_length_corrections=1, heat_conduction=1, hagen_resistance=1),
+                dict(soft_walls=0, paranasal_sinuses=0, radiation=1), dict(radiation=2, lung_pressure_dPa=8000.0),
+                dict(radiation=0, boundary_layer=0, static_pressure_drops=0))
+    for kw in variants:
+        a, b = _fast_opts(**kw)
+        for t, sec in ((2, 25), (2, 0), (2, 24), (2, 33), (2, 40), (2, 41), (2, 50), (2, 64), (2, 65), (3, 0), (3, 30),
+                       (3, 41), (3, -1), (0, 0), (0, 30), (0, 70), (1, 30), (1, 64), (1, 83)):
+            r1, i1 = ctx.tl_sweep(fr, F0_938, 938, spectrum_type=t, section=sec, opts=a)
+            r2, i2 = ctx.tl_sweep(fr, F0_938, 938, spectrum_type=t, section=sec, opts=b)
+            h1, h2 = r1 + 1j * i1, r2 + 1j * i2
+            assert np.all(np.isfinite(r2)) and np.all(np.isfinite(i2)), (kw, t, sec)
+            scale = np.max(np.abs(h1), axis=1, keepdims=True)
+            assert np.max(np.abs(h2 - h1) / scale) <= 1e-7, (kw, t, sec)
+            if t == 2:
+                assert np.max(np.abs(h2 - h1) / np.abs(h1)) <= 1e-8, (kw, t, sec)
+    # modes the fast kernel does not serve are routed to the reference arithmetic: identical results
+    a, b = _fast_opts(lumped_elements=0)
+    assert np.array_equal(ctx.tl_sweep(fr, F0_938, 938, opts=a)[0], ctx.tl_sweep(fr, F0_938, 938, opts=b)[0])
+    a, b = _fast_opts()
+    assert np.array_equal(ctx.tl_sweep(fr, F0_938, 938, spectrum_type=4, section=0, opts=a)[1],
+                          ctx.tl_sweep(fr, F0_938, 938, spectrum_type=4, section=0, opts=b)[1])
+
+
+def test_fast_arithmetic_formants(ctx, shapes):
+    a, b = _fast_opts()
+    fr = shapes["frames"]
+    f1, bw1, n1, fl1 = ctx.tl_formants(fr, opts=a)
+    f2, bw2, n2, fl2 = ctx.tl_formants(fr, opts=b)
+    assert np.array_equal(n1, n2) and np.array_equal(fl1, fl2)
+    assert np.max(np.abs(f2 - f1)) <= 1e-5 and np.max(np.abs(bw2 - bw1)) <= 1e-4  # Hz
