@@ -78,6 +78,8 @@ def load_library():
     lib.afs_tl_sweep.argtypes = [vp, vp, i32, vp, i32, i32, dbl, i32, vp, vp]
     lib.afs_tl_sweep_device.argtypes = [vp, vp, i32, vp, i32, i32, dbl, i32, vp, vp, vp]
     lib.afs_tl_formants.argtypes = [vp, vp, i32, vp, dbl, i32, i32, vp, vp, vp, vp]
+    lib.afs_tl_impulse_response.argtypes = [vp, vp, i32, vp, dbl, i32, vp]
+    lib.afs_tl_impulse_response_device.argtypes = [vp, vp, i32, vp, dbl, i32, vp, vp]
     lib.afs_tds_synthesize.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp]
     lib.afs_tds_synthesize_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
     lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
@@ -203,6 +205,16 @@ class Context:
         _check(self.lib, self.lib.afs_tl_sweep_device(self.h, C.byref(opts), int(n), _ptr(d_frames),
                                                       int(spectrum_type), int(section), float(f0_hz), int(num_freq),
                                                       _ptr(d_re), _ptr(d_im), C.c_void_p(stream)), self.h)
+
+    def tl_impulse_response(self, frames, sampling_rate_hz=22050.0, length_exponent=9, opts=None):
+        """TlModel::getImpulseResponse for a batch: returns [n, 2**length_exponent]."""
+        opts = opts or tl_options_default()
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        n = len(frames)
+        out = np.empty((n, 1 << int(length_exponent)))
+        _check(self.lib, self.lib.afs_tl_impulse_response(self.h, C.byref(opts), n, _ptr(frames), float(sampling_rate_hz),
+                                                          int(length_exponent), _ptr(out)), self.h)
+        return out
 
     def tl_formants(self, frames, sampling_rate_hz=22050.0, spectrum_length=2048, max_formants=8, opts=None):
         opts = opts or tl_options_default()

@@ -307,6 +307,65 @@ int afs_tl_formants(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes, const
   return AFS_OK;
 }
 
+int afs_tl_impulse_response_device(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes,
+                                   const afs_tube_frame *d_tubes, double sampling_rate_hz, int length_exponent,
+                                   double *d_out, void *stream) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (n_tubes < 0 || length_exponent < 4 || length_exponent > 11 || !(sampling_rate_hz > 0)) return AFS_ERR_BAD_ARGUMENT;
+  if (n_tubes == 0) return AFS_OK;
+  if (!d_tubes || !d_out) return AFS_ERR_BAD_ARGUMENT;
+  // bin grid of TlModel::getSpectrum (TlModel.cpp:125-148) without the MAX_NUM_FREQ cap
+  const int N = 1 << length_exponent;
+  const double f0 = sampling_rate_hz / (double)N;
+  int nf = (int)(10100.0 / f0);
+  if (nf >= N / 2) nf = N / 2 - 1;
+  if (nf < 2) return AFS_ERR_BAD_ARGUMENT;
+  void *d_re, *d_im, *d_tab;
+  const size_t nb = (size_t)n_tubes * nf * sizeof(double);
+  const size_t ntab = (size_t)(2 * (N - 1) + 2 * nf + N);
+  if ((rc = scratch(ctx, 1, nb, &d_re))) return rc;
+  if ((rc = scratch(ctx, 2, nb, &d_im))) return rc;
+  if ((rc = scratch(ctx, 7, ntab * sizeof(double), &d_tab))) return rc;
+  std::vector<double> tab(ntab);
+  double *tw_re = tab.data(), *tw_im = tw_re + (N - 1), *rad_re = tw_im + (N - 1), *rad_im = rad_re + nf,
+         *window = rad_im + nf;
+  impulse_response_tables(f0, length_exponent, nf, tw_re, tw_im, rad_re, rad_im, window);
+  cudaStream_t st = (cudaStream_t)stream;
+  // pageable source: the copy is staged before the call returns, `tab` may go out of scope
+  CU(cudaMemcpyAsync(d_tab, tab.data(), ntab * sizeof(double), cudaMemcpyHostToDevice, st));
+  rc = afs_tl_sweep_device(ctx, opts, n_tubes, d_tubes, AFS_FLOW_SOURCE_TF, AFS_FIRST_PHARYNX_SECTION, f0, nf,
+                           (double *)d_re, (double *)d_im, stream);
+  if (rc) return rc;
+  IrTables t;
+  const double *base = (const double *)d_tab;
+  t.tw_re = base; t.tw_im = base + (N - 1); t.rad_re = base + 2 * (N - 1); t.rad_im = t.rad_re + nf;
+  t.window = t.rad_im + nf;
+  CU(launch_impulse_response(n_tubes, length_exponent, nf, (const double *)d_re, (const double *)d_im, t, d_out, st));
+  ctx->launches++;
+  return AFS_OK;
+}
+
+int afs_tl_impulse_response(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
+                            double sampling_rate_hz, int length_exponent, double *impulse_response) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (n_tubes < 0 || length_exponent < 4 || length_exponent > 11) return AFS_ERR_BAD_ARGUMENT;
+  if (n_tubes == 0) return AFS_OK;
+  if (!tubes || !impulse_response) return AFS_ERR_BAD_ARGUMENT;
+  void *d_tubes, *d_out;
+  const size_t ob = (size_t)n_tubes * ((size_t)1 << length_exponent) * sizeof(double);
+  if ((rc = scratch(ctx, 0, (size_t)n_tubes * sizeof(afs_tube_frame), &d_tubes))) return rc;
+  if ((rc = scratch(ctx, 3, ob, &d_out))) return rc;
+  CU(cudaMemcpyAsync(d_tubes, tubes, (size_t)n_tubes * sizeof(afs_tube_frame), cudaMemcpyHostToDevice, ctx->stream));
+  rc = afs_tl_impulse_response_device(ctx, opts, n_tubes, (const afs_tube_frame *)d_tubes, sampling_rate_hz,
+                                      length_exponent, (double *)d_out, ctx->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(impulse_response, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return AFS_OK;
+}
+
 // ---------------------------------------------------------------------------
 // TDS
 // ---------------------------------------------------------------------------

@@ -9,6 +9,38 @@
 
 namespace afs {
 
+// Bin- and sample-dependent (tube-independent) factors of TlModel::getImpulseResponse, evaluated with the
+// host libm in the reference's own expressions so that the device result can be bit-identical:
+//   twiddles  the (ur, ui) sequence of complexFFT (Dsp.cpp:270-300): stage with half-length le2 owns
+//             entries [le2-1, 2*le2-1), entry j-1 being (sr + i*si)^(j-1) by repeated multiplication;
+//   radiation getRadiationCharacteristic (TlModel.cpp:685-697) at omega = 2 pi f0 i (TlModel.cpp:507-513);
+//   window    getImpulseResponseWindow (TlModel.cpp:70-80).
+void impulse_response_tables(double f0_hz, int length_exponent, int num_freq, double *tw_re, double *tw_im,
+                             double *rad_re, double *rad_im, double *window) {
+  const int N = 1 << length_exponent;
+  for (int l = 1; l <= length_exponent; l++) {
+    const int le2 = (1 << l) / 2;
+    double ur = 1.0, ui = 0.0;
+    const double sr = cos(M_PI / (double)le2), si = -sin(M_PI / (double)le2);
+    for (int j = 1; j <= le2; j++) {
+      tw_re[le2 - 1 + j - 1] = ur;
+      tw_im[le2 - 1 + j - 1] = ui;
+      const double tr = ur;
+      ur = tr * sr - ui * si;
+      ui = tr * si + ui * sr;
+    }
+  }
+  for (int i = 0; i < num_freq; i++) {
+    const double omega = 2.0 * M_PI * f0_hz * (double)i;
+    const double hr = 0.0, hi = (1.14e-3 * omega) / (4.0 * M_PI * 25.0);
+    const double angle = (omega * 25.0) / 3.5e4;
+    const double cr = cos(angle), ci = -sin(angle);
+    rad_re[i] = hr * cr - hi * ci;  // g++ inline std::complex product
+    rad_im[i] = hr * ci + hi * cr;
+  }
+  for (int i = 0; i < N; i++) window[i] = 0.5 - 0.5 * cos(M_PI + (M_PI * (double)i) / (double)(N - 1));
+}
+
 // Recursive Chebyshev type-I low-pass design, 0.5 % pass-band ripple, by
 // cascading two-pole stages (bilinear transform + low-pass-to-low-pass warp),
 // the classic table-driven recipe the reference uses in

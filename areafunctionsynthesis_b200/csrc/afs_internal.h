@@ -27,6 +27,16 @@ cudaError_t launch_formant_pick(const FormantParams &p, const afs_tube_frame *d_
                                 const double *d_im, double *d_freq, double *d_bw, int32_t *d_num, int32_t *d_flags,
                                 cudaStream_t stream);
 
+// impulse response: tables [N-1] twiddles (re, im), [num_freq] radiation characteristic (re, im), [N] window, all
+// computed on the host with libm exactly as the reference does (afs_host.cpp: impulse_response_tables)
+struct IrTables {
+  const double *tw_re, *tw_im, *rad_re, *rad_im, *window;
+};
+cudaError_t launch_impulse_response(int n_tubes, int length_exponent, int num_freq, const double *d_re,
+                                    const double *d_im, const IrTables &t, double *d_out, cudaStream_t stream);
+void impulse_response_tables(double f0_hz, int length_exponent, int num_freq, double *tw_re, double *tw_im,
+                             double *rad_re, double *rad_im, double *window);
+
 // ---- TDS ------------------------------------------------------------------
 struct TdsParams;  // tds_kernels.cu
 struct TdsLaunch {

@@ -192,18 +192,12 @@ void build_program(const TlParams &p, TlFastProgram &prog) {
   while (n < 128) o[n++] = OP_END;
 }
 
-}  // namespace
 
-// DIRECT: spectrum type FLOW_SOURCE_TF with the source in the trachea..pharynx chain (sections 0..40).
-template <bool DIRECT>
-__global__ void __launch_bounds__(TLF_THREADS, DIRECT ? 4 : 3)
-tl_sweep_fast_kernel(const TlParams p, const TlFastProgram prog, const afs_tube_frame *__restrict__ tubes,
-                     double *__restrict__ out_re, double *__restrict__ out_im) {
-  __shared__ TlFastShared S;
-  const int tube = blockIdx.y;
-  const afs_tube_frame *f = tubes + tube;
+// Per-CTA staging: sections, junction terms, static pressure drops, radiation constants, chain program.
+__device__ __forceinline__ void stage_all(const TlParams &p, const TlFastProgram *prog, const afs_tube_frame *f,
+                                          TlFastShared &S) {
   for (int k = threadIdx.x; k < NS; k += TLF_THREADS) stage_fast(p, f, S, k);
-  S.prog[threadIdx.x] = prog.op[threadIdx.x];
+  if (prog) S.prog[threadIdx.x] = prog->op[threadIdx.x];
   __syncthreads();
   if (threadIdx.x < NS) {  // junction inductances need both neighbours
     const int k = threadIdx.x;
@@ -240,129 +234,224 @@ tl_sweep_fast_kernel(const TlParams p, const TlFastProgram prog, const afs_tube_
     radiation_constants(p.o.radiation, S.raw_area[NOSE_LAST], S.rad[1]);
   }
   __syncthreads();
+}
 
+// Bin-dependent, section-independent factors.
+struct BinCtx {
+  double omega_raw, omega, sw;
+  cx g0, g1;  // wall admittance per unit (length*circumference): 1 / (Bw + j (w Mw - Kw / w)), two wall classes
+};
+__device__ __forceinline__ BinCtx bin_ctx(const TlParams &p, int bin) {
+  BinCtx c;
+  const int fi = bin == 0 ? 1 : bin;  // every accessor aliases bin 0 to bin 1 (TlModel.cpp:992,1065,1127,1293)
+  c.omega_raw = 2.0 * kPi * p.f0 * (double)fi;
+  c.omega = c.omega_raw < 0.0001 ? 0.0001 : c.omega_raw;
+  c.sw = sqrt(c.omega);
+  const double iw = 1.0 / c.omega;
+  const double x0 = c.omega * 2.1 - 84500.0 * iw, x1 = c.omega * 0.25 - 84500.0 * iw;
+  const double r0 = 1.0 / (800.0 * 800.0 + x0 * x0), r1 = 1.0 / (1000.0 * 1000.0 + x1 * x1);
+  c.g0 = cx_make(800.0 * r0, -x0 * r0);   // Tube.cpp:8-10
+  c.g1 = cx_make(1000.0 * r1, -x1 * r1);  // trachea, Tube.cpp:94-119
+  return c;
+}
+
+// Running state of a chain: product K, series impedance Zs not yet multiplied into K, elements of the last section.
+struct Chain {
+  m22 K;
+  cx Zs, Za, Yb;
+};
+__device__ __forceinline__ void chain_reset(Chain &c) { c.K = m22_unit(); c.Zs = cx_make(0, 0); }
+// one plain section: "series, shunt" (the second half-section stays pending in Zs)
+__device__ __forceinline__ void chain_section(const TlFastShared &S, const BinCtx &b, bool pre, cx g, int k, Chain &c) {
+  if (pre) {
+    const double2 z = S.pre[k];
+    c.Zs.re += z.x;
+    c.Zs.im = fma(b.omega_raw, z.y, c.Zs.im);
+  }
+  const TlElem e = S.e[k];
+  c.Za = cx_make(fma(e.rsq, b.sw, e.rf), b.omega * e.ls);
+  c.Yb = cx_make(fma(e.gp, b.sw, e.lc * g.re), fma(b.omega, e.cp, e.lc * g.im));
+  c.Zs = cx_add(c.Zs, c.Za);
+  series(c.K, c.Zs);
+  shunt(c.K, c.Yb);
+  c.Zs = c.Za;
+}
+__device__ __forceinline__ void chain_shunt(Chain &c, cx Y) {  // a shunt element closes the pending series element
+  series(c.K, c.Zs);
+  c.Zs = cx_make(0, 0);
+  shunt(c.K, Y);
+}
+// Helmholtz resonator shunt of a paranasal sinus (TlModel.cpp:659-670, 856-879)
+__device__ __forceinline__ void chain_sinus(const TlFastShared &S, const BinCtx &b, int k, Chain &c) {
+  const TlElem e = S.e[k];
+  const cx za = cx_make(e.rsq * b.sw, b.omega * e.ls), yb = cx_make(e.gp, b.omega * e.cp);
+  cx q = cx_mul(za, yb);
+  q.re += 1.0;
+  chain_shunt(c, cx_div(yb, q));
+}
+__device__ __forceinline__ m22 chain_product(const Chain &c) {  // matrixProduct[k] of the reference: K * series(Za)
+  m22 F = c.K;
+  series(F, c.Zs);
+  return F;
+}
+
+}  // namespace
+
+// Generic instantiation: every spectrum type / source section; the chains are walked by a small interpreter of
+// the host-built chain program, the five products the algebra may ask for are kept.
+__global__ void __launch_bounds__(TLF_THREADS, 3)
+tl_sweep_fast_kernel(const TlParams p, const TlFastProgram prog, const afs_tube_frame *__restrict__ tubes,
+                     double *__restrict__ out_re, double *__restrict__ out_im) {
+  __shared__ TlFastShared S;
+  const int tube = blockIdx.y;
+  stage_all(p, &prog, tubes + tube, S);
+  const bool pre = S.has_pre != 0;
   // a CTA serves every gridDim.x-th group of TLF_THREADS bins of its area function (staging amortised)
   for (int bin = blockIdx.x * TLF_THREADS + threadIdx.x; bin < p.num_freq; bin += gridDim.x * TLF_THREADS) {
-  const size_t o = (size_t)tube * p.num_freq + bin;
-
-  // Every accessor aliases bin 0 to bin 1 (TlModel.cpp:992,1065,1127,1293).
-  const int fi = bin == 0 ? 1 : bin;
-  const double omega_raw = 2.0 * kPi * p.f0 * (double)fi;
-  const double omega = omega_raw < 0.0001 ? 0.0001 : omega_raw;
-  const double sw = sqrt(omega);
-
-  // wall admittance per unit (length*circumference): 1 / (Bw + j (w Mw - Kw / w)), two wall classes
-  cx g0, g1;
-  {
-    const double iw = 1.0 / omega;
-    const double x0 = omega * 2.1 - 84500.0 * iw, x1 = omega * 0.25 - 84500.0 * iw;
-    const double r0 = 1.0 / (800.0 * 800.0 + x0 * x0), r1 = 1.0 / (1000.0 * 1000.0 + x1 * x1);
-    g0 = cx_make(800.0 * r0, -x0 * r0);   // Tube.cpp:8-10
-    g1 = cx_make(1000.0 * r1, -x1 * r1);  // trachea, Tube.cpp:94-119
-  }
-
-  Prods P;  // generic path only
-  m22 R = m22_unit(), P64 = m22_unit();  // DIRECT: rest of the main chain after the source section; mouth chain
-  cx zout = cx_make(0, 0);               // DIRECT: output impedance of the part in front of the source section
-  if (!DIRECT) {
+    const BinCtx b = bin_ctx(p, bin);
+    Prods P;
     P.section = p.section;
     P.sm1 = m22_unit(); P.s = m22_unit();
     P.p40 = m22_unit(); P.p64 = m22_unit(); P.p83 = m22_unit();
-  }
-
-  m22 K = m22_unit();
-  cx Zs = cx_make(0, 0);  // series impedance not yet multiplied into K
-  cx Za = cx_make(0, 0), Yb = cx_make(1, 0);  // elements of the last section
-  cx fossaY = cx_make(0, 0), srcZa = cx_make(0, 0), srcYb = cx_make(1, 0);
-  cx g = g0;
-  const bool pre = S.has_pre != 0;
-  const unsigned short *pc = S.prog;
-  int op = *pc;
-  for (;;) {
-    while (op < 0x80) {  // hot loop: plain sections
-      if (pre) {
-        const double2 z = S.pre[op];
-        Zs.re += z.x;
-        Zs.im = fma(omega_raw, z.y, Zs.im);
+    Chain c;
+    chain_reset(c);
+    c.Za = cx_make(0, 0); c.Yb = cx_make(1, 0);
+    cx fossaY = cx_make(0, 0), srcZa = cx_make(0, 0), srcYb = cx_make(1, 0);
+    cx g = b.g0;
+    const unsigned short *pc = S.prog;
+    int op = *pc;
+    for (;;) {
+      while (op < 0x80) {  // plain sections
+        chain_section(S, b, pre, g, op, c);
+        op = *++pc;
       }
-      const TlElem e = S.e[op];
-      Za = cx_make(fma(e.rsq, sw, e.rf), omega * e.ls);
-      Yb = cx_make(fma(e.gp, sw, e.lc * g.re), fma(omega, e.cp, e.lc * g.im));
-      Zs = cx_add(Zs, Za);
-      series(K, Zs);
-      shunt(K, Yb);
-      Zs = Za;
-      op = *++pc;
-    }
-    if (op == OP_END) break;
-    const int k = op & OP_K, what = op & ~OP_K;
-    if (what == OP_WALL) {
-      g = k ? g1 : g0;
-    } else if (what == OP_BRANCH) {
-      // end of the fossa chain (:554-561): input impedance A/C of the closed side branch (the pending series
-      // element does not touch A and C)
-      if (k == TRACHEA0 && p.o.piriform_fossa) fossaY = cx_div(K.C, K.A);
-      K = m22_unit();
-      Zs = cx_make(0, 0);
-    } else if (what == OP_SINUS) {  // Helmholtz resonator shunt on the nose chain (TlModel.cpp:659-670, 856-879)
-      const TlElem e = S.e[k];
-      const cx za = cx_make(e.rsq * sw, omega * e.ls), yb = cx_make(e.gp, omega * e.cp);
-      cx q = cx_mul(za, yb);
-      q.re += 1.0;
-      series(K, Zs);
-      Zs = cx_make(0, 0);
-      shunt(K, cx_div(yb, q));
-    } else if (what == OP_STORE) {
-      // matrixProduct[k] (stored BEFORE the series/shunt extras, TlModel.cpp:583) = K * series(Za)
-      m22 F = K;
-      series(F, Zs);
-      if (DIRECT) {
-        if (k == p.section - 1) zout = cx_div(F.B, F.A);  // getOutputImpedance, lung termination 0 (:1060-1105)
-        if (k == p.section) { srcZa = Za; srcYb = Yb; K = m22_unit(); Zs = cx_make(0, 0); F = K; }
-        if (k == PHAR_LAST) R = F;
-        if (k == MOUTH_LAST) P64 = F;
-        if (k == NOSE_LAST) K = F;
-      } else {
+      if (op == OP_END) break;
+      const int k = op & OP_K, what = op & ~OP_K;
+      if (what == OP_WALL) {
+        g = k ? b.g1 : b.g0;
+      } else if (what == OP_BRANCH) {
+        // end of the fossa chain (:554-561): input impedance A/C of the closed side branch (the pending series
+        // element does not touch A and C)
+        if (k == TRACHEA0 && p.o.piriform_fossa) fossaY = cx_div(c.K.C, c.K.A);
+        chain_reset(c);
+      } else if (what == OP_SINUS) {
+        chain_sinus(S, b, k, c);
+      } else if (what == OP_STORE) {  // stored BEFORE the series/shunt extras (TlModel.cpp:583)
+        const m22 F = chain_product(c);
         if (k == p.section - 1) P.sm1 = F;
-        if (k == p.section) { P.s = F; srcZa = Za; srcYb = Yb; }
+        if (k == p.section) { P.s = F; srcZa = c.Za; srcYb = c.Yb; }
         if (k == PHAR_LAST) P.p40 = F;
         if (k == MOUTH_LAST) P.p64 = F;
         if (k == NOSE_LAST) P.p83 = F;
+      } else {  // OP_FOSSA
+        chain_shunt(c, fossaY);
       }
-    } else {  // OP_FOSSA
-      series(K, Zs);
-      Zs = cx_make(0, 0);
-      shunt(K, fossaY);
+      op = *++pc;
     }
-    op = *++pc;
-  }
-
-  const cx mouthRad = radiation_fast(p.o.radiation, omega_raw, S.rad[0]);
-  const cx noseRad = radiation_fast(p.o.radiation, omega_raw, S.rad[1]);
-  cx v = cx_make(0, 0);
-  if (DIRECT) {
-    // TlModel::getFlowSourceTF, trachea..pharynx branch (TlModel.cpp:1312-1368) with R = inverse(P[section]) * P[40]
-    // formed directly; K holds P[83].  Only the bottom rows of the two coupled products are needed.
-    const cx zn = load_through(K, noseRad), zm = load_through(P64, mouthRad);
-    cx zin = cx_add(load_through(R, par(zn, zm)), srcZa);
-    zout = cx_add(zout, srcZa);
-    cx factor = par(cx_rdiv(1.0, srcYb), zout);
-    factor = cx_div(factor, cx_add(zin, factor));
-    cx c = cx_add(R.C, cx_div(R.D, zn));  // bottom row of R * shunt(1/zn), then * P[64]
-    cx kc = cx_add(cx_mul(c, P64.A), cx_mul(R.D, P64.C)), kd = cx_add(cx_mul(c, P64.B), cx_mul(R.D, P64.D));
-    v = cx_div(factor, cx_add(cx_mul(kc, mouthRad), kd));
-    c = cx_add(R.C, cx_div(R.D, zm));
-    kc = cx_add(cx_mul(c, K.A), cx_mul(R.D, K.C)); kd = cx_add(cx_mul(c, K.B), cx_mul(R.D, K.D));
-    v = cx_add(v, cx_div(factor, cx_add(cx_mul(kc, noseRad), kd)));
-  } else {
-    P.mouthRad = mouthRad; P.noseRad = noseRad;
+    P.mouthRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[0]);
+    P.noseRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[1]);
+    cx v = cx_make(0, 0);
     if (p.type == AFS_INPUT_IMPEDANCE) v = input_impedance(P, p.section);
     else if (p.type == AFS_OUTPUT_IMPEDANCE) v = output_impedance(P, p.section);
     else if (p.type == AFS_PRESSURE_SOURCE_TF) v = pressure_source_tf(P, p.section);
     else if (p.type == AFS_FLOW_SOURCE_TF) v = flow_source_tf(P, p.section, srcZa, cx_rdiv(1.0, srcYb));
+    const size_t o = (size_t)tube * p.num_freq + bin;
+    out_re[o] = v.re;
+    out_im[o] = v.im;
   }
-  out_re[o] = v.re;
-  out_im[o] = v.im;
+}
+
+// Direct instantiation: FLOW_SOURCE_TF with the source in the trachea..pharynx chain (sections 0..40) -- the
+// spectrum getFormants and getImpulseResponse ask for.  Straight-line walk of the chains, three live matrices.
+__global__ void __launch_bounds__(TLF_THREADS, 4)
+tl_sweep_fast_direct_kernel(const TlParams p, const afs_tube_frame *__restrict__ tubes, double *__restrict__ out_re,
+                            double *__restrict__ out_im) {
+  __shared__ TlFastShared S;
+  const int tube = blockIdx.y;
+  stage_all(p, nullptr, tubes + tube, S);
+  const bool pre = S.has_pre != 0;
+  const bool fossa = p.o.piriform_fossa != 0;
+  const int s = p.section;
+  for (int bin = blockIdx.x * TLF_THREADS + threadIdx.x; bin < p.num_freq; bin += gridDim.x * TLF_THREADS) {
+    const BinCtx b = bin_ctx(p, bin);
+    Chain c;
+    chain_reset(c);
+    c.Za = cx_make(0, 0); c.Yb = cx_make(1, 0);
+    cx fossaY = cx_make(0, 0);
+    // sections lo..hi of the main chain; splits where the wall class changes (22|23) and, with the fossa, behind its
+    // coupling section 28, whose shunt follows unless the range ends there and `tail` is false
+    auto run = [&](int lo, const int hi_all, const bool tail) {
+      while (lo <= hi_all) {
+        int hi = hi_all;
+        if (lo <= TRACHEA_LAST && hi > TRACHEA_LAST) hi = TRACHEA_LAST;
+        if (fossa && lo <= PHAR0 + FOSSA_COUPLING && hi > PHAR0 + FOSSA_COUPLING) hi = PHAR0 + FOSSA_COUPLING;
+        const cx g = lo <= TRACHEA_LAST ? b.g1 : b.g0;
+        for (int k = lo; k <= hi; k++) chain_section(S, b, pre, g, k, c);
+        if (fossa && hi == PHAR0 + FOSSA_COUPLING && (tail || hi < hi_all)) chain_shunt(c, fossaY);
+        lo = hi + 1;
+      }
+    };
+    if (fossa) {  // side-branch chain first (TlModel.cpp:554-561): its input impedance is A/C (closed end)
+      for (int k = FOSSA0; k <= FOSSA_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
+      fossaY = cx_div(c.K.C, c.K.A);
+      chain_reset(c);
+    }
+    // in front of the source: output impedance of matrixProduct[s-1] (stored before the extras of s-1), lung side
+    // shorted (TlModel.cpp:1060-1105, :518)
+    cx zout = cx_make(0, 0);
+    if (s >= 1) {
+      run(TRACHEA0, s - 1, false);
+      const m22 F = chain_product(c);
+      zout = cx_div(F.B, F.A);
+      if (fossa && s - 1 == PHAR0 + FOSSA_COUPLING) chain_shunt(c, fossaY);
+    }
+    // the source section, then the rest of the chain as its own product R = inverse(P[s]) * P[40]
+    run(s, s, false);
+    const cx srcZa = c.Za, srcYb = c.Yb;
+    chain_reset(c);
+    if (fossa && s == PHAR0 + FOSSA_COUPLING) chain_shunt(c, fossaY);
+    run(s + 1, PHAR_LAST, true);
+    const m22 R = chain_product(c);
+    // mouth
+    chain_reset(c);
+    for (int k = MOUTH0; k <= MOUTH_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
+    const m22 P64 = chain_product(c);
+    // nose with the sinus shunts behind sections 73, 74, 76, 77 (Tube.cpp:35-38)
+    chain_reset(c);
+    if (p.o.paranasal_sinuses) {
+      int k = NOSE0;
+      for (; k <= NOSE0 + 8; k++) chain_section(S, b, pre, b.g0, k, c);
+      chain_sinus(S, b, SINUS0, c);
+      chain_section(S, b, pre, b.g0, k++, c);
+      chain_sinus(S, b, SINUS0 + 1, c);
+      for (; k <= NOSE0 + 11; k++) chain_section(S, b, pre, b.g0, k, c);
+      chain_sinus(S, b, SINUS0 + 2, c);
+      chain_section(S, b, pre, b.g0, k++, c);
+      chain_sinus(S, b, SINUS0 + 3, c);
+      for (; k <= NOSE_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
+    } else {
+      for (int k = NOSE0; k <= NOSE_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
+    }
+    const m22 P83 = chain_product(c);
+
+    // TlModel::getFlowSourceTF, trachea..pharynx branch (TlModel.cpp:1312-1368); only the bottom rows of the two
+    // coupled products are needed
+    const cx mouthRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[0]);
+    const cx noseRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[1]);
+    const cx zn = load_through(P83, noseRad), zm = load_through(P64, mouthRad);
+    const cx zin = cx_add(load_through(R, par(zn, zm)), srcZa);
+    zout = cx_add(zout, srcZa);
+    cx factor = par(cx_rdiv(1.0, srcYb), zout);
+    factor = cx_div(factor, cx_add(zin, factor));
+    cx q = cx_add(R.C, cx_div(R.D, zn));  // bottom row of R * shunt(1/zn), then * P[64]
+    cx kc = cx_add(cx_mul(q, P64.A), cx_mul(R.D, P64.C)), kd = cx_add(cx_mul(q, P64.B), cx_mul(R.D, P64.D));
+    cx v = cx_div(factor, cx_add(cx_mul(kc, mouthRad), kd));
+    q = cx_add(R.C, cx_div(R.D, zm));
+    kc = cx_add(cx_mul(q, P83.A), cx_mul(R.D, P83.C)); kd = cx_add(cx_mul(q, P83.B), cx_mul(R.D, P83.D));
+    v = cx_add(v, cx_div(factor, cx_add(cx_mul(kc, noseRad), kd)));
+    const size_t o = (size_t)tube * p.num_freq + bin;
+    out_re[o] = v.re;
+    out_im[o] = v.im;
   }
 }
 
@@ -370,12 +459,13 @@ cudaError_t launch_tl_sweep_fast(const TlParams &p, const afs_tube_frame *d_tube
                                  cudaStream_t stream) {
   constexpr int BINS_PER_THREAD = 4;
   dim3 grid((p.num_freq + TLF_THREADS * BINS_PER_THREAD - 1) / (TLF_THREADS * BINS_PER_THREAD), p.n_tubes);
-  TlFastProgram prog;
-  build_program(p, prog);
-  if (p.type == AFS_FLOW_SOURCE_TF && p.section >= TRACHEA0 && p.section <= PHAR_LAST)
-    tl_sweep_fast_kernel<true><<<grid, TLF_THREADS, 0, stream>>>(p, prog, d_tubes, d_re, d_im);
-  else
-    tl_sweep_fast_kernel<false><<<grid, TLF_THREADS, 0, stream>>>(p, prog, d_tubes, d_re, d_im);
+  if (p.type == AFS_FLOW_SOURCE_TF && p.section >= TRACHEA0 && p.section <= PHAR_LAST) {
+    tl_sweep_fast_direct_kernel<<<grid, TLF_THREADS, 0, stream>>>(p, d_tubes, d_re, d_im);
+  } else {
+    TlFastProgram prog;
+    build_program(p, prog);
+    tl_sweep_fast_kernel<<<grid, TLF_THREADS, 0, stream>>>(p, prog, d_tubes, d_re, d_im);
+  }
   return cudaGetLastError();
 }
 

@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 W_TDS = 1.0e4  # algorithmic FP64 flop per tract-step
 W_TL = 8.0e3   # algorithmic FP64 flop per (area function, bin)
+W_TL_FAST = 4.4e3  # FP64 flop per (area function, bin) the ladder formulation of K2f executes (84 sections x 43 + sinuses + algebra)
 B_TDS = 4096
 T_SEC = 1.0  # overridden by --utt-seconds (profiling only)
 FS = 44100.0
@@ -356,6 +357,29 @@ def run_ours(args):
     barrier()
     tl_e2e = world * B_TL / max_over_ranks((time.perf_counter() - t0) / 3)
 
+    # same sweep with afs_tl_options.arithmetic = FAST (K2f: ladder recurrences, 1e-9 class instead of bit-identical)
+    fast = afs.tl_options_default(); fast.arithmetic = afs.TL_ARITHMETIC_FAST
+    d_re_f = torch.empty_like(d_re); d_im_f = torch.empty_like(d_re)
+
+    def tl_fast_dev():
+        ctx.tl_sweep_device(d_ftl, B_TL, F0_TL, K_TL, d_re_f, d_im_f, stream, opts=fast)
+
+    tlf_ms = timed(tl_fast_dev, tl_steps, 3) / tl_steps
+    tlf_tflops = W_TL_FAST * B_TL * K_TL / (tlf_ms * 1e-3) / 1e12
+    h_ref, h_fast = torch.complex(d_re, d_im), torch.complex(d_re_f, d_im_f)
+    rel = ((h_fast - h_ref).abs() / h_ref.abs()).flatten()
+    tlf_err = {"max_rel": float(rel.max()), "p999_rel": float(torch.quantile(rel[: 1 << 23], 0.999)),
+               "against": "the bit-identical kernel's output of this run; see tests/test_tl_gpu.py::"
+                          "test_fast_arithmetic_against_extended_precision for which of the two is nearer to the formulas"}
+    del h_ref, h_fast, rel
+    ctx.tl_sweep(f_tl, F0_TL, K_TL, opts=fast)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.tl_sweep(f_tl, F0_TL, K_TL, opts=fast)
+    barrier()
+    tlf_e2e = world * B_TL / max_over_ranks((time.perf_counter() - t0) / 3)
+
     # ---------------- rasteriser: parameter sets -> frames on the device --------------
     B_RA = 65536
     rng = np.random.default_rng(20260004 + rank)
@@ -437,7 +461,14 @@ def run_ours(args):
                "roofline": {"bound": "fp64", "achieved": tl_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                             "frac": tl_tflops / fp64_peak, "kernel": "tl_sweep_kernel", "flop_per_bin": W_TL,
                             "hbm_gbs_algorithmic": B_TL * K_TL * 16 / (tl_ms * 1e-3) / 1e9},
-               "cpu_baseline": tl_cpu},
+               "cpu_baseline": tl_cpu,
+               "fast_arithmetic": {"value": world * B_TL / (tlf_ms * 1e-3), "unit": "spectra/s", "ms_per_step": tlf_ms,
+                                   "e2e": {"value": tlf_e2e, "unit": "spectra/s"},
+                                   "roofline": {"bound": "fp64", "achieved": tlf_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                                                "frac": tlf_tflops / fp64_peak, "kernel": "tl_sweep_fast_kernel",
+                                                "flop_per_bin": W_TL_FAST,
+                                                "note": "flops the ladder formulation executes (DESIGN.md K2f), not the 8.0e3 of the reference-like formulation"},
+                                   "error": tlf_err}},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -229,6 +229,24 @@ int afs_tl_formants(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes,
                     int spectrum_length, int max_formants, double *formant_hz,
                     double *bandwidth_hz, int32_t *num_formants, int32_t *flags);
 
+/*
+ * Replaces TlModel::getImpulseResponse (TlModel.cpp:90-111) for a batch of tubes: the flow-source transfer
+ * function at FIRST_PHARYNX_SECTION times the radiation characteristic on the grid f0 = sampling_rate_hz / N,
+ * N = 1 << length_exponent (bins as in TlModel::getSpectrum, TlModel.cpp:125-148, without the MAX_NUM_FREQ
+ * cap), negative frequencies mirrored (Dsp.cpp:128-138), inverse FFT (complexIFFT, Dsp.cpp:228-326, same
+ * radix-2 butterflies and the same recursively multiplied twiddle factors) and the rising half-cosine window
+ * of getImpulseResponseWindow (TlModel.cpp:70-80).  impulse_response [n_tubes][N].  4 <= length_exponent <= 11.
+ * With REFERENCE arithmetic the result is bit-identical to the reference (reference call:
+ * getImpulseResponse(&signal, 9) at 22050 Hz, Synthesizer.cpp:719-724).
+ */
+int afs_tl_impulse_response(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes,
+                            const afs_tube_frame *tubes, double sampling_rate_hz,
+                            int length_exponent, double *impulse_response);
+/* d_tubes / d_impulse_response are device pointers; asynchronous on `stream`. */
+int afs_tl_impulse_response_device(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes,
+                                   const afs_tube_frame *d_tubes, double sampling_rate_hz,
+                                   int length_exponent, double *d_impulse_response, void *stream);
+
 /* ---- TdsModel + TriangularGlottis + driver loop ---------------------------- */
 /*
  * Replaces, for a batch of independent utterances ("tracts"), the per-sample

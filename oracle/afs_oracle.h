@@ -21,6 +21,9 @@ int orc_tl_formants(const afs_tl_options *opts, int n_tubes, const afs_tube_fram
                     double sampling_rate_hz, int spectrum_length, int max_formants,
                     double *freq, double *bw, int32_t *num, int32_t *flags);
 
+int orc_tl_impulse_response(const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
+                            double sampling_rate_hz, int length_exponent, double *out);
+
 void orc_chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double *b);
 
 int orc_tds_synthesize(const afs_tds_options *opts, int n_tracts, int n_frames,

@@ -123,6 +123,13 @@ class Ref:
                                       max_bins, _ptr(re), _ptr(im), threads)
         return re[:, :nf].copy(), im[:, :nf].copy()
 
+    def tl_impulse_response(self, frames, length_exponent=9, opts=None):
+        opts = opts or tl_options_default()
+        n = len(frames)
+        out = np.zeros((n, 1 << length_exponent))
+        self.lib.ref_tl_impulse_response(C.byref(opts), n, _ptr(np.ascontiguousarray(frames)), length_exponent, _ptr(out))
+        return out
+
     def tl_formants(self, frames, opts=None, max_formants=8):
         opts = opts or tl_options_default()
         n = len(frames)
@@ -198,6 +205,15 @@ class Oracle:
                                       C.c_double(f0_hz), num_freq, _ptr(re), _ptr(im))
         assert rc == 0, rc
         return re, im
+
+    def tl_impulse_response(self, frames, sampling_rate=22050.0, length_exponent=9, opts=None):
+        opts = opts or tl_options_default()
+        n = len(frames)
+        out = np.zeros((n, 1 << length_exponent))
+        rc = self.lib.orc_tl_impulse_response(C.byref(opts), n, _ptr(np.ascontiguousarray(frames)),
+                                              C.c_double(sampling_rate), length_exponent, _ptr(out))
+        assert rc == 0, rc
+        return out
 
     def tl_formants(self, frames, opts=None, sampling_rate=22050.0, spectrum_length=2048, max_formants=8):
         opts = opts or tl_options_default()

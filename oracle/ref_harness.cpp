@@ -117,6 +117,21 @@ int ref_tl_spectrum(const afs_tl_options *opts, int n_tubes, const afs_tube_fram
   return nf[0];
 }
 
+// TlModel::getImpulseResponse (TlModel.cpp:90-111) on a fresh TlModel per tube; out[n][1 << length_exponent].
+void ref_tl_impulse_response(const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
+                             int length_exponent, double *out) {
+  const int N = 1 << length_exponent;
+  for (int b = 0; b < n_tubes; b++) {
+    TlModel *tl = new TlModel();
+    set_tl_options(tl, opts);
+    frame_to_tube(&tubes[b], &tl->tube);
+    Signal h;
+    tl->getImpulseResponse(&h, length_exponent);
+    for (int i = 0; i < N; i++) out[(size_t)b * N + i] = h.x[i];
+    delete tl;
+  }
+}
+
 // TlModel::getFormants on a fresh TlModel per tube.
 void ref_tl_formants(const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
                      int max_formants, double *freq, double *bw, int32_t *num, int32_t *flags) {

@@ -66,6 +66,17 @@ def test_formants_bit_identical_to_golden(oracle, shapes):
     np.testing.assert_allclose(f[0, :3], [705.947857, 1246.117959, 2679.313681], atol=1e-6)
 
 
+def test_impulse_response_bit_identical_to_golden(oracle, shapes):
+    """TlModel::getImpulseResponse (spectrum product, mirror, complexIFFT with recursive twiddles, window)."""
+    from oracle.pyoracle import tl_options_default
+    g = load_golden("tl_impulse.npz")
+    fr = shapes["frames"]
+    assert np.array_equal(oracle.tl_impulse_response(fr[g["sel9"]], 22050.0, 9), g["h9"])
+    assert np.array_equal(oracle.tl_impulse_response(fr[g["sel11"]], 22050.0, 11), g["h11"])
+    o = tl_options_default(); o.piriform_fossa = 1; o.radiation = 1
+    assert np.array_equal(oracle.tl_impulse_response(fr[g["sel9"][:4]], 22050.0, 9, opts=o), g["h9_opts"])
+
+
 def test_tl_live_reference_random_tubes(oracle):
     if not have_ref():
         pytest.skip("compiled reference not available")

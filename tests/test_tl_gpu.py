@@ -212,6 +212,18 @@ def test_fast_arithmetic_against_extended_precision(ctx, oracle, shapes):
         worst_ref, worst_fast = max(worst_ref, e_ref), max(worst_fast, e_fast)
         assert e_fast <= 1e-11, (i, e_fast)
     assert worst_fast < worst_ref
+    # piriform fossa on, source behind its coupling section: near the side-branch resonance (~9.2 kHz) the
+    # reference arithmetic is 1e-5 away from its own formulas, the fast kernel 1e-8
+    a, b = _fast_opts(piriform_fossa=1)
+    fr = random_frames(64, seed=7)[[20, 23, 26, 50]]
+    re, im = ctx.tl_sweep(fr, F0_938, 938, section=33, opts=a)
+    rf, jf = ctx.tl_sweep(fr, F0_938, 938, section=33, opts=b)
+    bins = np.arange(938)
+    for i in range(len(fr)):
+        t = truth_flow_tf(oracle.expand_frame(fr[i:i + 1]), F0_938, bins, section=33, fossa=True)
+        e_ref = float(np.max(np.abs((re[i] + 1j * im[i]) - t) / np.abs(t)))
+        e_fast = float(np.max(np.abs((rf[i] + 1j * jf[i]) - t) / np.abs(t)))
+        assert e_fast <= 1e-7 and e_fast < e_ref, (i, e_fast, e_ref)
 
 
 def test_fast_arithmetic_types_sections_options(ctx, shapes):
@@ -221,10 +233,15 @@ def test_fast_arithmetic_types_sections_options(ctx, shapes):
     1e-7 of the spectrum's scale."""
     n = len(shapes["names"])
     fr = np.concatenate([shapes["frames"][[0, 9, n + 30]], random_frames(13, seed=7)])
-    variants = (dict(), dict(piriform_fossa=1, inner_length_corrections=1, heat_conduction=1, hagen_resistance=1),
-                dict(soft_walls=0, paranasal_sinuses=0, radiation=1), dict(radiation=2, lung_pressure_dPa=8000.0),
-                dict(radiation=0, boundary_layer=0, static_pressure_drops=0))
-    for kw in variants:
+    # pointwise bar of the flow-source TF per variant: where the reference arithmetic forms inverse(P[section]) *
+    # P[40] across a resonating side branch (piriform fossa) or without any radiation loss, ITS rounding noise
+    # reaches 1e-5 (measured against extended precision, next-but-one test and DESIGN.md) -- the bar follows it
+    variants = ((dict(), 1e-7, 2e-8),
+                (dict(piriform_fossa=1, inner_length_corrections=1, heat_conduction=1, hagen_resistance=1), 1e-5, 1e-4),
+                (dict(soft_walls=0, paranasal_sinuses=0, radiation=1), 1e-7, 2e-8),
+                (dict(radiation=2, lung_pressure_dPa=8000.0), 1e-7, 2e-8),
+                (dict(radiation=0, boundary_layer=0, static_pressure_drops=0), 1e-6, 1e-5))
+    for kw, of_scale, pointwise in variants:
         a, b = _fast_opts(**kw)
         for t, sec in ((2, 25), (2, 0), (2, 24), (2, 33), (2, 40), (2, 41), (2, 50), (2, 64), (2, 65), (3, 0), (3, 30),
                        (3, 41), (3, -1), (0, 0), (0, 30), (0, 70), (1, 30), (1, 64), (1, 83)):
@@ -233,9 +250,9 @@ def test_fast_arithmetic_types_sections_options(ctx, shapes):
             h1, h2 = r1 + 1j * i1, r2 + 1j * i2
             assert np.all(np.isfinite(r2)) and np.all(np.isfinite(i2)), (kw, t, sec)
             scale = np.max(np.abs(h1), axis=1, keepdims=True)
-            assert np.max(np.abs(h2 - h1) / scale) <= 1e-7, (kw, t, sec)
+            assert np.max(np.abs(h2 - h1) / scale) <= of_scale, (kw, t, sec)
             if t == 2:
-                assert np.max(np.abs(h2 - h1) / np.abs(h1)) <= 1e-8, (kw, t, sec)
+                assert np.max(np.abs(h2 - h1) / np.abs(h1)) <= pointwise, (kw, t, sec)
     # modes the fast kernel does not serve are routed to the reference arithmetic: identical results
     a, b = _fast_opts(lumped_elements=0)
     assert np.array_equal(ctx.tl_sweep(fr, F0_938, 938, opts=a)[0], ctx.tl_sweep(fr, F0_938, 938, opts=b)[0])
@@ -251,3 +268,24 @@ def test_fast_arithmetic_formants(ctx, shapes):
     f2, bw2, n2, fl2 = ctx.tl_formants(fr, opts=b)
     assert np.array_equal(n1, n2) and np.array_equal(fl1, fl2)
     assert np.max(np.abs(f2 - f1)) <= 1e-5 and np.max(np.abs(bw2 - bw1)) <= 1e-4  # Hz
+
+
+# ---- K5 impulse response (TlModel::getImpulseResponse) ------------------------------------------------------
+def test_impulse_response_bit_identical(ctx, oracle, shapes):
+    import areafunctionsynthesis_b200 as afs
+    g = load_golden("tl_impulse.npz")
+    fr = shapes["frames"]
+    assert np.array_equal(ctx.tl_impulse_response(fr[g["sel9"]], 22050.0, 9), g["h9"])
+    assert np.array_equal(ctx.tl_impulse_response(fr[g["sel11"]], 22050.0, 11), g["h11"])
+    o = afs.tl_options_default(); o.piriform_fossa = 1; o.radiation = 1
+    assert np.array_equal(ctx.tl_impulse_response(fr[g["sel9"][:4]], 22050.0, 9, opts=o), g["h9_opts"])
+    # random area functions and other lengths / rates against the oracle
+    rf = random_frames(64, seed=11)
+    for sr, ex in ((22050.0, 9), (44100.0, 10), (22050.0, 4), (16000.0, 8)):
+        assert np.array_equal(ctx.tl_impulse_response(rf, sr, ex), oracle.tl_impulse_response(rf, sr, ex)), (sr, ex)
+    # fast arithmetic: same response within 1e-9 of its scale
+    o = afs.tl_options_default(); o.arithmetic = afs.TL_ARITHMETIC_FAST
+    h, hf = ctx.tl_impulse_response(rf, 22050.0, 9), ctx.tl_impulse_response(rf, 22050.0, 9, opts=o)
+    assert np.max(np.abs(hf - h)) <= 1e-9 * np.max(np.abs(h))
+    with pytest.raises(afs.AfsError):
+        ctx.tl_impulse_response(rf, 22050.0, 12)

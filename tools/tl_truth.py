@@ -18,7 +18,7 @@ SINUS_AFTER = {65 + 8: 89, 65 + 9: 90, 65 + 11: 91, 65 + 12: 92}
 SINUS_VOL = [LD("11.3"), LD("6.8"), LD("33.0"), LD("6.2")]
 
 
-def truth_flow_tf(sections, f0_hz, bins, section=25):
+def truth_flow_tf(sections, f0_hz, bins, section=25, fossa=False):
     """sections: oracle expand_frame output (doubles, exact inputs); bins: integer array."""
     v = sections["v"].astype(LD)
     area = np.maximum(v[:, 1], MIN_AREA); length = v[:, 2]; volume = v[:, 3]
@@ -58,11 +58,19 @@ def truth_flow_tf(sections, f0_hz, bins, section=25):
 
     P = {}
     unit = (one, zero, zero, one)
+    fossa_zin = None
+    if fossa:  # TlModel.cpp:554-561
+        K = unit
+        for k in range(84, 89):
+            K = mul(K, smat(k))
+        fossa_zin = K[0] / K[2]
     for first, last in ((0, 40), (41, 64), (65, 83)):
         K = unit
         for k in range(first, last + 1):
             K = mul(K, smat(k))
             P[k] = K
+            if fossa and k == 25 + 3:  # Tube::FOSSA_COUPLING_SECTION (TlModel.cpp:586-590)
+                K = mul(K, (one, zero, 1 / fossa_zin, one))
             if k in SINUS_AFTER:
                 M = smat(SINUS_AFTER[k])
                 K = mul(K, (one, zero, 1 / (M[0] / M[2]), one))
@@ -100,10 +108,14 @@ if __name__ == "__main__":
     frames = d["frames"].view(FRAME_DTYPE).reshape(-1)
     f0 = float(d["f0"])
     e_ref, e_fast = [], []
+    section = int(d["section"]) if "section" in d else 25
+    fossa = bool(d["fossa"]) if "fossa" in d else False
+    from oracle.pyoracle import tl_options_default
+    oo = tl_options_default(); oo.piriform_fossa = int(fossa)
     for i, (fr, b) in enumerate(zip(frames, d["bins"])):
         bins = np.array([b])
-        t = truth_flow_tf(orc.expand_frame(fr.reshape(1)), f0, bins)[0]
-        ro, io = orc.tl_spectrum(fr.reshape(1), f0, int(b) + 1)
+        t = truth_flow_tf(orc.expand_frame(fr.reshape(1)), f0, bins, section=section, fossa=fossa)[0]
+        ro, io = orc.tl_spectrum(fr.reshape(1), f0, int(b) + 1, opts=oo, section=section)
         ref = CLD(ro[0, b]) + 1j * CLD(io[0, b])
         fast = CLD(d["fast_re"][i]) + 1j * CLD(d["fast_im"][i])
         gref = CLD(d["ref_re"][i]) + 1j * CLD(d["ref_im"][i])
