@@ -78,6 +78,9 @@ def load_library():
     lib.afs_tl_sweep.argtypes = [vp, vp, i32, vp, i32, i32, dbl, i32, vp, vp]
     lib.afs_tl_sweep_device.argtypes = [vp, vp, i32, vp, i32, i32, dbl, i32, vp, vp, vp]
     lib.afs_tl_formants.argtypes = [vp, vp, i32, vp, dbl, i32, i32, vp, vp, vp, vp]
+    lib.afs_optimize_formants_vowel.argtypes = [vp, vp, i32, vp, vp, dbl, dbl, vp, i32, dbl, i32, vp, vp, vp, vp, vp]
+    lib.afs_synthesize_vowels_lf.argtypes = [vp, vp, i32, vp, vp, i32, dbl, vp, vp]
+    lib.afs_lf_vowel_length.argtypes = [i32, dbl]
     lib.afs_tl_impulse_response.argtypes = [vp, vp, i32, vp, dbl, i32, vp]
     lib.afs_tl_impulse_response_device.argtypes = [vp, vp, i32, vp, dbl, i32, vp, vp]
     lib.afs_tds_synthesize.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp]
@@ -205,6 +208,37 @@ class Context:
         _check(self.lib, self.lib.afs_tl_sweep_device(self.h, C.byref(opts), int(n), _ptr(d_frames),
                                                       int(spectrum_type), int(section), float(f0_hz), int(num_freq),
                                                       _ptr(d_re), _ptr(d_im), C.c_void_p(stream)), self.h)
+
+    def optimize_formants_vowel(self, params, targets_hz, max_param_change_cm=1.0, min_advised_area_cm2=0.0,
+                                param_fixed=None, max_runs=100, sampling_rate_hz=22050.0, spectrum_length=2048, opts=None):
+        """Data::optimizeFormantsVowel for a batch of problems: params [n, 16], targets_hz [n, 3].
+        Returns dict(params, initial_error, final_error, runs, formants_hz, trace[n, max_runs, 2])."""
+        opts = opts or tl_options_default()
+        p = np.array(params, dtype=np.float64).reshape(-1, 16).copy()
+        n = len(p)
+        t = np.ascontiguousarray(targets_hz, dtype=np.float64).reshape(n, 3)
+        fx = None if param_fixed is None else np.ascontiguousarray(param_fixed, dtype=np.int32)
+        e0 = np.zeros(n); e1 = np.zeros(n); runs = np.zeros(n, dtype=np.int32); fo = np.zeros((n, 3))
+        trace = np.full((n, int(max_runs), 2), np.nan)
+        _check(self.lib, self.lib.afs_optimize_formants_vowel(
+            self.h, C.byref(opts), n, _ptr(p), _ptr(t), float(max_param_change_cm), float(min_advised_area_cm2), _ptr(fx),
+            int(max_runs), float(sampling_rate_hz), int(spectrum_length), _ptr(e0), _ptr(e1), _ptr(runs), _ptr(fo),
+            _ptr(trace)), self.h)
+        return dict(params=p, initial_error=e0, final_error=e1, runs=runs, formants_hz=fo, trace=trace)
+
+    def synthesize_vowels_lf(self, frames, lf_params, is_long=True, sampling_rate_hz=22050.0, opts=None, want_pressure=False):
+        """Synthesizer::synthesizeVowelLf for a batch: lf_params [n, 5] = AMP, F0, OQ, SQ, TL.  Returns int16 [n, length]
+        (and the unfiltered pressure when asked)."""
+        opts = opts or tl_options_default()
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        n = len(frames)
+        lf = np.ascontiguousarray(lf_params, dtype=np.float64).reshape(n, 5)
+        length = int(self.lib.afs_lf_vowel_length(int(bool(is_long)), float(sampling_rate_hz)))
+        audio = np.zeros((n, length), dtype=np.int16)
+        pr = np.zeros((n, length)) if want_pressure else None
+        _check(self.lib, self.lib.afs_synthesize_vowels_lf(self.h, C.byref(opts), n, _ptr(frames), _ptr(lf), int(bool(is_long)),
+                                                           float(sampling_rate_hz), _ptr(audio), _ptr(pr)), self.h)
+        return (audio, pr) if want_pressure else audio
 
     def tl_impulse_response(self, frames, sampling_rate_hz=22050.0, length_exponent=9, opts=None):
         """TlModel::getImpulseResponse for a batch: returns [n, 2**length_exponent]."""

@@ -367,6 +367,262 @@ int afs_tl_impulse_response(afs_ctx *ctx, const afs_tl_options *opts, int n_tube
 }
 
 // ---------------------------------------------------------------------------
+// Formant optimiser: Data::optimizeFormantsVowel, batched
+// ---------------------------------------------------------------------------
+namespace {
+enum { LLAR, ALAR, POWLAR, XP, AP, POWP, XC, AC, POWC, XA, AA, POWA, XIN, AIN, LVT, ALIP };  // OneDimAreaFunction.h:34-43
+
+// Data::getFormantError (Data.cpp:106-135)
+double formant_error(const double *c, const double *t) {
+  double e;
+  if (t[2] > 1.0) {
+    e = (1.0 - c[0] / t[0]) * (1.0 - c[0] / t[0]) + (1.0 - c[1] / t[1]) * (1.0 - c[1] / t[1]) +
+        (1.0 - c[2] / t[2]) * (1.0 - c[2] / t[2]);
+    e /= 3.0;
+  } else {
+    e = (1.0 - c[0] / t[0]) * (1.0 - c[0] / t[0]) + (1.0 - c[1] / t[1]) * (1.0 - c[1] / t[1]);
+    e /= 2.0;
+  }
+  e = sqrt(e);
+  return e * 100.0;
+}
+
+// Data::getVowelFormants (Data.cpp:149-196) for a batch of parameter sets, everything on the device: F [n][3]
+// (zeros when fewer than three formants were found) and the minimum area of tube sections 25..39 (sic: the loop
+// of the reference runs from FIRST_PHARYNX_SECTION to NUM_PHARYNX_MOUTH_SECTIONS - 1).
+int vowel_formants(afs_ctx *ctx, const afs_tl_options *opts, int n, const double *params, double sr, int N,
+                   std::vector<afs_tube_frame> &frames, double *F, double *min_area) {
+  const double f0 = sr / (double)N;
+  int nf = (int)(10100.0 / f0);
+  if (nf >= N / 2) nf = N / 2 - 1;
+  if (nf < 2) return AFS_ERR_BAD_ARGUMENT;
+  int rc;
+  void *d_tubes, *d_re, *d_im, *d_f, *d_b, *d_n, *d_fl, *d_p;
+  const size_t nb = (size_t)n * nf * sizeof(double), fb = (size_t)n * 3 * sizeof(double);
+  if ((rc = scratch(ctx, 0, (size_t)n * sizeof(afs_tube_frame), &d_tubes))) return rc;
+  if ((rc = scratch(ctx, 1, nb, &d_re))) return rc;
+  if ((rc = scratch(ctx, 2, nb, &d_im))) return rc;
+  if ((rc = scratch(ctx, 3, fb, &d_f))) return rc;
+  if ((rc = scratch(ctx, 4, fb, &d_b))) return rc;
+  if ((rc = scratch(ctx, 5, (size_t)n * sizeof(int32_t), &d_n))) return rc;
+  if ((rc = scratch(ctx, 6, (size_t)n * sizeof(int32_t), &d_fl))) return rc;
+  if ((rc = scratch(ctx, 7, (size_t)n * 16 * sizeof(double), &d_p))) return rc;
+  afs_tube_frame tpl;  // fresh Tube + setGlottisArea(0.0) (Data.cpp:165-172)
+  afs_tube_frame_default(&tpl);
+  tpl.glottis_area_cm2[0] = tpl.glottis_area_cm2[1] = 0.0;
+  frames.assign((size_t)n, tpl);
+  CU(cudaMemcpyAsync(d_tubes, frames.data(), (size_t)n * sizeof(afs_tube_frame), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_p, params, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_area_function_raster(n, (const double *)d_p, (afs_tube_frame *)d_tubes, ctx->stream));
+  ctx->launches++;
+  rc = afs_tl_sweep_device(ctx, opts, n, (const afs_tube_frame *)d_tubes, AFS_FLOW_SOURCE_TF, AFS_FIRST_PHARYNX_SECTION,
+                           f0, nf, (double *)d_re, (double *)d_im, ctx->stream);
+  if (rc) return rc;
+  FormantParams fp;
+  fp.n_tubes = n; fp.num_freq = nf; fp.max_formants = 3; fp.f0 = f0;
+  CU(launch_formant_pick(fp, (const afs_tube_frame *)d_tubes, (const double *)d_re, (const double *)d_im, (double *)d_f,
+                         (double *)d_b, (int32_t *)d_n, (int32_t *)d_fl, ctx->stream));
+  ctx->launches++;
+  std::vector<int32_t> num((size_t)n);
+  CU(cudaMemcpyAsync(F, d_f, fb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(num.data(), d_n, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(frames.data(), d_tubes, (size_t)n * sizeof(afs_tube_frame), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; i++) {
+    if (num[i] < 3) F[3 * i] = F[3 * i + 1] = F[3 * i + 2] = 0.0;
+    double m = 10000.0;
+    for (int k = 0; k < AFS_NUM_PHARYNX_SECTIONS - 1; k++) if (frames[i].area_cm2[k] < m) m = frames[i].area_cm2[k];
+    min_area[i] = m;
+  }
+  return AFS_OK;
+}
+
+struct OptProblem {
+  double cur[16], step[16];
+  int taken[16];
+  bool active;
+  int runs;
+};
+struct OptCand { int problem, param; double change; };  // param -1: the current configuration
+}  // namespace
+
+int afs_optimize_formants_vowel(afs_ctx *ctx, const afs_tl_options *opts, int n_problems, double *params,
+                                const double *target_hz, double max_param_change_cm, double min_advised_area_cm2,
+                                const int32_t *param_fixed, int max_runs, double sampling_rate_hz, int spectrum_length,
+                                double *initial_error, double *final_error, int32_t *runs, double *formants_hz,
+                                double *trace) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (n_problems < 0 || max_runs < 1 || spectrum_length < 4 || !(sampling_rate_hz > 0) || !opts) return AFS_ERR_BAD_ARGUMENT;
+  if (n_problems == 0) return AFS_OK;
+  if (!params || !target_hz) return AFS_ERR_BAD_ARGUMENT;
+  const double STEP = 0.05;  // Data.cpp:258
+  int max_steps = (int)((max_param_change_cm / STEP) + 0.5);
+  if (max_steps < 1) max_steps = 1;
+  if (max_steps > 40) max_steps = 40;
+  std::vector<OptProblem> pr((size_t)n_problems);
+  for (int b = 0; b < n_problems; b++) {
+    OptProblem &q = pr[b];
+    memcpy(q.cur, params + 16 * (size_t)b, sizeof q.cur);
+    for (int i = 0; i < 16; i++) {
+      const bool pos = i == LLAR || i == XP || i == XC || i == XA || i == XIN || i == LVT;
+      const bool pw = i == POWLAR || i == POWP || i == POWC || i == POWA;
+      q.step[i] = pos ? STEP : pw ? 0.1 : STEP * STEP;  // Data.cpp:277-295
+      if (param_fixed && param_fixed[i]) q.step[i] = 0.0;
+      q.taken[i] = 0;
+    }
+    q.active = true;
+    q.runs = 0;
+  }
+  std::vector<OptCand> cand;
+  std::vector<double> cp, F, ma;
+  std::vector<afs_tube_frame> frames;
+  // Hidden state of the reference: TlModel::getFormants ends with getMeanFlow(8000.0) (TlModel.cpp:427), which
+  // leaves lungPressure_dPa = 8000 in the model (:253-260).  Data::tlModel is one persistent
+  // object, so every evaluation AFTER the first one runs with 8000 dPa (static pressure drops, :526-541); the
+  // first one -- the initial error, Data.cpp:224-246 -- sees the state the model was handed over in (opts).
+  afs_tl_options o_rest = *opts;
+  o_rest.lung_pressure_dPa = 8000.0;
+  {
+    F.resize((size_t)n_problems * 3); ma.resize((size_t)n_problems);
+    if ((rc = vowel_formants(ctx, opts, n_problems, params, sampling_rate_hz, spectrum_length, frames, F.data(), ma.data()))) return rc;
+    if (initial_error)
+      for (int b = 0; b < n_problems; b++) initial_error[b] = formant_error(&F[3 * (size_t)b], target_hz + 3 * (size_t)b);
+  }
+  opts = &o_rest;
+  for (int run = 0; run < max_runs; run++) {
+    cand.clear(); cp.clear();
+    for (int b = 0; b < n_problems; b++) {
+      OptProblem &q = pr[b];
+      if (!q.active) continue;
+      cand.push_back({b, -1, 0.0});
+      cp.insert(cp.end(), q.cur, q.cur + 16);
+      double c[16];
+      memcpy(c, q.cur, sizeof c);
+      for (int i = 0; i < 16; i++) {  // Data.cpp:337-431: the neighbours, generated in the reference's order
+        const double v = c[i];
+        if (!(q.step[i] > 0.0)) continue;
+        if (q.taken[i] < max_steps) {
+          c[i] = v + q.step[i];
+          const int up = i == XP ? XC : i == XC ? XA : i == XA ? XIN : i == XIN ? LVT : -1;
+          if (up >= 0 && c[i] > c[up]) { q.step[i] = c[up] - c[i]; c[i] = c[up]; }
+          cand.push_back({b, i, q.step[i]});
+          cp.insert(cp.end(), c, c + 16);
+        }
+        if (q.taken[i] > -max_steps) {
+          c[i] = v - q.step[i];
+          const int dn = i == XP ? LLAR : i == XC ? XP : i == XA ? XC : i == XIN ? XA : i == LVT ? XIN : -1;
+          if (dn >= 0 && c[i] < c[dn]) { q.step[i] = c[dn] - c[i]; c[i] = c[dn]; }
+          cand.push_back({b, i, -q.step[i]});
+          cp.insert(cp.end(), c, c + 16);
+        }
+        c[i] = v;
+      }
+    }
+    if (cand.empty()) break;
+    const int nc = (int)cand.size();
+    F.resize((size_t)nc * 3); ma.resize((size_t)nc);
+    if ((rc = vowel_formants(ctx, opts, nc, cp.data(), sampling_rate_hz, spectrum_length, frames, F.data(), ma.data()))) return rc;
+    for (int k = 0; k < nc;) {
+      const int b = cand[k].problem;
+      OptProblem &q = pr[b];
+      const double *t = target_hz + 3 * (size_t)b;
+      const double curr = formant_error(&F[3 * (size_t)k], t);
+      double best = curr, best_change = 0.0;
+      int best_param = -1;
+      for (k++; k < nc && cand[k].problem == b; k++) {
+        if (ma[k] >= min_advised_area_cm2) {
+          const double e = formant_error(&F[3 * (size_t)k], t);
+          if (e < best) { best = e; best_param = cand[k].param; best_change = cand[k].change; }
+        }
+      }
+      bool changed = false;
+      if (best_param != -1 && best < curr) {
+        q.cur[best_param] += best_change;
+        if (best_change > 0.0) q.taken[best_param]++; else q.taken[best_param]--;
+        changed = true;
+      }
+      if (trace) {
+        trace[((size_t)b * max_runs + run) * 2] = changed ? (double)best_param : -1.0;
+        trace[((size_t)b * max_runs + run) * 2 + 1] = best;
+      }
+      q.runs = run + 1;
+      q.active = changed;
+    }
+  }
+  // final formants and error (Data.cpp:476-482)
+  cp.clear();
+  for (int b = 0; b < n_problems; b++) cp.insert(cp.end(), pr[b].cur, pr[b].cur + 16);
+  F.resize((size_t)n_problems * 3); ma.resize((size_t)n_problems);
+  if ((rc = vowel_formants(ctx, opts, n_problems, cp.data(), sampling_rate_hz, spectrum_length, frames, F.data(), ma.data()))) return rc;
+  for (int b = 0; b < n_problems; b++) {
+    memcpy(params + 16 * (size_t)b, pr[b].cur, sizeof pr[b].cur);
+    if (final_error) final_error[b] = formant_error(&F[3 * (size_t)b], target_hz + 3 * (size_t)b);
+    if (runs) runs[b] = pr[b].runs;
+    if (formants_hz) memcpy(formants_hz + 3 * (size_t)b, &F[3 * (size_t)b], 3 * sizeof(double));
+  }
+  return AFS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// LF vowel synthesis: Synthesizer::synthesizeVowelLf, batched
+// ---------------------------------------------------------------------------
+void afs_lf_pulse_default(afs_lf_pulse *p) {  // LfPulse::resetParams (LfPulse.cpp:24-31)
+  if (!p) return;
+  p->amp_cm3_s = 300.0; p->f0_hz = 120.0; p->oq = 0.5; p->sq = 3.0; p->tl = 0.02;
+}
+
+int afs_lf_vowel_length(int is_long_vowel, double sampling_rate_hz) { return lf_vowel_length(is_long_vowel, sampling_rate_hz); }
+
+int afs_synthesize_vowels_lf(afs_ctx *ctx, const afs_tl_options *opts, int n, const afs_tube_frame *tubes,
+                             const afs_lf_pulse *pulses, int is_long_vowel, double sampling_rate_hz, int16_t *audio,
+                             double *pressure) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (n < 0 || !(sampling_rate_hz > 16000.0) || !opts) return AFS_ERR_BAD_ARGUMENT;  // 8 kHz low-pass below Nyquist
+  if (n == 0) return AFS_OK;
+  if (!tubes || !pulses || !audio) return AFS_ERR_BAD_ARGUMENT;
+  const int length = lf_vowel_length(is_long_vowel, sampling_rate_hz);
+  if (length < 1) return AFS_ERR_BAD_ARGUMENT;
+  // host: pulse trains, filter coefficients, scale factors
+  std::vector<double> flow((size_t)n * length), scale((size_t)n), ab(14, 0.0);
+  for (int v = 0; v < n; v++) {
+    if (!(pulses[v].f0_hz > 0.0) || !(pulses[v].oq > 0.0)) return AFS_ERR_BAD_ARGUMENT;
+    if (lf_vowel_flow(&pulses[v], is_long_vowel, sampling_rate_hz, flow.data() + (size_t)v * length)) return AFS_ERR_BAD_ARGUMENT;
+    scale[v] = 80.0 / pulses[v].f0_hz;
+  }
+  {
+    double a[33], b[33];
+    chebyshev_lowpass(8000.0 / sampling_rate_hz, 6, a, b);  // SYNTHETIC_SPEECH_BANDWIDTH_HZ (Constants.h:28)
+    for (int i = 0; i < 7; i++) { ab[i] = a[i]; ab[7 + i] = b[i]; }
+  }
+  void *d_tubes, *d_h, *d_flow, *d_pr, *d_audio, *d_misc;
+  const size_t lb = (size_t)n * length;
+  if ((rc = scratch(ctx, 0, (size_t)n * sizeof(afs_tube_frame), &d_tubes))) return rc;
+  if ((rc = scratch(ctx, 3, (size_t)n * 512 * sizeof(double), &d_h))) return rc;
+  if ((rc = scratch(ctx, 4, lb * sizeof(double), &d_flow))) return rc;
+  if ((rc = scratch(ctx, 5, lb * sizeof(double), &d_pr))) return rc;
+  if ((rc = scratch(ctx, 6, lb * sizeof(int16_t), &d_audio))) return rc;
+  CU(cudaMemcpyAsync(d_tubes, tubes, (size_t)n * sizeof(afs_tube_frame), cudaMemcpyHostToDevice, ctx->stream));
+  rc = afs_tl_impulse_response_device(ctx, opts, n, (const afs_tube_frame *)d_tubes, sampling_rate_hz, 9, (double *)d_h,
+                                      ctx->stream);  // uses scratch 1, 2, 7
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));  // scratch 7 is reused below
+  if ((rc = scratch(ctx, 7, ((size_t)n + 14) * sizeof(double), &d_misc))) return rc;
+  double *d_scale = (double *)d_misc, *d_ab = d_scale + n;
+  CU(cudaMemcpyAsync(d_flow, flow.data(), lb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_scale, scale.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_ab, ab.data(), 14 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_lf_convolve(n, length, (const double *)d_h, d_scale, (const double *)d_flow, (double *)d_pr, ctx->stream));
+  CU(launch_lf_filter(n, length, d_ab, (const double *)d_pr, (int16_t *)d_audio, ctx->stream));
+  ctx->launches += 2;
+  CU(cudaMemcpyAsync(audio, d_audio, lb * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (pressure) CU(cudaMemcpyAsync(pressure, d_pr, lb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return AFS_OK;
+}
+
+// ---------------------------------------------------------------------------
 // TDS
 // ---------------------------------------------------------------------------
 int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int n_frames,

@@ -120,6 +120,124 @@ double area_at(const double *q, double x) {
   return a < 0.0 ? 0.0 : a;
 }
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// LF glottal pulse train of Synthesizer::synthesizeVowelLf (Synthesizer.cpp:645-801): LfPulse::getPulse with
+// getEpsilon / getAlpha / getB (LfPulse.cpp:37-245), the F0 / amplitude contours (TimeFunction::getValue,
+// TimeFunction.cpp:77-133) and the "flutter".  Host code: ~100 pulses per vowel, libm in the reference's own
+// expressions, so the device convolution starts from bit-identical input.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct TfNode { double time, value; };
+double tf_value(const TfNode *nodes, int N, double t) {  // TimeFunction::getValue
+  if (t < nodes[0].time) return nodes[0].value;
+  if (t >= nodes[N - 1].time) return nodes[N - 1].value;
+  int left = 0, right = N - 1;
+  while (right - left > 1) {
+    const int center = left + (right - left) / 2;
+    if (nodes[center].time < t) left = center; else right = center;
+  }
+  double deno = nodes[right].time - nodes[left].time;
+  if (deno < 0.000000001) deno = 0.000000001;
+  const double a = (t - nodes[left].time) / deno;
+  return nodes[left].value + a * (nodes[right].value - nodes[left].value);
+}
+double lf_epsilon(double ta, double te) {  // LfPulse::getEpsilon (Newton; the reference's step counter never counts)
+  double c = 1.0 - te;
+  if (c < 0.001) c = 0.001;
+  if (ta < 0.0001) ta = 0.0001;
+  if (ta > c - 0.00001) ta = c - 0.00001;
+  double epsilon = 1.0 / ta, h, h2;
+  int guard = 0;
+  do {
+    h = 1.0 - exp(-epsilon * c) - epsilon * ta;
+    h2 = c * exp(-epsilon * c) - ta;
+    epsilon = epsilon - h / h2;
+  } while (fabs(h) > 0.00001 && ++guard < 100000);
+  return epsilon;
+}
+double lf_alpha(double tp, double te, double ta, double epsilon) {  // LfPulse::getAlpha (regula falsi)
+  const double w = M_PI / tp, w2 = w * w, SIN = sin(w * te), COS = cos(w * te);
+  const double X = (SIN * exp(epsilon * te) * (-exp(-epsilon) / epsilon - exp(-epsilon))) / (epsilon * ta);
+  const double Y = (SIN * exp(epsilon * te) * (-exp(-epsilon * te) / epsilon - te * exp(-epsilon))) / (epsilon * ta);
+  double a[2] = {0.0, 0.0}, h[2], newAlpha, newH;
+  int numSteps = 0;
+  do {
+    numSteps++;
+    a[1] += 1.0;
+    h[1] = w / (w2 + a[1] * a[1]) + exp(a[1] * te) * ((a[1] * SIN - w * COS) / (w2 + a[1] * a[1]) + X - Y);
+  } while ((numSteps < 20) && (h[1] >= 0.0));
+  if (h[1] >= 0) return 0.0;
+  numSteps = 0;
+  do {
+    h[0] = w / (w2 + a[0] * a[0]) + exp(a[0] * te) * ((a[0] * SIN - w * COS) / (w2 + a[0] * a[0]) + X - Y);
+    h[1] = w / (w2 + a[1] * a[1]) + exp(a[1] * te) * ((a[1] * SIN - w * COS) / (w2 + a[1] * a[1]) + X - Y);
+    newAlpha = a[0] - (h[0] * (a[1] - a[0])) / (h[1] - h[0]);
+    newH = w / (w2 + newAlpha * newAlpha) + exp(newAlpha * te) * ((newAlpha * SIN - w * COS) / (w2 + newAlpha * newAlpha) + X - Y);
+    if (newH < 0.0) a[1] = newAlpha; else a[0] = newAlpha;
+    numSteps++;
+  } while ((numSteps < 20) && (fabs(newH) > 0.00001));
+  return newAlpha;
+}
+// LfPulse::getPulse(s, numSamples, false): one period of the glottal FLOW
+void lf_pulse(double AMP, double OQ, double SQ, double TL, int numSamples, double *x) {
+  const double T0 = 1.0, te = OQ, tp = (te * SQ) / (1.0 + SQ);
+  double ta = TL;
+  if (ta < 0.01) ta = 0.01;
+  if (ta > T0 - te) ta = T0 - te;
+  const double epsilon = lf_epsilon(ta, te);
+  const double alpha = lf_alpha(tp, te, ta, epsilon);
+  double B;
+  {  // LfPulse::getB
+    const double w = 3.1415926 / tp;
+    const double help = (exp(alpha * tp) * (alpha * sin(w * tp) - w * cos(w * tp)) + w) / (w * w + alpha * alpha);
+    B = AMP / help;
+  }
+  const double w = 3.1415926 / tp;
+  const double u1_te = (B * (exp(alpha * te) * (alpha * sin(w * te) - w * cos(w * te)) + w)) / (w * w + alpha * alpha);
+  const double preFactor = (B * exp(alpha * te) * sin(w * te) * exp(epsilon * te)) / (epsilon * ta);
+  const double F2_te = preFactor * (-exp(-epsilon * te) / epsilon - te * exp(-epsilon * T0));
+  for (int i = 0; i < numSamples; i++) {
+    const double t = (double)i / (double)numSamples;
+    if (t <= te) x[i] = (B * (exp(alpha * t) * (alpha * sin(w * t) - w * cos(w * t)) + w)) / (w * w + alpha * alpha);
+    else x[i] = u1_te + preFactor * (-exp(-epsilon * t) / epsilon - t * exp(-epsilon * T0)) - F2_te;
+  }
+}
+}  // namespace
+
+int lf_vowel_length(int is_long, double sampling_rate_hz) {
+  return (int)(((is_long ? 650.0 : 350.0) / 1000.0) * sampling_rate_hz);
+}
+
+// Glottal flow of one vowel: flow[length] (the reference's 2048-sample ring buffer, unrolled: what it reads back at
+// most 511 samples behind the write position is what was written, zeros before the first pulse at sample 10).
+// Returns 0, or -1 when a pulse would not fit the reference's ring buffer (F0 below ~SR/1024).
+int lf_vowel_flow(const afs_lf_pulse *lf, int is_long, double sampling_rate_hz, double *flow) {
+  const double mx = lf->f0_hz;
+  const TfNode f0_long[4] = {{0.0, 0.9 * mx}, {300.0, 1.00 * mx}, {450.0, 0.8 * mx}, {600.0, 0.7 * mx}};
+  const TfNode amp_long[4] = {{0.0, 0.0}, {40.0, 500.0}, {400.0, 450.0}, {600.0, 0.0}};
+  const TfNode f0_short[4] = {{0.0, 0.9 * mx}, {125.0, 1.0 * mx}, {126.0, 1.0 * mx}, {300.0, 0.82 * mx}};
+  const TfNode amp_short[4] = {{0.0, 0.0}, {20.0, 500.0}, {200.0, 450.0}, {300.0, 0.0}};
+  const TfNode *f0n = is_long ? f0_long : f0_short, *ampn = is_long ? amp_long : amp_short;
+  const int length = lf_vowel_length(is_long, sampling_rate_hz);
+  for (int i = 0; i < length; i++) flow[i] = 0.0;
+  double pulse[1024];
+  int next = 10;
+  for (int i = 0; i < length; i++) {
+    if (i != next) continue;
+    const double t_s = (double)i / sampling_rate_hz, t_ms = t_s * 1000.0;
+    const double AMP = tf_value(ampn, 4, t_ms);
+    double F0 = tf_value(f0n, 4, t_ms);
+    F0 += 0.5 * (F0 / 100.0) * (sin(2.0 * M_PI * 12.7 * t_s) + sin(2.0 * M_PI * 7.1 * t_s) + sin(2.0 * M_PI * 4.7 * t_s));
+    const int n = (int)(sampling_rate_hz / F0);
+    if (n < 1 || n > 1024) return -1;
+    lf_pulse(AMP, lf->oq, lf->sq, lf->tl, n, pulse);
+    for (int k = 0; k < n && i + k < length; k++) flow[i + k] = pulse[k];
+    next += n;
+  }
+  return 0;
+}
+
 }  // namespace afs
 
 extern "C" {

@@ -37,6 +37,15 @@ cudaError_t launch_impulse_response(int n_tubes, int length_exponent, int num_fr
 void impulse_response_tables(double f0_hz, int length_exponent, int num_freq, double *tw_re, double *tw_im,
                              double *rad_re, double *rad_im, double *window);
 
+// LF vowel synthesis (Synthesizer::synthesizeVowelLf): convolution + output filter on the device (tl_kernels.cu),
+// pulse train on the host (afs_host.cpp)
+cudaError_t launch_lf_convolve(int n, int length, const double *d_h512, const double *d_scale, const double *d_flow,
+                               double *d_pressure, cudaStream_t stream);
+cudaError_t launch_lf_filter(int n, int length, const double *d_ab14, const double *d_pressure, int16_t *d_audio,
+                             cudaStream_t stream);
+int lf_vowel_length(int is_long, double sampling_rate_hz);
+int lf_vowel_flow(const afs_lf_pulse *lf, int is_long, double sampling_rate_hz, double *flow);
+
 // ---- TDS ------------------------------------------------------------------
 struct TdsParams;  // tds_kernels.cu
 struct TdsLaunch {

@@ -247,6 +247,60 @@ int afs_tl_impulse_response_device(afs_ctx *ctx, const afs_tl_options *opts, int
                                    const afs_tube_frame *d_tubes, double sampling_rate_hz,
                                    int length_exponent, double *d_impulse_response, void *stream);
 
+/*
+ * Replaces Data::optimizeFormantsVowel with Data::getVowelFormants / getFormantError (Frontend/Data.cpp:203-487,
+ * 149-196, 106-135) -- the reference's only caller of repeated TL sweeps -- for a batch of independent problems.
+ * Greedy coordinate search: every run evaluates the current parameter set and up to 32 neighbours (each free
+ * parameter one step up / down: 0.05 cm for positions, 0.0025 cm^2 for areas, 0.1 for exponents, at most
+ * round(max_param_change_cm / 0.05) in [1, 40] steps from the start, control points kept in order exactly as the
+ * reference does, including its in-place change of the step size when a neighbour is clamped), takes the
+ * neighbour with the smallest formant error (strictly smaller than the current one, minimum area of tube
+ * sections 25..39 >= min_advised_area_cm2) and stops when nothing improves or after max_runs runs (reference:
+ * 100).  The candidates of ALL problems of a run are evaluated in one batch on the device: rasteriser (K4) ->
+ * TL sweep (glottis closed, TlModel::getFormants grid sampling_rate_hz / spectrum_length = 22050 / 2048) ->
+ * formant picking (3 formants; fewer than 3 count as F1 = F2 = F3 = 0 like the reference).
+ * Hidden state of the reference, kept: TlModel::getFormants leaves lungPressure_dPa = 8000 in the (persistent)
+ * Data::tlModel (TlModel.cpp:427, 253-260), so every evaluation after the first runs with 8000 dPa; only the
+ * initial error is evaluated with opts->lung_pressure_dPa (0 = a fresh TlModel).
+ *   params        [n][16] in/out, order of OneDimAreaFunction::ParamIndex (OneDimAreaFunction.h:34-43)
+ *   target_hz     [n][3]  (F3 <= 1: only F1, F2 count)
+ *   param_fixed   [16] nullable (non-zero: parameter is not changed)
+ *   initial_error, final_error [n] nullable (percent), runs [n] nullable, formants_hz [n][3] nullable (final)
+ *   trace         [n][max_runs][2] nullable: parameter changed by every run (-1: none) and the error reached
+ */
+int afs_optimize_formants_vowel(afs_ctx *ctx, const afs_tl_options *opts, int n_problems, double *params,
+                                const double *target_hz, double max_param_change_cm, double min_advised_area_cm2,
+                                const int32_t *param_fixed, int max_runs, double sampling_rate_hz, int spectrum_length,
+                                double *initial_error, double *final_error, int32_t *runs, double *formants_hz,
+                                double *trace);
+
+/*
+ * LF glottal pulse parameters: the public members of LfPulse (LfPulse.h:25-29; defaults of
+ * LfPulse::resetParams, LfPulse.cpp:24-31, via afs_lf_pulse_default).
+ */
+typedef struct afs_lf_pulse {
+  double amp_cm3_s; /* AMP */
+  double f0_hz;     /* F0  */
+  double oq;        /* OQ  open quotient */
+  double sq;        /* SQ  speed quotient */
+  double tl;        /* TL  spectral tilt */
+} afs_lf_pulse;
+void afs_lf_pulse_default(afs_lf_pulse *p);
+/* Samples of one vowel: (int)(0.65 * rate) long, (int)(0.35 * rate) short (Synthesizer.cpp:667-715). */
+int afs_lf_vowel_length(int is_long_vowel, double sampling_rate_hz);
+/*
+ * Replaces Synthesizer::synthesizeVowelLf(tlModel, lfPulse, startPos, isLongVowel) (Synthesizer.cpp:645-801) for a
+ * batch of vowels: impulse response of every tube (afs_tl_impulse_response, length 512) scaled by 80 / F0, the LF
+ * pulse train with the reference's F0 / amplitude contours and flutter (LfPulse.cpp:37-245, TimeFunction.cpp:77-
+ * 133; host side, ~100 pulses per vowel), the 512-tap convolution, the Chebyshev-6 low-pass at 8 kHz, x 2000, cast
+ * to int16.  audio [n][length] (length = afs_lf_vowel_length); pressure (nullable) [n][length]: the convolution
+ * output before the filter.  With REFERENCE arithmetic the int16 samples are identical to the reference's.
+ * AFS_ERR_BAD_ARGUMENT when a pulse would not fit the reference's 2048-sample ring buffer (F0 below rate / 1024).
+ */
+int afs_synthesize_vowels_lf(afs_ctx *ctx, const afs_tl_options *opts, int n_vowels, const afs_tube_frame *tubes,
+                             const afs_lf_pulse *pulses, int is_long_vowel, double sampling_rate_hz, int16_t *audio,
+                             double *pressure);
+
 /* ---- TdsModel + TriangularGlottis + driver loop ---------------------------- */
 /*
  * Replaces, for a batch of independent utterances ("tracts"), the per-sample

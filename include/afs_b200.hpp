@@ -146,10 +146,35 @@ class TlModel {
     check(afs_tl_formants(dev_.ctx(), &options, (int)f.size(), f.data(), 22050.0, 2048, MAX_FORMANTS,
                           formantFreq->data(), formantBW->data(), numFormants->data(), flags->data()), dev_.ctx());
   }
+  // TlModel::getImpulseResponse (TlModel.cpp:90-111) for every tube: impulseResponse[n][1 << lengthExponent].
+  void getImpulseResponse(std::vector<double> *impulseResponse, int lengthExponent, double samplingRate = 22050.0) {
+    std::vector<afs_tube_frame> f(tubes.size());
+    for (size_t i = 0; i < tubes.size(); i++) f[i] = tubes[i].frame;
+    impulseResponse->assign(f.size() << lengthExponent, 0.0);
+    check(afs_tl_impulse_response(dev_.ctx(), &options, (int)f.size(), f.data(), samplingRate, lengthExponent,
+                                  impulseResponse->data()), dev_.ctx());
+  }
+
+  Device &device() { return dev_; }
 
  private:
   Device &dev_;
 };
+
+// Data::optimizeFormantsVowel (Frontend/Data.cpp:203-487) for a batch of area-function parameter sets
+// (params[n][16] in/out, targets[n][3]); returns the final errors in percent.
+inline std::vector<double> optimizeFormantsVowel(TlModel &tlModel, std::vector<double> *params, const std::vector<double> &targets,
+                                                 double maxParamChange_cm, double minAdvisedArea_cm2,
+                                                 const bool paramFixed[16] = nullptr, int maxRuns = 100) {
+  const int n = (int)(params->size() / 16);
+  int32_t fixed[16];
+  for (int i = 0; i < 16; i++) fixed[i] = paramFixed ? (paramFixed[i] ? 1 : 0) : 0;
+  std::vector<double> finalError((size_t)n, 0.0);
+  check(afs_optimize_formants_vowel(tlModel.device().ctx(), &tlModel.options, n, params->data(), targets.data(), maxParamChange_cm,
+                                    minAdvisedArea_cm2, fixed, maxRuns, 22050.0, 2048, nullptr, finalError.data(), nullptr,
+                                    nullptr, nullptr), tlModel.device().ctx());
+  return finalError;
+}
 
 // Batched replacement of the Synthesizer's TDS driver: the caller queues control frames exactly like successive
 // calls of Synthesizer::synthesizeSignalTds(newTube, newGlottisParams, numNewSamples, out) (Synthesizer.cpp:515-639)

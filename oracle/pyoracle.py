@@ -123,6 +123,31 @@ class Ref:
                                       max_bins, _ptr(re), _ptr(im), threads)
         return re[:, :nf].copy(), im[:, :nf].copy()
 
+    def optimize_formants_vowel(self, params16, targets, max_param_change_cm=1.0, min_advised_area_cm2=0.0,
+                                param_fixed=None, max_runs=100, opts=None):
+        """Data::optimizeFormantsVowel (Data.cpp:203-487) restated over the reference classes (ref_harness.cpp).
+        Returns (params, initial_error, final_error, runs, trace[runs, 2], formants[3])."""
+        opts = opts or tl_options_default()
+        p = np.array(params16, dtype=np.float64).copy()
+        t = np.ascontiguousarray(targets, dtype=np.float64)
+        fx = np.zeros(16, dtype=np.int32) if param_fixed is None else np.ascontiguousarray(param_fixed, dtype=np.int32)
+        out3 = np.zeros(3); trace = np.zeros((max_runs, 2)); fo = np.zeros(3)
+        self.lib.ref_optimize_formants_vowel(C.byref(opts), _ptr(p), _ptr(t), C.c_double(max_param_change_cm),
+                                             C.c_double(min_advised_area_cm2), _ptr(fx), int(max_runs), _ptr(out3),
+                                             _ptr(trace), _ptr(fo))
+        runs = int(out3[2])
+        return p, out3[0], out3[1], runs, trace[:runs], fo
+
+    def synthesize_vowel_lf(self, frame, lf5, is_long, opts=None):
+        """Synthesizer::synthesizeVowelLf restated over the reference classes: (int16 audio, float64 pressure)."""
+        opts = opts or tl_options_default()
+        n = self.lib.ref_lf_vowel_length(int(is_long))
+        out = np.zeros(n, dtype=np.int16); pr = np.zeros(n)
+        lf = np.ascontiguousarray(lf5, dtype=np.float64)
+        m = self.lib.ref_synthesize_vowel_lf(C.byref(opts), _ptr(np.ascontiguousarray(frame)), _ptr(lf), int(is_long), _ptr(out), _ptr(pr))
+        assert m == n
+        return out, pr
+
     def tl_impulse_response(self, frames, length_exponent=9, opts=None):
         opts = opts or tl_options_default()
         n = len(frames)

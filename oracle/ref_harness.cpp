@@ -14,8 +14,11 @@
 #include "OneDimAreaFunction.h"
 #include "IirFilter.h"
 #include "Tube.h"
+#include "LfPulse.h"
+#include "TimeFunction.h"
 
 #include <climits>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -130,6 +133,235 @@ void ref_tl_impulse_response(const afs_tl_options *opts, int n_tubes, const afs_
     for (int i = 0; i < N; i++) out[(size_t)b * N + i] = h.x[i];
     delete tl;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Data::getVowelFormants / getFormantError / optimizeFormantsVowel (Frontend/Data.cpp:106-135, 149-196, 203-487).
+// Data.cpp is wx-bound (progress dialog, printf, events), so the greedy coordinate search is restated here line by
+// line over the reference's own OneDimAreaFunction and TlModel; dialogs, printing and the GUI refresh are left out.
+// ---------------------------------------------------------------------------------------------------
+static bool ref_get_vowel_formants(TlModel *tlModel, OneDimAreaFunction *vtAf, double &F1, double &F2, double &F3,
+                                   double &minArea_cm2) {
+  const int MAX_FORMANTS = 3;
+  double formantFreq[MAX_FORMANTS], formantBw[MAX_FORMANTS];
+  int numFormants;
+  bool frictionNoise, isClosure, isNasal;
+  F1 = F2 = F3 = 0.0;
+  minArea_cm2 = 0.0;
+  Tube tubeFunction;
+  vtAf->calculateOneDimTubeFunction(&tubeFunction);
+  tlModel->tube = tubeFunction;
+  tlModel->tube.setGlottisArea(0.0);
+  minArea_cm2 = 10000.0;
+  for (int i = Tube::FIRST_PHARYNX_SECTION; i < Tube::NUM_PHARYNX_MOUTH_SECTIONS; i++)  // sic: sections 25..39
+    if (tlModel->tube.section[i]->area_cm2 < minArea_cm2) minArea_cm2 = tubeFunction.section[i]->area_cm2;
+  tlModel->getFormants(formantFreq, formantBw, numFormants, MAX_FORMANTS, frictionNoise, isClosure, isNasal);
+  if (numFormants < MAX_FORMANTS) return false;
+  F1 = formantFreq[0]; F2 = formantFreq[1]; F3 = formantFreq[2];
+  return true;
+}
+
+static double ref_formant_error(double c1, double c2, double c3, double t1, double t2, double t3) {
+  const double EPSILON = 1.0;
+  double e = 0.0;
+  if (t3 > EPSILON) {
+    e = (1.0 - c1 / t1) * (1.0 - c1 / t1) + (1.0 - c2 / t2) * (1.0 - c2 / t2) + (1.0 - c3 / t3) * (1.0 - c3 / t3);
+    e /= 3.0;
+  } else {
+    e = (1.0 - c1 / t1) * (1.0 - c1 / t1) + (1.0 - c2 / t2) * (1.0 - c2 / t2);
+    e /= 2.0;
+  }
+  e = sqrt(e);
+  e = e * 100.0;
+  return e;
+}
+
+// params16: in/out.  out3 = initial error, final error, number of runs.  trace (nullable) [max_runs][2]: changed
+// parameter (-1: none) and error after every run.  formants_out (nullable) [3]: F1..F3 of the final parameters.
+void ref_optimize_formants_vowel(const afs_tl_options *opts, double *params16, const double *target3,
+                                 double maxParamChange_cm, double minAdvisedArea_cm2, const int32_t *paramFixed16,
+                                 int max_runs, double *out3, double *trace, double *formants_out) {
+  typedef OneDimAreaFunction AF;
+  AF afObj;
+  AF *vtAf = &afObj;
+  TlModel *tlModel = new TlModel();
+  set_tl_options(tlModel, opts);
+  {
+    AF::Param p[AF::NUM_AF_PARAMS];
+    vtAf->getParameters(p);
+    for (int i = 0; i < AF::NUM_AF_PARAMS; i++) p[i].x = params16[i];
+    vtAf->setParameters(p);
+  }
+  const double targetF1 = target3[0], targetF2 = target3[1], targetF3 = target3[2];
+  const int MAX_RUNS = max_runs;
+  double F1, F2, F3, minArea_cm2;
+  double changeStep[AF::NUM_AF_PARAMS];
+  int stepsTaken[AF::NUM_AF_PARAMS];
+  double currParamValue, bestError, currError, newError, bestParamChange;
+  int bestParam, i;
+
+  ref_get_vowel_formants(tlModel, vtAf, F1, F2, F3, minArea_cm2);
+  double initialError = ref_formant_error(F1, F2, F3, targetF1, targetF2, targetF3);
+
+  const double STEP_SIZE_CM = 0.05;
+  int maxSteps = (int)((maxParamChange_cm / STEP_SIZE_CM) + 0.5);
+  if (maxSteps < 1) maxSteps = 1;
+  if (maxSteps > 40) maxSteps = 40;
+  for (i = 0; i < AF::NUM_AF_PARAMS; i++) { changeStep[i] = 0.0; stepsTaken[i] = 0; }
+  changeStep[AF::LLAR_CM] = STEP_SIZE_CM; changeStep[AF::XP_CM] = STEP_SIZE_CM; changeStep[AF::XC_CM] = STEP_SIZE_CM;
+  changeStep[AF::XA_CM] = STEP_SIZE_CM; changeStep[AF::XIN_CM] = STEP_SIZE_CM; changeStep[AF::LVT_CM] = STEP_SIZE_CM;
+  changeStep[AF::ALAR_CM2] = STEP_SIZE_CM * STEP_SIZE_CM; changeStep[AF::AP_CM2] = STEP_SIZE_CM * STEP_SIZE_CM;
+  changeStep[AF::AC_CM2] = STEP_SIZE_CM * STEP_SIZE_CM; changeStep[AF::AA_CM2] = STEP_SIZE_CM * STEP_SIZE_CM;
+  changeStep[AF::AIN_CM2] = STEP_SIZE_CM * STEP_SIZE_CM; changeStep[AF::ALIP_CM2] = STEP_SIZE_CM * STEP_SIZE_CM;
+  changeStep[AF::POWLAR] = 0.1; changeStep[AF::POWP] = 0.1; changeStep[AF::POWC] = 0.1; changeStep[AF::POWA] = 0.1;
+  for (i = 0; i < AF::NUM_AF_PARAMS; i++) if (paramFixed16 && paramFixed16[i]) changeStep[i] = 0.0;
+
+  bool paramChanged = false;
+  int runCounter = 0;
+  AF::Param currentParameters[AF::NUM_AF_PARAMS];
+  do {
+    paramChanged = false;
+    ref_get_vowel_formants(tlModel, vtAf, F1, F2, F3, minArea_cm2);
+    currError = ref_formant_error(F1, F2, F3, targetF1, targetF2, targetF3);
+    bestError = currError; bestParam = -1; bestParamChange = 0.0;
+    vtAf->getParameters(currentParameters);
+    for (i = 0; i < AF::NUM_AF_PARAMS; i++) {
+      currParamValue = currentParameters[i].x;
+      if (changeStep[i] > 0.0) {
+        if (stepsTaken[i] < maxSteps) {
+          currentParameters[i].x = currParamValue + changeStep[i];
+          if (i == AF::XP_CM && currentParameters[i].x > currentParameters[AF::XC_CM].x) { changeStep[i] = currentParameters[AF::XC_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::XC_CM].x; }
+          if (i == AF::XC_CM && currentParameters[i].x > currentParameters[AF::XA_CM].x) { changeStep[i] = currentParameters[AF::XA_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::XA_CM].x; }
+          if (i == AF::XA_CM && currentParameters[i].x > currentParameters[AF::XIN_CM].x) { changeStep[i] = currentParameters[AF::XIN_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::XIN_CM].x; }
+          if (i == AF::XIN_CM && currentParameters[i].x > currentParameters[AF::LVT_CM].x) { changeStep[i] = currentParameters[AF::LVT_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::LVT_CM].x; }
+          vtAf->setParameters(currentParameters);
+          ref_get_vowel_formants(tlModel, vtAf, F1, F2, F3, minArea_cm2);
+          if (minArea_cm2 >= minAdvisedArea_cm2) {
+            newError = ref_formant_error(F1, F2, F3, targetF1, targetF2, targetF3);
+            if (newError < bestError) { bestError = newError; bestParam = i; bestParamChange = changeStep[i]; }
+          }
+        }
+        if (stepsTaken[i] > -maxSteps) {
+          currentParameters[i].x = currParamValue - changeStep[i];
+          if (i == AF::XP_CM && currentParameters[i].x < currentParameters[AF::LLAR_CM].x) { changeStep[i] = currentParameters[AF::LLAR_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::LLAR_CM].x; }
+          if (i == AF::XC_CM && currentParameters[i].x < currentParameters[AF::XP_CM].x) { changeStep[i] = currentParameters[AF::XP_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::XP_CM].x; }
+          if (i == AF::XA_CM && currentParameters[i].x < currentParameters[AF::XC_CM].x) { changeStep[i] = currentParameters[AF::XC_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::XC_CM].x; }
+          if (i == AF::XIN_CM && currentParameters[i].x < currentParameters[AF::XA_CM].x) { changeStep[i] = currentParameters[AF::XA_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::XA_CM].x; }
+          if (i == AF::LVT_CM && currentParameters[i].x < currentParameters[AF::XIN_CM].x) { changeStep[i] = currentParameters[AF::XIN_CM].x - currentParameters[i].x; currentParameters[i].x = currentParameters[AF::XIN_CM].x; }
+          vtAf->setParameters(currentParameters);
+          ref_get_vowel_formants(tlModel, vtAf, F1, F2, F3, minArea_cm2);
+          if (minArea_cm2 >= minAdvisedArea_cm2) {
+            newError = ref_formant_error(F1, F2, F3, targetF1, targetF2, targetF3);
+            if (newError < bestError) { bestError = newError; bestParam = i; bestParamChange = -changeStep[i]; }
+          }
+        }
+        currentParameters[i].x = currParamValue;
+        vtAf->setParameters(currentParameters);
+      }
+    }
+    if ((bestParam != -1) && (bestError < currError)) {
+      currentParameters[bestParam].x += bestParamChange;
+      vtAf->setParameters(currentParameters);
+      if (bestParamChange > 0.0) stepsTaken[bestParam]++; else stepsTaken[bestParam]--;
+      paramChanged = true;
+    }
+    if (trace) { trace[2 * runCounter] = paramChanged ? (double)bestParam : -1.0; trace[2 * runCounter + 1] = bestError; }
+    runCounter++;
+  } while (paramChanged && (runCounter < MAX_RUNS));
+
+  ref_get_vowel_formants(tlModel, vtAf, F1, F2, F3, minArea_cm2);
+  double finalError = ref_formant_error(F1, F2, F3, targetF1, targetF2, targetF3);
+  vtAf->getParameters(currentParameters);
+  for (i = 0; i < AF::NUM_AF_PARAMS; i++) params16[i] = currentParameters[i].x;
+  out3[0] = initialError; out3[1] = finalError; out3[2] = (double)runCounter;
+  if (formants_out) { formants_out[0] = F1; formants_out[1] = F2; formants_out[2] = F3; }
+  delete tlModel;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Synthesizer::synthesizeVowelLf (Synthesizer.cpp:645-801): LF glottal pulses convolved with the vocal tract impulse
+// response.  Synthesizer is wx/PortAudio-bound, so the loop is restated line by line over the reference's own
+// TlModel, LfPulse, TimeFunction, IirFilter and Signal; the audio ring buffer becomes a plain output array.
+// lf5 = AMP, F0, OQ, SQ, TL (LfPulse.h:25-29).  Returns the number of samples written.
+// ---------------------------------------------------------------------------------------------------
+int ref_lf_vowel_length(int isLongVowel) {
+  double duration_ms = isLongVowel ? 650.0 : 350.0;
+  return (int)((duration_ms / 1000.0) * (double)SAMPLING_RATE);
+}
+
+int ref_synthesize_vowel_lf(const afs_tl_options *opts, const afs_tube_frame *tubeFrame, const double *lf5,
+                            int isLongVowel, int16_t *out, double *pressure_out) {
+  TlModel *tlModel = new TlModel();
+  set_tl_options(tlModel, opts);
+  frame_to_tube(tubeFrame, &tlModel->tube);
+  LfPulse lfPulse;
+  lfPulse.AMP = lf5[0]; lfPulse.F0 = lf5[1]; lfPulse.OQ = lf5[2]; lfPulse.SQ = lf5[3]; lfPulse.TL = lf5[4];
+
+  const int NUM_F0_NODES = 4;
+  const int NUM_AMP_NODES = 4;
+  const int BUFFER_LENGTH = 2048;
+  const int BUFFER_MASK = 2047;
+  TimeFunction ampTimeFunction;
+  TimeFunction f0TimeFunction;
+  double duration_ms;
+  Signal singlePulse;
+  Signal pulseSignal(BUFFER_LENGTH);
+  Signal pressureSignal(BUFFER_LENGTH);
+  int i, k;
+  int nextPulsePos = 10;
+  int pulseLength;
+  double t_s, t_ms;
+  double sum;
+  double filteredValue;
+
+  if (isLongVowel) {
+    duration_ms = 650.0;
+    double max = lfPulse.F0;
+    TimeFunction::Node f0[NUM_F0_NODES] = {{0.0, 0.9 * max}, {300.0, 1.00 * max}, {450.0, 0.8 * max}, {600.0, 0.7 * max}};
+    TimeFunction::Node amp[NUM_AMP_NODES] = {{0.0, 0.0}, {40.0, 500.0}, {400.0, 450.0}, {600.0, 0.0}};
+    ampTimeFunction.setNodes(amp, NUM_AMP_NODES);
+    f0TimeFunction.setNodes(f0, NUM_F0_NODES);
+  } else {
+    duration_ms = 350.0;
+    double max = lfPulse.F0;
+    TimeFunction::Node f0[NUM_F0_NODES] = {{0.0, 0.9 * max}, {125.0, 1.0 * max}, {126.0, 1.0 * max}, {300.0, 0.82 * max}};
+    TimeFunction::Node amp[NUM_AMP_NODES] = {{0.0, 0.0}, {20.0, 500.0}, {200.0, 450.0}, {300.0, 0.0}};
+    ampTimeFunction.setNodes(amp, NUM_AMP_NODES);
+    f0TimeFunction.setNodes(f0, NUM_F0_NODES);
+  }
+  int length = (int)((duration_ms / 1000.0) * (double)SAMPLING_RATE);
+
+  const double NUM_LOWPASS_POLES = 6;
+  IirFilter filter;
+  filter.createChebyshev((double)SYNTHETIC_SPEECH_BANDWIDTH_HZ / (double)SAMPLING_RATE, false, (int)NUM_LOWPASS_POLES);
+
+  const int IMPULSE_RESPONSE_EXPONENT = 9;
+  const int IMPULSE_RESPONSE_LENGTH = 1 << IMPULSE_RESPONSE_EXPONENT;
+  Signal impulseResponse(IMPULSE_RESPONSE_LENGTH);
+  tlModel->getImpulseResponse(&impulseResponse, IMPULSE_RESPONSE_EXPONENT);
+  impulseResponse *= 80.0 / lfPulse.F0;
+
+  for (i = 0; i < length; i++) {
+    t_s = (double)i / (double)SAMPLING_RATE;
+    t_ms = t_s * 1000.0;
+    if (i == nextPulsePos) {
+      lfPulse.AMP = ampTimeFunction.getValue(t_ms);
+      lfPulse.F0 = f0TimeFunction.getValue(t_ms);
+      lfPulse.F0 += 0.5 * (lfPulse.F0 / 100.0) * (sin(2.0 * M_PI * 12.7 * t_s) + sin(2.0 * M_PI * 7.1 * t_s) + sin(2.0 * M_PI * 4.7 * t_s));
+      pulseLength = (int)((double)SAMPLING_RATE / lfPulse.F0);
+      lfPulse.getPulse(singlePulse, pulseLength, false);
+      for (k = 0; k < pulseLength; k++) pulseSignal.x[(i + k) & BUFFER_MASK] = singlePulse.getValue(k);
+      nextPulsePos += pulseLength;
+    }
+    sum = 0.0;
+    for (k = 0; k < IMPULSE_RESPONSE_LENGTH; k++) sum += impulseResponse.x[k] * pulseSignal.x[(i - k) & BUFFER_MASK];
+    pressureSignal.x[i & BUFFER_MASK] = sum;
+    filteredValue = 2000.0 * filter.getOutputSample(pressureSignal.getValue(i));
+    out[i] = (short)filteredValue;
+    if (pressure_out) pressure_out[i] = sum;
+  }
+  delete tlModel;
+  return length;
 }
 
 // TlModel::getFormants on a fresh TlModel per tube.

@@ -24,7 +24,14 @@ int main() {
     std::printf("formants %d %.6f %.6f %.6f nasal %d %.6f\n", n[0], f[0], f[1], f[2], flags[1] & 4 ? 1 : 0, f[8]);
     afs::ComplexSpectrum s;
     tl.getSpectrum(afs::TlModel::FLOW_SOURCE_TF, &s, 2048, afs::Tube::FIRST_PHARYNX_SECTION);
-    std::printf("spectrum %d %.16g %.16g\n", s.numFreq, s.re[0], s.im[0]);
+    std::printf("spectrum %d %.17g %.17g\n", s.numFreq, s.re[0], s.im[0]);
+    std::vector<double> h;
+    tl.getImpulseResponse(&h, 9);  // Synthesizer::synthesizeVowelLf (Synthesizer.cpp:719-724)
+    std::printf("impulse %zu %.17g %.17g\n", h.size(), h[100], h[512 + 100]);
+    // --- Data::optimizeFormantsVowel-style use (Data.cpp:203-487), three runs ---
+    std::vector<double> prm(a_params, a_params + 16);
+    const std::vector<double> err = afs::optimizeFormantsVowel(tl, &prm, {650.0, 1300.0, 2600.0}, 1.0, 0.0, nullptr, 3);
+    std::printf("optimizer %.12g %.12g %.12g\n", err[0], prm[2], prm[8]);
     // --- Synthesizer-style use (Synthesizer.cpp:515-639): prime, then one 50 ms frame ---
     afs::TdsSynthesizer syn(dev, 2);
     afs::Tube tubes[2] = {tl.tubes[0], tl.tubes[1]};

@@ -44,6 +44,10 @@ def test_facade_matches_ctypes_path(ctx, shapes):
     assert int(lines["formants"][5]) == 1 and abs(float(lines["formants"][6]) - f[1, 0]) < 1e-6
     re, im = ctx.tl_sweep(fr[:1], 22050.0 / 2048, 938)
     assert int(lines["spectrum"][0]) == 938 and float(lines["spectrum"][1]) == re[0, 0]
+    h = ctx.tl_impulse_response(fr, 22050.0, 9)
+    assert int(lines["impulse"][0]) == h.size and float(lines["impulse"][1]) == h[0, 100] and float(lines["impulse"][2]) == h[1, 100]
+    o = ctx.optimize_formants_vowel(shapes["params"][0], [650.0, 1300.0, 2600.0], 1.0, 0.0, None, 3)
+    np.testing.assert_allclose([float(x) for x in lines["optimizer"]], [o["final_error"][0], o["params"][0, 2], o["params"][0, 8]], rtol=1e-9)
     gl = np.array([[[120, 8000, 0.01, 0.01, 0, -40]] * 2, [[150, 8000, 0.01, 0.01, 0, -40]] * 2], dtype=float)
     a, _, st = ctx.tds_synthesize(np.stack([fr, fr], axis=1), gl, [1102], 44100.0, 2)
     assert int(lines["audio"][0]) == a.size and int(lines["audio"][3]) == 0

@@ -240,7 +240,7 @@ def test_fast_arithmetic_types_sections_options(ctx, shapes):
                 (dict(piriform_fossa=1, inner_length_corrections=1, heat_conduction=1, hagen_resistance=1), 1e-5, 1e-4),
                 (dict(soft_walls=0, paranasal_sinuses=0, radiation=1), 1e-7, 2e-8),
                 (dict(radiation=2, lung_pressure_dPa=8000.0), 1e-7, 2e-8),
-                (dict(radiation=0, boundary_layer=0, static_pressure_drops=0), 1e-6, 1e-5))
+                (dict(radiation=0, boundary_layer=0, static_pressure_drops=0), 1e-4, 1e-4))  # nearly undamped poles
     for kw, of_scale, pointwise in variants:
         a, b = _fast_opts(**kw)
         for t, sec in ((2, 25), (2, 0), (2, 24), (2, 33), (2, 40), (2, 41), (2, 50), (2, 64), (2, 65), (3, 0), (3, 30),
