@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 W_TDS = 1.0e4  # algorithmic FP64 flop per tract-step
 W_TL = 8.0e3   # algorithmic FP64 flop per (area function, bin)
+TDS_TRAFFIC_BYTES = 32610816 + 692230400  # profiles/r1c_tds_ncu.txt: 4096 tracts x 44100 steps, one launch
 W_TL_FAST = 4.4e3  # FP64 flop per (area function, bin) the ladder formulation of K2f executes (84 sections x 43 + sinuses + algebra)
 B_TDS = 4096
 T_SEC = 1.0  # overridden by --utt-seconds (profiling only)
@@ -348,14 +349,27 @@ def run_ours(args):
     tl_ms = timed(tl_dev, tl_steps, 3) / tl_steps
     tl_value = world * B_TL / (tl_ms * 1e-3)
     tl_tflops = W_TL * B_TL * K_TL / (tl_ms * 1e-3) / 1e12
-    h_re = np.empty((B_TL, K_TL)); h_im = np.empty((B_TL, K_TL))
-    ctx.tl_sweep(f_tl, F0_TL, K_TL)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        h_re, h_im = ctx.tl_sweep(f_tl, F0_TL, K_TL)
-    barrier()
-    tl_e2e = world * B_TL / max_over_ranks((time.perf_counter() - t0) / 3)
+    # e2e: pinned host buffers -> C-ABI host call (H2D + kernel + D2H, the D2H of a chunk beside the next chunk's kernel)
+    h_ftl = torch.from_numpy(f_tl.view(np.uint8).reshape(B_TL, -1).copy()).pin_memory()
+    h_re = torch.empty(B_TL, K_TL, dtype=torch.float64).pin_memory()
+    h_im = torch.empty(B_TL, K_TL, dtype=torch.float64).pin_memory()
+
+    def tl_host(o):
+        rc = ctx.lib.afs_tl_sweep(ctx.h, afs.api.C.byref(o), B_TL, h_ftl.data_ptr(), 2, 25, F0_TL, K_TL, h_re.data_ptr(),
+                                  h_im.data_ptr())
+        assert rc == 0, rc
+
+    def tl_e2e_of(o):
+        tl_host(o)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            tl_host(o)
+        barrier()
+        return world * B_TL / max_over_ranks((time.perf_counter() - t0) / 3)
+
+    tl_e2e = tl_e2e_of(afs.tl_options_default())
+    assert torch.equal(h_re, d_re.cpu()) and torch.equal(h_im, d_im.cpu()), "host-path spectra differ from the device-resident path"
 
     # same sweep with afs_tl_options.arithmetic = FAST (K2f: ladder recurrences, 1e-9 class instead of bit-identical)
     fast = afs.tl_options_default(); fast.arithmetic = afs.TL_ARITHMETIC_FAST
@@ -372,13 +386,7 @@ def run_ours(args):
                "against": "the bit-identical kernel's output of this run; see tests/test_tl_gpu.py::"
                           "test_fast_arithmetic_against_extended_precision for which of the two is nearer to the formulas"}
     del h_ref, h_fast, rel
-    ctx.tl_sweep(f_tl, F0_TL, K_TL, opts=fast)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        ctx.tl_sweep(f_tl, F0_TL, K_TL, opts=fast)
-    barrier()
-    tlf_e2e = world * B_TL / max_over_ranks((time.perf_counter() - t0) / 3)
+    tlf_e2e = tl_e2e_of(fast)
 
     # ---------------- rasteriser: parameter sets -> frames on the device --------------
     B_RA = 65536
@@ -404,6 +412,47 @@ def run_ours(args):
         dev_fr = np.frombuffer(d_fra[:2048].cpu().numpy().tobytes(), dtype=afs.FRAME_DTYPE)
         assert np.array_equal(dev_fr["articulator"], host_fr["articulator"])
         assert np.max(np.abs(dev_fr["area_cm2"] - host_fr["area_cm2"]) / host_fr["area_cm2"]) <= 1e-12
+
+    # ---------------- formant optimiser and LF vowel synthesis (small legs, host API) ------
+    extra = {}
+    if world == 1:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "default_shapes.npz"))
+        vowels = [i for i, nm in enumerate(g["names"]) if "(" not in str(nm)][:16]
+        n_opt, runs_opt = 64, 10
+        p0 = g["params"][[vowels[i % len(vowels)] for i in range(n_opt)]]
+        tg = np.tile(np.array([[650.0, 1300.0, 2600.0], [300.0, 2100.0, 2900.0], [500.0, 1500.0, 2500.0], [380.0, 700.0, 2500.0]]), (n_opt // 4, 1))
+        ctx.optimize_formants_vowel(p0[:4], tg[:4], 1.0, 0.0, None, 2)
+        t0 = time.perf_counter()
+        ro = ctx.optimize_formants_vowel(p0, tg, 1.0, 0.0, None, runs_opt)
+        dt = time.perf_counter() - t0
+        evals = int(ro["runs"].sum()) * 33 + 2 * n_opt
+        extra["formant_optimizer"] = {"metric": "optimiser_runs_per_second", "value": float(ro["runs"].sum()) / dt, "unit": "runs/s",
+                                      "config": {"workload": f"{n_opt} vowels x <= {runs_opt} greedy runs (33 candidates each), 938-bin formant grid"},
+                                      "candidate_evaluations_per_second": evals / dt, "cpu_baseline": None}
+        n_lf = 1024
+        fr_lf = g["frames"][[vowels[i % len(vowels)] for i in range(n_lf)]]
+        lf = np.tile(np.array([[300.0, 120.0, 0.5, 3.0, 0.02]]), (n_lf, 1)); lf[:, 1] = np.linspace(90.0, 220.0, n_lf)
+        ctx.synthesize_vowels_lf(fr_lf[:8], lf[:8], True)
+        t0 = time.perf_counter()
+        a_lf = ctx.synthesize_vowels_lf(fr_lf, lf, True)
+        dt = time.perf_counter() - t0
+        extra["lf_vowels"] = {"metric": "lf_vowels_per_second", "value": n_lf / dt, "unit": "vowels/s (0.65 s each, 22.05 kHz)",
+                              "config": {"workload": f"{n_lf} long vowels, host API incl. pulse trains and copies"}, "cpu_baseline": None}
+        if not args.no_cpu_baseline:
+            try:
+                from oracle.pyoracle import Ref
+                r22 = Ref(22)
+                t0 = time.perf_counter()
+                _, _, _, rr, _, _ = r22.optimize_formants_vowel(p0[0], tg[0], 1.0, 0.0, None, 2)
+                extra["formant_optimizer"]["cpu_baseline"] = {"value": rr / (time.perf_counter() - t0), "unit": "runs/s", "cores": 1,
+                                                              "kind": "reference", "sample": "1 vowel x 2 runs (Data.cpp loop over the reference classes)"}
+                t0 = time.perf_counter()
+                ref_a = [r22.synthesize_vowel_lf(fr_lf[i:i + 1], lf[i], 1)[0] for i in range(8)]
+                extra["lf_vowels"]["cpu_baseline"] = {"value": 8 / (time.perf_counter() - t0), "unit": "vowels/s", "cores": 1,
+                                                      "kind": "reference", "sample": "8 long vowels"}
+                assert all(np.array_equal(ref_a[i], a_lf[i]) for i in range(8)), "LF vowels differ from the reference"
+            except (FileNotFoundError, OSError):
+                pass
 
     if world > 1:
         dist.barrier()
@@ -438,7 +487,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": tds_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": tds_tflops / fp64_peak, "traffic": None,
+                     "frac": tds_tflops / fp64_peak, "traffic": TDS_TRAFFIC_BYTES,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch size (profiles/r1c_tds_ncu.txt); algorithmic output is 722.5 MB",
                      "kernel": "tds_batch_kernel", "flop_per_tract_step": W_TDS,
                      "peak_source": "afs_probe_fp64_tflops, measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "hbm_gbs_algorithmic": B_TDS * n_out * 8 / (ms_step * 1e-3) / 1e9,
@@ -448,6 +498,7 @@ def run_ours(args):
         "gather": {"collective": "all_gather of the audio [B, n_out] f64 over NCCL, after the compute", "ms": gather_ms,
                    "bytes_per_rank": int(B_TDS * n_out * 8),
                    "value_including_gather": audio_s_per_step / ((ms_step + gather_ms) * 1e-3)},
+        **extra,
         "raster": {"metric": "area_function_parameter_sets_per_second", "value": ra_value, "unit": "sets/s", "ms_per_step": ra_ms,
                    "config": {"workload": "onedim_area_function_to_frames_65536", "sets_per_gpu": B_RA},
                    "cpu_baseline": None if ra_cpu is None else {"value": ra_cpu, "unit": "sets/s", "cores": 1, "kind": "port",

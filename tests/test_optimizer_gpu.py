@@ -49,7 +49,7 @@ def test_optimizer_edge_cases(ctx, shapes):
     assert np.array_equal(r["params"], p) and np.all(r["runs"] == 1)
     # the initial error is evaluated in the state the TlModel is handed over in, everything later with the 8000 dPa
     # TlModel::getFormants leaves behind (TlModel.cpp:427): equal only when the model was "used" before
-    np.testing.assert_allclose(r["initial_error"], r["final_error"], rtol=1e-2)
+    assert np.all(r["initial_error"] != r["final_error"])
     o = afs.tl_options_default(); o.lung_pressure_dPa = 8000.0
     r = ctx.optimize_formants_vowel(p, t, 1.0, 0.0, np.ones(16, dtype=np.int32), 5, opts=o)
     assert np.array_equal(r["initial_error"], r["final_error"])
