@@ -14,12 +14,14 @@ from .api import (  # noqa: F401
     TdsOptions,
     TlOptions,
     area_function_to_frames,
+    audio_to_int16,
     chebyshev_lowpass,
     default_frames,
     library_path,
     load_library,
     tds_options_default,
     tl_options_default,
+    write_wav_int16,
 )
 
 __version__ = "0.1.0"

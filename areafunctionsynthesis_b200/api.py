@@ -88,6 +88,8 @@ def load_library():
     lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
     lib.afs_probe_fp64_tflops.argtypes = [vp, vp]
     lib.afs_chebyshev_lowpass.argtypes = [dbl, i32, vp, vp]
+    lib.afs_audio_to_int16.argtypes = [vp, C.c_int64, vp]
+    lib.afs_write_wav_int16.argtypes = [C.c_char_p, vp, C.c_int64, i32, i32]
     lib.afs_area_function_to_frame.argtypes = [vp, vp]
     lib.afs_area_functions_to_frames.argtypes = [vp, i32, vp, vp]
     lib.afs_area_functions_to_frames_device.argtypes = [vp, i32, vp, vp, vp]
@@ -147,6 +149,23 @@ def area_function_to_frames(params, frames=None):
     for i in range(len(p)):
         _check(lib, lib.afs_area_function_to_frame(_ptr(p[i]), _ptr(out[i:i + 1])))
     return out
+
+
+def audio_to_int16(audio):
+    """Synthesizer.cpp:955-965: double [-1, 1] -> int16 (truncation, clipping)."""
+    a = np.ascontiguousarray(audio, dtype=np.float64)
+    out = np.empty(a.shape, dtype=np.int16)
+    rc = load_library().afs_audio_to_int16(_ptr(a), a.size, _ptr(out))
+    if rc:
+        raise AfsError(f"afs_audio_to_int16: status {rc}")
+    return out
+
+
+def write_wav_int16(path, pcm, sample_rate_hz, n_channels=1):
+    p = np.ascontiguousarray(pcm, dtype=np.int16)
+    rc = load_library().afs_write_wav_int16(os.fsencode(path), _ptr(p), p.size // n_channels, int(n_channels), int(sample_rate_hz))
+    if rc:
+        raise AfsError(f"afs_write_wav_int16: status {rc}")
 
 
 def chebyshev_lowpass(cutoff_ratio, poles):

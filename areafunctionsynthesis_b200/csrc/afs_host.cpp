@@ -3,6 +3,8 @@
 // they produce INPUTS of it (filter coefficients, tube frames).
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <cstdint>
 #include <cstring>
 
 #include "../../include/afs_b200.h"
@@ -241,6 +243,39 @@ int lf_vowel_flow(const afs_lf_pulse *lf, int is_long, double sampling_rate_hz, 
 }  // namespace afs
 
 extern "C" {
+
+int afs_audio_to_int16(const double *audio, int64_t n, int16_t *pcm) {
+  if (n < 0 || (n > 0 && (!audio || !pcm))) return AFS_ERR_BAD_ARGUMENT;
+  for (int64_t i = 0; i < n; i++) {
+    const double v = audio[i];
+    int16_t s = (int16_t)(int)(v * 32767.0);  // Signal16::setValue((double)newSignal[i] * SHRT_MAX)
+    if (v > 1.0) s = 32767;
+    if (v < -1.0) s = -32768;
+    if (!(v == v)) s = 0;  // NaN: undefined in the reference, silence here
+    pcm[i] = s;
+  }
+  return AFS_OK;
+}
+
+int afs_write_wav_int16(const char *path, const int16_t *pcm, int64_t n_frames, int n_channels, int sample_rate_hz) {
+  if (!path || n_frames < 0 || n_channels < 1 || n_channels > 64 || sample_rate_hz < 1 || (n_frames > 0 && !pcm))
+    return AFS_ERR_BAD_ARGUMENT;
+  const uint64_t data_bytes = (uint64_t)n_frames * (uint64_t)n_channels * 2u;
+  if (data_bytes > 0xffffffffu - 36u) return AFS_ERR_BAD_ARGUMENT;  // RIFF sizes are 32 bit
+  FILE *fh = fopen(path, "wb");
+  if (!fh) return AFS_ERR_BAD_ARGUMENT;
+  unsigned char h[44];
+  auto le32 = [&](int at, uint32_t v) { for (int i = 0; i < 4; i++) h[at + i] = (unsigned char)(v >> (8 * i)); };
+  auto le16 = [&](int at, uint32_t v) { h[at] = (unsigned char)v; h[at + 1] = (unsigned char)(v >> 8); };
+  memcpy(h, "RIFF", 4); le32(4, 36u + (uint32_t)data_bytes); memcpy(h + 8, "WAVEfmt ", 8);
+  le32(16, 16); le16(20, 1); le16(22, (uint32_t)n_channels); le32(24, (uint32_t)sample_rate_hz);
+  le32(28, (uint32_t)sample_rate_hz * (uint32_t)n_channels * 2u); le16(32, (uint32_t)n_channels * 2u); le16(34, 16);
+  memcpy(h + 36, "data", 4); le32(40, (uint32_t)data_bytes);
+  bool ok = fwrite(h, 1, 44, fh) == 44;
+  if (ok && data_bytes) ok = fwrite(pcm, 1, (size_t)data_bytes, fh) == (size_t)data_bytes;  // little-endian host
+  ok = (fclose(fh) == 0) && ok;
+  return ok ? AFS_OK : AFS_ERR_BAD_ARGUMENT;
+}
 
 int afs_chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double *b) {
   if (!a || !b || num_poles < 2 || num_poles > 16 || (num_poles & 1) || !(cutoff_ratio > 0.0) || !(cutoff_ratio < 0.5))

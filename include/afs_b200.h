@@ -362,6 +362,13 @@ int afs_probe_fp64_tflops(afs_ctx *ctx, double *tflops);
  * coefficients a[0..num_poles], b[0..num_poles] (b[0] = 0) for
  * y[n] = sum a_i x[n-i] + sum b_i y[n-i].  num_poles even, <= 16. */
 int afs_chebyshev_lowpass(double cutoff_ratio, int num_poles, double *a, double *b);
+
+/* The int16 conversion of Synthesizer::synthesizeSegment (Synthesizer.cpp:955-965): sample * SHRT_MAX truncated
+ * towards zero, clipped to SHRT_MAX / SHRT_MIN outside [-1, 1].  n samples. */
+int afs_audio_to_int16(const double *audio, int64_t n, int16_t *pcm);
+/* On-disk replacement of the reference's PortAudio ring buffer (Synthesizer.cpp:955-973, 1429-1483): a
+ * canonical 16-bit PCM RIFF/WAVE file, `n_frames` sample frames of `n_channels` interleaved channels. */
+int afs_write_wav_int16(const char *path, const int16_t *pcm, int64_t n_frames, int n_channels, int sample_rate_hz);
 /* OneDimAreaFunction::calculateOneDimTubeFunction (OneDimAreaFunction.cpp:
  * 23-138): 16 parameters (Llar, Alar, powLar, xp, Ap, powP, xc, Ac, powC, xa,
  * Aa, powA, xin, Ain, Lvt, Alip) -> the 40 pharynx/mouth sections of `frame`

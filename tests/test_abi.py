@@ -76,3 +76,22 @@ def test_bad_arguments_are_reported_not_printed():
     assert lib.afs_chebyshev_lowpass(0.2, 7, None, None) == 3
     assert lib.afs_area_function_to_frame(None, None) == 3
     assert b"bad argument" in lib.afs_status_string(3)
+
+
+def test_int16_conversion_and_wav_writer(tmp_path):
+    """Synthesizer.cpp:955-965 (sample * SHRT_MAX truncated, clipped outside [-1, 1]) and the on-disk output format."""
+    import wave
+    x = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 1.5, -1.5, 0.99999, -0.99999, 1e-6, -3.0517578125e-05, 0.25000763])
+    pcm = afs.audio_to_int16(x)
+    want = np.trunc(x * 32767.0)
+    want[x > 1.0] = 32767; want[x < -1.0] = -32768
+    assert np.array_equal(pcm, want.astype(np.int16))
+    rng = np.random.default_rng(0)
+    stereo = (rng.standard_normal((1000, 2)) * 8000).astype(np.int16)
+    path = str(tmp_path / "out.wav")
+    afs.write_wav_int16(path, stereo, 22050, n_channels=2)
+    with wave.open(path, "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (2, 2, 22050, 1000)
+        assert np.array_equal(np.frombuffer(w.readframes(1000), dtype="<i2").reshape(1000, 2), stereo)
+    with pytest.raises(afs.AfsError):
+        afs.write_wav_int16(str(tmp_path / "no_such_dir" / "x.wav"), stereo, 22050)
