@@ -261,6 +261,23 @@ def test_fast_arithmetic_types_sections_options(ctx, shapes):
                           ctx.tl_sweep(fr, F0_938, 938, spectrum_type=4, section=0, opts=b)[1])
 
 
+def test_fast_arithmetic_full_size_properties(ctx):
+    """BASELINE config 2 size (4096 x 2048) through the fast kernel: a pure function of each tube (order / split
+    invariance, bit for bit), finite everywhere, bin 0 aliases bin 1, and within the stated bar of the bit-identical
+    kernel over all 8.4 M points."""
+    fr = random_frames(4096, seed=20260001)
+    a, b = _fast_opts()
+    rf, jf = ctx.tl_sweep(fr, F0_2048, 2048, opts=b)
+    assert np.isfinite(rf).all() and np.isfinite(jf).all()
+    perm = np.random.default_rng(2).permutation(4096)[:777]
+    r2, j2 = ctx.tl_sweep(fr[perm], F0_2048, 2048, opts=b)
+    assert np.array_equal(rf[perm], r2) and np.array_equal(jf[perm], j2)
+    assert np.array_equal(rf[:, 0], rf[:, 1]) and np.array_equal(jf[:, 0], jf[:, 1])
+    re, im = ctx.tl_sweep(fr, F0_2048, 2048, opts=a)
+    rel = np.hypot(rf - re, jf - im) / np.hypot(re, im)
+    assert rel.max() <= 1e-8 and np.quantile(rel[::7].ravel(), 0.999) <= 1e-9
+
+
 def test_fast_arithmetic_formants(ctx, shapes):
     a, b = _fast_opts()
     fr = shapes["frames"]
