@@ -17,6 +17,7 @@ from .api import (  # noqa: F401
     audio_to_int16,
     chebyshev_lowpass,
     default_frames,
+    lf_glottal_flow,
     library_path,
     load_library,
     tds_options_default,

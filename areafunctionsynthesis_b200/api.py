@@ -81,6 +81,7 @@ def load_library():
     lib.afs_optimize_formants_vowel.argtypes = [vp, vp, i32, vp, vp, dbl, dbl, vp, i32, dbl, i32, vp, vp, vp, vp, vp]
     lib.afs_synthesize_vowels_lf.argtypes = [vp, vp, i32, vp, vp, i32, dbl, vp, vp]
     lib.afs_lf_vowel_length.argtypes = [i32, dbl]
+    lib.afs_lf_glottal_flow.argtypes = [vp, i32, dbl, vp]
     lib.afs_tl_impulse_response.argtypes = [vp, vp, i32, vp, dbl, i32, vp]
     lib.afs_tl_impulse_response_device.argtypes = [vp, vp, i32, vp, dbl, i32, vp, vp]
     lib.afs_tds_synthesize.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp]
@@ -149,6 +150,18 @@ def area_function_to_frames(params, frames=None):
     for i in range(len(p)):
         _check(lib, lib.afs_area_function_to_frame(_ptr(p[i]), _ptr(out[i:i + 1])))
     return out
+
+
+def lf_glottal_flow(lf5, is_long=True, sampling_rate_hz=22050.0):
+    """Host helper: the LF pulse train of one vowel (lf5 = AMP, F0, OQ, SQ, TL)."""
+    lib = load_library()
+    lf = np.ascontiguousarray(lf5, dtype=np.float64)
+    n = int(lib.afs_lf_vowel_length(int(bool(is_long)), float(sampling_rate_hz)))
+    flow = np.zeros(n)
+    rc = lib.afs_lf_glottal_flow(_ptr(lf), int(bool(is_long)), float(sampling_rate_hz), _ptr(flow))
+    if rc:
+        raise AfsError(f"afs_lf_glottal_flow: status {rc}")
+    return flow
 
 
 def audio_to_int16(audio):

@@ -297,6 +297,9 @@ int afs_lf_vowel_length(int is_long_vowel, double sampling_rate_hz);
  * output before the filter.  With REFERENCE arithmetic the int16 samples are identical to the reference's.
  * AFS_ERR_BAD_ARGUMENT when a pulse would not fit the reference's 2048-sample ring buffer (F0 below rate / 1024).
  */
+/* Host helper (no device work): the glottal flow (LF pulse train) of one vowel, flow [afs_lf_vowel_length]:
+ * LfPulse::getPulse per period with the F0 / amplitude contours and flutter of Synthesizer.cpp:667-771. */
+int afs_lf_glottal_flow(const afs_lf_pulse *pulse, int is_long_vowel, double sampling_rate_hz, double *flow);
 int afs_synthesize_vowels_lf(afs_ctx *ctx, const afs_tl_options *opts, int n_vowels, const afs_tube_frame *tubes,
                              const afs_lf_pulse *pulses, int is_long_vowel, double sampling_rate_hz, int16_t *audio,
                              double *pressure);

@@ -142,10 +142,12 @@ class Ref:
         """Synthesizer::synthesizeVowelLf restated over the reference classes: (int16 audio, float64 pressure)."""
         opts = opts or tl_options_default()
         n = self.lib.ref_lf_vowel_length(int(is_long))
-        out = np.zeros(n, dtype=np.int16); pr = np.zeros(n)
+        out = np.zeros(n, dtype=np.int16); pr = np.zeros(n); fl = np.zeros(n)
         lf = np.ascontiguousarray(lf5, dtype=np.float64)
-        m = self.lib.ref_synthesize_vowel_lf(C.byref(opts), _ptr(np.ascontiguousarray(frame)), _ptr(lf), int(is_long), _ptr(out), _ptr(pr))
+        m = self.lib.ref_synthesize_vowel_lf(C.byref(opts), _ptr(np.ascontiguousarray(frame)), _ptr(lf), int(is_long), _ptr(out),
+                                             _ptr(pr), _ptr(fl))
         assert m == n
+        self.last_flow = fl
         return out, pr
 
     def tl_impulse_response(self, frames, length_exponent=9, opts=None):

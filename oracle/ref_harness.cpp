@@ -290,7 +290,7 @@ int ref_lf_vowel_length(int isLongVowel) {
 }
 
 int ref_synthesize_vowel_lf(const afs_tl_options *opts, const afs_tube_frame *tubeFrame, const double *lf5,
-                            int isLongVowel, int16_t *out, double *pressure_out) {
+                            int isLongVowel, int16_t *out, double *pressure_out, double *flow_out) {
   TlModel *tlModel = new TlModel();
   set_tl_options(tlModel, opts);
   frame_to_tube(tubeFrame, &tlModel->tube);
@@ -359,6 +359,7 @@ int ref_synthesize_vowel_lf(const afs_tl_options *opts, const afs_tube_frame *tu
     filteredValue = 2000.0 * filter.getOutputSample(pressureSignal.getValue(i));
     out[i] = (short)filteredValue;
     if (pressure_out) pressure_out[i] = sum;
+    if (flow_out) flow_out[i] = pulseSignal.x[i & BUFFER_MASK];
   }
   delete tlModel;
   return length;

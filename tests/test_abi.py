@@ -95,3 +95,16 @@ def test_int16_conversion_and_wav_writer(tmp_path):
         assert np.array_equal(np.frombuffer(w.readframes(1000), dtype="<i2").reshape(1000, 2), stereo)
     with pytest.raises(afs.AfsError):
         afs.write_wav_int16(str(tmp_path / "no_such_dir" / "x.wav"), stereo, 22050)
+
+
+def test_lf_pulse_train_matches_reference():
+    """Host side of afs_synthesize_vowels_lf: LfPulse::getPulse / TimeFunction::getValue / flutter
+    (LfPulse.cpp:37-245, TimeFunction.cpp:77-133, Synthesizer.cpp:667-771) -- bit-identical to the pulse signal of the
+    reference run that produced tests/golden/lf_vowels.npz."""
+    g = load_golden("lf_vowels.npz")
+    for is_long in (1, 0):
+        for k in range(len(g["lf"])):
+            flow = afs.lf_glottal_flow(g["lf"][k], bool(is_long))
+            assert np.array_equal(flow[::4], g[f"flow_{is_long}"][k]), (is_long, k)
+    with pytest.raises(afs.AfsError):
+        afs.lf_glottal_flow([300.0, 5.0, 0.5, 3.0, 0.02])  # pulse longer than the reference's ring buffer

@@ -26,7 +26,11 @@ def main():
     r = Ref(22)
     out = {"sel": sel, "lf": lf}
     for is_long in (1, 0):
-        a = [r.synthesize_vowel_lf(g["frames"][i:i + 1], lf[k], is_long) for k, i in enumerate(sel)]
+        a, fl = [], []
+        for k, i in enumerate(sel):
+            a.append(r.synthesize_vowel_lf(g["frames"][i:i + 1], lf[k], is_long))
+            fl.append(r.last_flow.copy())
+        out[f"flow_{is_long}"] = np.stack(fl)[:, ::4].copy()  # glottal flow (pulse train), every 4th sample, exact values
         out[f"audio_{is_long}"] = np.stack([x[0] for x in a])
         out[f"pressure_{is_long}"] = np.stack([x[1] for x in a])[:, ::16].copy()  # every 16th sample, exact values
         print(is_long, out[f"audio_{is_long}"].shape, out[f"audio_{is_long}"].min(), out[f"audio_{is_long}"].max())
