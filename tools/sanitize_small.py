@@ -1,5 +1,5 @@
-"""Small invocations of every kernel for compute-sanitizer (scratch tool):
-   compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+"""Small invocations of every kernel for smoke / memcheck purposes (scratch tool; compute-sanitizer is closed on the GPU pool):
+   python tools/sanitize_small.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
