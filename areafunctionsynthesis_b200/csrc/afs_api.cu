@@ -20,8 +20,8 @@ struct afs_ctx {
   int64_t launches = 0;
   char last_error[256] = {0};
   // grow-only device scratch
-  void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void *scratch[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int sm_count = 0;
   int dump_step = 0;          // diagnostics, see afs_tds_set_state_dump
   double *dump_host = nullptr;
@@ -118,7 +118,7 @@ int afs_destroy(afs_ctx *ctx) {
   if (!ctx) return AFS_OK;
   if (ctx->device >= 0) {
     cudaSetDevice(ctx->device);
-    for (int i = 0; i < 8; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 10; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; i++) if (ctx->chunk_done[i]) cudaEventDestroy(ctx->chunk_done[i]);
@@ -671,9 +671,28 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
     if ((rc = scratch(ctx, 6, 473 * sizeof(double), &d_dump))) return rc;
     CU(cudaMemsetAsync(d_dump, 0, 473 * sizeof(double), (cudaStream_t)stream));
   }
-  CU(launch_tds(L, (const int32_t *)d_bounds, d_tubes, d_glottis, d_seeds, d_audio, d_flow, d_status,
-                (double *)d_dump, ctx->dump_step, (cudaStream_t)stream));
-  ctx->launches++;
+  // Noise sources: the constriction records of the pre-pass (48 B per tract-step, 32 lanes per CTA) live in scratch
+  // slot 8; a batch whose records would exceed kNoiseScanBytes runs as several waves of CTAs that reuse the buffer.
+  const size_t per_cta = tds_noise_scan_bytes_per_cta(L);
+  const int lpc = tds_lanes_per_cta(L);
+  const int ctas = (n_tracts + lpc - 1) / lpc;
+  int wave_ctas = ctas;
+  void *d_nzc = nullptr;
+  if (per_cta) {
+    const size_t kNoiseScanBytes = (size_t)12 << 30;
+    if (per_cta > kNoiseScanBytes) return AFS_ERR_OUT_OF_MEMORY;  // a single utterance of > 2.9 h at 44.1 kHz
+    size_t fit = kNoiseScanBytes / per_cta;
+    if (fit >= (size_t)ctx->sm_count) fit -= fit % (size_t)ctx->sm_count;  // whole waves of one CTA per SM
+    if ((size_t)wave_ctas > fit) wave_ctas = (int)fit;
+    if ((rc = scratch(ctx, 8, per_cta * (size_t)wave_ctas, &d_nzc))) return rc;
+  }
+  for (int c0 = 0; c0 < ctas; c0 += wave_ctas) {
+    const int t0 = c0 * lpc;
+    const int nw = (c0 + wave_ctas >= ctas) ? n_tracts - t0 : wave_ctas * lpc;
+    CU(launch_tds(L, t0, nw, (const int32_t *)d_bounds, d_tubes, d_glottis, d_seeds, d_audio, d_flow, d_status,
+                  c0 == 0 ? (double *)d_dump : nullptr, ctx->dump_step, d_nzc, (cudaStream_t)stream));
+    ctx->launches += per_cta ? 2 : 1;
+  }
   if (d_dump) {
     CU(cudaMemcpyAsync(ctx->dump_host, d_dump, 473 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));

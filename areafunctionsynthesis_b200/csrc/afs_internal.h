@@ -55,9 +55,11 @@ struct TdsLaunch {
 };
 int tds_prepare_launch(const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
                        double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L);
-cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
+cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
-                       uint32_t *d_status, double *d_dump, int dump_step, cudaStream_t stream);
+                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, cudaStream_t stream);
+size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L);  // 0 without noise sources
+int tds_lanes_per_cta(const TdsLaunch &L);
 size_t tds_smem_bytes();
 
 // ---- area-function rasteriser -----------------------------------------------

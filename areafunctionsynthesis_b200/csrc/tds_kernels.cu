@@ -911,6 +911,22 @@ __device__ __forceinline__ void nzc_load(const TdsSmem &S, const int lane, int b
   }
 }
 
+// constriction records of step n from the pre-pass (tds_noise_scan_kernel) into the shared-memory buffer `buf`
+template <class KA>
+__device__ __forceinline__ void nzc_fetch(TdsSmem &S, const KA &A, const int lane, int total_steps, int n, int buf) {
+  const int hw_lane = threadIdx.x & 31;
+  const size_t base = ((size_t)blockIdx.x * (size_t)total_steps + (size_t)n) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    S.nzc_i[buf][k][lane] = __ldg(A.nzc_i + (base + k) * 32 + hw_lane);
+    S.nzc_f[buf][k][lane] = __ldg(A.nzc_f + (base + k) * 32 + hw_lane);
+  }
+}
+__device__ __forceinline__ uint32_t nzc_pack(const NoiseCons &c) {
+  return (uint32_t)(c.valid & 1) | ((uint32_t)(c.kind & 3) << 1) | ((uint32_t)(c.teeth & 1) << 3) | ((uint32_t)(c.lateral & 1) << 4) |
+         ((uint32_t)(c.nar + 1) << 8) | ((uint32_t)c.up << 16);
+}
+
 // glibc srand() (stdlib/random_r.c, TYPE_3): the reference draws from libc rand() (TdsModel.cpp:1690-1696); every
 // tract owns a private generator.
 __device__ __noinline__ void rng_seed(TdsSmem &S, const int lane, uint32_t seed, int &ri) {
@@ -936,6 +952,29 @@ __device__ __forceinline__ uint32_t rng_next(TdsSmem &S, const int lane, int &ri
   S.rng[ri][lane] = v;
   ri = ri == 33 ? 0 : ri + 1;
   return v >> 1;
+}
+
+// Twelve successive rng_next() calls summed with the reference's int wrap-around (TdsModel.cpp:1690-1696).  The
+// additive lagged-Fibonacci recurrence r[i] = r[i-3] + r[i-31] lets all operands be loaded up front (the fifteen old
+// words the twelve new ones depend on, three of the new ones feeding later ones from registers), so the loads
+// pipeline instead of forming twelve serial load-load-store chains through shared memory.
+__device__ __forceinline__ uint32_t rng_sum12(TdsSmem &S, const int lane, int &ri) {
+  uint32_t a[12], m[3], o[12];
+#pragma unroll
+  for (int q = 0; q < 12; q++) { int i = ri + 3 + q; if (i >= 34) i -= 34; a[q] = S.rng[i][lane]; }
+#pragma unroll
+  for (int q = 0; q < 3; q++) { int i = ri + 31 + q; if (i >= 34) i -= 34; m[q] = S.rng[i][lane]; }
+  uint32_t isum = 0;
+#pragma unroll
+  for (int q = 0; q < 12; q++) {
+    o[q] = a[q] + (q < 3 ? m[q] : o[q < 3 ? 0 : q - 3]);
+    isum += o[q] >> 1;
+  }
+#pragma unroll
+  for (int q = 0; q < 12; q++) { int i = ri + q; if (i >= 34) i -= 34; S.rng[i][lane] = o[q]; }
+  ri += 12;
+  if (ri >= 34) ri -= 34;
+  return isum;
 }
 
 // exp(t) for -0.75 <= t <= 0 (cutoff <= 2000 Hz at fs >= 16.8 kHz), Taylor series to full double accuracy; libm exp else
@@ -1135,8 +1174,7 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
     if ((old >= 0.001) && (a < 0.001)) out = 0.0;
     if (a >= 0.001) {
       const double x = exp_small(-2.0 * kPi * (cut * P.dt));  // IirFilter::createSinglePoleLowpass (IirFilter.cpp:235-243)
-      uint32_t isum = 0;  // 12 x rand() summed in an int: wraps around like the reference's
-      for (int q = 0; q < 12; q++) isum += rng_next(S, lane, N.ri);
+      const uint32_t isum = rng_sum12(S, lane, N.ri);  // 12 x rand() summed in an int: wraps around like the reference's
       double in = (double)(int32_t)isum;
       in = (in * (1.0 / 2147483647.0) - 6.0) * 0.28867513459481288225;  // / RAND_MAX, - 6, / sqrt(12)
       out = __dadd_rn(__dmul_rn(__dsub_rn(1.0, x), in), __dmul_rn(x, out));
@@ -1432,6 +1470,9 @@ struct KArgs {
   uint32_t *status;
   double *dump;
   const uint32_t *seeds;
+  // noise sources: constriction records of every (CTA, step) from tds_noise_scan_kernel, [cta][step][4][32]
+  uint32_t *nzc_i;
+  double *nzc_f;
 };
 
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
@@ -1524,21 +1565,12 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
 
   int interval = 0, i0 = 0, i1 = 0;
   double inv_len = 1.0;
-  unsigned long long latAlways = 0, latMaybe = 0;  // X2: laterality classes of the sections in this interval
-  auto lat_masks = [&](int iv) {
-    latAlways = 0; latMaybe = 0;
-    for (int j = 0; j < AFS_NUM_PM_SECTIONS; j++) {
-      const double a = my_frames[iv].laterality[j], b = my_frames[iv + 1].laterality[j];
-      if (a > 0.1000001 && b > 0.1000001) latAlways |= 1ull << j;
-      else if (!(a < 0.0999999 && b < 0.0999999)) latMaybe |= 1ull << j;
-    }
-  };
   if (T > 0) {
     i0 = A.bounds[0]; i1 = A.bounds[1];
     inv_len = 1.0 / (double)(i1 - i0);
-    if ((ROLE == 3 || ROLE == 2) && NOISE) lat_masks(0);
     stage_interval(S, lane, warp, my_frames, my_glottis, 0, NOISE);
     cta_sync();
+    if (ROLE == 2 && NOISE) nzc_fetch(S, A, lane, T, 0, 0);  // constrictions of step 0 for warp X2
     if (ROLE == 2) {  // glottis geometry of step 0
       double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
@@ -1559,7 +1591,6 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       interval++;
       i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
       inv_len = 1.0 / (double)(i1 - i0);
-      if ((ROLE == 3 || ROLE == 2) && NOISE) lat_masks(interval);
       stage_interval(S, lane, warp, my_frames, my_glottis, interval, NOISE);
       cta_sync();
     }
@@ -1581,22 +1612,16 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
       }
     }
-    if (ROLE == 2 && NOISE && n + 1 < i1 && n + 1 < T) {
-      // constrictions of step n+1 for warp X2 (same control interval: its frames are staged); runs beside X2's source
-      // stage of step n, the two meet at the end-of-step barrier
-      const double re = __ddiv_rn((double)(n + 1 - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);
-      NoiseCons cons[4];
-      noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, latAlways, latMaybe, cons);
-      nzc_store(S, lane, (n + 1) & 1, cons);
+    if (ROLE == 2 && NOISE && n + 1 < T) {
+      // constrictions of step n+1 for warp X2: found by the pre-pass kernel (they depend on the geometry of the step
+      // only), fetched one step ahead beside X2's source stage of step n; the two meet at the end-of-step barrier
+      nzc_fetch(S, A, lane, T, n + 1, (n + 1) & 1);
     }
     if (ROLE == 3 && NOISE && X.rows) {  // noise sources of step n (needs the update of the radiation currents above)
       const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
       NoiseCons cons[4];
 #ifndef AFS_NZ_SKIP_SCAN
-      // constrictions: found by X1 during the previous step, except on the first step of a control interval (the
-      // frames were not staged yet)
-      if (n == i0) noise_scan(S, lane, re, re1, my_frames + interval, my_frames + interval + 1, latAlways, latMaybe, cons);
-      else nzc_load(S, lane, n & 1, cons);
+      nzc_load(S, lane, n & 1, cons);
 #else
       for (int k = 0; k < 4; k++) { cons[k].valid = k == 0; cons[k].nar = -1; cons[k].kind = 0; cons[k].up = 3; cons[k].teeth = 0; cons[k].lateral = 0; cons[k].downF = 0.3; }
 #endif
@@ -1764,6 +1789,51 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
 }
 static_assert(NSEP == NW, "prologue zeroing assumes NSEP == NW");
 
+// ==================================================================================
+// Noise-source pre-pass: TdsModel::calcNoiseSources, state-independent part (TdsModel.cpp:1188-1430)
+// ==================================================================================
+// Which sections form a constriction and where its obstacle sits depends on the GEOMETRY of a step only, not on the
+// acoustic state.  Inside the time loop the scan cost one warp 27 k cycles per step (the other fifteen waited for
+// it); here every (tract, step) pair is independent: the same CTA <-> tract mapping as tds_batch_kernel, lane =
+// tract, the sixteen warps of a CTA take the steps of a control interval round robin.  Records (48 B per tract-step)
+// go to global memory in [cta][step][4][32] layout and are fetched one step ahead by warp X1.
+__global__ void __launch_bounds__(TDS_THREADS, 1)
+tds_noise_scan_kernel(const TdsParams P, const KArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TdsSmem &S = *reinterpret_cast<TdsSmem *>(smem_raw);
+  const int hw_lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = hw_lane < LANES ? hw_lane : LANES - 1;
+  const int tract_raw = blockIdx.x * P.lanes_per_cta + min(lane, P.lanes_per_cta - 1);
+  const int tract = tract_raw < P.n_tracts ? tract_raw : P.n_tracts - 1;
+  const afs_tube_frame *my_frames = A.tubes + (size_t)tract * P.n_frames;
+  const double *my_glottis = A.glottis + (size_t)tract * P.n_frames * AFS_NUM_GLOTTIS_CONTROL;
+  const int T = P.total_steps;
+  for (int iv = 0; iv + 1 < P.n_frames; iv++) {
+    const int i0 = A.bounds[iv], i1 = A.bounds[iv + 1];
+    __syncthreads();  // every warp is past its last read of the previous interval's frames
+    stage_interval(S, lane, warp, my_frames, my_glottis, iv, true);
+    // laterality classes of the sections in this interval (only `max > 0.1` matters, TdsModel.cpp:1545)
+    unsigned long long latAlways = 0, latMaybe = 0;
+    for (int j = 0; j < AFS_NUM_PM_SECTIONS; j++) {
+      const double a = my_frames[iv].laterality[j], b = my_frames[iv + 1].laterality[j];
+      if (a > 0.1000001 && b > 0.1000001) latAlways |= 1ull << j;
+      else if (!(a < 0.0999999 && b < 0.0999999)) latMaybe |= 1ull << j;
+    }
+    __syncthreads();
+    for (int n = i0 + warp; n < i1 && n < T; n += NW) {
+      const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
+      NoiseCons cons[4];
+      noise_scan(S, lane, re, re1, my_frames + iv, my_frames + iv + 1, latAlways, latMaybe, cons);
+      const size_t base = ((size_t)blockIdx.x * (size_t)T + (size_t)n) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        A.nzc_i[(base + k) * 32 + hw_lane] = nzc_pack(cons[k]);
+        A.nzc_f[(base + k) * 32 + hw_lane] = cons[k].downF;
+      }
+    }
+  }
+}
+
 // ---- host side ------------------------------------------------------------------
 int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, const int32_t *frame_len,
                        double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L) {
@@ -1826,12 +1896,26 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   return AFS_OK;
 }
 
-cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
+size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L) {
+  TdsParams P;
+  memcpy(&P, L.params.data(), sizeof P);
+  return P.noise ? (size_t)P.total_steps * 4 * 32 * (sizeof(uint32_t) + sizeof(double)) : 0;
+}
+int tds_lanes_per_cta(const TdsLaunch &L) {
+  TdsParams P;
+  memcpy(&P, L.params.data(), sizeof P);
+  return P.lanes_per_cta;
+}
+
+// Tracts [tract0, tract0 + n_wave) of the batch (one launch; the caller splits a batch into waves when the noise
+// pre-pass records of all its CTAs would not fit `d_nzc`).
+cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
-                       uint32_t *d_status, double *d_dump, int dump_step, cudaStream_t stream) {
+                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, cudaStream_t stream) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
+  P.n_tracts = n_wave;
   static_assert(sizeof(TdsSmem) <= 227 * 1024, "TdsSmem exceeds the 227 KB a CTA can have on sm_100a");
   const bool opt = P.transvelar || P.var_loss;  // non-default options: separate instantiations, like the noise sources
   auto kernel = P.noise ? (opt ? tds_batch_kernel<true, true> : tds_batch_kernel<true, false>)
@@ -1840,7 +1924,26 @@ cudaError_t launch_tds(const TdsLaunch &L, const int32_t *d_bounds, const afs_tu
                                        (int)sizeof(TdsSmem));  // per device; cheap
   if (e != cudaSuccess) return e;
   const int ctas = (P.n_tracts + P.lanes_per_cta - 1) / P.lanes_per_cta;
-  KArgs A{d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, d_dump, d_seeds};
+  const size_t n_out = (size_t)(P.total_steps / P.sr_factor);
+  KArgs A{d_bounds,
+          d_tubes + (size_t)tract0 * P.n_frames,
+          d_glottis + (size_t)tract0 * P.n_frames * AFS_NUM_GLOTTIS_CONTROL,
+          d_audio + (size_t)tract0 * n_out,
+          d_flow ? d_flow + (size_t)tract0 * (size_t)P.total_steps : nullptr,
+          d_status ? d_status + tract0 : nullptr,
+          d_dump,
+          d_seeds ? d_seeds + tract0 : nullptr,
+          nullptr, nullptr};
+  if (P.noise) {
+    if (!d_nzc) return cudaErrorInvalidValue;
+    A.nzc_i = (uint32_t *)d_nzc;
+    A.nzc_f = (double *)((unsigned char *)d_nzc + (size_t)ctas * (size_t)P.total_steps * 4 * 32 * sizeof(uint32_t));
+    e = cudaFuncSetAttribute(tds_noise_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TdsSmem));
+    if (e != cudaSuccess) return e;
+    tds_noise_scan_kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, A);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, A);
   return cudaGetLastError();
 }
