@@ -944,16 +944,6 @@ __device__ __noinline__ void rng_seed(TdsSmem &S, const int lane, uint32_t seed,
   for (int i = 34; i < 344; i++) S.rng[i % 34][lane] = S.rng[(i - 31) % 34][lane] + S.rng[(i - 3) % 34][lane];
   ri = 310 % 34;  // the oldest value
 }
-__device__ __forceinline__ uint32_t rng_next(TdsSmem &S, const int lane, int &ri) {
-  int i3 = ri + 3, i31 = ri + 31;
-  if (i3 >= 34) i3 -= 34;
-  if (i31 >= 34) i31 -= 34;
-  const uint32_t v = S.rng[i3][lane] + S.rng[i31][lane];
-  S.rng[ri][lane] = v;
-  ri = ri == 33 ? 0 : ri + 1;
-  return v >> 1;
-}
-
 // Twelve successive rng_next() calls summed with the reference's int wrap-around (TdsModel.cpp:1690-1696).  The
 // additive lagged-Fibonacci recurrence r[i] = r[i-3] + r[i-31] lets all operands be loaded up front (the fifteen old
 // words the twelve new ones depend on, three of the new ones feeding later ones from registers), so the loads
@@ -977,16 +967,20 @@ __device__ __forceinline__ uint32_t rng_sum12(TdsSmem &S, const int lane, int &r
   return isum;
 }
 
-// exp(t) for -0.75 <= t <= 0 (cutoff <= 2000 Hz at fs >= 16.8 kHz), Taylor series to full double accuracy; libm exp else
+// exp(t) for -0.75 <= t <= 0 (cutoff <= 2000 Hz at fs >= 16.8 kHz): Taylor polynomial of degree 17 (full double
+// accuracy on that range), evaluated by Estrin's scheme -- five dependent levels instead of seventeen: warp X2 runs
+// alone on the critical path of a step, so latency is what counts; libm exp else
 __device__ __forceinline__ double exp_small(double t) {
   if (t < -0.75) return exp(t);
-  double y = 1.0 / 355687428096000.0;  // 1/17!
-  const double c[17] = {1.0 / 20922789888000.0, 1.0 / 1307674368000.0, 1.0 / 87178291200.0, 1.0 / 6227020800.0,
-                        1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
-                        1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
-#pragma unroll
-  for (int i = 0; i < 17; i++) y = fma(y, t, c[i]);
-  return y;
+  const double t2 = t * t, t4 = t2 * t2, t8 = t4 * t4, t16 = t8 * t8;
+  const double p0 = fma(t, 1.0, 1.0), p1 = fma(t, 1.0 / 6.0, 0.5), p2 = fma(t, 1.0 / 120.0, 1.0 / 24.0),
+               p3 = fma(t, 1.0 / 5040.0, 1.0 / 720.0), p4 = fma(t, 1.0 / 362880.0, 1.0 / 40320.0),
+               p5 = fma(t, 1.0 / 39916800.0, 1.0 / 3628800.0), p6 = fma(t, 1.0 / 6227020800.0, 1.0 / 479001600.0),
+               p7 = fma(t, 1.0 / 1307674368000.0, 1.0 / 87178291200.0),
+               p8 = fma(t, 1.0 / 355687428096000.0, 1.0 / 20922789888000.0);
+  const double q0 = fma(t2, p1, p0), q1 = fma(t2, p3, p2), q2 = fma(t2, p5, p4), q3 = fma(t2, p7, p6);
+  const double o0 = fma(t4, q1, q0), o1 = fma(t4, q3, q2);
+  return fma(t16, p8, fma(t8, o1, o0));
 }
 // Tube::interpolate (Tube.cpp:449-466) exactly as the reference rounds it
 __device__ __forceinline__ double nz_lerp(double r1, double a, double r, double b) { return __dadd_rn(__dmul_rn(r1, a), __dmul_rn(r, b)); }
