@@ -679,7 +679,11 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   int wave_ctas = ctas;
   void *d_nzc = nullptr;
   if (per_cta) {
-    const size_t kNoiseScanBytes = (size_t)12 << 30;
+    size_t kNoiseScanBytes = (size_t)12 << 30;
+    if (const char *env = getenv("AFS_NOISE_SCAN_BYTES")) {  // (tests force several waves with a small budget)
+      const unsigned long long v = strtoull(env, nullptr, 10);
+      if (v >= per_cta) kNoiseScanBytes = (size_t)v;
+    }
     if (per_cta > kNoiseScanBytes) return AFS_ERR_OUT_OF_MEMORY;  // a single utterance of > 2.9 h at 44.1 kHz
     size_t fit = kNoiseScanBytes / per_cta;
     if (fit >= (size_t)ctx->sm_count) fit -= fit % (size_t)ctx->sm_count;  // whole waves of one CTA per SM

@@ -238,3 +238,29 @@ def test_transvelar_coupling_and_variable_entrance_loss(ctx, oracle, shapes, tv,
     a0, _ = oracle.tds_synthesize(fr[:4], gl[:4], fl, 44100.0, 2, opts=oracle_opts(noise=noise), seeds=seeds[:4], want_flow=False)
     if tv or loss == 2:
         assert rel_err(ao[:4], a0) > 1e-3
+
+
+def test_noise_prepass_waves(ctx, shapes, monkeypatch):
+    """The constriction records of the noise pre-pass live in a bounded device buffer; a batch that does not fit runs
+    as several waves of CTAs.  Forced here with a tiny budget: results identical to the single-wave run, and to the
+    same utterances run one by one (every tract depends on its own inputs and seed only)."""
+    import areafunctionsynthesis_b200 as afs
+    n = len(shapes["names"])
+    rng = np.random.default_rng(3)
+    B = 700  # 5 tracts per CTA on 148 SMs -> 140 CTAs
+    idx = rng.integers(0, n, size=(B, 2))
+    fr = np.stack([shapes["frames"][idx[:, 0]], shapes["frames"][n + idx[:, 1]]], axis=1)
+    gl = np.tile(np.array([[120.0, 8000.0, 0.01, 0.01, 0.0, -40.0], [160.0, 8000.0, 0.01, 0.01, 0.0, -40.0]]), (B, 1, 1))
+    gl[:, :, 0] += rng.uniform(-30, 60, size=(B, 1))
+    seeds = rng.integers(1, 2**31 - 1, size=B).astype(np.uint32)
+    o = afs.tds_options_default(noise=True)
+    a0, _, st0 = ctx.tds_synthesize(fr, gl, [150], 44100.0, 2, opts=o, seeds=seeds)
+    assert not st0.any() and np.abs(a0).max() > 0
+    per_cta = 300 * 4 * 32 * 12  # record bytes of one CTA for 300 steps
+    monkeypatch.setenv("AFS_NOISE_SCAN_BYTES", str(per_cta * 37))  # 37 CTAs per wave -> 4 waves
+    a1, _, st1 = ctx.tds_synthesize(fr, gl, [150], 44100.0, 2, opts=o, seeds=seeds)
+    monkeypatch.delenv("AFS_NOISE_SCAN_BYTES")
+    assert np.array_equal(a0, a1) and not st1.any()
+    for b in (0, 4, 5, 699):
+        ab, _, _ = ctx.tds_synthesize(fr[b:b + 1], gl[b:b + 1], [150], 44100.0, 2, opts=o, seeds=seeds[b:b + 1])
+        assert np.array_equal(ab[0], a0[b]), b
