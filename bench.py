@@ -192,7 +192,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -211,7 +211,6 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the ONE JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = afs.Context(local)
@@ -522,9 +521,28 @@ def run_ours(args):
                                                 "note": "flops the ladder formulation executes (DESIGN.md K2f), not the 8.0e3 of the reference-like formulation"},
                                    "error": tlf_err}},
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Native libraries write to fd 1 (NCCL prints its version banner there): point fd 1 at stderr until the ONE JSON
+    line is due, so that stdout carries nothing else."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -538,6 +556,7 @@ def main():
     args = ap.parse_args()
     global T_SEC
     T_SEC = args.utt_seconds
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
