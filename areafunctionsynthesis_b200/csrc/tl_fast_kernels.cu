@@ -1,4 +1,4 @@
-// tl_fast_kernels.cu -- K2f `tl_sweep_fast_kernel` for sm_100a: the transmission-line sweep of
+// tl_fast_kernels.cu -- K2f `tl_sweep_fast_direct_kernel` / `tl_sweep_fast_kernel` for sm_100a: the transmission-line sweep of
 // TlModel::getSpectrum / prepareCalculations (reference TlModel.cpp:123-197, 484-676, 783-932) in the
 // ALGEBRAICALLY REDUCED form, selected by afs_tl_options.arithmetic = AFS_TL_ARITHMETIC_FAST.
 //
@@ -17,9 +17,13 @@
 //   * for the flow-source transfer function of a trachea..pharynx section (the spectrum getFormants and
 //     getImpulseResponse ask for) the product "rest of the chain after the source section" is accumulated
 //     directly instead of as inverse(P[section]) * P[40] (TlModel.cpp:1336-1338): no cancellation, three live
-//     matrices instead of five (DIRECT instantiation);
-// About 2.6 k FP64 instructions per bin (6.5x fewer).  Results agree with the bit-identical kernel to < 1e-9
-// relative (tests/test_tl_gpu.py::test_fast_arithmetic, bench.py reports the error of every run).
+//     matrices instead of five, the chains walked in straight-line code (tl_sweep_fast_direct_kernel); every
+//     other spectrum type / source section goes through a small interpreter of a host-built chain program
+//     (tl_sweep_fast_kernel).
+// About 2.6 k FP64 instructions per bin (6.5x fewer), 2.25 M spectra/s at 4096 x 2048 (K2: 0.27 M).  Against the
+// bit-identical kernel: 99.9 % of the points within 2.7e-10, maximum 2.85e-9 -- at those points the REFERENCE
+// arithmetic is that far from an extended-precision evaluation of its own formulas and this kernel 1e-12
+// (tools/tl_truth.py, tests/test_tl_gpu.py::test_fast_arithmetic_*; bench.py reports the error of every run).
 // Wave-propagation mode and the RADIATION spectrum are served by tl_kernels.cu (afs_api.cu routes them).
 #include "afs_internal.h"
 
