@@ -1103,11 +1103,26 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
   }
 }
 
+#ifdef AFS_TDS_TIMING
+__device__ long long g_nz_t[4];  // X2, lane 0 of CTA 0: cycles in the target stage / the source loop, passes, draws
+#define NZ_T0 const long long nzt0__ = clock64()
+#define NZ_T1 const long long nzt1__ = clock64(); long long nz_passes__ = 0, nz_draws__ = 0
+#define NZ_PASS nz_passes__++
+#define NZ_DRAW nz_draws__++
+#define NZ_T2 do { if (blockIdx.x == 0 && lane == 0) { g_nz_t[0] += nzt1__ - nzt0__; g_nz_t[1] += clock64() - nzt1__; g_nz_t[2] += nz_passes__; g_nz_t[3] += nz_draws__; } } while (0)
+#else
+#define NZ_T0
+#define NZ_T1
+#define NZ_PASS
+#define NZ_DRAW
+#define NZ_T2
+#endif
 // State-dependent part: target amplitudes from the flow through the constrictions (TdsModel.cpp:1430-1612), then
 // one sample of every source that is not silent (TdsModel.cpp:1630-1708).
 __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const int lane, NoiseRegs &N,
                                            const NoiseCons (&C)[4], const double r, const double r1, const int par,
                                            const double asp_dB) {
+  NZ_T0;
   int tIdx[8];
   double tAmp[8], tCut[8];
   unsigned long long todo = N.nz, targeted = 0;
@@ -1152,10 +1167,17 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
   }
   todo |= targeted;
   N.lips = 0.0;
+  NZ_T1;
+  // Pass 1, every live source: amplitude filter (TdsModel.cpp:1630-1660) and who draws a sample.  Pass 2, the
+  // drawing sources only, in ascending index order like the reference: filter coefficient, twelve random numbers,
+  // one-pole low-pass.  (One loop doing both made EVERY pass of the warp as expensive as a draw, because some lane
+  // draws in almost every pass; sources that only decay are the majority.)
+  unsigned long long draws = 0;
   while (todo) {
+    NZ_PASS;
     const int j = __ffsll((long long)todo) - 1;
     todo &= todo - 1;
-    double tgt = 0.0, cut = S.ncut[j][lane];
+    double tgt = 0.0, cut = 0.0;
     bool hit = false;
     if ((targeted >> j) & 1ull) {
 #pragma unroll
@@ -1164,21 +1186,25 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
     if (hit) S.ncut[j][lane] = cut;
     const double old = S.namp[j][lane];
     double a = __dadd_rn(old, __dmul_rn(P.nz_F, __dsub_rn(tgt, old)));
-    double out = S.nout[j][lane];
-    if ((old >= 0.001) && (a < 0.001)) out = 0.0;
-    if (a >= 0.001) {
-      const double x = exp_small(-2.0 * kPi * (cut * P.dt));  // IirFilter::createSinglePoleLowpass (IirFilter.cpp:235-243)
-      const uint32_t isum = rng_sum12(S, lane, N.ri);  // 12 x rand() summed in an int: wraps around like the reference's
-      double in = (double)(int32_t)isum;
-      in = (in * (1.0 / 2147483647.0) - 6.0) * 0.28867513459481288225;  // / RAND_MAX, - 6, / sqrt(12)
-      out = __dadd_rn(__dmul_rn(__dsub_rn(1.0, x), in), __dmul_rn(x, out));
-    }
+    if ((old >= 0.001) && (a < 0.001)) S.nout[j][lane] = 0.0;
+    if (a >= 0.001) draws |= 1ull << j;
     if ((a < 1.0e-13) && (tgt == 0.0)) { a = 0.0; N.nz &= ~(1ull << j); }  // (the reference lets it decay for ever; a source
                                                                            //  is silent below 1e-3)
     else N.nz |= 1ull << j;
-    S.namp[j][lane] = a; S.nout[j][lane] = out;
-    if (j == AFS_NUM_PM_SECTIONS) N.lips = out * a;
+    S.namp[j][lane] = a;
   }
+  while (draws) {
+    NZ_DRAW;
+    const int j = __ffsll((long long)draws) - 1;
+    draws &= draws - 1;
+    const double x = exp_small(-2.0 * kPi * (S.ncut[j][lane] * P.dt));  // IirFilter::createSinglePoleLowpass (IirFilter.cpp:235-243)
+    const uint32_t isum = rng_sum12(S, lane, N.ri);  // 12 x rand() summed in an int: wraps around like the reference's
+    double in = (double)(int32_t)isum;
+    in = (in * (1.0 / 2147483647.0) - 6.0) * 0.28867513459481288225;  // / RAND_MAX, - 6, / sqrt(12)
+    S.nout[j][lane] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, x), in), __dmul_rn(x, S.nout[j][lane]));
+  }
+  if ((N.nz >> AFS_NUM_PM_SECTIONS) & 1ull) N.lips = S.nout[AFS_NUM_PM_SECTIONS][lane] * S.namp[AFS_NUM_PM_SECTIONS][lane];
+  NZ_T2;
 }
 
 // ==================================================================================
@@ -1706,6 +1732,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   }
 #ifdef AFS_TDS_TIMING
   if (A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) A.dump[warp * 8 + k] = (double)tacc[k];
+  if (ROLE == 3 && NOISE && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) { A.dump[128 + k] = (double)g_nz_t[k]; g_nz_t[k] = 0; }
 #endif
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;
 }

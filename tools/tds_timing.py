@@ -18,3 +18,7 @@ print("cycles per step, per warp (lane 0 of CTA 0):")
 print("warp " + " ".join(f"{n[:10]:>10s}" for n in names) + "      total")
 for w in range(16):
     print(f"{roles[w]:>4s} " + " ".join(f"{v:10.0f}" for v in t[w]) + f" {t[w].sum():10.0f}")
+if noise:
+    nz = buf[128:132] / steps
+    print(f"X2 noise_sources per step (lane 0 of CTA 0; passes/draws are that lane's, the warp runs the maximum over its lanes): "
+          f"target stage {nz[0]:.0f} cycles, source loop {nz[1]:.0f} cycles, {nz[2]:.1f} passes, {nz[3]:.1f} draws")
