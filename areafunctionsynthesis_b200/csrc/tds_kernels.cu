@@ -1123,47 +1123,60 @@ __device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const
                                            const NoiseCons (&C)[4], const double r, const double r1, const int par,
                                            const double asp_dB) {
   NZ_T0;
+  // The scan fixes the kind of every slot (0: vocal folds, 1 and 2: tongue, 3: lower lip), so the four slots are
+  // straight-line code without branches on the kind; an invalid slot is computed on clamped indices and masked out:
+  // four independent dependency chains that overlap instead of four divergent branches in a row.
   int tIdx[8];
   double tAmp[8], tCut[8];
   unsigned long long todo = N.nz, targeted = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    tIdx[2 * k] = -1; tIdx[2 * k + 1] = -1; tAmp[2 * k] = tAmp[2 * k + 1] = 0.0; tCut[2 * k] = tCut[2 * k + 1] = 0.0;
-    if (!C[k].valid) continue;
-    const int nar = C[k].nar;
-    double A, flow = 0.0;
-    if (nar < 0) {
-      A = S.glArea[par][1][lane];
-      flow += S.nmag[0][lane];
-    } else {
-      A = nz_area(S, lane, r, r1, nar);
-      if (nar == AFS_NUM_PM_SECTIONS - 1) { flow += N.nm93; flow += N.nm94; }
-      else {
-        flow += S.nmag[nar + 1][lane];
-        if (nar == 3) flow += S.nmag[41][lane];   // section 28: currents 29 and 84
-        if (nar == 15) flow += S.nmag[40][lane];  // section 40: currents 41 and 65
-      }
-    }
-    if (A < kMinArea) A = kMinArea;
-    if (A < 0.1) A = 0.1;
-    if (flow < 0.0) flow = 0.0;
-    const double v = fast_div(flow, A);
-    double gain, cutoff = 6000.0;
-    if (C[k].kind == 2) gain = 2.0e-7;
-    else if (C[k].kind == 0) gain = 0.5e-7 * exp(asp_dB * (2.302585092994045684 / 20.0));  // 10^(dB/20)
-    else {
-      const double id = fast_rsqrt(A * (4.0 / kPi));  // 1/d, d = sqrt(4 A / pi)
-      cutoff = 0.15 * v * id;
-      gain = C[k].teeth ? 10.0e-7 : 5.0e-7;
-    }
-    double fullAmp = gain * fabs(v) * v * v * fast_sqrt(A);
-    if (C[k].lateral) fullAmp = 0.0;
+  constexpr int NPM = AFS_NUM_PM_SECTIONS;
+  auto flow_through = [&](int nar) {  // noiseMagnitude of the currents leaving pharynx/mouth section nar (0..39)
+    const double f = S.nmag[nar + 1][lane];
+    const double extra = S.nmag[nar == 3 ? 41 : 40][lane];  // section 28: currents 29 and 84; section 40: currents 41 and 65
+    const double fl = (nar == 3 || nar == 15) ? f + extra : f;
+    return nar == NPM - 1 ? N.nm93 + N.nm94 : fl;
+  };
+  auto clamp_area = [](double A) { if (A < kMinArea) A = kMinArea; if (A < 0.1) A = 0.1; return A; };
+  auto emit = [&](int k, bool valid, double fullAmp, double cutoff) {
     if (cutoff < 50.0) cutoff = 50.0;
     if (cutoff > 2000.0) cutoff = 2000.0;
-    const int up = C[k].up, down = up < AFS_NUM_PM_SECTIONS - 1 ? up + 1 : AFS_NUM_PM_SECTIONS;
-    tIdx[2 * k] = up; tAmp[2 * k] = (1.0 - C[k].downF) * fullAmp; tCut[2 * k] = cutoff;
-    tIdx[2 * k + 1] = down; tAmp[2 * k + 1] = C[k].downF * fullAmp; tCut[2 * k + 1] = cutoff;
-    targeted |= (1ull << up) | (1ull << down);
+    const int up = C[k].up, down = up < NPM - 1 ? up + 1 : NPM;
+    tIdx[2 * k] = valid ? up : -1; tAmp[2 * k] = (1.0 - C[k].downF) * fullAmp; tCut[2 * k] = cutoff;
+    tIdx[2 * k + 1] = valid ? down : -1; tAmp[2 * k + 1] = C[k].downF * fullAmp; tCut[2 * k + 1] = cutoff;
+    if (valid) targeted |= (1ull << up) | (1ull << down);
+  };
+  {  // slot 0: the glottis (upper glottis section, current 25)
+    const double A = clamp_area(S.glArea[par][1][lane]);
+    double flow = S.nmag[0][lane];
+    if (flow < 0.0) flow = 0.0;
+    const double v = fast_div(flow, A);
+    const double gain = 0.5e-7 * exp(asp_dB * (2.302585092994045684 / 20.0));  // 10^(dB/20)
+    double fullAmp = gain * fabs(v) * v * v * fast_sqrt(A);
+    if (C[0].lateral) fullAmp = 0.0;
+    emit(0, C[0].valid != 0, fullAmp, 6000.0);
+  }
+#pragma unroll
+  for (int k = 1; k < 3; k++) {  // slots 1, 2: tongue constrictions
+    const int nar = min(max(C[k].nar, 0), NPM - 1);
+    const double A = clamp_area(nz_area(S, lane, r, r1, nar));
+    double flow = flow_through(nar);
+    if (flow < 0.0) flow = 0.0;
+    const double v = fast_div(flow, A);
+    const double id = fast_rsqrt(A * (4.0 / kPi));  // 1/d, d = sqrt(4 A / pi)
+    const double gain = C[k].teeth ? 10.0e-7 : 5.0e-7;
+    double fullAmp = gain * fabs(v) * v * v * fast_sqrt(A);
+    if (C[k].lateral) fullAmp = 0.0;
+    emit(k, C[k].valid != 0, fullAmp, 0.15 * v * id);
+  }
+  {  // slot 3: the lips
+    const int nar = min(max(C[3].nar, 0), NPM - 1);
+    const double A = clamp_area(nz_area(S, lane, r, r1, nar));
+    double flow = flow_through(nar);
+    if (flow < 0.0) flow = 0.0;
+    const double v = fast_div(flow, A);
+    double fullAmp = 2.0e-7 * fabs(v) * v * v * fast_sqrt(A);
+    if (C[3].lateral) fullAmp = 0.0;
+    emit(3, C[3].valid != 0, fullAmp, 6000.0);
   }
   todo |= targeted;
   N.lips = 0.0;
