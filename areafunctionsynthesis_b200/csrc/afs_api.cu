@@ -606,7 +606,7 @@ int afs_synthesize_vowels_lf(afs_ctx *ctx, const afs_tl_options *opts, int n, co
   // host: pulse trains, filter coefficients, scale factors
   std::vector<double> flow((size_t)n * length), scale((size_t)n), ab(14, 0.0);
   for (int v = 0; v < n; v++) {
-    if (!(pulses[v].f0_hz > 0.0) || !(pulses[v].oq > 0.0)) return AFS_ERR_BAD_ARGUMENT;
+    if (!(pulses[v].f0_hz > 0.0) || !(pulses[v].oq > 0.0) || !(pulses[v].oq < 1.0) || !(pulses[v].sq > 0.0)) return AFS_ERR_BAD_ARGUMENT;
     if (lf_vowel_flow(&pulses[v], is_long_vowel, sampling_rate_hz, flow.data() + (size_t)v * length)) return AFS_ERR_BAD_ARGUMENT;
     scale[v] = 80.0 / pulses[v].f0_hz;
   }

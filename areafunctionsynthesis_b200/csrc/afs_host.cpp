@@ -245,7 +245,9 @@ int lf_vowel_flow(const afs_lf_pulse *lf, int is_long, double sampling_rate_hz, 
 extern "C" {
 
 int afs_lf_glottal_flow(const afs_lf_pulse *pulse, int is_long_vowel, double sampling_rate_hz, double *flow) {
-  if (!pulse || !flow || !(sampling_rate_hz > 0.0) || !(pulse->f0_hz > 0.0) || !(pulse->oq > 0.0)) return AFS_ERR_BAD_ARGUMENT;
+  if (!pulse || !flow || !(sampling_rate_hz > 0.0) || !(pulse->f0_hz > 0.0) || !(pulse->oq > 0.0) || !(pulse->oq < 1.0) ||
+      !(pulse->sq > 0.0))
+    return AFS_ERR_BAD_ARGUMENT;
   return afs::lf_vowel_flow(pulse, is_long_vowel, sampling_rate_hz, flow) ? AFS_ERR_BAD_ARGUMENT : AFS_OK;
 }
 
