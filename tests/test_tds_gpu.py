@@ -264,3 +264,33 @@ def test_noise_prepass_waves(ctx, shapes, monkeypatch):
     for b in (0, 4, 5, 699):
         ab, _, _ = ctx.tds_synthesize(fr[b:b + 1], gl[b:b + 1], [150], 44100.0, 2, opts=o, seeds=seeds[b:b + 1])
         assert np.array_equal(ab[0], a0[b]), b
+
+
+@pytest.mark.parametrize("noise", [False, True])
+def test_per_sample_control_frames(ctx, oracle, shapes, noise):
+    """Synthesizer::playTargetSequence style driving (Synthesizer.cpp:1299-1422): one control frame per OUTPUT sample
+    (synthesizeSignalTds(tube, glottisParams, 1, out) in a loop), i.e. a new interpolation interval every sr_factor
+    simulation steps, glottis parameters gliding with the tube."""
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    n = len(shapes["names"])
+    nf = 301  # 300 output samples = 600 steps
+    a, b = shapes["frames"][0], shapes["frames"][8]  # /a:/ -> /i:/
+    w = 0.5 - 0.5 * np.cos(np.linspace(0.0, np.pi, nf))
+    fr = np.zeros((3, nf), dtype=shapes["frames"].dtype)
+    for t, (x, y) in enumerate(((a, b), (b, shapes["frames"][16]), (shapes["frames"][n + 4], a))):
+        fr[t] = x
+        fr[t]["area_cm2"] = (1 - w)[:, None] * x["area_cm2"] + w[:, None] * y["area_cm2"]
+        fr[t]["length_cm"] = (1 - w)[:, None] * x["length_cm"] + w[:, None] * y["length_cm"]
+        fr[t]["velum_area_cm2"] = (1 - w) * x["velum_area_cm2"] + w * y["velum_area_cm2"]
+        fr[t]["incisor_pos_cm"] = (1 - w) * x["incisor_pos_cm"] + w * y["incisor_pos_cm"]
+    gl = np.tile(G0, (3, nf, 1))
+    gl[:, :, 0] = 100.0 + 15.0 * w            # F0 contour
+    gl[:, :50, 1] = 8000.0 * np.linspace(0, 1, 50)  # lung pressure fade-in
+    seeds = np.array([5, 6, 7], dtype=np.uint32)
+    frame_len = [1] * (nf - 1)
+    audio, flow, st = ctx.tds_synthesize(fr, gl, frame_len, 44100.0, 2, opts=afs.tds_options_default(noise=noise), seeds=seeds,
+                                         want_flow=True)
+    ao, fo = oracle.tds_synthesize(fr, gl, frame_len, 44100.0, 2, opts=oracle_opts(noise=noise), seeds=seeds)
+    assert not st.any()
+    assert rel_err(audio, ao) <= TOL and rel_err(flow, fo) <= TOL
