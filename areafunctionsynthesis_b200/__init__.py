@@ -21,6 +21,7 @@ from .api import (  # noqa: F401
     library_path,
     load_library,
     tds_options_default,
+    target_sequence_trajectory,
     tl_options_default,
     write_wav_int16,
 )

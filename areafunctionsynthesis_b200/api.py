@@ -80,6 +80,9 @@ def load_library():
     lib.afs_tl_formants.argtypes = [vp, vp, i32, vp, dbl, i32, i32, vp, vp, vp, vp]
     lib.afs_optimize_formants_vowel.argtypes = [vp, vp, i32, vp, vp, dbl, dbl, vp, i32, dbl, i32, vp, vp, vp, vp, vp]
     lib.afs_synthesize_vowels_lf.argtypes = [vp, vp, i32, vp, vp, i32, dbl, vp, vp]
+    lib.afs_target_sequence_length.argtypes = [vp, vp, dbl]
+    lib.afs_target_sequence_trajectory.argtypes = [vp, vp, vp, vp, dbl, vp, vp]
+    lib.afs_play_target_sequences.argtypes = [vp, vp, i32, vp, vp, vp, vp, dbl, i32, vp, vp, vp]
     lib.afs_lf_vowel_length.argtypes = [i32, dbl]
     lib.afs_lf_glottal_flow.argtypes = [vp, i32, dbl, vp]
     lib.afs_tl_impulse_response.argtypes = [vp, vp, i32, vp, dbl, i32, vp]
@@ -150,6 +153,20 @@ def area_function_to_frames(params, frames=None):
     for i in range(len(p)):
         _check(lib, lib.afs_area_function_to_frame(_ptr(p[i]), _ptr(out[i:i + 1])))
     return out
+
+
+def target_sequence_trajectory(shapes4x16, stationary_s, transition_s, glottis_control, sampling_rate_hz=22050.0):
+    """Host helper: the per-sample trajectories of Synthesizer::playTargetSequence: (params [n, 16], glottis [n, 6])."""
+    lib = load_library()
+    sh = np.ascontiguousarray(shapes4x16, dtype=np.float64).reshape(4, 16)
+    st = np.ascontiguousarray(stationary_s, dtype=np.float64); tr = np.ascontiguousarray(transition_s, dtype=np.float64)
+    g6 = np.ascontiguousarray(glottis_control, dtype=np.float64)
+    n = int(lib.afs_target_sequence_length(_ptr(st), _ptr(tr), float(sampling_rate_hz)))
+    prm = np.zeros((n, 16)); gl = np.zeros((n, NUM_GLOTTIS_CONTROL))
+    rc = lib.afs_target_sequence_trajectory(_ptr(sh), _ptr(st), _ptr(tr), _ptr(g6), float(sampling_rate_hz), _ptr(prm), _ptr(gl))
+    if rc:
+        raise AfsError(f"afs_target_sequence_trajectory: status {rc}")
+    return prm, gl
 
 
 def lf_glottal_flow(lf5, is_long=True, sampling_rate_hz=22050.0):
@@ -257,6 +274,22 @@ class Context:
             int(max_runs), float(sampling_rate_hz), int(spectrum_length), _ptr(e0), _ptr(e1), _ptr(runs), _ptr(fo),
             _ptr(trace)), self.h)
         return dict(params=p, initial_error=e0, final_error=e1, runs=runs, formants_hz=fo, trace=trace)
+
+    def play_target_sequences(self, shapes, stationary_s, transition_s, glottis_control, sampling_rate_hz=22050.0, sr_factor=2,
+                              opts=None, seeds=None):
+        """Synthesizer::playTargetSequence for a batch: shapes [n, 4, 16].  Returns (audio [n, num_samples], status [n])."""
+        opts = opts or tds_options_default()
+        sh = np.ascontiguousarray(shapes, dtype=np.float64).reshape(-1, 4, 16)
+        n = len(sh)
+        st = np.ascontiguousarray(stationary_s, dtype=np.float64); tr = np.ascontiguousarray(transition_s, dtype=np.float64)
+        g6 = np.ascontiguousarray(glottis_control, dtype=np.float64)
+        ns = int(self.lib.afs_target_sequence_length(_ptr(st), _ptr(tr), float(sampling_rate_hz)))
+        audio = np.zeros((n, ns)); status = np.zeros(n, dtype=np.uint32)
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
+        _check(self.lib, self.lib.afs_play_target_sequences(self.h, C.byref(opts), n, _ptr(sh), _ptr(st), _ptr(tr), _ptr(g6),
+                                                            float(sampling_rate_hz), int(sr_factor), _ptr(s), _ptr(audio),
+                                                            _ptr(status)), self.h)
+        return audio, status
 
     def synthesize_vowels_lf(self, frames, lf_params, is_long=True, sampling_rate_hz=22050.0, opts=None, want_pressure=False):
         """Synthesizer::synthesizeVowelLf for a batch: lf_params [n, 5] = AMP, F0, OQ, SQ, TL.  Returns int16 [n, length]

@@ -386,6 +386,65 @@ int afs_tl_impulse_response(afs_ctx *ctx, const afs_tl_options *opts, int n_tube
 }
 
 // ---------------------------------------------------------------------------
+// Target sequences: Synthesizer::playTargetSequence, batched
+// ---------------------------------------------------------------------------
+int afs_play_target_sequences(afs_ctx *ctx, const afs_tds_options *opts, int n, const double *shapes,
+                              const double stationary_s[4], const double transition_s[3],
+                              const double glottis_control[AFS_NUM_GLOTTIS_CONTROL], double sampling_rate_hz,
+                              int sr_factor, const uint32_t *seeds, double *audio, uint32_t *status) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!opts || n < 0 || !stationary_s || !transition_s || !glottis_control || !(sampling_rate_hz > 0.0) || sr_factor < 1)
+    return AFS_ERR_BAD_ARGUMENT;
+  if (n == 0) return AFS_OK;
+  if (!shapes || !audio) return AFS_ERR_BAD_ARGUMENT;
+  const int ns = target_sequence_length(stationary_s, transition_s, sampling_rate_hz);
+  if (ns < 2) return AFS_ERR_BAD_ARGUMENT;
+  const size_t nf = (size_t)n * (size_t)ns;  // control frames = parameter sets
+  if (nf > 0x7fffffffull) return AFS_ERR_BAD_ARGUMENT;
+  {  // the frames (1184 B per output sample and sequence) stay on the device; they have to fit
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = nf * (sizeof(afs_tube_frame) + 22 * sizeof(double)) + (size_t)n * ns * sizeof(double);
+    if (need > free_b + ctx->scratch_bytes[0] + ctx->scratch_bytes[1] + ctx->scratch_bytes[2]) return AFS_ERR_OUT_OF_MEMORY;
+  }
+  // host: trajectories of every sequence
+  std::vector<double> params(nf * 16), gl(nf * AFS_NUM_GLOTTIS_CONTROL);
+  for (int b = 0; b < n; b++)
+    target_sequence_trajectory(shapes + (size_t)b * 64, stationary_s, transition_s, glottis_control, sampling_rate_hz, ns,
+                               params.data() + (size_t)b * ns * 16, gl.data() + (size_t)b * ns * AFS_NUM_GLOTTIS_CONTROL);
+  void *d_frames, *d_params, *d_gl, *d_audio, *d_status, *d_seeds = nullptr;
+  if ((rc = scratch(ctx, 0, nf * sizeof(afs_tube_frame), &d_frames))) return rc;
+  if ((rc = scratch(ctx, 1, nf * 16 * sizeof(double), &d_params))) return rc;
+  if ((rc = scratch(ctx, 2, nf * AFS_NUM_GLOTTIS_CONTROL * sizeof(double), &d_gl))) return rc;
+  if ((rc = scratch(ctx, 3, (size_t)n * (ns - 1) * sizeof(double), &d_audio))) return rc;
+  if ((rc = scratch(ctx, 4, (size_t)n * sizeof(uint32_t), &d_status))) return rc;
+  if (seeds) {
+    if ((rc = scratch(ctx, 5, (size_t)n * sizeof(uint32_t), &d_seeds))) return rc;
+    CU(cudaMemcpyAsync(d_seeds, seeds, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaMemcpyAsync(d_params, params.data(), nf * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_gl, gl.data(), nf * AFS_NUM_GLOTTIS_CONTROL * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  afs_tube_frame tpl;  // a fresh Tube (nasal port closed; the glottis sections come from the glottis model)
+  afs_tube_frame_default(&tpl);
+  CU(launch_fill_frames(nf, (afs_tube_frame *)d_frames, tpl, ctx->stream));
+  CU(launch_area_function_raster((int)nf, (const double *)d_params, (afs_tube_frame *)d_frames, ctx->stream));
+  ctx->launches += 2;
+  std::vector<int32_t> frame_len((size_t)ns - 1, 1);  // one synthesizeSignalTds(tube, glottisParams, 1, out) per sample
+  rc = afs_tds_synthesize_device(ctx, opts, n, ns, frame_len.data(), (const afs_tube_frame *)d_frames, (const double *)d_gl,
+                                 sampling_rate_hz * sr_factor, sr_factor, (const uint32_t *)d_seeds, (double *)d_audio, nullptr,
+                                 (uint32_t *)d_status, ctx->stream);
+  if (rc) return rc;
+  // sample 0: the priming call produces nothing
+  for (int b = 0; b < n; b++) audio[(size_t)b * ns] = 0.0;
+  CU(cudaMemcpy2DAsync(audio + 1, (size_t)ns * sizeof(double), d_audio, (size_t)(ns - 1) * sizeof(double),
+                       (size_t)(ns - 1) * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CU(cudaMemcpyAsync(status, d_status, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return AFS_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Formant optimiser: Data::optimizeFormantsVowel, batched
 // ---------------------------------------------------------------------------
 namespace {

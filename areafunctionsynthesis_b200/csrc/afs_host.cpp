@@ -240,9 +240,83 @@ int lf_vowel_flow(const afs_lf_pulse *lf, int is_long, double sampling_rate_hz, 
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Trajectories of Synthesizer::playTargetSequence (Synthesizer.cpp:1299-1422, interpolateParameters :1286-1294):
+// per output sample the 16 area-function parameters (cosine interpolation between four target shapes) and the
+// glottis control parameters (F0 contour 100 -> 115 -> 105 -> 80 Hz, lung pressure 8000 dPa with 50 ms silence +
+// 50 ms cosine fade-in and the reference's fade-out expression, operator-precedence slip included).  Host libm,
+// the reference's own expressions (SAMPLING_RATE is an int there: every product below converts it the same way).
+// ---------------------------------------------------------------------------------------------------
+int target_sequence_length(const double *stationary_s, const double *transition_s, double sampling_rate_hz) {
+  const double total = stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2] + transition_s[2] + stationary_s[3];
+  const double n = sampling_rate_hz * total;
+  return n > 0.0 && n < 2.0e9 ? (int)n : 0;
+}
+
+void target_sequence_trajectory(const double *shapes4x16, const double *stationary_s, const double *transition_s,
+                                const double *glottis6, double SR, int numSamples, double *params, double *glottis) {
+  double gp[AFS_NUM_GLOTTIS_CONTROL];
+  for (int i = 0; i < AFS_NUM_GLOTTIS_CONTROL; i++) gp[i] = glottis6[i];
+  const double f0_Hz[4] = {100, 115, 105, 80};
+  gp[1] = 8000.0;  // Glottis::PRESSURE (sensorDataToGlottisParams, Synthesizer.cpp:889-921)
+  const double steady = gp[1];
+  const double b[7] = {
+      stationary_s[0],
+      stationary_s[0] + transition_s[0],
+      stationary_s[0] + transition_s[0] + stationary_s[1],
+      stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1],
+      stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2],
+      stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2] + transition_s[2],
+      stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2] + transition_s[2] + stationary_s[3],
+  };
+  const double total = b[6];
+  const double *sh[4] = {shapes4x16, shapes4x16 + 16, shapes4x16 + 32, shapes4x16 + 48};
+  double cur[16];
+  for (int j = 0; j < 16; j++) cur[j] = sh[0][j];
+  for (int i = 0; i < numSamples; i++) {
+    if (i < 0.1 * SR) {
+      if (i < 0.05 * SR) gp[1] = 0.0;
+      else gp[1] = steady / 2 * cos((0.1 * SR - i) / (0.05 * SR) * M_PI) + steady / 2;
+    }
+    if (i < b[1] * SR) gp[0] = (f0_Hz[0] + f0_Hz[1]) / 2 + (f0_Hz[1] - f0_Hz[0]) / 2 * cos((b[1] * SR - i) / (b[1] * SR) * M_PI);
+    else if (i < b[3] * SR) gp[0] = (f0_Hz[2] + f0_Hz[1]) / 2 + (f0_Hz[2] - f0_Hz[1]) / 2 * cos((b[3] * SR - i) / ((b[3] - b[1]) * SR) * M_PI);
+    else gp[0] = (f0_Hz[3] + f0_Hz[2]) / 2 + (f0_Hz[3] - f0_Hz[2]) / 2 * cos((b[6] * SR - i) / ((b[6] - b[3]) * SR) * M_PI);
+    int seg = -1;  // 0, 2, 4, 6: stationary shape seg / 2; 1, 3, 5: transition between shapes (seg - 1) / 2 and (seg + 1) / 2
+    for (int k = 0; k < 7; k++) if (i <= b[k] * SR) { seg = k; break; }
+    if (seg >= 0) {
+      if ((seg & 1) == 0) { for (int j = 0; j < 16; j++) cur[j] = sh[seg / 2][j]; }
+      else {
+        const double *p0 = sh[(seg - 1) / 2], *p1 = sh[(seg + 1) / 2];
+        const double t0 = b[seg - 1] * SR, t1 = b[seg] * SR, tX = i;
+        for (int j = 0; j < 16; j++) cur[j] = (p1[j] - p0[j]) / 2 * cos((t1 - tX) / (t1 - t0) * M_PI) + (p1[j] + p0[j]) / 2;
+      }
+    }
+    if (i > (total - 0.1) * SR) gp[1] = -steady / 2 * cos((total * SR - i) / (total - 0.1 * SR) * M_PI) + steady / 2;
+    for (int j = 0; j < 16; j++) params[(size_t)i * 16 + j] = cur[j];
+    for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) glottis[(size_t)i * AFS_NUM_GLOTTIS_CONTROL + c] = gp[c];
+  }
+}
+
 }  // namespace afs
 
 extern "C" {
+
+int afs_target_sequence_length(const double stationary_s[4], const double transition_s[3], double sampling_rate_hz) {
+  if (!stationary_s || !transition_s || !(sampling_rate_hz > 0.0)) return 0;
+  return afs::target_sequence_length(stationary_s, transition_s, sampling_rate_hz);
+}
+
+int afs_target_sequence_trajectory(const double *shapes, const double stationary_s[4], const double transition_s[3],
+                                   const double glottis_control[AFS_NUM_GLOTTIS_CONTROL], double sampling_rate_hz,
+                                   double *params, double *glottis) {
+  if (!shapes || !stationary_s || !transition_s || !glottis_control || !params || !glottis || !(sampling_rate_hz > 0.0))
+    return AFS_ERR_BAD_ARGUMENT;
+  const int n = afs::target_sequence_length(stationary_s, transition_s, sampling_rate_hz);
+  if (n < 1) return AFS_ERR_BAD_ARGUMENT;
+  afs::target_sequence_trajectory(shapes, stationary_s, transition_s, glottis_control, sampling_rate_hz, n, params, glottis);
+  return AFS_OK;
+}
 
 int afs_lf_glottal_flow(const afs_lf_pulse *pulse, int is_long_vowel, double sampling_rate_hz, double *flow) {
   if (!pulse || !flow || !(sampling_rate_hz > 0.0) || !(pulse->f0_hz > 0.0) || !(pulse->oq > 0.0) || !(pulse->oq < 1.0) ||

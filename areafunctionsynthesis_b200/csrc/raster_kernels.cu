@@ -74,6 +74,19 @@ area_function_raster_kernel(int n_sets, const double *__restrict__ params, afs_t
   if (sec == 0) f->incisor_pos_cm = q[XIN];
 }
 
+// every frame := the template (the rasteriser only writes the pharynx / mouth fields and the incisor position)
+__global__ void fill_frames_kernel(size_t n_words, uint64_t *__restrict__ frames, const afs_tube_frame tpl) {
+  constexpr size_t W = sizeof(afs_tube_frame) / 8;
+  const uint64_t *t = reinterpret_cast<const uint64_t *>(&tpl);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) frames[i] = t[i % W];
+}
+cudaError_t launch_fill_frames(size_t n, afs_tube_frame *d_frames, const afs_tube_frame &tpl, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  static_assert(sizeof(afs_tube_frame) % 8 == 0, "frame is a whole number of 64-bit words");
+  fill_frames_kernel<<<148 * 8, 256, 0, stream>>>(n * (sizeof(afs_tube_frame) / 8), reinterpret_cast<uint64_t *>(d_frames), tpl);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_area_function_raster(int n_sets, const double *d_params, afs_tube_frame *d_frames, cudaStream_t stream) {
   if (n_sets <= 0) return cudaSuccess;
   const int ctas = (n_sets + RASTER_SETS_PER_CTA - 1) / RASTER_SETS_PER_CTA;

@@ -438,6 +438,30 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         extra["lf_vowels"] = {"metric": "lf_vowels_per_second", "value": n_lf / dt, "unit": "vowels/s (0.65 s each, 22.05 kHz)",
                               "config": {"workload": f"{n_lf} long vowels, host API incl. pulse trains and copies"}, "cpu_baseline": None}
+        n_ts = 256
+        gt = np.load(os.path.join(ROOT, "tests", "golden", "target_sequence.npz"))
+        sh_ts = np.tile(gt["shapes"], (n_ts // 3 + 1, 1, 1))[:n_ts]
+        ctx.play_target_sequences(sh_ts, gt["stationary"], gt["transition"], gt["glottis"], 22050.0, 2, opts=quiet)  # warm-up
+        t0 = time.perf_counter()
+        a_ts, st_ts = ctx.play_target_sequences(sh_ts, gt["stationary"], gt["transition"], gt["glottis"], 22050.0, 2, opts=quiet)
+        dt = time.perf_counter() - t0
+        ts_s = a_ts.shape[1] / 22050.0
+        assert not st_ts.any()
+        extra["target_sequences"] = {"metric": "target_sequence_audio_seconds_per_second", "value": n_ts * ts_s / dt, "unit": "audio-s/s",
+                                     "config": {"workload": f"{n_ts} sequences of 4 target shapes x {ts_s:.2f} s, one control frame per output sample "
+                                                            "(parameter sets rasterised on the device), noise sources off, host API"},
+                                     "cpu_baseline": None}
+        if not args.no_cpu_baseline:
+            try:
+                from oracle.pyoracle import Ref, tds_options_default as ref_tds_opts
+                t0 = time.perf_counter()
+                ra, _, _ = Ref(44).play_target_sequence(gt["shapes"][0], gt["stationary"], gt["transition"], gt["glottis"],
+                                                        opts=ref_tds_opts(noise=False))
+                extra["target_sequences"]["cpu_baseline"] = {"value": ts_s / (time.perf_counter() - t0), "unit": "audio-s/s", "cores": 1,
+                                                             "kind": "reference", "sample": "1 sequence"}
+                assert np.max(np.abs(ra - a_ts[0])) <= 1e-6 * np.max(np.abs(ra)), "target sequence differs from the reference"
+            except (FileNotFoundError, OSError):
+                pass
         if not args.no_cpu_baseline:
             try:
                 from oracle.pyoracle import Ref

@@ -304,6 +304,29 @@ int afs_synthesize_vowels_lf(afs_ctx *ctx, const afs_tl_options *opts, int n_vow
                              const afs_lf_pulse *pulses, int is_long_vowel, double sampling_rate_hz, int16_t *audio,
                              double *pressure);
 
+/*
+ * Replaces Synthesizer::playTargetSequence(targetShape[4], stationary_s[4], transition_s[3]) (Synthesizer.cpp:
+ * 1299-1422) for a batch of target sequences that share the timing: per OUTPUT sample the 16 area-function
+ * parameters are cosine-interpolated between four target shapes (interpolateParameters, :1286-1294), F0 follows
+ * the reference's contour 100 -> 115 -> 105 -> 80 Hz, the lung pressure (8000 dPa) its fade-in / fade-out, the
+ * parameter set is rasterised (OneDimAreaFunction, on the device: K4) and ONE synthesizeSignalTds(tube,
+ * glottisParams, 1, out) call is made per sample -- i.e. a control frame per output sample for the TDS kernel.
+ *   shapes [n][4][16] (OneDimAreaFunction::ParamIndex order); glottis_control [6]: control parameters of the
+ *   glottis object (FREQUENCY and PRESSURE are overwritten by the contour); audio [n][num_samples], num_samples =
+ *   afs_target_sequence_length (the reference's int truncation); sample 0 is the priming call of the reference
+ *   (it returns without writing, Synthesizer.cpp:522-532) and is 0 here.  seeds (nullable) [n] as in afs_tds_synthesize.
+ * Host helpers (no device work): afs_target_sequence_length, afs_target_sequence_trajectory (params
+ * [num_samples][16], glottis [num_samples][6] of one sequence).
+ */
+int afs_target_sequence_length(const double stationary_s[4], const double transition_s[3], double sampling_rate_hz);
+int afs_target_sequence_trajectory(const double *shapes, const double stationary_s[4], const double transition_s[3],
+                                   const double glottis_control[AFS_NUM_GLOTTIS_CONTROL], double sampling_rate_hz,
+                                   double *params, double *glottis);
+int afs_play_target_sequences(afs_ctx *ctx, const afs_tds_options *opts, int n_sequences, const double *shapes,
+                              const double stationary_s[4], const double transition_s[3],
+                              const double glottis_control[AFS_NUM_GLOTTIS_CONTROL], double sampling_rate_hz,
+                              int sr_factor, const uint32_t *seeds, double *audio, uint32_t *status);
+
 /* ---- TdsModel + TriangularGlottis + driver loop ---------------------------- */
 /*
  * Replaces, for a batch of independent utterances ("tracts"), the per-sample

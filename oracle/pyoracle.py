@@ -138,6 +138,20 @@ class Ref:
         runs = int(out3[2])
         return p, out3[0], out3[1], runs, trace[:runs], fo
 
+    def play_target_sequence(self, shapes4x16, stationary_s, transition_s, glottis6, opts=None, seed=1):
+        """Synthesizer::playTargetSequence restated over the reference classes (ref_harness.cpp).
+        Returns (audio [numSamples], params [numSamples, 16], glottis [numSamples, 6])."""
+        opts = opts or tds_options_default()
+        sh = np.ascontiguousarray(shapes4x16, dtype=np.float64).reshape(4, 16)
+        st = np.ascontiguousarray(stationary_s, dtype=np.float64); tr = np.ascontiguousarray(transition_s, dtype=np.float64)
+        g6 = np.ascontiguousarray(glottis6, dtype=np.float64)
+        n = self.lib.ref_target_sequence_length(_ptr(st), _ptr(tr))
+        audio = np.zeros(n); prm = np.zeros((n, 16)); gl = np.zeros((n, 6))
+        m = self.lib.ref_play_target_sequence(C.byref(opts), _ptr(sh), _ptr(st), _ptr(tr), _ptr(g6), C.c_uint32(seed), _ptr(audio),
+                                              _ptr(prm), _ptr(gl))
+        assert m == n
+        return audio, prm, gl
+
     def synthesize_vowel_lf(self, frame, lf5, is_long, opts=None):
         """Synthesizer::synthesizeVowelLf restated over the reference classes: (int16 audio, float64 pressure)."""
         opts = opts or tl_options_default()

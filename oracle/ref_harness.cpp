@@ -365,6 +365,102 @@ int ref_synthesize_vowel_lf(const afs_tl_options *opts, const afs_tube_frame *tu
   return length;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Synthesizer::playTargetSequence (Synthesizer.cpp:1299-1422) with interpolateParameters (:1286-1294): four target
+// shapes, cosine-interpolated parameter trajectories, F0 contour 100 -> 115 -> 105 -> 80 Hz, lung-pressure fade in /
+// out, ONE synthesizeSignalTds(tube, glottisParams, 1, out) call per output sample.  Synthesizer is wx/PortAudio-
+// bound: the trajectory is restated line by line (operator-precedence slips included), the tube of every sample comes
+// from the reference's own OneDimAreaFunction, the driver loop is tds_one above.  glottis6: the control parameters of
+// the glottis object (FREQUENCY and PRESSURE are overwritten).  audio [numSamples]; sample 0 is the priming call
+// (synthesizeSignalTds returns without writing, Synthesizer.cpp:522-532) and reads 0 here.
+// ---------------------------------------------------------------------------------------------------
+static void tds_one(const afs_tds_options *o, int n_frames, const int32_t *frame_len, const afs_tube_frame *frames,
+                    const double *glottis, unsigned seed, double *audio, double *flow, double *state_dump, int dump_step);
+
+int ref_target_sequence_length(const double *stationary_s, const double *transition_s) {
+  double totalTime_s = stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2] + transition_s[2] + stationary_s[3];
+  int numSamples = SAMPLING_RATE * totalTime_s;
+  return numSamples;
+}
+
+// params_out (nullable) [numSamples][16], glottis_out (nullable) [numSamples][6]: the trajectories
+int ref_play_target_sequence(const afs_tds_options *opts, const double *shapes4x16, const double *stationary_s,
+                             const double *transition_s, const double *glottis6, uint32_t seed, double *audio,
+                             double *params_out, double *glottis_out) {
+  typedef OneDimAreaFunction AF;
+  double glottisParams[AFS_NUM_GLOTTIS_CONTROL];
+  for (int i = 0; i < AFS_NUM_GLOTTIS_CONTROL; i++) glottisParams[i] = glottis6[i];
+  double f0_Hz[4] = {100, 115, 105, 80};
+  glottisParams[Glottis::PRESSURE] = 8000.0;  // sensorDataToGlottisParams (Synthesizer.cpp:889-921), no F0 wobble at t = 0
+  double steadyStateLungPressure = glottisParams[Glottis::PRESSURE];
+  double boundary_s[7] = {
+      stationary_s[0],
+      stationary_s[0] + transition_s[0],
+      stationary_s[0] + transition_s[0] + stationary_s[1],
+      stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1],
+      stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2],
+      stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2] + transition_s[2],
+      stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2] + transition_s[2] + stationary_s[3],
+  };
+  double totalTime_s = boundary_s[6];
+  int numSamples = SAMPLING_RATE * totalTime_s;
+  std::vector<afs_tube_frame> frames((size_t)numSamples);
+  std::vector<double> gl((size_t)numSamples * AFS_NUM_GLOTTIS_CONTROL);
+  AF vtAreaFunction;
+  AF::Param currentParams[AF::NUM_AF_PARAMS];
+  vtAreaFunction.getParameters(currentParams);
+  auto interpolateParameters = [&](const double *p0, const double *p1, double t0, double t1, double tX) {
+    for (int i = 0; i < AF::NUM_AF_PARAMS; i++) currentParams[i].x = (p1[i] - p0[i]) / 2 * cos((t1 - tX) / (t1 - t0) * M_PI) + (p1[i] + p0[i]) / 2;
+  };
+  for (int i = 0; i < numSamples; i++) {
+    if (i < (double)0.1 * (double)SAMPLING_RATE) {
+      if (i < (double)0.05 * (double)SAMPLING_RATE) glottisParams[Glottis::PRESSURE] = 0.0;
+      else glottisParams[Glottis::PRESSURE] = steadyStateLungPressure / 2 * cos((0.1 * SAMPLING_RATE - i) / (0.05 * SAMPLING_RATE) * M_PI) + steadyStateLungPressure / 2;
+    }
+    if (i < (double)boundary_s[1] * SAMPLING_RATE)
+      glottisParams[Glottis::FREQUENCY] = (f0_Hz[0] + f0_Hz[1]) / 2 + (f0_Hz[1] - f0_Hz[0]) / 2 * cos((boundary_s[1] * SAMPLING_RATE - i) / (boundary_s[1] * SAMPLING_RATE) * M_PI);
+    else if (i < (double)boundary_s[3] * SAMPLING_RATE)
+      glottisParams[Glottis::FREQUENCY] = (f0_Hz[2] + f0_Hz[1]) / 2 + (f0_Hz[2] - f0_Hz[1]) / 2 * cos((boundary_s[3] * SAMPLING_RATE - i) / ((boundary_s[3] - boundary_s[1]) * SAMPLING_RATE) * M_PI);
+    else
+      glottisParams[Glottis::FREQUENCY] = (f0_Hz[3] + f0_Hz[2]) / 2 + (f0_Hz[3] - f0_Hz[2]) / 2 * cos((boundary_s[6] * SAMPLING_RATE - i) / ((boundary_s[6] - boundary_s[3]) * SAMPLING_RATE) * M_PI);
+    const double *sh[4] = {shapes4x16, shapes4x16 + 16, shapes4x16 + 32, shapes4x16 + 48};
+    if (i <= boundary_s[0] * SAMPLING_RATE) { for (int j = 0; j < AF::NUM_AF_PARAMS; j++) currentParams[j].x = sh[0][j]; }
+    else if (i <= boundary_s[1] * SAMPLING_RATE) interpolateParameters(sh[0], sh[1], boundary_s[0] * SAMPLING_RATE, boundary_s[1] * SAMPLING_RATE, i);
+    else if (i <= boundary_s[2] * SAMPLING_RATE) { for (int j = 0; j < AF::NUM_AF_PARAMS; j++) currentParams[j].x = sh[1][j]; }
+    else if (i <= boundary_s[3] * SAMPLING_RATE) interpolateParameters(sh[1], sh[2], boundary_s[2] * SAMPLING_RATE, boundary_s[3] * SAMPLING_RATE, i);
+    else if (i <= boundary_s[4] * SAMPLING_RATE) { for (int j = 0; j < AF::NUM_AF_PARAMS; j++) currentParams[j].x = sh[2][j]; }
+    else if (i <= boundary_s[5] * SAMPLING_RATE) interpolateParameters(sh[2], sh[3], boundary_s[4] * SAMPLING_RATE, boundary_s[5] * SAMPLING_RATE, i);
+    else if (i <= boundary_s[6] * SAMPLING_RATE) { for (int j = 0; j < AF::NUM_AF_PARAMS; j++) currentParams[j].x = sh[3][j]; }
+    if (i > (double)(totalTime_s - 0.1) * (double)SAMPLING_RATE)
+      glottisParams[Glottis::PRESSURE] = -steadyStateLungPressure / 2 * cos((totalTime_s * SAMPLING_RATE - i) / (totalTime_s - 0.1 * SAMPLING_RATE) * M_PI) + steadyStateLungPressure / 2;
+
+    vtAreaFunction.setParameters(currentParams);
+    Tube tubeFunction;
+    vtAreaFunction.calculateOneDimTubeFunction(&tubeFunction);
+    tubeFunction.teethPosition_cm = currentParams[AF::XIN_CM].x;
+    afs_tube_frame &f = frames[i];
+    memset(&f, 0, sizeof f);
+    for (int k = 0; k < Tube::NUM_PHARYNX_MOUTH_SECTIONS; k++) {
+      f.area_cm2[k] = tubeFunction.pharynxMouthSection[k].area_cm2;
+      f.length_cm[k] = tubeFunction.pharynxMouthSection[k].length_cm;
+      f.laterality[k] = tubeFunction.pharynxMouthSection[k].laterality;
+      f.articulator[k] = (int)tubeFunction.pharynxMouthSection[k].articulator;
+    }
+    f.incisor_pos_cm = tubeFunction.teethPosition_cm;
+    f.velum_area_cm2 = 0.0;  // a fresh Tube: nasal port closed
+    f.aspiration_dB = tubeFunction.aspirationStrength_dB;
+    f.glottis_area_cm2[0] = f.glottis_area_cm2[1] = 0.1; f.glottis_length_cm[0] = f.glottis_length_cm[1] = 0.3;
+    for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) gl[(size_t)i * AFS_NUM_GLOTTIS_CONTROL + c] = glottisParams[c];
+    if (params_out) for (int j = 0; j < 16; j++) params_out[(size_t)i * 16 + j] = currentParams[j].x;
+    if (glottis_out) for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) glottis_out[(size_t)i * AFS_NUM_GLOTTIS_CONTROL + c] = glottisParams[c];
+  }
+  std::vector<int32_t> frame_len((size_t)(numSamples > 1 ? numSamples - 1 : 0), 1);
+  audio[0] = 0.0;
+  if (numSamples > 1)
+    tds_one(opts, numSamples, frame_len.data(), frames.data(), gl.data(), seed, audio + 1, nullptr, nullptr, 0);
+  return numSamples;
+}
+
 // TlModel::getFormants on a fresh TlModel per tube.
 void ref_tl_formants(const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
                      int max_formants, double *freq, double *bw, int32_t *num, int32_t *flags) {

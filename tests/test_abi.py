@@ -108,3 +108,14 @@ def test_lf_pulse_train_matches_reference():
             assert np.array_equal(flow[::4], g[f"flow_{is_long}"][k]), (is_long, k)
     with pytest.raises(afs.AfsError):
         afs.lf_glottal_flow([300.0, 5.0, 0.5, 3.0, 0.02])  # pulse longer than the reference's ring buffer
+
+
+def test_target_sequence_trajectory_matches_reference():
+    """Host side of afs_play_target_sequences: the per-sample parameter / glottis trajectories of
+    Synthesizer::playTargetSequence (Synthesizer.cpp:1286-1411), bit-identical to the reference run behind
+    tests/golden/target_sequence.npz."""
+    g = load_golden("target_sequence.npz")
+    prm, gl = afs.target_sequence_trajectory(g["shapes"][0], g["stationary"], g["transition"], g["glottis"])
+    assert len(prm) == g["audio_noise0"].shape[1] == 9702
+    assert np.array_equal(prm[::7], g["params"]) and np.array_equal(gl[::7], g["glottis_traj"])
+    assert gl[0, 1] == 0.0 and gl[3000, 1] > 7999.0 and abs(gl[0, 0] - 100.0) < 1e-9  # silence first, F0 contour from 100 Hz
