@@ -409,10 +409,13 @@ int afs_play_target_sequences(afs_ctx *ctx, const afs_tds_options *opts, int n, 
     if (need > free_b + ctx->scratch_bytes[0] + ctx->scratch_bytes[1] + ctx->scratch_bytes[2]) return AFS_ERR_OUT_OF_MEMORY;
   }
   // host: trajectories of every sequence
-  std::vector<double> params(nf * 16), gl(nf * AFS_NUM_GLOTTIS_CONTROL);
-  for (int b = 0; b < n; b++)
-    target_sequence_trajectory(shapes + (size_t)b * 64, stationary_s, transition_s, glottis_control, sampling_rate_hz, ns,
-                               params.data() + (size_t)b * ns * 16, gl.data() + (size_t)b * ns * AFS_NUM_GLOTTIS_CONTROL);
+  std::vector<double> params(nf * 16), gl(nf * AFS_NUM_GLOTTIS_CONTROL), cosv((size_t)ns);
+  std::vector<int> seg((size_t)ns);
+  target_sequence_timebase(stationary_s, transition_s, glottis_control, sampling_rate_hz, ns, seg.data(), cosv.data(), gl.data());
+  for (int b = 0; b < n; b++) {
+    target_sequence_params(shapes + (size_t)b * 64, seg.data(), cosv.data(), ns, params.data() + (size_t)b * ns * 16);
+    if (b > 0) memcpy(gl.data() + (size_t)b * ns * AFS_NUM_GLOTTIS_CONTROL, gl.data(), (size_t)ns * AFS_NUM_GLOTTIS_CONTROL * sizeof(double));
+  }
   void *d_frames, *d_params, *d_gl, *d_audio, *d_status, *d_seeds = nullptr;
   if ((rc = scratch(ctx, 0, nf * sizeof(afs_tube_frame), &d_frames))) return rc;
   if ((rc = scratch(ctx, 1, nf * 16 * sizeof(double), &d_params))) return rc;

@@ -254,8 +254,10 @@ int target_sequence_length(const double *stationary_s, const double *transition_
   return n > 0.0 && n < 2.0e9 ? (int)n : 0;
 }
 
-void target_sequence_trajectory(const double *shapes4x16, const double *stationary_s, const double *transition_s,
-                                const double *glottis6, double SR, int numSamples, double *params, double *glottis) {
+// The time base is shared by all sequences of a call: segment and cosine factor of every sample are computed once
+// (`seg`, `cosv`; also what the reference evaluates 16 times per sample with the same argument).
+void target_sequence_timebase(const double *stationary_s, const double *transition_s, const double *glottis6, double SR,
+                              int numSamples, int *seg_out, double *cosv, double *glottis) {
   double gp[AFS_NUM_GLOTTIS_CONTROL];
   for (int i = 0; i < AFS_NUM_GLOTTIS_CONTROL; i++) gp[i] = glottis6[i];
   const double f0_Hz[4] = {100, 115, 105, 80};
@@ -271,9 +273,6 @@ void target_sequence_trajectory(const double *shapes4x16, const double *stationa
       stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2] + transition_s[2] + stationary_s[3],
   };
   const double total = b[6];
-  const double *sh[4] = {shapes4x16, shapes4x16 + 16, shapes4x16 + 32, shapes4x16 + 48};
-  double cur[16];
-  for (int j = 0; j < 16; j++) cur[j] = sh[0][j];
   for (int i = 0; i < numSamples; i++) {
     if (i < 0.1 * SR) {
       if (i < 0.05 * SR) gp[1] = 0.0;
@@ -282,20 +281,47 @@ void target_sequence_trajectory(const double *shapes4x16, const double *stationa
     if (i < b[1] * SR) gp[0] = (f0_Hz[0] + f0_Hz[1]) / 2 + (f0_Hz[1] - f0_Hz[0]) / 2 * cos((b[1] * SR - i) / (b[1] * SR) * M_PI);
     else if (i < b[3] * SR) gp[0] = (f0_Hz[2] + f0_Hz[1]) / 2 + (f0_Hz[2] - f0_Hz[1]) / 2 * cos((b[3] * SR - i) / ((b[3] - b[1]) * SR) * M_PI);
     else gp[0] = (f0_Hz[3] + f0_Hz[2]) / 2 + (f0_Hz[3] - f0_Hz[2]) / 2 * cos((b[6] * SR - i) / ((b[6] - b[3]) * SR) * M_PI);
-    int seg = -1;  // 0, 2, 4, 6: stationary shape seg / 2; 1, 3, 5: transition between shapes (seg - 1) / 2 and (seg + 1) / 2
+    // 0, 2, 4, 6: stationary shape seg / 2; 1, 3, 5: transition between shapes (seg - 1) / 2 and (seg + 1) / 2; -1: keep
+    int seg = -1;
     for (int k = 0; k < 7; k++) if (i <= b[k] * SR) { seg = k; break; }
-    if (seg >= 0) {
-      if ((seg & 1) == 0) { for (int j = 0; j < 16; j++) cur[j] = sh[seg / 2][j]; }
+    double c = 0.0;
+    if (seg >= 0 && (seg & 1)) {
+      const double t0 = b[seg - 1] * SR, t1 = b[seg] * SR, tX = i;
+      c = cos((t1 - tX) / (t1 - t0) * M_PI);
+    }
+    seg_out[i] = seg; cosv[i] = c;
+    if (i > (total - 0.1) * SR) gp[1] = -steady / 2 * cos((total * SR - i) / (total - 0.1 * SR) * M_PI) + steady / 2;
+    for (int k = 0; k < AFS_NUM_GLOTTIS_CONTROL; k++) glottis[(size_t)i * AFS_NUM_GLOTTIS_CONTROL + k] = gp[k];
+  }
+}
+
+// interpolateParameters (Synthesizer.cpp:1286-1294) along the time base, one sequence
+void target_sequence_params(const double *shapes4x16, const int *seg, const double *cosv, int numSamples, double *params) {
+  const double *sh[4] = {shapes4x16, shapes4x16 + 16, shapes4x16 + 32, shapes4x16 + 48};
+  double cur[16];
+  for (int j = 0; j < 16; j++) cur[j] = sh[0][j];
+  for (int i = 0; i < numSamples; i++) {
+    const int s = seg[i];
+    if (s >= 0) {
+      if ((s & 1) == 0) { for (int j = 0; j < 16; j++) cur[j] = sh[s / 2][j]; }
       else {
-        const double *p0 = sh[(seg - 1) / 2], *p1 = sh[(seg + 1) / 2];
-        const double t0 = b[seg - 1] * SR, t1 = b[seg] * SR, tX = i;
-        for (int j = 0; j < 16; j++) cur[j] = (p1[j] - p0[j]) / 2 * cos((t1 - tX) / (t1 - t0) * M_PI) + (p1[j] + p0[j]) / 2;
+        const double *p0 = sh[(s - 1) / 2], *p1 = sh[(s + 1) / 2];
+        const double c = cosv[i];
+        for (int j = 0; j < 16; j++) cur[j] = (p1[j] - p0[j]) / 2 * c + (p1[j] + p0[j]) / 2;
       }
     }
-    if (i > (total - 0.1) * SR) gp[1] = -steady / 2 * cos((total * SR - i) / (total - 0.1 * SR) * M_PI) + steady / 2;
     for (int j = 0; j < 16; j++) params[(size_t)i * 16 + j] = cur[j];
-    for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) glottis[(size_t)i * AFS_NUM_GLOTTIS_CONTROL + c] = gp[c];
   }
+}
+
+void target_sequence_trajectory(const double *shapes4x16, const double *stationary_s, const double *transition_s,
+                                const double *glottis6, double SR, int numSamples, double *params, double *glottis) {
+  int *seg = new int[(size_t)numSamples];
+  double *cosv = new double[(size_t)numSamples];
+  target_sequence_timebase(stationary_s, transition_s, glottis6, SR, numSamples, seg, cosv, glottis);
+  target_sequence_params(shapes4x16, seg, cosv, numSamples, params);
+  delete[] seg;
+  delete[] cosv;
 }
 
 }  // namespace afs

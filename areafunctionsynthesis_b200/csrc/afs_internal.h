@@ -66,6 +66,9 @@ size_t tds_smem_bytes();
 cudaError_t launch_area_function_raster(int n_sets, const double *d_params, afs_tube_frame *d_frames, cudaStream_t stream);
 cudaError_t launch_fill_frames(size_t n, afs_tube_frame *d_frames, const afs_tube_frame &tpl, cudaStream_t stream);
 int target_sequence_length(const double *stationary_s, const double *transition_s, double sampling_rate_hz);
+void target_sequence_timebase(const double *stationary_s, const double *transition_s, const double *glottis6, double SR,
+                              int numSamples, int *seg_out, double *cosv, double *glottis);
+void target_sequence_params(const double *shapes4x16, const int *seg, const double *cosv, int numSamples, double *params);
 void target_sequence_trajectory(const double *shapes4x16, const double *stationary_s, const double *transition_s,
                                 const double *glottis6, double SR, int numSamples, double *params, double *glottis);
 

@@ -9,10 +9,12 @@
 // sample positions, the number of samples per section and the articulator labels are the reference's.  Only
 // pow()/cos() differ from glibc by an ulp or two, hence the areas agree to ~1e-15 relative, not bitwise.
 //
-// Mapping: the work per parameter set is 4000 (pow, cos) evaluations, embarrassingly parallel over (set, section).
-// One thread per (set, section): it first replays the cheap running-x additions of the sections before its own (no
-// area evaluation), then samples its own section.  A CTA = 40 threads x 4 sets; parameters are read through the
-// read-only path (16 doubles per set), the frame fields are written once.
+// Mapping: lane = parameter set (32 sets per CTA), warp w of RASTER_WARPS owns the sections w, w + RASTER_WARPS, ...
+// A thread walks the running sample position from 0 to the end of its last section (cheap exact additions and
+// comparisons) and evaluates A(x) only inside its own sections.  All lanes of a warp are in the same section at the
+// same time, and A(x) is evaluated branch-free (the segment only selects the operands of ONE pow + cos), so the
+// five-way segment choice costs no divergence.  Parameters are read through the read-only path (16 doubles per
+// set), the frame fields are written once.
 #include <cfloat>
 
 #include "afs_internal.h"
@@ -22,56 +24,65 @@ namespace afs {
 namespace {
 enum { LLAR, ALAR, POWLAR, XP, AP, POWP, XC, AC, POWC, XA, AA, POWA, XIN, AIN, LVT, ALIP };
 
-// OneDimAreaFunction::calculateArea (OneDimAreaFunction.cpp:23-61)
+// OneDimAreaFunction::calculateArea (OneDimAreaFunction.cpp:23-61): the raised-cosine segment that contains x only
+// selects the operands; the arithmetic is the reference's expression, operation by operation.
 __device__ __forceinline__ double area_at(const double *q, double x) {
-  double a;
-  if (x <= q[LLAR]) a = q[ALAR];
-  else if (x <= q[XP]) a = (q[AP] + q[ALAR]) / 2 + (q[AP] - q[ALAR]) / 2 * cos(kPi * pow((q[XP] - x) / (q[XP] - q[LLAR]), q[POWLAR]));
-  else if (x <= q[XC]) a = (q[AC] + q[AP]) / 2 + (q[AC] - q[AP]) / 2 * cos(kPi * pow((q[XC] - x) / (q[XC] - q[XP]), q[POWP]));
-  else if (x <= q[XA]) a = (q[AA] + q[AC]) / 2 + (q[AA] - q[AC]) / 2 * cos(kPi * pow((q[XA] - x) / (q[XA] - q[XC]), q[POWC]));
-  else if (x <= q[XIN]) a = (q[AIN] + q[AA]) / 2 + (q[AIN] - q[AA]) / 2 * cos(kPi * pow((q[XIN] - x) / (q[XIN] - q[XA]), q[POWA]));
-  else a = q[ALIP];
+  const bool s0 = x <= q[LLAR], s1 = x <= q[XP], s2 = x <= q[XC], s3 = x <= q[XA], s4 = x <= q[XIN];
+  // segment [x0, x1] with areas A0 -> A1 and exponent p
+  const double x1 = s1 ? q[XP] : s2 ? q[XC] : s3 ? q[XA] : q[XIN];
+  const double x0 = s1 ? q[LLAR] : s2 ? q[XP] : s3 ? q[XC] : q[XA];
+  const double A1 = s1 ? q[AP] : s2 ? q[AC] : s3 ? q[AA] : q[AIN];
+  const double A0 = s1 ? q[ALAR] : s2 ? q[AP] : s3 ? q[AC] : q[AA];
+  const double pw = s1 ? q[POWLAR] : s2 ? q[POWP] : s3 ? q[POWC] : q[POWA];
+  double a = (A1 + A0) / 2 + (A1 - A0) / 2 * cos(kPi * pow((x1 - x) / (x1 - x0), pw));
+  a = s0 ? q[ALAR] : (s4 ? a : q[ALIP]);
   return a < 0.0 ? 0.0 : a;
 }
 }  // namespace
 
-constexpr int RASTER_SETS_PER_CTA = 4;
+constexpr int RASTER_WARPS = 5;  // 8 sections per thread
+static_assert(AFS_NUM_PM_SECTIONS % RASTER_WARPS == 0, "sections are dealt round robin to the warps");
 
-__global__ void __launch_bounds__(AFS_NUM_PM_SECTIONS *RASTER_SETS_PER_CTA)
+__global__ void __launch_bounds__(32 * RASTER_WARPS)
 area_function_raster_kernel(int n_sets, const double *__restrict__ params, afs_tube_frame *__restrict__ frames) {
-  const int sec = threadIdx.x % AFS_NUM_PM_SECTIONS;
-  const int set = blockIdx.x * RASTER_SETS_PER_CTA + threadIdx.x / AFS_NUM_PM_SECTIONS;
-  if (set >= n_sets) return;
+  const int w = threadIdx.x >> 5;
+  const int set_raw = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool active = set_raw < n_sets;
+  const int set = active ? set_raw : n_sets - 1;
   double q[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) q[i] = __ldg(params + (size_t)set * 16 + i);
   const int n = AFS_NUM_PM_SECTIONS;
   const double width = __ddiv_rn(q[LVT], (double)n);
   const double step = __dmul_rn(width, 0.01);
-  // replay the running sample position of the sections before this one (OneDimAreaFunction.cpp:94-116)
-  double x = 0.0;
-  for (int i = 0; i < sec; i++) {
-    const double end = __dmul_rn((double)(i + 1), width);
-    while (x < end) x = __dadd_rn(x, step);
-  }
-  double amin = DBL_MAX;
-  const double end = __dmul_rn((double)(sec + 1), width);
-  while (x < end) {
-    const double a = area_at(q, x);
-    if (a < amin) amin = a;
-    x = __dadd_rn(x, step);
-  }
   afs_tube_frame *f = frames + set;
-  f->length_cm[sec] = width;
-  f->area_cm2[sec] = amin < kMinArea ? kMinArea : amin;  // Tube::setPharynxMouthGeometry clamps on the way in (Tube.cpp:337)
-  f->laterality[sec] = 0.0;
-  int art;  // articulator from the sample position left after the scan (OneDimAreaFunction.cpp:118-134)
-  if (x <= q[XP]) art = AFS_OTHER_ARTICULATOR;
-  else if (x <= q[XIN] && __dadd_rn(x, width) < q[XIN]) art = AFS_TONGUE;
-  else if (x <= q[XIN]) art = AFS_LOWER_INCISORS;
-  else art = AFS_LOWER_LIP;
-  f->articulator[sec] = art;
-  if (sec == 0) f->incisor_pos_cm = q[XIN];
+  // the running sample position of the reference (OneDimAreaFunction.cpp:94-116): `x += step` inside
+  // `while (x < (i + 1) * width)`, never reset between sections
+  double x = 0.0;
+  for (int sec = 0; sec <= n - RASTER_WARPS + w; sec++) {
+    const double end = __dmul_rn((double)(sec + 1), width);
+    if (sec % RASTER_WARPS != w) {  // (warp-uniform) not mine: only advance the position
+      while (x < end) x = __dadd_rn(x, step);
+      continue;
+    }
+    double amin = DBL_MAX;
+    while (x < end) {
+      const double a = area_at(q, x);
+      if (a < amin) amin = a;
+      x = __dadd_rn(x, step);
+    }
+    if (!active) continue;
+    f->length_cm[sec] = width;
+    f->area_cm2[sec] = amin < kMinArea ? kMinArea : amin;  // Tube::setPharynxMouthGeometry clamps on the way in (Tube.cpp:337)
+    f->laterality[sec] = 0.0;
+    int art;  // articulator from the sample position left after the scan (OneDimAreaFunction.cpp:118-134)
+    if (x <= q[XP]) art = AFS_OTHER_ARTICULATOR;
+    else if (x <= q[XIN] && __dadd_rn(x, width) < q[XIN]) art = AFS_TONGUE;
+    else if (x <= q[XIN]) art = AFS_LOWER_INCISORS;
+    else art = AFS_LOWER_LIP;
+    f->articulator[sec] = art;
+    if (sec == 0) f->incisor_pos_cm = q[XIN];
+  }
 }
 
 // every frame := the template (the rasteriser only writes the pharynx / mouth fields and the incisor position)
@@ -89,8 +100,8 @@ cudaError_t launch_fill_frames(size_t n, afs_tube_frame *d_frames, const afs_tub
 
 cudaError_t launch_area_function_raster(int n_sets, const double *d_params, afs_tube_frame *d_frames, cudaStream_t stream) {
   if (n_sets <= 0) return cudaSuccess;
-  const int ctas = (n_sets + RASTER_SETS_PER_CTA - 1) / RASTER_SETS_PER_CTA;
-  area_function_raster_kernel<<<ctas, AFS_NUM_PM_SECTIONS * RASTER_SETS_PER_CTA, 0, stream>>>(n_sets, d_params, d_frames);
+  const int ctas = (n_sets + 31) / 32;
+  area_function_raster_kernel<<<ctas, 32 * RASTER_WARPS, 0, stream>>>(n_sets, d_params, d_frames);
   return cudaGetLastError();
 }
 
