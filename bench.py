@@ -438,6 +438,20 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         extra["lf_vowels"] = {"metric": "lf_vowels_per_second", "value": n_lf / dt, "unit": "vowels/s (0.65 s each, 22.05 kHz)",
                               "config": {"workload": f"{n_lf} long vowels, host API incl. pulse trains and copies"}, "cpu_baseline": None}
+        # BASELINE configs[4] (C5), one GPU's share of 65 536 sets over 8 GPUs: parameter sets -> frames -> TL spectra + 0.5 s TDS
+        from areafunctionsynthesis_b200.sweep import dataset_sweep
+        n_ds = 8192
+        dataset_sweep(ctx, pr[:n_ds], want_formants=False, tds_opts=quiet)  # warm-up (buffers)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ds = dataset_sweep(ctx, pr[:n_ds], want_formants=False, tds_opts=quiet)
+        dt = time.perf_counter() - t0
+        assert int(ds["status"].sum().item()) == 0
+        extra["dataset_sweep"] = {"metric": "parameter_sets_per_second", "value": n_ds / dt, "unit": "sets/s", "seconds": dt,
+                                  "config": {"workload": f"{n_ds} parameter sets (one GPU's share of BASELINE configs[4]) -> frames (K4) -> 2048-bin "
+                                                         "spectra (K2, bit-identical arithmetic) + 0.5 s TDS audio at 44.1 kHz (K1, noise sources off), "
+                                                         "all stages on the device"}}
+        del ds
         n_ts = 256
         gt = np.load(os.path.join(ROOT, "tests", "golden", "target_sequence.npz"))
         sh_ts = np.tile(gt["shapes"], (n_ts // 3 + 1, 1, 1))[:n_ts]

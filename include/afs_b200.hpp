@@ -176,6 +176,31 @@ inline std::vector<double> optimizeFormantsVowel(TlModel &tlModel, std::vector<d
   return finalError;
 }
 
+// Synthesizer::synthesizeVowelLf (Synthesizer.cpp:645-801) for a batch of vowels: the tubes of `tlModel`, one LF pulse
+// parameter set per tube; returns int16 audio [n][afs_lf_vowel_length(isLongVowel, samplingRate)].
+inline std::vector<int16_t> synthesizeVowelsLf(TlModel &tlModel, const std::vector<afs_lf_pulse> &lfPulses, bool isLongVowel,
+                                               double samplingRate = 22050.0) {
+  std::vector<afs_tube_frame> f(tlModel.tubes.size());
+  for (size_t i = 0; i < f.size(); i++) f[i] = tlModel.tubes[i].frame;
+  std::vector<int16_t> audio(f.size() * (size_t)afs_lf_vowel_length(isLongVowel ? 1 : 0, samplingRate), 0);
+  check(afs_synthesize_vowels_lf(tlModel.device().ctx(), &tlModel.options, (int)f.size(), f.data(), lfPulses.data(),
+                                 isLongVowel ? 1 : 0, samplingRate, audio.data(), nullptr), tlModel.device().ctx());
+  return audio;
+}
+
+// Synthesizer::playTargetSequence (Synthesizer.cpp:1299-1422) for a batch of sequences sharing the timing:
+// targetShapes[n][4][16]; returns audio [n][afs_target_sequence_length(...)] in [-1, 1].
+inline std::vector<double> playTargetSequences(Device &dev, const afs_tds_options &options, const std::vector<double> &targetShapes,
+                                               const double stationary_s[4], const double transition_s[3],
+                                               const double glottisControl[AFS_NUM_GLOTTIS_CONTROL], double samplingRate = 22050.0,
+                                               int tdsSrFactor = 2) {
+  const int n = (int)(targetShapes.size() / 64);
+  std::vector<double> audio((size_t)n * (size_t)afs_target_sequence_length(stationary_s, transition_s, samplingRate), 0.0);
+  check(afs_play_target_sequences(dev.ctx(), &options, n, targetShapes.data(), stationary_s, transition_s, glottisControl,
+                                  samplingRate, tdsSrFactor, nullptr, audio.data(), nullptr), dev.ctx());
+  return audio;
+}
+
 // Batched replacement of the Synthesizer's TDS driver: the caller queues control frames exactly like successive
 // calls of Synthesizer::synthesizeSignalTds(newTube, newGlottisParams, numNewSamples, out) (Synthesizer.cpp:515-639)
 // -- the first call primes -- and flush() runs the whole batch of utterances in one kernel launch.

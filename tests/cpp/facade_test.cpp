@@ -32,6 +32,25 @@ int main() {
     std::vector<double> prm(a_params, a_params + 16);
     const std::vector<double> err = afs::optimizeFormantsVowel(tl, &prm, {650.0, 1300.0, 2600.0}, 1.0, 0.0, nullptr, 3);
     std::printf("optimizer %.12g %.12g %.12g\n", err[0], prm[2], prm[8]);
+    // --- Synthesizer::synthesizeVowelLf / playTargetSequence-style use ---
+    afs_lf_pulse lf;
+    afs_lf_pulse_default(&lf);
+    const std::vector<int16_t> pcm = afs::synthesizeVowelsLf(tl, {lf, lf}, false);
+    long long e16 = 0;
+    for (int16_t v : pcm) e16 += (long long)v * v;
+    std::printf("lfvowels %zu %lld\n", pcm.size(), e16);
+    {
+      afs_tds_options to;
+      afs_tds_options_default(&to);
+      to.generate_noise_sources = 0;
+      std::vector<double> shapes(64);
+      for (int k = 0; k < 4; k++) for (int j = 0; j < 16; j++) shapes[16 * k + j] = a_params[j] * (j == 7 ? 1.0 + 0.1 * k : 1.0);
+      const double st[4] = {0.02, 0.01, 0.01, 0.02}, tr[3] = {0.02, 0.02, 0.02}, g6[6] = {120, 8000, 0.01, 0.01, 0, -40};
+      const std::vector<double> a = afs::playTargetSequences(dev, to, shapes, st, tr, g6);
+      double et = 0;
+      for (double v : a) et += v * v;
+      std::printf("targets %zu %.12e\n", a.size(), et);
+    }
     // --- Synthesizer-style use (Synthesizer.cpp:515-639): prime, then one 50 ms frame ---
     afs::TdsSynthesizer syn(dev, 2);
     afs::Tube tubes[2] = {tl.tubes[0], tl.tubes[1]};

@@ -48,6 +48,15 @@ def test_facade_matches_ctypes_path(ctx, shapes):
     assert int(lines["impulse"][0]) == h.size and float(lines["impulse"][1]) == h[0, 100] and float(lines["impulse"][2]) == h[1, 100]
     o = ctx.optimize_formants_vowel(shapes["params"][0], [650.0, 1300.0, 2600.0], 1.0, 0.0, None, 3)
     np.testing.assert_allclose([float(x) for x in lines["optimizer"]], [o["final_error"][0], o["params"][0, 2], o["params"][0, 8]], rtol=1e-9)
+    import areafunctionsynthesis_b200 as afs
+    pcm = ctx.synthesize_vowels_lf(fr, [[300.0, 120.0, 0.5, 3.0, 0.02]] * 2, False)
+    assert int(lines["lfvowels"][0]) == pcm.size and int(lines["lfvowels"][1]) == int((pcm.astype(np.int64) ** 2).sum())
+    p0 = shapes["params"][0]
+    sh = np.stack([p0 * np.where(np.arange(16) == 7, 1.0 + 0.1 * k, 1.0) for k in range(4)])
+    ta, _ = ctx.play_target_sequences(sh, [0.02, 0.01, 0.01, 0.02], [0.02, 0.02, 0.02], [120, 8000, 0.01, 0.01, 0, -40], 22050.0, 2,
+                                      opts=afs.tds_options_default(noise=False))
+    assert int(lines["targets"][0]) == ta.size
+    assert abs(float(lines["targets"][1]) - float((ta ** 2).sum())) <= 1e-9 * float((ta ** 2).sum())
     gl = np.array([[[120, 8000, 0.01, 0.01, 0, -40]] * 2, [[150, 8000, 0.01, 0.01, 0, -40]] * 2], dtype=float)
     a, _, st = ctx.tds_synthesize(np.stack([fr, fr], axis=1), gl, [1102], 44100.0, 2)
     assert int(lines["audio"][0]) == a.size and int(lines["audio"][3]) == 0
