@@ -712,8 +712,20 @@ __device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, con
   }
 }
 
+#ifdef AFS_TDS_TIMING
+#define SW_TICK(k) do { const long long now__ = clock64(); sw_t[k] += now__ - sw_last; sw_last = now__; } while (0)
+#else
+#define SW_TICK(k) do { } while (0)
+#endif
 __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
-                                                const SCfg &c, SRegs &st, double psrc) {
+                                                const SCfg &c, SRegs &st, double psrc
+#ifdef AFS_TDS_TIMING
+                                                , long long *sw_t
+#endif
+                                                ) {
+#ifdef AFS_TDS_TIMING
+  long long sw_last = clock64();
+#endif
   const int n0 = c.base + c.ks, pw = wc_prev(wc_);
   const STab &C = S.stab[w];
   double d84 = 0.0, r0;
@@ -729,12 +741,14 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
     }
     set_first(c, st.x, r0);
   }
+  SW_TICK(0);
   {  // sinus leaves into their clique partners (zero constants in the warps without leaves)
     const double a0 = C.le[0] * C.lw[0] * st.lx[0], b0 = C.lg[0] * C.lw[0] * st.lx[0];
     const double a1 = C.le[1] * C.lw[1] * st.lx[1], b1 = C.lg[1] * C.lw[1] * st.lx[1];
     st.x[0] += c.n2 ? a0 : 0.0; st.x[1] += c.n2 ? a1 - b0 : 0.0; st.x[2] -= c.n2 ? b1 : 0.0;
     st.x[5] += c.n2 ? 0.0 : a0; st.x[6] += c.n2 ? 0.0 : a1 - b0; st.x[7] -= c.n2 ? 0.0 : b1;
   }
+  SW_TICK(1);
   double rc = st.x[0], dra = 0.0;
 #pragma unroll
   for (int k = 0; k < KS - 1; k++) {  // (T = W = H = 0 on the slots that are not interior currents)
@@ -744,6 +758,7 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
     st.x[k] = g;
   }
   st.x[KS - 1] = rc;
+  SW_TICK(2);
   if (!c.fossa) {
     S.sepR[wc_b(wc_)][lane] = rc;
     S.sideDR[w][lane] = dra;
@@ -760,6 +775,7 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
     S.lf[4][lane] = -e + e * g * wv;   // coupling 28 <-> 29
     st.x[3] = r84; st.w84 = wv; st.e28 = e; st.g28 = g;
   }
+  SW_TICK(3);
 }
 
 template <bool NOISE>
@@ -1615,6 +1631,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   }
 #ifdef AFS_TDS_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+  long long sw_acc[4] = {0, 0, 0, 0};
 #endif
 
   for (int n = 0; n <= T && T > 0; n++) {
@@ -1678,7 +1695,11 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     if (ROLE == 0) dwarp_eliminate<NOISE, OPT>(P, S, lane, warp, wcfg, dst, n & 1);
     if (ROLE == 1) {
       const double psrc = X.ratio1 * S.gctl[0][G_PRESSURE][lane] + X.ratio * S.gctl[1][G_PRESSURE][lane];
+#ifdef AFS_TDS_TIMING
+      swarp_eliminate(P, S, lane, warp, wcfg, scfg, sst, psrc, sw_acc);
+#else
       swarp_eliminate(P, S, lane, warp, wcfg, scfg, sst, psrc);
+#endif
     }
     if (ROLE == 3 && OPT && (P.transvelar || P.var_loss)) {
       // this step's filter outputs (same expression as their consumers use), then the history parts of the next step
@@ -1745,6 +1766,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   }
 #ifdef AFS_TDS_TIMING
   if (A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) A.dump[warp * 8 + k] = (double)tacc[k];
+  if (ROLE == 1 && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) A.dump[136 + warp * 4 + k] = (double)sw_acc[k];
   if (ROLE == 3 && NOISE && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) { A.dump[128 + k] = (double)g_nz_t[k]; g_nz_t[k] = 0; }
 #endif
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;

@@ -22,3 +22,8 @@ if noise:
     nz = buf[128:132] / steps
     print(f"X2 noise_sources per step (lane 0 of CTA 0; passes/draws are that lane's, the warp runs the maximum over its lanes): "
           f"target stage {nz[0]:.0f} cycles, source loop {nz[1]:.0f} cycles, {nz[2]:.1f} passes, {nz[3]:.1f} draws")
+sw = buf[136:200].reshape(16, 4) / steps
+print("static warps, swarp_eliminate: first row | sinus leaves | chain | publish")
+for w in range(16):
+    if sw[w].sum() > 0:
+        print(f"{roles[w]:>4s} " + " ".join(f"{v:8.0f}" for v in sw[w]))
