@@ -1743,15 +1743,15 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     if (ROLE != 2) {
       bar_sync(1, TDS_THREADS);
       // ============ reduced system over the separators ============
-      if (warp == W_T0) reduced_forward(S, lane, 0);
-      if (warp == W_T1) reduced_forward(S, lane, 1);
-      if (warp == W_T2) reduced_forward(S, lane, 2);
-      bar_sync(2, TDS_THREADS - 32);
-      if (warp == W_T0) reduced_junction(S, lane);
-      bar_sync(2, TDS_THREADS - 32);
-      if (warp == W_T0) reduced_back(S, lane, 0);
-      if (warp == W_T1) reduced_back(S, lane, 1);
-      if (warp == W_T2) reduced_back(S, lane, 2);
+      // (the three warps of the reduced system meet on their own barrier; the twelve others only wait for the result)
+      if (warp == W_T0 || warp == W_T1 || warp == W_T2) {
+        const int chain = warp == W_T0 ? 0 : warp == W_T1 ? 1 : 2;
+        reduced_forward(S, lane, chain);
+        bar_sync(3, 96);
+        if (warp == W_T0) reduced_junction(S, lane);
+        bar_sync(3, 96);
+        reduced_back(S, lane, chain);
+      }
       AFS_TICK(4);
       bar_sync(2, TDS_THREADS - 32);
     }
