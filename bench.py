@@ -19,6 +19,12 @@ stream; `e2e` is the same metric through the host-buffer C-ABI call (H2D + kerne
 region).  `roofline` is against the FP64 FMA peak measured live by afs_probe_fp64_tflops (both kernels are
 FP64-pipe bound scalar recurrences) with W_tds = 1.0e4 flop per tract-step and W_tl = 8.0e3
 flop per (area function, bin).  `cpu_baseline` times the compiled reference (oracle/_ref) on the host cores.
+
+Further objects of the same JSON line (rank 0; the small legs only at N = 1): `noise_sources_on` (the TDS batch with
+the reference's default noise sources), `gather` (NCCL all-gather of the audio after the compute),
+`tl.fast_arithmetic` (afs_tl_options.arithmetic = FAST, with its error against the bit-identical output of this run),
+`raster` (K4), `formant_optimizer`, `lf_vowels`, `target_sequences`, `dataset_sweep` (one GPU's share of BASELINE
+configs[4]) -- each with the reference's CPU figure beside it where the reference has that path.
 """
 import argparse
 import json
