@@ -45,6 +45,9 @@ __device__ __forceinline__ cx cx_rdiv(double x, cx d) {
 #include "tl_algebra.cuh"
 
 constexpr int TLF_THREADS = 128;
+#ifndef AFS_TLF_MINB
+#define AFS_TLF_MINB 4  // 128 registers, 16 warps/SM (96 registers / 20 warps spills: 1.96 vs 1.70 ms)
+#endif
 
 struct __align__(16) TlElem {
   double rsq;  // boundary layer: Re(Za) = rsq*sqrt(w)     (0 when the option is off)
@@ -367,7 +370,7 @@ tl_sweep_fast_kernel(const TlParams p, const TlFastProgram prog, const afs_tube_
 
 // Direct instantiation: FLOW_SOURCE_TF with the source in the trachea..pharynx chain (sections 0..40) -- the
 // spectrum getFormants and getImpulseResponse ask for.  Straight-line walk of the chains, three live matrices.
-__global__ void __launch_bounds__(TLF_THREADS, 4)
+__global__ void __launch_bounds__(TLF_THREADS, AFS_TLF_MINB)
 tl_sweep_fast_direct_kernel(const TlParams p, const afs_tube_frame *__restrict__ tubes, double *__restrict__ out_re,
                             double *__restrict__ out_im) {
   __shared__ TlFastShared S;
@@ -395,7 +398,39 @@ tl_sweep_fast_direct_kernel(const TlParams p, const afs_tube_frame *__restrict__
         lo = hi + 1;
       }
     };
-    if (fossa) {  // side-branch chain first (TlModel.cpp:554-561): its input impedance is A/C (closed end)
+    // The two radiating branches first: of the mouth and nose chains only (A*Zrad + B) and (C*Zrad + D) are ever
+    // needed (their ratio is the branch's input impedance, and they close the bottom row of the coupled products),
+    // so two complex numbers per branch stay live instead of a matrix.
+    const cx mouthRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[0]);
+    const cx noseRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[1]);
+    for (int k = MOUTH0; k <= MOUTH_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
+    cx mA, mC, nA, nC;
+    {
+      const m22 F = chain_product(c);
+      mA = cx_add(cx_mul(F.A, mouthRad), F.B); mC = cx_add(cx_mul(F.C, mouthRad), F.D);
+    }
+    // nose with the sinus shunts behind sections 73, 74, 76, 77 (Tube.cpp:35-38)
+    chain_reset(c);
+    if (p.o.paranasal_sinuses) {
+      int k = NOSE0;
+      for (; k <= NOSE0 + 8; k++) chain_section(S, b, pre, b.g0, k, c);
+      chain_sinus(S, b, SINUS0, c);
+      chain_section(S, b, pre, b.g0, k++, c);
+      chain_sinus(S, b, SINUS0 + 1, c);
+      for (; k <= NOSE0 + 11; k++) chain_section(S, b, pre, b.g0, k, c);
+      chain_sinus(S, b, SINUS0 + 2, c);
+      chain_section(S, b, pre, b.g0, k++, c);
+      chain_sinus(S, b, SINUS0 + 3, c);
+      for (; k <= NOSE_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
+    } else {
+      for (int k = NOSE0; k <= NOSE_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
+    }
+    {
+      const m22 F = chain_product(c);
+      nA = cx_add(cx_mul(F.A, noseRad), F.B); nC = cx_add(cx_mul(F.C, noseRad), F.D);
+    }
+    chain_reset(c);
+    if (fossa) {  // side-branch chain (TlModel.cpp:554-561): its input impedance is A/C (closed end)
       for (int k = FOSSA0; k <= FOSSA_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
       fossaY = cx_div(c.K.C, c.K.A);
       chain_reset(c);
@@ -416,43 +451,18 @@ tl_sweep_fast_direct_kernel(const TlParams p, const afs_tube_frame *__restrict__
     if (fossa && s == PHAR0 + FOSSA_COUPLING) chain_shunt(c, fossaY);
     run(s + 1, PHAR_LAST, true);
     const m22 R = chain_product(c);
-    // mouth
-    chain_reset(c);
-    for (int k = MOUTH0; k <= MOUTH_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
-    const m22 P64 = chain_product(c);
-    // nose with the sinus shunts behind sections 73, 74, 76, 77 (Tube.cpp:35-38)
-    chain_reset(c);
-    if (p.o.paranasal_sinuses) {
-      int k = NOSE0;
-      for (; k <= NOSE0 + 8; k++) chain_section(S, b, pre, b.g0, k, c);
-      chain_sinus(S, b, SINUS0, c);
-      chain_section(S, b, pre, b.g0, k++, c);
-      chain_sinus(S, b, SINUS0 + 1, c);
-      for (; k <= NOSE0 + 11; k++) chain_section(S, b, pre, b.g0, k, c);
-      chain_sinus(S, b, SINUS0 + 2, c);
-      chain_section(S, b, pre, b.g0, k++, c);
-      chain_sinus(S, b, SINUS0 + 3, c);
-      for (; k <= NOSE_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
-    } else {
-      for (int k = NOSE0; k <= NOSE_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
-    }
-    const m22 P83 = chain_product(c);
 
     // TlModel::getFlowSourceTF, trachea..pharynx branch (TlModel.cpp:1312-1368); only the bottom rows of the two
-    // coupled products are needed
-    const cx mouthRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[0]);
-    const cx noseRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[1]);
-    const cx zn = load_through(P83, noseRad), zm = load_through(P64, mouthRad);
+    // coupled products are needed: [R * shunt(1/zn) * P64] bottom row times (Zrad, 1) = (R.C + R.D/zn) mA + R.D mC
+    const cx zn = cx_div(nA, nC), zm = cx_div(mA, mC);
     const cx zin = cx_add(load_through(R, par(zn, zm)), srcZa);
     zout = cx_add(zout, srcZa);
     cx factor = par(cx_rdiv(1.0, srcYb), zout);
     factor = cx_div(factor, cx_add(zin, factor));
-    cx q = cx_add(R.C, cx_div(R.D, zn));  // bottom row of R * shunt(1/zn), then * P[64]
-    cx kc = cx_add(cx_mul(q, P64.A), cx_mul(R.D, P64.C)), kd = cx_add(cx_mul(q, P64.B), cx_mul(R.D, P64.D));
-    cx v = cx_div(factor, cx_add(cx_mul(kc, mouthRad), kd));
+    cx q = cx_add(R.C, cx_div(R.D, zn));
+    cx v = cx_div(factor, cx_add(cx_mul(q, mA), cx_mul(R.D, mC)));
     q = cx_add(R.C, cx_div(R.D, zm));
-    kc = cx_add(cx_mul(q, P83.A), cx_mul(R.D, P83.C)); kd = cx_add(cx_mul(q, P83.B), cx_mul(R.D, P83.D));
-    v = cx_add(v, cx_div(factor, cx_add(cx_mul(kc, noseRad), kd)));
+    v = cx_add(v, cx_div(factor, cx_add(cx_mul(q, nA), cx_mul(R.D, nC))));
     const size_t o = (size_t)tube * p.num_freq + bin;
     out_re[o] = v.re;
     out_im[o] = v.im;
