@@ -49,6 +49,9 @@
 #include "afs_internal.h"
 
 namespace afs {
+#ifdef AFS_TDS_TIMING
+__device__ long long g_nz_t[8];  // X2, lane 0 of CTA 0: cycles in the target stage / the source loop, passes, draws; [4] X2 waiting for X1, [5..7] X1: decay passes, waiting for X2, draws
+#endif
 
 constexpr int LANES = 28;                     // tracts per CTA = row length of the [item][lane] arrays (224 B).  4096
                                               // utterances on 148 SMs are 27.7 per SM; hardware lanes 28..31 duplicate
@@ -59,6 +62,19 @@ constexpr int TDS_THREADS = NW * 32;
 constexpr int KD = 6;                         // sections per dynamic-chain warp
 constexpr int NSX = NS + 1;                   // + one all-zero dummy section (index 93)
 constexpr double kTheta = 0.515;              // TdsModel.cpp:15
+#ifndef AFS_NZ_RING
+#define AFS_NZ_RING 18
+#endif
+#ifdef AFS_TDS_TIMING
+#define NZ_CLK(k, t0) do { if (blockIdx.x == 0 && lane == 0) { const long long now__ = clock64(); atomicAdd((unsigned long long *)&g_nz_t[k], (unsigned long long)(now__ - (t0))); (t0) = now__; } } while (0)
+#define NZ_CLK0(t0) long long t0 = clock64()
+#else
+#define NZ_CLK(k, t0) do { } while (0)
+#define NZ_CLK0(t0) do { } while (0)
+#endif
+constexpr int NZ_RING = AFS_NZ_RING;          // pre-generated noise sums per tract (even; more draws in one step fall
+                                              // back to in-line generation on warp X2)
+static_assert(NZ_RING % 2 == 0 && NZ_RING >= 2 && NZ_RING <= 32, "NZ_RING");
 constexpr double kTheta1 = 1.0 - kTheta;
 
 // Warp roles.  The id also fixes the SM sub-partition (id % 4); the order balances the FP64 work of the four.
@@ -79,6 +95,7 @@ struct TdsParams {
   int dump_step;
   int noise;                        // generate_noise_sources (TdsModel.h:87)
   double nz_F, nm_a, nm_1a;         // 1 - exp(-2 pi 40 dt) (TdsModel.cpp:1637), exp(-2 pi 500 dt) and 1 - that (:2052)
+  double nz_x2000;                  // exp(-2 pi 2000 dt): low-pass coefficient of a source at the upper cutoff limit
   double dt, idt, th, dtth, dtth1;  // 1/fs, 1/(dt*theta), theta1/theta, dt*theta, dt*theta1
   double ith, fs;                   // theta/theta1, fs
   double fsar, k_ent;
@@ -133,7 +150,12 @@ struct TdsSmem {
   double nmag[42][LANES];                        // noiseMagnitude (TdsModel.h:143) of the currents a constriction can feed
   double namp[41][LANES], ncut[41][LANES], nout[41][LANES];  // currentAmp, cutoff, last filter output (TdsModel.h:101-112)
   double inc[2][LANES];                          // incisor position of the two control frames
+  // the source stage is split between warps X2 (sources a constriction feeds this step) and X1 (sources that only
+  // decay): live sources and the sources that draw a sample this step, [0] = X2's share, [1] = X1's
+  unsigned long long nzlive[2][LANES], nzdraw[2][LANES];
+  double nzlip[LANES];                           // noiseMagnitude of the flow through the lips (currents 93 + 94)
   uint32_t rng[34][LANES];                       // glibc random() TYPE_3 ring (r[i] = r[i-3] + r[i-31])
+  uint32_t nzsum[NZ_RING][LANES];                // the next NZ_RING sums of twelve rand() draws, generated ahead by X2
   unsigned char art[AFS_NUM_PM_SECTIONS][LANES]; // articulator of the LEFT control frame (Tube.cpp:452)
   // constrictions of the NEXT step, found by warp X1 while the others solve (the scan does not depend on the state):
   // packed {valid, kind, teeth, lateral, nar + 1, up} and the downstream factor, double buffered by step parity
@@ -143,9 +165,10 @@ struct TdsSmem {
   SRec srec[NSX];
   double wallc[4][3];             // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = zeros
   double rcn[8];                  // constant factors of the reduced system (reduced_constants)
-  STab stab[NW];
+  STab stab[6];                   // static chains only (stab_slot)
 };
 
+__device__ __forceinline__ int stab_slot(int w) { return w == W_F ? 4 : w == W_N1 ? 5 : w - W_T0; }  // T0, T1, N2, T2 = 8..11
 __device__ __forceinline__ int wall_type(int s) { return s <= TRACHEA_LAST ? 1 : s >= SINUS0 ? 2 : 0; }
 __device__ __forceinline__ bool is_dyn(int s) { return s >= GLOT_LO && s <= 68; }
 
@@ -340,16 +363,23 @@ struct StepCtx {
   bool dumping;
 };
 
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+// Named barriers of the solve phase.  Warp X1 (glottis model, output filters) only has to be back for the next pass A:
+// it ARRIVES at barrier 1 once it has read what the others will overwrite and takes no part in barrier 2.
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
 // noise sources (warp X2), see noise_scan / noise_sources below
 struct NoiseCons {
   int valid, nar, kind, up, teeth, lateral;  // nar: narrowest section as pharynx/mouth index, -1 = upper glottis
   double downF;                              // kind: 0 vocal folds, 1 tongue, 2 lower lip
 };
 struct NoiseRegs {
-  unsigned long long nz;  // sources with a non-zero amplitude
   int ri;                 // position in the random() ring
+  int head, used;         // oldest entry of the ring of pre-generated sums; entries consumed by the current step
   double lips;            // sample of the lips dipole source (enters all four radiation rows)
   double nm93, nm94;      // noiseMagnitude of the mouth radiation currents
+  double asp, gain;       // aspiration strength (dB) the cached vocal-fold source gain belongs to
 };
 
 __device__ __forceinline__ void dump_section(const TdsParams &P, double *dump, int sec, double p, double pr, double wc,
@@ -634,7 +664,7 @@ __device__ __noinline__ void swarp_build(const TdsParams &P, TdsSmem &S, const i
   }
   T.DB = dc; T.FF = f; T.DDA = dda;
   if (c.fossa) { T.WB = 1.0 / dc; T.CA = dda + f * f * T.WB; }
-  if (lane == 0) S.stab[w] = T;
+  if (lane == 0) S.stab[stab_slot(w)] = T;
   // boundary record of the last section and the constant separator data
   const SRec last = S.srec[c.base + KS - 1];
   S.bE[w][lane] = last.E; S.bL[w][lane] = last.L; S.bR[w][lane] = last.R1; S.bI[w][lane] = last.invr;
@@ -727,7 +757,7 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
   long long sw_last = clock64();
 #endif
   const int n0 = c.base + c.ks, pw = wc_prev(wc_);
-  const STab &C = S.stab[w];
+  const STab &C = S.stab[stab_slot(w)];
   double d84 = 0.0, r0;
   {  // first row: the source section belongs to another warp (or is the lung pressure source)
     const double c0 = first_of(c, st.c);
@@ -781,7 +811,7 @@ __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, 
 template <bool NOISE>
 __device__ __forceinline__ void swarp_back(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
                                            const SCfg &c, SRegs &st) {
-  const STab &C = S.stab[w];
+  const STab &C = S.stab[stab_slot(w)];
   double ua, ub;
   if (c.fossa) {
     const double u28 = S.sepR[S28][lane], u29 = S.sepR[S29][lane];
@@ -884,13 +914,12 @@ __device__ __forceinline__ void radiation_update(const TdsParams &P, const int l
     const double ur = fma(u, P.idt, -rr.c[j]);
     rr.c[j] = fma(ur, P.th, u * P.idt);
   }
-  nr.nm93 = fma(P.nm_a, nr.nm93, P.nm_1a * rr.u[0]);
-  nr.nm94 = fma(P.nm_a, nr.nm94, P.nm_1a * rr.u[1]);
   if (X.dumping && lane == 0) {
     for (int j = 0; j < 4; j++) { dump[279 + 93 + j] = rr.u[j]; dump[376 + 93 + j] = (rr.c[j] - rr.u[j] * P.idt) * P.ith; }
   }
 }
-__device__ __forceinline__ void radiation_back(TdsSmem &S, const int lane, RadRegs &rr) {
+template <bool NOISE>
+__device__ __forceinline__ void radiation_back(const TdsParams &P, TdsSmem &S, const int lane, RadRegs &rr, NoiseRegs &nr) {
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     const double *kp = rr.keep[q];
@@ -899,6 +928,11 @@ __device__ __forceinline__ void radiation_back(TdsSmem &S, const int lane, RadRe
     const double uL = (kp[1] + kp[5] * us - kp[6] * uR) * kp[0];
     rr.u[2 * q] = uR; rr.u[2 * q + 1] = uL;
     S.uext[UX_RADM + q][lane] = uR + uL;
+  }
+  if (NOISE) {  // noiseMagnitude of the mouth radiation currents (TdsModel.cpp:2052), for the lip constriction of the next step
+    nr.nm93 = fma(P.nm_a, nr.nm93, P.nm_1a * rr.u[0]);
+    nr.nm94 = fma(P.nm_a, nr.nm94, P.nm_1a * rr.u[1]);
+    S.nzlip[lane] = nr.nm93 + nr.nm94;
   }
 }
 
@@ -928,15 +962,26 @@ __device__ __forceinline__ void nzc_load(const TdsSmem &S, const int lane, int b
 }
 
 // constriction records of step n from the pre-pass (tds_noise_scan_kernel) into the shared-memory buffer `buf`
+struct NzcRec { uint32_t i[4]; double f[4]; };
 template <class KA>
-__device__ __forceinline__ void nzc_fetch(TdsSmem &S, const KA &A, const int lane, int total_steps, int n, int buf) {
+__device__ __forceinline__ void nzc_fetch_issue(const KA &A, int total_steps, int n, NzcRec &R) {
   const int hw_lane = threadIdx.x & 31;
   const size_t base = ((size_t)blockIdx.x * (size_t)total_steps + (size_t)n) * 4;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    S.nzc_i[buf][k][lane] = __ldg(A.nzc_i + (base + k) * 32 + hw_lane);
-    S.nzc_f[buf][k][lane] = __ldg(A.nzc_f + (base + k) * 32 + hw_lane);
+    R.i[k] = __ldg(A.nzc_i + (base + k) * 32 + hw_lane);
+    R.f[k] = __ldg(A.nzc_f + (base + k) * 32 + hw_lane);
   }
+}
+__device__ __forceinline__ void nzc_fetch_store(TdsSmem &S, const int lane, int buf, const NzcRec &R) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) { S.nzc_i[buf][k][lane] = R.i[k]; S.nzc_f[buf][k][lane] = R.f[k]; }
+}
+template <class KA>
+__device__ __forceinline__ void nzc_fetch(TdsSmem &S, const KA &A, const int lane, int total_steps, int n, int buf) {
+  NzcRec R;
+  nzc_fetch_issue(A, total_steps, n, R);
+  nzc_fetch_store(S, lane, buf, R);
 }
 __device__ __forceinline__ uint32_t nzc_pack(const NoiseCons &c) {
   return (uint32_t)(c.valid & 1) | ((uint32_t)(c.kind & 3) << 1) | ((uint32_t)(c.teeth & 1) << 3) | ((uint32_t)(c.lateral & 1) << 4) |
@@ -1119,121 +1164,158 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
   }
 }
 
-#ifdef AFS_TDS_TIMING
-__device__ long long g_nz_t[4];  // X2, lane 0 of CTA 0: cycles in the target stage / the source loop, passes, draws
-#define NZ_T0 const long long nzt0__ = clock64()
-#define NZ_T1 const long long nzt1__ = clock64(); long long nz_passes__ = 0, nz_draws__ = 0
-#define NZ_PASS nz_passes__++
-#define NZ_DRAW nz_draws__++
-#define NZ_T2 do { if (blockIdx.x == 0 && lane == 0) { g_nz_t[0] += nzt1__ - nzt0__; g_nz_t[1] += clock64() - nzt1__; g_nz_t[2] += nz_passes__; g_nz_t[3] += nz_draws__; } } while (0)
-#else
-#define NZ_T0
-#define NZ_T1
-#define NZ_PASS
-#define NZ_DRAW
-#define NZ_T2
-#endif
-// State-dependent part: target amplitudes from the flow through the constrictions (TdsModel.cpp:1430-1612), then
-// one sample of every source that is not silent (TdsModel.cpp:1630-1708).
-__device__ __noinline__ void noise_sources(const TdsParams &P, TdsSmem &S, const int lane, NoiseRegs &N,
-                                           const NoiseCons (&C)[4], const double r, const double r1, const int par,
-                                           const double asp_dB) {
-  NZ_T0;
-  // The scan fixes the kind of every slot (0: vocal folds, 1 and 2: tongue, 3: lower lip), so the four slots are
-  // straight-line code without branches on the kind; an invalid slot is computed on clamped indices and masked out:
-  // four independent dependency chains that overlap instead of four divergent branches in a row.
-  int tIdx[8];
-  double tAmp[8], tCut[8];
-  unsigned long long todo = N.nz, targeted = 0;
-  constexpr int NPM = AFS_NUM_PM_SECTIONS;
-  auto flow_through = [&](int nar) {  // noiseMagnitude of the currents leaving pharynx/mouth section nar (0..39)
-    const double f = S.nmag[nar + 1][lane];
-    const double extra = S.nmag[nar == 3 ? 41 : 40][lane];  // section 28: currents 29 and 84; section 40: currents 41 and 65
-    const double fl = (nar == 3 || nar == 15) ? f + extra : f;
-    return nar == NPM - 1 ? N.nm93 + N.nm94 : fl;
-  };
-  auto clamp_area = [](double A) { if (A < kMinArea) A = kMinArea; if (A < 0.1) A = 0.1; return A; };
-  auto emit = [&](int k, bool valid, double fullAmp, double cutoff) {
-    if (cutoff < 50.0) cutoff = 50.0;
-    if (cutoff > 2000.0) cutoff = 2000.0;
-    const int up = C[k].up, down = up < NPM - 1 ? up + 1 : NPM;
-    tIdx[2 * k] = valid ? up : -1; tAmp[2 * k] = (1.0 - C[k].downF) * fullAmp; tCut[2 * k] = cutoff;
-    tIdx[2 * k + 1] = valid ? down : -1; tAmp[2 * k + 1] = C[k].downF * fullAmp; tCut[2 * k + 1] = cutoff;
-    if (valid) targeted |= (1ull << up) | (1ull << down);
-  };
-  {  // slot 0: the glottis (upper glottis section, current 25)
-    const double A = clamp_area(S.glArea[par][1][lane]);
-    double flow = S.nmag[0][lane];
-    if (flow < 0.0) flow = 0.0;
-    const double v = fast_div(flow, A);
-    const double gain = 0.5e-7 * exp(asp_dB * (2.302585092994045684 / 20.0));  // 10^(dB/20)
-    double fullAmp = gain * fabs(v) * v * v * fast_sqrt(A);
-    if (C[0].lateral) fullAmp = 0.0;
-    emit(0, C[0].valid != 0, fullAmp, 6000.0);
-  }
-#pragma unroll
-  for (int k = 1; k < 3; k++) {  // slots 1, 2: tongue constrictions
-    const int nar = min(max(C[k].nar, 0), NPM - 1);
-    const double A = clamp_area(nz_area(S, lane, r, r1, nar));
-    double flow = flow_through(nar);
-    if (flow < 0.0) flow = 0.0;
-    const double v = fast_div(flow, A);
-    const double id = fast_rsqrt(A * (4.0 / kPi));  // 1/d, d = sqrt(4 A / pi)
-    const double gain = C[k].teeth ? 10.0e-7 : 5.0e-7;
-    double fullAmp = gain * fabs(v) * v * v * fast_sqrt(A);
-    if (C[k].lateral) fullAmp = 0.0;
-    emit(k, C[k].valid != 0, fullAmp, 0.15 * v * id);
-  }
-  {  // slot 3: the lips
-    const int nar = min(max(C[3].nar, 0), NPM - 1);
-    const double A = clamp_area(nz_area(S, lane, r, r1, nar));
-    double flow = flow_through(nar);
-    if (flow < 0.0) flow = 0.0;
-    const double v = fast_div(flow, A);
-    double fullAmp = 2.0e-7 * fabs(v) * v * v * fast_sqrt(A);
-    if (C[3].lateral) fullAmp = 0.0;
-    emit(3, C[3].valid != 0, fullAmp, 6000.0);
-  }
-  todo |= targeted;
-  N.lips = 0.0;
-  NZ_T1;
-  // Pass 1, every live source: amplitude filter (TdsModel.cpp:1630-1660) and who draws a sample.  Pass 2, the
-  // drawing sources only, in ascending index order like the reference: filter coefficient, twelve random numbers,
-  // one-pole low-pass.  (One loop doing both made EVERY pass of the warp as expensive as a draw, because some lane
-  // draws in almost every pass; sources that only decay are the majority.)
-  unsigned long long draws = 0;
-  while (todo) {
-    NZ_PASS;
-    const int j = __ffsll((long long)todo) - 1;
-    todo &= todo - 1;
-    double tgt = 0.0, cut = 0.0;
-    bool hit = false;
-    if ((targeted >> j) & 1ull) {
-#pragma unroll
-      for (int e = 0; e < 8; e++) if (tIdx[e] == j) { tgt = tAmp[e]; cut = tCut[e]; hit = true; }  // the last one wins
+// One sample of source j from the sum of twelve rand() draws (TdsModel.cpp:1680-1708).  S.ncut[j] holds the low-pass
+// coefficient exp(-2 pi f_c dt) of the source's cutoff frequency (IirFilter::createSinglePoleLowpass,
+// IirFilter.cpp:235-243), written by warp X2 whenever a constriction feeds the source: a source that only decays
+// keeps its cutoff, so warp X1 never evaluates an exponential.
+__device__ __forceinline__ double nz_sample(const double x, const uint32_t isum, const double last) {
+  double in = (double)(int32_t)isum;  // 12 x rand() summed in an int: wraps around like the reference's
+  in = (in * (1.0 / 2147483647.0) - 6.0) * 0.28867513459481288225;  // / RAND_MAX, - 6, / sqrt(12)
+  return __dadd_rn(__dmul_rn(__dsub_rn(1.0, x), in), __dmul_rn(x, last));
+}
+__device__ __forceinline__ void nz_lowpass(TdsSmem &S, const int lane, const int j, const uint32_t isum) {
+  S.nout[j][lane] = nz_sample(S.ncut[j][lane], isum, S.nout[j][lane]);
+}
+// The drawing sources `mine` of one warp; `all` = every drawing source of the step (rank = position in the rand() stream)
+__device__ __forceinline__ void nz_draw_ranked(TdsSmem &S, const int lane, unsigned long long mine,
+                                               const unsigned long long all, const int head) {
+  while (mine) {
+    const int j = __ffsll((long long)mine) - 1;
+    mine &= mine - 1;
+    const int rank = __popcll(all & ((1ull << j) - 1ull));
+    if (rank < NZ_RING) {
+      int i = head + rank;
+      if (i >= NZ_RING) i -= NZ_RING;
+      nz_lowpass(S, lane, j, S.nzsum[i][lane]);
     }
-    if (hit) S.ncut[j][lane] = cut;
-    const double old = S.namp[j][lane];
-    double a = __dadd_rn(old, __dmul_rn(P.nz_F, __dsub_rn(tgt, old)));
-    if ((old >= 0.001) && (a < 0.001)) S.nout[j][lane] = 0.0;
-    if (a >= 0.001) draws |= 1ull << j;
-    if ((a < 1.0e-13) && (tgt == 0.0)) { a = 0.0; N.nz &= ~(1ull << j); }  // (the reference lets it decay for ever; a source
-                                                                           //  is silent below 1e-3)
-    else N.nz |= 1ull << j;
-    S.namp[j][lane] = a;
   }
-  while (draws) {
-    NZ_DRAW;
-    const int j = __ffsll((long long)draws) - 1;
-    draws &= draws - 1;
-    const double x = exp_small(-2.0 * kPi * (S.ncut[j][lane] * P.dt));  // IirFilter::createSinglePoleLowpass (IirFilter.cpp:235-243)
-    const uint32_t isum = rng_sum12(S, lane, N.ri);  // 12 x rand() summed in an int: wraps around like the reference's
-    double in = (double)(int32_t)isum;
-    in = (in * (1.0 / 2147483647.0) - 6.0) * 0.28867513459481288225;  // / RAND_MAX, - 6, / sqrt(12)
-    S.nout[j][lane] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, x), in), __dmul_rn(x, S.nout[j][lane]));
+}
+// Warp X2, between the barriers of the reduced system: replaces the sums the step has consumed
+__device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs &N) {
+  for (int k = 0; k < N.used; k++) {
+    S.nzsum[N.head][lane] = rng_sum12(S, lane, N.ri);
+    if (++N.head == NZ_RING) N.head = 0;
   }
-  if ((N.nz >> AFS_NUM_PM_SECTIONS) & 1ull) N.lips = S.nout[AFS_NUM_PM_SECTIONS][lane] * S.namp[AFS_NUM_PM_SECTIONS][lane];
-  NZ_T2;
+  N.used = 0;
+}
+
+// State-dependent part of the noise sources, the SAME code on warps X2 (k0 = 0: constriction slots 0 and 2, i.e. the
+// vocal folds and the second tongue constriction) and X1 (k0 = 1: slots 1 and 3, the first tongue constriction and
+// the lips; plus the sources no constriction feeds this step, which only decay).  Per slot: target amplitude from the
+// flow through the constriction (TdsModel.cpp:1430-1612), amplitude filter of the two sources it feeds
+// (TdsModel.cpp:1630-1660); then one sample of every source of this warp that is not silent (TdsModel.cpp:1680-1708).
+// A single warp runs this code once per step with nothing to hide its latencies behind, so what counts is the
+// number of instructions on its path: two warps with half of the slots each, loops instead of unrolled code, the
+// state-independent exponentials (aspiration gain, filter coefficients at the upper cutoff limit) cached.
+// Returns the number of sources that draw a sample this step (both warps).
+struct NzConst { double F, x2000, dt; };  // P.nz_F, P.nz_x2000, P.dt by value (the callee is not inlined)
+__device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int lane, const int par, const double r,
+                                        const double r1, const int k0, const double gain0, const int head, int &ri) {
+  constexpr int NPM = AFS_NUM_PM_SECTIONS;
+  // sections fed by the four slots: bits 0..7 up, 8..15 down, valid in bit 16
+  unsigned long long targeted = 0, mine = 0, alive = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t v = S.nzc_i[par][k][lane];
+    const int up = (int)(v >> 16), down = up < NPM - 1 ? up + 1 : NPM;
+    if (v & 1u) targeted |= (1ull << up) | (1ull << down);
+  }
+  const double lipflow = S.nzlip[lane];
+#pragma unroll 1
+  for (int k = k0; k < 4; k += 2) {
+    const uint32_t v = S.nzc_i[par][k][lane];
+    const bool valid = v & 1u, teeth = (v >> 3) & 1u, lateral = (v >> 4) & 1u;
+    const int nar = min(max((int)((v >> 8) & 255u) - 1, 0), NPM - 1), up = (int)(v >> 16), down = up < NPM - 1 ? up + 1 : NPM;
+    const double downF = S.nzc_f[par][k][lane];
+    // sources a later slot feeds as well are that slot's (the last one wins)
+    unsigned long long later = 0;
+    for (int q = k + 1; q < 4; q++) {
+      const uint32_t w = S.nzc_i[par][q][lane];
+      const int u2 = (int)(w >> 16), d2 = u2 < NPM - 1 ? u2 + 1 : NPM;
+      if (w & 1u) later |= (1ull << u2) | (1ull << d2);
+    }
+    double A, flow;
+    if (k == 0) {  // the glottis (upper glottis section, current 25)
+      A = S.glArea[par][1][lane];
+      flow = S.nmag[0][lane];
+    } else {       // tongue (k = 1, 2) and lip (k = 3) constrictions: pharynx/mouth section nar
+      A = nz_area(S, lane, r, r1, nar);
+      const double f = S.nmag[nar + 1][lane];
+      const double extra = S.nmag[nar == 3 ? 41 : 40][lane];  // section 28: currents 29 and 84; section 40: currents 41 and 65
+      flow = nar == NPM - 1 ? lipflow : (nar == 3 || nar == 15) ? f + extra : f;
+    }
+    if (A < kMinArea) A = kMinArea;
+    if (A < 0.1) A = 0.1;
+    if (flow < 0.0) flow = 0.0;
+    const double v_ = fast_div(flow, A);
+    const double gain = k == 0 ? gain0 : k == 3 ? 2.0e-7 : teeth ? 10.0e-7 : 5.0e-7;
+    double fullAmp = gain * fabs(v_) * v_ * v_ * fast_sqrt(A);
+    if (lateral) fullAmp = 0.0;
+    // cutoff: clamped to 50..2000 Hz; the vocal-fold and lip sources ask for 6000 Hz, i.e. sit at the upper limit
+    double x = P.x2000;
+    if (k == 1 || k == 2) {
+      double cutoff = 0.15 * v_ * fast_rsqrt(A * (4.0 / kPi));  // 0.15 v / d, d = sqrt(4 A / pi)
+      if (cutoff < 50.0) cutoff = 50.0;
+      if (cutoff < 2000.0) x = exp_small(-2.0 * kPi * (cutoff * P.dt));
+    }
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+      const int j = side ? down : up;
+      if (valid && !((later >> j) & 1ull)) {
+        const double tgt = side ? downF * fullAmp : (1.0 - downF) * fullAmp;
+        const double old = S.namp[j][lane];
+        double a = __dadd_rn(old, __dmul_rn(P.F, __dsub_rn(tgt, old)));
+        S.ncut[j][lane] = x;
+        if ((old >= 0.001) && (a < 0.001)) S.nout[j][lane] = 0.0;
+        if (a >= 0.001) mine |= 1ull << j;
+        if ((a < 1.0e-13) && (tgt == 0.0)) a = 0.0;  // (the reference lets it decay for ever; a source is silent below 1e-3)
+        else alive |= 1ull << j;
+        S.namp[j][lane] = a;
+      }
+    }
+  }
+  if (k0 == 1) {  // the sources that only decay, two per pass
+    unsigned long long todo = (S.nzlive[0][lane] | S.nzlive[1][lane]) & ~targeted;
+    while (todo) {
+      const int j0 = __ffsll((long long)todo) - 1;
+      todo &= todo - 1;
+      const bool two = todo != 0;
+      const int j1 = two ? __ffsll((long long)todo) - 1 : j0;
+      todo &= todo - 1;
+      const double old0 = S.namp[j0][lane], old1 = S.namp[j1][lane];
+      double a0 = __dadd_rn(old0, __dmul_rn(P.F, __dsub_rn(0.0, old0)));
+      double a1 = __dadd_rn(old1, __dmul_rn(P.F, __dsub_rn(0.0, old1)));
+      if ((old0 >= 0.001) && (a0 < 0.001)) S.nout[j0][lane] = 0.0;
+      if (two && (old1 >= 0.001) && (a1 < 0.001)) S.nout[j1][lane] = 0.0;
+      if (a0 >= 0.001) mine |= 1ull << j0;
+      if (two && (a1 >= 0.001)) mine |= 1ull << j1;
+      if (a0 < 1.0e-13) a0 = 0.0;
+      else alive |= 1ull << j0;
+      if (a1 < 1.0e-13) a1 = 0.0;
+      else if (two) alive |= 1ull << j1;
+      S.namp[j0][lane] = a0;
+      if (two) S.namp[j1][lane] = a1;
+    }
+  }
+  // The reference draws in ascending source order from ONE rand() stream: the k-th drawing source of the step takes
+  // the k-th sum.  The sums do not depend on the state, so warp X2 generates them ahead of time (nz_refill) and the
+  // two warps pick theirs by rank once they have told each other who draws.
+  S.nzdraw[k0][lane] = mine;
+  bar_sync(4, 64);
+  const unsigned long long all = mine | S.nzdraw[k0 ^ 1][lane];
+  S.nzlive[k0][lane] = alive;  // (the other warp read the old masks before the barrier)
+  nz_draw_ranked(S, lane, mine, all, head);
+  const int n_all = __popcll(all);
+  if (k0 == 0 && n_all > NZ_RING) {  // more than the ring holds: the rest takes its sums straight from the generator, in order
+    unsigned long long over = all;
+    for (int k = 0; k < NZ_RING; k++) over &= over - 1;
+    while (over) {
+      const int j = __ffsll((long long)over) - 1;
+      over &= over - 1;
+      nz_lowpass(S, lane, j, rng_sum12(S, lane, ri));
+    }
+  }
+  return n_all;
 }
 
 // ==================================================================================
@@ -1524,12 +1606,6 @@ struct KArgs {
   double *nzc_f;
 };
 
-__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
-// Named barriers of the solve phase.  Warp X1 (glottis model, output filters) only has to be back for the next pass A:
-// it ARRIVES at barrier 1 once it has read what the others will overwrite and takes no part in barrier 2.
-__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-
 #ifdef AFS_TDS_TIMING
 #define AFS_TICK(k) do { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } while (0)
 #else
@@ -1580,7 +1656,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   OptRegs orr;
   X1Regs xr;
   NoiseRegs nr;
-  nr.nz = 0; nr.ri = 0; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0;
+  nr.ri = 0; nr.head = 0; nr.used = 0; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0; nr.asp = nan(""); nr.gain = 0.0;
+  int nz_head = 0;  // warp X1's copy of nr.head
   const SCfg scfg = scfg_of(warp);
   const unsigned wcfg = wcfg_make(warp);
   if (ROLE == 0) {
@@ -1599,7 +1676,11 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (ROLE == 3) {
 #pragma unroll
     for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; orr.x1[j] = orr.y1[j] = orr.x2[j] = orr.y2[j] = orr.xg[j] = orr.yg[j] = 0.0; }
-    if (NOISE) rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ri);
+    if (NOISE) {
+      rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ri);
+      nr.used = NZ_RING;
+      nz_refill(S, lane, nr);
+    }
   }
   if (ROLE == 2) {
     xr.G = GlottisState{0.0, 0.0, 0.0, 0.0};
@@ -1662,22 +1743,30 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
       }
     }
-    if (ROLE == 2 && NOISE && n + 1 < T) {
-      // constrictions of step n+1 for warp X2: found by the pre-pass kernel (they depend on the geometry of the step
-      // only), fetched one step ahead beside X2's source stage of step n; the two meet at the end-of-step barrier
-      nzc_fetch(S, A, lane, T, n + 1, (n + 1) & 1);
-    }
-    if (ROLE == 3 && NOISE && X.rows) {  // noise sources of step n (needs the update of the radiation currents above)
-      const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
-      NoiseCons cons[4];
-#ifndef AFS_NZ_SKIP_SCAN
-      nzc_load(S, lane, n & 1, cons);
-#else
-      for (int k = 0; k < 4; k++) { cons[k].valid = k == 0; cons[k].nar = -1; cons[k].kind = 0; cons[k].up = 3; cons[k].teeth = 0; cons[k].lateral = 0; cons[k].downF = 0.3; }
-#endif
-      const double asp = nz_lerp(re1, S.gctl[0][G_ASP][lane], re, S.gctl[1][G_ASP][lane]);
+    if (ROLE == 2 && NOISE) {
+      // constrictions of step n+1: found by the pre-pass kernel (they depend on the geometry of the step only),
+      // fetched one step ahead; the loads are in flight while this warp does its share of the sources of step n
+      NzcRec rec;
+      if (n + 1 < T) nzc_fetch_issue(A, T, n + 1, rec);
 #ifndef AFS_NZ_SKIP_SRC
-      noise_sources(P, S, lane, nr, cons, re, re1, n & 1, asp);
+      if (X.rows) {
+        int no_rng = 0;
+        nz_head += min(noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 1, 0.0, nz_head, no_rng), NZ_RING);
+        if (nz_head >= NZ_RING) nz_head -= NZ_RING;
+      }
+#endif
+      if (n + 1 < T) nzc_fetch_store(S, lane, (n + 1) & 1, rec);
+    }
+    if (ROLE == 3 && NOISE && X.rows) {  // its share of the noise sources of step n
+      // (the control-frame ratio only enters smooth quantities here; the decisions that need the reference's own
+      //  rounding of it were made by the pre-pass)
+      const double asp = X.ratio1 * S.gctl[0][G_ASP][lane] + X.ratio * S.gctl[1][G_ASP][lane];
+      if (asp != nr.asp) {  // vocal-fold source gain 10^(dB/20) (TdsModel.cpp:1449): constant while the aspiration strength is
+        nr.asp = asp;
+        nr.gain = 0.5e-7 * exp(asp * (2.302585092994045684 / 20.0));
+      }
+#ifndef AFS_NZ_SKIP_SRC
+      nr.used = min(noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 0, nr.gain, nr.head, nr.ri), NZ_RING);
 #endif
     }
     AFS_TICK(1);
@@ -1722,6 +1811,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       }
     }
     if (ROLE == 3) {
+      // sample of the lips dipole source (amplitude 0 while it is silent; it may be either warp's this step)
+      if (NOISE) nr.lips = S.nout[AFS_NUM_PM_SECTIONS][lane] * S.namp[AFS_NUM_PM_SECTIONS][lane];
       radiation_eliminate(P, S, lane, W_M3, 0, rr.c[0], rr.c[1], nr.lips, rr.keep[0]);
       radiation_eliminate(P, S, lane, W_N2, 1, rr.c[2], rr.c[3], nr.lips, rr.keep[1]);
     }
@@ -1742,6 +1833,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(3);
     if (ROLE != 2) {
       bar_sync(1, TDS_THREADS);
+      if (ROLE == 3 && NOISE) nz_refill(S, lane, nr);  // (this warp only waits for the reduced system)
       // ============ reduced system over the separators ============
       // (the three warps of the reduced system meet on their own barrier; the twelve others only wait for the result)
       if (warp == W_T0 || warp == W_T1 || warp == W_T2) {
@@ -1759,7 +1851,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     // ============ back substitution inside the segments ============
     if (ROLE == 0) dwarp_back<NOISE>(P, S, lane, warp, wcfg, dst);
     if (ROLE == 1) swarp_back<NOISE>(P, S, lane, warp, wcfg, scfg, sst);
-    if (ROLE == 3) radiation_back(S, lane, rr);
+    if (ROLE == 3) radiation_back<NOISE>(P, S, lane, rr, nr);
     AFS_TICK(6);
     cta_sync();
     AFS_TICK(7);
@@ -1767,7 +1859,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
 #ifdef AFS_TDS_TIMING
   if (A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) A.dump[warp * 8 + k] = (double)tacc[k];
   if (ROLE == 1 && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) A.dump[136 + warp * 4 + k] = (double)sw_acc[k];
-  if (ROLE == 3 && NOISE && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) { A.dump[128 + k] = (double)g_nz_t[k]; g_nz_t[k] = 0; }
+  if (ROLE == 3 && NOISE && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) A.dump[128 + k] = 0.0;
 #endif
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;
 }
@@ -1828,6 +1920,8 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
     S.sepD[w][lane] = 1.0; S.sepR[w][lane] = 0.0; S.redW[w][lane] = 1.0;  // NSEP == NW
   }
   if (warp == 0) {
+    for (int i = 0; i < 2; i++) { S.nzlive[i][lane] = 0; S.nzdraw[i][lane] = 0; }
+    S.nzlip[lane] = 0.0;
     for (int i = 0; i < NUX; i++) S.uext[i][lane] = 0.0;
     for (int i = 0; i < 5; i++) S.lf[i][lane] = 0.0;
     for (int i = 0; i < 4; i++) { S.p4[i][lane] = 0.0; (&S.radc[0][0])[i][lane] = 0.0; }
@@ -1943,6 +2037,7 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   P.g_sqrt_mk[1] = sqrt(P.gs[S_MASS2] * P.gs[S_K2]);
   P.noise = o->generate_noise_sources ? 1 : 0;
   P.nz_F = 1.0 - exp(-2.0 * M_PI * 40.0 * dt);
+  P.nz_x2000 = exp(-2.0 * M_PI * (2000.0 * dt));
   P.nm_a = exp(-2.0 * M_PI * 500.0 * dt);
   P.nm_1a = 1.0 - P.nm_a;
   P.dump_step = 0;

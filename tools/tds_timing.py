@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import areafunctionsynthesis_b200 as afs
 from bench import make_tds_batch
-B, T = 4096, 2205
+B, T = 4096, int(os.environ.get("T", "2205"))
 ctx = afs.Context(0)
 fr, gl = make_tds_batch(B, 1)
 buf = np.zeros(473); ctx.set_state_dump(10**9, buf)
@@ -19,7 +19,8 @@ print("warp " + " ".join(f"{n[:10]:>10s}" for n in names) + "      total")
 for w in range(16):
     print(f"{roles[w]:>4s} " + " ".join(f"{v:10.0f}" for v in t[w]) + f" {t[w].sum():10.0f}")
 if noise:
-    nz = buf[128:132] / steps
+    nz = buf[128:136] / steps
+    print(f"X2 waits for X1 {nz[4]:.0f}; X1: decay passes {nz[5]:.0f}, waits for X2 {nz[6]:.0f}, draws {nz[7]:.0f}")
     print(f"X2 noise_sources per step (lane 0 of CTA 0; passes/draws are that lane's, the warp runs the maximum over its lanes): "
           f"target stage {nz[0]:.0f} cycles, source loop {nz[1]:.0f} cycles, {nz[2]:.1f} passes, {nz[3]:.1f} draws")
 sw = buf[136:200].reshape(16, 4) / steps
