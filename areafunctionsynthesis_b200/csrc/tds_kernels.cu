@@ -49,9 +49,6 @@
 #include "afs_internal.h"
 
 namespace afs {
-#ifdef AFS_TDS_TIMING
-__device__ long long g_nz_t[8];  // X2, lane 0 of CTA 0: cycles in the target stage / the source loop, passes, draws; [4] X2 waiting for X1, [5..7] X1: decay passes, waiting for X2, draws
-#endif
 
 constexpr int LANES = 28;                     // tracts per CTA = row length of the [item][lane] arrays (224 B).  4096
                                               // utterances on 148 SMs are 27.7 per SM; hardware lanes 28..31 duplicate
@@ -63,18 +60,11 @@ constexpr int KD = 6;                         // sections per dynamic-chain warp
 constexpr int NSX = NS + 1;                   // + one all-zero dummy section (index 93)
 constexpr double kTheta = 0.515;              // TdsModel.cpp:15
 #ifndef AFS_NZ_RING
-#define AFS_NZ_RING 18
-#endif
-#ifdef AFS_TDS_TIMING
-#define NZ_CLK(k, t0) do { if (blockIdx.x == 0 && lane == 0) { const long long now__ = clock64(); atomicAdd((unsigned long long *)&g_nz_t[k], (unsigned long long)(now__ - (t0))); (t0) = now__; } } while (0)
-#define NZ_CLK0(t0) long long t0 = clock64()
-#else
-#define NZ_CLK(k, t0) do { } while (0)
-#define NZ_CLK0(t0) do { } while (0)
+#define AFS_NZ_RING 28
 #endif
 constexpr int NZ_RING = AFS_NZ_RING;          // pre-generated noise sums per tract (even; more draws in one step fall
                                               // back to in-line generation on warp X2)
-static_assert(NZ_RING % 2 == 0 && NZ_RING >= 2 && NZ_RING <= 32, "NZ_RING");
+static_assert(NZ_RING % 2 == 0 && NZ_RING >= 4 && NZ_RING <= 64, "NZ_RING");
 constexpr double kTheta1 = 1.0 - kTheta;
 
 // Warp roles.  The id also fixes the SM sub-partition (id % 4); the order balances the FP64 work of the four.
@@ -149,14 +139,21 @@ struct TdsSmem {
   // pharynx/mouth sections 25..64, 40 = lips; nmag: j = current - 25 for the currents 25..65, 41 = current 84.
   double nmag[42][LANES];                        // noiseMagnitude (TdsModel.h:143) of the currents a constriction can feed
   double namp[41][LANES], ncut[41][LANES], nout[41][LANES];  // currentAmp, cutoff, last filter output (TdsModel.h:101-112)
-  double inc[2][LANES];                          // incisor position of the two control frames
   // the source stage is split between warps X2 (sources a constriction feeds this step) and X1 (sources that only
   // decay): live sources and the sources that draw a sample this step, [0] = X2's share, [1] = X1's
   unsigned long long nzlive[2][LANES], nzdraw[2][LANES];
   double nzlip[LANES];                           // noiseMagnitude of the flow through the lips (currents 93 + 94)
-  uint32_t rng[34][LANES];                       // glibc random() TYPE_3 ring (r[i] = r[i-3] + r[i-31])
-  uint32_t nzsum[NZ_RING][LANES];                // the next NZ_RING sums of twelve rand() draws, generated ahead by X2
-  unsigned char art[AFS_NUM_PM_SECTIONS][LANES]; // articulator of the LEFT control frame (Tube.cpp:452)
+  // glibc random() TYPE_3 (r[i] = r[i-3] + r[i-31]) in a ring of 36 = 3 x 12 words: the twelve draws of one noise
+  // sample never wrap inside the ring and three samples bring it back to the same phase (static addresses)
+  uint32_t rng[36][LANES];
+  uint32_t nzring[LANES];                        // ring of pre-generated sums: head | valid entries << 8 (written by X2)
+  union {
+    struct {                                     // pre-pass kernel only (tds_noise_scan_kernel)
+      double inc[2][LANES];                      // incisor position of the two control frames
+      unsigned char art[AFS_NUM_PM_SECTIONS][LANES];  // articulator of the LEFT control frame (Tube.cpp:452)
+    };
+    uint32_t nzsum[NZ_RING][LANES];              // time loop only: the next sums of twelve rand() draws, generated ahead by X2
+  };
   // constrictions of the NEXT step, found by warp X1 while the others solve (the scan does not depend on the state):
   // packed {valid, kind, teeth, lateral, nar + 1, up} and the downstream factor, double buffered by step parity
   uint32_t nzc_i[2][4][LANES];
@@ -375,8 +372,8 @@ struct NoiseCons {
   double downF;                              // kind: 0 vocal folds, 1 tongue, 2 lower lip
 };
 struct NoiseRegs {
-  int ri;                 // position in the random() ring
-  int head, used;         // oldest entry of the ring of pre-generated sums; entries consumed by the current step
+  int ph;                 // position in the random() ring: 0, 12 or 24
+  int head, free;         // oldest entry of the ring of pre-generated sums; entries that wait for a new sum
   double lips;            // sample of the lips dipole source (enters all four radiation rows)
   double nm93, nm94;      // noiseMagnitude of the mouth radiation currents
   double asp, gain;       // aspiration strength (dB) the cached vocal-fold source gain belongs to
@@ -989,32 +986,33 @@ __device__ __forceinline__ uint32_t nzc_pack(const NoiseCons &c) {
 }
 
 // glibc srand() (stdlib/random_r.c, TYPE_3): the reference draws from libc rand() (TdsModel.cpp:1690-1696); every
-// tract owns a private generator.
-__device__ __noinline__ void rng_seed(TdsSmem &S, const int lane, uint32_t seed, int &ri) {
+// tract owns a private generator.  Word i of the sequence sits at ring position (i + 28) % 36, so that the first
+// output (i = 344) starts a block of twelve at position 12.
+__device__ __noinline__ void rng_seed(TdsSmem &S, const int lane, uint32_t seed, int &ph) {
   if (seed == 0) seed = 1;
   long long r = (int32_t)seed;
-  S.rng[0][lane] = (uint32_t)(int32_t)r;
+  S.rng[28][lane] = (uint32_t)(int32_t)r;
   for (int i = 1; i < 31; i++) {
     const long long hi = r / 127773, lo = r % 127773;
     long long word = 16807 * lo - 2836 * hi;
     if (word < 0) word += 2147483647;
     r = (int32_t)word;
-    S.rng[i][lane] = (uint32_t)(int32_t)r;
+    S.rng[(i + 28) % 36][lane] = (uint32_t)(int32_t)r;
   }
-  for (int i = 31; i < 34; i++) S.rng[i][lane] = S.rng[i - 31][lane];
-  for (int i = 34; i < 344; i++) S.rng[i % 34][lane] = S.rng[(i - 31) % 34][lane] + S.rng[(i - 3) % 34][lane];
-  ri = 310 % 34;  // the oldest value
+  for (int i = 31; i < 34; i++) S.rng[(i + 28) % 36][lane] = S.rng[(i - 31 + 28) % 36][lane];
+  for (int i = 34; i < 344; i++) S.rng[(i + 28) % 36][lane] = S.rng[(i - 31 + 28) % 36][lane] + S.rng[(i - 3 + 28) % 36][lane];
+  ph = 12;
 }
-// Twelve successive rng_next() calls summed with the reference's int wrap-around (TdsModel.cpp:1690-1696).  The
-// additive lagged-Fibonacci recurrence r[i] = r[i-3] + r[i-31] lets all operands be loaded up front (the fifteen old
-// words the twelve new ones depend on, three of the new ones feeding later ones from registers), so the loads
-// pipeline instead of forming twelve serial load-load-store chains through shared memory.
-__device__ __forceinline__ uint32_t rng_sum12(TdsSmem &S, const int lane, int &ri) {
+// Twelve successive rand() calls summed with the reference's int wrap-around (TdsModel.cpp:1690-1696), the new words
+// going to ring positions PH .. PH + 11.  The additive lagged-Fibonacci recurrence lets all operands be loaded up
+// front (the fifteen old words the twelve new ones depend on); every address is a compile-time constant.
+template <int PH>
+__device__ __forceinline__ uint32_t rng_block(TdsSmem &S, const int lane) {
   uint32_t a[12], m[3], o[12];
 #pragma unroll
-  for (int q = 0; q < 12; q++) { int i = ri + 3 + q; if (i >= 34) i -= 34; a[q] = S.rng[i][lane]; }
+  for (int q = 0; q < 12; q++) a[q] = S.rng[(PH + q + 5) % 36][lane];   // word i - 31
 #pragma unroll
-  for (int q = 0; q < 3; q++) { int i = ri + 31 + q; if (i >= 34) i -= 34; m[q] = S.rng[i][lane]; }
+  for (int q = 0; q < 3; q++) m[q] = S.rng[(PH + q + 33) % 36][lane];   // word i - 3
   uint32_t isum = 0;
 #pragma unroll
   for (int q = 0; q < 12; q++) {
@@ -1022,10 +1020,16 @@ __device__ __forceinline__ uint32_t rng_sum12(TdsSmem &S, const int lane, int &r
     isum += o[q] >> 1;
   }
 #pragma unroll
-  for (int q = 0; q < 12; q++) { int i = ri + q; if (i >= 34) i -= 34; S.rng[i][lane] = o[q]; }
-  ri += 12;
-  if (ri >= 34) ri -= 34;
+  for (int q = 0; q < 12; q++) S.rng[PH + q][lane] = o[q];
   return isum;
+}
+// one sum from whatever phase the generator is in (rare: only when a step draws more samples than the ring holds)
+__device__ __noinline__ uint32_t rng_sum12(TdsSmem &S, const int lane, int &ph) {
+  uint32_t s;
+  if (ph == 12) { s = rng_block<12>(S, lane); ph = 24; }
+  else if (ph == 24) { s = rng_block<24>(S, lane); ph = 0; }
+  else { s = rng_block<0>(S, lane); ph = 12; }
+  return s;
 }
 
 // exp(t) for -0.75 <= t <= 0 (cutoff <= 2000 Hz at fs >= 16.8 kHz): Taylor polynomial of degree 17 (full double
@@ -1178,25 +1182,34 @@ __device__ __forceinline__ void nz_lowpass(TdsSmem &S, const int lane, const int
 }
 // The drawing sources `mine` of one warp; `all` = every drawing source of the step (rank = position in the rand() stream)
 __device__ __forceinline__ void nz_draw_ranked(TdsSmem &S, const int lane, unsigned long long mine,
-                                               const unsigned long long all, const int head) {
+                                               const unsigned long long all, const int head, const int avail) {
   while (mine) {
     const int j = __ffsll((long long)mine) - 1;
     mine &= mine - 1;
     const int rank = __popcll(all & ((1ull << j) - 1ull));
-    if (rank < NZ_RING) {
+    if (rank < avail) {
       int i = head + rank;
       if (i >= NZ_RING) i -= NZ_RING;
       nz_lowpass(S, lane, j, S.nzsum[i][lane]);
     }
   }
 }
-// Warp X2, between the barriers of the reduced system: replaces the sums the step has consumed
+// Warp X2, while the reduced system is solved: new sums for the entries the step has consumed, three at a time (the
+// generator is back at phase 12 after three sums, so all lanes run the same straight-line code); up to two entries
+// wait for the next step.  Publishes head and fill level for both warps.
 __device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs &N) {
-  for (int k = 0; k < N.used; k++) {
-    S.nzsum[N.head][lane] = rng_sum12(S, lane, N.ri);
-    if (++N.head == NZ_RING) N.head = 0;
+  auto put = [&](uint32_t v) {
+    int t = N.head + (NZ_RING - N.free);
+    if (t >= NZ_RING) t -= NZ_RING;
+    S.nzsum[t][lane] = v;
+    N.free--;
+  };
+  while (N.free > 0 && N.ph != 12) put(rng_sum12(S, lane, N.ph));  // (only after an overflow)
+  while (N.free >= 3) {
+    const uint32_t s0 = rng_block<12>(S, lane), s1 = rng_block<24>(S, lane), s2 = rng_block<0>(S, lane);
+    put(s0); put(s1); put(s2);
   }
-  N.used = 0;
+  S.nzring[lane] = (uint32_t)N.head | ((uint32_t)(NZ_RING - N.free) << 8);
 }
 
 // State-dependent part of the noise sources, the SAME code on warps X2 (k0 = 0: constriction slots 0 and 2, i.e. the
@@ -1207,10 +1220,10 @@ __device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs 
 // A single warp runs this code once per step with nothing to hide its latencies behind, so what counts is the
 // number of instructions on its path: two warps with half of the slots each, loops instead of unrolled code, the
 // state-independent exponentials (aspiration gain, filter coefficients at the upper cutoff limit) cached.
-// Returns the number of sources that draw a sample this step (both warps).
+// Returns the number of ring entries the step has consumed (both warps).
 struct NzConst { double F, x2000, dt; };  // P.nz_F, P.nz_x2000, P.dt by value (the callee is not inlined)
 __device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int lane, const int par, const double r,
-                                        const double r1, const int k0, const double gain0, const int head, int &ri) {
+                                        const double r1, const int k0, const double gain0, int &ph) {
   constexpr int NPM = AFS_NUM_PM_SECTIONS;
   // sections fed by the four slots: bits 0..7 up, 8..15 down, valid in bit 16
   unsigned long long targeted = 0, mine = 0, alive = 0;
@@ -1221,12 +1234,15 @@ __device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int l
     if (v & 1u) targeted |= (1ull << up) | (1ull << down);
   }
   const double lipflow = S.nzlip[lane];
+  const uint32_t ring = S.nzring[lane];
+  const int head = (int)(ring & 255u), avail = (int)(ring >> 8);
 #pragma unroll 1
   for (int k = k0; k < 4; k += 2) {
     const uint32_t v = S.nzc_i[par][k][lane];
     const bool valid = v & 1u, teeth = (v >> 3) & 1u, lateral = (v >> 4) & 1u;
     const int nar = min(max((int)((v >> 8) & 255u) - 1, 0), NPM - 1), up = (int)(v >> 16), down = up < NPM - 1 ? up + 1 : NPM;
     const double downF = S.nzc_f[par][k][lane];
+    if (!__any_sync(0xffffffffu, valid)) continue;  // (the second tongue constriction and the lips are rare)
     // sources a later slot feeds as well are that slot's (the last one wins)
     unsigned long long later = 0;
     for (int q = k + 1; q < 4; q++) {
@@ -1247,14 +1263,15 @@ __device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int l
     if (A < kMinArea) A = kMinArea;
     if (A < 0.1) A = 0.1;
     if (flow < 0.0) flow = 0.0;
-    const double v_ = fast_div(flow, A);
+    const double rs = fast_rsqrt(A);  // 1/sqrt(A): v = flow / A, sqrt(A) and the jet diameter all come from it
+    const double v_ = flow * (rs * rs);
     const double gain = k == 0 ? gain0 : k == 3 ? 2.0e-7 : teeth ? 10.0e-7 : 5.0e-7;
-    double fullAmp = gain * fabs(v_) * v_ * v_ * fast_sqrt(A);
+    double fullAmp = gain * fabs(v_) * v_ * v_ * (A * rs);
     if (lateral) fullAmp = 0.0;
     // cutoff: clamped to 50..2000 Hz; the vocal-fold and lip sources ask for 6000 Hz, i.e. sit at the upper limit
     double x = P.x2000;
     if (k == 1 || k == 2) {
-      double cutoff = 0.15 * v_ * fast_rsqrt(A * (4.0 / kPi));  // 0.15 v / d, d = sqrt(4 A / pi)
+      double cutoff = 0.15 * v_ * (rs * 0.88622692545275801365);  // 0.15 v / d, d = sqrt(4 A / pi)
       if (cutoff < 50.0) cutoff = 50.0;
       if (cutoff < 2000.0) x = exp_small(-2.0 * kPi * (cutoff * P.dt));
     }
@@ -1304,18 +1321,18 @@ __device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int l
   bar_sync(4, 64);
   const unsigned long long all = mine | S.nzdraw[k0 ^ 1][lane];
   S.nzlive[k0][lane] = alive;  // (the other warp read the old masks before the barrier)
-  nz_draw_ranked(S, lane, mine, all, head);
+  nz_draw_ranked(S, lane, mine, all, head, avail);
   const int n_all = __popcll(all);
-  if (k0 == 0 && n_all > NZ_RING) {  // more than the ring holds: the rest takes its sums straight from the generator, in order
+  if (k0 == 0 && n_all > avail) {  // more than the ring holds: the rest takes its sums straight from the generator, in order
     unsigned long long over = all;
-    for (int k = 0; k < NZ_RING; k++) over &= over - 1;
+    for (int k = 0; k < avail; k++) over &= over - 1;
     while (over) {
       const int j = __ffsll((long long)over) - 1;
       over &= over - 1;
-      nz_lowpass(S, lane, j, rng_sum12(S, lane, ri));
+      nz_lowpass(S, lane, j, rng_sum12(S, lane, ph));
     }
   }
-  return n_all;
+  return min(n_all, avail);
 }
 
 // ==================================================================================
@@ -1614,7 +1631,7 @@ struct KArgs {
 
 // Stages the control frames of interval `interval` (all warps; the caller puts barriers around it).
 __device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const int warp, const afs_tube_frame *my_frames,
-                                               const double *my_glottis, int interval, bool noise) {
+                                               const double *my_glottis, int interval, bool scan) {
   for (int item = warp; item < 2 * AFS_NUM_PM_SECTIONS + 2; item += NW) {
     if (item < 2 * AFS_NUM_PM_SECTIONS) {
       const int f = item / AFS_NUM_PM_SECTIONS, j = item % AFS_NUM_PM_SECTIONS;
@@ -1623,13 +1640,13 @@ __device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const
       if (a < kMinArea) a = kMinArea;  // Tube::setPharynxMouthGeometry clamps on the way in
       S.fA[f][j][lane] = a;
       S.fLen[f][j][lane] = fr->length_cm[j];
-      if (noise && f == 0) S.art[j][lane] = (unsigned char)fr->articulator[j];
+      if (scan && f == 0) S.art[j][lane] = (unsigned char)fr->articulator[j];
     } else {
       const int f = item - 2 * AFS_NUM_PM_SECTIONS;
       double v = my_frames[interval + f].velum_area_cm2;
       if (v < kMinArea) v = kMinArea;  // Tube::getVelumOpening_cm2 returns the clamped nose[0] area
       S.velum[f][lane] = v;
-      S.inc[f][lane] = my_frames[interval + f].incisor_pos_cm;
+      if (scan) S.inc[f][lane] = my_frames[interval + f].incisor_pos_cm;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
         S.gctl[f][c][lane] = my_glottis[(size_t)(interval + f) * AFS_NUM_GLOTTIS_CONTROL + c];
     }
@@ -1656,8 +1673,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   OptRegs orr;
   X1Regs xr;
   NoiseRegs nr;
-  nr.ri = 0; nr.head = 0; nr.used = 0; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0; nr.asp = nan(""); nr.gain = 0.0;
-  int nz_head = 0;  // warp X1's copy of nr.head
+  nr.ph = 12; nr.head = 0; nr.free = 0; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0; nr.asp = nan(""); nr.gain = 0.0;
   const SCfg scfg = scfg_of(warp);
   const unsigned wcfg = wcfg_make(warp);
   if (ROLE == 0) {
@@ -1677,8 +1693,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
 #pragma unroll
     for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; orr.x1[j] = orr.y1[j] = orr.x2[j] = orr.y2[j] = orr.xg[j] = orr.yg[j] = 0.0; }
     if (NOISE) {
-      rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ri);
-      nr.used = NZ_RING;
+      rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ph);
+      nr.free = NZ_RING;
       nz_refill(S, lane, nr);
     }
   }
@@ -1698,7 +1714,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (T > 0) {
     i0 = A.bounds[0]; i1 = A.bounds[1];
     inv_len = 1.0 / (double)(i1 - i0);
-    stage_interval(S, lane, warp, my_frames, my_glottis, 0, NOISE);
+    stage_interval(S, lane, warp, my_frames, my_glottis, 0, false);
     cta_sync();
     if (ROLE == 2 && NOISE) nzc_fetch(S, A, lane, T, 0, 0);  // constrictions of step 0 for warp X2
     if (ROLE == 2) {  // glottis geometry of step 0
@@ -1722,7 +1738,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       interval++;
       i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
       inv_len = 1.0 / (double)(i1 - i0);
-      stage_interval(S, lane, warp, my_frames, my_glottis, interval, NOISE);
+      stage_interval(S, lane, warp, my_frames, my_glottis, interval, false);
       cta_sync();
     }
     X.ratio = (double)(n - i0) * inv_len;  // (1 ulp from the reference's i / N; irrelevant at the 1e-6 bar)
@@ -1750,9 +1766,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       if (n + 1 < T) nzc_fetch_issue(A, T, n + 1, rec);
 #ifndef AFS_NZ_SKIP_SRC
       if (X.rows) {
-        int no_rng = 0;
-        nz_head += min(noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 1, 0.0, nz_head, no_rng), NZ_RING);
-        if (nz_head >= NZ_RING) nz_head -= NZ_RING;
+        int no_rng = 12;
+        noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 1, 0.0, no_rng);
       }
 #endif
       if (n + 1 < T) nzc_fetch_store(S, lane, (n + 1) & 1, rec);
@@ -1766,7 +1781,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         nr.gain = 0.5e-7 * exp(asp * (2.302585092994045684 / 20.0));
       }
 #ifndef AFS_NZ_SKIP_SRC
-      nr.used = min(noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 0, nr.gain, nr.head, nr.ri), NZ_RING);
+      const int used = noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 0, nr.gain, nr.ph);
+      nr.head += used; nr.free += used;
+      if (nr.head >= NZ_RING) nr.head -= NZ_RING;
 #endif
     }
     AFS_TICK(1);
@@ -1859,7 +1876,6 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
 #ifdef AFS_TDS_TIMING
   if (A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) A.dump[warp * 8 + k] = (double)tacc[k];
   if (ROLE == 1 && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) A.dump[136 + warp * 4 + k] = (double)sw_acc[k];
-  if (ROLE == 3 && NOISE && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) A.dump[128 + k] = 0.0;
 #endif
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;
 }

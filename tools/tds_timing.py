@@ -18,11 +18,6 @@ print("cycles per step, per warp (lane 0 of CTA 0):")
 print("warp " + " ".join(f"{n[:10]:>10s}" for n in names) + "      total")
 for w in range(16):
     print(f"{roles[w]:>4s} " + " ".join(f"{v:10.0f}" for v in t[w]) + f" {t[w].sum():10.0f}")
-if noise:
-    nz = buf[128:136] / steps
-    print(f"X2 waits for X1 {nz[4]:.0f}; X1: decay passes {nz[5]:.0f}, waits for X2 {nz[6]:.0f}, draws {nz[7]:.0f}")
-    print(f"X2 noise_sources per step (lane 0 of CTA 0; passes/draws are that lane's, the warp runs the maximum over its lanes): "
-          f"target stage {nz[0]:.0f} cycles, source loop {nz[1]:.0f} cycles, {nz[2]:.1f} passes, {nz[3]:.1f} draws")
 sw = buf[136:200].reshape(16, 4) / steps
 print("static warps, swarp_eliminate: first row | sinus leaves | chain | publish")
 for w in range(16):
