@@ -44,6 +44,7 @@
 // elimination order), FMA contraction on; parity gate 1e-6 relative max-abs.
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 
 #include "afs_internal.h"
@@ -85,6 +86,7 @@ struct TdsParams {
   int dump_step;
   int noise;                        // generate_noise_sources (TdsModel.h:87)
   double nz_F, nm_a, nm_1a;         // 1 - exp(-2 pi 40 dt) (TdsModel.cpp:1637), exp(-2 pi 500 dt) and 1 - that (:2052)
+  int nz_ring;                      // entries of the ring of pre-generated noise sums in use (<= NZ_RING)
   double nz_x2000;                  // exp(-2 pi 2000 dt): low-pass coefficient of a source at the upper cutoff limit
   double dt, idt, th, dtth, dtth1;  // 1/fs, 1/(dt*theta), theta1/theta, dt*theta, dt*theta1
   double ith, fs;                   // theta/theta1, fs
@@ -146,7 +148,7 @@ struct TdsSmem {
   // glibc random() TYPE_3 (r[i] = r[i-3] + r[i-31]) in a ring of 36 = 3 x 12 words: the twelve draws of one noise
   // sample never wrap inside the ring and three samples bring it back to the same phase (static addresses)
   uint32_t rng[36][LANES];
-  uint32_t nzring[LANES];                        // ring of pre-generated sums: head | valid entries << 8 (written by X2)
+  uint32_t nzring[LANES];                        // ring of pre-generated sums: head | valid entries << 8 | entries in use << 16 (written by X2)
   union {
     struct {                                     // pre-pass kernel only (tds_noise_scan_kernel)
       double inc[2][LANES];                      // incisor position of the two control frames
@@ -373,7 +375,7 @@ struct NoiseCons {
 };
 struct NoiseRegs {
   int ph;                 // position in the random() ring: 0, 12 or 24
-  int head, free;         // oldest entry of the ring of pre-generated sums; entries that wait for a new sum
+  int head, free, cap;    // ring of pre-generated sums: oldest entry; entries that wait for a new sum; entries in use
   double lips;            // sample of the lips dipole source (enters all four radiation rows)
   double nm93, nm94;      // noiseMagnitude of the mouth radiation currents
   double asp, gain;       // aspiration strength (dB) the cached vocal-fold source gain belongs to
@@ -1182,14 +1184,15 @@ __device__ __forceinline__ void nz_lowpass(TdsSmem &S, const int lane, const int
 }
 // The drawing sources `mine` of one warp; `all` = every drawing source of the step (rank = position in the rand() stream)
 __device__ __forceinline__ void nz_draw_ranked(TdsSmem &S, const int lane, unsigned long long mine,
-                                               const unsigned long long all, const int head, const int avail) {
+                                               const unsigned long long all, const int head, const int avail,
+                                               const int cap) {
   while (mine) {
     const int j = __ffsll((long long)mine) - 1;
     mine &= mine - 1;
     const int rank = __popcll(all & ((1ull << j) - 1ull));
     if (rank < avail) {
       int i = head + rank;
-      if (i >= NZ_RING) i -= NZ_RING;
+      if (i >= cap) i -= cap;
       nz_lowpass(S, lane, j, S.nzsum[i][lane]);
     }
   }
@@ -1199,8 +1202,8 @@ __device__ __forceinline__ void nz_draw_ranked(TdsSmem &S, const int lane, unsig
 // wait for the next step.  Publishes head and fill level for both warps.
 __device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs &N) {
   auto put = [&](uint32_t v) {
-    int t = N.head + (NZ_RING - N.free);
-    if (t >= NZ_RING) t -= NZ_RING;
+    int t = N.head + (N.cap - N.free);
+    if (t >= N.cap) t -= N.cap;
     S.nzsum[t][lane] = v;
     N.free--;
   };
@@ -1209,7 +1212,7 @@ __device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs 
     const uint32_t s0 = rng_block<12>(S, lane), s1 = rng_block<24>(S, lane), s2 = rng_block<0>(S, lane);
     put(s0); put(s1); put(s2);
   }
-  S.nzring[lane] = (uint32_t)N.head | ((uint32_t)(NZ_RING - N.free) << 8);
+  S.nzring[lane] = (uint32_t)N.head | ((uint32_t)(N.cap - N.free) << 8) | ((uint32_t)N.cap << 16);
 }
 
 // State-dependent part of the noise sources, the SAME code on warps X2 (k0 = 0: constriction slots 0 and 2, i.e. the
@@ -1235,7 +1238,7 @@ __device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int l
   }
   const double lipflow = S.nzlip[lane];
   const uint32_t ring = S.nzring[lane];
-  const int head = (int)(ring & 255u), avail = (int)(ring >> 8);
+  const int head = (int)(ring & 255u), avail = (int)((ring >> 8) & 255u), cap = (int)(ring >> 16);
 #pragma unroll 1
   for (int k = k0; k < 4; k += 2) {
     const uint32_t v = S.nzc_i[par][k][lane];
@@ -1321,7 +1324,7 @@ __device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int l
   bar_sync(4, 64);
   const unsigned long long all = mine | S.nzdraw[k0 ^ 1][lane];
   S.nzlive[k0][lane] = alive;  // (the other warp read the old masks before the barrier)
-  nz_draw_ranked(S, lane, mine, all, head, avail);
+  nz_draw_ranked(S, lane, mine, all, head, avail, cap);
   const int n_all = __popcll(all);
   if (k0 == 0 && n_all > avail) {  // more than the ring holds: the rest takes its sums straight from the generator, in order
     unsigned long long over = all;
@@ -1673,7 +1676,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   OptRegs orr;
   X1Regs xr;
   NoiseRegs nr;
-  nr.ph = 12; nr.head = 0; nr.free = 0; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0; nr.asp = nan(""); nr.gain = 0.0;
+  nr.ph = 12; nr.head = 0; nr.free = 0; nr.cap = NZ_RING; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0; nr.asp = nan(""); nr.gain = 0.0;
   const SCfg scfg = scfg_of(warp);
   const unsigned wcfg = wcfg_make(warp);
   if (ROLE == 0) {
@@ -1694,7 +1697,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; orr.x1[j] = orr.y1[j] = orr.x2[j] = orr.y2[j] = orr.xg[j] = orr.yg[j] = 0.0; }
     if (NOISE) {
       rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ph);
-      nr.free = NZ_RING;
+      nr.cap = nr.free = P.nz_ring;
       nz_refill(S, lane, nr);
     }
   }
@@ -1783,7 +1786,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
 #ifndef AFS_NZ_SKIP_SRC
       const int used = noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 0, nr.gain, nr.ph);
       nr.head += used; nr.free += used;
-      if (nr.head >= NZ_RING) nr.head -= NZ_RING;
+      if (nr.head >= nr.cap) nr.head -= nr.cap;
 #endif
     }
     AFS_TICK(1);
@@ -2054,6 +2057,11 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   P.noise = o->generate_noise_sources ? 1 : 0;
   P.nz_F = 1.0 - exp(-2.0 * M_PI * 40.0 * dt);
   P.nz_x2000 = exp(-2.0 * M_PI * (2000.0 * dt));
+  P.nz_ring = NZ_RING;
+  if (const char *env = getenv("AFS_NOISE_RING_ENTRIES")) {  // (tests force the overflow path with a short ring)
+    const int v = atoi(env);
+    if (v >= 4 && v <= NZ_RING) P.nz_ring = v;
+  }
   P.nm_a = exp(-2.0 * M_PI * 500.0 * dt);
   P.nm_1a = 1.0 - P.nm_a;
   P.dump_step = 0;

@@ -210,6 +210,34 @@ def test_noise_sources_against_oracle(ctx, oracle, shapes):
     assert np.array_equal(a[perm], a2)
 
 
+def test_noise_sum_ring_overflow(ctx, oracle, shapes, monkeypatch):
+    """The sums of twelve rand() draws are generated ahead of time into a per-tract ring (28 entries); a step that
+    draws more samples than the ring holds takes the rest straight from the generator, in the reference's order.
+    Forced here with a ring of 4 (consonant transitions draw 5-12 samples per step): bit-identical to the run with
+    the full ring, and within tolerance of the oracle."""
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    n = len(shapes["names"])
+    rng = np.random.default_rng(20260005)
+    B = 30
+    fr = shapes["frames"][rng.integers(0, n, size=(B, 3))].copy()
+    gl = np.tile(G0, (B, 3, 1))
+    gl[:, :, 0] = rng.uniform(90, 220, size=(B, 3))
+    gl[:, :, 5] = rng.uniform(-30.0, -10.0, size=(B, 3))
+    seeds = rng.integers(0, 2**32, size=B, dtype=np.uint64).astype(np.uint32)
+    fl = [700, 500]
+    on = afs.tds_options_default(noise=True)
+    a0, u0, st0 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
+    monkeypatch.setenv("AFS_NOISE_RING_ENTRIES", "4")
+    a1, u1, st1 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
+    monkeypatch.delenv("AFS_NOISE_RING_ENTRIES")
+    assert not st0.any() and not st1.any()
+    assert np.array_equal(a0, a1) and np.array_equal(u0, u1)
+    ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=oracle_opts(noise=True), seeds=seeds)
+    for b in range(B):
+        assert rel_err(u1[b], uo[b]) <= TOL and rel_err(a1[b], ao[b]) <= TOL, (b, rel_err(u1[b], uo[b]))
+
+
 # ---------------------------------------------------------------------------------------------
 # non-default options of TdsModel::Options: transvelar coupling (TdsModel.cpp:476-533, 966-999) and the variable
 # glottal entrance loss of Fulcher et al. 2011 (TdsModel.cpp:1019-1092)
