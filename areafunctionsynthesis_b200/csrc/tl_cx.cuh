@@ -29,6 +29,18 @@ __device__ __forceinline__ m22 m22_mul(const m22 &k, const m22 &x) {
   r.D = cx_add(cx_mul(k.C, x.B), cx_mul(k.D, x.D));
   return r;
 }
+// K * [[1, Z], [0, 1]] and K * [[1, 0], [Y, 1]] (series impedance / shunt admittance as the reference builds them:
+// Matrix2x2::unit() with one element replaced, then the full product).  In the full product the unit entries
+// contribute x * 1 - y * 0 and x * 0 + y * 0, i.e. x and (signed) zero exactly, so leaving them out gives the same
+// bits up to the sign of an exact zero.
+__device__ __forceinline__ void m22_series(m22 &k, cx Z) {
+  k.B = cx_add(cx_mul(k.A, Z), k.B);
+  k.D = cx_add(cx_mul(k.C, Z), k.D);
+}
+__device__ __forceinline__ void m22_shunt(m22 &k, cx Y) {
+  k.A = cx_add(k.A, cx_mul(k.B, Y));
+  k.C = cx_add(k.C, cx_mul(k.D, Y));
+}
 __device__ __forceinline__ m22 m22_inv(const m22 &m) {  // det == 1 assumed, as in the reference
   m22 r; r.A = m.D; r.D = m.A; r.B = cx_neg(m.B); r.C = cx_neg(m.C); return r;
 }
