@@ -1,0 +1,8 @@
+set -x
+python __graft_entry__.py --smoke 2>&1 | tail -3
+python -m pytest tests -m gpu -q 2>&1 | tail -3
+python bench.py > gpurun_out/r1k_bench.json 2> gpurun_out/r1k_bench.err; tail -2 gpurun_out/r1k_bench.err
+python bench.py --impl reference > gpurun_out/r1k_bench_reference_arm.json 2>/dev/null
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r1k_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/r1k_ncu_bench.log 2>&1
+FAST=0 ncu --set full --clock-control none --import-source on -k regex:tl_sweep --launch-skip 3 -c 1 -f -o gpurun_out/r1k_tl python tools/tl_quick_bench.py > gpurun_out/r1k_ncu_tl.log 2>&1
+ls -la gpurun_out | tail -6
