@@ -1966,7 +1966,11 @@ static_assert(NSEP == NW, "prologue zeroing assumes NSEP == NW");
 // it); here every (tract, step) pair is independent: the same CTA <-> tract mapping as tds_batch_kernel, lane =
 // tract, the sixteen warps of a CTA take the steps of a control interval round robin.  Records (48 B per tract-step)
 // go to global memory in [cta][step][4][32] layout and are fetched one step ahead by warp X1.
-__global__ void __launch_bounds__(TDS_THREADS, 1)
+#ifndef AFS_SCAN_THREADS
+#define AFS_SCAN_THREADS 640  // 20 warps at <= 102 registers: the scan is latency-bound, every warp more is throughput
+#endif
+constexpr int SCAN_THREADS = AFS_SCAN_THREADS, SCAN_WARPS = SCAN_THREADS / 32;
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
 tds_noise_scan_kernel(const TdsParams P, const KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TdsSmem &S = *reinterpret_cast<TdsSmem *>(smem_raw);
@@ -1989,7 +1993,7 @@ tds_noise_scan_kernel(const TdsParams P, const KArgs A) {
       else if (!(a < 0.0999999 && b < 0.0999999)) latMaybe |= 1ull << j;
     }
     __syncthreads();
-    for (int n = i0 + warp; n < i1 && n < T; n += NW) {
+    for (int n = i0 + warp; n < i1 && n < T; n += SCAN_WARPS) {
       const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
       NoiseCons cons[4];
       noise_scan(S, lane, re, re1, my_frames + iv, my_frames + iv + 1, latAlways, latMaybe, cons);
@@ -2115,7 +2119,7 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
     A.nzc_f = (double *)((unsigned char *)d_nzc + (size_t)ctas * (size_t)P.total_steps * 4 * 32 * sizeof(uint32_t));
     e = cudaFuncSetAttribute(tds_noise_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TdsSmem));
     if (e != cudaSuccess) return e;
-    tds_noise_scan_kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, A);
+    tds_noise_scan_kernel<<<ctas, SCAN_THREADS, sizeof(TdsSmem), stream>>>(P, A);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
