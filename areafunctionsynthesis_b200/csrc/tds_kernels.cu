@@ -73,7 +73,7 @@ constexpr double kTheta1 = 1.0 - kTheta;
 //                   M3 59..64, NV 65..70 (velum port 65..68 + two rigid nose sections)
 //   static chains:  T0 0..7, T1 8..15, T2 16..22 (trachea), N1 71..75 (+ sinuses 89, 90), N2 76..83 (+ sinuses
 //                   91, 92), F 84..88 (piriform fossa; + the radiation currents 93..96)
-//   X1 glottis model + output filters, X2 noise sources
+//   X1 glottis model + output filters (+ half of the noise-source stage), X2 radiation loads + noise sources
 enum { W_GP = 0, W_P1, W_P2, W_M0, W_M1, W_M2, W_M3, W_NV, W_T0, W_T1, W_N2, W_T2, W_X1, W_F, W_X2, W_N1 };
 // separators of the partition (last current of every segment + the first currents of the branches)
 enum { S7 = 0, S15, S22, S28, S29, S34, S40, S41, S46, S52, S58, S64, S65, S70, S75, S83, NSEP };
@@ -141,8 +141,8 @@ struct TdsSmem {
   // pharynx/mouth sections 25..64, 40 = lips; nmag: j = current - 25 for the currents 25..65, 41 = current 84.
   double nmag[42][LANES];                        // noiseMagnitude (TdsModel.h:143) of the currents a constriction can feed
   double namp[41][LANES], ncut[41][LANES], nout[41][LANES];  // currentAmp, cutoff, last filter output (TdsModel.h:101-112)
-  // the source stage is split between warps X2 (sources a constriction feeds this step) and X1 (sources that only
-  // decay): live sources and the sources that draw a sample this step, [0] = X2's share, [1] = X1's
+  // the source stage is shared by warps X2 and X1 (noise_stage): live sources and the sources that draw a sample
+  // this step, [0] = X2's share, [1] = X1's
   unsigned long long nzlive[2][LANES], nzdraw[2][LANES];
   double nzlip[LANES];                           // noiseMagnitude of the flow through the lips (currents 93 + 94)
   // glibc random() TYPE_3 (r[i] = r[i-3] + r[i-31]) in a ring of 36 = 3 x 12 words: the twelve draws of one noise
@@ -368,7 +368,7 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "mem
 __device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-// noise sources (warp X2), see noise_scan / noise_sources below
+// noise sources (warps X2 and X1), see noise_scan / noise_stage below
 struct NoiseCons {
   int valid, nar, kind, up, teeth, lateral;  // nar: narrowest section as pharynx/mouth index, -1 = upper glottis
   double downF;                              // kind: 0 vocal folds, 1 tongue, 2 lower lip
@@ -936,7 +936,7 @@ __device__ __forceinline__ void radiation_back(const TdsParams &P, TdsSmem &S, c
 }
 
 // ==================================================================================
-// Noise sources (warp X2): TdsModel::calcNoiseSources / calcNoiseSample (TdsModel.cpp:1188-1708)
+// Noise sources (pre-pass kernel; warps X2 and X1): TdsModel::calcNoiseSources / calcNoiseSample (TdsModel.cpp:1188-1708)
 // ==================================================================================
 // Everything that DECIDES something (which sections form a constriction, where its obstacle is, how many random
 // numbers are drawn) repeats the reference's arithmetic operation by operation (explicit round-to-nearest
