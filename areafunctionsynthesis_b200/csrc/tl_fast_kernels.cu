@@ -393,6 +393,9 @@ tl_sweep_fast_direct_kernel(const TlParams p, const afs_tube_frame *__restrict__
         if (lo <= TRACHEA_LAST && hi > TRACHEA_LAST) hi = TRACHEA_LAST;
         if (fossa && lo <= PHAR0 + FOSSA_COUPLING && hi > PHAR0 + FOSSA_COUPLING) hi = PHAR0 + FOSSA_COUPLING;
         const cx g = lo <= TRACHEA_LAST ? b.g1 : b.g0;
+#ifdef AFS_TLF_UNROLL2
+#pragma unroll 2
+#endif
         for (int k = lo; k <= hi; k++) chain_section(S, b, pre, g, k, c);
         if (fossa && hi == PHAR0 + FOSSA_COUPLING && (tail || hi < hi_all)) chain_shunt(c, fossaY);
         lo = hi + 1;
@@ -403,6 +406,9 @@ tl_sweep_fast_direct_kernel(const TlParams p, const afs_tube_frame *__restrict__
     // so two complex numbers per branch stay live instead of a matrix.
     const cx mouthRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[0]);
     const cx noseRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[1]);
+#ifdef AFS_TLF_UNROLL2
+#pragma unroll 2
+#endif
     for (int k = MOUTH0; k <= MOUTH_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
     cx mA, mC, nA, nC;
     {
