@@ -46,7 +46,7 @@ __device__ __forceinline__ cx cx_rdiv(double x, cx d) {
 
 constexpr int TLF_THREADS = 128;
 #ifndef AFS_TLF_MINB
-#define AFS_TLF_MINB 4  // 128 registers, 16 warps/SM (96 registers / 20 warps spills: 1.96 vs 1.70 ms)
+#define AFS_TLF_MINB 4  // 128 registers, 16 warps/SM (96 registers / 20 warps spills: 1.96 vs 1.70 ms; unrolling the section loops by 2: 1.73 ms)
 #endif
 
 struct __align__(16) TlElem {
@@ -393,9 +393,6 @@ tl_sweep_fast_direct_kernel(const TlParams p, const afs_tube_frame *__restrict__
         if (lo <= TRACHEA_LAST && hi > TRACHEA_LAST) hi = TRACHEA_LAST;
         if (fossa && lo <= PHAR0 + FOSSA_COUPLING && hi > PHAR0 + FOSSA_COUPLING) hi = PHAR0 + FOSSA_COUPLING;
         const cx g = lo <= TRACHEA_LAST ? b.g1 : b.g0;
-#ifdef AFS_TLF_UNROLL2
-#pragma unroll 2
-#endif
         for (int k = lo; k <= hi; k++) chain_section(S, b, pre, g, k, c);
         if (fossa && hi == PHAR0 + FOSSA_COUPLING && (tail || hi < hi_all)) chain_shunt(c, fossaY);
         lo = hi + 1;
@@ -406,9 +403,6 @@ tl_sweep_fast_direct_kernel(const TlParams p, const afs_tube_frame *__restrict__
     // so two complex numbers per branch stay live instead of a matrix.
     const cx mouthRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[0]);
     const cx noseRad = radiation_fast(p.o.radiation, b.omega_raw, S.rad[1]);
-#ifdef AFS_TLF_UNROLL2
-#pragma unroll 2
-#endif
     for (int k = MOUTH0; k <= MOUTH_LAST; k++) chain_section(S, b, pre, b.g0, k, c);
     cx mA, mC, nA, nC;
     {
