@@ -144,65 +144,88 @@ double tf_value(const TfNode *nodes, int N, double t) {  // TimeFunction::getVal
   const double a = (t - nodes[left].time) / deno;
   return nodes[left].value + a * (nodes[right].value - nodes[left].value);
 }
-double lf_epsilon(double ta, double te) {  // LfPulse::getEpsilon (Newton; the reference's step counter never counts)
-  double c = 1.0 - te;
-  if (c < 0.001) c = 0.001;
-  if (ta < 0.0001) ta = 0.0001;
-  if (ta > c - 0.00001) ta = c - 0.00001;
-  double epsilon = 1.0 / ta, h, h2;
-  int guard = 0;
-  do {
-    h = 1.0 - exp(-epsilon * c) - epsilon * ta;
-    h2 = c * exp(-epsilon * c) - ta;
-    epsilon = epsilon - h / h2;
-  } while (fabs(h) > 0.00001 && ++guard < 100000);
-  return epsilon;
-}
-double lf_alpha(double tp, double te, double ta, double epsilon) {  // LfPulse::getAlpha (regula falsi)
-  const double w = M_PI / tp, w2 = w * w, SIN = sin(w * te), COS = cos(w * te);
-  const double X = (SIN * exp(epsilon * te) * (-exp(-epsilon) / epsilon - exp(-epsilon))) / (epsilon * ta);
-  const double Y = (SIN * exp(epsilon * te) * (-exp(-epsilon * te) / epsilon - te * exp(-epsilon))) / (epsilon * ta);
-  double a[2] = {0.0, 0.0}, h[2], newAlpha, newH;
-  int numSteps = 0;
-  do {
-    numSteps++;
-    a[1] += 1.0;
-    h[1] = w / (w2 + a[1] * a[1]) + exp(a[1] * te) * ((a[1] * SIN - w * COS) / (w2 + a[1] * a[1]) + X - Y);
-  } while ((numSteps < 20) && (h[1] >= 0.0));
-  if (h[1] >= 0) return 0.0;
-  numSteps = 0;
-  do {
-    h[0] = w / (w2 + a[0] * a[0]) + exp(a[0] * te) * ((a[0] * SIN - w * COS) / (w2 + a[0] * a[0]) + X - Y);
-    h[1] = w / (w2 + a[1] * a[1]) + exp(a[1] * te) * ((a[1] * SIN - w * COS) / (w2 + a[1] * a[1]) + X - Y);
-    newAlpha = a[0] - (h[0] * (a[1] - a[0])) / (h[1] - h[0]);
-    newH = w / (w2 + newAlpha * newAlpha) + exp(newAlpha * te) * ((newAlpha * SIN - w * COS) / (w2 + newAlpha * newAlpha) + X - Y);
-    if (newH < 0.0) a[1] = newAlpha; else a[0] = newAlpha;
-    numSteps++;
-  } while ((numSteps < 20) && (fabs(newH) > 0.00001));
-  return newAlpha;
-}
+// One period of the LF model on the unit interval (LfPulse.cpp:37-245).  The reference solves two scalar equations
+// per period -- the return-phase constant by Newton's method, the growth constant of the open phase by bracketing +
+// false position -- and then evaluates the two closed-form branches of the flow.  The numerical procedures are the
+// reference's (same iterates in the same order => same bits); they are organised here around the residual of each
+// equation.
+struct ReturnPhase {   // 1 - exp(-eps c) = eps ta, c = 1 - te
+  double c, ta;
+  ReturnPhase(double ta_in, double te) : c(1.0 - te), ta(ta_in) {
+    if (c < 0.001) c = 0.001;
+    if (ta < 0.0001) ta = 0.0001;
+    const double ta_max = c - 0.00001;
+    if (ta > ta_max) ta = ta_max;
+  }
+  double residual(double eps) const { return 1.0 - exp(-eps * c) - eps * ta; }
+  double slope(double eps) const { return c * exp(-eps * c) - ta; }
+  // Newton from 1 / ta until the residual BEFORE the update is within 1e-5 (the reference's step counter never
+  // counts, LfPulse.cpp:139-146; the guard only protects against NaN input)
+  double solve() const {
+    double eps = 1.0 / ta;
+    for (int guard = 0; guard < 100000; guard++) {
+      const double f = residual(eps);
+      eps = eps - f / slope(eps);
+      if (!(fabs(f) > 0.00001)) break;
+    }
+    return eps;
+  }
+};
+struct OpenPhase {     // area balance of the pulse as a function of the growth constant
+  double w, w2, s_te, c_te, te, tail_end, tail_te;
+  OpenPhase(double tp, double te_in, double ta, double eps) : te(te_in) {
+    w = M_PI / tp;
+    w2 = w * w;
+    s_te = sin(w * te);
+    c_te = cos(w * te);
+    const double lead = s_te * exp(eps * te);
+    const double at_end = (lead * (-exp(-eps) / eps - exp(-eps))) / (eps * ta);
+    const double at_te = (lead * (-exp(-eps * te) / eps - te * exp(-eps))) / (eps * ta);
+    tail_end = at_end; tail_te = at_te;  // (two terms: the reference adds them one after the other)
+  }
+  double operator()(double a) const {
+    const double q = w2 + a * a;
+    return w / q + exp(a * te) * ((a * s_te - w * c_te) / q + tail_end - tail_te);
+  }
+  // bracket [0, n] with unit steps (at most 20), then at most 20 false-position updates
+  double solve() const {
+    double lo = 0.0, hi = 0.0, f_hi = 0.0;
+    for (int n = 0; n < 20; n++) {
+      hi += 1.0;
+      f_hi = (*this)(hi);
+      if (!(f_hi >= 0.0)) break;
+    }
+    if (f_hi >= 0) return 0.0;
+    double root = 0.0;
+    for (int n = 0; n < 20; n++) {
+      const double f_lo = (*this)(lo);
+      f_hi = (*this)(hi);
+      root = lo - (f_lo * (hi - lo)) / (f_hi - f_lo);
+      const double f_root = (*this)(root);
+      (f_root < 0.0 ? hi : lo) = root;
+      if (!(fabs(f_root) > 0.00001)) break;
+    }
+    return root;
+  }
+};
 // LfPulse::getPulse(s, numSamples, false): one period of the glottal FLOW
 void lf_pulse(double AMP, double OQ, double SQ, double TL, int numSamples, double *x) {
-  const double T0 = 1.0, te = OQ, tp = (te * SQ) / (1.0 + SQ);
-  double ta = TL;
-  if (ta < 0.01) ta = 0.01;
-  if (ta > T0 - te) ta = T0 - te;
-  const double epsilon = lf_epsilon(ta, te);
-  const double alpha = lf_alpha(tp, te, ta, epsilon);
-  double B;
-  {  // LfPulse::getB
-    const double w = 3.1415926 / tp;
-    const double help = (exp(alpha * tp) * (alpha * sin(w * tp) - w * cos(w * tp)) + w) / (w * w + alpha * alpha);
-    B = AMP / help;
-  }
-  const double w = 3.1415926 / tp;
-  const double u1_te = (B * (exp(alpha * te) * (alpha * sin(w * te) - w * cos(w * te)) + w)) / (w * w + alpha * alpha);
-  const double preFactor = (B * exp(alpha * te) * sin(w * te) * exp(epsilon * te)) / (epsilon * ta);
-  const double F2_te = preFactor * (-exp(-epsilon * te) / epsilon - te * exp(-epsilon * T0));
+  const double te = OQ, tp = (te * SQ) / (1.0 + SQ);
+  double ta = TL < 0.01 ? 0.01 : TL;
+  if (ta > 1.0 - te) ta = 1.0 - te;
+  const double eps = ReturnPhase(ta, te).solve();
+  const double alpha = OpenPhase(tp, te, ta, eps).solve();
+  const double w = 3.1415926 / tp;  // (sic: the flow branches use the truncated constant, LfPulse.cpp:81,214)
+  const double den = w * w + alpha * alpha;
+  auto rise = [&](double t) { return exp(alpha * t) * (alpha * sin(w * t) - w * cos(w * t)) + w; };
+  const double B = AMP / (rise(tp) / den);  // LfPulse::getB
+  const double flow_te = (B * rise(te)) / den;
+  const double k = (B * exp(alpha * te) * sin(w * te) * exp(eps * te)) / (eps * ta);
+  auto decay = [&](double t) { return k * (-exp(-eps * t) / eps - t * exp(-eps * 1.0)); };
+  const double decay_te = decay(te);
   for (int i = 0; i < numSamples; i++) {
     const double t = (double)i / (double)numSamples;
-    if (t <= te) x[i] = (B * (exp(alpha * t) * (alpha * sin(w * t) - w * cos(w * t)) + w)) / (w * w + alpha * alpha);
-    else x[i] = u1_te + preFactor * (-exp(-epsilon * t) / epsilon - t * exp(-epsilon * T0)) - F2_te;
+    x[i] = t <= te ? (B * rise(t)) / den : flow_te + decay(t) - decay_te;
   }
 }
 }  // namespace
