@@ -9,10 +9,17 @@ transfer functions per second at 2048 bins (reported in the same JSON line under
 A "step" is one pass of the hot path over one batch of synthetic input:
   TDS  4096 independent utterances per GPU, each a 1 s vowel-to-vowel transition simulated at 44.1 kHz
        with the nasal branch open (velum U[0,1] cm^2 per endpoint) and the subglottal tract (always
-       part of the 93-section network) -- BASELINE config 4 ("workload": "tds_nasal_subglottal_b4096").
-       N > 1: every rank gets its own 4096 utterances (weak scaling, no data-path collective; a small
-       NCCL all_gather of per-utterance checksums after the timed region collects the outputs' digest).
-  TL   4096 random parametric area functions x 2048 bins -- BASELINE config 2.
+       part of the 93-section network), the reference's DEFAULT options (TdsModel.cpp:35-44, i.e.
+       generateNoiseSources = true; every utterance owns a seeded random() stream) -- BASELINE configs[3]
+       ("workload": "tds_nasal_subglottal_b4096").  N > 1: every rank gets its own 4096 utterances
+       ("scaling": "weak", no data-path collective); the same JSON line carries `strong`: BASELINE configs[3]
+       as written, 4096 utterances IN TOTAL sharded over the N ranks.
+  TL   4096 random parametric area functions x 2048 bins -- BASELINE configs[1].
+Other BASELINE configs in the same line: `c1_default_a` (configs[0]: Default.params /a/, one TL spectrum + 1 s TDS,
+reference on one core beside the batch-of-one latency here), `oral_b1024` (configs[2]), `dataset_sweep` (configs[4]:
+65 536 parameter sets in total sharded over the N ranks).
+`parity` (N = 1): the audio of the first utterances of the ACTUAL bench batch against the compiled reference run on the
+host cores, 1 s each, noise sources off and on (the reference seeded with srand(seed_b) per utterance).
 
 `value` is device-resident throughput (inputs already in HBM), timed with CUDA events on the launching
 stream; `e2e` is the same metric through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed
@@ -39,9 +46,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W_TDS = 1.0e4  # algorithmic FP64 flop per tract-step
+W_TDS = 1.0e4  # algorithmic FP64 flop per tract-step, noise sources off
+W_TDS_NOISE = 1.06e4  # ... with the noise sources (+0.6 k)
 W_TL = 8.0e3   # algorithmic FP64 flop per (area function, bin)
-TDS_TRAFFIC_BYTES = 32610816 + 692230400  # profiles/r1c_tds_ncu.txt: 4096 tracts x 44100 steps, one launch
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 DFMA/clk x 2 flop x 1.965 GHz = 37.2
 W_TL_FAST = 4.4e3  # FP64 flop per (area function, bin) the ladder formulation of K2f executes (84 sections x 43 + sinuses + algebra)
 B_TDS = 4096
 T_SEC = 1.0  # overridden by --utt-seconds (profiling only)
@@ -129,7 +137,7 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU implementation (oracle/_ref), all host threads
+# reference arm: the reference's own CPU implementation (oracle/_ref), all host cores
 # ---------------------------------------------------------------------------------------------------
 def host_threads():
     try:
@@ -138,27 +146,54 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_reference(n_threads, utt_seconds, n_utts=None, seed=20260003):
-    """Times the compiled reference on `n_utts` utterances of `utt_seconds` each over `n_threads` threads."""
-    from oracle.pyoracle import Oracle, Ref
-    fr, gl = make_tds_batch(n_utts or n_threads, seed)
-    n_out = int(round(utt_seconds * FS / SR_FACTOR))
+def bench_seeds(n, rank=0):
+    """srand() seed of utterance b of rank r's bench batch."""
+    return (np.arange(1, n + 1, dtype=np.int64) + 7919 * rank).astype(np.uint32)
+
+
+def _ref_worker(job):
+    """One worker PROCESS of the reference pool: the compiled reference (oracle/_ref) on a slice of utterances, one
+    after the other on one core.  Processes, not threads: with generateNoiseSources = true the reference draws from
+    libc rand() (TdsModel.cpp:1690-1696), which is per-process state."""
+    fr_bytes, gl, seeds, n_out, noise, want_audio = job
+    from oracle.pyoracle import FRAME_DTYPE, Oracle, Ref, tds_options_default
+    fr = np.frombuffer(fr_bytes, dtype=FRAME_DTYPE).reshape(len(gl), -1)
+    opts = tds_options_default(noise=noise)
     try:
-        ref = Ref(44)
-        kind = "reference"
-        t0 = time.perf_counter()
-        ref.tds_synthesize(fr, gl, [n_out], want_flow=False, threads=n_threads)
-        dt = time.perf_counter() - t0
-        cores = n_threads
+        ref, kind = Ref(44), "reference"
     except (FileNotFoundError, OSError):
-        orc = Oracle()  # scalar restatement, one thread
-        kind, cores = "port", 1
-        fr, gl = fr[:1], gl[:1]
-        t0 = time.perf_counter()
-        orc.tds_synthesize(fr, gl, [n_out], FS, SR_FACTOR, want_flow=False)
-        dt = time.perf_counter() - t0
-    audio_s = len(fr) * n_out * SR_FACTOR / FS
-    return audio_s / dt, kind, cores, dt, len(fr)
+        ref, kind = Oracle(), "port"
+    t0 = time.time()
+    if kind == "reference":
+        audio, _ = ref.tds_synthesize(fr, gl, [n_out], opts=opts, seeds=seeds, want_flow=False, threads=1)
+    else:
+        audio, _ = ref.tds_synthesize(fr, gl, [n_out], FS, SR_FACTOR, opts=opts, seeds=seeds, want_flow=False)
+    t1 = time.time()
+    return t0, t1, kind, (audio if want_audio else None)
+
+
+class RefPool:
+    """Persistent pool of worker processes (spawned: nothing of CUDA / NCCL is inherited)."""
+
+    def __init__(self, workers):
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        self.workers = workers
+        self.ex = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn"))
+
+    def run(self, fr, gl, seeds, n_out, noise, want_audio=False):
+        """Utterances split into `workers` contiguous slices.  Returns (audio-s/s, wall s, kind, audio or None)."""
+        n = len(fr)
+        cuts = np.linspace(0, n, min(self.workers, n) + 1).astype(int)
+        jobs = [(np.ascontiguousarray(fr[lo:hi]).tobytes(), np.ascontiguousarray(gl[lo:hi]),
+                 np.ascontiguousarray(seeds[lo:hi]), n_out, bool(noise), want_audio) for lo, hi in zip(cuts[:-1], cuts[1:])]
+        res = list(self.ex.map(_ref_worker, jobs))
+        wall = max(r[1] for r in res) - min(r[0] for r in res)
+        audio = np.concatenate([r[3] for r in res]) if want_audio else None
+        return n * n_out * SR_FACTOR / FS / wall, wall, res[0][2], audio
+
+    def close(self):
+        self.ex.shutdown()
 
 
 def cpu_reference_tl(n_threads, n_tubes):
@@ -180,21 +215,27 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = host_threads()
+    cores = host_threads()
     utt = 0.25  # seconds of audio per utterance per step: bounded sample of the 1 s workload
+    n_out = int(round(utt * FS / SR_FACTOR))
+    fr, gl = make_tds_batch(cores, 20260003)
+    seeds = bench_seeds(cores)
+    pool = RefPool(cores)
     vals = []
     for i in range(args.warmup + args.steps):
-        v, kind, cores, dt, n = cpu_reference(threads, utt)
+        v, dt, kind, _ = pool.run(fr, gl, seeds, n_out, noise=True)
         if i >= args.warmup:
             vals.append((v, dt))
+    pool.close()
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([d for _, d in vals]) * 1e3)
-    sample = f"{n} utterances x {utt} s @44.1 kHz per step, one per thread ({kind})"
+    sample = (f"{cores} utterances x {utt} s @44.1 kHz per step, one per core ({cores} worker processes, {kind}), "
+              "default options (noise sources on)")
     line = {"impl": "reference", "metric": "tds_audio_seconds_per_second", "value": value,
             "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "tds_nasal_subglottal_b4096", "batch_per_gpu": B_TDS, "utterance_s": T_SEC,
-                       "fs_tds_hz": FS, "sample": sample},
+                       "fs_tds_hz": FS, "noise_sources": True, "sample": sample},
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -204,6 +245,56 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def traffic_of(key):
+    """DRAM bytes per launch of the dominant kernel from this round's `ncu --set full` capture (profiles/traffic.json,
+    written by tools/ncu_summary.py from the .ncu-rep); null when the kernel has not been captured since it changed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        return {"traffic": t["bytes"], "traffic_source": t["source"]}
+    except Exception:
+        return {"traffic": None, "traffic_source": "no capture of the current kernel"}
+
+
+def config1_default_a(ctx):
+    """BASELINE configs[0]: Default.params /a:/ -- one TL transfer function (N = 8192, K = 2048) and 1 s of TDS audio at
+    44.1 kHz, the reference on ONE core beside the batch-of-one latency of the device path (host API, copies included)."""
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import Ref, tds_options_default as ref_opts
+    g = np.load(os.path.join(ROOT, "tests", "golden", "default_shapes.npz"))
+    k = [str(x) for x in g["names"]].index("a:")
+    f = g["frames"][k:k + 1].copy()
+    f["glottis_area_cm2"] = 0.0
+    out = {"workload": "Default.params a: -- FLOW_SOURCE_TF 2048 bins + 1 s TDS at 44.1 kHz (F0 120 Hz, 8000 dPa)"}
+    try:
+        r22, r44 = Ref(22), Ref(44)
+    except (FileNotFoundError, OSError):
+        return None
+    t0 = time.perf_counter(); rre, rim = r22.tl_spectrum(f, 8192); t_ref_tl = time.perf_counter() - t0
+    ctx.tl_sweep(f, F0_TL, K_TL)
+    t0 = time.perf_counter(); re, im = ctx.tl_sweep(f, F0_TL, K_TL); t_tl = time.perf_counter() - t0
+    fr2 = np.stack([g["frames"][k], g["frames"][k]])[None]
+    gl2 = np.tile(np.array([120.0, 8000.0, 0.01, 0.01, 0.0, -40.0]), (1, 2, 1))
+    n_out = int(round(FS / SR_FACTOR))
+    sd = np.array([1234], dtype=np.uint32)
+    tds = {}
+    for name, noise in (("noise_sources_on", True), ("noise_sources_off", False)):
+        t0 = time.perf_counter()
+        ra, _ = r44.tds_synthesize(fr2, gl2, [n_out], opts=ref_opts(noise=noise), seeds=sd, want_flow=False)
+        t_ref = time.perf_counter() - t0
+        o = afs.tds_options_default(noise=noise)
+        ctx.tds_synthesize(fr2, gl2, [n_out], FS, SR_FACTOR, opts=o, seeds=sd)
+        t0 = time.perf_counter()
+        a, _, _ = ctx.tds_synthesize(fr2, gl2, [n_out], FS, SR_FACTOR, opts=o, seeds=sd)
+        t_dev = time.perf_counter() - t0
+        tds[name] = {"reference_s": t_ref, "device_s": t_dev, "rel_err": float(np.max(np.abs(a - ra)) / np.max(np.abs(ra)))}
+    nb = rre.shape[1]
+    out["tl"] = {"reference_s": t_ref_tl, "device_s": t_tl, "bins_compared": int(nb),
+                 "bit_identical": bool(np.array_equal(re[:, :nb], rre) and np.array_equal(im[:, :nb], rim))}
+    out["tds"] = tds
+    out["cores"] = 1
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -255,25 +346,27 @@ def run_ours(args):
         barrier()
         return max_over_ranks(tot)
 
-    # ---------------- TDS: headline --------------------------------------------------------------
+    # ---------------- TDS: headline (reference-default options: noise sources ON) -----------------------
     n_out = int(round(T_SEC * FS / SR_FACTOR))
     total_steps = n_out * SR_FACTOR
     fr, gl = make_tds_batch(B_TDS, 20260003 + rank)
+    seeds = bench_seeds(B_TDS, rank)
     frame_len = np.array([n_out], dtype=np.int32)
     d_fr = torch.from_numpy(fr.view(np.uint8).reshape(B_TDS, -1)).to(dev)
     d_gl = torch.from_numpy(gl).to(dev)
-    d_audio = torch.empty(B_TDS, n_out, dtype=torch.float64, device=dev)
+    d_seeds = torch.from_numpy(seeds.view(np.int32)).to(dev)
+    d_audio = torch.empty(B_TDS, n_out, dtype=torch.float64, device=dev)       # noise sources on
+    d_audio_off = torch.empty(B_TDS, n_out, dtype=torch.float64, device=dev)   # noise sources off
     d_status = torch.zeros(B_TDS, dtype=torch.int32, device=dev)
+    noisy = afs.tds_options_default(noise=True)    # TdsModel::TdsModel() defaults (TdsModel.cpp:35-44)
+    quiet = afs.tds_options_default(noise=False)
 
-    quiet = afs.tds_options_default(noise=False)  # headline: noise sources off (the multi-threaded reference arm needs that)
-
-    def tds_dev():
-        ctx.tds_synthesize_device(d_fr, d_gl, B_TDS, 2, frame_len, d_audio, stream, FS, SR_FACTOR, opts=quiet,
-                                  d_status=d_status)
+    def tds_dev(n=B_TDS, opts=noisy, out=d_audio):
+        ctx.tds_synthesize_device(d_fr, d_gl, n, 2, frame_len, out, stream, FS, SR_FACTOR, opts=opts,
+                                  d_seeds=d_seeds, d_status=d_status)
 
     fp64_peak = ctx.probe_fp64_tflops()
     sampler = ClockSampler(local)
-    l0 = ctx.launch_count
     for _ in range(args.warmup):
         tds_dev()
     barrier()
@@ -286,29 +379,39 @@ def run_ours(args):
     audio_s_per_step = world * B_TDS * T_SEC
     value = audio_s_per_step / (ms_step * 1e-3)
     assert int(d_status.sum().item()) == 0, "non-finite values in the TDS batch"
-    tds_tflops = W_TDS * B_TDS * total_steps / (ms_step * 1e-3) / 1e12  # this rank's kernel
+    tds_tflops = W_TDS_NOISE * B_TDS * total_steps / (ms_step * 1e-3) / 1e12  # this rank's kernels (pre-pass + time loop)
 
-    # e2e: pinned host buffers -> C-ABI host call (H2D + kernel + D2H)
+    # same batch with generateNoiseSources = false
+    off_steps = max(1, min(args.steps, 3))
+    off_ms = timed(lambda: tds_dev(opts=quiet, out=d_audio_off), off_steps, 1) / off_steps
+    assert int(d_status.sum().item()) == 0, "non-finite values in the TDS batch (noise sources off)"
+    off_tflops = W_TDS * B_TDS * total_steps / (off_ms * 1e-3) / 1e12
+
+    # e2e: pinned host buffers -> C-ABI host call (H2D + kernels + D2H inside the timed region)
     h_fr = torch.from_numpy(fr.view(np.uint8).reshape(B_TDS, -1).copy()).pin_memory()
     h_gl = torch.from_numpy(gl.copy()).pin_memory()
+    h_seeds = torch.from_numpy(seeds.view(np.int32).copy()).pin_memory()
     h_audio = torch.empty(B_TDS, n_out, dtype=torch.float64).pin_memory()
     h_status = torch.zeros(B_TDS, dtype=torch.int32).pin_memory()
-    opts = quiet
 
-    def tds_host():
+    def tds_host(opts):
         rc = ctx.lib.afs_tds_synthesize(ctx.h, afs.api.C.byref(opts), B_TDS, 2, frame_len.ctypes.data,
-                                        h_fr.data_ptr(), h_gl.data_ptr(), FS, SR_FACTOR, None, h_audio.data_ptr(), None,
-                                        h_status.data_ptr())
+                                        h_fr.data_ptr(), h_gl.data_ptr(), FS, SR_FACTOR, h_seeds.data_ptr(), h_audio.data_ptr(),
+                                        None, h_status.data_ptr())
         assert rc == 0, rc
 
-    tds_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        tds_host()
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    e2e_value = audio_s_per_step / e2e_s
+    def e2e_of(opts, steps):
+        tds_host(opts)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tds_host(opts)
+        barrier()
+        return audio_s_per_step / max_over_ranks((time.perf_counter() - t0) / steps)
+
+    e2e_off = e2e_of(quiet, off_steps)
+    assert torch.equal(h_audio, d_audio_off.cpu()), "host-path audio differs from the device-resident path (noise off)"
+    e2e_value = e2e_of(noisy, args.steps)
     assert torch.equal(h_audio, d_audio.cpu()), "host-path audio differs from the device-resident path"
 
     # the only collective of the path: one all-gather of the outputs, after the compute; timed separately
@@ -330,17 +433,35 @@ def run_ours(args):
         del all_audio
     digest_mean = float(digest.mean().item())
 
-    # same workload with the reference's default generateNoiseSources = true (per-utterance random() streams)
-    noisy = afs.tds_options_default(noise=True)
-    d_seeds = torch.arange(1, B_TDS + 1, dtype=torch.int32, device=dev) + 7919 * rank
+    # ---------------- BASELINE configs[3] as written: 4096 utterances IN TOTAL, sharded over the ranks -----
+    # (strong scaling; contiguous shards, no data-path collective.  Rank r runs the first hi - lo utterances of its own
+    #  batch: same work as a slice of one global batch.)
+    from areafunctionsynthesis_b200.sharding import shard_bounds
+    lo_s, hi_s = shard_bounds(B_TDS, world)[rank]
+    n_shard = hi_s - lo_s
+    strong_steps = max(1, min(args.steps, 3))
+    strong = {}
+    for name, o in (("noise_sources_on", noisy), ("noise_sources_off", quiet)):
+        ms = timed(lambda: tds_dev(n=n_shard, opts=o), strong_steps, 1) / strong_steps
+        strong[name] = {"value": B_TDS * T_SEC / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms}
+    assert int(d_status[:n_shard].sum().item()) == 0
 
-    def tds_noise_dev():
-        ctx.tds_synthesize_device(d_fr, d_gl, B_TDS, 2, frame_len, d_audio, stream, FS, SR_FACTOR, opts=noisy,
-                                  d_seeds=d_seeds, d_status=d_status)
-
-    noise_steps = max(1, min(args.steps, 2))
-    noise_ms = timed(tds_noise_dev, noise_steps, 1) / noise_steps
-    assert int(d_status.sum().item()) == 0, "non-finite values in the TDS batch (noise sources on)"
+    # ---------------- BASELINE configs[2]: 1024 oral vowel-to-vowel transitions per GPU ---------------------
+    B_ORAL = 1024
+    fr_o, gl_o = make_tds_batch(B_ORAL, 20260002 + rank)
+    fr_o["velum_area_cm2"] = 0.0
+    d_fr_o = torch.from_numpy(fr_o.view(np.uint8).reshape(B_ORAL, -1)).to(dev)
+    d_gl_o = torch.from_numpy(gl_o).to(dev)
+    oral = {}
+    for name, o in (("noise_sources_on", noisy), ("noise_sources_off", quiet)):
+        def oral_dev():
+            ctx.tds_synthesize_device(d_fr_o, d_gl_o, B_ORAL, 2, frame_len, d_audio_off, stream, FS, SR_FACTOR, opts=o,
+                                      d_seeds=d_seeds, d_status=d_status)
+        ms = timed(oral_dev, strong_steps, 1) / strong_steps
+        oral[name] = {"value": world * B_ORAL * T_SEC / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms}
+    assert int(d_status[:B_ORAL].sum().item()) == 0
+    tds_dev(opts=quiet, out=d_audio_off)  # (d_audio_off served as scratch above: restore the noise-off audio for `parity`)
+    torch.cuda.synchronize()
 
     # ---------------- TL: second metric -----------------------------------------------------------
     f_tl = make_tl_batch(B_TL, 20260001 + rank)
@@ -419,6 +540,27 @@ def run_ours(args):
         assert np.array_equal(dev_fr["articulator"], host_fr["articulator"])
         assert np.max(np.abs(dev_fr["area_cm2"] - host_fr["area_cm2"]) / host_fr["area_cm2"]) <= 1e-12
 
+    # ---------------- BASELINE configs[4] (C5): 65 536 parameter sets IN TOTAL sharded over the ranks ----------
+    # parameter sets -> frames (K4) -> 2048-bin spectra (K2) + 0.5 s TDS audio at 44.1 kHz (K1, default options)
+    from areafunctionsynthesis_b200.sweep import dataset_sweep
+    lo_d, hi_d = shard_bounds(B_RA, world)[rank]
+    n_ds = hi_d - lo_d
+    ds_seeds = bench_seeds(n_ds, rank)
+    ds = dataset_sweep(ctx, pr[:min(n_ds, 4096)], want_formants=False, tds_opts=noisy, seeds=ds_seeds[:min(n_ds, 4096)])  # warm-up
+    del ds
+    barrier()
+    t0 = time.perf_counter()
+    ds = dataset_sweep(ctx, pr[:n_ds], want_formants=False, tds_opts=noisy, seeds=ds_seeds)
+    barrier()
+    ds_s = max_over_ranks(time.perf_counter() - t0)
+    assert int(ds["status"].sum().item()) == 0
+    del ds
+    torch.cuda.empty_cache()
+    dataset = {"metric": "parameter_sets_per_second", "value": B_RA / ds_s, "unit": "sets/s", "seconds": ds_s,
+               "config": {"workload": f"{B_RA} parameter sets in total, {n_ds} on this rank (BASELINE configs[4]) -> frames (K4) -> "
+                                      "2048-bin spectra (K2, bit-identical arithmetic) + 0.5 s TDS audio at 44.1 kHz (K1, default "
+                                      "options: noise sources on), all stages on the device; wall clock incl. the H2D of the parameters"}}
+
     # ---------------- formant optimiser and LF vowel synthesis (small legs, host API) ------
     extra = {}
     if world == 1:
@@ -444,20 +586,6 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         extra["lf_vowels"] = {"metric": "lf_vowels_per_second", "value": n_lf / dt, "unit": "vowels/s (0.65 s each, 22.05 kHz)",
                               "config": {"workload": f"{n_lf} long vowels, host API incl. pulse trains and copies"}, "cpu_baseline": None}
-        # BASELINE configs[4] (C5), one GPU's share of 65 536 sets over 8 GPUs: parameter sets -> frames -> TL spectra + 0.5 s TDS
-        from areafunctionsynthesis_b200.sweep import dataset_sweep
-        n_ds = 8192
-        dataset_sweep(ctx, pr[:n_ds], want_formants=False, tds_opts=quiet)  # warm-up (buffers)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ds = dataset_sweep(ctx, pr[:n_ds], want_formants=False, tds_opts=quiet)
-        dt = time.perf_counter() - t0
-        assert int(ds["status"].sum().item()) == 0
-        extra["dataset_sweep"] = {"metric": "parameter_sets_per_second", "value": n_ds / dt, "unit": "sets/s", "seconds": dt,
-                                  "config": {"workload": f"{n_ds} parameter sets (one GPU's share of BASELINE configs[4]) -> frames (K4) -> 2048-bin "
-                                                         "spectra (K2, bit-identical arithmetic) + 0.5 s TDS audio at 44.1 kHz (K1, noise sources off), "
-                                                         "all stages on the device"}}
-        del ds
         n_ts = 256
         gt = np.load(os.path.join(ROOT, "tests", "golden", "target_sequence.npz"))
         sh_ts = np.tile(gt["shapes"], (n_ts // 3 + 1, 1, 1))[:n_ts]
@@ -505,17 +633,39 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------------------------------------
+    # ---------------- CPU baseline, parity of the bench batch, BASELINE configs[0] (rank 0, N = 1 only) -------------
     cpu = None
     tl_cpu = None
+    parity = None
+    c1 = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = host_threads()
-        v, kind, cores, dt, n = cpu_reference(threads, 1.0, n_utts=min(4 * threads, 512))
-        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind,
-               "sample": f"{n} utterances x 1.0 s @44.1 kHz of the same workload over {cores} threads, {dt:.1f} s wall"}
-        tv, tkind, tcores = cpu_reference_tl(threads, 4 * threads)
+        cores = host_threads()
+        pool = RefPool(cores)
+        # the compiled reference on the FIRST utterances of this very batch (same frames, glottis parameters and seeds),
+        # full length; its audio is the parity check of the headline configuration, its wall time the CPU baseline
+        n_par = min(4 * cores, 64)
+        v_on, dt_on, kind, ref_on = pool.run(fr[:n_par], gl[:n_par], seeds[:n_par], n_out, noise=True, want_audio=True)
+        v_off, dt_off, _, ref_off = pool.run(fr[:n_par], gl[:n_par], seeds[:n_par], n_out, noise=False, want_audio=True)
+        pool.close()
+        cpu = {"value": v_on, "unit": "audio-s/s", "cores": cores, "kind": kind,
+               "sample": f"{n_par} utterances x {T_SEC} s @44.1 kHz: the first {n_par} of the bench batch, default options (noise sources "
+                         f"on, srand(seed_b) per utterance), {cores} worker processes, {dt_on:.1f} s wall",
+               "noise_sources_off": {"value": v_off, "unit": "audio-s/s", "seconds": dt_off}}
+
+        def rel_errs(dev_audio, ref):
+            a = dev_audio[:len(ref)].cpu().numpy()
+            return np.max(np.abs(a - ref), axis=1) / np.max(np.abs(ref), axis=1)
+
+        e_on, e_off = rel_errs(d_audio, ref_on), rel_errs(d_audio_off, ref_off)
+        parity = {"bar": 1e-6, "measure": "max_t |audio - reference| / max_t |reference| per utterance, 1 s at 44.1 kHz",
+                  "against": kind, "n": int(n_par),
+                  "noise_sources_on": {"max_rel": float(e_on.max()), "median_rel": float(np.median(e_on))},
+                  "noise_sources_off": {"max_rel": float(e_off.max()), "median_rel": float(np.median(e_off))},
+                  "ok": bool(e_on.max() <= 1e-6 and e_off.max() <= 1e-6)}
+        tv, tkind, tcores = cpu_reference_tl(cores, 4 * cores)
         tl_cpu = {"value": tv, "unit": "spectra/s", "cores": tcores, "kind": tkind,
-                  "sample": f"{4 * threads} area functions x 2048 bins"}
+                  "sample": f"{4 * cores} area functions x 2048 bins"}
+        c1 = config1_default_a(ctx)
 
     peaks = load_peaks()
     line = {
@@ -523,18 +673,20 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "tds_nasal_subglottal_b4096", "batch_per_gpu": B_TDS, "utterance_s": T_SEC,
-                   "fs_tds_hz": FS, "sr_factor": SR_FACTOR, "control_frames": 2, "noise_sources": False,
+                   "fs_tds_hz": FS, "sr_factor": SR_FACTOR, "control_frames": 2, "noise_sources": True,
+                   "options": "TdsModel::TdsModel() defaults (TdsModel.cpp:35-44)",
                    "parallelism": f"independent utterances sharded over {world} GPU(s), no data-path collective",
                    "l2": "flushed between timed steps (256 MiB write, untimed)"},
-        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h_fr.numel() + h_gl.numel() * 8),
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h_fr.numel() + h_gl.numel() * 8 + h_seeds.numel() * 4),
                 "d2h_bytes_per_step": int(h_audio.numel() * 8 + h_status.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": tds_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": tds_tflops / fp64_peak, "traffic": TDS_TRAFFIC_BYTES,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch size (profiles/r1c_tds_ncu.txt); algorithmic output is 722.5 MB",
-                     "kernel": "tds_batch_kernel", "flop_per_tract_step": W_TDS,
+                     "frac": tds_tflops / fp64_peak, **traffic_of("tds_noise_on"),
+                     "kernel": "tds_batch_kernel<noise> (+ tds_noise_scan_kernel, inside the timed step)",
+                     "flop_per_tract_step": W_TDS_NOISE,
                      "peak_source": "afs_probe_fp64_tflops, measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                     "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": tds_tflops / FP64_NOMINAL_TFLOPS,
                      "hbm_gbs_algorithmic": B_TDS * n_out * 8 / (ms_step * 1e-3) / 1e9,
                      "hbm_gbs_peak_measured": peaks.get("hbm_gbs")},
         "cpu_baseline": cpu,
@@ -547,8 +699,18 @@ def run_ours(args):
                    "config": {"workload": "onedim_area_function_to_frames_65536", "sets_per_gpu": B_RA},
                    "cpu_baseline": None if ra_cpu is None else {"value": ra_cpu, "unit": "sets/s", "cores": 1, "kind": "port",
                                                                 "sample": "2048 sets, host rasteriser of the C ABI (bit-identical to the reference on Default.params)"}},
-        "noise_sources_on": {"value": audio_s_per_step / (noise_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": noise_ms,
-                             "steps": noise_steps},
+        "noise_sources_off": {"value": audio_s_per_step / (off_ms * 1e-3), "unit": "audio-s/s", "ms_per_step": off_ms,
+                              "steps": off_steps, "e2e": {"value": e2e_off, "unit": "audio-s/s"},
+                              "roofline": {"bound": "fp64", "achieved": off_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                                           "frac": off_tflops / fp64_peak, "flop_per_tract_step": W_TDS,
+                                           "kernel": "tds_batch_kernel", **traffic_of("tds_noise_off")}},
+        "parity": parity,
+        "strong": {"workload": "BASELINE configs[3] as written: 4096 utterances in total, contiguous shards over the ranks",
+                   "scaling": "strong", "utterances_this_rank": int(n_shard), **strong},
+        "oral_b1024": {"workload": "BASELINE configs[2]: 1024 oral vowel-to-vowel transitions x 1 s per GPU (velum closed)",
+                       "scaling": "weak", **oral},
+        "dataset_sweep": dataset,
+        "c1_default_a": c1,
         "tl": {"metric": "tl_spectra_per_second_2048_bins", "value": tl_value, "unit": "spectra/s", "ms_per_step": tl_ms,
                "config": {"workload": "tl_sweep_4096x2048", "area_functions_per_gpu": B_TL, "bins": K_TL},
                "e2e": {"value": tl_e2e, "unit": "spectra/s", "h2d_bytes_per_step": int(f_tl.nbytes),
