@@ -441,8 +441,8 @@ def run_ours(args):
     n_shard = hi_s - lo_s
     strong_steps = max(1, min(args.steps, 3))
     strong = {}
-    for name, o in (("noise_sources_on", noisy), ("noise_sources_off", quiet)):
-        ms = timed(lambda: tds_dev(n=n_shard, opts=o), strong_steps, 1) / strong_steps
+    for name, o, out in (("noise_sources_on", noisy, d_audio), ("noise_sources_off", quiet, d_audio_off)):
+        ms = timed(lambda: tds_dev(n=n_shard, opts=o, out=out), strong_steps, 1) / strong_steps
         strong[name] = {"value": B_TDS * T_SEC / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms}
     assert int(d_status[:n_shard].sum().item()) == 0
 

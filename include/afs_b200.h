@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AFS_VERSION 100 /* 0.1.0 */
+#define AFS_VERSION 200 /* 0.2.0 */
 
 /* ---- tube topology (Tube.h:53-79) ---------------------------------------- */
 #define AFS_NUM_TRACHEA_SECTIONS 23
@@ -156,7 +156,9 @@ typedef struct afs_tl_options {
  * generate_noise_sources every tract draws from its own glibc-compatible
  * random() stream (the reference shares libc rand(), TdsModel.cpp:1690-1696),
  * seeded by `seeds[tract]` (1 when no seeds are given, like an unseeded
- * process). */
+ * process).  A noise source whose amplitude has decayed below 1e-13 with no constriction feeding it is switched
+ * off (amplitude 0); the reference lets it decay for ever.  A source is silent below 1e-3 (TdsModel.cpp:1642-
+ * 1660), so the samples are the same. */
 typedef struct afs_tds_options {
   int32_t turbulence_losses;
   int32_t soft_walls;
@@ -170,6 +172,14 @@ typedef struct afs_tds_options {
   /* TriangularGlottis static parameters; afs_tds_options_default fills the
    * reference defaults. */
   double glottis_static[AFS_NUM_GLOTTIS_STATIC];
+  /* TdsModel::setFlowSource(flow_cm3_s, section) (TdsModel.cpp:629-633): a constant volume-velocity source
+   * added to the source term of one tube section (TdsModel.cpp:996-1008).  section -1 = none, the state of a
+   * fresh TdsModel (TdsModel.cpp:84) and the default here.  (TdsModel::setPressureSource: the lung pressure is
+   * the PRESSURE entry of the glottis control parameters, applied at the first trachea section like
+   * Synthesizer.cpp:597 does.) */
+  double flow_source_cm3_s;
+  int32_t flow_source_section;
+  int32_t reserved; /* must be 0 */
 } afs_tds_options;
 
 typedef struct afs_ctx afs_ctx; /* opaque: one CUDA device, scratch buffers, one stream */
@@ -228,6 +238,16 @@ int afs_tl_formants(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes,
                     const afs_tube_frame *tubes, double sampling_rate_hz,
                     int spectrum_length, int max_formants, double *formant_hz,
                     double *bandwidth_hz, int32_t *num_formants, int32_t *flags);
+
+/*
+ * Replaces TlModel::getMostConstrictedSection (TlModel.cpp:204-217) and TlModel::getMeanFlow(lungPressure_dPa)
+ * (TlModel.cpp:226-246) for a batch of tubes: the narrowest pharynx / mouth section (tube section index 25..64;
+ * of equally narrow sections the last one) and sqrt(2 P / (rho (1/A_g^2 + 1/A_c^2))) with A_g the lower glottis
+ * area of the frame and A_c the area of that section, both clamped to 0.001 cm^2.  Either output may be null.
+ * (The reference's getMeanFlow also stores the pressure in the model; here it is afs_tl_options.lung_pressure_dPa.)
+ */
+int afs_tl_mean_flow(afs_ctx *ctx, int n_tubes, const afs_tube_frame *tubes, double lung_pressure_dPa,
+                     double *mean_flow_cm3_s, int32_t *most_constricted_section);
 
 /*
  * Replaces TlModel::getImpulseResponse (TlModel.cpp:90-111) for a batch of tubes: the flow-source transfer
@@ -370,6 +390,31 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts,
                               int sr_factor, const uint32_t *d_seeds,
                               double *d_audio, double *d_flow,
                               uint32_t *d_status, void *stream);
+
+/*
+ * Batched taps into the running simulation: TdsModel::getSectionPressure(section) (TdsModel.cpp:1725-1734) and
+ * TdsModel::getSectionFlow(section, inflow, outflow) (TdsModel.cpp:1715-1719), i.e. the pressure in the centre of
+ * a tube section and the volume velocities into / out of it, as a caller of the reference reads them after every
+ * proceedTimeStep.  Up to AFS_MAX_TDS_PROBES sections (tube section indices 0..92) per call; outputs
+ * [n_tracts][n_probes][n_steps] with n_steps = n_out * sr_factor simulation steps; each of the three may be null.
+ */
+#define AFS_MAX_TDS_PROBES 8
+typedef struct afs_tds_probes {
+  int32_t n_probes;
+  int32_t section[AFS_MAX_TDS_PROBES];
+  double *pressure_dPa;
+  double *inflow_cm3_s;
+  double *outflow_cm3_s;
+} afs_tds_probes;
+/* afs_tds_synthesize / afs_tds_synthesize_device with probes (host resp. device output pointers). */
+int afs_tds_synthesize_probed(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int n_frames,
+                              const int32_t *frame_len, const afs_tube_frame *tubes, const double *glottis,
+                              double fs_tds_hz, int sr_factor, const uint32_t *seeds, double *audio, double *flow,
+                              uint32_t *status, const afs_tds_probes *probes);
+int afs_tds_synthesize_probed_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int n_frames,
+                                     const int32_t *frame_len, const afs_tube_frame *d_tubes, const double *d_glottis,
+                                     double fs_tds_hz, int sr_factor, const uint32_t *d_seeds, double *d_audio,
+                                     double *d_flow, uint32_t *d_status, const afs_tds_probes *d_probes, void *stream);
 
 /* Diagnostics: the next afs_tds_synthesize* calls copy the recurrent state of
  * tract 0 right after simulation step `step` (1-based; 0 disables) into

@@ -32,6 +32,12 @@ int orc_tds_synthesize(const afs_tds_options *opts, int n_tracts, int n_frames,
                        const uint32_t *seeds, double *audio, double *flow,
                        double *state473, int dump_step);
 
+int orc_tds_synthesize_probed(const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
+                              const afs_tube_frame *tubes, const double *glottis, double fs_tds_hz, int sr_factor,
+                              const uint32_t *seeds, double *audio, int n_probes, const int32_t *sections,
+                              double *pressure, double *inflow, double *outflow);
+int orc_tl_mean_flow(int n, const afs_tube_frame *frames, double lung_pressure_dPa, double *flow, int32_t *section);
+
 void orc_area_function_to_frame(const double params[16], afs_tube_frame *frame);
 
 #ifdef __cplusplus

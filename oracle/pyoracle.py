@@ -46,7 +46,8 @@ class TdsOptions(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "turbulence_losses", "soft_walls", "generate_noise_sources", "radiation_from_skin",
         "piriform_fossa", "inner_length_corrections", "transvelar_coupling", "glottis_loss_option")] + [
-        ("flow_separation_area_ratio", C.c_double), ("glottis_static", C.c_double * 16)]
+        ("flow_separation_area_ratio", C.c_double), ("glottis_static", C.c_double * 16),
+        ("flow_source_cm3_s", C.c_double), ("flow_source_section", C.c_int32), ("reserved", C.c_int32)]
 
 
 GLOTTIS_STATIC_DEFAULT = (1.3, 0.24, 0.06, 0.12, 0.03, 0.1, 0.6, 80000.0, 8000.0, 240000.0, 24000.0,
@@ -63,6 +64,7 @@ def tds_options_default(noise=False):
     o = TdsOptions(1, 1, 1 if noise else 0, 1, 0, 1, 0, 0, 1.0)
     for i, v in enumerate(GLOTTIS_STATIC_DEFAULT):
         o.glottis_static[i] = v
+    o.flow_source_cm3_s, o.flow_source_section = 0.0, -1  # TdsModel.cpp:84
     return o
 
 
@@ -193,6 +195,26 @@ class Ref:
                                     _ptr(s), _ptr(audio), _ptr(flow), threads)
         return audio, flow
 
+    def tds_probed(self, frames, glottis, frame_len, sections, opts=None, seed=1):
+        """One utterance (frames [F]) with TdsModel::getSectionPressure / getSectionFlow read after every step:
+        (audio, pressure, inflow, outflow), the last three [n_probes, steps]."""
+        opts = opts or tds_options_default()
+        F = frames.shape[0]
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.int32)
+        n_out = int(frame_len.sum()); steps = n_out * self.sr_factor
+        sec = np.ascontiguousarray(sections, dtype=np.int32)
+        audio = np.zeros(n_out); pr = np.zeros((len(sec), steps)); fi = np.zeros_like(pr); fo = np.zeros_like(pr)
+        g = np.ascontiguousarray(glottis, dtype=np.float64)
+        self.lib.ref_tds_probed(C.byref(opts), F, _ptr(frame_len), _ptr(np.ascontiguousarray(frames)), _ptr(g), C.c_uint32(seed),
+                                _ptr(audio), len(sec), _ptr(sec), _ptr(pr), _ptr(fi), _ptr(fo))
+        return audio, pr, fi, fo
+
+    def tl_mean_flow(self, frames, lung_pressure_dPa):
+        n = len(frames)
+        flow = np.zeros(n); sec = np.zeros(n, dtype=np.int32)
+        self.lib.ref_tl_mean_flow(n, _ptr(np.ascontiguousarray(frames)), C.c_double(lung_pressure_dPa), _ptr(flow), _ptr(sec))
+        return flow, sec
+
     def tds_state_after(self, frames, glottis, frame_len, step, opts=None):
         opts = opts or tds_options_default()
         F = frames.shape[0]
@@ -285,6 +307,29 @@ class Oracle:
         if dump_step:
             return audio, flow, st
         return audio, flow
+
+    def tds_synthesize_probed(self, frames, glottis, frame_len, sections, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None):
+        """(audio [B, n_out], pressure, inflow, outflow [B, n_probes, steps])."""
+        opts = opts or tds_options_default()
+        frames = np.ascontiguousarray(frames)
+        B, F = frames.shape
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.int32)
+        n_out = int(frame_len.sum()); steps = n_out * sr_factor
+        sec = np.ascontiguousarray(sections, dtype=np.int32)
+        audio = np.zeros((B, n_out)); pr = np.zeros((B, len(sec), steps)); fi = np.zeros_like(pr); fo = np.zeros_like(pr)
+        g = np.ascontiguousarray(glottis, dtype=np.float64)
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
+        rc = self.lib.orc_tds_synthesize_probed(C.byref(opts), B, F, _ptr(frame_len), _ptr(frames), _ptr(g), C.c_double(fs_tds_hz),
+                                                sr_factor, _ptr(sd), _ptr(audio), len(sec), _ptr(sec), _ptr(pr), _ptr(fi), _ptr(fo))
+        assert rc == 0, rc
+        return audio, pr, fi, fo
+
+    def tl_mean_flow(self, frames, lung_pressure_dPa):
+        n = len(frames)
+        flow = np.zeros(n); sec = np.zeros(n, dtype=np.int32)
+        rc = self.lib.orc_tl_mean_flow(n, _ptr(np.ascontiguousarray(frames)), C.c_double(lung_pressure_dPa), _ptr(flow), _ptr(sec))
+        assert rc == 0, rc
+        return flow, sec
 
     def chebyshev_lowpass(self, cutoff_ratio, poles):
         a = np.zeros(poles + 1); b = np.zeros(poles + 1)

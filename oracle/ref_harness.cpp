@@ -374,8 +374,10 @@ int ref_synthesize_vowel_lf(const afs_tl_options *opts, const afs_tube_frame *tu
 // the glottis object (FREQUENCY and PRESSURE are overwritten).  audio [numSamples]; sample 0 is the priming call
 // (synthesizeSignalTds returns without writing, Synthesizer.cpp:522-532) and reads 0 here.
 // ---------------------------------------------------------------------------------------------------
+struct RefProbes { int n; const int32_t *section; double *pressure, *inflow, *outflow; };  // per step, [n][steps]
 static void tds_one(const afs_tds_options *o, int n_frames, const int32_t *frame_len, const afs_tube_frame *frames,
-                    const double *glottis, unsigned seed, double *audio, double *flow, double *state_dump, int dump_step);
+                    const double *glottis, unsigned seed, double *audio, double *flow, double *state_dump, int dump_step,
+                    const RefProbes *probes = nullptr);
 
 int ref_target_sequence_length(const double *stationary_s, const double *transition_s) {
   double totalTime_s = stationary_s[0] + transition_s[0] + stationary_s[1] + transition_s[1] + stationary_s[2] + transition_s[2] + stationary_s[3];
@@ -486,7 +488,9 @@ void ref_tl_formants(const afs_tl_options *opts, int n_tubes, const afs_tube_fra
 // (libc rand()).
 static void tds_one(const afs_tds_options *o, int n_frames, const int32_t *frame_len,
                     const afs_tube_frame *frames, const double *glottis, unsigned seed,
-                    double *audio, double *flow, double *state_dump, int dump_step) {
+                    double *audio, double *flow, double *state_dump, int dump_step, const RefProbes *probes) {
+  long total_steps = 0;
+  for (int k = 0; k + 1 < n_frames; k++) total_steps += (long)frame_len[k] * TDS_SR_FACTOR;
   TdsModel *tds = new TdsModel();
   TriangularGlottis *gl = new TriangularGlottis();
   tds->options.turbulenceLosses = o->turbulence_losses;
@@ -529,7 +533,7 @@ static void tds_one(const afs_tds_options *o, int n_frames, const int32_t *frame
       tube.setGlottisGeometry(length_cm, area_cm2);
       tube.setAspirationStrength(gl->getAspirationStrength_dB());
       tds->setTube(&tube, tds->getSampleIndex() != 0);
-      tds->setFlowSource(0.0, -1);
+      tds->setFlowSource(o->flow_source_cm3_s, o->flow_source_section);
       tds->setPressureSource(gl->controlParam[Glottis::PRESSURE].x, Tube::FIRST_TRACHEA_SECTION);
       pressure_dPa[0] = tds->getSectionPressure(Tube::LAST_TRACHEA_SECTION);
       pressure_dPa[1] = tds->getSectionPressure(Tube::LOWER_GLOTTIS_SECTION);
@@ -539,6 +543,15 @@ static void tds_one(const afs_tds_options *o, int n_frames, const int32_t *frame
       double u = tds->proceedTimeStep();
       int pos = tds->getSampleIndex();
       if (flow) flow[flowPos] = u;
+      if (probes) {  // what a caller of the reference reads after every proceedTimeStep (TdsModel.h:279-280)
+        for (int q = 0; q < probes->n; q++) {
+          double in = 0.0, out = 0.0;
+          tds->getSectionFlow(probes->section[q], in, out);
+          if (probes->pressure) probes->pressure[q * total_steps + flowPos] = tds->getSectionPressure(probes->section[q]);
+          if (probes->inflow) probes->inflow[q * total_steps + flowPos] = in;
+          if (probes->outflow) probes->outflow[q * total_steps + flowPos] = out;
+        }
+      }
       flowPos++;
       if (state_dump && pos == dump_step) {
         // [0..92] pressure, [93..185] pressureRate, [186..278] wallCurrent,
@@ -587,6 +600,25 @@ void ref_tds_synthesize(const afs_tds_options *opts, int n_tracts, int n_frames,
   for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
   work(0);
   for (auto &t : th) t.join();
+}
+
+// Single utterance with taps: pressure / inflow / outflow [n_probes][steps] of the given tube sections.
+void ref_tds_probed(const afs_tds_options *opts, int n_frames, const int32_t *frame_len, const afs_tube_frame *tubes,
+                    const double *glottis, uint32_t seed, double *audio, int n_probes, const int32_t *sections,
+                    double *pressure, double *inflow, double *outflow) {
+  RefProbes pr{n_probes, sections, pressure, inflow, outflow};
+  tds_one(opts, n_frames, frame_len, tubes, glottis, seed, audio, nullptr, nullptr, 0, &pr);
+}
+
+// TlModel::getMostConstrictedSection / getMeanFlow (TlModel.cpp:204-246) for a batch of frames.
+void ref_tl_mean_flow(int n, const afs_tube_frame *frames, double lung_pressure_dPa, double *flow, int32_t *section) {
+  TlModel *tl = new TlModel();
+  for (int i = 0; i < n; i++) {
+    frame_to_tube(&frames[i], &tl->tube);
+    if (section) section[i] = tl->getMostConstrictedSection();
+    if (flow) flow[i] = tl->getMeanFlow(lung_pressure_dPa);
+  }
+  delete tl;
 }
 
 // Single utterance with a state dump after simulation step `dump_step` (1-based).
