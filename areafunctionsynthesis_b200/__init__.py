@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     AfsError,
     Context,
     TdsOptions,
+    TdsProbes,
     TlOptions,
     area_function_to_frames,
     audio_to_int16,
@@ -26,4 +27,4 @@ from .api import (  # noqa: F401
     write_wav_int16,
 )
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

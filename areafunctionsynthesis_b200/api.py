@@ -47,7 +47,17 @@ class TdsOptions(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "turbulence_losses", "soft_walls", "generate_noise_sources", "radiation_from_skin",
         "piriform_fossa", "inner_length_corrections", "transvelar_coupling", "glottis_loss_option")] + [
-        ("flow_separation_area_ratio", C.c_double), ("glottis_static", C.c_double * 16)]
+        ("flow_separation_area_ratio", C.c_double), ("glottis_static", C.c_double * 16),
+        ("flow_source_cm3_s", C.c_double), ("flow_source_section", C.c_int32), ("reserved", C.c_int32)]
+
+
+MAX_TDS_PROBES = 8
+
+
+class TdsProbes(C.Structure):
+    """afs_tds_probes: taps into the simulation (TdsModel::getSectionPressure / getSectionFlow)."""
+    _fields_ = [("n_probes", C.c_int32), ("section", C.c_int32 * MAX_TDS_PROBES), ("pressure_dPa", C.c_void_p),
+                ("inflow_cm3_s", C.c_void_p), ("outflow_cm3_s", C.c_void_p)]
 
 
 _lib = None
@@ -89,6 +99,9 @@ def load_library():
     lib.afs_tl_impulse_response_device.argtypes = [vp, vp, i32, vp, dbl, i32, vp, vp]
     lib.afs_tds_synthesize.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp]
     lib.afs_tds_synthesize_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
+    lib.afs_tds_synthesize_probed.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
+    lib.afs_tds_synthesize_probed_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp, vp]
+    lib.afs_tl_mean_flow.argtypes = [vp, i32, vp, dbl, vp, vp]
     lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
     lib.afs_probe_fp64_tflops.argtypes = [vp, vp]
     lib.afs_chebyshev_lowpass.argtypes = [dbl, i32, vp, vp]
@@ -315,6 +328,14 @@ class Context:
                                                           int(length_exponent), _ptr(out)), self.h)
         return out
 
+    def tl_mean_flow(self, frames, lung_pressure_dPa):
+        """TlModel::getMeanFlow / getMostConstrictedSection for a batch: (flow [n], section [n])."""
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        n = len(frames)
+        flow = np.zeros(n); sec = np.zeros(n, dtype=np.int32)
+        _check(self.lib, self.lib.afs_tl_mean_flow(self.h, n, _ptr(frames), float(lung_pressure_dPa), _ptr(flow), _ptr(sec)), self.h)
+        return flow, sec
+
     def tl_formants(self, frames, sampling_rate_hz=22050.0, spectrum_length=2048, max_formants=8, opts=None):
         opts = opts or tl_options_default()
         frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
@@ -363,6 +384,30 @@ class Context:
                                                      _ptr(glottis), float(fs_tds_hz), int(sr_factor), _ptr(s),
                                                      _ptr(audio), _ptr(flow), _ptr(status)), self.h)
         return audio, flow, status
+
+    def tds_synthesize_probed(self, frames, glottis, frame_len, sections, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None,
+                              want=("pressure", "inflow", "outflow")):
+        """afs_tds_synthesize_probed: returns (audio, status, dict(pressure / inflow / outflow -> [B, n_probes, steps]))."""
+        opts = opts or tds_options_default()
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        B, F = frames.shape
+        glottis = np.ascontiguousarray(glottis, dtype=np.float64).reshape(B, F, NUM_GLOTTIS_CONTROL)
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.int32)
+        n_out = int(frame_len.sum())
+        audio = np.empty((B, n_out)); status = np.zeros(B, dtype=np.uint32)
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
+        pr = TdsProbes()
+        pr.n_probes = len(sections)
+        for q, sc in enumerate(sections[:MAX_TDS_PROBES]):
+            pr.section[q] = int(sc)
+        taps = {k: np.zeros((B, len(sections), n_out * sr_factor)) for k in want}
+        pr.pressure_dPa = taps["pressure"].ctypes.data if "pressure" in taps else None
+        pr.inflow_cm3_s = taps["inflow"].ctypes.data if "inflow" in taps else None
+        pr.outflow_cm3_s = taps["outflow"].ctypes.data if "outflow" in taps else None
+        _check(self.lib, self.lib.afs_tds_synthesize_probed(self.h, C.byref(opts), B, F, _ptr(frame_len), _ptr(frames), _ptr(glottis),
+                                                            float(fs_tds_hz), int(sr_factor), _ptr(s), _ptr(audio), None,
+                                                            _ptr(status), C.byref(pr)), self.h)
+        return audio, status, taps
 
     def tds_synthesize_device(self, d_frames, d_glottis, n_tracts, n_frames, frame_len, d_audio, stream,
                               fs_tds_hz=44100.0, sr_factor=2, opts=None, d_seeds=None, d_flow=None, d_status=None):

@@ -147,6 +147,7 @@ void afs_tds_options_default(afs_tds_options *o) {
   o->piriform_fossa = 0; o->inner_length_corrections = 1; o->transvelar_coupling = 0;
   o->glottis_loss_option = AFS_STANDARD_ENTRANCE_LOSS; o->flow_separation_area_ratio = 1.0;
   for (int i = 0; i < AFS_NUM_GLOTTIS_STATIC; i++) o->glottis_static[i] = gs[i];
+  o->flow_source_cm3_s = 0.0; o->flow_source_section = -1; o->reserved = 0;  // TdsModel.cpp:84
 }
 
 void afs_tube_frame_default(afs_tube_frame *f) {
@@ -322,6 +323,27 @@ int afs_tl_formants(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes, const
   CU(cudaMemcpyAsync(bandwidth_hz, d_b, fb, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(num_formants, d_n, (size_t)n_tubes * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(flags, d_fl, (size_t)n_tubes * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return AFS_OK;
+}
+
+int afs_tl_mean_flow(afs_ctx *ctx, int n_tubes, const afs_tube_frame *tubes, double lung_pressure_dPa,
+                     double *mean_flow_cm3_s, int32_t *most_constricted_section) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (n_tubes < 0) return AFS_ERR_BAD_ARGUMENT;
+  if (n_tubes == 0) return AFS_OK;
+  if (!tubes) return AFS_ERR_BAD_ARGUMENT;
+  void *d_tubes, *d_f, *d_s;
+  if ((rc = scratch(ctx, 0, (size_t)n_tubes * sizeof(afs_tube_frame), &d_tubes))) return rc;
+  if ((rc = scratch(ctx, 3, (size_t)n_tubes * sizeof(double), &d_f))) return rc;
+  if ((rc = scratch(ctx, 5, (size_t)n_tubes * sizeof(int32_t), &d_s))) return rc;
+  CU(cudaMemcpyAsync(d_tubes, tubes, (size_t)n_tubes * sizeof(afs_tube_frame), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_tl_mean_flow(n_tubes, (const afs_tube_frame *)d_tubes, lung_pressure_dPa, (double *)d_f, (int32_t *)d_s, ctx->stream));
+  ctx->launches++;
+  if (mean_flow_cm3_s) CU(cudaMemcpyAsync(mean_flow_cm3_s, d_f, (size_t)n_tubes * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (most_constricted_section)
+    CU(cudaMemcpyAsync(most_constricted_section, d_s, (size_t)n_tubes * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return AFS_OK;
 }
@@ -710,6 +732,14 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
                               const int32_t *frame_len, const afs_tube_frame *d_tubes, const double *d_glottis,
                               double fs_tds_hz, int sr_factor, const uint32_t *d_seeds, double *d_audio,
                               double *d_flow, uint32_t *d_status, void *stream) {
+  return afs_tds_synthesize_probed_device(ctx, opts, n_tracts, n_frames, frame_len, d_tubes, d_glottis, fs_tds_hz, sr_factor,
+                                          d_seeds, d_audio, d_flow, d_status, nullptr, stream);
+}
+
+int afs_tds_synthesize_probed_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int n_frames,
+                                     const int32_t *frame_len, const afs_tube_frame *d_tubes, const double *d_glottis,
+                                     double fs_tds_hz, int sr_factor, const uint32_t *d_seeds, double *d_audio,
+                                     double *d_flow, uint32_t *d_status, const afs_tds_probes *d_probes, void *stream) {
   int rc = bind(ctx);
   if (rc) return rc;
   if (!opts || n_tracts < 0 || n_frames < 2 || !frame_len || sr_factor < 1 || !(fs_tds_hz > 0))
@@ -717,6 +747,11 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   if (opts->glottis_loss_option < AFS_STANDARD_ENTRANCE_LOSS || opts->glottis_loss_option > AFS_VARIABLE_ENTRANCE_LOSS)
     return AFS_ERR_BAD_ARGUMENT;
   for (int k = 0; k + 1 < n_frames; k++) if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT;
+  if (d_probes) {
+    if (d_probes->n_probes < 0 || d_probes->n_probes > AFS_MAX_TDS_PROBES) return AFS_ERR_BAD_ARGUMENT;
+    for (int q = 0; q < d_probes->n_probes; q++)
+      if (d_probes->section[q] < 0 || d_probes->section[q] >= AFS_NUM_SECTIONS) return AFS_ERR_BAD_ARGUMENT;
+  }
   if (n_tracts == 0) return AFS_OK;
   if (!d_tubes || !d_glottis || !d_audio) return AFS_ERR_BAD_ARGUMENT;
 
@@ -756,7 +791,7 @@ int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_t
     const int t0 = c0 * lpc;
     const int nw = (c0 + wave_ctas >= ctas) ? n_tracts - t0 : wave_ctas * lpc;
     CU(launch_tds(L, t0, nw, (const int32_t *)d_bounds, d_tubes, d_glottis, d_seeds, d_audio, d_flow, d_status,
-                  c0 == 0 ? (double *)d_dump : nullptr, ctx->dump_step, d_nzc, (cudaStream_t)stream));
+                  c0 == 0 ? (double *)d_dump : nullptr, ctx->dump_step, d_nzc, d_probes, (cudaStream_t)stream));
     ctx->launches += per_cta ? 2 : 1;
   }
   if (d_dump) {
@@ -777,6 +812,14 @@ int afs_tds_synthesize(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, 
                        const int32_t *frame_len, const afs_tube_frame *tubes, const double *glottis,
                        double fs_tds_hz, int sr_factor, const uint32_t *seeds, double *audio, double *flow,
                        uint32_t *status) {
+  return afs_tds_synthesize_probed(ctx, opts, n_tracts, n_frames, frame_len, tubes, glottis, fs_tds_hz, sr_factor, seeds,
+                                   audio, flow, status, nullptr);
+}
+
+int afs_tds_synthesize_probed(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int n_frames,
+                              const int32_t *frame_len, const afs_tube_frame *tubes, const double *glottis,
+                              double fs_tds_hz, int sr_factor, const uint32_t *seeds, double *audio, double *flow,
+                              uint32_t *status, const afs_tds_probes *probes) {
   int rc = bind(ctx);
   if (rc) return rc;
   if (n_tracts < 0 || n_frames < 2 || !frame_len || sr_factor < 1) return AFS_ERR_BAD_ARGUMENT;
@@ -800,13 +843,36 @@ int afs_tds_synthesize(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, 
   }
   CU(cudaMemcpyAsync(d_tubes, tubes, tb, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_gl, glottis, gb, cudaMemcpyHostToDevice, ctx->stream));
-  rc = afs_tds_synthesize_device(ctx, opts, n_tracts, n_frames, frame_len, (const afs_tube_frame *)d_tubes,
-                                 (const double *)d_gl, fs_tds_hz, sr_factor, (const uint32_t *)d_seeds,
-                                 (double *)d_audio, (double *)d_flow, (uint32_t *)d_status, ctx->stream);
+  // taps: device copies of whichever of the three outputs the caller asked for, back to back in scratch slot 9
+  afs_tds_probes dp;
+  const afs_tds_probes *use = nullptr;
+  size_t pb = 0;
+  if (probes && probes->n_probes > 0) {
+    if (probes->n_probes > AFS_MAX_TDS_PROBES) return AFS_ERR_BAD_ARGUMENT;
+    dp = *probes;
+    pb = (size_t)n_tracts * (size_t)probes->n_probes * n_out * (size_t)sr_factor * sizeof(double);
+    const int n_arr = (probes->pressure_dPa ? 1 : 0) + (probes->inflow_cm3_s ? 1 : 0) + (probes->outflow_cm3_s ? 1 : 0);
+    void *d_p = nullptr;
+    if (n_arr && (rc = scratch(ctx, 9, pb * n_arr, &d_p))) return rc;
+    unsigned char *at = (unsigned char *)d_p;
+    dp.pressure_dPa = dp.inflow_cm3_s = dp.outflow_cm3_s = nullptr;
+    if (probes->pressure_dPa) { dp.pressure_dPa = (double *)at; at += pb; }
+    if (probes->inflow_cm3_s) { dp.inflow_cm3_s = (double *)at; at += pb; }
+    if (probes->outflow_cm3_s) { dp.outflow_cm3_s = (double *)at; at += pb; }
+    use = &dp;
+  }
+  rc = afs_tds_synthesize_probed_device(ctx, opts, n_tracts, n_frames, frame_len, (const afs_tube_frame *)d_tubes,
+                                        (const double *)d_gl, fs_tds_hz, sr_factor, (const uint32_t *)d_seeds,
+                                        (double *)d_audio, (double *)d_flow, (uint32_t *)d_status, use, ctx->stream);
   if (rc) return rc;
   CU(cudaMemcpyAsync(audio, d_audio, ab, cudaMemcpyDeviceToHost, ctx->stream));
   if (flow) CU(cudaMemcpyAsync(flow, d_flow, fb, cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CU(cudaMemcpyAsync(status, d_status, (size_t)n_tracts * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (use) {
+    if (dp.pressure_dPa) CU(cudaMemcpyAsync(probes->pressure_dPa, dp.pressure_dPa, pb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dp.inflow_cm3_s) CU(cudaMemcpyAsync(probes->inflow_cm3_s, dp.inflow_cm3_s, pb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dp.outflow_cm3_s) CU(cudaMemcpyAsync(probes->outflow_cm3_s, dp.outflow_cm3_s, pb, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CU(cudaStreamSynchronize(ctx->stream));
   return AFS_OK;
 }

@@ -27,6 +27,9 @@ cudaError_t launch_formant_pick(const FormantParams &p, const afs_tube_frame *d_
                                 const double *d_im, double *d_freq, double *d_bw, int32_t *d_num, int32_t *d_flags,
                                 cudaStream_t stream);
 
+cudaError_t launch_tl_mean_flow(int n, const afs_tube_frame *d_tubes, double lung_pressure_dPa, double *d_flow,
+                                int32_t *d_section, cudaStream_t stream);
+
 // impulse response: tables [N-1] twiddles (re, im), [num_freq] radiation characteristic (re, im), [N] window, all
 // computed on the host with libm exactly as the reference does (afs_host.cpp: impulse_response_tables)
 struct IrTables {
@@ -57,7 +60,8 @@ int tds_prepare_launch(const afs_tds_options *opts, int n_tracts, int n_frames, 
                        double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L);
 cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
-                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, cudaStream_t stream);
+                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const afs_tds_probes *d_probes,
+                       cudaStream_t stream);
 size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L);  // 0 without noise sources
 int tds_lanes_per_cta(const TdsLaunch &L);
 size_t tds_smem_bytes();

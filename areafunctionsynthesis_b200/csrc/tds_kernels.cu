@@ -92,6 +92,9 @@ struct TdsParams {
   double ith, fs;                   // theta/theta1, fs
   double fsar, k_ent;
   int transvelar, var_loss;         // transvelarCoupling, glottisLossOption == VARIABLE_ENTRANCE_LOSS (TdsModel.h:75-87)
+  int fsrc_sec;                     // TdsModel::setFlowSource (TdsModel.cpp:629-633): section of the flow source, -1 = none
+  double fsrc_amp;                  // ... and its strength in cm^3/s
+  int n_probes, probe_sec[AFS_MAX_TDS_PROBES];  // taps (getSectionPressure / getSectionFlow, TdsModel.cpp:1715-1734)
   double tg_a[5], tg_b[5];          // 50 Hz Chebyshev low-pass of the transglottal pressure (TdsModel.cpp:474)
   double k_sondhi, k_bern;          // 8 rho/(3 pi^2) resp. rho/2, or 0 when the option is off
   double kalpha[3], c1[3], c2[3], c3[3];  // wall constants: 0 standard, 1 trachea, 2 sinus
@@ -360,7 +363,21 @@ struct StepCtx {
   bool upd, rows;
   double ratio, ratio1;
   bool dumping;
+  // taps (OPT kernels only): where this lane's values of step n-1 go, null when the lane is idle or nothing is tapped
+  double *tap_p, *tap_in, *tap_out;
+  size_t tap_stride;  // distance between two probes of one tract (= total_steps)
 };
+
+// getSectionPressure / getSectionFlow of section `sec` after a step (TdsModel.cpp:1715-1734): pressure in the centre of
+// the section, volume velocity into and out of it.
+__device__ __forceinline__ void tap_section(const TdsParams &P, const StepCtx &X, int sec, double p, double in, double out) {
+  for (int q = 0; q < P.n_probes; q++) {
+    if (P.probe_sec[q] != sec) continue;
+    if (X.tap_p) X.tap_p[q * X.tap_stride] = p;
+    if (X.tap_in) X.tap_in[q * X.tap_stride] = in;
+    if (X.tap_out) X.tap_out[q * X.tap_stride] = out;
+  }
+}
 
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 // Named barriers of the solve phase.  Warp X1 (glottis model, output filters) only has to be back for the next pass A:
@@ -424,6 +441,7 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       const double beta_old = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
       double D_old = fma(-E_old, beta_old, fma(P.dtth1, pr_, p_));
       if (OPT && k == 2 && P.transvelar && w == W_NV) D_old = fma(E_old, S.tvflow[lane], D_old);  // source term of section 67
+      if (OPT && P.fsrc_sec == sec) D_old = fma(E_old, P.fsrc_amp, D_old);                         // TdsModel.cpp:999-1002
       // current: u' = (u_new - u_old)/(dt theta) - (theta1/theta) u'_old = u_new/(dt theta) - c
       const double ur = fma(u, P.idt, -c_);
       c_ = fma(ur, P.th, u * P.idt);
@@ -437,6 +455,7 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
       S.wall[sec][0][lane] = wc; S.wall[sec][1][lane] = wcr; S.wall[sec][2][lane] = wcr2;
       if (k < 3 && sec <= PHAR0) S.p4[sec - TRACHEA_LAST][lane] = p_new;  // sections 23, 24, 25
+      if (OPT && P.n_probes > 0) tap_section(P, X, sec, p_new, u, out);
     }
     if (rows) {
       // Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350); the index is clamped for the other kinds
@@ -460,7 +479,8 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       const double alpha = fmax(circ * length, kMinArea) * ka;  // TdsModel.cpp:805-832
       const double E = P.dtth * fast_rcp1(C + alpha);
       const double beta = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
-      const double D = fma(-E, beta, fma(P.dtth1, pr_, p_));  // TdsModel.cpp:988-1008, no flow sources
+      double D = fma(-E, beta, fma(P.dtth1, pr_, p_));  // TdsModel.cpp:988-1008
+      if (OPT && P.fsrc_sec == sec) D = fma(E, P.fsrc_amp, D);
       S.Ed[rec][lane] = E; S.Al[rec][lane] = alpha;
       if (k == 0) {
         st.L0 = L; st.R0 = R; st.I0 = invr; st.D0 = D;
@@ -675,6 +695,7 @@ __device__ __noinline__ void swarp_build(const TdsParams &P, TdsSmem &S, const i
 }
 
 // One static section: update with the last solution (TdsModel.cpp:2046-2098), then D of the new step (:988-1008).
+template <bool OPT>
 __device__ __forceinline__ void static_section(const TdsParams &P, TdsSmem &S, const int lane, const StepCtx &X, int sec,
                                                double &p, double &pr, double &c, double u, double out, double &Dnew) {
   const SRec &r = S.srec[sec];
@@ -683,10 +704,12 @@ __device__ __forceinline__ void static_section(const TdsParams &P, TdsSmem &S, c
   const double E = r.E;
   if (X.upd) {
     const double beta_old = wall_beta3(wk, wc, wcr, wcr2);
-    const double D_old = fma(-E, beta_old, fma(P.dtth1, pr, p));
+    double D_old = fma(-E, beta_old, fma(P.dtth1, pr, p));
+    if (OPT && P.fsrc_sec == sec) D_old = fma(E, P.fsrc_amp, D_old);  // TdsModel.cpp:999-1002
     const double ur = fma(u, P.idt, -c);
     c = fma(ur, P.th, u * P.idt);
     const double p_new = fma(E, u - out, D_old);
+    if (OPT && P.n_probes > 0) tap_section(P, X, sec, p_new, u, out);
     const double pr_new = (p_new - p) * P.idt - pr * P.th;
     const double wc_new = fma(pr_new, r.alpha, beta_old);
     const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
@@ -696,8 +719,10 @@ __device__ __forceinline__ void static_section(const TdsParams &P, TdsSmem &S, c
     if (sec == TRACHEA_LAST) S.p4[0][lane] = p_new;
   }
   Dnew = fma(-E, wall_beta3(wk, wc, wcr, wcr2), fma(P.dtth1, pr, p));
+  if (OPT && P.fsrc_sec == sec) Dnew = fma(E, P.fsrc_amp, Dnew);
 }
 
+template <bool OPT>
 __device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
                                              const SCfg &c, SRegs &st, const StepCtx &X) {
   double outLast = 0.0;
@@ -711,11 +736,11 @@ __device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, con
     double out = (k < KS - 1) ? st.x[k + 1] : outLast;
     if (k == j0) out += st.lx[0];
     if (k == j0 + 1) out += st.lx[1];
-    static_section(P, S, lane, X, c.base + k, st.p[k], st.pr[k], st.c[k], st.x[k], out, dn[k]);
+    static_section<OPT>(P, S, lane, X, c.base + k, st.p[k], st.pr[k], st.c[k], st.x[k], out, dn[k]);
   }
   if (c.leaves) {
 #pragma unroll
-    for (int j = 0; j < 2; j++) static_section(P, S, lane, X, c.leaf0 + j, st.lp[j], st.lpr[j], st.lc[j], st.lx[j], 0.0, dl[j]);
+    for (int j = 0; j < 2; j++) static_section<OPT>(P, S, lane, X, c.leaf0 + j, st.lp[j], st.lpr[j], st.lc[j], st.lx[j], 0.0, dl[j]);
   }
   if (X.rows) {
     // rows of the static currents: constant pivots, only the right-hand side is assembled (the rows of the slots
@@ -1624,6 +1649,8 @@ struct KArgs {
   // noise sources: constriction records of every (CTA, step) from tds_noise_scan_kernel, [cta][step][4][32]
   uint32_t *nzc_i;
   double *nzc_f;
+  // taps: [tract][probe][step], each nullable
+  double *tap_p, *tap_in, *tap_out;
 };
 
 #ifdef AFS_TDS_TIMING
@@ -1747,6 +1774,13 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     X.ratio = (double)(n - i0) * inv_len;  // (1 ulp from the reference's i / N; irrelevant at the 1e-6 bar)
     X.ratio1 = 1.0 - X.ratio;
     X.dumping = A.dump != nullptr && P.dump_step == n && blockIdx.x == 0;
+    X.tap_p = X.tap_in = X.tap_out = nullptr; X.tap_stride = (size_t)T;
+    if (OPT && P.n_probes > 0 && active && n > 0) {  // values of step n-1 (0-based), written by the update of pass A
+      const size_t at = (size_t)tract * P.n_probes * (size_t)T + (size_t)(n - 1);
+      if (A.tap_p) X.tap_p = A.tap_p + at;
+      if (A.tap_in) X.tap_in = A.tap_in + at;
+      if (A.tap_out) X.tap_out = A.tap_out + at;
+    }
     AFS_TICK(0);
     // ============ pass A: update (step n-1), elements + rows (step n) ============
     // (state dump requested for this step: update and rows in two separate passes, the dump in between)
@@ -1755,7 +1789,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       StepCtx Y = X;
       if (X.dumping) { Y.upd = X.upd && half == 0; Y.rows = X.rows && half == 1; }
       if (ROLE == 0) dwarp_pass_a<false, OPT>(P, S, lane, warp, wcfg, dst, Y);
-      if (ROLE == 1) swarp_pass_a(P, S, lane, warp, wcfg, scfg, sst, Y);
+      if (ROLE == 1) swarp_pass_a<OPT>(P, S, lane, warp, wcfg, scfg, sst, Y);
       if (ROLE == 3 && Y.upd) radiation_update(P, lane, rr, nr, Y, A.dump);
       if (X.dumping && half == 0) {
         if (ROLE == 0) dwarp_dump(P, S, lane, warp, dst, A.dump);
@@ -2032,6 +2066,10 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   P.k_ent = o->glottis_loss_option == AFS_ENTRANCE_LOSS_VAN_DEN_BERG ? 1.375 : 1.0;
   P.transvelar = o->transvelar_coupling ? 1 : 0;
   P.var_loss = o->glottis_loss_option == AFS_VARIABLE_ENTRANCE_LOSS ? 1 : 0;
+  if (o->flow_source_section < -1 || o->flow_source_section >= NS || o->reserved != 0) return AFS_ERR_BAD_ARGUMENT;
+  P.fsrc_sec = o->flow_source_section;
+  P.fsrc_amp = o->flow_source_section >= 0 ? o->flow_source_cm3_s : 0.0;
+  P.n_probes = 0;
   chebyshev_lowpass(50.0 / fs_tds_hz, 4, P.tg_a, P.tg_b);
   P.k_sondhi = o->inner_length_corrections ? 8.0 * kRho / (3.0 * kPi * kPi) : 0.0;
   P.k_bern = o->turbulence_losses ? 0.5 * kRho : 0.0;
@@ -2090,13 +2128,23 @@ int tds_lanes_per_cta(const TdsLaunch &L) {
 // pre-pass records of all its CTAs would not fit `d_nzc`).
 cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
-                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, cudaStream_t stream) {
+                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const afs_tds_probes *probes,
+                       cudaStream_t stream) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
   P.n_tracts = n_wave;
+  if (probes && probes->n_probes > 0) {
+    if (probes->n_probes > AFS_MAX_TDS_PROBES) return cudaErrorInvalidValue;
+    P.n_probes = probes->n_probes;
+    for (int q = 0; q < P.n_probes; q++) {
+      if (probes->section[q] < 0 || probes->section[q] >= NS) return cudaErrorInvalidValue;
+      P.probe_sec[q] = probes->section[q];
+    }
+  }
   static_assert(sizeof(TdsSmem) <= 227 * 1024, "TdsSmem exceeds the 227 KB a CTA can have on sm_100a");
-  const bool opt = P.transvelar || P.var_loss;  // non-default options: separate instantiations, like the noise sources
+  // non-default options, a flow source, taps: separate instantiations, like the noise sources
+  const bool opt = P.transvelar || P.var_loss || P.fsrc_sec >= 0 || P.n_probes > 0;
   auto kernel = P.noise ? (opt ? tds_batch_kernel<true, true> : tds_batch_kernel<true, false>)
                         : (opt ? tds_batch_kernel<false, true> : tds_batch_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2112,7 +2160,13 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
           d_status ? d_status + tract0 : nullptr,
           d_dump,
           d_seeds ? d_seeds + tract0 : nullptr,
-          nullptr, nullptr};
+          nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (P.n_probes > 0) {
+    const size_t off = (size_t)tract0 * P.n_probes * (size_t)P.total_steps;
+    A.tap_p = probes->pressure_dPa ? probes->pressure_dPa + off : nullptr;
+    A.tap_in = probes->inflow_cm3_s ? probes->inflow_cm3_s + off : nullptr;
+    A.tap_out = probes->outflow_cm3_s ? probes->outflow_cm3_s + off : nullptr;
+  }
   if (P.noise) {
     if (!d_nzc) return cudaErrorInvalidValue;
     A.nzc_i = (uint32_t *)d_nzc;

@@ -25,13 +25,14 @@ def test_library_is_built_in_tree_and_exports_the_header():
     assert len(syms) >= 14
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/afs_b200.h but not exported"
-    assert lib.afs_version() == 100
+    assert lib.afs_version() == 200
 
 
 def test_struct_layouts_match_the_header():
     assert afs.FRAME_DTYPE.itemsize == 1184
     assert C.sizeof(afs.TlOptions) == 56
-    assert C.sizeof(afs.TdsOptions) == 8 * 4 + 8 + 16 * 8
+    assert C.sizeof(afs.TdsOptions) == 8 * 4 + 8 + 16 * 8 + 8 + 4 + 4
+    assert C.sizeof(afs.TdsProbes) == 4 + 8 * 4 + 4 + 3 * 8  # n_probes, sections, padding, three pointers
     o = afs.tl_options_default()
     assert (o.radiation, o.boundary_layer, o.soft_walls, o.lumped_elements, o.paranasal_sinuses,
             o.piriform_fossa, o.static_pressure_drops, o.lung_pressure_dPa) == (3, 1, 1, 1, 1, 0, 1, 0.0)
@@ -39,6 +40,7 @@ def test_struct_layouts_match_the_header():
     assert (t.turbulence_losses, t.soft_walls, t.generate_noise_sources, t.radiation_from_skin, t.piriform_fossa,
             t.inner_length_corrections) == (1, 1, 1, 1, 0, 1)  # TdsModel.cpp:35-44
     assert t.glottis_static[14] == 129.0 and t.glottis_static[15] == 125.51
+    assert (t.flow_source_section, t.flow_source_cm3_s, t.reserved) == (-1, 0.0, 0)  # TdsModel.cpp:84
     f = afs.default_frames(2)
     assert np.all(f["area_cm2"] == 4.0) and np.all(f["articulator"] == 4) and np.all(f["glottis_area_cm2"] == 0.1)
 

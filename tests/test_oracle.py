@@ -172,3 +172,36 @@ def test_chebyshev_restatement(oracle):
     g = load_golden("chebyshev.npz")
     a, b = oracle.chebyshev_lowpass(7000.0 / 44100.0, 8)
     assert np.array_equal(a, g["a44"]) and np.array_equal(b, g["b44"])
+
+
+def test_flow_source_probes_and_mean_flow_match_live_reference(oracle, shapes):
+    """Pins the oracle's restatement of TdsModel::setFlowSource (TdsModel.cpp:629-633, 996-1008), of the taps
+    getSectionPressure / getSectionFlow (:1715-1734) and of TlModel::getMeanFlow / getMostConstrictedSection
+    (TlModel.cpp:204-246) to the compiled reference, bit for bit."""
+    if not have_ref():
+        pytest.skip("compiled reference not available")
+    from oracle.pyoracle import Ref, tds_options_default
+    r = Ref(44)
+    n = len(shapes["names"])
+    fr = np.stack([shapes["frames"][0], shapes["frames"][n + 8]])  # /a:/ -> /i:/ with nasal coupling
+    gl = np.array([[120.0, 8000.0, 0.01, 0.01, 0.0, -40.0], [150.0, 8000.0, 0.01, 0.01, 0.0, -40.0]])
+    sections = [0, 22, 24, 28, 40, 64, 66, 83, 84, 90][:8]
+    for src_sec, amp in ((-1, 0.0), (30, 50.0), (5, -20.0), (70, 10.0)):
+        o = tds_options_default(noise=False); o.piriform_fossa = 1
+        o.flow_source_section = src_sec; o.flow_source_cm3_s = amp
+        ra, rp, ri, ro = r.tds_probed(fr, gl, [300], sections, opts=o)
+        oa, op, oi, oo = oracle.tds_synthesize_probed(fr[None], gl[None], [300], sections, opts=o)
+        assert np.array_equal(ra, oa[0]), src_sec
+        assert np.array_equal(rp, op[0]) and np.array_equal(ri, oi[0]) and np.array_equal(ro, oo[0]), src_sec
+    # the source really acts
+    o0 = tds_options_default(noise=False); o1 = tds_options_default(noise=False)
+    o1.flow_source_section = 30; o1.flow_source_cm3_s = 50.0
+    a0, _ = oracle.tds_synthesize(fr[None], gl[None], [300], opts=o0)
+    a1, _ = oracle.tds_synthesize(fr[None], gl[None], [300], opts=o1)
+    assert np.max(np.abs(a0 - a1)) > 1e-3 * np.max(np.abs(a0))
+    f = shapes["frames"].copy()
+    f["glottis_area_cm2"][::3] = 0.0
+    for P in (8000.0, 0.0, 1234.5):
+        rf, rs = Ref(22).tl_mean_flow(f, P)
+        of, os_ = oracle.tl_mean_flow(f, P)
+        assert np.array_equal(rf, of) and np.array_equal(rs, os_)

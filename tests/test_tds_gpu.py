@@ -347,3 +347,46 @@ def test_per_sample_control_frames(ctx, oracle, shapes, noise):
     ao, fo = oracle.tds_synthesize(fr, gl, frame_len, 44100.0, 2, opts=oracle_opts(noise=noise), seeds=seeds)
     assert not st.any()
     assert rel_err(audio, ao) <= TOL and rel_err(flow, fo) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# TdsModel::setFlowSource (TdsModel.cpp:629-633) and the taps getSectionPressure / getSectionFlow (:1715-1734)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("noise", [False, True])
+def test_flow_source_and_probes_against_oracle(ctx, oracle, shapes, noise):
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    fr, gl, _ = _vowel_transitions(shapes, 30, 77, nasal=True, dur=400)  # more tracts than one CTA holds... of 1 lane each
+    fl = [400]
+    seeds = np.arange(11, 41, dtype=np.uint32)
+    sections = [0, 22, 23, 24, 28, 40, 64, 83]     # trachea ends, glottis, branch points, mouth and nose ends
+    for src_sec, amp in ((-1, 0.0), (30, 50.0), (5, -20.0)):
+        o = afs.tds_options_default(noise=noise); o.piriform_fossa = 1
+        o.flow_source_section = src_sec; o.flow_source_cm3_s = amp
+        oo = oracle_opts(noise=noise); oo.piriform_fossa = 1
+        oo.flow_source_section = src_sec; oo.flow_source_cm3_s = amp
+        a, st, taps = ctx.tds_synthesize_probed(fr, gl, fl, sections, opts=o, seeds=seeds)
+        ao, po, io_, oo_ = oracle.tds_synthesize_probed(fr, gl, fl, sections, opts=oo, seeds=seeds)
+        assert not st.any()
+        assert rel_err(a, ao) <= TOL, (src_sec, rel_err(a, ao))
+        for name, ref in (("pressure", po), ("inflow", io_), ("outflow", oo_)):
+            for q in range(len(sections)):
+                scale = np.max(np.abs(ref[:, q])) + 1e-300
+                err = np.max(np.abs(taps[name][:, q] - ref[:, q])) / scale
+                assert err <= TOL, (src_sec, name, sections[q], err)
+        # the plain entry point gives the same audio (the taps do not disturb the simulation)
+        a2, _, _ = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=o, seeds=seeds)
+        assert np.array_equal(a, a2)
+    # sinus and fossa sections, a source in a static section, only one of the three outputs requested
+    o = afs.tds_options_default(noise=False); o.flow_source_section = 70; o.flow_source_cm3_s = 10.0
+    oo = oracle_opts(noise=False); oo.flow_source_section = 70; oo.flow_source_cm3_s = 10.0
+    sec2 = [66, 84, 88, 89, 92]
+    a, st, taps = ctx.tds_synthesize_probed(fr[:5], gl[:5], fl, sec2, opts=o, want=("pressure",))
+    ao, po, _, _ = oracle.tds_synthesize_probed(fr[:5], gl[:5], fl, sec2, opts=oo)
+    assert rel_err(a, ao) <= TOL and rel_err(taps["pressure"], po) <= TOL
+    # bad arguments
+    bad = afs.tds_options_default(); bad.flow_source_section = 93
+    with pytest.raises(afs.AfsError):
+        ctx.tds_synthesize(fr[:1], gl[:1], fl, 44100.0, 2, opts=bad)
+    with pytest.raises(afs.AfsError):
+        ctx.tds_synthesize_probed(fr[:1], gl[:1], fl, [93], opts=afs.tds_options_default())

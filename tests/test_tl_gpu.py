@@ -306,3 +306,15 @@ def test_impulse_response_bit_identical(ctx, oracle, shapes):
     assert np.max(np.abs(hf - h)) <= 1e-9 * np.max(np.abs(h))
     with pytest.raises(afs.AfsError):
         ctx.tl_impulse_response(rf, 22050.0, 12)
+
+
+def test_mean_flow_and_most_constricted_section(ctx, oracle, shapes):
+    """TlModel::getMeanFlow / getMostConstrictedSection (TlModel.cpp:204-246): bit-identical to the oracle."""
+    from conftest import random_frames
+    f = np.concatenate([shapes["frames"], random_frames(200, seed=5, glottis_area=0.1)])
+    f["glottis_area_cm2"][::3] = 0.0
+    for P in (8000.0, 0.0, 1234.5):
+        flow, sec = ctx.tl_mean_flow(f, P)
+        of, os_ = oracle.tl_mean_flow(f, P)
+        assert np.array_equal(sec, os_) and np.array_equal(flow, of)
+    assert ctx.tl_mean_flow(f[:0], 8000.0)[0].shape == (0,)
