@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
     TL_ARITHMETIC_REFERENCE,
     AfsError,
     Context,
+    Group,
     TdsOptions,
     TdsProbes,
     TlOptions,
@@ -21,6 +22,8 @@ from .api import (  # noqa: F401
     lf_glottal_flow,
     library_path,
     load_library,
+    pinned_empty,
+    pinned_free,
     tds_options_default,
     target_sequence_trajectory,
     tl_options_default,

@@ -103,6 +103,17 @@ def load_library():
     lib.afs_tds_synthesize_probed_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp, vp]
     lib.afs_tl_mean_flow.argtypes = [vp, i32, vp, dbl, vp, vp]
     lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
+    lib.afs_debug_set.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.afs_group_create.argtypes = [C.POINTER(C.c_void_p), vp, i32]
+    lib.afs_group_destroy.argtypes = [vp]
+    lib.afs_group_size.argtypes = [vp]
+    lib.afs_group_context.argtypes = [vp, i32]
+    lib.afs_group_context.restype = C.c_void_p
+    lib.afs_group_shard.argtypes = [vp, i32, i32, vp, vp]
+    lib.afs_group_tds_synthesize.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp]
+    lib.afs_group_tl_sweep.argtypes = [vp, vp, i32, vp, i32, i32, dbl, i32, vp, vp]
+    lib.afs_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.afs_host_free.argtypes = [vp]
     lib.afs_probe_fp64_tflops.argtypes = [vp, vp]
     lib.afs_chebyshev_lowpass.argtypes = [dbl, i32, vp, vp]
     lib.afs_audio_to_int16.argtypes = [vp, C.c_int64, vp]
@@ -217,6 +228,84 @@ def chebyshev_lowpass(cutoff_ratio, poles):
     b = np.zeros(poles + 1)
     _check(lib, lib.afs_chebyshev_lowpass(cutoff_ratio, poles, _ptr(a), _ptr(b)))
     return a, b
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (afs_host_alloc); keep the returned array alive while it is in use."""
+    lib = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _check(lib, lib.afs_host_alloc(C.byref(p), n))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[p.value] = (buf, lib)
+    return a
+
+
+_PINNED = {}
+
+
+def pinned_free(a):
+    addr = a.ctypes.data
+    buf, lib = _PINNED.pop(addr)
+    lib.afs_host_free(C.c_void_p(addr))
+
+
+class Group:
+    """Several devices of one box in one process (afs_group): contiguous shards, one host thread per device."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        ids = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        _check(self.lib, self.lib.afs_group_create(C.byref(h), _ptr(ids), 0 if ids is None else len(ids)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.afs_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.lib.afs_group_size(self.h))
+
+    def shard(self, n_units, index):
+        lo, hi = C.c_int(), C.c_int()
+        _check(self.lib, self.lib.afs_group_shard(self.h, int(n_units), int(index), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def tds_synthesize(self, frames, glottis, frame_len, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None, audio=None,
+                       want_flow=False):
+        opts = opts or tds_options_default()
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        B, F = frames.shape
+        glottis = np.ascontiguousarray(glottis, dtype=np.float64).reshape(B, F, NUM_GLOTTIS_CONTROL)
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.int32)
+        n_out = int(frame_len.sum())
+        if audio is None:
+            audio = np.empty((B, n_out))
+        flow = np.empty((B, n_out * sr_factor)) if want_flow else None
+        status = np.zeros(B, dtype=np.uint32)
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
+        _check(self.lib, self.lib.afs_group_tds_synthesize(self.h, C.byref(opts), B, F, _ptr(frame_len), _ptr(frames), _ptr(glottis),
+                                                           float(fs_tds_hz), int(sr_factor), _ptr(s), _ptr(audio), _ptr(flow),
+                                                           _ptr(status)))
+        return audio, flow, status
+
+    def tl_sweep(self, frames, f0_hz, num_freq, spectrum_type=2, section=FIRST_PHARYNX_SECTION, opts=None):
+        opts = opts or tl_options_default()
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        n = len(frames)
+        re = np.empty((n, num_freq)); im = np.empty((n, num_freq))
+        _check(self.lib, self.lib.afs_group_tl_sweep(self.h, C.byref(opts), n, _ptr(frames), int(spectrum_type), int(section),
+                                                     float(f0_hz), int(num_freq), _ptr(re), _ptr(im)))
+        return re, im
 
 
 class Context:
@@ -364,6 +453,10 @@ class Context:
         """Diagnostics: dump tract 0's state after simulation step `step` (1-based) on the next calls."""
         self._dump = out473 if step else None
         _check(self.lib, self.lib.afs_tds_set_state_dump(self.h, int(step), _ptr(self._dump)), self.h)
+
+    def debug_set(self, key, value):
+        """Test hooks of the library (afs_debug_set)."""
+        _check(self.lib, self.lib.afs_debug_set(self.h, key.encode(), int(value)), self.h)
 
     def tds_synthesize(self, frames, glottis, frame_len, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None,
                        want_flow=False):

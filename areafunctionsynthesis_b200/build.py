@@ -28,6 +28,7 @@ UNITS = {
     "raster_kernels.cu": ["-fmad=false"],
     "afs_api.cu": [],
     "afs_host.cpp": [],
+    "afs_multi.cpp": [],
 }
 
 

@@ -25,7 +25,17 @@ struct afs_ctx {
   int sm_count = 0;
   int dump_step = 0;          // diagnostics, see afs_tds_set_state_dump
   double *dump_host = nullptr;
+  // Stream-ordered pool for what the *_device entry points need beyond the caller's buffers: allocated and freed on
+  // the caller's stream, so calls on different streams never share a buffer (the grow-only `scratch` slots above
+  // belong to the host-buffer entry points, which run on ctx->stream and return synchronised).
+  cudaMemPool_t pool = nullptr;
+  // progress marks of a running TDS launch, in mapped host memory (see afs_tds_synthesize_probed)
+  unsigned int *progress_h = nullptr, *progress_d = nullptr;
+  // test hooks (afs_debug_set)
+  int64_t dbg_noise_scan_bytes = 0;
+  int dbg_noise_ring_entries = 0;
 };
+static constexpr int kMaxProgressCtas = 4096;
 
 namespace {
 
@@ -43,6 +53,15 @@ int bind(afs_ctx *ctx) {
   if (!ctx || ctx->device < 0) return AFS_ERR_BAD_CONTEXT;
   CU(cudaSetDevice(ctx->device));
   return AFS_OK;
+}
+
+// Stream-ordered temporary: valid for work enqueued on `stream` until pool_free on the same stream.
+int pool_alloc(afs_ctx *ctx, size_t bytes, cudaStream_t stream, void **out) {
+  CU(cudaMallocFromPoolAsync(out, bytes ? bytes : 1, ctx->pool, stream));
+  return AFS_OK;
+}
+void pool_free(void *p, cudaStream_t stream) {
+  if (p) cudaFreeAsync(p, stream);
 }
 
 int scratch(afs_ctx *ctx, int slot, size_t bytes, void **out) {
@@ -109,7 +128,22 @@ int afs_create(afs_ctx **out, int device_ordinal) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
-  if (e != cudaSuccess) { delete ctx; cudaGetLastError(); return AFS_ERR_CUDA; }
+  if (e == cudaSuccess) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device_ordinal;
+    e = cudaMemPoolCreate(&ctx->pool, &props);
+    if (e == cudaSuccess) {  // keep freed blocks: the same sizes come back call after call
+      unsigned long long keep = ~0ull;
+      e = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->progress_h, kMaxProgressCtas * sizeof(unsigned int), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&ctx->progress_d, ctx->progress_h, 0);
+  if (e != cudaSuccess) { afs_destroy(ctx); cudaGetLastError(); return AFS_ERR_CUDA; }
   *out = ctx;
   return AFS_OK;
 }
@@ -118,10 +152,13 @@ int afs_destroy(afs_ctx *ctx) {
   if (!ctx) return AFS_OK;
   if (ctx->device >= 0) {
     cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
     for (int i = 0; i < 10; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; i++) if (ctx->chunk_done[i]) cudaEventDestroy(ctx->chunk_done[i]);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    if (ctx->progress_h) cudaFreeHost(ctx->progress_h);
   }
   delete ctx;
   return AFS_OK;
@@ -271,20 +308,26 @@ int afs_tl_sweep(afs_ctx *ctx, const afs_tl_options *opts, int n_tubes, const af
   // staged by the driver and gain nothing, but lose nothing either.
   const int chunk = n_tubes >= 1024 ? (n_tubes + 7) / 8 : n_tubes;
   int k = 0;
-  for (int b = 0; b < n_tubes; b += chunk, k++) {
+  cudaError_t e = cudaSuccess;
+  rc = AFS_OK;
+  for (int b = 0; b < n_tubes && rc == AFS_OK && e == cudaSuccess; b += chunk, k++) {
     const int nb_t = n_tubes - b < chunk ? n_tubes - b : chunk;
     const size_t off = (size_t)b * num_freq, bytes = (size_t)nb_t * num_freq * sizeof(double);
     rc = afs_tl_sweep_device(ctx, opts, nb_t, (const afs_tube_frame *)d_tubes + b, spectrum_type, section, f0_hz,
                              num_freq, (double *)d_re + off, (double *)d_im + off, ctx->stream);
-    if (rc) return rc;
+    if (rc) break;
     cudaEvent_t ev = ctx->chunk_done[k & 1];
-    CU(cudaEventRecord(ev, ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
-    CU(cudaMemcpyAsync(re + off, (double *)d_re + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    CU(cudaMemcpyAsync(im + off, (double *)d_im + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if ((e = cudaEventRecord(ev, ctx->stream)) != cudaSuccess) break;
+    if ((e = cudaStreamWaitEvent(ctx->copy_stream, ev, 0)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(re + off, (double *)d_re + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream)) != cudaSuccess) break;
+    e = cudaMemcpyAsync(im + off, (double *)d_im + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
   }
-  CU(cudaStreamSynchronize(ctx->copy_stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  // both streams are drained on EVERY path: earlier chunks may still be on their way into the caller's buffers
+  const cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "afs_tl_sweep: chunk copy");
+  if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "cudaStreamSynchronize(copy stream)");
+  if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "cudaStreamSynchronize");
   return AFS_OK;
 }
 
@@ -362,27 +405,31 @@ int afs_tl_impulse_response_device(afs_ctx *ctx, const afs_tl_options *opts, int
   int nf = (int)(10100.0 / f0);
   if (nf >= N / 2) nf = N / 2 - 1;
   if (nf < 2) return AFS_ERR_BAD_ARGUMENT;
-  void *d_re, *d_im, *d_tab;
+  void *d_re = nullptr, *d_im = nullptr, *d_tab = nullptr;
   const size_t nb = (size_t)n_tubes * nf * sizeof(double);
   const size_t ntab = (size_t)(2 * (N - 1) + 2 * nf + N);
-  if ((rc = scratch(ctx, 1, nb, &d_re))) return rc;
-  if ((rc = scratch(ctx, 2, nb, &d_im))) return rc;
-  if ((rc = scratch(ctx, 7, ntab * sizeof(double), &d_tab))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // stream-ordered temporaries (see afs_ctx::pool): calls on different streams do not share them
+  auto release = [&]() { pool_free(d_re, st); pool_free(d_im, st); pool_free(d_tab, st); };
+  if ((rc = pool_alloc(ctx, nb, st, &d_re)) || (rc = pool_alloc(ctx, nb, st, &d_im)) ||
+      (rc = pool_alloc(ctx, ntab * sizeof(double), st, &d_tab))) { release(); return rc; }
   std::vector<double> tab(ntab);
   double *tw_re = tab.data(), *tw_im = tw_re + (N - 1), *rad_re = tw_im + (N - 1), *rad_im = rad_re + nf,
          *window = rad_im + nf;
   impulse_response_tables(f0, length_exponent, nf, tw_re, tw_im, rad_re, rad_im, window);
-  cudaStream_t st = (cudaStream_t)stream;
   // pageable source: the copy is staged before the call returns, `tab` may go out of scope
-  CU(cudaMemcpyAsync(d_tab, tab.data(), ntab * sizeof(double), cudaMemcpyHostToDevice, st));
+  cudaError_t e = cudaMemcpyAsync(d_tab, tab.data(), ntab * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "cudaMemcpyAsync(impulse-response tables)"); }
   rc = afs_tl_sweep_device(ctx, opts, n_tubes, d_tubes, AFS_FLOW_SOURCE_TF, AFS_FIRST_PHARYNX_SECTION, f0, nf,
                            (double *)d_re, (double *)d_im, stream);
-  if (rc) return rc;
+  if (rc) { release(); return rc; }
   IrTables t;
   const double *base = (const double *)d_tab;
   t.tw_re = base; t.tw_im = base + (N - 1); t.rad_re = base + 2 * (N - 1); t.rad_im = t.rad_re + nf;
   t.window = t.rad_im + nf;
-  CU(launch_impulse_response(n_tubes, length_exponent, nf, (const double *)d_re, (const double *)d_im, t, d_out, st));
+  e = launch_impulse_response(n_tubes, length_exponent, nf, (const double *)d_re, (const double *)d_im, t, d_out, st);
+  release();
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_impulse_response");
   ctx->launches++;
   return AFS_OK;
 }
@@ -708,9 +755,8 @@ int afs_synthesize_vowels_lf(afs_ctx *ctx, const afs_tl_options *opts, int n, co
   if ((rc = scratch(ctx, 6, lb * sizeof(int16_t), &d_audio))) return rc;
   CU(cudaMemcpyAsync(d_tubes, tubes, (size_t)n * sizeof(afs_tube_frame), cudaMemcpyHostToDevice, ctx->stream));
   rc = afs_tl_impulse_response_device(ctx, opts, n, (const afs_tube_frame *)d_tubes, sampling_rate_hz, 9, (double *)d_h,
-                                      ctx->stream);  // uses scratch 1, 2, 7
+                                      ctx->stream);
   if (rc) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));  // scratch 7 is reused below
   if ((rc = scratch(ctx, 7, ((size_t)n + 14) * sizeof(double), &d_misc))) return rc;
   double *d_scale = (double *)d_misc, *d_ab = d_scale + n;
   CU(cudaMemcpyAsync(d_flow, flow.data(), lb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -728,6 +774,92 @@ int afs_synthesize_vowels_lf(afs_ctx *ctx, const afs_tl_options *opts, int n, co
 // ---------------------------------------------------------------------------
 // TDS
 // ---------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// One call of the time-domain path on device buffers, asynchronous on `stream`.  `d_progress` (nullable, with
+// progress_every > 0): the kernel publishes per-CTA progress marks there; only possible when the batch runs as ONE
+// launch (*single_launch tells).
+int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
+                   const afs_tube_frame *d_tubes, const double *d_glottis, double fs_tds_hz, int sr_factor,
+                   const uint32_t *d_seeds, double *d_audio, double *d_flow, uint32_t *d_status,
+                   const afs_tds_probes *d_probes, cudaStream_t stream, unsigned int *d_progress, int progress_every,
+                   int *ctas_out /* [2]: CTAs of the single launch (0: several launches), tracts per CTA */) {
+  int rc;
+  if (!opts || n_tracts < 0 || n_frames < 2 || !frame_len || sr_factor < 1 || !(fs_tds_hz > 0))
+    return AFS_ERR_BAD_ARGUMENT;
+  if (opts->glottis_loss_option < AFS_STANDARD_ENTRANCE_LOSS || opts->glottis_loss_option > AFS_VARIABLE_ENTRANCE_LOSS)
+    return AFS_ERR_BAD_ARGUMENT;
+  for (int k = 0; k + 1 < n_frames; k++) if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT;
+  if (d_probes) {
+    if (d_probes->n_probes < 0 || d_probes->n_probes > AFS_MAX_TDS_PROBES) return AFS_ERR_BAD_ARGUMENT;
+    for (int q = 0; q < d_probes->n_probes; q++)
+      if (d_probes->section[q] < 0 || d_probes->section[q] >= AFS_NUM_SECTIONS) return AFS_ERR_BAD_ARGUMENT;
+  }
+  if (ctas_out) *ctas_out = 0;
+  if (n_tracts == 0) return AFS_OK;
+  if (!d_tubes || !d_glottis || !d_audio) return AFS_ERR_BAD_ARGUMENT;
+
+  TdsLaunch L;
+  rc = tds_prepare_launch(opts, n_tracts, n_frames, frame_len, fs_tds_hz, sr_factor, ctx->sm_count,
+                          ctx->dbg_noise_ring_entries, &L);
+  if (rc) return rc;
+  // everything below the caller's buffers is a stream-ordered temporary (see afs_ctx::pool)
+  void *d_bounds = nullptr, *d_dump = nullptr, *d_nzc = nullptr;
+  auto release = [&]() { pool_free(d_bounds, stream); pool_free(d_dump, stream); pool_free(d_nzc, stream); };
+  if ((rc = pool_alloc(ctx, sizeof(int32_t) * (size_t)(n_frames + 1), stream, &d_bounds))) return rc;
+  // (pageable source: staged before the call returns)
+  cudaError_t e = cudaMemcpyAsync(d_bounds, L.step_bounds.data(), sizeof(int32_t) * (size_t)n_frames, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "cudaMemcpyAsync(step bounds)"); }
+  if (ctx->dump_step > 0 && ctx->dump_host) {
+    if ((rc = pool_alloc(ctx, 473 * sizeof(double), stream, &d_dump))) { release(); return rc; }
+    cudaMemsetAsync(d_dump, 0, 473 * sizeof(double), stream);
+  }
+  // Noise sources: the constriction records of the pre-pass (48 B per tract-step, 32 lanes per CTA); a batch whose
+  // records would not fit the budget runs as several waves of CTAs that reuse the buffer.
+  const size_t per_cta = tds_noise_scan_bytes_per_cta(L);
+  const int lpc = tds_lanes_per_cta(L);
+  const int ctas = (n_tracts + lpc - 1) / lpc;
+  int wave_ctas = ctas;
+  if (per_cta) {
+    size_t free_b = 0, total_b = 0;
+    unsigned long long cached = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &cached);
+    size_t budget = (size_t)((free_b + (size_t)cached) / 10 * 6);  // 60 % of what this context could get
+    if (budget > ((size_t)12 << 30)) budget = (size_t)12 << 30;
+    if (ctx->dbg_noise_scan_bytes > 0) budget = (size_t)ctx->dbg_noise_scan_bytes;  // (tests force several waves)
+    if (per_cta > budget) { release(); return AFS_ERR_OUT_OF_MEMORY; }  // a single utterance of hours
+    size_t fit = budget / per_cta;
+    if (fit >= (size_t)ctx->sm_count) fit -= fit % (size_t)ctx->sm_count;  // whole waves of one CTA per SM
+    if ((size_t)wave_ctas > fit) wave_ctas = (int)fit;
+    if ((rc = pool_alloc(ctx, per_cta * (size_t)wave_ctas, stream, &d_nzc))) { release(); return rc; }
+  }
+  const bool single = wave_ctas >= ctas && ctas <= kMaxProgressCtas;  // (one launch, and a mark per CTA fits)
+  if (ctas_out) *ctas_out = single ? ctas : 0;
+  if (ctas_out && single) ctas_out[1] = lpc;
+  for (int c0 = 0; c0 < ctas; c0 += wave_ctas) {
+    const int t0 = c0 * lpc;
+    const int nw = (c0 + wave_ctas >= ctas) ? n_tracts - t0 : wave_ctas * lpc;
+    e = launch_tds(L, t0, nw, (const int32_t *)d_bounds, d_tubes, d_glottis, d_seeds, d_audio, d_flow, d_status,
+                   c0 == 0 ? (double *)d_dump : nullptr, ctx->dump_step, d_nzc, d_probes,
+                   single ? d_progress : nullptr, single ? progress_every : 0, stream);
+    if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "launch_tds"); }
+    ctx->launches += per_cta ? 2 : 1;
+  }
+  if (d_dump) {
+    cudaMemcpyAsync(ctx->dump_host, d_dump, 473 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+  }
+  release();
+  return AFS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int afs_tds_synthesize_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int n_frames,
                               const int32_t *frame_len, const afs_tube_frame *d_tubes, const double *d_glottis,
                               double fs_tds_hz, int sr_factor, const uint32_t *d_seeds, double *d_audio,
@@ -742,69 +874,23 @@ int afs_tds_synthesize_probed_device(afs_ctx *ctx, const afs_tds_options *opts, 
                                      double *d_flow, uint32_t *d_status, const afs_tds_probes *d_probes, void *stream) {
   int rc = bind(ctx);
   if (rc) return rc;
-  if (!opts || n_tracts < 0 || n_frames < 2 || !frame_len || sr_factor < 1 || !(fs_tds_hz > 0))
-    return AFS_ERR_BAD_ARGUMENT;
-  if (opts->glottis_loss_option < AFS_STANDARD_ENTRANCE_LOSS || opts->glottis_loss_option > AFS_VARIABLE_ENTRANCE_LOSS)
-    return AFS_ERR_BAD_ARGUMENT;
-  for (int k = 0; k + 1 < n_frames; k++) if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT;
-  if (d_probes) {
-    if (d_probes->n_probes < 0 || d_probes->n_probes > AFS_MAX_TDS_PROBES) return AFS_ERR_BAD_ARGUMENT;
-    for (int q = 0; q < d_probes->n_probes; q++)
-      if (d_probes->section[q] < 0 || d_probes->section[q] >= AFS_NUM_SECTIONS) return AFS_ERR_BAD_ARGUMENT;
-  }
-  if (n_tracts == 0) return AFS_OK;
-  if (!d_tubes || !d_glottis || !d_audio) return AFS_ERR_BAD_ARGUMENT;
-
-  TdsLaunch L;
-  rc = tds_prepare_launch(opts, n_tracts, n_frames, frame_len, fs_tds_hz, sr_factor, ctx->sm_count, &L);
-  if (rc) return rc;
-  // per-launch frame boundaries live in device scratch slot 7
-  void *d_bounds;
-  if ((rc = scratch(ctx, 7, sizeof(int32_t) * (size_t)(n_frames + 1), &d_bounds))) return rc;
-  CU(cudaMemcpyAsync(d_bounds, L.step_bounds.data(), sizeof(int32_t) * (size_t)n_frames, cudaMemcpyHostToDevice,
-                     (cudaStream_t)stream));
-  void *d_dump = nullptr;
-  if (ctx->dump_step > 0 && ctx->dump_host) {
-    if ((rc = scratch(ctx, 6, 473 * sizeof(double), &d_dump))) return rc;
-    CU(cudaMemsetAsync(d_dump, 0, 473 * sizeof(double), (cudaStream_t)stream));
-  }
-  // Noise sources: the constriction records of the pre-pass (48 B per tract-step, 32 lanes per CTA) live in scratch
-  // slot 8; a batch whose records would exceed kNoiseScanBytes runs as several waves of CTAs that reuse the buffer.
-  const size_t per_cta = tds_noise_scan_bytes_per_cta(L);
-  const int lpc = tds_lanes_per_cta(L);
-  const int ctas = (n_tracts + lpc - 1) / lpc;
-  int wave_ctas = ctas;
-  void *d_nzc = nullptr;
-  if (per_cta) {
-    size_t kNoiseScanBytes = (size_t)12 << 30;
-    if (const char *env = getenv("AFS_NOISE_SCAN_BYTES")) {  // (tests force several waves with a small budget)
-      const unsigned long long v = strtoull(env, nullptr, 10);
-      if (v >= per_cta) kNoiseScanBytes = (size_t)v;
-    }
-    if (per_cta > kNoiseScanBytes) return AFS_ERR_OUT_OF_MEMORY;  // a single utterance of > 2.9 h at 44.1 kHz
-    size_t fit = kNoiseScanBytes / per_cta;
-    if (fit >= (size_t)ctx->sm_count) fit -= fit % (size_t)ctx->sm_count;  // whole waves of one CTA per SM
-    if ((size_t)wave_ctas > fit) wave_ctas = (int)fit;
-    if ((rc = scratch(ctx, 8, per_cta * (size_t)wave_ctas, &d_nzc))) return rc;
-  }
-  for (int c0 = 0; c0 < ctas; c0 += wave_ctas) {
-    const int t0 = c0 * lpc;
-    const int nw = (c0 + wave_ctas >= ctas) ? n_tracts - t0 : wave_ctas * lpc;
-    CU(launch_tds(L, t0, nw, (const int32_t *)d_bounds, d_tubes, d_glottis, d_seeds, d_audio, d_flow, d_status,
-                  c0 == 0 ? (double *)d_dump : nullptr, ctx->dump_step, d_nzc, d_probes, (cudaStream_t)stream));
-    ctx->launches += per_cta ? 2 : 1;
-  }
-  if (d_dump) {
-    CU(cudaMemcpyAsync(ctx->dump_host, d_dump, 473 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CU(cudaStreamSynchronize((cudaStream_t)stream));
-  }
-  return AFS_OK;
+  return tds_run_device(ctx, opts, n_tracts, n_frames, frame_len, d_tubes, d_glottis, fs_tds_hz, sr_factor, d_seeds, d_audio,
+                        d_flow, d_status, d_probes, (cudaStream_t)stream, nullptr, 0, nullptr);
 }
 
 int afs_tds_set_state_dump(afs_ctx *ctx, int step, double *host_out473) {
   if (!ctx) return AFS_ERR_BAD_CONTEXT;
   ctx->dump_step = step;
   ctx->dump_host = host_out473;
+  return AFS_OK;
+}
+
+int afs_debug_set(afs_ctx *ctx, const char *key, int64_t value) {
+  if (!ctx) return AFS_ERR_BAD_CONTEXT;
+  if (!key) return AFS_ERR_BAD_ARGUMENT;
+  if (!strcmp(key, "tds.noise_scan_bytes")) ctx->dbg_noise_scan_bytes = value;
+  else if (!strcmp(key, "tds.noise_ring_entries")) ctx->dbg_noise_ring_entries = (int)value;
+  else return AFS_ERR_BAD_ARGUMENT;
   return AFS_OK;
 }
 
@@ -816,6 +902,10 @@ int afs_tds_synthesize(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, 
                                    audio, flow, status, nullptr);
 }
 
+// Host buffers.  The audio leaves the device WHILE the kernel runs: the kernel publishes, per CTA, how many
+// simulation steps are complete (progress marks in mapped host memory, every 1/16 of the utterance); as soon as all
+// CTAs have passed a mark, the finished time slice of every utterance -- a [n_tracts] x [slice] column block of the
+// [n_tracts][n_out] array -- is copied on the second stream.  What is left after the kernel is the last slice.
 int afs_tds_synthesize_probed(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int n_frames,
                               const int32_t *frame_len, const afs_tube_frame *tubes, const double *glottis,
                               double fs_tds_hz, int sr_factor, const uint32_t *seeds, double *audio, double *flow,
@@ -861,19 +951,65 @@ int afs_tds_synthesize_probed(afs_ctx *ctx, const afs_tds_options *opts, int n_t
     if (probes->outflow_cm3_s) { dp.outflow_cm3_s = (double *)at; at += pb; }
     use = &dp;
   }
-  rc = afs_tds_synthesize_probed_device(ctx, opts, n_tracts, n_frames, frame_len, (const afs_tube_frame *)d_tubes,
-                                        (const double *)d_gl, fs_tds_hz, sr_factor, (const uint32_t *)d_seeds,
-                                        (double *)d_audio, (double *)d_flow, (uint32_t *)d_status, use, ctx->stream);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(audio, d_audio, ab, cudaMemcpyDeviceToHost, ctx->stream));
-  if (flow) CU(cudaMemcpyAsync(flow, d_flow, fb, cudaMemcpyDeviceToHost, ctx->stream));
-  if (status) CU(cudaMemcpyAsync(status, d_status, (size_t)n_tracts * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (use) {
-    if (dp.pressure_dPa) CU(cudaMemcpyAsync(probes->pressure_dPa, dp.pressure_dPa, pb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (dp.inflow_cm3_s) CU(cudaMemcpyAsync(probes->inflow_cm3_s, dp.inflow_cm3_s, pb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (dp.outflow_cm3_s) CU(cudaMemcpyAsync(probes->outflow_cm3_s, dp.outflow_cm3_s, pb, cudaMemcpyDeviceToHost, ctx->stream));
+  // time slices: worth it from a few MB of audio on; the progress marks are in simulation steps
+  const size_t total_steps = n_out * (size_t)sr_factor;
+  int n_slices = ab >= ((size_t)8 << 20) && n_out >= 64 ? 16 : 1;
+  const size_t slice_out = (n_out + (size_t)n_slices - 1) / (size_t)n_slices;
+  const int every = n_slices > 1 && total_steps < 0x7fffffffull ? (int)(slice_out * (size_t)sr_factor) : 0;
+  if (every) memset(ctx->progress_h, 0, kMaxProgressCtas * sizeof(unsigned int));
+  int grid[2] = {0, 0};
+  rc = tds_run_device(ctx, opts, n_tracts, n_frames, frame_len, (const afs_tube_frame *)d_tubes, (const double *)d_gl,
+                      fs_tds_hz, sr_factor, (const uint32_t *)d_seeds, (double *)d_audio, (double *)d_flow,
+                      (uint32_t *)d_status, use, ctx->stream, every ? ctx->progress_d : nullptr, every, grid);
+  if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+  const int ctas = grid[0], lpc = grid[1];
+  const volatile unsigned int *mark = ctx->progress_h;
+  // waits until the CTAs [c0, c1) have all published `need` steps; false when the kernel is over (or failed) first
+  auto wait_for = [&](int c0, int c1, unsigned int need) {
+    for (int spin = 0;; spin++) {
+      bool ready = true;
+      for (int c = c0; c < c1; c++) if (mark[c] < need) { ready = false; break; }
+      if (ready) return true;
+      if ((spin & 1023) == 1023 && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) return false;
+    }
+  };
+  size_t copied = 0;       // output samples per utterance already on their way to the host (time slices) ...
+  size_t rows_copied = 0;  // ... or whole utterances (batches of more CTAs than SMs: the CTAs finish wave after wave)
+  cudaError_t ce = cudaSuccess;
+  if (every && ctas > 0 && ctas <= ctx->sm_count) {
+    while (ce == cudaSuccess && copied + slice_out < n_out) {  // (the last slice goes after the kernel)
+      if (!wait_for(0, ctas, (unsigned int)((copied + slice_out) * (size_t)sr_factor))) break;
+      ce = cudaMemcpy2DAsync(audio + copied, n_out * sizeof(double), (const double *)d_audio + copied, n_out * sizeof(double),
+                             slice_out * sizeof(double), (size_t)n_tracts, cudaMemcpyDeviceToHost, ctx->copy_stream);
+      copied += slice_out;
+    }
+  } else if (every && ctas > ctx->sm_count) {
+    for (int c0 = 0; ce == cudaSuccess && c0 + ctx->sm_count < ctas; c0 += ctx->sm_count) {  // (the last wave goes after the kernel)
+      if (!wait_for(c0, c0 + ctx->sm_count, (unsigned int)total_steps)) break;
+      const size_t r1 = (size_t)(c0 + ctx->sm_count) * (size_t)lpc;
+      ce = cudaMemcpyAsync(audio + rows_copied * n_out, (const double *)d_audio + rows_copied * n_out,
+                           (r1 - rows_copied) * n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream);
+      rows_copied = r1;
+    }
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (ce != cudaSuccess) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); return cuda_fail(ctx, ce, "device-to-host copy of finished audio"); }
+  cudaError_t e = cudaSuccess;
+  if (copied == 0) e = cudaMemcpyAsync(audio + rows_copied * n_out, (const double *)d_audio + rows_copied * n_out,
+                                       ((size_t)n_tracts - rows_copied) * n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  else e = cudaMemcpy2DAsync(audio + copied, n_out * sizeof(double), (const double *)d_audio + copied, n_out * sizeof(double),
+                             (n_out - copied) * sizeof(double), (size_t)n_tracts, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && flow) e = cudaMemcpyAsync(flow, d_flow, fb, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_status, (size_t)n_tracts * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && use) {
+    if (dp.pressure_dPa) e = cudaMemcpyAsync(probes->pressure_dPa, dp.pressure_dPa, pb, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && dp.inflow_cm3_s) e = cudaMemcpyAsync(probes->inflow_cm3_s, dp.inflow_cm3_s, pb, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && dp.outflow_cm3_s) e = cudaMemcpyAsync(probes->outflow_cm3_s, dp.outflow_cm3_s, pb, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  // both streams are drained on every path: the caller owns the host buffers again when this returns
+  const cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "device-to-host copies");
+  if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "cudaStreamSynchronize(copy stream)");
+  if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "cudaStreamSynchronize");
   return AFS_OK;
 }
 

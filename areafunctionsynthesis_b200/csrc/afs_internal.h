@@ -57,11 +57,12 @@ struct TdsLaunch {
   int n_tracts = 0, n_frames = 0;
 };
 int tds_prepare_launch(const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
-                       double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L);
+                       double fs_tds_hz, int sr_factor, int sm_count, int ring_entries, TdsLaunch *L);
 cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
                        uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const afs_tds_probes *d_probes,
-                       cudaStream_t stream);
+                       unsigned int *d_progress, int progress_every, cudaStream_t stream);
+int tds_total_steps(const TdsLaunch &L);
 size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L);  // 0 without noise sources
 int tds_lanes_per_cta(const TdsLaunch &L);
 size_t tds_smem_bytes();

@@ -1651,6 +1651,10 @@ struct KArgs {
   double *nzc_f;
   // taps: [tract][probe][step], each nullable
   double *tap_p, *tap_in, *tap_out;
+  // progress[cta] = simulation steps whose outputs are complete and visible system-wide, published every
+  // `progress_every` steps (nullable): lets the host copy finished time slices while the kernel runs
+  unsigned int *progress;
+  int progress_every;
 };
 
 #ifdef AFS_TDS_TIMING
@@ -1832,6 +1836,14 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       for (int c = 0; c < 4; c++) x1p[c] = S.p4[c][lane];
       if (X.rows) bar_arrive(1, TDS_THREADS);
       if (n > 0) emit_output(P, xr, u_rad, x1p[3], n, active, tract, n_out, A.audio, A.flow, bad);
+      if (A.progress && n > 0 && (n % A.progress_every == 0 || n == T)) {
+        __threadfence_system();  // this lane's samples first, ...
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+          __threadfence_system();
+          *(volatile unsigned int *)(A.progress + blockIdx.x) = (unsigned int)n;  // ... then the mark
+        }
+      }
     }
     if (!X.rows) break;
     // ============ first rows + elimination of the segments || glottis ============
@@ -2043,7 +2055,7 @@ tds_noise_scan_kernel(const TdsParams P, const KArgs A) {
 
 // ---- host side ------------------------------------------------------------------
 int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, const int32_t *frame_len,
-                       double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L) {
+                       double fs_tds_hz, int sr_factor, int sm_count, int ring_entries, TdsLaunch *L) {
   TdsParams P;
   memset(&P, 0, sizeof P);
   long total = 0;
@@ -2100,10 +2112,7 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   P.nz_F = 1.0 - exp(-2.0 * M_PI * 40.0 * dt);
   P.nz_x2000 = exp(-2.0 * M_PI * (2000.0 * dt));
   P.nz_ring = NZ_RING;
-  if (const char *env = getenv("AFS_NOISE_RING_ENTRIES")) {  // (tests force the overflow path with a short ring)
-    const int v = atoi(env);
-    if (v >= 4 && v <= NZ_RING) P.nz_ring = v;
-  }
+  if (ring_entries >= 4 && ring_entries <= NZ_RING) P.nz_ring = ring_entries & ~1;  // (test hook: forces the overflow path)
   P.nm_a = exp(-2.0 * M_PI * 500.0 * dt);
   P.nm_1a = 1.0 - P.nm_a;
   P.dump_step = 0;
@@ -2129,7 +2138,7 @@ int tds_lanes_per_cta(const TdsLaunch &L) {
 cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
                        uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const afs_tds_probes *probes,
-                       cudaStream_t stream) {
+                       unsigned int *d_progress, int progress_every, cudaStream_t stream) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
@@ -2160,7 +2169,8 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
           d_status ? d_status + tract0 : nullptr,
           d_dump,
           d_seeds ? d_seeds + tract0 : nullptr,
-          nullptr, nullptr, nullptr, nullptr, nullptr};
+          nullptr, nullptr, nullptr, nullptr, nullptr,
+          progress_every > 0 ? d_progress : nullptr, progress_every};
   if (P.n_probes > 0) {
     const size_t off = (size_t)tract0 * P.n_probes * (size_t)P.total_steps;
     A.tap_p = probes->pressure_dPa ? probes->pressure_dPa + off : nullptr;
@@ -2182,5 +2192,10 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
 }
 
 size_t tds_smem_bytes() { return sizeof(TdsSmem); }
+int tds_total_steps(const TdsLaunch &L) {
+  TdsParams P;
+  memcpy(&P, L.params.data(), sizeof P);
+  return P.total_steps;
+}
 
 }  // namespace afs

@@ -21,6 +21,7 @@
 #ifndef AFS_B200_H
 #define AFS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -182,7 +183,12 @@ typedef struct afs_tds_options {
   int32_t reserved; /* must be 0 */
 } afs_tds_options;
 
-typedef struct afs_ctx afs_ctx; /* opaque: one CUDA device, scratch buffers, one stream */
+/* Opaque: one CUDA device, its streams and buffers.  Threading / streams: a context serves one host thread at a time.
+ * The host-buffer entry points run on the context's own stream and return synchronised.  The *_device entry points
+ * are asynchronous on the caller's stream and keep their temporaries in a stream-ordered pool (allocated and freed
+ * on that stream), so calls on DIFFERENT streams of one context may be in flight together; outputs are valid once
+ * the caller's stream has reached the point of the call. */
+typedef struct afs_ctx afs_ctx;
 
 /* ---- life cycle ----------------------------------------------------------- */
 int afs_version(void);
@@ -423,10 +429,44 @@ int afs_tds_synthesize_probed_device(afs_ctx *ctx, const afs_tds_options *opts, 
  * (TdsModel.h:141-143,166-167,184). */
 int afs_tds_set_state_dump(afs_ctx *ctx, int step, double *host_out473);
 
+/* Test hooks, not tuning knobs of the product: "tds.noise_scan_bytes" (device budget of the noise pre-pass records;
+ * 0 = derived from the free device memory: tests force several waves with a small value), "tds.noise_ring_entries"
+ * (ring of pre-generated noise sums; 0 = full: tests force the overflow path).  Unknown keys: AFS_ERR_BAD_ARGUMENT. */
+int afs_debug_set(afs_ctx *ctx, const char *key, int64_t value);
+
 /* Measures the FP64 FMA peak of the bound device (independent DFMA chains,
  * best of 4), in TFLOP/s: the roofline denominator of both kernels
  * (MEASURED_PEAKS.json has no FP64 figure). */
 int afs_probe_fp64_tflops(afs_ctx *ctx, double *tflops);
+
+/* ---- several devices of one box, one process ------------------------------------ */
+/*
+ * The units of the path (utterances, area functions) are independent (Synthesizer.cpp:557-629 keeps one TdsModel
+ * per utterance): a group shards a batch into contiguous ranges [r*B/G, (r+1)*B/G) over its G
+ * devices, runs every shard through the single-device entry point of the same name on its own host thread and
+ * stream, and lets every device write its rows of the caller's output arrays directly -- there is no data-path
+ * collective and no gather step: the outputs of all devices land in ONE host array.  Results are those of the
+ * single-device call, bit for bit, whatever the number of devices.
+ *   afs_group_create: device_ordinals null / n_devices <= 0 = every visible device.
+ *   afs_group_context: the afs_ctx of device `index` (for the *_device entry points).
+ * Pinned buffers (afs_host_alloc) let the copies of the eight devices run at full PCIe rate beside the kernels.
+ */
+typedef struct afs_group afs_group;
+int afs_group_create(afs_group **group, const int *device_ordinals, int n_devices);
+int afs_group_destroy(afs_group *group);
+int afs_group_size(const afs_group *group);
+afs_ctx *afs_group_context(afs_group *group, int index);
+/* [lo, hi) of the batch of n_units that device `index` takes (sizes differ by at most one). */
+int afs_group_shard(const afs_group *group, int n_units, int index, int *lo, int *hi);
+int afs_group_tds_synthesize(afs_group *group, const afs_tds_options *opts, int n_tracts, int n_frames,
+                             const int32_t *frame_len, const afs_tube_frame *tubes, const double *glottis,
+                             double fs_tds_hz, int sr_factor, const uint32_t *seeds, double *audio, double *flow,
+                             uint32_t *status);
+int afs_group_tl_sweep(afs_group *group, const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
+                       int spectrum_type, int section, double f0_hz, int num_freq, double *re, double *im);
+/* Page-locked host memory (cudaHostAlloc, portable across the devices of a group). */
+int afs_host_alloc(void **ptr, size_t bytes);
+int afs_host_free(void *ptr);
 
 /* ---- host-side helpers of the boundary (no device work) -------------------- */
 /* IirFilter::createChebyshev low-pass (IirFilter.cpp:286-432): recursion

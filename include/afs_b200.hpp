@@ -11,7 +11,8 @@
 //                                             setVelumOpening, setAspirationStrength, interpolate
 //   afs::TlModel         TlModel.h:24-131     public `options`, `tube`; getSpectrum, getFormants
 //   afs::TdsSynthesizer  Synthesizer.h:161    synthesizeSignalTds(newTube, newGlottisParams, numNewSamples, out)
-//                        + TdsModel.h:257-280 options, resetMotion
+//                        + TdsModel.h:257-280 options, resetMotion, setFlowSource, getSectionPressure / getSectionFlow
+//   afs::DeviceGroup     (no counterpart: the reference is single-threaded) several B200s of one box, one process
 #pragma once
 #include <cstdint>
 #include <stdexcept>
@@ -44,6 +45,21 @@ class Device {
 
  private:
   afs_ctx *ctx_ = nullptr;
+};
+
+// Several devices of one box (afs_group): a batch is split into contiguous shards, one host thread per device.
+class DeviceGroup {
+ public:
+  DeviceGroup() { check(afs_group_create(&g_, nullptr, 0)); }  // every visible device
+  explicit DeviceGroup(const std::vector<int> &ordinals) { check(afs_group_create(&g_, ordinals.data(), (int)ordinals.size())); }
+  ~DeviceGroup() { afs_group_destroy(g_); }
+  DeviceGroup(const DeviceGroup &) = delete;
+  DeviceGroup &operator=(const DeviceGroup &) = delete;
+  afs_group *group() const { return g_; }
+  int size() const { return afs_group_size(g_); }
+
+ private:
+  afs_group *g_ = nullptr;
 };
 
 // The dynamic part of the reference Tube as a value type (a reference Tube holds pointers into itself and cannot
@@ -114,6 +130,24 @@ class TlModel {
 
   explicit TlModel(Device &dev) : dev_(dev) { afs_tl_options_default(&options); }
   void setLungPressure(double lungPressure_dPa) { options.lung_pressure_dPa = lungPressure_dPa; }
+  // TlModel::getMostConstrictedSection (TlModel.cpp:204-217) for every tube.
+  std::vector<int32_t> getMostConstrictedSection() {
+    std::vector<afs_tube_frame> f(tubes.size());
+    for (size_t i = 0; i < tubes.size(); i++) f[i] = tubes[i].frame;
+    std::vector<int32_t> sec(f.size(), 0);
+    check(afs_tl_mean_flow(dev_.ctx(), (int)f.size(), f.data(), 0.0, nullptr, sec.data()), dev_.ctx());
+    return sec;
+  }
+  // TlModel::getMeanFlow(lungPressure_dPa) (TlModel.cpp:226-246) for every tube; like the reference it also sets the
+  // lung pressure of the model.
+  std::vector<double> getMeanFlow(double lungPressure_dPa) {
+    std::vector<afs_tube_frame> f(tubes.size());
+    for (size_t i = 0; i < tubes.size(); i++) f[i] = tubes[i].frame;
+    std::vector<double> flow(f.size(), 0.0);
+    check(afs_tl_mean_flow(dev_.ctx(), (int)f.size(), f.data(), lungPressure_dPa, flow.data(), nullptr), dev_.ctx());
+    setLungPressure(lungPressure_dPa);
+    return flow;
+  }
 
   // TlModel::getSpectrum (TlModel.cpp:123-197) for every tube; the bin grid is explicit: bin i at i*f0_hz.
   void getSpectrum(SpectrumType type, ComplexSpectrum *spectrum, double f0_hz, int numFreq, int section) {
@@ -193,7 +227,7 @@ inline std::vector<int16_t> synthesizeVowelsLf(TlModel &tlModel, const std::vect
 inline std::vector<double> playTargetSequences(Device &dev, const afs_tds_options &options, const std::vector<double> &targetShapes,
                                                const double stationary_s[4], const double transition_s[3],
                                                const double glottisControl[AFS_NUM_GLOTTIS_CONTROL], double samplingRate = 22050.0,
-                                               int tdsSrFactor = 2) {
+                                               int tdsSrFactor = 2 /* 1 = the reference as shipped, see TdsSynthesizer */) {
   const int n = (int)(targetShapes.size() / 64);
   std::vector<double> audio((size_t)n * (size_t)afs_target_sequence_length(stationary_s, transition_s, samplingRate), 0.0);
   check(afs_play_target_sequences(dev.ctx(), &options, n, targetShapes.data(), stationary_s, transition_s, glottisControl,
@@ -208,10 +242,23 @@ class TdsSynthesizer {
  public:
   afs_tds_options options;  // TdsModel::options + TriangularGlottis static parameters
   double samplingRate = 22050.0;
-  int tdsSrFactor = 2;  // TDS_SR_FACTOR (Constants.h:25): simulation at 44.1 kHz
+  // Simulation rate = tdsSrFactor * samplingRate.  The reference ships TDS_SR_FACTOR = 1 (Constants.h:25: TDS at
+  // 22.05 kHz); 2 -- a simulation at 44.1 kHz, the configuration BASELINE.json is quoted on -- is the default HERE.
+  // Set it to 1 for the audio of an unmodified reference build.
+  int tdsSrFactor = 2;
 
-  TdsSynthesizer(Device &dev, int numUtterances) : dev_(dev), n_(numUtterances) { afs_tds_options_default(&options); }
+  TdsSynthesizer(Device &dev, int numUtterances) : dev_(&dev), n_(numUtterances) { afs_tds_options_default(&options); }
+  // the same over several devices (contiguous shards of the utterances)
+  TdsSynthesizer(DeviceGroup &group, int numUtterances) : group_(&group), n_(numUtterances) { afs_tds_options_default(&options); }
   void resetMotion() { tubes_.clear(); glottis_.clear(); frameLen_.clear(); frames_ = 0; }
+  // TdsModel::setFlowSource(flow_cm3_s, section) (TdsModel.cpp:629-633); section -1 switches it off.
+  void setFlowSource(double flow_cm3_s, int section) { options.flow_source_cm3_s = flow_cm3_s; options.flow_source_section = section; }
+  // Taps for the next flush(): TdsModel::getSectionPressure / getSectionFlow (TdsModel.cpp:1715-1734) of these tube
+  // sections after every simulation step; read them with sectionPressure() / sectionInflow() / sectionOutflow().
+  void setProbeSections(const std::vector<int> &sections) { probeSections_ = sections; }
+  const std::vector<double> &sectionPressure() const { return probeP_; }  // [n][sections][steps]
+  const std::vector<double> &sectionInflow() const { return probeIn_; }
+  const std::vector<double> &sectionOutflow() const { return probeOut_; }
 
   // One control frame for ALL utterances: newTubes[n], newGlottisParams[n][6].  The first call primes (returns
   // without producing samples, Synthesizer.cpp:522-532); later calls append numNewSamples output samples.
@@ -238,14 +285,32 @@ class TdsSynthesizer {
     audio->assign((size_t)n_ * n_out, 0.0);
     if (flow) flow->assign((size_t)n_ * n_out * tdsSrFactor, 0.0);
     if (status) status->assign((size_t)n_, 0u);
-    check(afs_tds_synthesize(dev_.ctx(), &options, n_, frames_, frameLen_.data(), t.data(), g.data(),
-                             samplingRate * tdsSrFactor, tdsSrFactor, nullptr, audio->data(),
-                             flow ? flow->data() : nullptr, status ? status->data() : nullptr), dev_.ctx());
+    if (group_) {
+      if (!probeSections_.empty()) throw Error(AFS_ERR_UNSUPPORTED, "taps are a single-device feature");
+      check(afs_group_tds_synthesize(group_->group(), &options, n_, frames_, frameLen_.data(), t.data(), g.data(),
+                                     samplingRate * tdsSrFactor, tdsSrFactor, nullptr, audio->data(),
+                                     flow ? flow->data() : nullptr, status ? status->data() : nullptr));
+    } else {
+      afs_tds_probes pr;
+      pr.n_probes = (int32_t)probeSections_.size();
+      if (pr.n_probes > AFS_MAX_TDS_PROBES) throw Error(AFS_ERR_BAD_ARGUMENT, "too many probe sections");
+      const size_t pn = (size_t)n_ * probeSections_.size() * n_out * (size_t)tdsSrFactor;
+      probeP_.assign(pn, 0.0); probeIn_.assign(pn, 0.0); probeOut_.assign(pn, 0.0);
+      for (int q = 0; q < pr.n_probes; q++) pr.section[q] = probeSections_[(size_t)q];
+      pr.pressure_dPa = probeP_.data(); pr.inflow_cm3_s = probeIn_.data(); pr.outflow_cm3_s = probeOut_.data();
+      check(afs_tds_synthesize_probed(dev_->ctx(), &options, n_, frames_, frameLen_.data(), t.data(), g.data(),
+                                      samplingRate * tdsSrFactor, tdsSrFactor, nullptr, audio->data(),
+                                      flow ? flow->data() : nullptr, status ? status->data() : nullptr,
+                                      pr.n_probes ? &pr : nullptr), dev_->ctx());
+    }
     resetMotion();
   }
 
  private:
-  Device &dev_;
+  Device *dev_ = nullptr;
+  DeviceGroup *group_ = nullptr;
+  std::vector<int> probeSections_;
+  std::vector<double> probeP_, probeIn_, probeOut_;
   int n_;
   int frames_ = 0;
   std::vector<afs_tube_frame> tubes_;

@@ -63,6 +63,29 @@ int main() {
     double e = 0;
     for (double v : audio) e += v * v;
     std::printf("audio %zu %.12e status %u\n", audio.size(), e, status[0] | status[1]);
+    // --- TdsModel::setFlowSource / getSectionPressure / getSectionFlow, TlModel::getMeanFlow ---
+    syn.setFlowSource(50.0, 30);
+    syn.setProbeSections({24, 40});
+    syn.synthesizeSignalTds(tubes, g, 200);
+    syn.synthesizeSignalTds(tubes, g, 200);
+    syn.flush(&audio);
+    double ep = 0, ei = 0;
+    for (double v : syn.sectionPressure()) ep += v * v;
+    for (size_t i = 0; i < syn.sectionInflow().size(); i++) ei += syn.sectionInflow()[i] * syn.sectionOutflow()[i];
+    std::printf("probes %zu %.12e %.12e\n", syn.sectionPressure().size(), ep, ei);
+    const std::vector<double> mf = tl.getMeanFlow(8000.0);
+    const std::vector<int32_t> mc = tl.getMostConstrictedSection();
+    std::printf("meanflow %.17g %d\n", mf[0], mc[0]);
+    // --- the same utterances over every visible device (afs_group) ---
+    afs::DeviceGroup grp;
+    afs::TdsSynthesizer gsyn(grp, 2);
+    gsyn.synthesizeSignalTds(tubes, g, 1102);
+    gsyn.synthesizeSignalTds(tubes, g, 1102);
+    std::vector<double> gaudio;
+    gsyn.flush(&gaudio);
+    double ge = 0;
+    for (double v : gaudio) ge += v * v;
+    std::printf("group %d %zu %.12e\n", grp.size(), gaudio.size(), ge);
   } catch (const afs::Error &err) {
     std::printf("error %d %s\n", err.status, err.what());
     return err.status == AFS_ERR_NO_DEVICE ? 0 : 2;

@@ -61,3 +61,15 @@ def test_facade_matches_ctypes_path(ctx, shapes):
     a, _, st = ctx.tds_synthesize(np.stack([fr, fr], axis=1), gl, [1102], 44100.0, 2)
     assert int(lines["audio"][0]) == a.size and int(lines["audio"][3]) == 0
     assert abs(float(lines["audio"][1]) - float((a ** 2).sum())) <= 1e-9 * float((a ** 2).sum())
+    # setFlowSource + taps, getMeanFlow, the device group
+    o = afs.tds_options_default(); o.flow_source_section = 30; o.flow_source_cm3_s = 50.0
+    a2, _, taps = ctx.tds_synthesize_probed(np.stack([fr, fr], axis=1), gl, [200], [24, 40], opts=o)
+    assert int(lines["probes"][0]) == taps["pressure"].size
+    ep, ei = float((taps["pressure"] ** 2).sum()), float((taps["inflow"] * taps["outflow"]).sum())
+    assert abs(float(lines["probes"][1]) - ep) <= 1e-9 * ep and abs(float(lines["probes"][2]) - ei) <= 1e-9 * abs(ei)
+    mf, mc = ctx.tl_mean_flow(fr[:1], 8000.0)
+    assert float(lines["meanflow"][0]) == mf[0] and int(lines["meanflow"][1]) == mc[0]
+    a3, _, _ = ctx.tds_synthesize(np.stack([fr, fr], axis=1), gl, [1102], 44100.0, 2)  # default options, default seed
+    import torch
+    assert int(lines["group"][0]) == torch.cuda.device_count() and int(lines["group"][1]) == a3.size
+    assert abs(float(lines["group"][2]) - float((a3 ** 2).sum())) <= 1e-12 * float((a3 ** 2).sum())

@@ -53,3 +53,48 @@ def test_two_rank_gloo_gather(n_units):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+@pytest.mark.gpu
+def test_device_group_equals_single_device(shapes):
+    """afs_group_*: the C-ABI multi-device layer (one process, one host thread per device, contiguous shards, every
+    device writing its rows of the caller's arrays).  Bit-identical to the single-device call on every visible
+    device count, ragged shards included; the shard rule is sharding.shard_bounds'."""
+    import torch
+    import areafunctionsynthesis_b200 as afs
+    from areafunctionsynthesis_b200.sharding import shard_bounds
+    n_dev = torch.cuda.device_count()
+    names = shapes["names"]
+    rng = np.random.default_rng(11)
+    B = 301  # ragged over 2, 4 and 8 devices
+    idx = rng.integers(0, 16, size=(B, 2))
+    fr = shapes["frames"][idx].copy()
+    fr["velum_area_cm2"] = rng.random((B, 2)) * 0.5
+    gl = np.tile(np.array([120.0, 8000.0, 0.01, 0.01, 0.0, -40.0]), (B, 2, 1))
+    gl[:, :, 0] = rng.uniform(90, 220, size=(B, 2))
+    seeds = rng.integers(1, 2**31 - 1, size=B).astype(np.uint32)
+    one = afs.Context(0)
+    a1, f1, s1 = one.tds_synthesize(fr, gl, [120], 44100.0, 2, seeds=seeds, want_flow=True)
+    re1, im1 = one.tl_sweep(fr[:, 0], 22050.0 / 2048, 512)
+    one.close()
+    for devices in (None, [0], list(range(n_dev))[::-1]):
+        g = afs.Group(devices)
+        G = len(g)
+        assert G == (n_dev if devices is None else len(devices))
+        assert [g.shard(B, r) for r in range(G)] == shard_bounds(B, G)
+        a, f, s = g.tds_synthesize(fr, gl, [120], 44100.0, 2, seeds=seeds, want_flow=True)
+        assert np.array_equal(a, a1) and np.array_equal(f, f1) and np.array_equal(s, s1)
+        re, im = g.tl_sweep(fr[:, 0], 22050.0 / 2048, 512)
+        assert np.array_equal(re, re1) and np.array_equal(im, im1)
+        # fewer units than devices, empty batch, pinned output
+        a, _, _ = g.tds_synthesize(fr[:1], gl[:1], [120], 44100.0, 2, seeds=seeds[:1])
+        assert np.array_equal(a, a1[:1])
+        a, _, _ = g.tds_synthesize(fr[:0], gl[:0], [120], 44100.0, 2)
+        assert a.shape == (0, 120)
+        pin = afs.pinned_empty((B, 120))
+        g.tds_synthesize(fr, gl, [120], 44100.0, 2, seeds=seeds, audio=pin)
+        assert np.array_equal(pin, a1)
+        afs.pinned_free(pin)
+        g.close()
+    with pytest.raises(afs.AfsError):
+        afs.Group([0, 0])

@@ -235,7 +235,7 @@ def test_noise_sources_against_oracle(ctx, oracle, shapes):
     assert np.array_equal(a[perm], a2)
 
 
-def test_noise_sum_ring_overflow(ctx, oracle, shapes, monkeypatch):
+def test_noise_sum_ring_overflow(ctx, oracle, shapes):
     """The sums of twelve rand() draws are generated ahead of time into a per-tract ring (28 entries); a step that
     draws more samples than the ring holds takes the rest straight from the generator, in the reference's order.
     Forced here with a ring of 4 (consonant transitions draw 5-12 samples per step): bit-identical to the run with
@@ -253,9 +253,11 @@ def test_noise_sum_ring_overflow(ctx, oracle, shapes, monkeypatch):
     fl = [700, 500]
     on = afs.tds_options_default(noise=True)
     a0, u0, st0 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
-    monkeypatch.setenv("AFS_NOISE_RING_ENTRIES", "4")
-    a1, u1, st1 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
-    monkeypatch.delenv("AFS_NOISE_RING_ENTRIES")
+    ctx.debug_set("tds.noise_ring_entries", 4)
+    try:
+        a1, u1, st1 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
+    finally:
+        ctx.debug_set("tds.noise_ring_entries", 0)
     assert not st0.any() and not st1.any()
     assert np.array_equal(a0, a1) and np.array_equal(u0, u1)
     ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=oracle_opts(noise=True), seeds=seeds)
@@ -293,7 +295,7 @@ def test_transvelar_coupling_and_variable_entrance_loss(ctx, oracle, shapes, tv,
         assert rel_err(ao[:4], a0) > 1e-3
 
 
-def test_noise_prepass_waves(ctx, shapes, monkeypatch):
+def test_noise_prepass_waves(ctx, shapes):
     """The constriction records of the noise pre-pass live in a bounded device buffer; a batch that does not fit runs
     as several waves of CTAs.  Forced here with a tiny budget: results identical to the single-wave run, and to the
     same utterances run one by one (every tract depends on its own inputs and seed only)."""
@@ -310,9 +312,11 @@ def test_noise_prepass_waves(ctx, shapes, monkeypatch):
     a0, _, st0 = ctx.tds_synthesize(fr, gl, [150], 44100.0, 2, opts=o, seeds=seeds)
     assert not st0.any() and np.abs(a0).max() > 0
     per_cta = 300 * 4 * 32 * 12  # record bytes of one CTA for 300 steps
-    monkeypatch.setenv("AFS_NOISE_SCAN_BYTES", str(per_cta * 37))  # 37 CTAs per wave -> 4 waves
-    a1, _, st1 = ctx.tds_synthesize(fr, gl, [150], 44100.0, 2, opts=o, seeds=seeds)
-    monkeypatch.delenv("AFS_NOISE_SCAN_BYTES")
+    ctx.debug_set("tds.noise_scan_bytes", per_cta * 37)  # 37 CTAs per wave -> 4 waves
+    try:
+        a1, _, st1 = ctx.tds_synthesize(fr, gl, [150], 44100.0, 2, opts=o, seeds=seeds)
+    finally:
+        ctx.debug_set("tds.noise_scan_bytes", 0)
     assert np.array_equal(a0, a1) and not st1.any()
     for b in (0, 4, 5, 699):
         ab, _, _ = ctx.tds_synthesize(fr[b:b + 1], gl[b:b + 1], [150], 44100.0, 2, opts=o, seeds=seeds[b:b + 1])
@@ -390,3 +394,31 @@ def test_flow_source_and_probes_against_oracle(ctx, oracle, shapes, noise):
         ctx.tds_synthesize(fr[:1], gl[:1], fl, 44100.0, 2, opts=bad)
     with pytest.raises(afs.AfsError):
         ctx.tds_synthesize_probed(fr[:1], gl[:1], fl, [93], opts=afs.tds_options_default())
+
+
+def test_host_call_overlapped_copies_equal_device_path(ctx, shapes):
+    """afs_tds_synthesize copies finished time slices (batches of up to one CTA per SM) or finished waves of CTAs
+    (larger batches) to the host while the kernel runs; the result must be the device-resident path's, bit for bit,
+    for pinned and for pageable host buffers."""
+    import torch
+    import areafunctionsynthesis_b200 as afs
+    for B, n_out in ((600, 2000), (148 * 28 + 300, 300)):   # time-slice mode / wave mode (more CTAs than SMs)
+        fr, gl, _ = _vowel_transitions(shapes, B, 5 + B, nasal=True)
+        seeds = np.arange(B, dtype=np.uint32) + 3
+        for noise in (False, True):
+            o = afs.tds_options_default(noise=noise)
+            d_fr = torch.from_numpy(fr.view(np.uint8).reshape(B, -1)).cuda()
+            d_gl = torch.from_numpy(gl).cuda()
+            d_seeds = torch.from_numpy(seeds.view(np.int32)).cuda()
+            d_a = torch.zeros(B, n_out, dtype=torch.float64, device="cuda")
+            ctx.tds_synthesize_device(d_fr, d_gl, B, 2, [n_out], d_a, torch.cuda.current_stream().cuda_stream, opts=o, d_seeds=d_seeds)
+            torch.cuda.synchronize()
+            a, _, st = ctx.tds_synthesize(fr, gl, [n_out], 44100.0, 2, opts=o, seeds=seeds)   # pageable
+            assert not st.any() and np.array_equal(a, d_a.cpu().numpy()), (B, noise)
+            h_a = torch.zeros(B, n_out, dtype=torch.float64).pin_memory()
+            h_fr = torch.from_numpy(fr.view(np.uint8).reshape(B, -1).copy()).pin_memory()
+            h_gl = torch.from_numpy(gl.copy()).pin_memory()
+            fl = np.array([n_out], dtype=np.int32)
+            rc = ctx.lib.afs_tds_synthesize(ctx.h, afs.api.C.byref(o), B, 2, fl.ctypes.data, h_fr.data_ptr(), h_gl.data_ptr(),
+                                            44100.0, 2, seeds.ctypes.data, h_a.data_ptr(), None, None)
+            assert rc == 0 and torch.equal(h_a, d_a.cpu()), (B, noise)
