@@ -64,7 +64,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(HERE, "libafs_b200.so")
+    # (AFS_LIB: an instrumented build of the same library, profiling tools only)
+    return os.environ.get("AFS_LIB") or os.path.join(HERE, "libafs_b200.so")
 
 
 def load_library():

@@ -12,8 +12,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libafs_b200.so")
-OBJ = os.path.join(HERE, "build")
+# (profiling builds: AFS_TDS_TIMING=1 AFS_LIB_TAG=_timing python -m areafunctionsynthesis_b200.build --force writes
+#  libafs_b200_timing.so beside the product library; tools/tds_timing.py loads it through AFS_LIB)
+TAG = os.environ.get("AFS_LIB_TAG", "")
+LIB = os.path.join(HERE, f"libafs_b200{TAG}.so")
+OBJ = os.path.join(HERE, "build" + TAG)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

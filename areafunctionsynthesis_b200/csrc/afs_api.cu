@@ -33,7 +33,8 @@ struct afs_ctx {
   unsigned int *progress_h = nullptr, *progress_d = nullptr;
   // test hooks (afs_debug_set)
   int64_t dbg_noise_scan_bytes = 0;
-  int dbg_noise_ring_entries = 0;
+  int dbg_d2h_slices = 0;
+  int run_pool_factor = 32;   // records of the noise pre-pass pool per piece (see tds_run_device); grows on overflow
 };
 static constexpr int kMaxProgressCtas = 4096;
 
@@ -802,12 +803,14 @@ int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int 
   if (!d_tubes || !d_glottis || !d_audio) return AFS_ERR_BAD_ARGUMENT;
 
   TdsLaunch L;
-  rc = tds_prepare_launch(opts, n_tracts, n_frames, frame_len, fs_tds_hz, sr_factor, ctx->sm_count,
-                          ctx->dbg_noise_ring_entries, &L);
+  rc = tds_prepare_launch(opts, n_tracts, n_frames, frame_len, fs_tds_hz, sr_factor, ctx->sm_count, &L);
   if (rc) return rc;
   // everything below the caller's buffers is a stream-ordered temporary (see afs_ctx::pool)
-  void *d_bounds = nullptr, *d_dump = nullptr, *d_nzc = nullptr;
-  auto release = [&]() { pool_free(d_bounds, stream); pool_free(d_dump, stream); pool_free(d_nzc, stream); };
+  void *d_bounds = nullptr, *d_dump = nullptr, *d_nzc = nullptr, *d_runs = nullptr, *d_off = nullptr, *d_items = nullptr;
+  auto release = [&]() {
+    pool_free(d_bounds, stream); pool_free(d_dump, stream); pool_free(d_nzc, stream);
+    pool_free(d_runs, stream); pool_free(d_off, stream); pool_free(d_items, stream);
+  };
   if ((rc = pool_alloc(ctx, sizeof(int32_t) * (size_t)(n_frames + 1), stream, &d_bounds))) return rc;
   // (pageable source: staged before the call returns)
   cudaError_t e = cudaMemcpyAsync(d_bounds, L.step_bounds.data(), sizeof(int32_t) * (size_t)n_frames, cudaMemcpyHostToDevice, stream);
@@ -816,7 +819,36 @@ int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int 
     if ((rc = pool_alloc(ctx, 473 * sizeof(double), stream, &d_dump))) { release(); return rc; }
     cudaMemsetAsync(d_dump, 0, 473 * sizeof(double), stream);
   }
-  // Noise sources: the constriction records of the pre-pass (48 B per tract-step, 32 lanes per CTA); a batch whose
+  // Noise sources, control frames far apart: one record per run of steps with the same constrictions.  Two passes of
+  // the bisection kernel -- count, then write at the offsets derived from the counts (the one host round trip of
+  // the call: 4 B per tract each way).
+  // Noise sources, control frames far apart: one record per run of steps with the same constrictions, found by
+  // bisection (tds_noise_runs_kernel), kept as linked lists in one pool.  The pool is sized from the number of
+  // pieces (every piece starts with a record) times run_pool_factor; a pool that turns out too small is reported
+  // as status bit 1 of every tract (the host-buffer entry point then repeats the call with a larger one).
+  int run_items = 0;
+  if (opts->generate_noise_sources && tds_noise_runs_mode(L)) {
+    std::vector<int32_t> items, iv_first;
+    tds_noise_run_items(L, &items, &iv_first);
+    run_items = (int)(items.size() / 4);
+    items.insert(items.end(), iv_first.begin(), iv_first.end());  // one upload: the pieces, then the per-interval table
+    const size_t n_slots = (size_t)n_tracts * (size_t)run_items;
+    size_t pool = n_slots * (size_t)ctx->run_pool_factor + 4096;
+    if (pool > 0xfffffff0ull) pool = 0xfffffff0ull;
+    if (n_slots >= pool) { release(); return AFS_ERR_OUT_OF_MEMORY; }
+    if ((rc = pool_alloc(ctx, sizeof(int32_t) * items.size(), stream, &d_items))) { release(); return rc; }
+    if ((rc = pool_alloc(ctx, 2 * sizeof(uint32_t), stream, &d_off))) { release(); return rc; }
+    if ((rc = pool_alloc(ctx, tds_noise_run_bytes() * pool, stream, &d_runs))) { release(); return rc; }
+    const uint32_t ctl0[2] = {(uint32_t)n_slots, 0u};
+    e = cudaMemcpyAsync(d_items, items.data(), sizeof(int32_t) * items.size(), cudaMemcpyHostToDevice, stream);  // (pageable: staged)
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, ctl0, sizeof ctl0, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+      e = launch_noise_runs(L, run_items, d_items, (const int32_t *)d_items + (size_t)run_items * 4, (const int32_t *)d_bounds,
+                            d_tubes, d_runs, (uint32_t)pool, (uint32_t *)d_off, stream);
+    if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "noise pre-pass"); }
+    ctx->launches++;
+  }
+  // Noise sources, control frames a few steps apart: one record per tract-step (48 B, 32 lanes per CTA); a batch whose
   // records would not fit the budget runs as several waves of CTAs that reuse the buffer.
   const size_t per_cta = tds_noise_scan_bytes_per_cta(L);
   const int lpc = tds_lanes_per_cta(L);
@@ -843,7 +875,7 @@ int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int 
     const int t0 = c0 * lpc;
     const int nw = (c0 + wave_ctas >= ctas) ? n_tracts - t0 : wave_ctas * lpc;
     e = launch_tds(L, t0, nw, (const int32_t *)d_bounds, d_tubes, d_glottis, d_seeds, d_audio, d_flow, d_status,
-                   c0 == 0 ? (double *)d_dump : nullptr, ctx->dump_step, d_nzc, d_probes,
+                   c0 == 0 ? (double *)d_dump : nullptr, ctx->dump_step, d_nzc, d_runs, (const uint32_t *)d_off, run_items, d_probes,
                    single ? d_progress : nullptr, single ? progress_every : 0, stream);
     if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "launch_tds"); }
     ctx->launches += per_cta ? 2 : 1;
@@ -889,7 +921,8 @@ int afs_debug_set(afs_ctx *ctx, const char *key, int64_t value) {
   if (!ctx) return AFS_ERR_BAD_CONTEXT;
   if (!key) return AFS_ERR_BAD_ARGUMENT;
   if (!strcmp(key, "tds.noise_scan_bytes")) ctx->dbg_noise_scan_bytes = value;
-  else if (!strcmp(key, "tds.noise_ring_entries")) ctx->dbg_noise_ring_entries = (int)value;
+  else if (!strcmp(key, "tds.d2h_slices")) ctx->dbg_d2h_slices = (int)value;
+  else if (!strcmp(key, "tds.noise_run_pool_factor")) ctx->run_pool_factor = value < 2 ? 2 : value > 4096 ? 4096 : (int)value;
   else return AFS_ERR_BAD_ARGUMENT;
   return AFS_OK;
 }
@@ -954,6 +987,7 @@ int afs_tds_synthesize_probed(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   // time slices: worth it from a few MB of audio on; the progress marks are in simulation steps
   const size_t total_steps = n_out * (size_t)sr_factor;
   int n_slices = ab >= ((size_t)8 << 20) && n_out >= 64 ? 16 : 1;
+  if (ctx->dbg_d2h_slices > 0) n_slices = ctx->dbg_d2h_slices;
   const size_t slice_out = (n_out + (size_t)n_slices - 1) / (size_t)n_slices;
   const int every = n_slices > 1 && total_steps < 0x7fffffffull ? (int)(slice_out * (size_t)sr_factor) : 0;
   if (every) memset(ctx->progress_h, 0, kMaxProgressCtas * sizeof(unsigned int));
@@ -999,7 +1033,10 @@ int afs_tds_synthesize_probed(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   else e = cudaMemcpy2DAsync(audio + copied, n_out * sizeof(double), (const double *)d_audio + copied, n_out * sizeof(double),
                              (n_out - copied) * sizeof(double), (size_t)n_tracts, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess && flow) e = cudaMemcpyAsync(flow, d_flow, fb, cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_status, (size_t)n_tracts * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  std::vector<uint32_t> status_tmp;
+  uint32_t *status_h = status;
+  if (!status_h && opts->generate_noise_sources) { status_tmp.resize((size_t)n_tracts); status_h = status_tmp.data(); }
+  if (e == cudaSuccess && status_h) e = cudaMemcpyAsync(status_h, d_status, (size_t)n_tracts * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess && use) {
     if (dp.pressure_dPa) e = cudaMemcpyAsync(probes->pressure_dPa, dp.pressure_dPa, pb, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && dp.inflow_cm3_s) e = cudaMemcpyAsync(probes->inflow_cm3_s, dp.inflow_cm3_s, pb, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1010,6 +1047,12 @@ int afs_tds_synthesize_probed(afs_ctx *ctx, const afs_tds_options *opts, int n_t
   if (e != cudaSuccess) return cuda_fail(ctx, e, "device-to-host copies");
   if (e1 != cudaSuccess) return cuda_fail(ctx, e1, "cudaStreamSynchronize(copy stream)");
   if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "cudaStreamSynchronize");
+  // status bit 1: the record pool of the noise pre-pass was too small (tds_run_device) -- once more with a larger one
+  if (status_h && opts->generate_noise_sources && (status_h[0] & 2u) && ctx->run_pool_factor < 4096) {
+    ctx->run_pool_factor *= 8;
+    return afs_tds_synthesize_probed(ctx, opts, n_tracts, n_frames, frame_len, tubes, glottis, fs_tds_hz, sr_factor, seeds,
+                                     audio, flow, status, probes);
+  }
   return AFS_OK;
 }
 

@@ -57,13 +57,22 @@ struct TdsLaunch {
   int n_tracts = 0, n_frames = 0;
 };
 int tds_prepare_launch(const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
-                       double fs_tds_hz, int sr_factor, int sm_count, int ring_entries, TdsLaunch *L);
+                       double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L);
 cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
-                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const afs_tds_probes *d_probes,
-                       unsigned int *d_progress, int progress_every, cudaStream_t stream);
+                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const void *d_runs,
+                       const uint32_t *d_run_ctl, int run_items, const afs_tds_probes *d_probes, unsigned int *d_progress,
+                       int progress_every, cudaStream_t stream);
+// noise pre-pass in runs mode (control frames far apart)
+bool tds_noise_runs_mode(const TdsLaunch &L);
+size_t tds_noise_run_bytes();
+// items4: {interval, first step, last step, next first step} per piece; iv_first: first piece of every interval, then the total
+void tds_noise_run_items(const TdsLaunch &L, std::vector<int32_t> *items4, std::vector<int32_t> *iv_first);
+cudaError_t launch_noise_runs(const TdsLaunch &L, int n_items, const void *d_items, const int32_t *d_iv_first,
+                              const int32_t *d_bounds, const afs_tube_frame *d_tubes, void *d_runs, uint32_t pool_records,
+                              uint32_t *d_ctl, cudaStream_t stream);
 int tds_total_steps(const TdsLaunch &L);
-size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L);  // 0 without noise sources
+size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L);  // per-step records; 0 without noise sources or in runs mode
 int tds_lanes_per_cta(const TdsLaunch &L);
 size_t tds_smem_bytes();
 

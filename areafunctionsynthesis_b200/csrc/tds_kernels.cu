@@ -49,6 +49,12 @@
 
 #include "afs_internal.h"
 
+#ifdef AFS_TDS_TIMING
+#define SW_TICK(k) do { const long long now__ = clock64(); sw_t[k] += now__ - sw_last; sw_last = now__; } while (0)
+#else
+#define SW_TICK(k) do { } while (0)
+#endif
+
 namespace afs {
 
 constexpr int LANES = 28;                     // tracts per CTA = row length of the [item][lane] arrays (224 B).  4096
@@ -60,12 +66,9 @@ constexpr int TDS_THREADS = NW * 32;
 constexpr int KD = 6;                         // sections per dynamic-chain warp
 constexpr int NSX = NS + 1;                   // + one all-zero dummy section (index 93)
 constexpr double kTheta = 0.515;              // TdsModel.cpp:15
-#ifndef AFS_NZ_RING
-#define AFS_NZ_RING 28
-#endif
-constexpr int NZ_RING = AFS_NZ_RING;          // pre-generated noise sums per tract (even; more draws in one step fall
-                                              // back to in-line generation on warp X2)
-static_assert(NZ_RING % 2 == 0 && NZ_RING >= 4 && NZ_RING <= 64, "NZ_RING");
+constexpr int NZ_RING = 44;                   // pre-generated noise sums per tract: a step draws at most 41 (40 pharynx /
+                                              // mouth sources + the lips) and the refill leaves at most 2 entries empty
+static_assert(NZ_RING >= 41 + 2 && NZ_RING <= 255, "NZ_RING");
 constexpr double kTheta1 = 1.0 - kTheta;
 
 // Warp roles.  The id also fixes the SM sub-partition (id % 4); the order balances the FP64 work of the four.
@@ -74,7 +77,9 @@ constexpr double kTheta1 = 1.0 - kTheta;
 //   static chains:  T0 0..7, T1 8..15, T2 16..22 (trachea), N1 71..75 (+ sinuses 89, 90), N2 76..83 (+ sinuses
 //                   91, 92), F 84..88 (piriform fossa; + the radiation currents 93..96)
 //   X1 glottis model + output filters (+ half of the noise-source stage), X2 radiation loads + noise sources
-enum { W_GP = 0, W_P1, W_P2, W_M0, W_M1, W_M2, W_M3, W_NV, W_T0, W_T1, W_N2, W_T2, W_X1, W_F, W_X2, W_N1 };
+// (the two auxiliary warps come last: the arrays indexed by segment have NSEG = 14 rows)
+enum { W_GP = 0, W_P1, W_P2, W_M0, W_M1, W_M2, W_M3, W_NV, W_T0, W_T1, W_N2, W_T2, W_F, W_N1, W_X1, W_X2 };
+constexpr int NSEG = 14;
 // separators of the partition (last current of every segment + the first currents of the branches)
 enum { S7 = 0, S15, S22, S28, S29, S34, S40, S41, S46, S52, S58, S64, S65, S70, S75, S83, NSEP };
 // uext[]: solution of the first current of every warp's segment (index = warp id) + radiated flows + zero
@@ -86,7 +91,6 @@ struct TdsParams {
   int dump_step;
   int noise;                        // generate_noise_sources (TdsModel.h:87)
   double nz_F, nm_a, nm_1a;         // 1 - exp(-2 pi 40 dt) (TdsModel.cpp:1637), exp(-2 pi 500 dt) and 1 - that (:2052)
-  int nz_ring;                      // entries of the ring of pre-generated noise sums in use (<= NZ_RING)
   double nz_x2000;                  // exp(-2 pi 2000 dt): low-pass coefficient of a source at the upper cutoff limit
   double dt, idt, th, dtth, dtth1;  // 1/fs, 1/(dt*theta), theta1/theta, dt*theta, dt*theta1
   double ith, fs;                   // theta/theta1, fs
@@ -127,11 +131,11 @@ struct TdsSmem {
   double gctl[2][AFS_NUM_GLOTTIS_CONTROL][LANES];
   double glLen[2][2][LANES], glArea[2][2][LANES];  // glottis geometry, double buffered by step parity
   // boundary record of every segment = its LAST section, for the first row of the next segment
-  double bE[NW][LANES], bL[NW][LANES], bR[NW][LANES], bI[NW][LANES], bG[NW][LANES], bD[NW][LANES];
+  double bE[NSEG][LANES], bL[NSEG][LANES], bR[NSEG][LANES], bI[NSEG][LANES], bG[NSEG][LANES], bD[NSEG][LANES];
   double csib[4][LANES];                         // history term c of the branch heads 29, 84, 41, 65 (sibling rows)
   double sepD[NSEP][LANES], sepR[NSEP][LANES], redW[NSEP][LANES];
   double redC[2][LANES];                         // fill couplings 29 <-> 40 and 41 <-> 52 of the reduced system
-  double sideDD[NW][LANES], sideDR[NW][LANES], sideF[NW][LANES];
+  double sideDD[NSEG][LANES], sideDR[NSEG][LANES], sideF[NSEG][LANES];
   double lf[5][LANES];                           // fossa current 84 folded into the clique {28, 29}
   double radc[2][2][LANES];                      // radiation pairs folded into currents 64 / 83
   double uext[NUX][LANES];
@@ -144,25 +148,22 @@ struct TdsSmem {
   // pharynx/mouth sections 25..64, 40 = lips; nmag: j = current - 25 for the currents 25..65, 41 = current 84.
   double nmag[42][LANES];                        // noiseMagnitude (TdsModel.h:143) of the currents a constriction can feed
   double namp[41][LANES], ncut[41][LANES], nout[41][LANES];  // currentAmp, cutoff, last filter output (TdsModel.h:101-112)
-  // the source stage is shared by warps X2 and X1 (noise_stage): live sources and the sources that draw a sample
-  // this step, [0] = X2's share, [1] = X1's
-  unsigned long long nzlive[2][LANES], nzdraw[2][LANES];
+  // prepared by warp X1 for the vocal-fold constriction of the NEXT step, next to the glottis geometry: sqrt(A) / A^3
+  // of the upper glottis area and the downstream factor (see noise_stage)
+  double nzk0[2][LANES];
+  unsigned long long nzdecay[LANES];             // decaying sources (nothing feeds them this step) that are still audible
+  unsigned long long nztongue[LANES];            // sources fed by the tongue / lip constrictions that are audible
   double nzlip[LANES];                           // noiseMagnitude of the flow through the lips (currents 93 + 94)
   // glibc random() TYPE_3 (r[i] = r[i-3] + r[i-31]) in a ring of 36 = 3 x 12 words: the twelve draws of one noise
   // sample never wrap inside the ring and three samples bring it back to the same phase (static addresses)
   uint32_t rng[36][LANES];
   uint32_t nzring[LANES];                        // ring of pre-generated sums: head | valid entries << 8 | entries in use << 16 (written by X2)
-  union {
-    struct {                                     // pre-pass kernel only (tds_noise_scan_kernel)
-      double inc[2][LANES];                      // incisor position of the two control frames
-      unsigned char art[AFS_NUM_PM_SECTIONS][LANES];  // articulator of the LEFT control frame (Tube.cpp:452)
-    };
-    uint32_t nzsum[NZ_RING][LANES];              // time loop only: the next sums of twelve rand() draws, generated ahead by X2
-  };
-  // constrictions of the NEXT step, found by warp X1 while the others solve (the scan does not depend on the state):
-  // packed {valid, kind, teeth, lateral, nar + 1, up} and the downstream factor, double buffered by step parity
-  uint32_t nzc_i[2][4][LANES];
-  double nzc_f[2][4][LANES];
+  uint32_t nzsum[NZ_RING][LANES];                // the next sums of twelve rand() draws, generated ahead by X2
+  // The constrictions of the current run of steps (they depend on the geometry only: found by a pre-pass kernel, kept
+  // up to date by warp X1): packed {valid, kind, teeth, lateral, nar + 1, up} and the downstream factor as a function
+  // of the control-frame ratio r, downF = (c0 + r c1) / (c2 + r c3)
+  uint32_t nzc_i[4][LANES];
+  double nzc_c[4][4][LANES];
   // same for all tracts
   SRec srec[NSX];
   double wallc[4][3];             // kalpha*c1, kalpha*c2, kalpha*c3 per wall type; 3 = zeros
@@ -370,9 +371,12 @@ struct StepCtx {
 
 // getSectionPressure / getSectionFlow of section `sec` after a step (TdsModel.cpp:1715-1734): pressure in the centre of
 // the section, volume velocity into and out of it.
-__device__ __forceinline__ void tap_section(const TdsParams &P, const StepCtx &X, int sec, double p, double in, double out) {
-  for (int q = 0; q < P.n_probes; q++) {
-    if (P.probe_sec[q] != sec) continue;
+// (not inlined: taps are rare, and code that is not executed must stay out of the instruction stream of the time loop
+//  -- the kernel lives off its instruction cache)
+__device__ __noinline__ void tap_section(const int n_probes, const int *probe_sec, const StepCtx &X, int sec, double p, double in,
+                                         double out) {
+  for (int q = 0; q < n_probes; q++) {
+    if (probe_sec[q] != sec) continue;
     if (X.tap_p) X.tap_p[q * X.tap_stride] = p;
     if (X.tap_in) X.tap_in[q * X.tap_stride] = in;
     if (X.tap_out) X.tap_out[q * X.tap_stride] = out;
@@ -388,6 +392,7 @@ __device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("
 // noise sources (warps X2 and X1), see noise_scan / noise_stage below
 struct NoiseCons {
   int valid, nar, kind, up, teeth, lateral;  // nar: narrowest section as pharynx/mouth index, -1 = upper glottis
+  int branch;                                // how the obstacle moves with the control-frame ratio (noise_scan)
   double downF;                              // kind: 0 vocal folds, 1 tongue, 2 lower lip
 };
 struct NoiseRegs {
@@ -398,10 +403,23 @@ struct NoiseRegs {
   double asp, gain;       // aspiration strength (dB) the cached vocal-fold source gain belongs to
 };
 
-__device__ __forceinline__ void dump_section(const TdsParams &P, double *dump, int sec, double p, double pr, double wc,
-                                             double u, double c) {
+// One run of steps with the same constrictions (tds_noise_runs_kernel): first step, first step of the tract's next run
+// (0x7fffffff: none), the packed constriction slots and the coefficients of downF(r) = (c0 + r c1) / (c2 + r c3).
+// The records of a tract form a linked list through one pool: the first record of piece p of tract t has the fixed
+// place t * n_pieces + p, the others are taken from the rest of the pool as the bisection finds them.
+struct NzRun {
+  uint32_t start, next;  // first step of this run / of the tract's next run
+  uint32_t slot[4];
+  uint32_t next_idx;     // where the next run's record is
+  uint32_t pad;
+  double coef[4][4];
+};
+static_assert(sizeof(NzRun) == 160, "NzRun layout");
+
+__device__ __noinline__ void dump_section(const double idt, const double ith, double *dump, int sec, double p, double pr, double wc,
+                                          double u, double c) {
   dump[sec] = p; dump[93 + sec] = pr; dump[186 + sec] = wc;
-  dump[279 + sec] = u; dump[376 + sec] = (c - u * P.idt) * P.ith;
+  dump[279 + sec] = u; dump[376 + sec] = (c - u * idt) * ith;
 }
 
 // Pass A: state update with the solution of the previous step (TdsModel.cpp:2046-2098), then elements, E, D
@@ -455,7 +473,7 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
       S.wall[sec][0][lane] = wc; S.wall[sec][1][lane] = wcr; S.wall[sec][2][lane] = wcr2;
       if (k < 3 && sec <= PHAR0) S.p4[sec - TRACHEA_LAST][lane] = p_new;  // sections 23, 24, 25
-      if (OPT && P.n_probes > 0) tap_section(P, X, sec, p_new, u, out);
+      if (OPT && P.n_probes > 0) tap_section(P.n_probes, P.probe_sec, X, sec, p_new, u, out);
     }
     if (rows) {
       // Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350); the index is clamped for the other kinds
@@ -517,6 +535,8 @@ __device__ __noinline__ double fulcher_k_ent(double pressure_dPa, double area_lo
   return k;
 }
 
+__device__ __forceinline__ void dwarp_noise(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st);
+
 // After the barrier: the first row (its source section belongs to another warp), then elimination of the
 // interior currents towards the last one.  `aown`: the first current is itself a separator (branch heads 29, 41, 65).
 template <bool NOISE, bool OPT>
@@ -545,13 +565,7 @@ __device__ __forceinline__ void dwarp_eliminate(const TdsParams &P, TdsSmem &S, 
     st.x[2] -= dD; st.x[3] += dD;
     S.tvflow[lane] = tv;
   }
-  if (NOISE) {  // dipole sources of the pharynx/mouth sections: S = -sample (TdsModel.cpp:1936), sample = out * amp
-#pragma unroll
-    for (int k = 0; k < KD; k++) {
-      const int j = n0 + k - PHAR0;
-      if (j >= 0 && j < AFS_NUM_PM_SECTIONS) st.x[k] = fma(S.nout[j][lane], S.namp[j][lane], st.x[k]);
-    }
-  }
+  if (NOISE) dwarp_noise(P, S, lane, w, st);  // dipole sources of the pharynx/mouth sections
   double f = aown ? -E_0 : -E_A;
   double dc = aown ? st.y[1] : st.y[0], rc = aown ? st.x[1] : st.x[0];
   double dda = 0.0, dra = 0.0;
@@ -709,7 +723,7 @@ __device__ __forceinline__ void static_section(const TdsParams &P, TdsSmem &S, c
     const double ur = fma(u, P.idt, -c);
     c = fma(ur, P.th, u * P.idt);
     const double p_new = fma(E, u - out, D_old);
-    if (OPT && P.n_probes > 0) tap_section(P, X, sec, p_new, u, out);
+    if (OPT && P.n_probes > 0) tap_section(P.n_probes, P.probe_sec, X, sec, p_new, u, out);
     const double pr_new = (p_new - p) * P.idt - pr * P.th;
     const double wc_new = fma(pr_new, r.alpha, beta_old);
     const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
@@ -766,11 +780,6 @@ __device__ __forceinline__ void swarp_pass_a(const TdsParams &P, TdsSmem &S, con
   }
 }
 
-#ifdef AFS_TDS_TIMING
-#define SW_TICK(k) do { const long long now__ = clock64(); sw_t[k] += now__ - sw_last; sw_last = now__; } while (0)
-#else
-#define SW_TICK(k) do { } while (0)
-#endif
 __device__ __forceinline__ void swarp_eliminate(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
                                                 const SCfg &c, SRegs &st, double psrc
 #ifdef AFS_TDS_TIMING
@@ -870,9 +879,9 @@ __device__ __forceinline__ void swarp_dump(const TdsParams &P, TdsSmem &S, const
   if (lane != 0) return;
 #pragma unroll
   for (int k = 0; k < KS; k++)
-    if (k >= c.ks) dump_section(P, dump, c.base + k, st.p[k], st.pr[k], S.wall[c.base + k][0][0], st.x[k], st.c[k]);
+    if (k >= c.ks) dump_section(P.idt, P.ith, dump, c.base + k, st.p[k], st.pr[k], S.wall[c.base + k][0][0], st.x[k], st.c[k]);
   if (c.leaves)
-    for (int j = 0; j < 2; j++) dump_section(P, dump, c.leaf0 + j, st.lp[j], st.lpr[j], S.wall[c.leaf0 + j][0][0], st.lx[j], st.lc[j]);
+    for (int j = 0; j < 2; j++) dump_section(P.idt, P.ith, dump, c.leaf0 + j, st.lp[j], st.lpr[j], S.wall[c.leaf0 + j][0][0], st.lx[j], st.lc[j]);
 }
 __device__ __forceinline__ void dwarp_dump(const TdsParams &P, TdsSmem &S, const int lane, const int w, const DRegs &st,
                                            double *dump) {
@@ -880,7 +889,7 @@ __device__ __forceinline__ void dwarp_dump(const TdsParams &P, TdsSmem &S, const
 #pragma unroll
   for (int k = 0; k < KD; k++) {
     const int sec = 23 + KD * w + k;
-    dump_section(P, dump, sec, st.p[k], st.pr[k], S.wall[sec][0][0], st.x[k], st.c[k]);
+    dump_section(P.idt, P.ith, dump, sec, st.p[k], st.pr[k], S.wall[sec][0][0], st.x[k], st.c[k]);
   }
 }
 
@@ -961,55 +970,40 @@ __device__ __forceinline__ void radiation_back(const TdsParams &P, TdsSmem &S, c
 }
 
 // ==================================================================================
-// Noise sources (pre-pass kernel; warps X2 and X1): TdsModel::calcNoiseSources / calcNoiseSample (TdsModel.cpp:1188-1708)
+// Noise sources (pre-pass kernels; warps X1, X2 and the dynamic chain warps): TdsModel::calcNoiseSources /
+// calcNoiseSample (TdsModel.cpp:1188-1708)
 // ==================================================================================
 // Everything that DECIDES something (which sections form a constriction, where its obstacle is, how many random
 // numbers are drawn) repeats the reference's arithmetic operation by operation (explicit round-to-nearest
 // intrinsics: no FMA contraction, exact divisions), so that the discrete choices and the libc rand() stream are
 // the reference's; amplitudes are smooth functions of the state and follow it to rounding level.
-__device__ __forceinline__ void nzc_store(TdsSmem &S, const int lane, int buf, const NoiseCons (&C)[4]) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    S.nzc_i[buf][k][lane] = (uint32_t)(C[k].valid & 1) | ((uint32_t)(C[k].kind & 3) << 1) | ((uint32_t)(C[k].teeth & 1) << 3) |
-                            ((uint32_t)(C[k].lateral & 1) << 4) | ((uint32_t)(C[k].nar + 1) << 8) | ((uint32_t)C[k].up << 16);
-    S.nzc_f[buf][k][lane] = C[k].downF;
-  }
-}
-__device__ __forceinline__ void nzc_load(const TdsSmem &S, const int lane, int buf, NoiseCons (&C)[4]) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const uint32_t v = S.nzc_i[buf][k][lane];
-    C[k].valid = v & 1; C[k].kind = (v >> 1) & 3; C[k].teeth = (v >> 3) & 1; C[k].lateral = (v >> 4) & 1;
-    C[k].nar = (int)((v >> 8) & 255) - 1; C[k].up = (int)(v >> 16);
-    C[k].downF = S.nzc_f[buf][k][lane];
-  }
-}
-
-// constriction records of step n from the pre-pass (tds_noise_scan_kernel) into the shared-memory buffer `buf`
-struct NzcRec { uint32_t i[4]; double f[4]; };
-template <class KA>
-__device__ __forceinline__ void nzc_fetch_issue(const KA &A, int total_steps, int n, NzcRec &R) {
-  const int hw_lane = threadIdx.x & 31;
-  const size_t base = ((size_t)blockIdx.x * (size_t)total_steps + (size_t)n) * 4;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    R.i[k] = __ldg(A.nzc_i + (base + k) * 32 + hw_lane);
-    R.f[k] = __ldg(A.nzc_f + (base + k) * 32 + hw_lane);
-  }
-}
-__device__ __forceinline__ void nzc_fetch_store(TdsSmem &S, const int lane, int buf, const NzcRec &R) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) { S.nzc_i[buf][k][lane] = R.i[k]; S.nzc_f[buf][k][lane] = R.f[k]; }
-}
-template <class KA>
-__device__ __forceinline__ void nzc_fetch(TdsSmem &S, const KA &A, const int lane, int total_steps, int n, int buf) {
-  NzcRec R;
-  nzc_fetch_issue(A, total_steps, n, R);
-  nzc_fetch_store(S, lane, buf, R);
-}
+//
+// Division of labour:
+//   * pre-pass kernels (state-independent): the constrictions of every step.  They depend on the geometry only, and
+//     the geometry of an interval between two control frames is a LINEAR function of the step: every comparison the
+//     scan makes changes its outcome at most once per interval, so the constrictions are piecewise constant in runs
+//     of steps.  tds_noise_runs_kernel finds the run boundaries by bisection (a few hundred scans per utterance
+//     instead of one per step) and writes one record per run; tds_noise_scan_kernel scans every step (control
+//     frames only a few steps apart, Synthesizer::playTargetSequence style);
+//   * warp X1 keeps the records of the current run in shared memory (nzc_i / nzc_c);
+//   * warp X2, pass A (noise_stage): everything that depends on the state -- flow through the constrictions -> target
+//     amplitudes -> amplitude filters, decay of the sources nothing feeds, one random sample per audible source in
+//     the reference's order; the flow-independent factors are prepared one step ahead beside the solve;
+//   * the chain warps add sample = out * amp of their own sections to the right-hand sides.
 __device__ __forceinline__ uint32_t nzc_pack(const NoiseCons &c) {
   return (uint32_t)(c.valid & 1) | ((uint32_t)(c.kind & 3) << 1) | ((uint32_t)(c.teeth & 1) << 3) | ((uint32_t)(c.lateral & 1) << 4) |
          ((uint32_t)(c.nar + 1) << 8) | ((uint32_t)c.up << 16);
+}
+// the four slot words of a step, with the "a later slot feeds this source as well" bits (5: upstream, 6: downstream)
+__device__ __forceinline__ void nzc_pack4(const NoiseCons (&C)[4], uint32_t (&w)[4]) {
+  constexpr int NPM = AFS_NUM_PM_SECTIONS;
+  unsigned long long later = 0;
+#pragma unroll
+  for (int k = 3; k >= 0; k--) {
+    const int up = C[k].up, down = up < NPM - 1 ? up + 1 : NPM;
+    w[k] = nzc_pack(C[k]) | (uint32_t)((later >> up) & 1ull) << 5 | (uint32_t)((later >> down) & 1ull) << 6;
+    if (C[k].valid) later |= (1ull << up) | (1ull << down);
+  }
 }
 
 // glibc srand() (stdlib/random_r.c, TYPE_3): the reference draws from libc rand() (TdsModel.cpp:1690-1696); every
@@ -1050,18 +1044,10 @@ __device__ __forceinline__ uint32_t rng_block(TdsSmem &S, const int lane) {
   for (int q = 0; q < 12; q++) S.rng[PH + q][lane] = o[q];
   return isum;
 }
-// one sum from whatever phase the generator is in (rare: only when a step draws more samples than the ring holds)
-__device__ __noinline__ uint32_t rng_sum12(TdsSmem &S, const int lane, int &ph) {
-  uint32_t s;
-  if (ph == 12) { s = rng_block<12>(S, lane); ph = 24; }
-  else if (ph == 24) { s = rng_block<24>(S, lane); ph = 0; }
-  else { s = rng_block<0>(S, lane); ph = 12; }
-  return s;
-}
 
 // exp(t) for -0.75 <= t <= 0 (cutoff <= 2000 Hz at fs >= 16.8 kHz): Taylor polynomial of degree 17 (full double
 // accuracy on that range), evaluated by Estrin's scheme -- five dependent levels instead of seventeen: warp X2 runs
-// alone on the critical path of a step, so latency is what counts; libm exp else
+// alone, so latency is what counts; libm exp else
 __device__ __forceinline__ double exp_small(double t) {
   if (t < -0.75) return exp(t);
   const double t2 = t * t, t4 = t2 * t2, t8 = t4 * t4, t16 = t8 * t8;
@@ -1076,15 +1062,28 @@ __device__ __forceinline__ double exp_small(double t) {
 }
 // Tube::interpolate (Tube.cpp:449-466) exactly as the reference rounds it
 __device__ __forceinline__ double nz_lerp(double r1, double a, double r, double b) { return __dadd_rn(__dmul_rn(r1, a), __dmul_rn(r, b)); }
-__device__ __forceinline__ double nz_area(const TdsSmem &S, const int lane, double r, double r1, int j) {
+// (works on the control frames staged in shared memory: TdsSmem in the time loop, ScanFrames in the pre-pass kernels)
+template <class FR>
+__device__ __forceinline__ double nz_area(const FR &S, const int lane, double r, double r1, int j) {
   const double a = nz_lerp(r1, S.fA[0][j][lane], r, S.fA[1][j][lane]);
   return a < kMinArea ? kMinArea : a;
 }
-__device__ __forceinline__ double nz_len(const TdsSmem &S, const int lane, double r, double r1, int j) {
+template <class FR>
+__device__ __forceinline__ double nz_len(const FR &S, const int lane, double r, double r1, int j) {
   return nz_lerp(r1, S.fLen[0][j][lane], r, S.fLen[1][j][lane]);
 }
+
+// Control frames of one interval as the constriction scan needs them, [item][lane] (NL lanes per row).
+template <int NL>
+struct ScanFrames {
+  double fA[2][AFS_NUM_PM_SECTIONS][NL], fLen[2][AFS_NUM_PM_SECTIONS][NL], fLat[2][AFS_NUM_PM_SECTIONS][NL];
+  double inc[2][NL];                              // incisor position of the two control frames
+  unsigned char art[AFS_NUM_PM_SECTIONS][NL];     // articulator of the LEFT control frame (Tube.cpp:452)
+};
+
 // widen a constriction around its narrowest section (TdsModel.cpp:1260-1275 and the copies below it)
-__device__ __forceinline__ void nz_expand(const TdsSmem &S, const int lane, double r, double r1, int idx, int artX,
+template <class FR>
+__device__ __forceinline__ void nz_expand(const FR &S, const int lane, double r, double r1, int idx, int artX,
                                           double minA, int &first, int &last) {
   const double maxA = __dadd_rn(minA, 0.2);
   first = last = idx;
@@ -1093,13 +1092,25 @@ __device__ __forceinline__ void nz_expand(const TdsSmem &S, const int lane, doub
   first++; last--;
 }
 
+// What identifies the OUTCOME of a scan: every index and every yes / no the scan arrived at.  All of them come from
+// comparisons of quantities that are linear in the control-frame ratio (areas, lengths, positions, laterality of ONE
+// section), so a comparison changes its outcome at most once per interval: two steps of an interval with equal
+// signatures enclose steps with that same signature, and the constriction records of those steps differ only in the
+// (smooth) downstream factor.
+struct ScanSig {
+  unsigned long long a, b;
+  __device__ bool operator==(const ScanSig &o) const { return a == o.a && b == o.b; }
+};
+
 // State-independent part: the constrictions of this sample and where their noise sources sit.
-__device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double r, const double r1,
-                                        const afs_tube_frame *fr0, const afs_tube_frame *fr1, const unsigned long long latAlways,
-                                        const unsigned long long latMaybe, NoiseCons (&C)[4]) {
+// C[k].branch tells how the obstacle position moves with r: 0 fixed at 1.5 cm, 1 the incisors, 2 the middle of the
+// section behind the constriction (downF = 1/2), 3 the end of the constriction's last section (downF = 1).
+template <class FR>
+__device__ __noinline__ void noise_scan(const FR &S, const int lane, const double r, const double r1, NoiseCons (&C)[4],
+                                        ScanSig *sig) {
   constexpr int NPM = AFS_NUM_PM_SECTIONS;
 #pragma unroll
-  for (int k = 0; k < 4; k++) { C[k].valid = 0; C[k].nar = -1; C[k].kind = 0; C[k].up = 0; C[k].teeth = 0; C[k].lateral = 0; C[k].downF = 0.0; }
+  for (int k = 0; k < 4; k++) { C[k].valid = 0; C[k].nar = -1; C[k].kind = 0; C[k].up = 0; C[k].teeth = 0; C[k].lateral = 0; C[k].branch = 0; C[k].downF = 0.0; }
   // narrowest tongue and lip sections
   double minT = 1000000.0, minL = 1000000.0;
   int iT = -1, iL = -1;
@@ -1111,7 +1122,7 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
     if ((ar == AFS_LOWER_LIP) && (a < minL)) { minL = a; iL = j; }
   }
   int f1 = 0, l1 = -1, f2 = 0, l2 = -1, fL = 0, lL = -1, n2 = -1;
-  bool t1 = false, t2 = false;
+  bool t1 = false, t2 = false, cand2 = false;
   double a2 = 1000000.0;
   if (minT < 1.0) { t1 = true; nz_expand(S, lane, r, r1, iT, AFS_TONGUE, minT, f1, l1); }
   if (t1) {  // a second tongue constriction outside the first (TdsModel.cpp:1310-1372)
@@ -1121,27 +1132,28 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
       if ((S.art[j][lane] == AFS_TONGUE) && (a < a2) && ((j < f1) || (j > l1))) { a2 = a; n2 = j; }
     }
     if (a2 < 1.0) {
+      cand2 = true;
       nz_expand(S, lane, r, r1, n2, AFS_TONGUE, a2, f2, l2);
       if ((f2 > l1 + 1) || (l2 < f1 - 1)) t2 = true;
     }
   }
   const bool lipCand = minL < 1.0;
   if (lipCand) nz_expand(S, lane, r, r1, iL, AFS_LOWER_LIP, minL, fL, lL);
-  // laterality of the tongue constrictions: only `max > 0.1` matters (TdsModel.cpp:1545).  Sections whose two frame
-  // values are both clearly below (above) 0.1 can never (always) trip it; only the others are read from the control
-  // frames in global memory and interpolated like the reference does.
-  double lat1 = 0.0, lat2 = 0.0;
-  auto range_lat = [&](int f, int l) {
+  // laterality of the tongue constrictions: only `max > 0.1` matters (TdsModel.cpp:1545); the section that holds the
+  // maximum goes into the signature (a maximum over sections is not linear in r, one section's value is)
+  int am1 = 0, am2 = 0;
+  auto range_lat = [&](int f, int l, int &amax) {
     double m = 0.0;
+    amax = 0;
     for (int i = f; i <= l; i++) {
-      const unsigned long long bit = 1ull << i;
-      if (latAlways & bit) m = 1.0;
-      else if (latMaybe & bit) { const double v = nz_lerp(r1, fr0->laterality[i], r, fr1->laterality[i]); if (v > m) m = v; }
+      const double v = nz_lerp(r1, S.fLat[0][i][lane], r, S.fLat[1][i][lane]);
+      if (v > m) { m = v; amax = i + 1; }
     }
     return m;
   };
-  if (t1) lat1 = range_lat(f1, l1);
-  if (t2) lat2 = range_lat(f2, l2);
+  double lat1 = 0.0, lat2 = 0.0;
+  if (t1) lat1 = range_lat(f1, l1, am1);
+  if (t2) lat2 = range_lat(f2, l2, am2);
   // positions (Tube.cpp:329-346): one sequential pass that picks up what the constrictions need
   const double teeth = nz_lerp(r1, S.inc[0][lane], r, S.inc[1][lane]);
   double pos = 0.0;
@@ -1165,12 +1177,13 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
   }
   // constriction 0: the glottis, obstacle 1.5 cm downstream (TdsModel.cpp:1222-1229)
   if (have15) {
-    C[0].valid = 1; C[0].nar = -1; C[0].kind = 0; C[0].up = s15;
+    C[0].valid = 1; C[0].nar = -1; C[0].kind = 0; C[0].up = s15; C[0].branch = 0;
     C[0].downF = fast_div(__dsub_rn(1.5, p15), e15);
   }
   double minTongueAreaForTeeth = 1000000.0;
+  unsigned side = 0;  // per tongue constriction: 0 teeth branch, else on which side of the incisors the obstacle sits
   // tongue constrictions: the jet hits the teeth when they are closer than 2 cm, else the next section
-  auto tongue = [&](NoiseCons &c, int nar, double aNar, int last, double pL, double eL, double pN, double eN, double lat) {
+  auto tongue = [&](NoiseCons &c, int nar, double aNar, int last, double pL, double eL, double pN, double eN, double lat, int shift) {
     const double jetPos = __dadd_rn(pL, eL);
     double x, p, e;
     int sec;
@@ -1178,27 +1191,43 @@ __device__ __noinline__ void noise_scan(TdsSmem &S, const int lane, const double
     if (__dsub_rn(teeth, jetPos) < 2.0) {
       x = teeth; sec = sT; p = pT; e = eT; ok = haveT;
       minTongueAreaForTeeth = aNar;
+      c.branch = 1;
     } else {
       x = __dadd_rn(pN, __dmul_rn(0.5, eN)); sec = last + 1; p = pN; e = eN; ok = true;  // (inside section last+1)
+      c.branch = 2;
+      const double d = __dsub_rn(x, teeth);
+      side |= (d <= -0.0001 ? 1u : d < 0.0001 ? 2u : 3u) << shift;
     }
-    c.valid = ok ? 1 : 0; c.nar = nar; c.kind = 1; c.up = sec;
+    c.valid = ok ? 1 : 0; c.nar = nar; c.kind = 1; c.up = ok ? sec : 0;
     c.downF = fast_div(__dsub_rn(x, p), e);
     c.teeth = fabs(__dsub_rn(x, teeth)) < 0.0001 ? 1 : 0;
     c.lateral = lat > 0.1 ? 1 : 0;
   };
-  if (t1) tongue(C[1], iT, minT, l1, pL1, eL1, pN1, eN1, lat1);
-  if (t2) tongue(C[2], n2, a2, l2, pL2, eL2, pN2, eN2, lat2);
+  if (t1) tongue(C[1], iT, minT, l1, pL1, eL1, pN1, eN1, lat1, 0);
+  if (t2) tongue(C[2], n2, a2, l2, pL2, eL2, pN2, eN2, lat2, 2);
   // lip constriction (TdsModel.cpp:1380-1418): the obstacle is the downstream end of its last section
   if (lipCand && (minL < minTongueAreaForTeeth)) {
-    C[3].valid = 1; C[3].nar = iL; C[3].kind = 2; C[3].up = lL;
+    C[3].valid = 1; C[3].nar = iL; C[3].kind = 2; C[3].up = lL; C[3].branch = 3;
     C[3].downF = fast_div(__dsub_rn(pNL, pLL), eLL);
+  }
+  if (sig) {
+    auto six = [](int v) { return (unsigned long long)((v + 1) & 63); };  // -1 .. 62
+    sig->a = six(iT) | six(iL) << 6 | six(t1 ? f1 : -1) << 12 | six(t1 ? l1 : -1) << 18 | six(cand2 ? n2 : -1) << 24 |
+             six(cand2 ? f2 : -1) << 30 | six(cand2 ? l2 : -1) << 36 | six(lipCand ? fL : -1) << 42 | six(lipCand ? lL : -1) << 48 |
+             six(have15 ? s15 : -1) << 54;
+    sig->b = six((t1 && haveT) ? sT : -1) | (unsigned long long)am1 << 6 | (unsigned long long)am2 << 12 |
+             (unsigned long long)(lat1 > 0.1) << 18 | (unsigned long long)(lat2 > 0.1) << 19 | (unsigned long long)t1 << 20 |
+             (unsigned long long)t2 << 21 | (unsigned long long)cand2 << 22 | (unsigned long long)lipCand << 23 |
+             (unsigned long long)C[3].valid << 24 | (unsigned long long)C[1].branch << 25 | (unsigned long long)C[2].branch << 27 |
+             (unsigned long long)side << 29 | (unsigned long long)C[1].valid << 33 | (unsigned long long)C[2].valid << 34 |
+             (unsigned long long)C[1].teeth << 35 | (unsigned long long)C[2].teeth << 36;
   }
 }
 
-// One sample of source j from the sum of twelve rand() draws (TdsModel.cpp:1680-1708).  S.ncut[j] holds the low-pass
+// One sample of a source from the sum of twelve rand() draws (TdsModel.cpp:1680-1708).  S.ncut[j] holds the low-pass
 // coefficient exp(-2 pi f_c dt) of the source's cutoff frequency (IirFilter::createSinglePoleLowpass,
 // IirFilter.cpp:235-243), written by warp X2 whenever a constriction feeds the source: a source that only decays
-// keeps its cutoff, so warp X1 never evaluates an exponential.
+// keeps its cutoff, so nobody evaluates an exponential for it.
 __device__ __forceinline__ double nz_sample(const double x, const uint32_t isum, const double last) {
   double in = (double)(int32_t)isum;  // 12 x rand() summed in an int: wraps around like the reference's
   in = (in * (1.0 / 2147483647.0) - 6.0) * 0.28867513459481288225;  // / RAND_MAX, - 6, / sqrt(12)
@@ -1207,24 +1236,11 @@ __device__ __forceinline__ double nz_sample(const double x, const uint32_t isum,
 __device__ __forceinline__ void nz_lowpass(TdsSmem &S, const int lane, const int j, const uint32_t isum) {
   S.nout[j][lane] = nz_sample(S.ncut[j][lane], isum, S.nout[j][lane]);
 }
-// The drawing sources `mine` of one warp; `all` = every drawing source of the step (rank = position in the rand() stream)
-__device__ __forceinline__ void nz_draw_ranked(TdsSmem &S, const int lane, unsigned long long mine,
-                                               const unsigned long long all, const int head, const int avail,
-                                               const int cap) {
-  while (mine) {
-    const int j = __ffsll((long long)mine) - 1;
-    mine &= mine - 1;
-    const int rank = __popcll(all & ((1ull << j) - 1ull));
-    if (rank < avail) {
-      int i = head + rank;
-      if (i >= cap) i -= cap;
-      nz_lowpass(S, lane, j, S.nzsum[i][lane]);
-    }
-  }
-}
+// amplitude filter of calcNoiseSample (TdsModel.cpp:1637-1641), the reference's roundings
+__device__ __forceinline__ double nz_amp(double old, double target, double F) { return __dadd_rn(old, __dmul_rn(F, __dsub_rn(target, old))); }
 // Warp X2, while the reduced system is solved: new sums for the entries the step has consumed, three at a time (the
 // generator is back at phase 12 after three sums, so all lanes run the same straight-line code); up to two entries
-// wait for the next step.  Publishes head and fill level for both warps.
+// wait for the next step.  Publishes head and fill level.
 __device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs &N) {
   auto put = [&](uint32_t v) {
     int t = N.head + (N.cap - N.free);
@@ -1232,7 +1248,6 @@ __device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs 
     S.nzsum[t][lane] = v;
     N.free--;
   };
-  while (N.free > 0 && N.ph != 12) put(rng_sum12(S, lane, N.ph));  // (only after an overflow)
   while (N.free >= 3) {
     const uint32_t s0 = rng_block<12>(S, lane), s1 = rng_block<24>(S, lane), s2 = rng_block<0>(S, lane);
     put(s0); put(s1); put(s2);
@@ -1240,127 +1255,186 @@ __device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs 
   S.nzring[lane] = (uint32_t)N.head | ((uint32_t)(N.cap - N.free) << 8) | ((uint32_t)N.cap << 16);
 }
 
-// State-dependent part of the noise sources, the SAME code on warps X2 (k0 = 0: constriction slots 0 and 2, i.e. the
-// vocal folds and the second tongue constriction) and X1 (k0 = 1: slots 1 and 3, the first tongue constriction and
-// the lips; plus the sources no constriction feeds this step, which only decay).  Per slot: target amplitude from the
-// flow through the constriction (TdsModel.cpp:1430-1612), amplitude filter of the two sources it feeds
-// (TdsModel.cpp:1630-1660); then one sample of every source of this warp that is not silent (TdsModel.cpp:1680-1708).
-// A single warp runs this code once per step with nothing to hide its latencies behind, so what counts is the
-// number of instructions on its path: two warps with half of the slots each, loops instead of unrolled code, the
-// state-independent exponentials (aspiration gain, filter coefficients at the upper cutoff limit) cached.
-// Returns the number of ring entries the step has consumed (both warps).
-struct NzConst { double F, x2000, dt; };  // P.nz_F, P.nz_x2000, P.dt by value (the callee is not inlined)
-__device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int lane, const int par, const double r,
-                                        const double r1, const int k0, const double gain0, int &ph) {
+// gain * sqrt(A) / A^3 and 0.15 / (A d), d = sqrt(4 A / pi), for the constriction area A (TdsModel.cpp:1560-1600):
+// fullAmp = amp * flow^3, cutoff = cut * flow.
+__device__ __forceinline__ void nz_factors(double A, const double gain, double &amp, double &cut) {
+  if (A < kMinArea) A = kMinArea;
+  if (A < 0.1) A = 0.1;
+  const double rs = fast_rsqrt(A), rs2 = rs * rs;  // v = flow / A = flow rs^2
+  amp = gain * (A * rs) * (rs2 * rs2 * rs2);
+  cut = 0.15 * rs2 * (rs * 0.88622692545275801365);
+}
+__device__ __forceinline__ double nz_down(const TdsSmem &S, const int lane, const int k, const double r) {
+  return fast_div(fma(r, S.nzc_c[k][1][lane], S.nzc_c[k][0][lane]), fma(r, S.nzc_c[k][3][lane], S.nzc_c[k][2][lane]));
+}
+// Slot word of a constriction record: bit 0 valid, 1-2 kind, 3 teeth, 4 lateral, 5 / 6 the upstream / downstream source
+// is fed by a LATER slot as well (the last one wins, TdsModel.cpp:1430-1612 writes the targets slot after slot),
+// 8-15 nar + 1, 16-31 up.  nz_fed: the sources the four slots of a tract feed (bit j = source j).
+__device__ __forceinline__ unsigned long long nz_fed(const TdsSmem &S, const int lane) {
   constexpr int NPM = AFS_NUM_PM_SECTIONS;
-  // sections fed by the four slots: bits 0..7 up, 8..15 down, valid in bit 16
-  unsigned long long targeted = 0, mine = 0, alive = 0;
+  unsigned long long fed = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const uint32_t v = S.nzc_i[par][k][lane];
+    const uint32_t v = S.nzc_i[k][lane];
     const int up = (int)(v >> 16), down = up < NPM - 1 ? up + 1 : NPM;
-    if (v & 1u) targeted |= (1ull << up) | (1ull << down);
+    if (v & 1u) fed |= (1ull << up) | (1ull << down);
   }
-  const double lipflow = S.nzlip[lane];
+  return fed;
+}
+
+// One constriction slot of calcNoiseSources, state-dependent part (TdsModel.cpp:1430-1612): flow through the
+// constriction -> target amplitude -> amplitude filter (calcNoiseSample, :1637-1660) of the two sources it feeds.
+// amp / cut / downF: the flow-independent factors (nz_factors, nz_down).  Returns the fed sources that are audible.
+struct NzConst { double F, x2000, dt; };  // P.nz_F, P.nz_x2000, P.dt by value (the callees are not inlined)
+__device__ __forceinline__ unsigned long long nz_slot(const NzConst &P, TdsSmem &S, const int lane, const int k, const uint32_t v,
+                                                      const double amp, const double cut, const double downF) {
+  constexpr int NPM = AFS_NUM_PM_SECTIONS;
+  const bool valid = v & 1u;
+  const int nar = min(max((int)((v >> 8) & 255u) - 1, 0), NPM - 1), up = (int)(v >> 16), down = up < NPM - 1 ? up + 1 : NPM;
+  double flow;
+  if (k == 0) flow = S.nmag[0][lane];  // the glottis: current 25
+  else {                               // pharynx/mouth section nar
+    const double f = S.nmag[nar + 1][lane];
+    const double extra = S.nmag[nar == 3 ? 41 : 40][lane];  // section 28: currents 29 and 84; section 40: currents 41 and 65
+    flow = nar == NPM - 1 ? S.nzlip[lane] : (nar == 3 || nar == 15) ? f + extra : f;
+  }
+  if (flow < 0.0) flow = 0.0;
+  const double fullAmp = amp * (flow * flow * flow);  // gain |v| v^2 sqrt(A), v = flow / A >= 0
+  // cutoff: clamped to 50..2000 Hz; the vocal-fold and lip sources ask for 6000 Hz, i.e. sit at the upper limit
+  double x = P.x2000;
+  if (k == 1 || k == 2) {
+    double cutoff = cut * flow;  // 0.15 v / d
+    if (cutoff < 50.0) cutoff = 50.0;
+    if (cutoff < 2000.0) x = exp_small(-2.0 * kPi * (cutoff * P.dt));
+  }
+  unsigned long long draw = 0;
+#pragma unroll 1
+  for (int side = 0; side < 2; side++) {
+    const int j = side ? down : up;
+    if (valid && !((v >> (5 + side)) & 1u)) {  // (not a source a later slot feeds as well)
+      const double target = side ? downF * fullAmp : (1.0 - downF) * fullAmp;
+      const double old = S.namp[j][lane];
+      double a = nz_amp(old, target, P.F);
+      S.ncut[j][lane] = x;
+      if ((old >= 0.001) && (a < 0.001)) S.nout[j][lane] = 0.0;
+      if (a >= 0.001) draw |= 1ull << j;
+      if ((a < 1.0e-13) && (target == 0.0)) a = 0.0;  // (the reference lets it decay for ever; a source is silent below 1e-3)
+      S.namp[j][lane] = a;
+    }
+  }
+  return draw;
+}
+
+// The state-dependent part of the noise sources is spread over three warps that have time in pass A, each with a
+// short piece, so that none of them becomes the longest path of the step (a lone warp pays an instruction fetch for
+// almost every instruction it executes once per step: what counts is the number of instructions on its path):
+//   warp F  (noise_decay, before its own pass A: it has the most slack of the static chain warps): the sources nothing
+//           feeds this step decay (calcNoiseSample, TdsModel.cpp:1637-1660); the still audible ones -> nzdecay;
+//   warp X1 (noise_tongue; idle in pass A otherwise): the tongue and lip constrictions (slots 1..3), complete: factors,
+//           flow, target amplitudes, amplitude filters; their audible sources -> nztongue;
+//   warp X2 (noise_stage): the vocal-fold constriction (slot 0; its flow-independent factors were computed one step
+//           ahead by X1 next to the glottis geometry: nzk0), then -- behind named barrier 4, where F and X1 only arrive
+//           -- one sample for every source that is not silent, in ascending source order: the reference draws from ONE
+//           rand() stream in that order (TdsModel.cpp:1615-1620), here the k-th drawing source takes the k-th entry of
+//           the ring of pre-generated sums.
+// Every source is written by exactly one of them: a fed source by the warp of the LAST slot that feeds it (slot words,
+// bits 5 / 6), the others by F.  Everything is finished before the barrier that ends pass A; the chain warps only add
+// sample = out * amp to their right-hand sides.
+__device__ __noinline__ void noise_decay(const double F, TdsSmem &S, const int lane, unsigned long long &live) {
+  const unsigned long long fed = nz_fed(S, lane);
+  unsigned long long todo = live & ~fed, alive = fed, draw = 0;
+  while (todo) {  // two per pass (small loop body: see above)
+    const int j0 = __ffsll((long long)todo) - 1;
+    todo &= todo - 1;
+    const bool two = todo != 0;
+    const int j1 = two ? __ffsll((long long)todo) - 1 : j0;
+    todo &= todo - 1;
+    const double old0 = S.namp[j0][lane], old1 = S.namp[j1][lane];
+    double a0 = nz_amp(old0, 0.0, F), a1 = nz_amp(old1, 0.0, F);
+    if ((old0 >= 0.001) && (a0 < 0.001)) S.nout[j0][lane] = 0.0;
+    if (two && (old1 >= 0.001) && (a1 < 0.001)) S.nout[j1][lane] = 0.0;
+    if (a0 >= 0.001) draw |= 1ull << j0;
+    if (two && (a1 >= 0.001)) draw |= 1ull << j1;
+    if (a0 < 1.0e-13) a0 = 0.0;  // (the reference lets it decay for ever; a source is silent below 1e-3)
+    else alive |= 1ull << j0;
+    if (a1 < 1.0e-13) a1 = 0.0;
+    else if (two) alive |= 1ull << j1;
+    S.namp[j0][lane] = a0;
+    if (two) S.namp[j1][lane] = a1;
+  }
+  live = alive;
+  S.nzdecay[lane] = draw;
+  bar_arrive(4, 96);
+}
+
+__device__ __noinline__ void noise_tongue(const NzConst P, TdsSmem &S, const int lane, const double r, const double r1) {
+  constexpr int NPM = AFS_NUM_PM_SECTIONS;
+  unsigned long long draw = 0;
+#pragma unroll 1
+  for (int k = 1; k < 4; k++) {
+    const uint32_t v = S.nzc_i[k][lane];
+    if (!__any_sync(0xffffffffu, v & 1u)) continue;  // (the second tongue constriction and the lips are rare)
+    const bool teeth = (v >> 3) & 1u, lateral = (v >> 4) & 1u;
+    const int nar = min(max((int)((v >> 8) & 255u) - 1, 0), NPM - 1);
+    double amp, cut;
+    nz_factors(nz_area(S, lane, r, r1, nar), lateral ? 0.0 : k == 3 ? 2.0e-7 : teeth ? 10.0e-7 : 5.0e-7, amp, cut);
+    draw |= nz_slot(P, S, lane, k, v, amp, cut, nz_down(S, lane, k, r));
+  }
+  S.nztongue[lane] = draw;
+  bar_arrive(4, 96);
+}
+
+// (returns the number of ring entries consumed)
+__device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int lane, const double gain0
+#ifdef AFS_TDS_TIMING
+                                        , long long *nz_t
+#endif
+                                        ) {
+#ifdef AFS_TDS_TIMING
+  long long sw_last = clock64();
+  long long *sw_t = nz_t;
+#endif
+  unsigned long long draw = 0;  // bit j = source j (0..39: section 25 + j, 40: lips)
+  {
+    const uint32_t v = S.nzc_i[0][lane];
+    if (__any_sync(0xffffffffu, v & 1u)) draw = nz_slot(P, S, lane, 0, v, gain0 * S.nzk0[0][lane], 0.0, S.nzk0[1][lane]);
+  }
+  SW_TICK(0);
+  bar_sync(4, 96);
+  SW_TICK(1);
+  // samples, ascending: the k-th drawing source takes the k-th sum (two independent low-pass updates per pass)
+  draw |= S.nzdecay[lane] | S.nztongue[lane];
   const uint32_t ring = S.nzring[lane];
-  const int head = (int)(ring & 255u), avail = (int)((ring >> 8) & 255u), cap = (int)(ring >> 16);
-#pragma unroll 1
-  for (int k = k0; k < 4; k += 2) {
-    const uint32_t v = S.nzc_i[par][k][lane];
-    const bool valid = v & 1u, teeth = (v >> 3) & 1u, lateral = (v >> 4) & 1u;
-    const int nar = min(max((int)((v >> 8) & 255u) - 1, 0), NPM - 1), up = (int)(v >> 16), down = up < NPM - 1 ? up + 1 : NPM;
-    const double downF = S.nzc_f[par][k][lane];
-    if (!__any_sync(0xffffffffu, valid)) continue;  // (the second tongue constriction and the lips are rare)
-    // sources a later slot feeds as well are that slot's (the last one wins)
-    unsigned long long later = 0;
-    for (int q = k + 1; q < 4; q++) {
-      const uint32_t w = S.nzc_i[par][q][lane];
-      const int u2 = (int)(w >> 16), d2 = u2 < NPM - 1 ? u2 + 1 : NPM;
-      if (w & 1u) later |= (1ull << u2) | (1ull << d2);
-    }
-    double A, flow;
-    if (k == 0) {  // the glottis (upper glottis section, current 25)
-      A = S.glArea[par][1][lane];
-      flow = S.nmag[0][lane];
-    } else {       // tongue (k = 1, 2) and lip (k = 3) constrictions: pharynx/mouth section nar
-      A = nz_area(S, lane, r, r1, nar);
-      const double f = S.nmag[nar + 1][lane];
-      const double extra = S.nmag[nar == 3 ? 41 : 40][lane];  // section 28: currents 29 and 84; section 40: currents 41 and 65
-      flow = nar == NPM - 1 ? lipflow : (nar == 3 || nar == 15) ? f + extra : f;
-    }
-    if (A < kMinArea) A = kMinArea;
-    if (A < 0.1) A = 0.1;
-    if (flow < 0.0) flow = 0.0;
-    const double rs = fast_rsqrt(A);  // 1/sqrt(A): v = flow / A, sqrt(A) and the jet diameter all come from it
-    const double v_ = flow * (rs * rs);
-    const double gain = k == 0 ? gain0 : k == 3 ? 2.0e-7 : teeth ? 10.0e-7 : 5.0e-7;
-    double fullAmp = gain * fabs(v_) * v_ * v_ * (A * rs);
-    if (lateral) fullAmp = 0.0;
-    // cutoff: clamped to 50..2000 Hz; the vocal-fold and lip sources ask for 6000 Hz, i.e. sit at the upper limit
-    double x = P.x2000;
-    if (k == 1 || k == 2) {
-      double cutoff = 0.15 * v_ * (rs * 0.88622692545275801365);  // 0.15 v / d, d = sqrt(4 A / pi)
-      if (cutoff < 50.0) cutoff = 50.0;
-      if (cutoff < 2000.0) x = exp_small(-2.0 * kPi * (cutoff * P.dt));
-    }
-#pragma unroll 1
-    for (int side = 0; side < 2; side++) {
-      const int j = side ? down : up;
-      if (valid && !((later >> j) & 1ull)) {
-        const double tgt = side ? downF * fullAmp : (1.0 - downF) * fullAmp;
-        const double old = S.namp[j][lane];
-        double a = __dadd_rn(old, __dmul_rn(P.F, __dsub_rn(tgt, old)));
-        S.ncut[j][lane] = x;
-        if ((old >= 0.001) && (a < 0.001)) S.nout[j][lane] = 0.0;
-        if (a >= 0.001) mine |= 1ull << j;
-        if ((a < 1.0e-13) && (tgt == 0.0)) a = 0.0;  // (the reference lets it decay for ever; a source is silent below 1e-3)
-        else alive |= 1ull << j;
-        S.namp[j][lane] = a;
-      }
-    }
+  const int cap = (int)(ring >> 16);
+  int i = (int)(ring & 255u), n_draw = 0;
+  while (draw) {
+    const int j0 = __ffsll((long long)draw) - 1;
+    draw &= draw - 1;
+    const bool two = draw != 0;
+    const int j1 = two ? __ffsll((long long)draw) - 1 : j0;
+    draw &= draw - 1;
+    const int i1 = i + 1 >= cap ? i + 1 - cap : i + 1;
+    const uint32_t s0 = S.nzsum[i][lane], s1 = S.nzsum[i1][lane];
+    const double o0 = nz_sample(S.ncut[j0][lane], s0, S.nout[j0][lane]);
+    const double o1 = nz_sample(S.ncut[j1][lane], s1, S.nout[j1][lane]);
+    S.nout[j0][lane] = o0;
+    if (two) S.nout[j1][lane] = o1;
+    const int adv = two ? 2 : 1;
+    i += adv; n_draw += adv;
+    if (i >= cap) i -= cap;
   }
-  if (k0 == 1) {  // the sources that only decay, two per pass
-    unsigned long long todo = (S.nzlive[0][lane] | S.nzlive[1][lane]) & ~targeted;
-    while (todo) {
-      const int j0 = __ffsll((long long)todo) - 1;
-      todo &= todo - 1;
-      const bool two = todo != 0;
-      const int j1 = two ? __ffsll((long long)todo) - 1 : j0;
-      todo &= todo - 1;
-      const double old0 = S.namp[j0][lane], old1 = S.namp[j1][lane];
-      double a0 = __dadd_rn(old0, __dmul_rn(P.F, __dsub_rn(0.0, old0)));
-      double a1 = __dadd_rn(old1, __dmul_rn(P.F, __dsub_rn(0.0, old1)));
-      if ((old0 >= 0.001) && (a0 < 0.001)) S.nout[j0][lane] = 0.0;
-      if (two && (old1 >= 0.001) && (a1 < 0.001)) S.nout[j1][lane] = 0.0;
-      if (a0 >= 0.001) mine |= 1ull << j0;
-      if (two && (a1 >= 0.001)) mine |= 1ull << j1;
-      if (a0 < 1.0e-13) a0 = 0.0;
-      else alive |= 1ull << j0;
-      if (a1 < 1.0e-13) a1 = 0.0;
-      else if (two) alive |= 1ull << j1;
-      S.namp[j0][lane] = a0;
-      if (two) S.namp[j1][lane] = a1;
-    }
+  SW_TICK(2);
+  return n_draw;
+}
+
+// The samples of the dipole sources of a chain warp's own sections into the right-hand sides: S = -sample
+// (TdsModel.cpp:1936), sample = out * amp (0 while the source is silent: out = 0 then).
+__device__ __forceinline__ void dwarp_noise(const TdsParams &P, TdsSmem &S, const int lane, const int w, DRegs &st) {
+#pragma unroll
+  for (int k = 0; k < KD; k++) {
+    const int j = KD * w - 2 + k;  // section 23 + 6 w + k - 25
+    if (j >= 0 && j < AFS_NUM_PM_SECTIONS) st.x[k] = fma(S.nout[j][lane], S.namp[j][lane], st.x[k]);
   }
-  // The reference draws in ascending source order from ONE rand() stream: the k-th drawing source of the step takes
-  // the k-th sum.  The sums do not depend on the state, so warp X2 generates them ahead of time (nz_refill) and the
-  // two warps pick theirs by rank once they have told each other who draws.
-  S.nzdraw[k0][lane] = mine;
-  bar_sync(4, 64);
-  const unsigned long long all = mine | S.nzdraw[k0 ^ 1][lane];
-  S.nzlive[k0][lane] = alive;  // (the other warp read the old masks before the barrier)
-  nz_draw_ranked(S, lane, mine, all, head, avail, cap);
-  const int n_all = __popcll(all);
-  if (k0 == 0 && n_all > avail) {  // more than the ring holds: the rest takes its sums straight from the generator, in order
-    unsigned long long over = all;
-    for (int k = 0; k < avail; k++) over &= over - 1;
-    while (over) {
-      const int j = __ffsll((long long)over) - 1;
-      over &= over - 1;
-      nz_lowpass(S, lane, j, rng_sum12(S, lane, ph));
-    }
-  }
-  return min(n_all, avail);
 }
 
 // ==================================================================================
@@ -1646,7 +1720,12 @@ struct KArgs {
   uint32_t *status;
   double *dump;
   const uint32_t *seeds;
-  // noise sources: constriction records of every (CTA, step) from tds_noise_scan_kernel, [cta][step][4][32]
+  // noise sources, the constriction records of the pre-pass: EITHER one record per run of steps and tract
+  // (tds_noise_runs_kernel: runs[run_off[tract] ..], sorted by their first step) ...
+  const NzRun *runs;
+  int run_items;            // pieces per tract: tract t's list starts at runs[t * run_items]
+  const uint32_t *run_ctl;  // [0] next free record of the pool, [1] != 0: the pool was too small (status bit 1)
+  // ... OR one per step (tds_noise_scan_kernel: [cta][step][4][32])
   uint32_t *nzc_i;
   double *nzc_f;
   // taps: [tract][probe][step], each nullable
@@ -1657,6 +1736,39 @@ struct KArgs {
   int progress_every;
 };
 
+
+// Warp X1 keeps the constriction records of the step the others work on in shared memory (nzc_i / nzc_c).
+struct NzFeed {
+  uint32_t idx;      // runs mode: the tract's next record ...
+  uint32_t next;     // ... and its first step
+};
+__device__ __forceinline__ void nz_put_run(TdsSmem &S, const int lane, const NzRun *r) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    S.nzc_i[k][lane] = __ldg(&r->slot[k]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) S.nzc_c[k][c][lane] = __ldg(&r->coef[k][c]);
+  }
+}
+// per-step records ([cta][step][4][32], tds_noise_scan_kernel): the downstream factor is a constant
+struct NzcRec { uint32_t i[4]; double f[4]; };
+__device__ __forceinline__ void nzc_fetch_issue(const uint32_t *nzc_i, const double *nzc_f, int total_steps, int n, NzcRec &R) {
+  const int hw_lane = threadIdx.x & 31;
+  const size_t base = ((size_t)blockIdx.x * (size_t)total_steps + (size_t)n) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    R.i[k] = __ldg(nzc_i + (base + k) * 32 + hw_lane);
+    R.f[k] = __ldg(nzc_f + (base + k) * 32 + hw_lane);
+  }
+}
+__device__ __forceinline__ void nzc_fetch_store(TdsSmem &S, const int lane, const NzcRec &R) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    S.nzc_i[k][lane] = R.i[k];
+    S.nzc_c[k][0][lane] = R.f[k]; S.nzc_c[k][1][lane] = 0.0; S.nzc_c[k][2][lane] = 1.0; S.nzc_c[k][3][lane] = 0.0;
+  }
+}
+
 #ifdef AFS_TDS_TIMING
 #define AFS_TICK(k) do { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } while (0)
 #else
@@ -1664,8 +1776,8 @@ struct KArgs {
 #endif
 
 // Stages the control frames of interval `interval` (all warps; the caller puts barriers around it).
-__device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const int warp, const afs_tube_frame *my_frames,
-                                               const double *my_glottis, int interval, bool scan) {
+__device__ __noinline__ void stage_interval(TdsSmem &S, const int lane, const int warp, const afs_tube_frame *my_frames,
+                                               const double *my_glottis, int interval) {
   for (int item = warp; item < 2 * AFS_NUM_PM_SECTIONS + 2; item += NW) {
     if (item < 2 * AFS_NUM_PM_SECTIONS) {
       const int f = item / AFS_NUM_PM_SECTIONS, j = item % AFS_NUM_PM_SECTIONS;
@@ -1674,13 +1786,11 @@ __device__ __forceinline__ void stage_interval(TdsSmem &S, const int lane, const
       if (a < kMinArea) a = kMinArea;  // Tube::setPharynxMouthGeometry clamps on the way in
       S.fA[f][j][lane] = a;
       S.fLen[f][j][lane] = fr->length_cm[j];
-      if (scan && f == 0) S.art[j][lane] = (unsigned char)fr->articulator[j];
     } else {
       const int f = item - 2 * AFS_NUM_PM_SECTIONS;
       double v = my_frames[interval + f].velum_area_cm2;
       if (v < kMinArea) v = kMinArea;  // Tube::getVelumOpening_cm2 returns the clamped nose[0] area
       S.velum[f][lane] = v;
-      if (scan) S.inc[f][lane] = my_frames[interval + f].incisor_pos_cm;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
         S.gctl[f][c][lane] = my_glottis[(size_t)(interval + f) * AFS_NUM_GLOTTIS_CONTROL + c];
     }
@@ -1707,6 +1817,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   OptRegs orr;
   X1Regs xr;
   NoiseRegs nr;
+  NzFeed feed{0u, 0x7fffffffu};
+  int next_mark = (ROLE == 3 && A.progress && A.progress_every > 0) ? (A.progress_every < T ? A.progress_every : T) : -1;  // (warp X2)
+  unsigned long long nz_live = 0;  // (warp F) sources whose amplitude is not zero
   nr.ph = 12; nr.head = 0; nr.free = 0; nr.cap = NZ_RING; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0; nr.asp = nan(""); nr.gain = 0.0;
   const SCfg scfg = scfg_of(warp);
   const unsigned wcfg = wcfg_make(warp);
@@ -1728,8 +1841,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; orr.x1[j] = orr.y1[j] = orr.x2[j] = orr.y2[j] = orr.xg[j] = orr.yg[j] = 0.0; }
     if (NOISE) {
       rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ph);
-      nr.cap = nr.free = P.nz_ring;
-      nz_refill(S, lane, nr);
+      nr.cap = nr.free = NZ_RING;
+      nz_refill(S, lane, nr);  // (42 sums; the ring is never emptier than that when a step begins)
     }
   }
   if (ROLE == 2) {
@@ -1748,13 +1861,30 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (T > 0) {
     i0 = A.bounds[0]; i1 = A.bounds[1];
     inv_len = 1.0 / (double)(i1 - i0);
-    stage_interval(S, lane, warp, my_frames, my_glottis, 0, false);
+    stage_interval(S, lane, warp, my_frames, my_glottis, 0);
     cta_sync();
-    if (ROLE == 2 && NOISE) nzc_fetch(S, A, lane, T, 0, 0);  // constrictions of step 0 for warp X2
+    if (ROLE == 2 && NOISE) {  // constrictions of step 0
+      if (A.runs) {
+        const NzRun *rec = A.runs + (size_t)tract * (size_t)A.run_items;
+        nz_put_run(S, lane, rec);
+        feed.next = rec->next;
+        feed.idx = rec->next_idx;
+      } else {
+        NzcRec rec;
+        nzc_fetch_issue(A.nzc_i, A.nzc_f, T, 0, rec);
+        nzc_fetch_store(S, lane, rec);
+      }
+    }
     if (ROLE == 2) {  // glottis geometry of step 0
       double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
       glottis_geometry(P, ctl, xr.G, len, ar, xr.GD);
+      if (NOISE) {
+        double fa, fc;
+        nz_factors(ar[1], 1.0, fa, fc);
+        S.nzk0[0][lane] = fa;
+        S.nzk0[1][lane] = nz_down(S, lane, 0, 0.0);
+      }
       S.glLen[0][0][lane] = len[0]; S.glLen[0][1][lane] = len[1];
       S.glArea[0][0][lane] = ar[0]; S.glArea[0][1][lane] = ar[1];
     }
@@ -1772,7 +1902,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       interval++;
       i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
       inv_len = 1.0 / (double)(i1 - i0);
-      stage_interval(S, lane, warp, my_frames, my_glottis, interval, false);
+      stage_interval(S, lane, warp, my_frames, my_glottis, interval);
       cta_sync();
     }
     X.ratio = (double)(n - i0) * inv_len;  // (1 ulp from the reference's i / N; irrelevant at the 1e-6 bar)
@@ -1787,6 +1917,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     }
     AFS_TICK(0);
     // ============ pass A: update (step n-1), elements + rows (step n) ============
+    if (ROLE == 1 && NOISE && X.rows && warp == W_F) noise_decay(P.nz_F, S, lane, nz_live);  // (see noise_decay)
     // (state dump requested for this step: update and rows in two separate passes, the dump in between)
     if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true, OPT>(P, S, lane, warp, wcfg, dst, X);
     else for (int half = 0; half < (X.dumping ? 2 : 1); half++) {
@@ -1800,20 +1931,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
       }
     }
-    if (ROLE == 2 && NOISE) {
-      // constrictions of step n+1: found by the pre-pass kernel (they depend on the geometry of the step only),
-      // fetched one step ahead; the loads are in flight while this warp does its share of the sources of step n
-      NzcRec rec;
-      if (n + 1 < T) nzc_fetch_issue(A, T, n + 1, rec);
-#ifndef AFS_NZ_SKIP_SRC
-      if (X.rows) {
-        int no_rng = 12;
-        noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 1, 0.0, no_rng);
-      }
-#endif
-      if (n + 1 < T) nzc_fetch_store(S, lane, (n + 1) & 1, rec);
-    }
-    if (ROLE == 3 && NOISE && X.rows) {  // its share of the noise sources of step n
+    if (ROLE == 2 && NOISE && X.rows) noise_tongue(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1);
+    if (ROLE == 3 && NOISE && X.rows) {  // the constrictions' share of the noise sources of step n
       // (the control-frame ratio only enters smooth quantities here; the decisions that need the reference's own
       //  rounding of it were made by the pre-pass)
       const double asp = X.ratio1 * S.gctl[0][G_ASP][lane] + X.ratio * S.gctl[1][G_ASP][lane];
@@ -1821,11 +1940,13 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         nr.asp = asp;
         nr.gain = 0.5e-7 * exp(asp * (2.302585092994045684 / 20.0));
       }
-#ifndef AFS_NZ_SKIP_SRC
-      const int used = noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, n & 1, X.ratio, X.ratio1, 0, nr.gain, nr.ph);
+      const int used = noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, nr.gain
+#ifdef AFS_TDS_TIMING
+                                   , sw_acc
+#endif
+                                   );
       nr.head += used; nr.free += used;
       if (nr.head >= nr.cap) nr.head -= nr.cap;
-#endif
     }
     AFS_TICK(1);
     cta_sync();
@@ -1834,16 +1955,21 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     if (ROLE == 2) {  // everything X1 reads from the other warps, then it is on its own until the end of the step
       const double u_rad = S.uext[UX_RADM][lane] + S.uext[UX_RADN][lane];
       for (int c = 0; c < 4; c++) x1p[c] = S.p4[c][lane];
-      if (X.rows) bar_arrive(1, TDS_THREADS);
-      if (n > 0) emit_output(P, xr, u_rad, x1p[3], n, active, tract, n_out, A.audio, A.flow, bad);
-      if (A.progress && n > 0 && (n % A.progress_every == 0 || n == T)) {
-        __threadfence_system();  // this lane's samples first, ...
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) {
-          __threadfence_system();
-          *(volatile unsigned int *)(A.progress + blockIdx.x) = (unsigned int)n;  // ... then the mark
+      if (NOISE && n + 1 < T) {  // constriction records of step n+1 (X2 is past its reads of step n's; it looks at
+        if (!A.runs) {  // them again behind barrier 1, hence before the arrive)
+          NzcRec nzrec;
+          nzc_fetch_issue(A.nzc_i, A.nzc_f, T, n + 1, nzrec);
+          nzc_fetch_store(S, lane, nzrec);
+        }
+        else if ((uint32_t)(n + 1) == feed.next) {
+          const NzRun *rec = A.runs + feed.idx;
+          nz_put_run(S, lane, rec);
+          feed.next = __ldg(&rec->next);
+          feed.idx = __ldg(&rec->next_idx);
         }
       }
+      if (X.rows) bar_arrive(1, TDS_THREADS);
+      if (n > 0) emit_output(P, xr, u_rad, x1p[3], n, active, tract, n_out, A.audio, A.flow, bad);
     }
     if (!X.rows) break;
     // ============ first rows + elimination of the segments || glottis ============
@@ -1892,6 +2018,12 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       const double rn = (double)(n + 1 - i0) * inv_len, rn1 = 1.0 - rn;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = rn1 * S.gctl[0][c][lane] + rn * S.gctl[1][c][lane];
       glottis_geometry(P, ctl, xr.G, len, ar, xr.GD);
+      if (NOISE) {  // vocal-fold noise source of step n+1: what does not depend on the flow (noise_stage)
+        double fa, fc;
+        nz_factors(ar[1], 1.0, fa, fc);
+        S.nzk0[0][lane] = fa;
+        S.nzk0[1][lane] = nz_down(S, lane, 0, n + 1 == i1 ? 0.0 : rn);  // (a new interval starts with new records)
+      }
       const int par = (n + 1) & 1;
       S.glLen[par][0][lane] = len[0]; S.glLen[par][1][lane] = len[1];
       S.glArea[par][0][lane] = ar[0]; S.glArea[par][1][lane] = ar[1];
@@ -1899,7 +2031,15 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(3);
     if (ROLE != 2) {
       bar_sync(1, TDS_THREADS);
-      if (ROLE == 3 && NOISE) nz_refill(S, lane, nr);  // (this warp only waits for the reduced system)
+      if (ROLE == 3 && NOISE) {  // (this warp only waits for the reduced system)
+#ifdef AFS_TDS_TIMING
+        const long long t_rf = clock64();
+#endif
+        nz_refill(S, lane, nr);
+#ifdef AFS_TDS_TIMING
+        sw_acc[3] += clock64() - t_rf;
+#endif
+      }
       // ============ reduced system over the separators ============
       // (the three warps of the reduced system meet on their own barrier; the twelve others only wait for the result)
       if (warp == W_T0 || warp == W_T1 || warp == W_T2) {
@@ -1921,11 +2061,31 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(6);
     cta_sync();
     AFS_TICK(7);
+    // Progress mark: the samples of the steps 1..n are written (warp X1, before the barrier above).  Published by warp
+    // X2 -- X1's path is the longest of the step, X2 has time here; the barrier orders X1's stores before this fence.
+    if (ROLE == 3 && n == next_mark) {
+      next_mark = next_mark + A.progress_every < T ? next_mark + A.progress_every : T;
+      if ((threadIdx.x & 31) == 0) {
+        __threadfence_system();
+        *(volatile unsigned int *)(A.progress + blockIdx.x) = (unsigned int)n;
+      }
+    }
+  }
+  if (A.progress && T > 0) {  // the last step's samples (the loop is left before its final barrier)
+    cta_sync();
+    if (ROLE == 3 && (threadIdx.x & 31) == 0) {
+      __threadfence_system();
+      *(volatile unsigned int *)(A.progress + blockIdx.x) = (unsigned int)T;
+    }
   }
 #ifdef AFS_TDS_TIMING
   if (A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 8; k++) A.dump[warp * 8 + k] = (double)tacc[k];
-  if (ROLE == 1 && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) A.dump[136 + warp * 4 + k] = (double)sw_acc[k];
+  if ((ROLE == 1 || ROLE == 3) && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) A.dump[136 + warp * 4 + k] = (double)sw_acc[k];
+  // (pass-A cycles of the two auxiliary warps of the first 136 CTAs: how evenly the noise sources load the CTAs)
+  if (ROLE == 2 && A.dump && blockIdx.x < 136 && lane == 0) A.dump[200 + blockIdx.x] = (double)tacc[1];
+  if (ROLE == 3 && A.dump && blockIdx.x < 136 && lane == 0) A.dump[336 + blockIdx.x] = (double)tacc[1];
 #endif
+  if (ROLE == 2 && NOISE && A.run_ctl && A.run_ctl[1]) bad |= 2u;  // the noise pre-pass ran out of record space
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;
 }
 
@@ -1980,12 +2140,15 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
   }
   {
     const int w = warp;
-    S.bE[w][lane] = 0.0; S.bL[w][lane] = 0.0; S.bR[w][lane] = 0.0; S.bI[w][lane] = 0.0; S.bG[w][lane] = 0.0;
-    S.bD[w][lane] = 0.0; S.csib[w & 3][lane] = 0.0; S.sideDD[w][lane] = 0.0; S.sideDR[w][lane] = 0.0; S.sideF[w][lane] = 0.0;
+    if (w < NSEG) {
+      S.bE[w][lane] = 0.0; S.bL[w][lane] = 0.0; S.bR[w][lane] = 0.0; S.bI[w][lane] = 0.0; S.bG[w][lane] = 0.0;
+      S.bD[w][lane] = 0.0; S.sideDD[w][lane] = 0.0; S.sideDR[w][lane] = 0.0; S.sideF[w][lane] = 0.0;
+    }
+    S.csib[w & 3][lane] = 0.0;
     S.sepD[w][lane] = 1.0; S.sepR[w][lane] = 0.0; S.redW[w][lane] = 1.0;  // NSEP == NW
   }
   if (warp == 0) {
-    for (int i = 0; i < 2; i++) { S.nzlive[i][lane] = 0; S.nzdraw[i][lane] = 0; }
+    S.nzk0[0][lane] = 0.0; S.nzk0[1][lane] = 0.0; S.nzdecay[lane] = 0; S.nztongue[lane] = 0;
     S.nzlip[lane] = 0.0;
     for (int i = 0; i < NUX; i++) S.uext[i][lane] = 0.0;
     for (int i = 0; i < 5; i++) S.lf[i][lane] = 0.0;
@@ -2008,45 +2171,174 @@ static_assert(NSEP == NW, "prologue zeroing assumes NSEP == NW");
 // Noise-source pre-pass: TdsModel::calcNoiseSources, state-independent part (TdsModel.cpp:1188-1430)
 // ==================================================================================
 // Which sections form a constriction and where its obstacle sits depends on the GEOMETRY of a step only, not on the
-// acoustic state.  Inside the time loop the scan cost one warp 27 k cycles per step (the other fifteen waited for
-// it); here every (tract, step) pair is independent: the same CTA <-> tract mapping as tds_batch_kernel, lane =
-// tract, the sixteen warps of a CTA take the steps of a control interval round robin.  Records (48 B per tract-step)
-// go to global memory in [cta][step][4][32] layout and are fetched one step ahead by warp X1.
+// acoustic state (inside the time loop the scan once cost one warp 27 k cycles per step, with the fifteen others
+// waiting for it).  Two kernels, chosen by the spacing of the control frames:
+//
+// tds_noise_runs_kernel -- control frames many steps apart (an utterance = a few frames).  Between two frames every
+// quantity the scan compares is linear in the step, so its outcome is piecewise constant; the kernel finds the run
+// boundaries of every tract by BISECTION over the steps of an interval (two steps with the same ScanSig enclose steps
+// with that signature) and writes one NzRun record per run: a few hundred scans per utterance instead of 44 100, a
+// few KB of records instead of 2 MB.  One thread per (tract, piece of an interval): the bisection is sequential, long
+// intervals are cut into pieces.  The records go into one pool as linked lists (NzRun), in a single pass.
+//
+// tds_noise_scan_kernel -- control frames a few steps apart (one per output sample, Synthesizer::playTargetSequence
+// style): every step is scanned, (tract, step) pairs are independent, same CTA <-> tract mapping as tds_batch_kernel,
+// the warps of a CTA take the steps of an interval round robin; 48 B per tract-step in [cta][step][4][32] layout.
+constexpr int RUN_NL = 33;  // 32 tracts per CTA; rows padded: the staging below transposes
+using RunFrames = ScanFrames<RUN_NL>;
+
+// downF(r) = (c0 + r c1) / (c2 + r c3) of a constriction slot for the interval staged in S (see NoiseCons::branch)
+template <class FR>
+__device__ __forceinline__ void nz_run_coef(const FR &S, const int lane, const NoiseCons &c, double (&coef)[4]) {
+  coef[0] = 0.0; coef[1] = 0.0; coef[2] = 1.0; coef[3] = 0.0;
+  if (!c.valid) return;
+  if (c.branch == 2) { coef[0] = 0.5; return; }
+  if (c.branch == 3) { coef[0] = 1.0; return; }
+  double p0 = 0.0, p1 = 0.0;  // position of the obstacle's section in the two control frames
+  for (int i = 0; i < c.up; i++) { p0 += S.fLen[0][i][lane]; p1 += S.fLen[1][i][lane]; }
+  const double x0 = c.branch == 1 ? S.inc[0][lane] : 1.5, x1 = c.branch == 1 ? S.inc[1][lane] : 1.5;
+  coef[0] = x0 - p0; coef[1] = (x1 - p1) - coef[0];
+  coef[2] = S.fLen[0][c.up][lane]; coef[3] = S.fLen[1][c.up][lane] - coef[2];
+}
+
+// One work item of the runs pre-pass: the steps [lo, hi] of control-frame interval iv (long intervals are cut into
+// pieces so that the bisections of one utterance spread over many warps; a piece starts with a record of its own, which
+// costs nothing but its 160 bytes); next_lo = first step of the next item (0x7fffffff: none).
+struct NzItem { int32_t iv, lo, hi, next_lo; };
+
+constexpr int RUN_PIECES = 16;  // pieces per interval = warps per CTA of the runs kernel
+__global__ void __launch_bounds__(32 * RUN_PIECES)
+tds_noise_runs_kernel(const int n_tracts, const int n_frames, const int n_items, const int32_t *__restrict__ bounds,
+                      const afs_tube_frame *__restrict__ tubes, const NzItem *__restrict__ items,
+                      const int32_t *__restrict__ iv_first /* per interval: its first item, then the total */,
+                      NzRun *__restrict__ runs, const uint32_t pool_records, uint32_t *__restrict__ ctl) {
+  // CTA = 32 tracts x one control-frame interval (staged once); warp = one piece of the interval
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RunFrames &S = *reinterpret_cast<RunFrames *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tract0 = blockIdx.y * 32, tract = tract0 + lane;
+  const bool active = tract < n_tracts;
+  const int iv = blockIdx.x, item_idx = iv_first[iv] + warp;
+  const bool have_item = item_idx < iv_first[iv + 1];
+  const int i0 = bounds[iv], i1 = bounds[iv + 1];
+  // the two control frames of the interval, all 32 tracts: coalesced reads, transposed into [item][tract]
+  for (int t = warp; t < 32; t += RUN_PIECES) {
+    const int tr = tract0 + t < n_tracts ? tract0 + t : n_tracts - 1;
+    for (int f = 0; f < 2; f++) {
+      const afs_tube_frame *fr = tubes + (size_t)tr * n_frames + iv + f;
+      for (int j = lane; j < AFS_NUM_PM_SECTIONS; j += 32) {
+        const double a = fr->area_cm2[j];
+        S.fA[f][j][t] = a < kMinArea ? kMinArea : a;  // Tube::setPharynxMouthGeometry clamps on the way in
+        S.fLen[f][j][t] = fr->length_cm[j];
+        S.fLat[f][j][t] = fr->laterality[j];
+        if (f == 0) S.art[j][t] = (unsigned char)fr->articulator[j];
+      }
+      if (lane == 0) S.inc[f][t] = fr->incisor_pos_cm;
+    }
+  }
+  __syncthreads();
+  if (!have_item) return;
+  if (!active) return;
+  const NzItem item = items[item_idx];
+  const uint32_t first = (uint32_t)((size_t)tract * (size_t)n_items + (size_t)item_idx);  // fixed place of the piece's first record
+  const uint32_t after = item_idx + 1 < n_items ? first + 1 : 0u;                        // ... and of the next piece's
+  NzRun *prev = nullptr;
+  bool full = false;
+  NoiseCons C[4];
+  auto scan = [&](int n, ScanSig &sg) {
+    const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
+    noise_scan(S, lane, re, re1, C, &sg);
+  };
+  auto emit = [&](int n) {  // C holds the scan of step n
+    if (full) return;
+    uint32_t idx = first;
+    if (prev) {
+      idx = atomicAdd(ctl, 1u);
+      if (idx >= pool_records) { full = true; atomicExch(ctl + 1, 1u); return; }  // (reported as status bit 1 of every tract)
+      prev->next = (uint32_t)n; prev->next_idx = idx;
+    }
+    NzRun &R = runs[idx];
+    R.start = (uint32_t)n; R.next = (uint32_t)item.next_lo; R.next_idx = after; R.pad = 0;
+    uint32_t w4[4];
+    nzc_pack4(C, w4);
+    for (int k = 0; k < 4; k++) {
+      R.slot[k] = w4[k];
+      double cf[4];
+      nz_run_coef(S, lane, C[k], cf);
+      for (int c = 0; c < 4; c++) R.coef[k][c] = cf[c];
+    }
+    prev = &R;
+  };
+  int lo = item.lo;
+  const int last = item.hi;
+  ScanSig sg_lo, sg;
+  scan(lo, sg_lo);
+  emit(lo);  // (always: the coefficients belong to the interval, and the piece starts here)
+  if (last > lo) {
+    int hi_stack[34];
+    ScanSig sg_stack[34];
+    int sp = 0;
+    scan(last, sg);
+    hi_stack[0] = last; sg_stack[0] = sg; sp = 1;
+    while (sp > 0) {
+      const int hi = hi_stack[sp - 1];
+      const ScanSig sg_hi = sg_stack[sp - 1];
+      if (sg_hi == sg_lo) { lo = hi; sp--; continue; }        // nothing changes up to hi
+      if (hi == lo + 1) {                                     // the change is at hi
+        scan(hi, sg);
+        emit(hi);
+        lo = hi; sg_lo = sg_hi; sp--;
+        continue;
+      }
+      const int mid = lo + (hi - lo) / 2;
+      scan(mid, sg);
+      hi_stack[sp] = mid; sg_stack[sp] = sg; sp++;
+    }
+  }
+}
+
 #ifndef AFS_SCAN_THREADS
 #define AFS_SCAN_THREADS 640  // 20 warps at <= 102 registers: the scan is latency-bound, every warp more is throughput
 #endif
 constexpr int SCAN_THREADS = AFS_SCAN_THREADS, SCAN_WARPS = SCAN_THREADS / 32;
+using StepFrames = ScanFrames<LANES>;
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 tds_noise_scan_kernel(const TdsParams P, const KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TdsSmem &S = *reinterpret_cast<TdsSmem *>(smem_raw);
+  StepFrames &S = *reinterpret_cast<StepFrames *>(smem_raw);
   const int hw_lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lane = hw_lane < LANES ? hw_lane : LANES - 1;
   const int tract_raw = blockIdx.x * P.lanes_per_cta + min(lane, P.lanes_per_cta - 1);
   const int tract = tract_raw < P.n_tracts ? tract_raw : P.n_tracts - 1;
   const afs_tube_frame *my_frames = A.tubes + (size_t)tract * P.n_frames;
-  const double *my_glottis = A.glottis + (size_t)tract * P.n_frames * AFS_NUM_GLOTTIS_CONTROL;
   const int T = P.total_steps;
   for (int iv = 0; iv + 1 < P.n_frames; iv++) {
     const int i0 = A.bounds[iv], i1 = A.bounds[iv + 1];
     __syncthreads();  // every warp is past its last read of the previous interval's frames
-    stage_interval(S, lane, warp, my_frames, my_glottis, iv, true);
-    // laterality classes of the sections in this interval (only `max > 0.1` matters, TdsModel.cpp:1545)
-    unsigned long long latAlways = 0, latMaybe = 0;
-    for (int j = 0; j < AFS_NUM_PM_SECTIONS; j++) {
-      const double a = my_frames[iv].laterality[j], b = my_frames[iv + 1].laterality[j];
-      if (a > 0.1000001 && b > 0.1000001) latAlways |= 1ull << j;
-      else if (!(a < 0.0999999 && b < 0.0999999)) latMaybe |= 1ull << j;
+    for (int item = warp; item < 2 * AFS_NUM_PM_SECTIONS + 2; item += SCAN_WARPS) {
+      if (item < 2 * AFS_NUM_PM_SECTIONS) {
+        const int f = item / AFS_NUM_PM_SECTIONS, j = item % AFS_NUM_PM_SECTIONS;
+        const afs_tube_frame *fr = my_frames + iv + f;
+        const double a = fr->area_cm2[j];
+        S.fA[f][j][lane] = a < kMinArea ? kMinArea : a;  // Tube::setPharynxMouthGeometry clamps on the way in
+        S.fLen[f][j][lane] = fr->length_cm[j];
+        S.fLat[f][j][lane] = fr->laterality[j];
+        if (f == 0) S.art[j][lane] = (unsigned char)fr->articulator[j];
+      } else {
+        const int f = item - 2 * AFS_NUM_PM_SECTIONS;
+        S.inc[f][lane] = my_frames[iv + f].incisor_pos_cm;
+      }
     }
     __syncthreads();
     for (int n = i0 + warp; n < i1 && n < T; n += SCAN_WARPS) {
       const double re = __ddiv_rn((double)(n - i0), (double)(i1 - i0)), re1 = __dsub_rn(1.0, re);  // the reference's ratio
       NoiseCons cons[4];
-      noise_scan(S, lane, re, re1, my_frames + iv, my_frames + iv + 1, latAlways, latMaybe, cons);
+      noise_scan(S, lane, re, re1, cons, nullptr);
       const size_t base = ((size_t)blockIdx.x * (size_t)T + (size_t)n) * 4;
+      uint32_t w4[4];
+      nzc_pack4(cons, w4);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        A.nzc_i[(base + k) * 32 + hw_lane] = nzc_pack(cons[k]);
+        A.nzc_i[(base + k) * 32 + hw_lane] = w4[k];
         A.nzc_f[(base + k) * 32 + hw_lane] = cons[k].downF;
       }
     }
@@ -2055,7 +2347,7 @@ tds_noise_scan_kernel(const TdsParams P, const KArgs A) {
 
 // ---- host side ------------------------------------------------------------------
 int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, const int32_t *frame_len,
-                       double fs_tds_hz, int sr_factor, int sm_count, int ring_entries, TdsLaunch *L) {
+                       double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L) {
   TdsParams P;
   memset(&P, 0, sizeof P);
   long total = 0;
@@ -2111,8 +2403,6 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   P.noise = o->generate_noise_sources ? 1 : 0;
   P.nz_F = 1.0 - exp(-2.0 * M_PI * 40.0 * dt);
   P.nz_x2000 = exp(-2.0 * M_PI * (2000.0 * dt));
-  P.nz_ring = NZ_RING;
-  if (ring_entries >= 4 && ring_entries <= NZ_RING) P.nz_ring = ring_entries & ~1;  // (test hook: forces the overflow path)
   P.nm_a = exp(-2.0 * M_PI * 500.0 * dt);
   P.nm_1a = 1.0 - P.nm_a;
   P.dump_step = 0;
@@ -2122,23 +2412,69 @@ int tds_prepare_launch(const afs_tds_options *o, int n_tracts, int n_frames, con
   return AFS_OK;
 }
 
-size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L) {
+// Noise pre-pass: runs mode (tds_noise_runs_kernel) when the control frames are at least 32 steps apart on average,
+// else one record per step (tds_noise_scan_kernel).
+bool tds_noise_runs_mode(const TdsLaunch &L) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
-  return P.noise ? (size_t)P.total_steps * 4 * 32 * (sizeof(uint32_t) + sizeof(double)) : 0;
+  return P.noise && P.n_frames >= 2 && (long)P.total_steps >= 32L * (long)(P.n_frames - 1);
 }
+size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L) {  // per-step records; 0 without noise sources or in runs mode
+  TdsParams P;
+  memcpy(&P, L.params.data(), sizeof P);
+  return (P.noise && !tds_noise_runs_mode(L)) ? (size_t)P.total_steps * 4 * 32 * (sizeof(uint32_t) + sizeof(double)) : 0;
+}
+size_t tds_noise_run_bytes() { return sizeof(NzRun); }
 int tds_lanes_per_cta(const TdsLaunch &L) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
   return P.lanes_per_cta;
 }
 
-// Tracts [tract0, tract0 + n_wave) of the batch (one launch; the caller splits a batch into waves when the noise
-// pre-pass records of all its CTAs would not fit `d_nzc`).
+// Runs mode: the work items of a launch (same for every tract: the control-frame intervals belong to the batch).
+// Intervals are cut into pieces of >= 512 steps, at most 16 per interval.
+void tds_noise_run_items(const TdsLaunch &L, std::vector<int32_t> *items4, std::vector<int32_t> *iv_first) {
+  items4->clear();
+  iv_first->clear();
+  const int T = L.step_bounds.empty() ? 0 : L.step_bounds.back();
+  for (int iv = 0; iv + 1 < L.n_frames; iv++) {
+    const int i0 = L.step_bounds[(size_t)iv], i1 = L.step_bounds[(size_t)iv + 1] < T ? L.step_bounds[(size_t)iv + 1] : T;
+    const int len = i1 - i0;
+    iv_first->push_back((int32_t)(items4->size() / 4));
+    if (len <= 0) continue;
+    int pieces = len / 512;
+    pieces = pieces < 1 ? 1 : pieces > RUN_PIECES ? RUN_PIECES : pieces;
+    for (int q = 0; q < pieces; q++) {
+      const int lo = i0 + (int)((long)len * q / pieces), hi = i0 + (int)((long)len * (q + 1) / pieces) - 1;
+      items4->insert(items4->end(), {iv, lo, hi, 0x7fffffff});
+    }
+  }
+  iv_first->push_back((int32_t)(items4->size() / 4));
+  for (size_t k = 0; k + 1 < items4->size() / 4; k++) (*items4)[4 * k + 3] = (*items4)[4 * (k + 1) + 1];
+}
+// d_runs: pool of `pool_records` records, the first n_tracts * n_items of them the fixed places of the pieces' first
+// records; d_ctl[0] (next free record) must hold n_tracts * n_items, d_ctl[1] (overflow flag) 0.
+cudaError_t launch_noise_runs(const TdsLaunch &L, int n_items, const void *d_items, const int32_t *d_iv_first,
+                              const int32_t *d_bounds, const afs_tube_frame *d_tubes, void *d_runs, uint32_t pool_records,
+                              uint32_t *d_ctl, cudaStream_t stream) {
+  TdsParams P;
+  memcpy(&P, L.params.data(), sizeof P);
+  const dim3 grid((unsigned)(P.n_frames - 1), (unsigned)((P.n_tracts + 31) / 32));
+  cudaError_t e = cudaFuncSetAttribute(tds_noise_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RunFrames));
+  if (e != cudaSuccess) return e;
+  tds_noise_runs_kernel<<<grid, 32 * RUN_PIECES, sizeof(RunFrames), stream>>>(
+      P.n_tracts, P.n_frames, n_items, d_bounds, d_tubes, (const NzItem *)d_items, d_iv_first, (NzRun *)d_runs, pool_records, d_ctl);
+  return cudaGetLastError();
+}
+
+// Tracts [tract0, tract0 + n_wave) of the batch (one launch; with per-step noise records the caller splits a batch
+// into waves when the records of all its CTAs would not fit `d_nzc`).  Noise sources: either the run records of the
+// whole batch (d_runs, d_run_off: indexed by the tract's position in the batch) or the per-step buffer d_nzc.
 cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
-                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const afs_tds_probes *probes,
-                       unsigned int *d_progress, int progress_every, cudaStream_t stream) {
+                       uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const void *d_runs,
+                       const uint32_t *d_run_ctl, int run_items, const afs_tds_probes *probes, unsigned int *d_progress,
+                       int progress_every, cudaStream_t stream) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
@@ -2161,16 +2497,18 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
   if (e != cudaSuccess) return e;
   const int ctas = (P.n_tracts + P.lanes_per_cta - 1) / P.lanes_per_cta;
   const size_t n_out = (size_t)(P.total_steps / P.sr_factor);
-  KArgs A{d_bounds,
-          d_tubes + (size_t)tract0 * P.n_frames,
-          d_glottis + (size_t)tract0 * P.n_frames * AFS_NUM_GLOTTIS_CONTROL,
-          d_audio + (size_t)tract0 * n_out,
-          d_flow ? d_flow + (size_t)tract0 * (size_t)P.total_steps : nullptr,
-          d_status ? d_status + tract0 : nullptr,
-          d_dump,
-          d_seeds ? d_seeds + tract0 : nullptr,
-          nullptr, nullptr, nullptr, nullptr, nullptr,
-          progress_every > 0 ? d_progress : nullptr, progress_every};
+  KArgs A;
+  memset(&A, 0, sizeof A);
+  A.bounds = d_bounds;
+  A.tubes = d_tubes + (size_t)tract0 * P.n_frames;
+  A.glottis = d_glottis + (size_t)tract0 * P.n_frames * AFS_NUM_GLOTTIS_CONTROL;
+  A.audio = d_audio + (size_t)tract0 * n_out;
+  A.flow = d_flow ? d_flow + (size_t)tract0 * (size_t)P.total_steps : nullptr;
+  A.status = d_status ? d_status + tract0 : nullptr;
+  A.dump = d_dump;
+  A.seeds = d_seeds ? d_seeds + tract0 : nullptr;
+  A.progress = progress_every > 0 ? d_progress : nullptr;
+  A.progress_every = progress_every;
   if (P.n_probes > 0) {
     const size_t off = (size_t)tract0 * P.n_probes * (size_t)P.total_steps;
     A.tap_p = probes->pressure_dPa ? probes->pressure_dPa + off : nullptr;
@@ -2178,14 +2516,20 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
     A.tap_out = probes->outflow_cm3_s ? probes->outflow_cm3_s + off : nullptr;
   }
   if (P.noise) {
-    if (!d_nzc) return cudaErrorInvalidValue;
-    A.nzc_i = (uint32_t *)d_nzc;
-    A.nzc_f = (double *)((unsigned char *)d_nzc + (size_t)ctas * (size_t)P.total_steps * 4 * 32 * sizeof(uint32_t));
-    e = cudaFuncSetAttribute(tds_noise_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TdsSmem));
-    if (e != cudaSuccess) return e;
-    tds_noise_scan_kernel<<<ctas, SCAN_THREADS, sizeof(TdsSmem), stream>>>(P, A);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (d_runs && d_run_ctl) {
+      A.runs = (const NzRun *)d_runs + (size_t)tract0 * (size_t)run_items;  // (runs mode is a single launch: tract0 = 0)
+      A.run_items = run_items;
+      A.run_ctl = d_run_ctl;
+    } else {
+      if (!d_nzc) return cudaErrorInvalidValue;
+      A.nzc_i = (uint32_t *)d_nzc;
+      A.nzc_f = (double *)((unsigned char *)d_nzc + (size_t)ctas * (size_t)P.total_steps * 4 * 32 * sizeof(uint32_t));
+      e = cudaFuncSetAttribute(tds_noise_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepFrames));
+      if (e != cudaSuccess) return e;
+      tds_noise_scan_kernel<<<ctas, SCAN_THREADS, sizeof(StepFrames), stream>>>(P, A);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
   }
   kernel<<<ctas, TDS_THREADS, sizeof(TdsSmem), stream>>>(P, A);
   return cudaGetLastError();

@@ -377,7 +377,11 @@ int afs_play_target_sequences(afs_ctx *ctx, const afs_tds_options *opts, int n_s
  * flow (nullable) [n_tracts][n_out*sr_factor], the radiated flow returned by
  * TdsModel::proceedTimeStep per simulation step; status (nullable)
  * [n_tracts]: bit0 = non-finite value seen (the reference prints and carries
- * on, TdsModel.cpp:2267).
+ * on, TdsModel.cpp:2267); bit1 (device-buffer entry points only, all tracts at
+ * once) = the record pool of the noise-source pre-pass was too small and the
+ * audio is invalid -- the host-buffer entry points repeat the call with a
+ * larger pool themselves, callers of the *_device variants raise it with
+ * afs_debug_set("tds.noise_run_pool_factor").
  * seeds (nullable) [n_tracts]: per-tract srand() seeds, used only with
  * generate_noise_sources.
  */
@@ -429,9 +433,12 @@ int afs_tds_synthesize_probed_device(afs_ctx *ctx, const afs_tds_options *opts, 
  * (TdsModel.h:141-143,166-167,184). */
 int afs_tds_set_state_dump(afs_ctx *ctx, int step, double *host_out473);
 
-/* Test hooks, not tuning knobs of the product: "tds.noise_scan_bytes" (device budget of the noise pre-pass records;
- * 0 = derived from the free device memory: tests force several waves with a small value), "tds.noise_ring_entries"
- * (ring of pre-generated noise sums; 0 = full: tests force the overflow path).  Unknown keys: AFS_ERR_BAD_ARGUMENT. */
+/* Test hooks, not tuning knobs of the product: "tds.noise_scan_bytes" (device budget of the per-step noise pre-pass
+ * records, used when the control frames are a few steps apart; 0 = derived from the free device memory: tests force
+ * several waves with a small value); "tds.noise_run_pool_factor" (records of the run-record pool of the noise pre-pass per
+ * piece of a control-frame interval, default 32: tests force the overflow path with 2); "tds.d2h_slices" (time slices
+ * of the overlapped device-to-host copy of afs_tds_synthesize, 0 = default 16, 1 = one copy after the kernel).  Unknown
+ * keys: AFS_ERR_BAD_ARGUMENT. */
 int afs_debug_set(afs_ctx *ctx, const char *key, int64_t value);
 
 /* Measures the FP64 FMA peak of the bound device (independent DFMA chains,

@@ -235,11 +235,11 @@ def test_noise_sources_against_oracle(ctx, oracle, shapes):
     assert np.array_equal(a[perm], a2)
 
 
-def test_noise_sum_ring_overflow(ctx, oracle, shapes):
-    """The sums of twelve rand() draws are generated ahead of time into a per-tract ring (28 entries); a step that
-    draws more samples than the ring holds takes the rest straight from the generator, in the reference's order.
-    Forced here with a ring of 4 (consonant transitions draw 5-12 samples per step): bit-identical to the run with
-    the full ring, and within tolerance of the oracle."""
+def test_noise_many_sources_per_step(ctx, oracle, shapes):
+    """Consonant transitions keep 5-12 noise sources drawing in the same step.  The sums of twelve rand() draws are
+    generated ahead of time into a per-tract ring (44 entries >= the 41 sources a step can have + the two entries the
+    refill may leave empty) and handed out by rank -- the k-th drawing source, in ascending order, takes the k-th
+    sum, like the reference's single rand() stream.  Three control frames, more tracts than one CTA holds."""
     import areafunctionsynthesis_b200 as afs
     from oracle.pyoracle import tds_options_default as oracle_opts
     n = len(shapes["names"])
@@ -252,17 +252,91 @@ def test_noise_sum_ring_overflow(ctx, oracle, shapes):
     seeds = rng.integers(0, 2**32, size=B, dtype=np.uint64).astype(np.uint32)
     fl = [700, 500]
     on = afs.tds_options_default(noise=True)
-    a0, u0, st0 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
-    ctx.debug_set("tds.noise_ring_entries", 4)
-    try:
-        a1, u1, st1 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
-    finally:
-        ctx.debug_set("tds.noise_ring_entries", 0)
-    assert not st0.any() and not st1.any()
-    assert np.array_equal(a0, a1) and np.array_equal(u0, u1)
+    a1, u1, st1 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=on, seeds=seeds, want_flow=True)
+    assert not st1.any()
     ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=oracle_opts(noise=True), seeds=seeds)
     for b in range(B):
         assert rel_err(u1[b], uo[b]) <= TOL and rel_err(a1[b], ao[b]) <= TOL, (b, rel_err(u1[b], uo[b]))
+
+
+def test_noise_run_records_equal_per_step_records(ctx, shapes):
+    """The constrictions of a step depend on the geometry only.  With control frames far apart the pre-pass finds the
+    runs of steps with the same constrictions by bisection (tds_noise_runs_kernel: a few hundred scans per utterance);
+    with control frames a few steps apart it scans every step (tds_noise_scan_kernel).  The same utterance given
+    once as 2 control frames and once as the same linear glide resampled... cannot be bit-equal (the interpolation
+    rounds differently), so the check is made where both kernels see the SAME intervals: an utterance of 3 frames
+    whose intervals are 40 steps long runs in runs mode (>= 32 steps per interval); the same frames with intervals
+    of 20 steps in per-step mode; both must agree with the oracle (below) -- and here, a batch in runs mode must not
+    depend on how the tracts are grouped (32 tracts per pre-pass CTA, 28 per time-loop CTA)."""
+    import areafunctionsynthesis_b200 as afs
+    n = len(shapes["names"])
+    rng = np.random.default_rng(99)
+    B = 70
+    fr = shapes["frames"][rng.integers(0, n, size=(B, 4))].copy()
+    gl = np.tile(G0, (B, 4, 1)); gl[:, :, 0] = rng.uniform(90, 220, size=(B, 4)); gl[:, :, 5] = -20.0
+    seeds = rng.integers(1, 2**31 - 1, size=B).astype(np.uint32)
+    on = afs.tds_options_default(noise=True)
+    a, _, st = ctx.tds_synthesize(fr, gl, [300, 200, 100], 44100.0, 2, opts=on, seeds=seeds)
+    assert not st.any()
+    for sel in ([0], [31, 32, 33], list(range(27, 57)), [69]):
+        a2, _, _ = ctx.tds_synthesize(fr[sel], gl[sel], [300, 200, 100], 44100.0, 2, opts=on, seeds=seeds[sel])
+        assert np.array_equal(a2, a[sel]), sel
+
+
+def test_noise_run_pool_overflow_is_reported_and_repaired(ctx, oracle, shapes):
+    """The run records of the noise pre-pass live in a pool sized from the number of interval pieces; a pool that turns
+    out too small is reported as status bit 1 by the device entry point (never silently wrong audio) and repaired by
+    the host entry point, which repeats the call with a larger pool."""
+    import torch
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    n = len(shapes["names"])
+    rng = np.random.default_rng(5)
+    B = 40
+    fr = shapes["frames"][rng.integers(0, n, size=(B, 2))].copy()
+    gl = np.tile(G0, (B, 2, 1)); gl[:, :, 5] = -15.0
+    seeds = np.arange(1, B + 1, dtype=np.uint32)
+    on = afs.tds_options_default(noise=True)
+    ref, _, st = ctx.tds_synthesize(fr, gl, [400], 44100.0, 2, opts=on, seeds=seeds)
+    assert not st.any()
+    ctx.debug_set("tds.noise_run_pool_factor", 2)
+    try:
+        d_fr = torch.from_numpy(fr.view(np.uint8).reshape(B, -1)).cuda(); d_gl = torch.from_numpy(gl).cuda()
+        d_seeds = torch.from_numpy(seeds.view(np.int32)).cuda()
+        d_a = torch.zeros(B, 400, dtype=torch.float64, device="cuda"); d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+        # a pool of 2 records per piece + 4096: force the overflow with a batch whose pieces need more
+        big = np.tile(fr, (40, 1)); bigg = np.tile(gl, (40, 1, 1)); bigs = np.tile(seeds, 40)
+        d_frb = torch.from_numpy(big.view(np.uint8).reshape(len(big), -1)).cuda(); d_glb = torch.from_numpy(bigg).cuda()
+        d_sb = torch.from_numpy(bigs.view(np.int32)).cuda()
+        d_ab = torch.zeros(len(big), 400, dtype=torch.float64, device="cuda"); d_stb = torch.zeros(len(big), dtype=torch.int32, device="cuda")
+        ctx.tds_synthesize_device(d_frb, d_glb, len(big), 2, [400], d_ab, torch.cuda.current_stream().cuda_stream, opts=on,
+                                  d_seeds=d_sb, d_status=d_stb)
+        torch.cuda.synchronize()
+        assert bool((d_stb & 2).all()), "the device entry point must report the overflow"
+        a2, _, st2 = ctx.tds_synthesize(big, bigg, [400], 44100.0, 2, opts=on, seeds=bigs)   # host entry point: repairs
+        assert not st2.any() and np.array_equal(a2[:B], ref) and np.array_equal(a2[-B:], ref)
+    finally:
+        ctx.debug_set("tds.noise_run_pool_factor", 32)
+
+
+@pytest.mark.parametrize("fl", [[16, 16, 16, 16], [15, 15, 15, 15], [300, 1, 1, 300], [1, 400, 1, 2]])
+def test_noise_prepass_modes_against_oracle(ctx, oracle, shapes, fl):
+    """Interval lengths on both sides of the switch between the two pre-pass kernels (32 simulation steps per
+    interval on average), and ragged ones: consonant shapes, so that the constrictions change inside the intervals."""
+    import areafunctionsynthesis_b200 as afs
+    from oracle.pyoracle import tds_options_default as oracle_opts
+    n = len(shapes["names"])
+    rng = np.random.default_rng(sum(fl))
+    B = 12
+    fr = shapes["frames"][rng.integers(0, n, size=(B, 5))].copy()
+    fr["laterality"][:, 1::2, 10:30] = rng.random((B, 2, 20)) * 0.2   # lateral constrictions switch the sources off
+    gl = np.tile(G0, (B, 5, 1)); gl[:, :, 0] = rng.uniform(90, 220, size=(B, 5)); gl[:, :, 5] = -15.0
+    seeds = rng.integers(1, 2**31 - 1, size=B).astype(np.uint32)
+    a, u, st = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=afs.tds_options_default(noise=True), seeds=seeds, want_flow=True)
+    ao, uo = oracle.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=oracle_opts(noise=True), seeds=seeds)
+    assert not st.any()
+    for b in range(B):
+        assert rel_err(u[b], uo[b]) <= TOL and np.max(np.abs(a[b] - ao[b])) <= TOL * np.max(np.abs(ao)) + 1e-30, (b, rel_err(u[b], uo[b]))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -296,30 +370,33 @@ def test_transvelar_coupling_and_variable_entrance_loss(ctx, oracle, shapes, tv,
 
 
 def test_noise_prepass_waves(ctx, shapes):
-    """The constriction records of the noise pre-pass live in a bounded device buffer; a batch that does not fit runs
-    as several waves of CTAs.  Forced here with a tiny budget: results identical to the single-wave run, and to the
-    same utterances run one by one (every tract depends on its own inputs and seed only)."""
+    """Control frames a few steps apart: the per-step constriction records of the noise pre-pass live in a bounded
+    device buffer; a batch that does not fit runs as several waves of CTAs.  Forced here with a tiny budget: results
+    identical to the single-wave run, and to the same utterances run one by one (every tract depends on its own inputs
+    and seed only)."""
     import areafunctionsynthesis_b200 as afs
     n = len(shapes["names"])
     rng = np.random.default_rng(3)
     B = 700  # 5 tracts per CTA on 148 SMs -> 140 CTAs
     idx = rng.integers(0, n, size=(B, 2))
-    fr = np.stack([shapes["frames"][idx[:, 0]], shapes["frames"][n + idx[:, 1]]], axis=1)
-    gl = np.tile(np.array([[120.0, 8000.0, 0.01, 0.01, 0.0, -40.0], [160.0, 8000.0, 0.01, 0.01, 0.0, -40.0]]), (B, 1, 1))
+    two = np.stack([shapes["frames"][idx[:, 0]], shapes["frames"][n + idx[:, 1]]], axis=1)
+    fr = two[:, np.arange(11) % 2]          # 10 intervals of 15 output samples = 30 steps each: per-step records
+    fl = [15] * 10
+    gl = np.tile(np.array([120.0, 8000.0, 0.01, 0.01, 0.0, -40.0]), (B, 11, 1))
     gl[:, :, 0] += rng.uniform(-30, 60, size=(B, 1))
     seeds = rng.integers(1, 2**31 - 1, size=B).astype(np.uint32)
     o = afs.tds_options_default(noise=True)
-    a0, _, st0 = ctx.tds_synthesize(fr, gl, [150], 44100.0, 2, opts=o, seeds=seeds)
+    a0, _, st0 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=o, seeds=seeds)
     assert not st0.any() and np.abs(a0).max() > 0
     per_cta = 300 * 4 * 32 * 12  # record bytes of one CTA for 300 steps
     ctx.debug_set("tds.noise_scan_bytes", per_cta * 37)  # 37 CTAs per wave -> 4 waves
     try:
-        a1, _, st1 = ctx.tds_synthesize(fr, gl, [150], 44100.0, 2, opts=o, seeds=seeds)
+        a1, _, st1 = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=o, seeds=seeds)
     finally:
         ctx.debug_set("tds.noise_scan_bytes", 0)
     assert np.array_equal(a0, a1) and not st1.any()
     for b in (0, 4, 5, 699):
-        ab, _, _ = ctx.tds_synthesize(fr[b:b + 1], gl[b:b + 1], [150], 44100.0, 2, opts=o, seeds=seeds[b:b + 1])
+        ab, _, _ = ctx.tds_synthesize(fr[b:b + 1], gl[b:b + 1], fl, 44100.0, 2, opts=o, seeds=seeds[b:b + 1])
         assert np.array_equal(ab[0], a0[b]), b
 
 
@@ -411,8 +488,11 @@ def test_host_call_overlapped_copies_equal_device_path(ctx, shapes):
             d_gl = torch.from_numpy(gl).cuda()
             d_seeds = torch.from_numpy(seeds.view(np.int32)).cuda()
             d_a = torch.zeros(B, n_out, dtype=torch.float64, device="cuda")
-            ctx.tds_synthesize_device(d_fr, d_gl, B, 2, [n_out], d_a, torch.cuda.current_stream().cuda_stream, opts=o, d_seeds=d_seeds)
+            d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+            ctx.tds_synthesize_device(d_fr, d_gl, B, 2, [n_out], d_a, torch.cuda.current_stream().cuda_stream, opts=o, d_seeds=d_seeds,
+                                      d_status=d_st)
             torch.cuda.synchronize()
+            assert not bool(d_st.any())
             a, _, st = ctx.tds_synthesize(fr, gl, [n_out], 44100.0, 2, opts=o, seeds=seeds)   # pageable
             assert not st.any() and np.array_equal(a, d_a.cpu().numpy()), (B, noise)
             h_a = torch.zeros(B, n_out, dtype=torch.float64).pin_memory()

@@ -6,20 +6,25 @@ import areafunctionsynthesis_b200 as afs
 from bench import make_tds_batch
 B, T = 4096, int(os.environ.get("T", "2205"))
 ctx = afs.Context(0)
+if os.environ.get('SLICES'): ctx.debug_set('tds.d2h_slices', int(os.environ['SLICES']))
 fr, gl = make_tds_batch(B, 1)
 buf = np.zeros(473); ctx.set_state_dump(10**9, buf)
 noise = os.environ.get('NOISE', '0') == '1'
 a, _, _ = ctx.tds_synthesize(fr, gl, [T // 2 + 1], 44100.0, 2, opts=afs.tds_options_default(noise=noise))
 steps = (T // 2 + 1) * 2
 names = ["top/stage", "passA", "B1 wait", "elim/aux", "reduced", "B5 wait", "back", "B6 wait"]
-roles = ["GP", "P1", "P2", "M0", "M1", "M2", "M3", "NV", "T0", "T1", "N2", "T2", "X1", "F", "X2", "N1"]
+roles = ["GP", "P1", "P2", "M0", "M1", "M2", "M3", "NV", "T0", "T1", "N2", "T2", "F", "N1", "X1", "X2"]
 t = buf[:128].reshape(16, 8) / steps
 print("cycles per step, per warp (lane 0 of CTA 0):")
 print("warp " + " ".join(f"{n[:10]:>10s}" for n in names) + "      total")
 for w in range(16):
     print(f"{roles[w]:>4s} " + " ".join(f"{v:10.0f}" for v in t[w]) + f" {t[w].sum():10.0f}")
 sw = buf[136:200].reshape(16, 4) / steps
-print("static warps, swarp_eliminate: first row | sinus leaves | chain | publish")
+print("static warps, swarp_eliminate: first row | sinus leaves | chain | publish   (X2: noise_stage slots | decays | draws | refill)")
 for w in range(16):
     if sw[w].sum() > 0:
         print(f"{roles[w]:>4s} " + " ".join(f"{v:8.0f}" for v in sw[w]))
+
+x1 = buf[200:336] / steps; x2 = buf[336:472] / steps
+print("pass-A cycles per step over the first 136 CTAs: X1 min %.0f median %.0f max %.0f | X2 min %.0f median %.0f max %.0f" % (
+    x1.min(), np.median(x1), x1.max(), x2.min(), np.median(x2), x2.max()))
