@@ -33,6 +33,7 @@ struct afs_ctx {
   unsigned int *progress_h = nullptr, *progress_d = nullptr;
   // test hooks (afs_debug_set)
   int64_t dbg_noise_scan_bytes = 0;
+  int dbg_small_batch_max = -1;  // largest batch served by tds_small_kernel (-1: 3 tracts per SM, 0: never)
   int dbg_d2h_slices = 0;
   int run_pool_factor = 32;   // records of the noise pre-pass pool per piece (see tds_run_device); grows on overflow
 };
@@ -815,6 +816,19 @@ int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int 
   // (pageable source: staged before the call returns)
   cudaError_t e = cudaMemcpyAsync(d_bounds, L.step_bounds.data(), sizeof(int32_t) * (size_t)n_frames, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "cudaMemcpyAsync(step bounds)"); }
+  // Small batches: tds_batch_kernel advances up to 28 tracts per SM in lock step and takes the same time for one; a
+  // batch that leaves most of its lanes empty runs on tds_small_kernel (one tract per CTA, one tube section per lane).
+  {
+    const int small_max = ctx->dbg_small_batch_max >= 0 ? ctx->dbg_small_batch_max : 3 * ctx->sm_count;  // (three resident CTAs per SM)
+    if (n_tracts <= small_max && tds_small_supported(L) && !(d_probes && d_probes->n_probes > 0) &&
+        !(ctx->dump_step > 0 && ctx->dump_host)) {
+      e = launch_tds_small(L, (const int32_t *)d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, stream);
+      release();
+      if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_tds_small");
+      ctx->launches++;
+      return AFS_OK;
+    }
+  }
   if (ctx->dump_step > 0 && ctx->dump_host) {
     if ((rc = pool_alloc(ctx, 473 * sizeof(double), stream, &d_dump))) { release(); return rc; }
     cudaMemsetAsync(d_dump, 0, 473 * sizeof(double), stream);
@@ -922,6 +936,7 @@ int afs_debug_set(afs_ctx *ctx, const char *key, int64_t value) {
   if (!key) return AFS_ERR_BAD_ARGUMENT;
   if (!strcmp(key, "tds.noise_scan_bytes")) ctx->dbg_noise_scan_bytes = value;
   else if (!strcmp(key, "tds.d2h_slices")) ctx->dbg_d2h_slices = (int)value;
+  else if (!strcmp(key, "tds.small_batch_max")) ctx->dbg_small_batch_max = (int)value;
   else if (!strcmp(key, "tds.noise_run_pool_factor")) ctx->run_pool_factor = value < 2 ? 2 : value > 4096 ? 4096 : (int)value;
   else return AFS_ERR_BAD_ARGUMENT;
   return AFS_OK;

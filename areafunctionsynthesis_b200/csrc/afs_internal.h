@@ -72,6 +72,10 @@ cudaError_t launch_noise_runs(const TdsLaunch &L, int n_items, const void *d_ite
                               const int32_t *d_bounds, const afs_tube_frame *d_tubes, void *d_runs, uint32_t pool_records,
                               uint32_t *d_ctl, cudaStream_t stream);
 int tds_total_steps(const TdsLaunch &L);
+// small batches: one tract per CTA, one tube section per lane (tds_small_kernel)
+bool tds_small_supported(const TdsLaunch &L);
+cudaError_t launch_tds_small(const TdsLaunch &L, const int32_t *d_bounds, const afs_tube_frame *d_tubes, const double *d_glottis,
+                             double *d_audio, double *d_flow, uint32_t *d_status, cudaStream_t stream);
 size_t tds_noise_scan_bytes_per_cta(const TdsLaunch &L);  // per-step records; 0 without noise sources or in runs mode
 int tds_lanes_per_cta(const TdsLaunch &L);
 size_t tds_smem_bytes();

@@ -43,6 +43,7 @@
 // section instead of ~15 div/sqrt, branch-free MUFU+Newton rcp/sqrt, zero-fill
 // elimination order), FMA contraction on; parity gate 1e-6 relative max-abs.
 #include <cmath>
+#include <cstdio>
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
@@ -2343,6 +2344,631 @@ tds_noise_scan_kernel(const TdsParams P, const KArgs A) {
       }
     }
   }
+}
+
+// ==================================================================================
+// K1s `tds_small_kernel`: the same simulation for SMALL batches -- one tract per CTA, one tube section per lane
+// ==================================================================================
+// tds_batch_kernel maps a tract to a lane: a CTA advances 28 tracts in ~5.5 us per step whether it holds 28 tracts or
+// one, so a batch of a few hundred utterances (a shard of BASELINE configs[3] on one of eight GPUs) leaves the SM
+// idle.  Here the roles are turned round: a CTA (4 section warps + 1 auxiliary warp) is ONE tract, a lane is one of
+// the 93 tube sections (and the current flowing into it), several CTAs share an SM.  The step of a tract is then
+// bound by the depth of its dependency chain, not by the serial work of a warp:
+//   * update, elements, matrix rows: all sections at once (one lane each);
+//   * the linear system (negated: SPD, a tree of chains) in O(log n) depth: the rigid chains (trachea, nose behind
+//     the velum port, piriform fossa, sinuses, nostril radiation) have CONSTANT pivots -- factored once in the
+//     prologue, only their right-hand sides are eliminated per step, a first-order linear recurrence evaluated as a
+//     prefix scan with warp shuffles; the three chains with changing geometry (glottis + pharynx 23..40, mouth
+//     41..64, velum port 65..69) are solved by parallel cyclic reduction with warp shuffles, each for two right-hand
+//     sides (its own, and a unit load at its junction end), and joined by the 3 x 3 system of the velum clique
+//     {40, 41, 65};
+//   * the glottis model and the output filters run on the auxiliary warp beside the solve.
+// Same arithmetic building blocks as tds_batch_kernel (section_elements, row_dyn, the glottis functions, fast_rcp);
+// parity bar 1e-6 like there.  Default-path options only (turbulence, soft walls, skin radiation, fossa, inner length
+// corrections, entrance loss constants); noise sources, transvelar coupling, the variable entrance loss, taps and the
+// flow source stay with tds_batch_kernel (tds_small_supported).
+namespace k1s {
+
+constexpr int NSW = 4;                 // section warps
+constexpr int THREADS = 32 * (NSW + 1);
+constexpr int ZC = NC;                 // index of an always-zero current in U[]
+// chain T = currents 23..40 on warp 0, chain M = 41..64 on warp 1, chain N = 65..69 on warp 2 (lanes 0..4)
+
+struct Smem {
+  // section records (index = tube section; NS = all-zero dummy), written in phase 1
+  double E[NSX], D[NSX], L[NSX], R0[NSX], R1[NSX], I[NSX], AR[NSX], C[NSX];
+  double U[NC + 1];                    // last solution of every current; U[ZC] = 0
+  double fA[2][AFS_NUM_PM_SECTIONS], fLen[2][AFS_NUM_PM_SECTIONS], velum[2], gctl[2][AFS_NUM_GLOTTIS_CONTROL];
+  double glLen[2][2], glArea[2][2];    // glottis geometry, double buffered by step parity
+  double p4[4];                        // pressures of sections 22..25 after the last update
+  double sch[8];                       // Schur contributions across warps: [0] rhs of 23 (trachea), [1..5] fossa -> {28, 29}
+  double jn[6];                        // y, z of the junction ends of the chains T, M, N
+  double urad[2][2];                   // radiated flow of the mouth / the nostrils, double buffered by step parity
+  double toneX[4], toneY[4], chebX[8], chebY[8];  // output filters (auxiliary warp, lane 0)
+};
+
+// static description of a lane
+struct Lane {
+  int sec;        // tube section = current flowing into it; -1: idle lane
+  int prev;       // section the current comes from (-1: lungs)
+  int sib;        // the other current flowing out of `prev` (ZC: none)
+  int out1, out2; // currents flowing out of the section (ZC: none)
+  int wall;       // 0 standard, 1 trachea, 2 sinus, 3 none (glottis)
+  bool dyn, glottal, velum;
+};
+__device__ __forceinline__ Lane lane_of(int warp, int lane) {
+  Lane q;
+  int s = -1;
+  if (warp == 0) s = lane < 18 ? 23 + lane : -1;
+  else if (warp == 1) s = lane < 24 ? 41 + lane : -1;
+  else if (warp == 2) s = lane < 19 ? 65 + lane : lane < 23 ? SINUS0 + (lane - 19) : -1;
+  else if (warp == 3) s = lane < 23 ? lane : lane < 28 ? FOSSA0 + (lane - 23) : -1;
+  q.sec = s;
+  q.prev = s <= 0 ? -1 : s == NOSE0 ? PHAR_LAST : s == FOSSA0 ? PHAR0 + FOSSA_COUPLING : s == 89 ? 73 : s == 90 ? 74 : s == 91 ? 76 : s == 92 ? 77 : s - 1;
+  q.sib = s == 29 ? 84 : s == 84 ? 29 : s == 41 ? 65 : s == 65 ? 41 : s == 74 ? 89 : s == 89 ? 74 : s == 75 ? 90 : s == 90 ? 75 :
+          s == 77 ? 91 : s == 91 ? 77 : s == 78 ? 92 : s == 92 ? 78 : ZC;
+  q.out1 = s < 0 ? ZC : s == MOUTH_LAST ? 93 : s == NOSE_LAST ? 95 : (s == FOSSA_LAST || s >= SINUS0) ? ZC : s + 1;
+  q.out2 = s == 28 ? 84 : s == 40 ? 65 : s == MOUTH_LAST ? 94 : s == NOSE_LAST ? 96 : s == 73 ? 89 : s == 74 ? 90 : s == 76 ? 91 : s == 77 ? 92 : ZC;
+  q.glottal = s == GLOT_LO || s == GLOT_UP;
+  q.velum = s >= NOSE0 && s <= NOSE0 + 3;
+  q.dyn = s >= GLOT_LO && s <= NOSE0 + 3;
+  q.wall = s < 0 ? 3 : q.glottal ? 3 : s <= TRACHEA_LAST ? 1 : s >= SINUS0 ? 2 : 0;
+  return q;
+}
+
+__device__ __forceinline__ void bar_sec() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NSW) : "memory"); }
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// Parallel cyclic reduction of a symmetric tridiagonal system on the lanes 0..n-1 of a warp, two right-hand sides.
+// lo = coupling to lane - 1 (0 on lane 0), d = pivot, r1 / r2 = right-hand sides; lanes >= n pass d = 1, lo = r = 0.
+// Returns the two solutions.
+__device__ __forceinline__ void pcr2(const int lane, const int n, double lo, double d, double r1, double r2, double &y, double &z) {
+  double up = shfl(lo, lane + 1);  // coupling to lane + 1 (symmetry)
+  if (lane + 1 >= n) up = 0.0;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    if (s >= n) break;  // (warp-uniform)
+    const double w = fast_rcp(d);
+    const int im = lane - s, ip = lane + s;
+    const double wm = shfl(w, im), wp = shfl(w, ip);
+    const double lm = shfl(lo, im), um = shfl(up, im), lp = shfl(lo, ip), upp = shfl(up, ip);
+    const double r1m = shfl(r1, im), r1p = shfl(r1, ip), r2m = shfl(r2, im), r2p = shfl(r2, ip);
+    const double k1 = im >= 0 ? lo * wm : 0.0, k2 = ip < n ? up * wp : 0.0;
+    d = fma(-k1, um, fma(-k2, lp, d));
+    r1 = fma(-k1, r1m, fma(-k2, r1p, r1));
+    r2 = fma(-k1, r2m, fma(-k2, r2p, r2));
+    lo = -k1 * lm;
+    up = -k2 * upp;
+  }
+  const double w = fast_rcp(d);
+  y = r1 * w; z = r2 * w;
+}
+
+// Inclusive scan of the affine recurrence x_k = b_k + a_k x_{k-1} over the lanes lo..hi of a warp (upwards: dir = +1,
+// x_{lo-1} = 0) or x_k = b_k + a_k x_{k+1} (downwards: dir = -1, x_{hi+1} = 0).  The a_k are constants of the launch:
+// aw[j] = product of the a's of the window of 2^j lanes ending at this lane (precomputed), so a step is one shuffle
+// and one FMA.
+__device__ __forceinline__ double scan_affine(const int lane, const int lo, const int hi, const int dir, double b, const double (&aw)[5]) {
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const int src = lane - dir * (1 << j);
+    const double bp = shfl(b, src);
+    if (lane >= lo && lane <= hi && src >= lo && src <= hi) b = fma(aw[j], bp, b);
+  }
+  return b;
+}
+// window products for scan_affine (prologue): a = this lane's own factor
+__device__ __forceinline__ void scan_windows(const int lane, const int lo, const int hi, const int dir, double a, double (&aw)[5]) {
+  if (lane < lo || lane > hi) a = 0.0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    aw[j] = a;
+    const int src = lane - dir * (1 << j);
+    const double ap = shfl(a, src);
+    a = (src >= lo && src <= hi) ? a * ap : 0.0;   // (a window that would leave the chain is never used)
+  }
+}
+
+struct Args {
+  const int32_t *bounds;
+  const afs_tube_frame *tubes;
+  const double *glottis;
+  double *audio, *flow;
+  uint32_t *status;
+};
+
+__global__ void __launch_bounds__(THREADS, 3)
+tds_small_kernel(const TdsParams P, const Args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tract = blockIdx.x;
+  const Lane Q = lane_of(warp, lane);
+  const int sec = Q.sec;
+  const bool aux = warp == NSW;
+  const bool on = !aux && sec >= 0;
+  const afs_tube_frame *my_frames = A.tubes + (size_t)tract * P.n_frames;
+  const double *my_glottis = A.glottis + (size_t)tract * P.n_frames * AFS_NUM_GLOTTIS_CONTROL;
+  const int T = P.total_steps, n_out = T / P.sr_factor;
+
+  // ---- prologue: zero state, static records --------------------------------------------
+  for (int i = threadIdx.x; i < NSX; i += THREADS) { S.E[i] = S.D[i] = S.L[i] = S.R0[i] = S.R1[i] = S.I[i] = S.AR[i] = S.C[i] = 0.0; }
+  for (int i = threadIdx.x; i <= NC; i += THREADS) S.U[i] = 0.0;
+  if (threadIdx.x < 8) S.sch[threadIdx.x] = 0.0;
+  if (threadIdx.x < 6) S.jn[threadIdx.x] = 0.0;
+  if (threadIdx.x < 4) { S.p4[threadIdx.x] = 0.0; (&S.urad[0][0])[threadIdx.x] = 0.0; S.toneX[threadIdx.x] = 0.0; S.toneY[threadIdx.x] = 0.0; }
+  if (threadIdx.x < 8) { S.chebX[threadIdx.x] = 0.0; S.chebY[threadIdx.x] = 0.0; }
+  // static record of this lane's section (as in tds_batch_kernel's prologue)
+  SRec rec{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double kc0 = 0.0, kc1 = 0.0, kc2 = 0.0, ka = 0.0;
+  if (on) {
+    const int wt = Q.wall;
+    if (wt < 3) { ka = P.kalpha[wt]; kc0 = P.kc[wt][0]; kc1 = P.kc[wt][1]; kc2 = P.kc[wt][2]; }
+    if (!Q.dyn) {
+      const StaticSection q = static_section(sec);
+      double Ls, Rs, invr, circ, surface;
+      if (sec >= SINUS0) {
+        Ls = kRho * (q.length / q.area);
+        Rs = (8.0 * kMu * kPi * q.length) / (q.area * q.area);
+        invr = 1.0 / sqrt(q.area / kPi);
+        surface = P.sinus_surface[sec - SINUS0];
+      } else {
+        section_elements(q.area, q.length, false, Ls, Rs, invr, circ);
+        surface = circ * q.length;
+      }
+      if (surface < kMinArea) surface = kMinArea;
+      const double Cc = q.volume / (kRho * kC * kC);
+      const double alpha = P.soft_walls ? surface * P.kalpha[wt] : 0.0;
+      rec.L = Ls; rec.R1 = Rs; rec.R0 = Rs; rec.invr = invr; rec.alpha = alpha;
+      rec.E = P.dtth / (Cc + alpha);
+      if (sec == FOSSA0 && !P.fossa) rec.R0 = 8.0 * kMu * q.length * kPi / (kMinArea * kMinArea);
+      S.E[sec] = rec.E; S.L[sec] = rec.L; S.R0[sec] = rec.R0; S.R1[sec] = rec.R1; S.I[sec] = rec.invr; S.AR[sec] = q.area;
+    }
+  }
+  __syncthreads();
+
+  // ---- prologue: constant pivots of the rigid chains --------------------------------------
+  // Rows whose two sections are rigid have constant coefficients: currents 0..22 (trachea), 70..83 (nose), 85..88
+  // (fossa), the sinus leaves 89..92 and the nostril radiation pair 95, 96.  Elimination order: leaves first, then
+  // every chain towards the current that links it to the moving part (23, 69, 84).
+  //   sw   = 1 / pivot of this lane's current after the eliminations before it
+  //   st   = coupling to the next current in elimination order * sw  (the factor of the right-hand-side recurrence)
+  //   sdd  = what the chain takes off the pivot of the linking current (lane of the chain's last eliminated current)
+  double sw = 0.0, st = 0.0;
+  double fw[5] = {0, 0, 0, 0, 0}, bw[5] = {0, 0, 0, 0, 0};  // window products of the forward / backward scans
+  // sinus leaf constants (leaf lanes 19..22 of warp 2) and what they do to their two hosts (host lanes)
+  double leaf_w = 0.0, leaf_e = 0.0, leaf_g = 0.0;
+  // nostril radiation pair (lane of section 83): factors of radiation_eliminate with constant geometry
+  double nr_wL = 0.0, nr_wR = 0.0, nr_o = 0.0, nr_e = 0.0, nr_g = 0.0, nr_LA = 0.0, nr_LAB = 0.0;
+  double sdd_link = 0.0;  // (lanes of the linking currents 23 / 69 / 84: constant Schur term of their pivot)
+  {
+    // plain diagonal of a static row and its coupling to the current before it
+    auto sdiag = [&](int s) {
+      const int a = s == 0 ? NS : (s == 89 ? 73 : s == 90 ? 74 : s == 91 ? 76 : s == 92 ? 77 : s - 1);
+      return S.E[s] + S.E[a] + (S.L[a] + S.L[s]) * P.idt + S.R1[a] + S.R0[s];
+    };
+    // every lane evaluates the (short) serial recurrences it needs itself: launch-constant, a few dozen flops
+    auto nose_pivot = [&](int k) {  // pivot of current k in 70..83 after leaves, radiation and the currents behind it
+      double d_next = 0.0, o_next = 0.0;  // of current k+1 (eliminated before k)
+      double dk = 0.0;
+      for (int c = NOSE_LAST; c >= k; c--) {
+        dk = sdiag(c);
+        if (c == NOSE_LAST) {  // nostril radiation pair folded into 83 (radiation_eliminate)
+          const double E_A = S.E[c], L_A = S.L[c], R_A = S.R1[c], invr = S.I[c], G_A = L_A * P.idt + R_A;
+          const double R_rad = (128.0 * kRho * kC / (9.0 * kPi * kPi)) * (invr * invr * (1.0 / kPi));
+          const double L_rad = (8.0 * kRho / (3.0 * kPi * kPi)) * invr;
+          const double dR = E_A + G_A + R_rad, dL = E_A + (L_A + L_rad) * P.idt + R_A;
+          const double e = E_A, g = e + G_A, wL = 1.0 / dL;
+          const double dR2 = dR - g * g * wL, o = -e + e * g * wL, wR = 1.0 / dR2;
+          dk -= e * e * wL + o * o * wR;
+        }
+        // sinus leaves: host section h has currents h (in), h+1 (out) and the leaf
+        for (int q = 0; q < 4; q++) {
+          const int h = q == 0 ? 73 : q == 1 ? 74 : q == 2 ? 76 : 77, l = SINUS0 + q;
+          const double e = S.E[h], g = e + S.L[h] * P.idt + S.R1[h], wl = 1.0 / sdiag(l);
+          if (c == h) dk -= e * e * wl;
+          if (c == h + 1) dk -= g * g * wl;
+        }
+        if (c < NOSE_LAST) dk -= o_next * o_next / d_next;
+        // coupling of current c to current c-1 (through section c-1), with the leaf on section c-1 folded in
+        double oc = -S.E[c - 1];
+        for (int q = 0; q < 4; q++) {
+          const int h = q == 0 ? 73 : q == 1 ? 74 : q == 2 ? 76 : 77, l = SINUS0 + q;
+          if (c - 1 == h) { const double e = S.E[h], g = e + S.L[h] * P.idt + S.R1[h]; oc += e * g / sdiag(l); }
+        }
+        d_next = dk; o_next = oc;
+      }
+      return dk;
+    };
+    auto nose_coupling = [&](int c) {  // coupling of current c (70..83) to current c-1
+      double oc = -S.E[c - 1];
+      for (int q = 0; q < 4; q++) {
+        const int h = q == 0 ? 73 : q == 1 ? 74 : q == 2 ? 76 : 77, l = SINUS0 + q;
+        if (c - 1 == h) { const double e = S.E[h], g = e + S.L[h] * P.idt + S.R1[h]; oc += e * g / sdiag(l); }
+      }
+      return oc;
+    };
+    auto up_pivot = [&](int first, int k) {  // chain eliminated upwards from `first` (trachea): pivot of current k
+      double dk = sdiag(first);
+      for (int c = first + 1; c <= k; c++) { const double o = -S.E[c - 1]; dk = sdiag(c) - o * o / dk; }
+      return dk;
+    };
+    auto down_pivot = [&](int last, int k) {  // chain eliminated downwards from `last` (fossa): pivot of current k
+      double dk = sdiag(last);
+      for (int c = last - 1; c >= k; c--) { const double o = -S.E[c]; dk = sdiag(c) - o * o / dk; }
+      return dk;
+    };
+    if (warp == 3 && lane < 23) {                 // trachea: eliminated upwards 0 -> 22, links to 23 through section 22
+      sw = 1.0 / up_pivot(0, sec);
+      st = -S.E[sec] * sw;                        // coupling to current sec+1 is -E_sec
+    } else if (warp == 3 && lane >= 24 && lane < 28) {  // fossa 85..88: eliminated downwards 88 -> 85, links to 84 through section 84
+      sw = 1.0 / down_pivot(FOSSA_LAST, sec);
+      st = -S.E[sec - 1] * sw;                    // coupling to current sec-1 is -E_{sec-1}
+    } else if (warp == 2 && lane >= 5 && lane < 19) {   // nose 70..83: eliminated downwards 83 -> 70, links to 69 through section 69
+      sw = 1.0 / nose_pivot(sec);
+      st = nose_coupling(sec) * sw;
+    }
+    // Schur terms on the linking currents
+    if (warp == 0 && lane == 0) { const double e = S.E[TRACHEA_LAST]; sdd_link = e * e / up_pivot(0, TRACHEA_LAST); }
+    if (warp == 2 && lane == 4) { const double o = nose_coupling(70); sdd_link = o * o / nose_pivot(70); }
+    if (warp == 3 && lane == 23) { const double e = S.E[FOSSA0]; sdd_link = e * e / down_pivot(FOSSA_LAST, FOSSA0 + 1); }
+    if (warp == 2 && lane >= 19 && lane < 23) {   // sinus leaves
+      const int h = Q.prev;
+      leaf_e = S.E[h]; leaf_g = leaf_e + S.L[h] * P.idt + S.R1[h]; leaf_w = 1.0 / sdiag(sec);
+    }
+    if (warp == 2 && lane == 18) {                // nostril radiation pair on section 83
+      const double E_A = S.E[sec], L_A = S.L[sec], R_A = S.R1[sec], invr = S.I[sec], G_A = L_A * P.idt + R_A;
+      const double R_rad = (128.0 * kRho * kC / (9.0 * kPi * kPi)) * (invr * invr * (1.0 / kPi));
+      const double L_rad = (8.0 * kRho / (3.0 * kPi * kPi)) * invr;
+      nr_LA = L_A; nr_LAB = L_A + L_rad;
+      const double dR = E_A + G_A + R_rad, dL = E_A + nr_LAB * P.idt + R_A;
+      nr_e = E_A; nr_g = nr_e + G_A; nr_wL = 1.0 / dL;
+      nr_o = -nr_e + nr_e * nr_g * nr_wL;
+      nr_wR = 1.0 / (dR - nr_g * nr_g * nr_wL);
+    }
+  }
+  // right-hand-side recurrences: forward (elimination)  r'_k = r_k - st_prev * r'_prev,  backward (solution)
+  // u_k = sw_k r'_k - st_k u_link...: both first-order affine recurrences over the lanes of a chain
+  {
+    // forward: factor applied to the value coming from the previously eliminated current = -st of THAT current
+    const int fdir = (warp == 3 && lane < 23) ? +1 : -1;
+    const int flo = (warp == 3 && lane < 23) ? 0 : warp == 3 ? 24 : 5, fhi = (warp == 3 && lane < 23) ? 22 : warp == 3 ? 27 : 18;
+    const double st_src = shfl(st, lane - fdir);
+    scan_windows(lane, flo, fhi, fdir, -st_src, fw);
+    // backward: u_k = sw r'_k - st_k u_{toward link}: factor -st of THIS current, direction opposite
+    scan_windows(lane, flo, fhi, -fdir, -st, bw);
+  }
+  const bool chain_tr = warp == 3 && lane < 23, chain_fo = warp == 3 && lane >= 24 && lane < 28, chain_no = warp == 2 && lane >= 5 && lane < 19;
+  const int clo = chain_tr ? 0 : chain_fo ? 24 : 5, chi = chain_tr ? 22 : chain_fo ? 27 : 18, cdir = chain_tr ? +1 : -1;
+
+  // ---- per-lane state ----------------------------------------------------------------------
+  double p = 0.0, pr = 0.0, wc = 0.0, wcr = 0.0, wcr2 = 0.0;   // section
+  double u = 0.0, c = 0.0;                                     // its in-current: last solution, history term
+  double E_old = rec.E, al_old = rec.alpha;
+  double gbf = 0.0;
+  double ru[2] = {0.0, 0.0}, rc[2] = {0.0, 0.0};               // radiation pair of sections 64 / 83 (R, L)
+  double rk[7] = {0, 0, 0, 0, 0, 0, 0};                        // (section 64: factors kept for the back substitution)
+  // auxiliary warp, lane 0: glottis + output filters
+  GlottisState G{0.0, 0.0, 0.0, 0.0};
+  GlottisDims GD;
+  double prevFlow = 0.0;
+  uint32_t bad = 0;
+
+  auto stage = [&](int interval) {  // control frames `interval`, `interval + 1` (all threads)
+    for (int i = threadIdx.x; i < 2 * AFS_NUM_PM_SECTIONS; i += THREADS) {
+      const int f = i / AFS_NUM_PM_SECTIONS, j = i % AFS_NUM_PM_SECTIONS;
+      const afs_tube_frame *fr = my_frames + interval + f;
+      const double a = fr->area_cm2[j];
+      S.fA[f][j] = a < kMinArea ? kMinArea : a;
+      S.fLen[f][j] = fr->length_cm[j];
+    }
+    if (threadIdx.x < 2) {
+      const double v = my_frames[interval + threadIdx.x].velum_area_cm2;
+      S.velum[threadIdx.x] = v < kMinArea ? kMinArea : v;
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + 2 * AFS_NUM_GLOTTIS_CONTROL) {
+      const int i = threadIdx.x - 32, f = i / AFS_NUM_GLOTTIS_CONTROL, cc = i % AFS_NUM_GLOTTIS_CONTROL;
+      S.gctl[f][cc] = my_glottis[(size_t)(interval + f) * AFS_NUM_GLOTTIS_CONTROL + cc];
+    }
+  };
+
+  int interval = 0, i0 = 0, i1 = 0;
+  double inv_len = 1.0;
+  if (T > 0) {
+    i0 = A.bounds[0]; i1 = A.bounds[1];
+    inv_len = 1.0 / (double)(i1 - i0);
+    stage(0);
+    __syncthreads();
+    if (aux && lane == 0) {  // glottis geometry of step 0
+      double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
+      for (int cc = 0; cc < AFS_NUM_GLOTTIS_CONTROL; cc++) ctl[cc] = S.gctl[0][cc];
+      glottis_geometry(P, ctl, G, len, ar, GD);
+      S.glLen[0][0] = len[0]; S.glLen[0][1] = len[1]; S.glArea[0][0] = ar[0]; S.glArea[0][1] = ar[1];
+    }
+    __syncthreads();
+  }
+
+#ifdef AFS_TDS_TIMING
+  long long kt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, klast = clock64();
+#define K_TICK(i) do { const long long now__ = clock64(); kt[i] += now__ - klast; klast = now__; } while (0)
+#else
+#define K_TICK(i) do { } while (0)
+#endif
+  for (int n = 0; n <= T && T > 0; n++) {
+    const bool upd = n > 0, rows = n < T;
+    if (rows && n == i1) {
+      interval++;
+      i0 = A.bounds[interval]; i1 = A.bounds[interval + 1];
+      inv_len = 1.0 / (double)(i1 - i0);
+      __syncthreads();
+      stage(interval);
+      __syncthreads();
+    }
+    const double ratio = (double)(n - i0) * inv_len, ratio1 = 1.0 - ratio;
+    const int par = n & 1;
+    double area = 0.0;
+    // ============ phase 1: update with the solution of step n-1, elements and D of step n ============
+    if (on) {
+      double Ls = rec.L, R0s = rec.R0, R1s = rec.R1, invr = rec.invr, Es = rec.E, Dn;
+      if (upd) {
+        const double out = S.U[Q.out1] + S.U[Q.out2];
+        const double beta_old = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
+        const double D_old = fma(-E_old, beta_old, fma(P.dtth1, pr, p));
+        const double ur = fma(u, P.idt, -c);
+        c = fma(ur, P.th, u * P.idt);
+        const double p_new = fma(E_old, u - out, D_old);
+        const double pr_new = (p_new - p) * P.idt - pr * P.th;
+        const double wc_new = fma(pr_new, al_old, beta_old);
+        const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
+        const double wcr2_new = (wcr_new - wcr) * P.idt - wcr2 * P.th;
+        p = p_new; pr = pr_new; wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
+        if (sec >= TRACHEA_LAST && sec <= PHAR0) S.p4[sec - TRACHEA_LAST] = p_new;
+        if (sec == MOUTH_LAST || sec == NOSE_LAST) {  // radiation currents (TdsModel.cpp:2063-2072)
+#pragma unroll
+          for (int j = 0; j < 2; j++) { const double urr = fma(ru[j], P.idt, -rc[j]); rc[j] = fma(urr, P.th, ru[j] * P.idt); }
+        }
+      }
+      if (rows) {
+        if (Q.dyn) {
+          const int j = min(max(sec - PHAR0, 0), AFS_NUM_PM_SECTIONS - 1);
+          area = ratio1 * S.fA[0][j] + ratio * S.fA[1][j];
+          double length = ratio1 * S.fLen[0][j] + ratio * S.fLen[1][j];
+          if (Q.glottal) { area = S.glArea[par][sec - GLOT_LO]; length = S.glLen[par][sec - GLOT_LO]; }
+          if (Q.velum) {
+            const double vel = ratio1 * S.velum[0] + ratio * S.velum[1];
+            const int k = sec - NOSE0;
+            area = vel + ((double)(k * k) * (4.24 - vel)) / 16.0; length = (11.4 / 11.4) * 0.6;
+          }
+          area = fmax(area, kMinArea);
+          double circ;
+          section_elements(area, length, Q.glottal, Ls, R0s, invr, circ);
+          R1s = R0s;
+          const double Cc = (area * length) * (1.0 / (kRho * kC * kC));
+          const double alpha = fmax(circ * length, kMinArea) * ka;
+          Es = P.dtth * fast_rcp1(Cc + alpha);
+          E_old = Es; al_old = alpha;
+        } else area = S.AR[sec];
+        const double beta = fma(wc, kc0, fma(wcr, kc1, wcr2 * kc2));
+        Dn = fma(-Es, beta, fma(P.dtth1, pr, p));
+        if (Q.dyn) { S.E[sec] = Es; S.L[sec] = Ls; S.R0[sec] = R0s; S.R1[sec] = R1s; S.I[sec] = invr; S.AR[sec] = area; }
+        S.D[sec] = Dn; S.C[sec] = c;
+      }
+    }
+    K_TICK(0);
+    bar_all();   // records and p4 visible; the auxiliary warp starts the glottis model
+    K_TICK(1);
+    if (aux) {
+      // ---- auxiliary warp: output of step n-1, glottis model of step n, geometry of step n+1 ----
+      if (lane == 0) {
+        if (n > 0) {
+          double uo = S.urad[par ^ 1][0] + S.urad[par ^ 1][1];  // (step n-1: not touched again before this warp is done)
+          if (P.skin) uo += iir_step<4>(c_tone_a, c_tone_b, S.toneX, S.toneY, S.p4[3]);
+          if (!isfinite(uo)) bad |= 1u;
+          const double outP = (uo - prevFlow) * P.fs;
+          prevFlow = uo;
+          const double filt = iir_step<8>(P.cheb_a, P.cheb_b, S.chebX, S.chebY, outP);
+          if (A.flow) A.flow[(size_t)tract * T + (n - 1)] = uo;
+          if ((n % P.sr_factor) == 0) A.audio[(size_t)tract * n_out + (n / P.sr_factor - 1)] = filt * (0.004 / 32767);
+        }
+        if (rows) {
+          double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2], pp[4];
+          for (int cc = 0; cc < 4; cc++) pp[cc] = S.p4[cc];
+          for (int cc = 0; cc < AFS_NUM_GLOTTIS_CONTROL; cc++) ctl[cc] = ratio1 * S.gctl[0][cc] + ratio * S.gctl[1][cc];
+          glottis_dims(P, ctl, G, GD);
+          glottis_inc_time(P, ctl, G, pp, GD);
+          const double rn = (double)(n + 1 - i0) * inv_len, rn1 = 1.0 - rn;
+          for (int cc = 0; cc < AFS_NUM_GLOTTIS_CONTROL; cc++) ctl[cc] = rn1 * S.gctl[0][cc] + rn * S.gctl[1][cc];
+          glottis_geometry(P, ctl, G, len, ar, GD);
+          S.glLen[par ^ 1][0] = len[0]; S.glLen[par ^ 1][1] = len[1]; S.glArea[par ^ 1][0] = ar[0]; S.glArea[par ^ 1][1] = ar[1];
+        }
+      }
+      if (!rows) break;
+      K_TICK(2);
+      bar_all();  // end of the step
+      K_TICK(3);
+      continue;
+    }
+    if (!rows) break;
+    // ============ phase 2: matrix rows; right-hand sides of the rigid chains eliminated ============
+    double diag = 1.0, rhs = 0.0, lo = 0.0;   // row of this lane's current: pivot, right-hand side, coupling to the current before it
+    if (on) {
+      const int a = Q.prev < 0 ? NS : Q.prev;
+      const double E_A = S.E[a], L_A = S.L[a], R_A = S.R1[a], I_A = S.I[a], D_A = S.D[a];
+      const double c_sib = Q.sib == ZC ? 0.0 : S.C[Q.sib];
+      const double k_ent = P.k_ent;
+      row_dyn(P, row_flags(sec), E_A, L_A, R_A, I_A, D_A, S.E[sec], S.L[sec], S.R0[sec], S.I[sec], S.D[sec], c, c_sib, u,
+              sec == GLOT_UP ? S.AR[GLOT_LO] : 0.0, area, k_ent, gbf, diag, rhs);
+      if (sec == 0) rhs += ratio1 * S.gctl[0][G_PRESSURE] + ratio * S.gctl[1][G_PRESSURE];  // pressure source at the lungs
+      lo = -E_A;
+    }
+    // sinus leaves into their hosts (warp 2: leaf lanes 19..22, hosts 73, 74, 76, 77 and the current after each)
+    if (warp == 2) {
+      const double lr = rhs * leaf_w;   // (leaf lanes; 0 elsewhere)
+      const double a0 = shfl(leaf_e * lr, 19), b0 = shfl(leaf_g * lr, 19), a1 = shfl(leaf_e * lr, 20), b1 = shfl(leaf_g * lr, 20);
+      const double a2 = shfl(leaf_e * lr, 21), b2 = shfl(leaf_g * lr, 21), a3 = shfl(leaf_e * lr, 22), b3 = shfl(leaf_g * lr, 22);
+      // leaf l on host section h: r_h += e w r_l, r_{h+1} -= g w r_l
+      if (sec == 73) rhs += a0;
+      if (sec == 74) rhs += a1 - b0;
+      if (sec == 75) rhs -= b1;
+      if (sec == 76) rhs += a2;
+      if (sec == 77) rhs += a3 - b2;
+      if (sec == 78) rhs -= b3;
+      if (sec == NOSE_LAST) {  // nostril radiation pair into 83 (constant pivots)
+        const double D_A = S.D[sec];
+        const double rR = fma(nr_LA, rc[0] + rc[1], D_A), rL = fma(nr_LA, rc[0], nr_LAB * rc[1]) + D_A;
+        const double rR2 = rR - nr_g * nr_wL * rL;
+        rhs -= -nr_e * nr_wL * rL + nr_o * nr_wR * rR2;
+        rk[1] = rL; rk[3] = rR2;
+      }
+    }
+    // rigid chains: r'_k = r_k - st_prev r'_prev (prefix scan), then the Schur contribution to the linking current
+    double rel = 0.0;  // eliminated right-hand side of a rigid-chain current
+    if (warp >= 2) {
+      rel = scan_affine(lane, clo, chi, cdir, (chain_tr || chain_fo || chain_no) ? rhs : 0.0, fw);
+      if (warp == 2) {  // nose -> current 69 (lane 4), same warp
+        const double t70 = shfl(st * rel, 5);  // coupling(69,70) * r'_70 / pivot_70
+        if (lane == 4) { rhs -= t70; diag -= sdd_link; }
+      } else {
+        if (lane == 22) S.sch[0] = st * rel;           // trachea -> current 23: r_23 -= (-E_22 / pivot_22) r'_22
+        const double t85 = shfl(st * rel, 24);          // fossa -> current 84 (lane 23)
+        if (lane == 23) {
+          rhs -= t85; diag -= sdd_link;
+          // current 84 out of the clique {28, 29, 84} (couplings through section 28)
+          const double e = S.E[28], g = e + fma(S.L[28], P.idt, S.R1[28]);
+          const double wv = fast_rcp(diag);
+          S.sch[1] = e * e * wv; S.sch[2] = -e * wv * rhs; S.sch[3] = g * g * wv; S.sch[4] = g * wv * rhs; S.sch[5] = e * g * wv;
+          rk[0] = wv; rk[1] = e; rk[2] = g;
+        }
+      }
+    }
+    if (warp == 1 && sec == MOUTH_LAST) {  // mouth radiation pair into 64 (radiation_eliminate, geometry of this step)
+      const double E_A = S.E[sec], L_A = S.L[sec], R_A = S.R1[sec], invr = S.I[sec], D_A = S.D[sec], G_A = fma(L_A, P.idt, R_A);
+      const double R_rad = (128.0 * kRho * kC / (9.0 * kPi * kPi)) * (invr * invr * (1.0 / kPi));
+      const double L_rad = (8.0 * kRho / (3.0 * kPi * kPi)) * invr;
+      const double L_AB = L_A + L_rad;
+      const double dR = E_A + G_A + R_rad, rR = fma(L_A, rc[0] + rc[1], D_A);
+      const double dL = E_A + fma(L_AB, P.idt, R_A), rL = fma(L_A, rc[0], L_AB * rc[1]) + D_A;
+      const double e = E_A, g = e + G_A;
+      const double wL = fast_rcp(dL);
+      double dds = e * e * wL, drs = -e * wL * rL;
+      const double dR2 = dR - g * g * wL, rR2 = rR - g * wL * rL;
+      const double o = -e + e * g * wL;
+      const double wR = fast_rcp(dR2);
+      dds += o * o * wR; drs += o * wR * rR2;
+      diag -= dds; rhs -= drs;
+      rk[0] = wL; rk[1] = rL; rk[2] = wR; rk[3] = rR2; rk[4] = o; rk[5] = e; rk[6] = g;
+    }
+    K_TICK(2);
+    bar_sec();
+    K_TICK(3);
+    // ============ phase 3: the three moving chains by parallel cyclic reduction ============
+    double y = 0.0, z = 0.0;
+    if (warp <= 2) {
+      int nch = warp == 0 ? 18 : warp == 1 ? 24 : 5;
+      if (warp == 0) {
+        if (lane == 0) { rhs -= S.sch[0]; diag -= sdd_link; lo = 0.0; }          // trachea folded into current 23
+        if (lane == 5) { diag -= S.sch[1]; rhs -= S.sch[2]; }                     // fossa folded into 28 ...
+        if (lane == 6) { diag -= S.sch[3]; rhs -= S.sch[4]; lo += S.sch[5]; }     // ... and 29 (coupling 28 <-> 29)
+      }
+      const bool in = lane < nch;
+      // second right-hand side: unit load at the junction end (40: last of T; 41, 65: first of M, N)
+      const double r2 = (warp == 0 ? lane == nch - 1 : lane == 0) ? 1.0 : 0.0;
+      const double lo_c = (in && lane > 0) ? lo : 0.0;   // (the first currents of M and N couple to 40 through the junction)
+      pcr2(lane, nch, lo_c, in ? diag : 1.0, in ? rhs : 0.0, in ? r2 : 0.0, y, z);
+      if (warp == 0 && lane == nch - 1) { S.jn[0] = y; S.jn[1] = z; }
+      if (warp == 1 && lane == 0) { S.jn[2] = y; S.jn[3] = z; }
+      if (warp == 2 && lane == 0) { S.jn[4] = y; S.jn[5] = z; }
+    }
+    K_TICK(4);
+    bar_sec();
+    // ============ phase 4: the velum clique {40, 41, 65}; solution of the moving currents ============
+    if (warp <= 2) {
+      // a = u40, b = u41, cc = u65;  e = E_40, g = E_40 + G_40:
+      //   a = yT + zT e (b + cc),   b = yM + zM (e a - g cc),   cc = yN + zN (e a - g b)
+      const double e = S.E[40], g = e + fma(S.L[40], P.idt, S.R1[40]);
+      const double yT = S.jn[0], zT = S.jn[1], yM = S.jn[2], zM = S.jn[3], yN = S.jn[4], zN = S.jn[5];
+      // eliminate a:  b (1 - zM e zT e) + cc (zM g - zM e zT e) = yM + zM e yT   (and the same with N)
+      const double q = e * zT * e;
+      const double m11 = 1.0 - zM * q, m12 = zM * (g - q), m21 = zN * (g - q), m22 = 1.0 - zN * q;
+      const double f1 = fma(zM * e, yT, yM), f2 = fma(zN * e, yT, yN);
+      const double idet = fast_rcp(m11 * m22 - m12 * m21);
+      const double b = (f1 * m22 - m12 * f2) * idet, cc = (m11 * f2 - m21 * f1) * idet;
+      const double a = fma(zT * e, b + cc, yT);
+      const double wj = warp == 0 ? e * (b + cc) : warp == 1 ? fma(e, a, -g * cc) : fma(e, a, -g * b);
+      const int nch = warp == 0 ? 18 : warp == 1 ? 24 : 5;
+      if (lane < nch) { u = fma(z, wj, y); S.U[sec] = u; }
+    }
+    K_TICK(5);
+    bar_sec();
+    // ============ phase 5: back substitution of the rigid chains, leaves, radiation ============
+    if (warp == 1 && sec == MOUTH_LAST) {
+      const double us = u;
+      const double uR = (rk[3] - rk[4] * us) * rk[2];
+      const double uL = (rk[1] + rk[5] * us - rk[6] * uR) * rk[0];
+      ru[0] = uR; ru[1] = uL;
+      S.U[93] = uR; S.U[94] = uL; S.urad[par][0] = uR + uL;
+    }
+    if (warp >= 2) {
+      // value of the linking current, then u_k = sw r'_k - st u_{towards the link}
+      double ulink = 0.0;
+      if (warp == 3) {
+        if (lane == 23) {  // current 84 from 28 and 29
+          u = (rhs + rk[1] * S.U[28] - rk[2] * S.U[29]) * rk[0];
+          S.U[sec] = u;
+        }
+        const double u84 = shfl(u, 23);
+        ulink = chain_tr ? S.U[23] : u84;
+      } else ulink = shfl(u, 4);   // current 69
+      const bool first = chain_tr ? lane == 22 : chain_fo ? lane == 24 : chain_no ? lane == 5 : false;  // next to the link
+      double b = sw * rel;
+      if (first) b = fma(-st, ulink, b);
+      const double uk = scan_affine(lane, clo, chi, -cdir, (chain_tr || chain_fo || chain_no) ? b : 0.0, bw);
+      if (chain_tr || chain_fo || chain_no) { u = uk; S.U[sec] = u; }
+      if (warp == 2) {
+        // sinus leaves: u_l = w_l (r_l + e u_h - g u_{h+1})
+        const double u73 = shfl(u, 8), u74 = shfl(u, 9), u75 = shfl(u, 10), u76 = shfl(u, 11), u77 = shfl(u, 12), u78 = shfl(u, 13);
+        if (lane >= 19 && lane < 23) {
+          const double uh = lane == 19 ? u73 : lane == 20 ? u74 : lane == 21 ? u76 : u77;
+          const double un = lane == 19 ? u74 : lane == 20 ? u75 : lane == 21 ? u77 : u78;
+          u = (rhs + leaf_e * uh - leaf_g * un) * leaf_w;
+          S.U[sec] = u;
+        }
+        if (sec == NOSE_LAST) {
+          const double uR = (rk[3] - nr_o * u) * nr_wR;
+          const double uL = (rk[1] + nr_e * u - nr_g * uR) * nr_wL;
+          ru[0] = uR; ru[1] = uL;
+          S.U[95] = uR; S.U[96] = uL; S.urad[par][1] = uR + uL;
+        }
+      }
+    }
+    K_TICK(6);
+    bar_all();  // end of the step: solution visible to the update and to the auxiliary warp
+    K_TICK(7);
+  }
+#ifdef AFS_TDS_TIMING
+  if (blockIdx.x == 0 && lane == 0)
+    printf("k1s warp %d cycles/step: ph1 %lld | wait %lld | ph2 (aux: work) %lld | wait %lld | pcr %lld | junction %lld | back %lld | wait %lld\n", warp,
+           kt[0] / T, kt[1] / T, kt[2] / T, kt[3] / T, kt[4] / T, kt[5] / T, kt[6] / T, kt[7] / T);
+#endif
+  if (aux && lane == 0 && A.status) A.status[tract] = bad;
+}
+
+}  // namespace k1s
+
+bool tds_small_supported(const TdsLaunch &L) {
+  TdsParams P;
+  memcpy(&P, L.params.data(), sizeof P);
+  return !P.noise && !P.transvelar && !P.var_loss && P.fsrc_sec < 0 && P.total_steps > 0;
+}
+
+cudaError_t launch_tds_small(const TdsLaunch &L, const int32_t *d_bounds, const afs_tube_frame *d_tubes, const double *d_glottis,
+                             double *d_audio, double *d_flow, uint32_t *d_status, cudaStream_t stream) {
+  TdsParams P;
+  memcpy(&P, L.params.data(), sizeof P);
+  k1s::Args A{d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status};
+  k1s::tds_small_kernel<<<P.n_tracts, k1s::THREADS, sizeof(k1s::Smem), stream>>>(P, A);
+  return cudaGetLastError();
 }
 
 // ---- host side ------------------------------------------------------------------

@@ -28,6 +28,15 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
 
 
+@pytest.fixture(params=["auto", "batch_kernel"])
+def kernel(request, ctx):
+    """Small noise-free batches are served by tds_small_kernel (one tract per CTA), everything else by tds_batch_kernel
+    (tract per lane): the tests that take this fixture run on both."""
+    ctx.debug_set("tds.small_batch_max", -1 if request.param == "auto" else 0)
+    yield request.param
+    ctx.debug_set("tds.small_batch_max", -1)
+
+
 def test_state_after_single_steps_matches_reference(ctx):
     g = load_golden("tds_reference.npz")
     for step, tol in ((1, 1e-12), (2, 1e-12), (500, 1e-9)):
@@ -43,7 +52,7 @@ def test_state_after_single_steps_matches_reference(ctx):
             assert err <= tol, (step, name, err)
 
 
-def test_golden_static_vowel(ctx):
+def test_golden_static_vowel(ctx, kernel):
     g = load_golden("tds_reference.npz")
     a, u, status = synth(ctx, g["static_frames"], g["static_glottis"], [2205], 44100.0, 2, want_flow=True)
     assert status[0] == 0
@@ -53,7 +62,7 @@ def test_golden_static_vowel(ctx):
     assert rel_err(u, g["static_flow22"]) <= TOL and rel_err(a, g["static_audio22"]) <= TOL
 
 
-def test_golden_transition_and_options(ctx):
+def test_golden_transition_and_options(ctx, kernel):
     import areafunctionsynthesis_b200 as afs
     g = load_golden("tds_reference.npz")
     a, u, _ = synth(ctx, g["trans_frames"], g["trans_glottis"], g["trans_len"], 44100.0, 2, want_flow=True)
@@ -76,7 +85,7 @@ def _vowel_transitions(shapes, n, seed, nasal=False, dur=2205):
     return fr, gl, [dur]
 
 
-def test_batch_of_vowel_transitions_against_oracle(ctx, oracle, shapes):
+def test_batch_of_vowel_transitions_against_oracle(ctx, oracle, shapes, kernel):
     """SURVEY 8d config C3 at a size the oracle finishes in seconds: 40 oral vowel-to-vowel transitions
     (more tracts than one CTA holds), 0.1 s each at 44.1 kHz."""
     fr, gl, fl = _vowel_transitions(shapes, 40, 20260002)
@@ -88,7 +97,7 @@ def test_batch_of_vowel_transitions_against_oracle(ctx, oracle, shapes):
         assert rel_err(a[b], ao[b]) <= TOL, b
 
 
-def test_nasal_and_fossa_against_oracle(ctx, oracle, shapes):
+def test_nasal_and_fossa_against_oracle(ctx, oracle, shapes, kernel):
     """SURVEY 8d config C4 flavour: velum open U[0,1] cm^2 per endpoint, piriform fossa on."""
     import areafunctionsynthesis_b200 as afs
     from oracle.pyoracle import tds_options_default as oracle_opts
@@ -101,7 +110,7 @@ def test_nasal_and_fossa_against_oracle(ctx, oracle, shapes):
         assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, b
 
 
-def test_consonant_closures_and_random_area_functions(ctx, oracle, shapes):
+def test_consonant_closures_and_random_area_functions(ctx, oracle, shapes, kernel):
     """Closures (areas clamped to 0.001 cm^2) and random parametric tubes."""
     n = len(shapes["names"])
     rng = np.random.default_rng(7)
@@ -120,7 +129,7 @@ def test_consonant_closures_and_random_area_functions(ctx, oracle, shapes):
         assert rel_err(u[b], uo[b]) <= TOL and rel_err(a[b], ao[b]) <= TOL, b
 
 
-def test_edge_cases(ctx, oracle, shapes):
+def test_edge_cases(ctx, oracle, shapes, kernel):
     import areafunctionsynthesis_b200 as afs
     fr, gl, _ = _vowel_transitions(shapes, 3, 5)
     # empty batch
@@ -148,7 +157,7 @@ def test_edge_cases(ctx, oracle, shapes):
         assert rel_err(u, uo) <= TOL and rel_err(a, ao) <= TOL, name
 
 
-def test_full_length_utterances_permutation_property(ctx, oracle, shapes):
+def test_full_length_utterances_permutation_property(ctx, oracle, shapes, kernel):
     """1 s utterances (44100 steps): a handful against the oracle, plus the size-independent property that a
     tract's audio does not depend on which lane / CTA / batch it was computed in."""
     fr, gl, _ = _vowel_transitions(shapes, 96, 20260002)
@@ -455,8 +464,13 @@ def test_flow_source_and_probes_against_oracle(ctx, oracle, shapes, noise):
                 scale = np.max(np.abs(ref[:, q])) + 1e-300
                 err = np.max(np.abs(taps[name][:, q] - ref[:, q])) / scale
                 assert err <= TOL, (src_sec, name, sections[q], err)
-        # the plain entry point gives the same audio (the taps do not disturb the simulation)
-        a2, _, _ = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=o, seeds=seeds)
+        # the plain entry point gives the same audio (the taps do not disturb the simulation); same kernel: taps always
+        # run on tds_batch_kernel
+        ctx.debug_set("tds.small_batch_max", 0)
+        try:
+            a2, _, _ = ctx.tds_synthesize(fr, gl, fl, 44100.0, 2, opts=o, seeds=seeds)
+        finally:
+            ctx.debug_set("tds.small_batch_max", -1)
         assert np.array_equal(a, a2)
     # sinus and fossa sections, a source in a static section, only one of the three outputs requested
     o = afs.tds_options_default(noise=False); o.flow_source_section = 70; o.flow_source_cm3_s = 10.0
@@ -502,3 +516,19 @@ def test_host_call_overlapped_copies_equal_device_path(ctx, shapes):
             rc = ctx.lib.afs_tds_synthesize(ctx.h, afs.api.C.byref(o), B, 2, fl.ctypes.data, h_fr.data_ptr(), h_gl.data_ptr(),
                                             44100.0, 2, seeds.ctypes.data, h_a.data_ptr(), None, None)
             assert rc == 0 and torch.equal(h_a, d_a.cpu()), (B, noise)
+
+
+def test_small_and_batch_kernels_agree(ctx, shapes):
+    """The two mappings of the same simulation (tract per lane / tract per CTA with a shuffle-based solve) on the same
+    batch: far inside the parity bar of each against the reference."""
+    fr, gl, fl = _vowel_transitions(shapes, 300, 123, nasal=True, dur=1500)
+    res = {}
+    for mode, mx in (("small", 1 << 30), ("batch", 0)):
+        ctx.debug_set("tds.small_batch_max", mx)
+        try:
+            res[mode] = synth(ctx, fr, gl, fl, 44100.0, 2, want_flow=True)
+        finally:
+            ctx.debug_set("tds.small_batch_max", -1)
+    assert not res["small"][2].any() and not res["batch"][2].any()
+    for b in range(len(fr)):
+        assert rel_err(res["small"][0][b], res["batch"][0][b]) <= 1e-8 and rel_err(res["small"][1][b], res["batch"][1][b]) <= 1e-8, b
