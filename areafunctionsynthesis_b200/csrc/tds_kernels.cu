@@ -1692,20 +1692,40 @@ __device__ __forceinline__ double iir_step(const double *a, const double *b, dou
 struct X1Regs {
   GlottisState G;
   GlottisDims GD;
-  double toneX[4], toneY[4];  // skin-radiation filter history
-  double chebX[8], chebY[8];  // output low-pass history
+  // The two output filters (IirFilter::getOutputSample, IirFilter.cpp:47-65) in TRANSPOSED direct form II:
+  //   y = a0 x + s1;   s_i <- a_i x + b_i y + s_{i+1};   s_N <- a_N x + b_N y
+  // -- the same recursion as the reference's direct form (identical in exact arithmetic, zero initial state alike),
+  // with N states instead of 2 N histories, no shifting, and an output that needs ONE multiply-add once the input is
+  // there: the state updates wait for the next pass A, where this warp has time (its path behind the barrier is the
+  // longest of the step).
+  double toneS[4];            // skin-radiation filter (TdsModel.cpp:494-510)
+  double chebS[8];            // output low-pass (Synthesizer.cpp:52)
+  double pend[4];             // input / output of the last sample of the two filters, not yet in the states
   double prevFlow;
 };
+template <int ORDER>
+__device__ __forceinline__ void df2t_update(const double *a, const double *b, double (&s)[ORDER], double x, double y) {
+#pragma unroll
+  for (int i = 1; i < ORDER; i++) s[i - 1] = fma(a[i], x, fma(b[i], y, s[i]));
+  s[ORDER - 1] = fma(a[ORDER], x, b[ORDER] * y);
+}
+// pass A of warp X1: the filter states take in the sample emitted behind the last barrier
+__device__ __forceinline__ void emit_update(const TdsParams &P, X1Regs &xr) {
+  if (P.skin) df2t_update<4>(c_tone_a, c_tone_b, xr.toneS, xr.pend[0], xr.pend[1]);
+  df2t_update<8>(P.cheb_a, P.cheb_b, xr.chebS, xr.pend[2], xr.pend[3]);
+}
 // Output of the step whose radiated flows sit in uext[]: radiated flow (TdsModel.cpp:687-705), pressure
 // differentiator + Chebyshev low-pass + decimation (Synthesizer.cpp:614-627).  `n_done` = steps finished.
 __device__ __forceinline__ void emit_output(const TdsParams &P, X1Regs &xr, double u_rad, double p25, int n_done, bool active,
                                             int tract, int n_out, double *audio, double *flow, uint32_t &bad) {
   double u = u_rad;
-  if (P.skin) u += iir_step<4>(c_tone_a, c_tone_b, xr.toneX, xr.toneY, p25);
+  const double tone = fma(c_tone_a[0], p25, xr.toneS[0]);
+  if (P.skin) u += tone;
   if (!isfinite(u)) bad |= 1u;
   const double outP = (u - xr.prevFlow) * P.fs;
   xr.prevFlow = u;
-  const double filt = iir_step<8>(P.cheb_a, P.cheb_b, xr.chebX, xr.chebY, outP);
+  const double filt = fma(P.cheb_a[0], outP, xr.chebS[0]);
+  xr.pend[0] = p25; xr.pend[1] = tone; xr.pend[2] = outP; xr.pend[3] = filt;
   if (active) {
     if (flow) flow[(size_t)tract * P.total_steps + (n_done - 1)] = u;
     if ((n_done % P.sr_factor) == 0) audio[(size_t)tract * n_out + (n_done / P.sr_factor - 1)] = filt * (0.004 / 32767);
@@ -1849,9 +1869,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if (ROLE == 2) {
     xr.G = GlottisState{0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int i = 0; i < 4; i++) { xr.toneX[i] = 0.0; xr.toneY[i] = 0.0; }
+    for (int i = 0; i < 4; i++) { xr.toneS[i] = 0.0; xr.pend[i] = 0.0; }
 #pragma unroll
-    for (int i = 0; i < 8; i++) { xr.chebX[i] = 0.0; xr.chebY[i] = 0.0; }
+    for (int i = 0; i < 8; i++) xr.chebS[i] = 0.0;
     xr.prevFlow = 0.0;
   }
   cta_sync();  // static boundary records / pivots visible
@@ -1932,6 +1952,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
       }
     }
+    if (ROLE == 2 && n > 1) emit_update(P, xr);  // (the sample emitted in iteration n-1)
     if (ROLE == 2 && NOISE && X.rows) noise_tongue(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1);
     if (ROLE == 3 && NOISE && X.rows) {  // the constrictions' share of the noise sources of step n
       // (the control-frame ratio only enters smooth quantities here; the decisions that need the reference's own
@@ -2014,7 +2035,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
       const double (&p)[4] = x1p;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = X.ratio1 * S.gctl[0][c][lane] + X.ratio * S.gctl[1][c][lane];
-      glottis_dims(P, ctl, xr.G, xr.GD);  // (recomputed rather than carried over from the last step: X1 is short of registers)
+      // (xr.GD: the dimensions for the current displacement and control values are what the geometry call of the last
+      //  step computed -- same inputs, also across a change of control frames, where the old interval ends at ratio 1
+      //  on the frame the new one starts from)
       glottis_inc_time(P, ctl, xr.G, p, xr.GD);
       const double rn = (double)(n + 1 - i0) * inv_len, rn1 = 1.0 - rn;
       for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = rn1 * S.gctl[0][c][lane] + rn * S.gctl[1][c][lane];
