@@ -462,7 +462,9 @@ class Context:
     def tds_synthesize(self, frames, glottis, frame_len, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None,
                        want_flow=False):
         """frames [B, F] FRAME_DTYPE, glottis [B, F, 6], frame_len [F-1] output samples per interval.
-        Host buffers (H2D + kernel + D2H).  Returns (audio [B, n_out], flow or None, status [B])."""
+        Host buffers (H2D + kernel + D2H).  Returns (audio [B, n_out], flow or None, status [B]).
+        Defaults: a simulation at 44.1 kHz (sr_factor 2), the BASELINE configuration; the reference as shipped runs at
+        fs_tds_hz = 22050, sr_factor = 1 (Constants.h:25)."""
         opts = opts or tds_options_default()
         frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
         B, F = frames.shape
