@@ -295,6 +295,53 @@ def config1_default_a(ctx):
     return out
 
 
+def run_single_process(args):
+    """`--single-process`: N GPUs of the box from ONE process through the C ABI (afs_group_*, csrc/afs_multi.cpp) -- what
+    a C++ caller of the drop-in boundary gets: contiguous shards, one host thread + stream per device, every device
+    copying its rows straight into the caller's (pinned) arrays.  Host buffers in, host buffers out: this is an e2e
+    number by construction; timed with the wall clock around the call."""
+    import areafunctionsynthesis_b200 as afs
+    n_dev = args.gpus
+    grp = afs.Group(list(range(n_dev)))
+    B = n_dev * B_TDS
+    n_out = int(round(T_SEC * FS / SR_FACTOR))
+    fr, gl = make_tds_batch(B, 20260003)
+    seeds = bench_seeds(B)
+    audio = afs.pinned_empty((B, n_out))
+    out = {}
+    for name, noise in (("noise_sources_on", True), ("noise_sources_off", False)):
+        o = afs.tds_options_default(noise=noise)
+        for _ in range(max(1, args.warmup)):
+            grp.tds_synthesize(fr, gl, [n_out], FS, SR_FACTOR, opts=o, seeds=seeds, audio=audio)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _, _, st = grp.tds_synthesize(fr, gl, [n_out], FS, SR_FACTOR, opts=o, seeds=seeds, audio=audio)
+        dt = (time.perf_counter() - t0) / args.steps
+        assert not st.any()
+        out[name] = {"value": B * T_SEC / dt, "unit": "audio-s/s", "ms_per_step": dt * 1e3}
+    f_tl = make_tl_batch(n_dev * B_TL, 20260001)
+    grp.tl_sweep(f_tl, F0_TL, K_TL)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        grp.tl_sweep(f_tl, F0_TL, K_TL)
+    tl_dt = (time.perf_counter() - t0) / 3
+    line = {"metric": "tds_audio_seconds_per_second", "value": out["noise_sources_on"]["value"], "unit": "audio-s/s", "n_gpus": n_dev,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": out["noise_sources_on"]["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "tds_nasal_subglottal_b4096", "batch_per_gpu": B_TDS, "utterance_s": T_SEC, "fs_tds_hz": FS,
+                       "noise_sources": True, "parallelism": f"ONE process, afs_group over {n_dev} GPU(s): contiguous shards, one host "
+                                                             "thread per device, no collective; host buffers (pageable inputs, pinned output)"},
+            "e2e": {"value": out["noise_sources_on"]["value"], "unit": "audio-s/s",
+                    "h2d_bytes_per_step": int(fr.nbytes + gl.nbytes + seeds.nbytes), "d2h_bytes_per_step": int(audio.nbytes)},
+            "noise_sources_off": out["noise_sources_off"],
+            "tl": {"metric": "tl_spectra_per_second_2048_bins", "value": n_dev * B_TL / tl_dt, "unit": "spectra/s",
+                   "note": "afs_group_tl_sweep, pageable host buffers"},
+            "single_process": True}
+    emit_json_line(line)
+    afs.pinned_free(audio)
+    grp.close()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -765,6 +812,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N GPUs from one process through afs_group_* (the C-ABI multi-device layer) instead of one rank per GPU")
     ap.add_argument("--utt-seconds", type=float, default=1.0, help="utterance length; != 1.0 is for profiling only")
     args = ap.parse_args()
     global T_SEC
@@ -772,6 +821,8 @@ def main():
     quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_ours(args)
 
