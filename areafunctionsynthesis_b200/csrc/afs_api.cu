@@ -479,26 +479,31 @@ int afs_play_target_sequences(afs_ctx *ctx, const afs_tds_options *opts, int n, 
     const size_t need = nf * (sizeof(afs_tube_frame) + 22 * sizeof(double)) + (size_t)n * ns * sizeof(double);
     if (need > free_b + ctx->scratch_bytes[0] + ctx->scratch_bytes[1] + ctx->scratch_bytes[2]) return AFS_ERR_OUT_OF_MEMORY;
   }
-  // host: trajectories of every sequence
-  std::vector<double> params(nf * 16), gl(nf * AFS_NUM_GLOTTIS_CONTROL), cosv((size_t)ns);
+  // host: the time base (shared by all sequences: per-sample segment, cosine and glottis parameters, ~70 B per
+  // sample); device: the parameter trajectories of every sequence (n x ns x 16 doubles never cross PCIe)
+  std::vector<double> gl((size_t)ns * AFS_NUM_GLOTTIS_CONTROL), cosv((size_t)ns);
   std::vector<int> seg((size_t)ns);
   target_sequence_timebase(stationary_s, transition_s, glottis_control, sampling_rate_hz, ns, seg.data(), cosv.data(), gl.data());
-  for (int b = 0; b < n; b++) {
-    target_sequence_params(shapes + (size_t)b * 64, seg.data(), cosv.data(), ns, params.data() + (size_t)b * ns * 16);
-    if (b > 0) memcpy(gl.data() + (size_t)b * ns * AFS_NUM_GLOTTIS_CONTROL, gl.data(), (size_t)ns * AFS_NUM_GLOTTIS_CONTROL * sizeof(double));
-  }
-  void *d_frames, *d_params, *d_gl, *d_audio, *d_status, *d_seeds = nullptr;
+  void *d_frames, *d_params, *d_gl, *d_audio, *d_status, *d_seeds = nullptr, *d_tb;
   if ((rc = scratch(ctx, 0, nf * sizeof(afs_tube_frame), &d_frames))) return rc;
   if ((rc = scratch(ctx, 1, nf * 16 * sizeof(double), &d_params))) return rc;
   if ((rc = scratch(ctx, 2, nf * AFS_NUM_GLOTTIS_CONTROL * sizeof(double), &d_gl))) return rc;
   if ((rc = scratch(ctx, 3, (size_t)n * (ns - 1) * sizeof(double), &d_audio))) return rc;
   if ((rc = scratch(ctx, 4, (size_t)n * sizeof(uint32_t), &d_status))) return rc;
+  if ((rc = scratch(ctx, 9, (size_t)n * 64 * sizeof(double) + (size_t)ns * (sizeof(double) + sizeof(int32_t)), &d_tb))) return rc;
+  double *d_shapes = (double *)d_tb, *d_cosv = d_shapes + (size_t)n * 64;
+  int32_t *d_seg = (int32_t *)(d_cosv + ns);
   if (seeds) {
     if ((rc = scratch(ctx, 5, (size_t)n * sizeof(uint32_t), &d_seeds))) return rc;
     CU(cudaMemcpyAsync(d_seeds, seeds, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
-  CU(cudaMemcpyAsync(d_params, params.data(), nf * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(d_gl, gl.data(), nf * AFS_NUM_GLOTTIS_CONTROL * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_shapes, shapes, (size_t)n * 64 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_cosv, cosv.data(), (size_t)ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_seg, seg.data(), (size_t)ns * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_gl, gl.data(), (size_t)ns * AFS_NUM_GLOTTIS_CONTROL * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_target_params(n, ns, d_shapes, d_seg, d_cosv, (double *)d_params, ctx->stream));
+  CU(launch_broadcast_row((size_t)n, (size_t)ns * AFS_NUM_GLOTTIS_CONTROL, (double *)d_gl, ctx->stream));
+  ctx->launches += 2;
   afs_tube_frame tpl;  // a fresh Tube (nasal port closed; the glottis sections come from the glottis model)
   afs_tube_frame_default(&tpl);
   CU(launch_fill_frames(nf, (afs_tube_frame *)d_frames, tpl, ctx->stream));

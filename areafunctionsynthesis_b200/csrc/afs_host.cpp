@@ -312,6 +312,11 @@ void target_sequence_timebase(const double *stationary_s, const double *transiti
       const double t0 = b[seg - 1] * SR, t1 = b[seg] * SR, tX = i;
       c = cos((t1 - tX) / (t1 - t0) * M_PI);
     }
+    // (seg -1 = keep the last values: past the end of the last stationary part, which rounding can put one sample
+    //  before the end.  Passed on as the previous sample's (segment, cosine): the same values, and the interpolation
+    //  needs no state)
+    if (seg < 0 && i > 0) { seg = seg_out[i - 1]; c = cosv[i - 1]; }
+    if (seg < 0) seg = 0;
     seg_out[i] = seg; cosv[i] = c;
     if (i > (total - 0.1) * SR) gp[1] = -steady / 2 * cos((total * SR - i) / (total - 0.1 * SR) * M_PI) + steady / 2;
     for (int k = 0; k < AFS_NUM_GLOTTIS_CONTROL; k++) glottis[(size_t)i * AFS_NUM_GLOTTIS_CONTROL + k] = gp[k];

@@ -83,6 +83,9 @@ size_t tds_smem_bytes();
 // ---- area-function rasteriser -----------------------------------------------
 cudaError_t launch_area_function_raster(int n_sets, const double *d_params, afs_tube_frame *d_frames, cudaStream_t stream);
 cudaError_t launch_fill_frames(size_t n, afs_tube_frame *d_frames, const afs_tube_frame &tpl, cudaStream_t stream);
+cudaError_t launch_target_params(int n_seq, int ns, const double *d_shapes, const int32_t *d_seg, const double *d_cosv,
+                                 double *d_params, cudaStream_t stream);
+cudaError_t launch_broadcast_row(size_t n, size_t row_doubles, double *d_a, cudaStream_t stream);
 int target_sequence_length(const double *stationary_s, const double *transition_s, double sampling_rate_hz);
 void target_sequence_timebase(const double *stationary_s, const double *transition_s, const double *glottis6, double SR,
                               int numSamples, int *seg_out, double *cosv, double *glottis);

@@ -98,6 +98,46 @@ cudaError_t launch_fill_frames(size_t n, afs_tube_frame *d_frames, const afs_tub
   return cudaGetLastError();
 }
 
+// Synthesizer::interpolateParameters (Synthesizer.cpp:1286-1294) along the time base of playTargetSequence
+// (:1299-1422), for a batch of sequences that share the timing: params[b][i][j] from the four target shapes of
+// sequence b and the per-sample (segment, cosine) of the time base (afs_host.cpp: target_sequence_timebase).
+// Same expression as the reference, no FMA contraction in this translation unit => the same bits.
+__global__ void target_params_kernel(const int n_seq, const int ns, const double *__restrict__ shapes, const int32_t *__restrict__ seg,
+                                     const double *__restrict__ cosv, double *__restrict__ params) {
+  const size_t total = (size_t)n_seq * (size_t)ns * 16;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx & 15);
+    const size_t bi = idx >> 4;
+    const int i = (int)(bi % (size_t)ns), b = (int)(bi / (size_t)ns);
+    const double *sh = shapes + (size_t)b * 64;
+    const int s = seg[i];
+    double v;
+    if ((s & 1) == 0) v = sh[(s / 2) * 16 + j];
+    else {
+      const double p0 = sh[((s - 1) / 2) * 16 + j], p1 = sh[((s + 1) / 2) * 16 + j];
+      v = (p1 - p0) / 2 * cosv[i] + (p1 + p0) / 2;
+    }
+    params[idx] = v;
+  }
+}
+cudaError_t launch_target_params(int n_seq, int ns, const double *d_shapes, const int32_t *d_seg, const double *d_cosv,
+                                 double *d_params, cudaStream_t stream) {
+  if (n_seq <= 0 || ns <= 0) return cudaSuccess;
+  target_params_kernel<<<148 * 8, 256, 0, stream>>>(n_seq, ns, d_shapes, d_seg, d_cosv, d_params);
+  return cudaGetLastError();
+}
+// rows 1 .. n-1 of a [n][row_doubles] array = row 0 (the glottis trajectory is the same for every sequence)
+__global__ void broadcast_row_kernel(const size_t n, const size_t row_doubles, double *__restrict__ a) {
+  const size_t total = (n - 1) * row_doubles;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    a[row_doubles + idx] = a[idx % row_doubles];
+}
+cudaError_t launch_broadcast_row(size_t n, size_t row_doubles, double *d_a, cudaStream_t stream) {
+  if (n <= 1 || row_doubles == 0) return cudaSuccess;
+  broadcast_row_kernel<<<148 * 8, 256, 0, stream>>>(n, row_doubles, d_a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_area_function_raster(int n_sets, const double *d_params, afs_tube_frame *d_frames, cudaStream_t stream) {
   if (n_sets <= 0) return cudaSuccess;
   const int ctas = (n_sets + 31) / 32;
