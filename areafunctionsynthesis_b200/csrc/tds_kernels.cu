@@ -153,7 +153,7 @@ struct TdsSmem {
   // of the upper glottis area and the downstream factor (see noise_stage)
   double nzk0[2][LANES];
   unsigned long long nzdecay[LANES];             // decaying sources (nothing feeds them this step) that are still audible
-  unsigned long long nztongue[LANES];            // sources fed by the tongue / lip constrictions that are audible
+  unsigned long long nztongue[3][LANES];         // sources fed by the tongue / lip constrictions (slots 1..3) that are audible
   double nzlip[LANES];                           // noiseMagnitude of the flow through the lips (currents 93 + 94)
   // glibc random() TYPE_3 (r[i] = r[i-3] + r[i-31]) in a ring of 36 = 3 x 12 words: the twelve draws of one noise
   // sample never wrap inside the ring and three samples bring it back to the same phase (static addresses)
@@ -1286,6 +1286,7 @@ __device__ __forceinline__ unsigned long long nz_fed(const TdsSmem &S, const int
 // One constriction slot of calcNoiseSources, state-dependent part (TdsModel.cpp:1430-1612): flow through the
 // constriction -> target amplitude -> amplitude filter (calcNoiseSample, :1637-1660) of the two sources it feeds.
 // amp / cut / downF: the flow-independent factors (nz_factors, nz_down).  Returns the fed sources that are audible.
+constexpr int NZ_BAR4 = 160;  // named barrier 4: F, X1, N1 and T2 arrive, X2 waits
 struct NzConst { double F, x2000, dt; };  // P.nz_F, P.nz_x2000, P.dt by value (the callees are not inlined)
 __device__ __forceinline__ unsigned long long nz_slot(const NzConst &P, TdsSmem &S, const int lane, const int k, const uint32_t v,
                                                       const double amp, const double cut, const double downF) {
@@ -1331,10 +1332,11 @@ __device__ __forceinline__ unsigned long long nz_slot(const NzConst &P, TdsSmem 
 // almost every instruction it executes once per step: what counts is the number of instructions on its path):
 //   warp F  (noise_decay, before its own pass A: it has the most slack of the static chain warps): the sources nothing
 //           feeds this step decay (calcNoiseSample, TdsModel.cpp:1637-1660); the still audible ones -> nzdecay;
-//   warp X1 (noise_tongue; idle in pass A otherwise): the tongue and lip constrictions (slots 1..3), complete: factors,
+//   warps X1, N1, T2 (noise_tongue; slots 1, 2, 3: X1 is idle in pass A otherwise, N1 and T2 are the static chain warps
+//           with the most slack after F): the two tongue constrictions and the lip constriction, complete: factors,
 //           flow, target amplitudes, amplitude filters; their audible sources -> nztongue;
 //   warp X2 (noise_stage): the vocal-fold constriction (slot 0; its flow-independent factors were computed one step
-//           ahead by X1 next to the glottis geometry: nzk0), then -- behind named barrier 4, where F and X1 only arrive
+//           ahead by X1 next to the glottis geometry: nzk0), then -- behind named barrier 4, where the others only arrive
 //           -- one sample for every source that is not silent, in ascending source order: the reference draws from ONE
 //           rand() stream in that order (TdsModel.cpp:1615-1620), here the k-th drawing source takes the k-th entry of
 //           the ring of pre-generated sums.
@@ -1365,24 +1367,22 @@ __device__ __noinline__ void noise_decay(const double F, TdsSmem &S, const int l
   }
   live = alive;
   S.nzdecay[lane] = draw;
-  bar_arrive(4, 96);
+  bar_arrive(4, NZ_BAR4);
 }
 
-__device__ __noinline__ void noise_tongue(const NzConst P, TdsSmem &S, const int lane, const double r, const double r1) {
+__device__ __noinline__ void noise_tongue(const NzConst P, TdsSmem &S, const int lane, const double r, const double r1, const int k) {
   constexpr int NPM = AFS_NUM_PM_SECTIONS;
   unsigned long long draw = 0;
-#pragma unroll 1
-  for (int k = 1; k < 4; k++) {
-    const uint32_t v = S.nzc_i[k][lane];
-    if (!__any_sync(0xffffffffu, v & 1u)) continue;  // (the second tongue constriction and the lips are rare)
+  const uint32_t v = S.nzc_i[k][lane];
+  if (__any_sync(0xffffffffu, v & 1u)) {  // (the second tongue constriction and the lips are rare)
     const bool teeth = (v >> 3) & 1u, lateral = (v >> 4) & 1u;
     const int nar = min(max((int)((v >> 8) & 255u) - 1, 0), NPM - 1);
     double amp, cut;
     nz_factors(nz_area(S, lane, r, r1, nar), lateral ? 0.0 : k == 3 ? 2.0e-7 : teeth ? 10.0e-7 : 5.0e-7, amp, cut);
-    draw |= nz_slot(P, S, lane, k, v, amp, cut, nz_down(S, lane, k, r));
+    draw = nz_slot(P, S, lane, k, v, amp, cut, nz_down(S, lane, k, r));
   }
-  S.nztongue[lane] = draw;
-  bar_arrive(4, 96);
+  S.nztongue[k - 1][lane] = draw;
+  bar_arrive(4, NZ_BAR4);
 }
 
 // (returns the number of ring entries consumed)
@@ -1401,10 +1401,10 @@ __device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int l
     if (__any_sync(0xffffffffu, v & 1u)) draw = nz_slot(P, S, lane, 0, v, gain0 * S.nzk0[0][lane], 0.0, S.nzk0[1][lane]);
   }
   SW_TICK(0);
-  bar_sync(4, 96);
+  bar_sync(4, NZ_BAR4);
   SW_TICK(1);
   // samples, ascending: the k-th drawing source takes the k-th sum (two independent low-pass updates per pass)
-  draw |= S.nzdecay[lane] | S.nztongue[lane];
+  draw |= S.nzdecay[lane] | S.nztongue[0][lane] | S.nztongue[1][lane] | S.nztongue[2][lane];
   const uint32_t ring = S.nzring[lane];
   const int cap = (int)(ring >> 16);
   int i = (int)(ring & 255u), n_draw = 0;
@@ -1938,7 +1938,11 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     }
     AFS_TICK(0);
     // ============ pass A: update (step n-1), elements + rows (step n) ============
-    if (ROLE == 1 && NOISE && X.rows && warp == W_F) noise_decay(P.nz_F, S, lane, nz_live);  // (see noise_decay)
+    if (ROLE == 1 && NOISE && X.rows) {  // (see noise_decay)
+      if (warp == W_F) noise_decay(P.nz_F, S, lane, nz_live);
+      else if (warp == W_N1 || warp == W_T2)  // the two static chain warps with the most slack after F
+        noise_tongue(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1, warp == W_N1 ? 2 : 3);
+    }
     // (state dump requested for this step: update and rows in two separate passes, the dump in between)
     if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true, OPT>(P, S, lane, warp, wcfg, dst, X);
     else for (int half = 0; half < (X.dumping ? 2 : 1); half++) {
@@ -1953,7 +1957,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       }
     }
     if (ROLE == 2 && n > 1) emit_update(P, xr);  // (the sample emitted in iteration n-1)
-    if (ROLE == 2 && NOISE && X.rows) noise_tongue(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1);
+    if (ROLE == 2 && NOISE && X.rows) noise_tongue(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1, 1);
     if (ROLE == 3 && NOISE && X.rows) {  // the constrictions' share of the noise sources of step n
       // (the control-frame ratio only enters smooth quantities here; the decisions that need the reference's own
       //  rounding of it were made by the pre-pass)
@@ -2107,7 +2111,11 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   if ((ROLE == 1 || ROLE == 3) && A.dump && blockIdx.x == 0 && lane == 0) for (int k = 0; k < 4; k++) A.dump[136 + warp * 4 + k] = (double)sw_acc[k];
   // (pass-A cycles of the two auxiliary warps of the first 136 CTAs: how evenly the noise sources load the CTAs)
   if (ROLE == 2 && A.dump && blockIdx.x < 136 && lane == 0) A.dump[200 + blockIdx.x] = (double)tacc[1];
-  if (ROLE == 3 && A.dump && blockIdx.x < 136 && lane == 0) A.dump[336 + blockIdx.x] = (double)tacc[1];
+  if (ROLE == 3 && A.dump && blockIdx.x < 136 && lane == 0) {  // (whole time loop of the CTA)
+    long long all = 0;
+    for (int k = 0; k < 8; k++) all += tacc[k];
+    A.dump[336 + blockIdx.x] = (double)all;
+  }
 #endif
   if (ROLE == 2 && NOISE && A.run_ctl && A.run_ctl[1]) bad |= 2u;  // the noise pre-pass ran out of record space
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;
@@ -2172,7 +2180,7 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
     S.sepD[w][lane] = 1.0; S.sepR[w][lane] = 0.0; S.redW[w][lane] = 1.0;  // NSEP == NW
   }
   if (warp == 0) {
-    S.nzk0[0][lane] = 0.0; S.nzk0[1][lane] = 0.0; S.nzdecay[lane] = 0; S.nztongue[lane] = 0;
+    S.nzk0[0][lane] = 0.0; S.nzk0[1][lane] = 0.0; S.nzdecay[lane] = 0; S.nztongue[0][lane] = 0; S.nztongue[1][lane] = 0; S.nztongue[2][lane] = 0;
     S.nzlip[lane] = 0.0;
     for (int i = 0; i < NUX; i++) S.uext[i][lane] = 0.0;
     for (int i = 0; i < 5; i++) S.lf[i][lane] = 0.0;
