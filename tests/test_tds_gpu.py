@@ -532,3 +532,30 @@ def test_small_and_batch_kernels_agree(ctx, shapes):
     assert not res["small"][2].any() and not res["batch"][2].any()
     for b in range(len(fr)):
         assert rel_err(res["small"][0][b], res["batch"][0][b]) <= 1e-8 and rel_err(res["small"][1][b], res["batch"][1][b]) <= 1e-8, b
+
+
+@pytest.mark.parametrize("noise", [False, True])
+def test_result_does_not_depend_on_cta_packing_or_run(ctx, shapes, noise):
+    """Sixteen warps of a CTA exchange everything through shared memory and named barriers; a missing barrier would show
+    up as run-to-run differences or as a dependence on how many tracts share a CTA.  The same batch packed 28 tracts
+    per CTA ("tds.spread_sms" = 4 CTAs), spread over all SMs (one tract per CTA), and run twice: identical bits."""
+    import areafunctionsynthesis_b200 as afs
+    n = len(shapes["names"])
+    rng = np.random.default_rng(5)
+    B = 100
+    fr = shapes["frames"][rng.integers(0, n, size=(B, 3))].copy()
+    gl = np.tile(G0, (B, 3, 1)); gl[:, :, 0] = rng.uniform(90, 220, size=(B, 3)); gl[:, :, 5] = -15.0
+    seeds = rng.integers(1, 2**31 - 1, size=B).astype(np.uint32)
+    o = afs.tds_options_default(noise=noise)
+    ctx.debug_set("tds.small_batch_max", 0)
+    try:
+        ref, _, st = ctx.tds_synthesize(fr, gl, [500, 400], 44100.0, 2, opts=o, seeds=seeds)
+        assert not st.any() and np.isfinite(ref).all() and np.abs(ref).max() > 0
+        again, _, _ = ctx.tds_synthesize(fr, gl, [500, 400], 44100.0, 2, opts=o, seeds=seeds)
+        assert np.array_equal(again, ref)
+        ctx.debug_set("tds.spread_sms", 4)
+        packed, _, _ = ctx.tds_synthesize(fr, gl, [500, 400], 44100.0, 2, opts=o, seeds=seeds)
+        assert np.array_equal(packed, ref)
+    finally:
+        ctx.debug_set("tds.spread_sms", 0)
+        ctx.debug_set("tds.small_batch_max", -1)
