@@ -1026,23 +1026,30 @@ __device__ __noinline__ void rng_seed(TdsSmem &S, const int lane, uint32_t seed,
   ph = 12;
 }
 // Twelve successive rand() calls summed with the reference's int wrap-around (TdsModel.cpp:1690-1696), the new words
-// going to ring positions PH .. PH + 11.  The additive lagged-Fibonacci recurrence lets all operands be loaded up
-// front (the fifteen old words the twelve new ones depend on); every address is a compile-time constant.
-template <int PH>
-__device__ __forceinline__ uint32_t rng_block(TdsSmem &S, const int lane) {
+// going to ring positions ph .. ph + 11 (ph = 0, 12 or 24).  The additive lagged-Fibonacci recurrence lets all operands
+// be loaded up front (the fifteen old words the twelve new ones depend on).  ONE copy of the code for the three
+// phases (the time loop lives off its instruction cache): the three runs of old words start at ring positions that
+// depend on the phase, inside a run every address is base + constant.
+__device__ __forceinline__ uint32_t rng_block(TdsSmem &S, const int lane, const int ph) {
+  const uint32_t *a0 = &S.rng[ph + 5][lane];                        // words i - 31 of the first seven: ph + 5 .. ph + 11
+  const uint32_t *a1 = &S.rng[ph == 24 ? 0 : ph + 12][lane];        // ... of the last five: (ph + 12 .. ph + 16) mod 36
+  const uint32_t *m0 = &S.rng[ph == 0 ? 33 : ph - 3][lane];         // words i - 3 of the first three: (ph - 3 .. ph - 1) mod 36
   uint32_t a[12], m[3], o[12];
 #pragma unroll
-  for (int q = 0; q < 12; q++) a[q] = S.rng[(PH + q + 5) % 36][lane];   // word i - 31
+  for (int q = 0; q < 7; q++) a[q] = a0[q * LANES];
 #pragma unroll
-  for (int q = 0; q < 3; q++) m[q] = S.rng[(PH + q + 33) % 36][lane];   // word i - 3
+  for (int q = 7; q < 12; q++) a[q] = a1[(q - 7) * LANES];
+#pragma unroll
+  for (int q = 0; q < 3; q++) m[q] = m0[q * LANES];
   uint32_t isum = 0;
 #pragma unroll
   for (int q = 0; q < 12; q++) {
     o[q] = a[q] + (q < 3 ? m[q] : o[q < 3 ? 0 : q - 3]);
     isum += o[q] >> 1;
   }
+  uint32_t *w = &S.rng[ph][lane];
 #pragma unroll
-  for (int q = 0; q < 12; q++) S.rng[PH + q][lane] = o[q];
+  for (int q = 0; q < 12; q++) w[q * LANES] = o[q];
   return isum;
 }
 
@@ -1243,15 +1250,15 @@ __device__ __forceinline__ double nz_amp(double old, double target, double F) { 
 // generator is back at phase 12 after three sums, so all lanes run the same straight-line code); up to two entries
 // wait for the next step.  Publishes head and fill level.
 __device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs &N) {
-  auto put = [&](uint32_t v) {
-    int t = N.head + (N.cap - N.free);
-    if (t >= N.cap) t -= N.cap;
-    S.nzsum[t][lane] = v;
-    N.free--;
-  };
+  int t = N.head + (N.cap - N.free);
+  if (t >= N.cap) t -= N.cap;
   while (N.free >= 3) {
-    const uint32_t s0 = rng_block<12>(S, lane), s1 = rng_block<24>(S, lane), s2 = rng_block<0>(S, lane);
-    put(s0); put(s1); put(s2);
+#pragma unroll 1
+    for (int j = 0; j < 3; j++) {  // phases 12, 24, 0
+      S.nzsum[t][lane] = rng_block(S, lane, j == 2 ? 0 : 12 + 12 * j);
+      t = t + 1 >= N.cap ? 0 : t + 1;
+    }
+    N.free -= 3;
   }
   S.nzring[lane] = (uint32_t)N.head | ((uint32_t)(N.cap - N.free) << 8) | ((uint32_t)N.cap << 16);
 }
@@ -1332,10 +1339,10 @@ __device__ __forceinline__ unsigned long long nz_slot(const NzConst &P, TdsSmem 
 // almost every instruction it executes once per step: what counts is the number of instructions on its path):
 //   warp F  (noise_decay, before its own pass A: it has the most slack of the static chain warps): the sources nothing
 //           feeds this step decay (calcNoiseSample, TdsModel.cpp:1637-1660); the still audible ones -> nzdecay;
-//   warps X1, N1, T2 (noise_tongue; slots 1, 2, 3: X1 is idle in pass A otherwise, N1 and T2 are the static chain warps
+//   warps X1, N1, T2 (noise_slot; slots 1, 2, 3: X1 is idle in pass A otherwise, N1 and T2 are the static chain warps
 //           with the most slack after F): the two tongue constrictions and the lip constriction, complete: factors,
 //           flow, target amplitudes, amplitude filters; their audible sources -> nztongue;
-//   warp X2 (noise_stage): the vocal-fold constriction (slot 0; its flow-independent factors were computed one step
+//   warp X2 (noise_slot, noise_stage): the vocal-fold constriction (slot 0; its flow-independent factors were computed one step
 //           ahead by X1 next to the glottis geometry: nzk0), then -- behind named barrier 4, where the others only arrive
 //           -- one sample for every source that is not silent, in ascending source order: the reference draws from ONE
 //           rand() stream in that order (TdsModel.cpp:1615-1620), here the k-th drawing source takes the k-th entry of
@@ -1370,23 +1377,29 @@ __device__ __noinline__ void noise_decay(const double F, TdsSmem &S, const int l
   bar_arrive(4, NZ_BAR4);
 }
 
-__device__ __noinline__ void noise_tongue(const NzConst P, TdsSmem &S, const int lane, const double r, const double r1, const int k) {
+__device__ __noinline__ unsigned long long noise_slot(const NzConst P, TdsSmem &S, const int lane, const double r, const double r1,
+                                                      const int k, const double gain0) {
   constexpr int NPM = AFS_NUM_PM_SECTIONS;
   unsigned long long draw = 0;
   const uint32_t v = S.nzc_i[k][lane];
   if (__any_sync(0xffffffffu, v & 1u)) {  // (the second tongue constriction and the lips are rare)
-    const bool teeth = (v >> 3) & 1u, lateral = (v >> 4) & 1u;
-    const int nar = min(max((int)((v >> 8) & 255u) - 1, 0), NPM - 1);
-    double amp, cut;
-    nz_factors(nz_area(S, lane, r, r1, nar), lateral ? 0.0 : k == 3 ? 2.0e-7 : teeth ? 10.0e-7 : 5.0e-7, amp, cut);
-    draw = nz_slot(P, S, lane, k, v, amp, cut, nz_down(S, lane, k, r));
+    double amp, cut, down;
+    if (k == 0) {  // vocal folds: the flow-independent factors were computed one step ahead by X1 (nzk0)
+      amp = gain0 * S.nzk0[0][lane]; cut = 0.0; down = S.nzk0[1][lane];
+    } else {
+      const bool teeth = (v >> 3) & 1u, lateral = (v >> 4) & 1u;
+      const int nar = min(max((int)((v >> 8) & 255u) - 1, 0), NPM - 1);
+      nz_factors(nz_area(S, lane, r, r1, nar), lateral ? 0.0 : k == 3 ? 2.0e-7 : teeth ? 10.0e-7 : 5.0e-7, amp, cut);
+      down = nz_down(S, lane, k, r);
+    }
+    draw = nz_slot(P, S, lane, k, v, amp, cut, down);
   }
-  S.nztongue[k - 1][lane] = draw;
-  bar_arrive(4, NZ_BAR4);
+  return draw;
 }
 
-// (returns the number of ring entries consumed)
-__device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int lane, const double gain0
+// Warp X2 behind barrier 4: one sample for every source that is not silent, ascending (returns the number of ring
+// entries consumed); draw: the sources of its own slot 0.
+__device__ __noinline__ int noise_stage(TdsSmem &S, const int lane, unsigned long long draw
 #ifdef AFS_TDS_TIMING
                                         , long long *nz_t
 #endif
@@ -1395,11 +1408,6 @@ __device__ __noinline__ int noise_stage(const NzConst P, TdsSmem &S, const int l
   long long sw_last = clock64();
   long long *sw_t = nz_t;
 #endif
-  unsigned long long draw = 0;  // bit j = source j (0..39: section 25 + j, 40: lips)
-  {
-    const uint32_t v = S.nzc_i[0][lane];
-    if (__any_sync(0xffffffffu, v & 1u)) draw = nz_slot(P, S, lane, 0, v, gain0 * S.nzk0[0][lane], 0.0, S.nzk0[1][lane]);
-  }
   SW_TICK(0);
   bar_sync(4, NZ_BAR4);
   SW_TICK(1);
@@ -1940,8 +1948,11 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     // ============ pass A: update (step n-1), elements + rows (step n) ============
     if (ROLE == 1 && NOISE && X.rows) {  // (see noise_decay)
       if (warp == W_F) noise_decay(P.nz_F, S, lane, nz_live);
-      else if (warp == W_N1 || warp == W_T2)  // the two static chain warps with the most slack after F
-        noise_tongue(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1, warp == W_N1 ? 2 : 3);
+      else if (warp == W_N1 || warp == W_T2) {  // the two static chain warps with the most slack after F
+        const int k = warp == W_N1 ? 2 : 3;
+        S.nztongue[k - 1][lane] = noise_slot(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1, k, 0.0);
+        bar_arrive(4, NZ_BAR4);
+      }
     }
     // (state dump requested for this step: update and rows in two separate passes, the dump in between)
     if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true, OPT>(P, S, lane, warp, wcfg, dst, X);
@@ -1957,7 +1968,10 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       }
     }
     if (ROLE == 2 && n > 1) emit_update(P, xr);  // (the sample emitted in iteration n-1)
-    if (ROLE == 2 && NOISE && X.rows) noise_tongue(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1, 1);
+    if (ROLE == 2 && NOISE && X.rows) {
+      S.nztongue[0][lane] = noise_slot(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1, 1, 0.0);
+      bar_arrive(4, NZ_BAR4);
+    }
     if (ROLE == 3 && NOISE && X.rows) {  // the constrictions' share of the noise sources of step n
       // (the control-frame ratio only enters smooth quantities here; the decisions that need the reference's own
       //  rounding of it were made by the pre-pass)
@@ -1966,7 +1980,8 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         nr.asp = asp;
         nr.gain = 0.5e-7 * exp(asp * (2.302585092994045684 / 20.0));
       }
-      const int used = noise_stage(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, nr.gain
+      const unsigned long long draw0 = noise_slot(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1, 0, nr.gain);
+      const int used = noise_stage(S, lane, draw0
 #ifdef AFS_TDS_TIMING
                                    , sw_acc
 #endif
