@@ -152,6 +152,7 @@ struct TdsSmem {
   // prepared by warp X1 for the vocal-fold constriction of the NEXT step, next to the glottis geometry: sqrt(A) / A^3
   // of the upper glottis area and the downstream factor (see noise_stage)
   double nzk0[2][LANES];
+  unsigned long long nzfed[LANES];               // sources the four constriction slots feed (run records: kept by X1)
   unsigned long long nzdecay[LANES];             // decaying sources (nothing feeds them this step) that are still audible
   unsigned long long nztongue[3][LANES];         // sources fed by the tongue / lip constrictions (slots 1..3) that are audible
   double nzlip[LANES];                           // noiseMagnitude of the flow through the lips (currents 93 + 94)
@@ -1350,27 +1351,19 @@ __device__ __forceinline__ unsigned long long nz_slot(const NzConst &P, TdsSmem 
 // Every source is written by exactly one of them: a fed source by the warp of the LAST slot that feeds it (slot words,
 // bits 5 / 6), the others by F.  Everything is finished before the barrier that ends pass A; the chain warps only add
 // sample = out * amp to their right-hand sides.
-__device__ __noinline__ void noise_decay(const double F, TdsSmem &S, const int lane, unsigned long long &live) {
-  const unsigned long long fed = nz_fed(S, lane);
+__device__ __noinline__ void noise_decay(const double F, TdsSmem &S, const int lane, unsigned long long &live, const bool have_fed) {
+  const unsigned long long fed = have_fed ? S.nzfed[lane] : nz_fed(S, lane);
   unsigned long long todo = live & ~fed, alive = fed, draw = 0;
-  while (todo) {  // two per pass (small loop body: see above)
-    const int j0 = __ffsll((long long)todo) - 1;
+  while (todo) {  // (one source per pass: the loop body stays in the instruction buffer of the sub-partition)
+    const int j = __ffsll((long long)todo) - 1;
     todo &= todo - 1;
-    const bool two = todo != 0;
-    const int j1 = two ? __ffsll((long long)todo) - 1 : j0;
-    todo &= todo - 1;
-    const double old0 = S.namp[j0][lane], old1 = S.namp[j1][lane];
-    double a0 = nz_amp(old0, 0.0, F), a1 = nz_amp(old1, 0.0, F);
-    if ((old0 >= 0.001) && (a0 < 0.001)) S.nout[j0][lane] = 0.0;
-    if (two && (old1 >= 0.001) && (a1 < 0.001)) S.nout[j1][lane] = 0.0;
-    if (a0 >= 0.001) draw |= 1ull << j0;
-    if (two && (a1 >= 0.001)) draw |= 1ull << j1;
-    if (a0 < 1.0e-13) a0 = 0.0;  // (the reference lets it decay for ever; a source is silent below 1e-3)
-    else alive |= 1ull << j0;
-    if (a1 < 1.0e-13) a1 = 0.0;
-    else if (two) alive |= 1ull << j1;
-    S.namp[j0][lane] = a0;
-    if (two) S.namp[j1][lane] = a1;
+    const double old = S.namp[j][lane];
+    double a = nz_amp(old, 0.0, F);
+    if ((old >= 0.001) && (a < 0.001)) S.nout[j][lane] = 0.0;
+    if (a >= 0.001) draw |= 1ull << j;
+    if (a < 1.0e-13) a = 0.0;  // (the reference lets it decay for ever; a source is silent below 1e-3)
+    else alive |= 1ull << j;
+    S.namp[j][lane] = a;
   }
   live = alive;
   S.nzdecay[lane] = draw;
@@ -1411,26 +1404,17 @@ __device__ __noinline__ int noise_stage(TdsSmem &S, const int lane, unsigned lon
   SW_TICK(0);
   bar_sync(4, NZ_BAR4);
   SW_TICK(1);
-  // samples, ascending: the k-th drawing source takes the k-th sum (two independent low-pass updates per pass)
+  // samples, ascending: the k-th drawing source takes the k-th sum
   draw |= S.nzdecay[lane] | S.nztongue[0][lane] | S.nztongue[1][lane] | S.nztongue[2][lane];
   const uint32_t ring = S.nzring[lane];
   const int cap = (int)(ring >> 16);
   int i = (int)(ring & 255u), n_draw = 0;
-  while (draw) {
-    const int j0 = __ffsll((long long)draw) - 1;
+  while (draw) {  // (one source per pass, see noise_decay)
+    const int j = __ffsll((long long)draw) - 1;
     draw &= draw - 1;
-    const bool two = draw != 0;
-    const int j1 = two ? __ffsll((long long)draw) - 1 : j0;
-    draw &= draw - 1;
-    const int i1 = i + 1 >= cap ? i + 1 - cap : i + 1;
-    const uint32_t s0 = S.nzsum[i][lane], s1 = S.nzsum[i1][lane];
-    const double o0 = nz_sample(S.ncut[j0][lane], s0, S.nout[j0][lane]);
-    const double o1 = nz_sample(S.ncut[j1][lane], s1, S.nout[j1][lane]);
-    S.nout[j0][lane] = o0;
-    if (two) S.nout[j1][lane] = o1;
-    const int adv = two ? 2 : 1;
-    i += adv; n_draw += adv;
-    if (i >= cap) i -= cap;
+    S.nout[j][lane] = nz_sample(S.ncut[j][lane], S.nzsum[i][lane], S.nout[j][lane]);
+    i = i + 1 >= cap ? 0 : i + 1;
+    n_draw++;
   }
   SW_TICK(2);
   return n_draw;
@@ -1896,6 +1880,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
       if (A.runs) {
         const NzRun *rec = A.runs + (size_t)tract * (size_t)A.run_items;
         nz_put_run(S, lane, rec);
+        S.nzfed[lane] = nz_fed(S, lane);
         feed.next = rec->next;
         feed.idx = rec->next_idx;
       } else {
@@ -1947,7 +1932,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(0);
     // ============ pass A: update (step n-1), elements + rows (step n) ============
     if (ROLE == 1 && NOISE && X.rows) {  // (see noise_decay)
-      if (warp == W_F) noise_decay(P.nz_F, S, lane, nz_live);
+      if (warp == W_F) noise_decay(P.nz_F, S, lane, nz_live, A.runs != nullptr);
       else if (warp == W_N1 || warp == W_T2) {  // the two static chain warps with the most slack after F
         const int k = warp == W_N1 ? 2 : 3;
         S.nztongue[k - 1][lane] = noise_slot(NzConst{P.nz_F, P.nz_x2000, P.dt}, S, lane, X.ratio, X.ratio1, k, 0.0);
@@ -2005,6 +1990,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         else if ((uint32_t)(n + 1) == feed.next) {
           const NzRun *rec = A.runs + feed.idx;
           nz_put_run(S, lane, rec);
+          S.nzfed[lane] = nz_fed(S, lane);
           feed.next = __ldg(&rec->next);
           feed.idx = __ldg(&rec->next_idx);
         }
@@ -2195,7 +2181,7 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
     S.sepD[w][lane] = 1.0; S.sepR[w][lane] = 0.0; S.redW[w][lane] = 1.0;  // NSEP == NW
   }
   if (warp == 0) {
-    S.nzk0[0][lane] = 0.0; S.nzk0[1][lane] = 0.0; S.nzdecay[lane] = 0; S.nztongue[0][lane] = 0; S.nztongue[1][lane] = 0; S.nztongue[2][lane] = 0;
+    S.nzk0[0][lane] = 0.0; S.nzk0[1][lane] = 0.0; S.nzdecay[lane] = 0; S.nzfed[lane] = 0; S.nztongue[0][lane] = 0; S.nztongue[1][lane] = 0; S.nztongue[2][lane] = 0;
     S.nzlip[lane] = 0.0;
     for (int i = 0; i < NUX; i++) S.uext[i][lane] = 0.0;
     for (int i = 0; i < 5; i++) S.lf[i][lane] = 0.0;
