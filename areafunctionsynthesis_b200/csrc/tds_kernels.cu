@@ -134,8 +134,8 @@ struct TdsSmem {
   // boundary record of every segment = its LAST section, for the first row of the next segment
   double bE[NSEG][LANES], bL[NSEG][LANES], bR[NSEG][LANES], bI[NSEG][LANES], bG[NSEG][LANES], bD[NSEG][LANES];
   double csib[4][LANES];                         // history term c of the branch heads 29, 84, 41, 65 (sibling rows)
-  double sepD[NSEP][LANES], sepR[NSEP][LANES], redW[NSEP][LANES];
-  double redC[2][LANES];                         // fill couplings 29 <-> 40 and 41 <-> 52 of the reduced system
+  double sepD[NSEP][LANES], sepR[NSEP][LANES];
+  double redJ[3][2][LANES];                      // pivot and right-hand side of the chain ends 40, 41, 65 (junction of the reduced system)
   double sideDD[NSEG][LANES], sideDR[NSEG][LANES], sideF[NSEG][LANES];
   double lf[5][LANES];                           // fossa current 84 folded into the clique {28, 29}
   double radc[2][2][LANES];                      // radiation pairs folded into currents 64 / 83
@@ -1247,13 +1247,13 @@ __device__ __forceinline__ void nz_lowpass(TdsSmem &S, const int lane, const int
 }
 // amplitude filter of calcNoiseSample (TdsModel.cpp:1637-1641), the reference's roundings
 __device__ __forceinline__ double nz_amp(double old, double target, double F) { return __dadd_rn(old, __dmul_rn(F, __dsub_rn(target, old))); }
-// Warp X2, while the reduced system is solved: new sums for the entries the step has consumed, three at a time (the
-// generator is back at phase 12 after three sums, so all lanes run the same straight-line code); up to two entries
-// wait for the next step.  Publishes head and fill level.
-__device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs &N) {
+// Warp X2, behind its sample loop: new sums for the entries the step has consumed, three at a time (the generator is
+// back at phase 12 after three sums, so all lanes run the same code); up to two entries wait for the next step.
+// Publishes head and fill level.
+__device__ __forceinline__ void nz_refill(TdsSmem &S, const int lane, NoiseRegs &N, int triples) {
   int t = N.head + (N.cap - N.free);
   if (t >= N.cap) t -= N.cap;
-  while (N.free >= 3) {
+  for (; N.free >= 3 && triples > 0; triples--) {
 #pragma unroll 1
     for (int j = 0; j < 3; j++) {  // phases 12, 24, 0
       S.nzsum[t][lane] = rng_block(S, lane, j == 2 ? 0 : 12 + 12 * j);
@@ -1450,128 +1450,138 @@ __device__ __noinline__ void reduced_constants(TdsSmem &S, const int lane) {
   const double t15 = c1 * w15;
   if (lane == 0) { S.rcn[0] = w7; S.rcn[1] = t7; S.rcn[2] = w15; S.rcn[3] = t15; S.rcn[4] = t15 * c1; }
 }
-// forward: chain T (7,15,22,28,29,34 -> 40), chain M (64,58,52,46 -> 41), chain N (83,75,70 -> 65).  In the two long
-// chains two independent eliminations run interleaved in the same warp (22 -> 28 beside 34 -> {29, 40}; 64 -> 58 beside
-// 46 -> {41, 52}), which shortens the serial chain of reciprocals -- the reduced system is pure latency.
-__device__ __noinline__ void reduced_forward(TdsSmem &S, const int lane, const int chain) {
-  if (chain == 0) {
-    const double c2 = S.sideF[W_GP][lane], c3 = S.lf[4][lane], c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane];
-    const double r7 = S.sepR[S7][lane] - S.sideDR[W_T1][lane];
-    const double r15 = fma(-S.rcn[1], r7, S.sepR[S15][lane] - S.sideDR[W_T2][lane]);
-    double d22 = S.sepD[S22][lane] - S.sideDD[W_GP][lane] - S.rcn[4];
-    const double r22 = fma(-S.rcn[3], r15, S.sepR[S22][lane] - S.sideDR[W_GP][lane]);
-    double d28 = S.sepD[S28][lane] - S.lf[0][lane], r28 = S.sepR[S28][lane] - S.lf[1][lane];
-    double d29 = S.sepD[S29][lane] - S.lf[2][lane], r29 = S.sepR[S29][lane] - S.lf[3][lane];
-    double d34 = S.sepD[S34][lane] - S.sideDD[W_P2][lane];
-    const double r34 = S.sepR[S34][lane] - S.sideDR[W_P2][lane];
-    double d40 = S.sepD[S40][lane], r40 = S.sepR[S40][lane];
-    // 22 -> 28  ||  34 -> {29, 40} (fill: coupling 29 <-> 40)
-    const double w22 = fast_rcp(d22), w34 = fast_rcp(d34);
-    const double t22 = c2 * w22, ta = c4 * w34, tb = c5 * w34;
-    d28 = fma(-t22, c2, d28); r28 = fma(-t22, r22, r28);
-    d29 = fma(-ta, c4, d29); r29 = fma(-ta, r34, r29);
-    d40 = fma(-tb, c5, d40); r40 = fma(-tb, r34, r40);
-    const double c6 = -ta * c5;
-    // 28 -> 29, 29 -> 40
-    const double w28 = fast_rcp(d28);
-    const double t28 = c3 * w28;
-    d29 = fma(-t28, c3, d29); r29 = fma(-t28, r28, r29);
-    const double w29 = fast_rcp(d29);
-    const double t29 = c6 * w29;
-    d40 = fma(-t29, c6, d40); r40 = fma(-t29, r29, r40);
-    S.sepR[S7][lane] = r7; S.sepR[S15][lane] = r15;
-    S.redW[S22][lane] = w22; S.sepR[S22][lane] = r22; S.redW[S28][lane] = w28; S.sepR[S28][lane] = r28;
-    S.redW[S29][lane] = w29; S.sepR[S29][lane] = r29; S.redW[S34][lane] = w34; S.sepR[S34][lane] = r34;
-    S.redW[S40][lane] = d40; S.sepR[S40][lane] = r40;
-    S.redC[0][lane] = c6;
-  } else if (chain == 1) {
-    const double c0 = S.sideF[W_M3][lane], c1 = S.sideF[W_M2][lane], c2 = S.sideF[W_M1][lane], c3 = S.sideF[W_M0][lane];
-    double d41 = S.sepD[S41][lane], r41 = S.sepR[S41][lane];
-    double d46 = S.sepD[S46][lane] - S.sideDD[W_M1][lane];
-    const double r46 = S.sepR[S46][lane] - S.sideDR[W_M1][lane];
-    double d52 = S.sepD[S52][lane] - S.sideDD[W_M2][lane], r52 = S.sepR[S52][lane] - S.sideDR[W_M2][lane];
-    double d58 = S.sepD[S58][lane] - S.sideDD[W_M3][lane], r58 = S.sepR[S58][lane] - S.sideDR[W_M3][lane];
-    double d64 = S.sepD[S64][lane] - S.radc[0][0][lane];
-    const double r64 = S.sepR[S64][lane] - S.radc[0][1][lane];
-    // 64 -> 58  ||  46 -> {41, 52} (fill: coupling 41 <-> 52)
-    const double w64 = fast_rcp(d64), w46 = fast_rcp(d46);
-    const double t64 = c0 * w64, ta = c3 * w46, tb = c2 * w46;
-    d58 = fma(-t64, c0, d58); r58 = fma(-t64, r64, r58);
-    d41 = fma(-ta, c3, d41); r41 = fma(-ta, r46, r41);
-    d52 = fma(-tb, c2, d52); r52 = fma(-tb, r46, r52);
-    const double c6 = -ta * c2;
-    // 58 -> 52, 52 -> 41
-    const double w58 = fast_rcp(d58);
-    const double t58 = c1 * w58;
-    d52 = fma(-t58, c1, d52); r52 = fma(-t58, r58, r52);
-    const double w52 = fast_rcp(d52);
-    const double t52 = c6 * w52;
-    d41 = fma(-t52, c6, d41); r41 = fma(-t52, r52, r41);
-    S.redW[S64][lane] = w64; S.sepR[S64][lane] = r64; S.redW[S58][lane] = w58; S.sepR[S58][lane] = r58;
-    S.redW[S52][lane] = w52; S.sepR[S52][lane] = r52; S.redW[S46][lane] = w46; S.sepR[S46][lane] = r46;
-    S.redW[S41][lane] = d41; S.sepR[S41][lane] = r41;
-    S.redC[1][lane] = c6;
-  } else {
-    const double c0 = S.sideF[W_N2][lane], c1 = S.sideF[W_N1][lane], c2 = S.sideF[W_NV][lane];
-    double d65 = S.sepD[S65][lane], r65 = S.sepR[S65][lane];
-    double d70 = S.sepD[S70][lane] - S.sideDD[W_N1][lane], r70 = S.sepR[S70][lane] - S.sideDR[W_N1][lane];
-    double d75 = S.sepD[S75][lane] - S.sideDD[W_N2][lane], r75 = S.sepR[S75][lane] - S.sideDR[W_N2][lane];
-    double d83 = S.sepD[S83][lane] - S.radc[1][0][lane], r83 = S.sepR[S83][lane] - S.radc[1][1][lane];
-    red_elim(d83, r83, c0, d75, r75);
-    red_elim(d75, r75, c1, d70, r70);
-    red_elim(d70, r70, c2, d65, r65);
-    S.redW[S83][lane] = d83; S.sepR[S83][lane] = r83; S.redW[S75][lane] = d75; S.sepR[S75][lane] = r75;
-    S.redW[S70][lane] = d70; S.sepR[S70][lane] = r70; S.redW[S65][lane] = d65; S.sepR[S65][lane] = r65;
-  }
+// One call per step and chain warp: forward elimination of the own chain -- chain T (7,15,22,28,29,34 -> 40) on T0,
+// chain M (64,58,52,46 -> 41) on T1, chain N (83,75,70 -> 65) on T2 --, ONE barrier, the junction at the velum (clique
+// {40, 41, 65} through section 40, the last section of warp P2) solved by all three warps for themselves, back
+// substitution of the own chain.  The reduced system is pure latency of a warp that runs alone: the reciprocals and
+// right-hand sides of the own chain stay in registers between the two sweeps, and in the two long chains two
+// independent eliminations run interleaved (22 -> 28 beside 34 -> {29, 40}; 64 -> 58 beside 46 -> {41, 52}).
+struct RedKeep { double w[4], r[6], c[7]; };
+__device__ __forceinline__ void red_fwd_T(TdsSmem &S, const int lane, RedKeep &K, double &dj, double &rj) {
+  const double c2 = S.sideF[W_GP][lane], c3 = S.lf[4][lane], c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane];
+  const double r7 = S.sepR[S7][lane] - S.sideDR[W_T1][lane];
+  const double r15 = fma(-S.rcn[1], r7, S.sepR[S15][lane] - S.sideDR[W_T2][lane]);
+  double d22 = S.sepD[S22][lane] - S.sideDD[W_GP][lane] - S.rcn[4];
+  const double r22 = fma(-S.rcn[3], r15, S.sepR[S22][lane] - S.sideDR[W_GP][lane]);
+  double d28 = S.sepD[S28][lane] - S.lf[0][lane], r28 = S.sepR[S28][lane] - S.lf[1][lane];
+  double d29 = S.sepD[S29][lane] - S.lf[2][lane], r29 = S.sepR[S29][lane] - S.lf[3][lane];
+  double d34 = S.sepD[S34][lane] - S.sideDD[W_P2][lane];
+  const double r34 = S.sepR[S34][lane] - S.sideDR[W_P2][lane];
+  double d40 = S.sepD[S40][lane], r40 = S.sepR[S40][lane];
+  // 22 -> 28  ||  34 -> {29, 40} (fill: coupling 29 <-> 40)
+  const double w22 = fast_rcp(d22), w34 = fast_rcp(d34);
+  const double t22 = c2 * w22, ta = c4 * w34, tb = c5 * w34;
+  d28 = fma(-t22, c2, d28); r28 = fma(-t22, r22, r28);
+  d29 = fma(-ta, c4, d29); r29 = fma(-ta, r34, r29);
+  d40 = fma(-tb, c5, d40); r40 = fma(-tb, r34, r40);
+  const double c6 = -ta * c5;
+  // 28 -> 29, 29 -> 40
+  const double w28 = fast_rcp(d28);
+  const double t28 = c3 * w28;
+  d29 = fma(-t28, c3, d29); r29 = fma(-t28, r28, r29);
+  const double w29 = fast_rcp(d29);
+  const double t29 = c6 * w29;
+  d40 = fma(-t29, c6, d40); r40 = fma(-t29, r29, r40);
+  K.w[0] = w22; K.w[1] = w28; K.w[2] = w29; K.w[3] = w34;
+  K.r[0] = r7; K.r[1] = r15; K.r[2] = r22; K.r[3] = r28; K.r[4] = r29; K.r[5] = r34;
+  K.c[2] = c2; K.c[3] = c3; K.c[4] = c4; K.c[5] = c5; K.c[6] = c6;
+  dj = d40; rj = r40;
 }
-// Junction at the velum: clique {40, 41, 65} through section 40 (last section of warp P2).
-__device__ __noinline__ void reduced_junction(TdsSmem &S, const int lane) {
+__device__ __forceinline__ void red_back_T(TdsSmem &S, const int lane, const RedKeep &K, const double u40) {
+  const double c0 = S.sideF[W_T1][lane], c1 = S.sideF[W_T2][lane];
+  const double u29 = (K.r[4] - K.c[6] * u40) * K.w[2];
+  const double u34 = (K.r[5] - K.c[4] * u29 - K.c[5] * u40) * K.w[3];
+  const double u28 = (K.r[3] - K.c[3] * u29) * K.w[1];
+  const double u22 = (K.r[2] - K.c[2] * u28) * K.w[0];
+  const double u15 = (K.r[1] - c1 * u22) * S.rcn[2];
+  const double u7 = (K.r[0] - c0 * u15) * S.rcn[0];
+  S.sepR[S40][lane] = u40;
+  S.sepR[S34][lane] = u34; S.sepR[S29][lane] = u29; S.sepR[S28][lane] = u28; S.sepR[S22][lane] = u22;
+  S.sepR[S15][lane] = u15; S.sepR[S7][lane] = u7;
+}
+__device__ __forceinline__ void red_fwd_M(TdsSmem &S, const int lane, RedKeep &K, double &dj, double &rj) {
+  const double c0 = S.sideF[W_M3][lane], c1 = S.sideF[W_M2][lane], c2 = S.sideF[W_M1][lane], c3 = S.sideF[W_M0][lane];
+  double d41 = S.sepD[S41][lane], r41 = S.sepR[S41][lane];
+  double d46 = S.sepD[S46][lane] - S.sideDD[W_M1][lane];
+  const double r46 = S.sepR[S46][lane] - S.sideDR[W_M1][lane];
+  double d52 = S.sepD[S52][lane] - S.sideDD[W_M2][lane], r52 = S.sepR[S52][lane] - S.sideDR[W_M2][lane];
+  double d58 = S.sepD[S58][lane] - S.sideDD[W_M3][lane], r58 = S.sepR[S58][lane] - S.sideDR[W_M3][lane];
+  double d64 = S.sepD[S64][lane] - S.radc[0][0][lane];
+  const double r64 = S.sepR[S64][lane] - S.radc[0][1][lane];
+  // 64 -> 58  ||  46 -> {41, 52} (fill: coupling 41 <-> 52)
+  const double w64 = fast_rcp(d64), w46 = fast_rcp(d46);
+  const double t64 = c0 * w64, ta = c3 * w46, tb = c2 * w46;
+  d58 = fma(-t64, c0, d58); r58 = fma(-t64, r64, r58);
+  d41 = fma(-ta, c3, d41); r41 = fma(-ta, r46, r41);
+  d52 = fma(-tb, c2, d52); r52 = fma(-tb, r46, r52);
+  const double c6 = -ta * c2;
+  // 58 -> 52, 52 -> 41
+  const double w58 = fast_rcp(d58);
+  const double t58 = c1 * w58;
+  d52 = fma(-t58, c1, d52); r52 = fma(-t58, r58, r52);
+  const double w52 = fast_rcp(d52);
+  const double t52 = c6 * w52;
+  d41 = fma(-t52, c6, d41); r41 = fma(-t52, r52, r41);
+  K.w[0] = w64; K.w[1] = w58; K.w[2] = w52; K.w[3] = w46;
+  K.r[0] = r64; K.r[1] = r58; K.r[2] = r52; K.r[3] = r46;
+  K.c[0] = c0; K.c[1] = c1; K.c[2] = c2; K.c[3] = c3; K.c[6] = c6;
+  dj = d41; rj = r41;
+}
+__device__ __forceinline__ void red_back_M(TdsSmem &S, const int lane, const RedKeep &K, const double u41) {
+  const double u52 = (K.r[2] - K.c[6] * u41) * K.w[2];
+  const double u46 = (K.r[3] - K.c[3] * u41 - K.c[2] * u52) * K.w[3];
+  const double u58 = (K.r[1] - K.c[1] * u52) * K.w[1];
+  const double u64 = (K.r[0] - K.c[0] * u58) * K.w[0];
+  S.sepR[S41][lane] = u41;
+  S.sepR[S46][lane] = u46; S.sepR[S52][lane] = u52; S.sepR[S58][lane] = u58; S.sepR[S64][lane] = u64;
+}
+__device__ __forceinline__ void red_fwd_N(TdsSmem &S, const int lane, RedKeep &K, double &dj, double &rj) {
+  const double c0 = S.sideF[W_N2][lane], c1 = S.sideF[W_N1][lane], c2 = S.sideF[W_NV][lane];
+  double d65 = S.sepD[S65][lane], r65 = S.sepR[S65][lane];
+  double d70 = S.sepD[S70][lane] - S.sideDD[W_N1][lane], r70 = S.sepR[S70][lane] - S.sideDR[W_N1][lane];
+  double d75 = S.sepD[S75][lane] - S.sideDD[W_N2][lane], r75 = S.sepR[S75][lane] - S.sideDR[W_N2][lane];
+  double d83 = S.sepD[S83][lane] - S.radc[1][0][lane], r83 = S.sepR[S83][lane] - S.radc[1][1][lane];
+  red_elim(d83, r83, c0, d75, r75);   // (leaves the reciprocal of the pivot in d)
+  red_elim(d75, r75, c1, d70, r70);
+  red_elim(d70, r70, c2, d65, r65);
+  K.w[0] = d83; K.w[1] = d75; K.w[2] = d70;
+  K.r[0] = r83; K.r[1] = r75; K.r[2] = r70;
+  K.c[0] = c0; K.c[1] = c1; K.c[2] = c2;
+  dj = d65; rj = r65;
+}
+__device__ __forceinline__ void red_back_N(TdsSmem &S, const int lane, const RedKeep &K, const double u65) {
+  const double u70 = (K.r[2] - K.c[2] * u65) * K.w[2];
+  const double u75 = (K.r[1] - K.c[1] * u70) * K.w[1];
+  const double u83 = (K.r[0] - K.c[0] * u75) * K.w[0];
+  S.sepR[S65][lane] = u65;
+  S.sepR[S70][lane] = u70; S.sepR[S75][lane] = u75; S.sepR[S83][lane] = u83;
+}
+__device__ __noinline__ void reduced_solve(TdsSmem &S, const int lane, const int chain) {
+  RedKeep K;
+  double dj, rj;
+  if (chain == 0) red_fwd_T(S, lane, K, dj, rj);
+  else if (chain == 1) red_fwd_M(S, lane, K, dj, rj);
+  else red_fwd_N(S, lane, K, dj, rj);
+  S.redJ[chain][0][lane] = dj; S.redJ[chain][1][lane] = rj;
+  bar_sync(3, 96);
+  // junction (the same few instructions on the three warps, which share a sub-partition: no second barrier)
   const double e = S.bE[W_P2][lane], g = e + S.bG[W_P2][lane];
-  const double r65 = S.sepR[S65][lane], r41i = S.sepR[S41][lane];
-  const double w65 = fast_rcp(S.redW[S65][lane]);
-  double d40 = S.redW[S40][lane] - e * e * w65;
-  const double d41 = S.redW[S41][lane] - g * g * w65;
+  const double r65 = S.redJ[2][1][lane], r41i = S.redJ[1][1][lane];
+  const double w65 = fast_rcp(S.redJ[2][0][lane]);
+  double d40 = S.redJ[0][0][lane] - e * e * w65;
+  const double d41 = S.redJ[1][0][lane] - g * g * w65;
   const double o = -e + e * g * w65;
-  double r40 = S.sepR[S40][lane] + e * w65 * r65;
+  double r40 = S.redJ[0][1][lane] + e * w65 * r65;
   const double r41 = r41i - g * w65 * r65;
   const double w41 = fast_rcp(d41);
   d40 -= o * o * w41;
   r40 -= o * w41 * r41;
   const double u40 = fast_div(r40, d40);
+  if (chain == 0) { red_back_T(S, lane, K, u40); return; }
   const double u41 = (r41 - o * u40) * w41;
+  if (chain == 1) { red_back_M(S, lane, K, u41); return; }
   const double u65 = (r65 + e * u40 - g * u41) * w65;
-  S.sepR[S40][lane] = u40; S.sepR[S41][lane] = u41; S.sepR[S65][lane] = u65;
-}
-__device__ __noinline__ void reduced_back(TdsSmem &S, const int lane, const int chain) {
-  if (chain == 0) {
-    const double c0 = S.sideF[W_T1][lane], c1 = S.sideF[W_T2][lane], c2 = S.sideF[W_GP][lane], c3 = S.lf[4][lane];
-    const double c4 = S.sideF[W_P1][lane], c5 = S.sideF[W_P2][lane], c6 = S.redC[0][lane];
-    const double u40 = S.sepR[S40][lane];
-    const double u29 = (S.sepR[S29][lane] - c6 * u40) * S.redW[S29][lane];
-    const double u34 = (S.sepR[S34][lane] - c4 * u29 - c5 * u40) * S.redW[S34][lane];
-    const double u28 = (S.sepR[S28][lane] - c3 * u29) * S.redW[S28][lane];
-    const double u22 = (S.sepR[S22][lane] - c2 * u28) * S.redW[S22][lane];
-    const double u15 = (S.sepR[S15][lane] - c1 * u22) * S.rcn[2];
-    const double u7 = (S.sepR[S7][lane] - c0 * u15) * S.rcn[0];
-    S.sepR[S34][lane] = u34; S.sepR[S29][lane] = u29; S.sepR[S28][lane] = u28; S.sepR[S22][lane] = u22;
-    S.sepR[S15][lane] = u15; S.sepR[S7][lane] = u7;
-  } else if (chain == 1) {
-    const double c0 = S.sideF[W_M3][lane], c1 = S.sideF[W_M2][lane], c2 = S.sideF[W_M1][lane], c3 = S.sideF[W_M0][lane];
-    const double c6 = S.redC[1][lane];
-    const double u41 = S.sepR[S41][lane];
-    const double u52 = (S.sepR[S52][lane] - c6 * u41) * S.redW[S52][lane];
-    const double u46 = (S.sepR[S46][lane] - c3 * u41 - c2 * u52) * S.redW[S46][lane];
-    const double u58 = (S.sepR[S58][lane] - c1 * u52) * S.redW[S58][lane];
-    const double u64 = (S.sepR[S64][lane] - c0 * u58) * S.redW[S64][lane];
-    S.sepR[S46][lane] = u46; S.sepR[S52][lane] = u52; S.sepR[S58][lane] = u58; S.sepR[S64][lane] = u64;
-  } else {
-    const double c0 = S.sideF[W_N2][lane], c1 = S.sideF[W_N1][lane], c2 = S.sideF[W_NV][lane];
-    const double u65 = S.sepR[S65][lane];
-    const double u70 = (S.sepR[S70][lane] - c2 * u65) * S.redW[S70][lane];
-    const double u75 = (S.sepR[S75][lane] - c1 * u70) * S.redW[S75][lane];
-    const double u83 = (S.sepR[S83][lane] - c0 * u75) * S.redW[S83][lane];
-    S.sepR[S70][lane] = u70; S.sepR[S75][lane] = u75; S.sepR[S83][lane] = u83;
-  }
+  red_back_N(S, lane, K, u65);
 }
 
 // ---- glottis (TriangularGlottis.cpp:154-576) -----------------------------------
@@ -1855,7 +1865,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     if (NOISE) {
       rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ph);
       nr.cap = nr.free = NZ_RING;
-      nz_refill(S, lane, nr);  // (42 sums; the ring is never emptier than that when a step begins)
+      nz_refill(S, lane, nr, NZ_RING);  // (42 sums; the ring is never emptier than that when a step begins)
     }
   }
   if (ROLE == 2) {
@@ -1973,6 +1983,9 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
                                    );
       nr.head += used; nr.free += used;
       if (nr.head >= nr.cap) nr.head -= nr.cap;
+      // new sums for the entries just consumed: X2 waits for the dynamic chain warps at the end of pass A anyway (in
+      // the reduced-system phase, where this used to be, it made X2 the warp the others wait for)
+      nz_refill(S, lane, nr, NZ_RING);
     }
     AFS_TICK(1);
     cta_sync();
@@ -2060,24 +2073,11 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     AFS_TICK(3);
     if (ROLE != 2) {
       bar_sync(1, TDS_THREADS);
-      if (ROLE == 3 && NOISE) {  // (this warp only waits for the reduced system)
-#ifdef AFS_TDS_TIMING
-        const long long t_rf = clock64();
-#endif
-        nz_refill(S, lane, nr);
-#ifdef AFS_TDS_TIMING
-        sw_acc[3] += clock64() - t_rf;
-#endif
-      }
       // ============ reduced system over the separators ============
       // (the three warps of the reduced system meet on their own barrier; the twelve others only wait for the result)
       if (warp == W_T0 || warp == W_T1 || warp == W_T2) {
         const int chain = warp == W_T0 ? 0 : warp == W_T1 ? 1 : 2;
-        reduced_forward(S, lane, chain);
-        bar_sync(3, 96);
-        if (warp == W_T0) reduced_junction(S, lane);
-        bar_sync(3, 96);
-        reduced_back(S, lane, chain);
+        reduced_solve(S, lane, chain);
       }
       AFS_TICK(4);
       bar_sync(2, TDS_THREADS - 32);
@@ -2178,7 +2178,7 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
       S.bD[w][lane] = 0.0; S.sideDD[w][lane] = 0.0; S.sideDR[w][lane] = 0.0; S.sideF[w][lane] = 0.0;
     }
     S.csib[w & 3][lane] = 0.0;
-    S.sepD[w][lane] = 1.0; S.sepR[w][lane] = 0.0; S.redW[w][lane] = 1.0;  // NSEP == NW
+    S.sepD[w][lane] = 1.0; S.sepR[w][lane] = 0.0;  // NSEP == NW
   }
   if (warp == 0) {
     S.nzk0[0][lane] = 0.0; S.nzk0[1][lane] = 0.0; S.nzdecay[lane] = 0; S.nzfed[lane] = 0; S.nztongue[0][lane] = 0; S.nztongue[1][lane] = 0; S.nztongue[2][lane] = 0;
