@@ -737,7 +737,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": tds_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": tds_tflops / fp64_peak, **traffic_of("tds_noise_on"),
-                     "kernel": "tds_batch_kernel<noise> (+ tds_noise_scan_kernel, inside the timed step)",
+                     "kernel": "tds_batch_kernel<noise> (+ tds_noise_runs_kernel: the 3.5 ms pre-pass is inside the timed step)",
                      "flop_per_tract_step": W_TDS_NOISE,
                      "peak_source": "afs_probe_fp64_tflops, measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": tds_tflops / FP64_NOMINAL_TFLOPS,
