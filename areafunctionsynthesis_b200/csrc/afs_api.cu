@@ -33,7 +33,7 @@ struct afs_ctx {
   unsigned int *progress_h = nullptr, *progress_d = nullptr;
   // test hooks (afs_debug_set)
   int64_t dbg_noise_scan_bytes = 0;
-  int dbg_tds_spread_sms = 0;      // > 0: spread a TDS batch over this many CTAs at most (experiments: SMs left idle)
+  int dbg_tds_spread_sms = 0;      // > 0: spread a TDS batch over this many CTAs (default: 28 tracts per CTA, as few CTAs as possible)
   int dbg_small_batch_max = -1;  // largest batch served by tds_small_kernel (-1: 3 tracts per SM, 0: never)
   int dbg_d2h_slices = 0;
   int run_pool_factor = 32;   // records of the noise pre-pass pool per piece (see tds_run_device); grows on overflow
@@ -811,7 +811,7 @@ int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int 
 
   TdsLaunch L;
   rc = tds_prepare_launch(opts, n_tracts, n_frames, frame_len, fs_tds_hz, sr_factor,
-                          ctx->dbg_tds_spread_sms > 0 ? ctx->dbg_tds_spread_sms : ctx->sm_count, &L);
+                          ctx->dbg_tds_spread_sms, &L);
   if (rc) return rc;
   // everything below the caller's buffers is a stream-ordered temporary (see afs_ctx::pool)
   void *d_bounds = nullptr, *d_dump = nullptr, *d_nzc = nullptr, *d_runs = nullptr, *d_off = nullptr, *d_items = nullptr;

@@ -57,7 +57,7 @@ struct TdsLaunch {
   int n_tracts = 0, n_frames = 0;
 };
 int tds_prepare_launch(const afs_tds_options *opts, int n_tracts, int n_frames, const int32_t *frame_len,
-                       double fs_tds_hz, int sr_factor, int sm_count, TdsLaunch *L);
+                       double fs_tds_hz, int sr_factor, int spread_ctas, TdsLaunch *L);
 cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t *d_bounds, const afs_tube_frame *d_tubes,
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
                        uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const void *d_runs,

@@ -449,8 +449,8 @@ int afs_tds_set_state_dump(afs_ctx *ctx, int step, double *host_out473);
  * piece of a control-frame interval, default 32: tests force the overflow path with 2); "tds.d2h_slices" (time slices
  * of the overlapped device-to-host copy of afs_tds_synthesize, 0 = default 16, 1 = one copy after the kernel);
  * "tds.small_batch_max" (largest batch served by the one-tract-per-CTA kernel tds_small_kernel; -1 = default, three
- * tracts per SM; 0 = never: tests run both kernels on the same input); "tds.spread_sms" (spread a TDS batch over at most
- * this many CTAs instead of one per SM, 0 = default: measurements with SMs left idle).  Unknown keys: AFS_ERR_BAD_ARGUMENT. */
+ * tracts per SM; 0 = never: tests run both kernels on the same input); "tds.spread_sms" (spread a TDS batch over
+ * this many CTAs instead of packing 28 tracts into every CTA, 0 = default: tests and measurements of the packing).  Unknown keys: AFS_ERR_BAD_ARGUMENT. */
 int afs_debug_set(afs_ctx *ctx, const char *key, int64_t value);
 
 /* Measures the FP64 FMA peak of the bound device (independent DFMA chains,

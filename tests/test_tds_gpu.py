@@ -538,7 +538,7 @@ def test_small_and_batch_kernels_agree(ctx, shapes):
 def test_result_does_not_depend_on_cta_packing_or_run(ctx, shapes, noise):
     """Sixteen warps of a CTA exchange everything through shared memory and named barriers; a missing barrier would show
     up as run-to-run differences or as a dependence on how many tracts share a CTA.  The same batch packed 28 tracts
-    per CTA ("tds.spread_sms" = 4 CTAs), spread over all SMs (one tract per CTA), and run twice: identical bits."""
+    per CTA (the default), spread over 148 CTAs ("tds.spread_sms": one tract per CTA), and run twice: identical bits."""
     import areafunctionsynthesis_b200 as afs
     n = len(shapes["names"])
     rng = np.random.default_rng(5)
@@ -553,9 +553,10 @@ def test_result_does_not_depend_on_cta_packing_or_run(ctx, shapes, noise):
         assert not st.any() and np.isfinite(ref).all() and np.abs(ref).max() > 0
         again, _, _ = ctx.tds_synthesize(fr, gl, [500, 400], 44100.0, 2, opts=o, seeds=seeds)
         assert np.array_equal(again, ref)
-        ctx.debug_set("tds.spread_sms", 4)
-        packed, _, _ = ctx.tds_synthesize(fr, gl, [500, 400], 44100.0, 2, opts=o, seeds=seeds)
-        assert np.array_equal(packed, ref)
+        for spread in (148, 7):
+            ctx.debug_set("tds.spread_sms", spread)
+            other, _, _ = ctx.tds_synthesize(fr, gl, [500, 400], 44100.0, 2, opts=o, seeds=seeds)
+            assert np.array_equal(other, ref), spread
     finally:
         ctx.debug_set("tds.spread_sms", 0)
         ctx.debug_set("tds.small_batch_max", -1)
