@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     Group,
     TdsOptions,
     TdsProbes,
+    TdsStream,
     TlOptions,
     area_function_to_frames,
     audio_to_int16,

@@ -103,6 +103,16 @@ def load_library():
     lib.afs_tds_synthesize_probed.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp]
     lib.afs_tds_synthesize_probed_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp, vp]
     lib.afs_tl_mean_flow.argtypes = [vp, i32, vp, dbl, vp, vp]
+    lib.afs_tds_stream_create.argtypes = [vp, vp, i32, dbl, i32, vp, C.POINTER(C.c_void_p)]
+    lib.afs_tds_stream_destroy.argtypes = [vp]
+    lib.afs_tds_stream_reset.argtypes = [vp]
+    lib.afs_tds_stream_samples.argtypes = [vp]
+    lib.afs_tds_stream_samples.restype = C.c_int64
+    lib.afs_tds_stream_synthesize.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.afs_tds_stream_checkpoint_bytes.argtypes = [vp]
+    lib.afs_tds_stream_checkpoint_bytes.restype = C.c_size_t
+    lib.afs_tds_stream_save.argtypes = [vp, vp, C.c_size_t]
+    lib.afs_tds_stream_load.argtypes = [vp, vp, C.c_size_t]
     lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
     lib.afs_debug_set.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.afs_group_create.argtypes = [C.POINTER(C.c_void_p), vp, i32]
@@ -307,6 +317,66 @@ class Group:
         _check(self.lib, self.lib.afs_group_tl_sweep(self.h, C.byref(opts), n, _ptr(frames), int(spectrum_type), int(section),
                                                      float(f0_hz), int(num_freq), _ptr(re), _ptr(im)))
         return re, im
+
+
+class TdsStream:
+    """afs_tds_stream: a batch of utterances whose models live across calls (chunked synthesis, checkpoint / resume)."""
+
+    def __init__(self, ctx, n_tracts, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None):
+        self.ctx, self.lib, self.n, self.sr_factor = ctx, ctx.lib, int(n_tracts), int(sr_factor)
+        self.opts = opts or tds_options_default()
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.afs_tds_stream_create(ctx.h, C.byref(self.opts), self.n, float(fs_tds_hz), self.sr_factor,
+                                                        _ptr(s), C.byref(self.h)), ctx.h)
+        self._primed = False
+
+    def close(self):
+        if self.h:
+            self.lib.afs_tds_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(self.lib, self.lib.afs_tds_stream_reset(self.h), self.ctx.h)
+        self._primed = False
+
+    @property
+    def samples(self):
+        return int(self.lib.afs_tds_stream_samples(self.h))
+
+    def synthesize(self, frames, glottis, frame_len, want_flow=False):
+        """frames [B, F], glottis [B, F, 6], frame_len [F]: frame k yields frame_len[k] samples interpolated from the
+        previous frame; the first frame of a fresh stream only primes.  Returns (audio [B, n_out], flow or None, status)."""
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        B, F = frames.shape
+        assert B == self.n
+        glottis = np.ascontiguousarray(glottis, dtype=np.float64).reshape(B, F, NUM_GLOTTIS_CONTROL)
+        frame_len = np.ascontiguousarray(frame_len, dtype=np.int32)
+        assert frame_len.shape == (F,)
+        n_out = int(frame_len[0 if self._primed else 1:].sum())
+        audio = np.empty((B, n_out))
+        flow = np.empty((B, n_out * self.sr_factor)) if want_flow else None
+        status = np.zeros(B, dtype=np.uint32)
+        _check(self.lib, self.lib.afs_tds_stream_synthesize(self.h, F, _ptr(frame_len), _ptr(frames), _ptr(glottis), _ptr(audio),
+                                                            _ptr(flow), _ptr(status)), self.ctx.h)
+        self._primed = True
+        return audio, flow, status
+
+    def save(self):
+        blob = np.empty(int(self.lib.afs_tds_stream_checkpoint_bytes(self.h)), dtype=np.uint8)
+        _check(self.lib, self.lib.afs_tds_stream_save(self.h, _ptr(blob), blob.size), self.ctx.h)
+        return blob
+
+    def load(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        _check(self.lib, self.lib.afs_tds_stream_load(self.h, _ptr(blob), blob.size), self.ctx.h)
+        self._primed = bool(np.frombuffer(blob[16:20].tobytes(), dtype=np.int32)[0])  # StreamHeader.primed
 
 
 class Context:

@@ -793,7 +793,8 @@ int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int 
                    const afs_tube_frame *d_tubes, const double *d_glottis, double fs_tds_hz, int sr_factor,
                    const uint32_t *d_seeds, double *d_audio, double *d_flow, uint32_t *d_status,
                    const afs_tds_probes *d_probes, cudaStream_t stream, unsigned int *d_progress, int progress_every,
-                   int *ctas_out /* [2]: CTAs of the single launch (0: several launches), tracts per CTA */) {
+                   int *ctas_out /* [2]: CTAs of the single launch (0: several launches), tracts per CTA */,
+                   const double *d_state_in = nullptr, double *d_state_out = nullptr /* chunked synthesis, see afs_tds_stream */) {
   int rc;
   if (!opts || n_tracts < 0 || n_frames < 2 || !frame_len || sr_factor < 1 || !(fs_tds_hz > 0))
     return AFS_ERR_BAD_ARGUMENT;
@@ -828,7 +829,7 @@ int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int 
   {
     const int small_max = ctx->dbg_small_batch_max >= 0 ? ctx->dbg_small_batch_max : 3 * ctx->sm_count;  // (three resident CTAs per SM)
     if (n_tracts <= small_max && tds_small_supported(L) && !(d_probes && d_probes->n_probes > 0) &&
-        !(ctx->dump_step > 0 && ctx->dump_host)) {
+        !(ctx->dump_step > 0 && ctx->dump_host) && !d_state_in && !d_state_out) {
       e = launch_tds_small(L, (const int32_t *)d_bounds, d_tubes, d_glottis, d_audio, d_flow, d_status, stream);
       release();
       if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_tds_small");
@@ -897,7 +898,7 @@ int tds_run_device(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, int 
     const int nw = (c0 + wave_ctas >= ctas) ? n_tracts - t0 : wave_ctas * lpc;
     e = launch_tds(L, t0, nw, (const int32_t *)d_bounds, d_tubes, d_glottis, d_seeds, d_audio, d_flow, d_status,
                    c0 == 0 ? (double *)d_dump : nullptr, ctx->dump_step, d_nzc, d_runs, (const uint32_t *)d_off, run_items, d_probes,
-                   single ? d_progress : nullptr, single ? progress_every : 0, stream);
+                   single ? d_progress : nullptr, single ? progress_every : 0, d_state_in, d_state_out, stream);
     if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "launch_tds"); }
     ctx->launches += per_cta ? 2 : 1;
   }
@@ -1076,6 +1077,195 @@ int afs_tds_synthesize_probed(afs_ctx *ctx, const afs_tds_options *opts, int n_t
     return afs_tds_synthesize_probed(ctx, opts, n_tracts, n_frames, frame_len, tubes, glottis, fs_tds_hz, sr_factor, seeds,
                                      audio, flow, status, probes);
   }
+  return AFS_OK;
+}
+
+}  // extern "C"
+
+// ---- chunked synthesis: afs_tds_stream -------------------------------------------------------------------------------
+// A batch of TdsModel + TriangularGlottis + driver objects that live across calls, like the reference's Synthesizer
+// (one synthesizeSignalTds call per control frame, Synthesizer.cpp:515-639).  The recurrent state of every tract stays
+// in device memory between calls (two buffers: a chunk reads one and writes the other, so a failed chunk leaves the
+// stream where it was), next to the last control frame of every tract (prevTube / prevGlottisParams).
+struct afs_tds_stream {
+  afs_ctx *ctx = nullptr;
+  afs_tds_options opts;
+  int n = 0, sr_factor = 1;
+  double fs = 0.0;
+  bool primed = false;     // the first frame has been stored (Synthesizer.cpp:522-532)
+  bool has_state = false;  // at least one chunk has run
+  int cur = 0;             // which state buffer is current
+  int64_t samples = 0;     // output samples produced so far (per tract)
+  double *d_state[2] = {nullptr, nullptr};
+  afs_tube_frame *d_prev_tubes = nullptr;
+  double *d_prev_gl = nullptr;
+  uint32_t *d_seeds = nullptr;
+};
+
+namespace {
+constexpr uint64_t kStreamMagic = 0x3153445453464100ull;  // "\0AFSTDS1"
+struct StreamHeader {
+  uint64_t magic;
+  int32_t n, sr_factor, primed, has_state;
+  int64_t samples;
+  uint64_t state_words;
+  double fs;
+  afs_tds_options opts;
+};
+size_t stream_state_bytes(const afs_tds_stream *s) { return (size_t)s->n * tds_state_words() * sizeof(double); }
+size_t stream_blob_bytes(const afs_tds_stream *s) {
+  return sizeof(StreamHeader) + (size_t)s->n * (sizeof(afs_tube_frame) + AFS_NUM_GLOTTIS_CONTROL * sizeof(double)) + stream_state_bytes(s);
+}
+void stream_release(afs_tds_stream *s) {
+  cudaFree(s->d_state[0]); cudaFree(s->d_state[1]); cudaFree(s->d_prev_tubes); cudaFree(s->d_prev_gl); cudaFree(s->d_seeds);
+  delete s;
+}
+}  // namespace
+
+extern "C" {
+
+int afs_tds_stream_create(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, double fs_tds_hz, int sr_factor,
+                          const uint32_t *seeds, afs_tds_stream **out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!opts || !out || n_tracts < 1 || sr_factor < 1 || !(fs_tds_hz > 0)) return AFS_ERR_BAD_ARGUMENT;
+  if (opts->glottis_loss_option < AFS_STANDARD_ENTRANCE_LOSS || opts->glottis_loss_option > AFS_VARIABLE_ENTRANCE_LOSS ||
+      opts->reserved != 0 || opts->flow_source_section < -1 || opts->flow_source_section >= AFS_NUM_SECTIONS)
+    return AFS_ERR_BAD_ARGUMENT;
+  afs_tds_stream *s = new (std::nothrow) afs_tds_stream;
+  if (!s) return AFS_ERR_OUT_OF_MEMORY;
+  s->ctx = ctx; s->opts = *opts; s->n = n_tracts; s->sr_factor = sr_factor; s->fs = fs_tds_hz;
+  cudaError_t e = cudaMalloc((void **)&s->d_state[0], stream_state_bytes(s));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_state[1], stream_state_bytes(s));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_prev_tubes, (size_t)n_tracts * sizeof(afs_tube_frame));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_prev_gl, (size_t)n_tracts * AFS_NUM_GLOTTIS_CONTROL * sizeof(double));
+  if (e == cudaSuccess && seeds) {
+    e = cudaMalloc((void **)&s->d_seeds, (size_t)n_tracts * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_seeds, seeds, (size_t)n_tracts * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) { stream_release(s); return cuda_fail(ctx, e, "afs_tds_stream_create"); }
+  *out = s;
+  return AFS_OK;
+}
+
+int afs_tds_stream_destroy(afs_tds_stream *s) {
+  if (!s) return AFS_OK;
+  int rc = bind(s->ctx);
+  if (rc) return rc;
+  cudaStreamSynchronize(s->ctx->stream);
+  stream_release(s);
+  return AFS_OK;
+}
+
+int afs_tds_stream_reset(afs_tds_stream *s) {
+  if (!s) return AFS_ERR_BAD_ARGUMENT;
+  s->primed = false; s->has_state = false; s->samples = 0;
+  return AFS_OK;
+}
+
+int64_t afs_tds_stream_samples(const afs_tds_stream *s) { return s ? s->samples : -1; }
+
+int afs_tds_stream_synthesize(afs_tds_stream *s, int n_frames, const int32_t *frame_len, const afs_tube_frame *tubes,
+                              const double *glottis, double *audio, double *flow, uint32_t *status) {
+  if (!s) return AFS_ERR_BAD_ARGUMENT;
+  afs_ctx *ctx = s->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (n_frames < 1 || !frame_len || !tubes || !glottis) return AFS_ERR_BAD_ARGUMENT;
+  const int k0 = s->primed ? 0 : 1;  // frames that only prime
+  const int m = n_frames - k0;       // frames that produce samples
+  size_t n_out = 0;
+  for (int k = k0; k < n_frames; k++) { if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT; n_out += (size_t)frame_len[k]; }
+  if (m > 0 && !audio) return AFS_ERR_BAD_ARGUMENT;
+  const size_t n = (size_t)s->n, fsz = sizeof(afs_tube_frame), gsz = AFS_NUM_GLOTTIS_CONTROL * sizeof(double);
+  if (!s->primed) {  // prevTube = the first frame, no samples (Synthesizer.cpp:522-532)
+    CU(cudaMemcpy2DAsync(s->d_prev_tubes, fsz, tubes, (size_t)n_frames * fsz, fsz, n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(s->d_prev_gl, gsz, glottis, (size_t)n_frames * gsz, gsz, n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    s->primed = true;
+  }
+  if (m == 0) return AFS_OK;
+  // the chunk's frames on the device: [tract][prev, new 0 .. m-1]
+  const size_t ab = n * n_out * sizeof(double), fb = ab * (size_t)s->sr_factor;
+  void *d_tubes, *d_gl, *d_audio, *d_flow = nullptr, *d_status;
+  if ((rc = scratch(ctx, 0, n * (size_t)(m + 1) * fsz, &d_tubes))) return rc;
+  if ((rc = scratch(ctx, 1, n * (size_t)(m + 1) * gsz, &d_gl))) return rc;
+  if ((rc = scratch(ctx, 2, ab, &d_audio))) return rc;
+  if (flow && (rc = scratch(ctx, 3, fb, &d_flow))) return rc;
+  if ((rc = scratch(ctx, 4, n * sizeof(uint32_t), &d_status))) return rc;
+  const size_t dp_t = (size_t)(m + 1) * fsz, dp_g = (size_t)(m + 1) * gsz;
+  CU(cudaMemcpy2DAsync(d_tubes, dp_t, s->d_prev_tubes, fsz, fsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpy2DAsync(d_gl, dp_g, s->d_prev_gl, gsz, gsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpy2DAsync((unsigned char *)d_tubes + fsz, dp_t, tubes + k0, (size_t)n_frames * fsz, (size_t)m * fsz, n,
+                       cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpy2DAsync((unsigned char *)d_gl + gsz, dp_g, glottis + (size_t)k0 * AFS_NUM_GLOTTIS_CONTROL, (size_t)n_frames * gsz,
+                       (size_t)m * gsz, n, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<uint32_t> st((size_t)s->n);
+  for (;;) {
+    rc = tds_run_device(ctx, &s->opts, s->n, m + 1, frame_len + k0, (const afs_tube_frame *)d_tubes, (const double *)d_gl, s->fs,
+                        s->sr_factor, s->d_seeds, (double *)d_audio, (double *)d_flow, (uint32_t *)d_status, nullptr, ctx->stream,
+                        nullptr, 0, nullptr, s->has_state ? s->d_state[s->cur] : nullptr, s->d_state[s->cur ^ 1]);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    cudaError_t e = cudaMemcpyAsync(st.data(), d_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "afs_tds_stream_synthesize");
+    // status bit 1: the record pool of the noise pre-pass was too small -- the chunk is repeated from the same state
+    if (s->opts.generate_noise_sources && (st[0] & 2u) && ctx->run_pool_factor < 4096) { ctx->run_pool_factor *= 8; continue; }
+    break;
+  }
+  // the chunk is in: its last frame is the next prevTube, the state buffers change roles
+  CU(cudaMemcpy2DAsync(s->d_prev_tubes, fsz, (unsigned char *)d_tubes + (size_t)m * fsz, dp_t, fsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpy2DAsync(s->d_prev_gl, gsz, (unsigned char *)d_gl + (size_t)m * gsz, dp_g, gsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(audio, d_audio, ab, cudaMemcpyDeviceToHost, ctx->stream));
+  if (flow) CU(cudaMemcpyAsync(flow, d_flow, fb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (status) memcpy(status, st.data(), n * sizeof(uint32_t));
+  s->cur ^= 1; s->has_state = true; s->samples += (int64_t)n_out;
+  return AFS_OK;
+}
+
+size_t afs_tds_stream_checkpoint_bytes(const afs_tds_stream *s) { return s ? stream_blob_bytes(s) : 0; }
+
+int afs_tds_stream_save(afs_tds_stream *s, void *blob, size_t bytes) {
+  if (!s || !blob || bytes < stream_blob_bytes(s)) return AFS_ERR_BAD_ARGUMENT;
+  afs_ctx *ctx = s->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  StreamHeader h;
+  memset(&h, 0, sizeof h);
+  h.magic = kStreamMagic; h.n = s->n; h.sr_factor = s->sr_factor; h.primed = s->primed; h.has_state = s->has_state;
+  h.samples = s->samples; h.state_words = tds_state_words(); h.fs = s->fs; h.opts = s->opts;
+  unsigned char *at = (unsigned char *)blob;
+  memcpy(at, &h, sizeof h); at += sizeof h;
+  const size_t tb = (size_t)s->n * sizeof(afs_tube_frame), gb = (size_t)s->n * AFS_NUM_GLOTTIS_CONTROL * sizeof(double);
+  memset(at, 0, tb + gb + stream_state_bytes(s));
+  if (s->primed) {
+    CU(cudaMemcpyAsync(at, s->d_prev_tubes, tb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(at + tb, s->d_prev_gl, gb, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (s->has_state) CU(cudaMemcpyAsync(at + tb + gb, s->d_state[s->cur], stream_state_bytes(s), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return AFS_OK;
+}
+
+int afs_tds_stream_load(afs_tds_stream *s, const void *blob, size_t bytes) {
+  if (!s || !blob || bytes < stream_blob_bytes(s)) return AFS_ERR_BAD_ARGUMENT;
+  afs_ctx *ctx = s->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  StreamHeader h;
+  const unsigned char *at = (const unsigned char *)blob;
+  memcpy(&h, at, sizeof h); at += sizeof h;
+  // a checkpoint belongs to one batch size, rate, option set and build of the kernels
+  if (h.magic != kStreamMagic || h.n != s->n || h.sr_factor != s->sr_factor || h.fs != s->fs ||
+      h.state_words != tds_state_words() || memcmp(&h.opts, &s->opts, sizeof h.opts) != 0)
+    return AFS_ERR_BAD_ARGUMENT;
+  const size_t tb = (size_t)s->n * sizeof(afs_tube_frame), gb = (size_t)s->n * AFS_NUM_GLOTTIS_CONTROL * sizeof(double);
+  CU(cudaMemcpyAsync(s->d_prev_tubes, at, tb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s->d_prev_gl, at + tb, gb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s->d_state[s->cur], at + tb + gb, stream_state_bytes(s), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  s->primed = h.primed != 0; s->has_state = h.has_state != 0; s->samples = h.samples;
   return AFS_OK;
 }
 

@@ -62,7 +62,9 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
                        uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const void *d_runs,
                        const uint32_t *d_run_ctl, int run_items, const afs_tds_probes *d_probes, unsigned int *d_progress,
-                       int progress_every, cudaStream_t stream);
+                       int progress_every, const double *d_state_in, double *d_state_out, cudaStream_t stream);
+// chunked synthesis: doubles of recurrent state per tract (d_state_in: null = a fresh model; d_state_out: null = dropped)
+size_t tds_state_words();
 // noise pre-pass in runs mode (control frames far apart)
 bool tds_noise_runs_mode(const TdsLaunch &L);
 size_t tds_noise_run_bytes();

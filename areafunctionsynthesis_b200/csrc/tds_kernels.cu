@@ -1757,6 +1757,10 @@ struct KArgs {
   // `progress_every` steps (nullable): lets the host copy finished time slices while the kernel runs
   unsigned int *progress;
   int progress_every;
+  // chunked synthesis (OPT kernels only): recurrent state of every tract, ST_WORDS doubles each (see "state in / state
+  // out" below); state_in null = a fresh model, state_out null = the state is dropped at the end
+  const double *state_in;
+  double *state_out;
 };
 
 
@@ -1791,6 +1795,90 @@ __device__ __forceinline__ void nzc_fetch_store(TdsSmem &S, const int lane, cons
     S.nzc_c[k][0][lane] = R.f[k]; S.nzc_c[k][1][lane] = 0.0; S.nzc_c[k][2][lane] = 1.0; S.nzc_c[k][3][lane] = 0.0;
   }
 }
+
+// ---- state in / state out ---------------------------------------------------------
+// Everything that survives a step (pressures, wall currents, branch currents and their rates, noise
+// sources and random() stream, glottis displacements, the filters of the driver) lives in the registers of the warp
+// that owns it and in the per-tract rows of shared memory.  A chunked utterance (afs_tds_stream_*) leaves the time loop
+// after the update of its last step, writes both to global memory -- one opaque block of ST_WORDS doubles per tract,
+// independent of how the tracts are packed into CTAs -- and the next chunk starts from it: its iteration 0 assembles
+// rows from that state exactly as iteration T of an unchunked run would.
+constexpr size_t ST_U32_AT = offsetof(TdsSmem, rng), ST_D1_AT = offsetof(TdsSmem, nzc_c), ST_END_AT = offsetof(TdsSmem, srec);
+static_assert(ST_U32_AT % (8 * LANES) == 0 && (ST_D1_AT - ST_U32_AT) % (4 * LANES) == 0 && (ST_END_AT - ST_D1_AT) % (8 * LANES) == 0 &&
+              ST_D1_AT % 8 == 0, "per-tract rows of TdsSmem");
+constexpr int ST_ROWS_A = (int)(ST_U32_AT / (8 * LANES));               // [row][lane] doubles in front of the random() ring
+constexpr int ST_ROWS_U = (int)((ST_D1_AT - ST_U32_AT) / (4 * LANES));  // 32-bit rows: random() ring, ring of sums, constriction slots
+constexpr int ST_ROWS_B = (int)((ST_END_AT - ST_D1_AT) / (8 * LANES));  // doubles behind them
+constexpr int ST_REG_WORDS = 56;                                        // registers of one warp role (the largest: X2)
+constexpr int ST_PARITY_AT = 33;                                       // where X1 keeps the parity of the chunk's step count
+constexpr int ST_SMEM_AT = NW * ST_REG_WORDS;
+constexpr int ST_WORDS = ST_SMEM_AT + ST_ROWS_A + ST_ROWS_B + (ST_ROWS_U + 1) / 2;
+
+template <bool LOAD>
+__device__ __forceinline__ void st_word(double *w, int &k, double &v) {
+  if (LOAD) v = w[k]; else w[k] = v;
+  k++;
+}
+template <bool LOAD>
+__device__ __forceinline__ void st_int(double *w, int &k, int &v) {
+  if (LOAD) v = (int)w[k]; else w[k] = (double)v;
+  k++;
+}
+template <bool LOAD, int N>
+__device__ __forceinline__ void st_arr(double *w, int &k, double (&a)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; i++) st_word<LOAD>(w, k, a[i]);
+}
+template <bool LOAD>
+__device__ __forceinline__ void st_dregs(double *w, DRegs &r) {
+  int k = 0;
+  st_arr<LOAD>(w, k, r.p); st_arr<LOAD>(w, k, r.pr); st_arr<LOAD>(w, k, r.c); st_arr<LOAD>(w, k, r.x); st_arr<LOAD>(w, k, r.y); st_arr<LOAD>(w, k, r.h);
+  st_word<LOAD>(w, k, r.L0); st_word<LOAD>(w, k, r.R0); st_word<LOAD>(w, k, r.I0); st_word<LOAD>(w, k, r.D0); st_word<LOAD>(w, k, r.gbf);
+}
+template <bool LOAD>
+__device__ __forceinline__ void st_sregs(double *w, SRegs &r, unsigned long long &live) {
+  int k = 0;
+  st_arr<LOAD>(w, k, r.p); st_arr<LOAD>(w, k, r.pr); st_arr<LOAD>(w, k, r.c); st_arr<LOAD>(w, k, r.x);
+  st_arr<LOAD>(w, k, r.lp); st_arr<LOAD>(w, k, r.lpr); st_arr<LOAD>(w, k, r.lc); st_arr<LOAD>(w, k, r.lx);
+  st_word<LOAD>(w, k, r.D0); st_word<LOAD>(w, k, r.w84); st_word<LOAD>(w, k, r.e28); st_word<LOAD>(w, k, r.g28);
+  double lv = __longlong_as_double((long long)live);  // (warp F: the noise sources whose amplitude is not zero)
+  st_word<LOAD>(w, k, lv);
+  if (LOAD) live = (unsigned long long)__double_as_longlong(lv);
+}
+template <bool LOAD>
+__device__ __forceinline__ void st_x1regs(double *w, X1Regs &r, int &parity) {
+  int k = 0;
+  st_word<LOAD>(w, k, r.G.x0); st_word<LOAD>(w, k, r.G.x1); st_word<LOAD>(w, k, r.G.xp0); st_word<LOAD>(w, k, r.G.xp1);
+  st_word<LOAD>(w, k, r.GD.cordLength); st_word<LOAD>(w, k, r.GD.th0); st_word<LOAD>(w, k, r.GD.th1); st_word<LOAD>(w, k, r.GD.ol0);
+  st_word<LOAD>(w, k, r.GD.ol1); st_word<LOAD>(w, k, r.GD.cl0); st_word<LOAD>(w, k, r.GD.cl1); st_word<LOAD>(w, k, r.GD.mw0);
+  st_word<LOAD>(w, k, r.GD.mw1); st_word<LOAD>(w, k, r.GD.mz0); st_word<LOAD>(w, k, r.GD.mz1); st_word<LOAD>(w, k, r.GD.Q);
+  st_arr<LOAD>(w, k, r.toneS); st_arr<LOAD>(w, k, r.chebS); st_arr<LOAD>(w, k, r.pend);
+  st_word<LOAD>(w, k, r.prevFlow);
+  st_int<LOAD>(w, k, parity);  // parity of the chunk's step count: which half of the step-parity buffers is current
+}
+template <bool LOAD>
+__device__ __forceinline__ void st_x2regs(double *w, RadRegs &rr, OptRegs &o, NoiseRegs &nr) {
+  int k = 0;
+  st_arr<LOAD>(w, k, rr.c); st_arr<LOAD>(w, k, rr.u); st_arr<LOAD>(w, k, rr.keep[0]); st_arr<LOAD>(w, k, rr.keep[1]);
+  st_arr<LOAD>(w, k, o.x1); st_arr<LOAD>(w, k, o.y1); st_arr<LOAD>(w, k, o.x2); st_arr<LOAD>(w, k, o.y2); st_arr<LOAD>(w, k, o.xg); st_arr<LOAD>(w, k, o.yg);
+  st_int<LOAD>(w, k, nr.ph); st_int<LOAD>(w, k, nr.head); st_int<LOAD>(w, k, nr.free); st_int<LOAD>(w, k, nr.cap);
+  st_word<LOAD>(w, k, nr.lips); st_word<LOAD>(w, k, nr.nm93); st_word<LOAD>(w, k, nr.nm94); st_word<LOAD>(w, k, nr.asp); st_word<LOAD>(w, k, nr.gain);
+}
+static_assert(6 * KD + 5 <= ST_REG_WORDS && 4 * KS + 8 + 4 + 1 <= ST_REG_WORDS && 4 + 12 + 16 + 1 + 1 <= ST_REG_WORDS &&
+              8 + 14 + 24 + 4 + 5 <= ST_REG_WORDS, "ST_REG_WORDS");
+// The per-tract rows of shared memory (all warps of the CTA; `blk`: the tract's block).  Saving: active lanes only.
+template <bool LOAD>
+__device__ __noinline__ void st_smem(TdsSmem &S, double *blk, const int lane, const int warp, const bool on) {
+  if (!on) return;
+  double *d0 = reinterpret_cast<double *>(&S), *d1 = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(&S) + ST_D1_AT);
+  uint32_t *u = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(&S) + ST_U32_AT);
+  double *ga = blk + ST_SMEM_AT, *gb = ga + ST_ROWS_A;
+  uint32_t *gu = reinterpret_cast<uint32_t *>(gb + ST_ROWS_B);
+  for (int r = warp; r < ST_ROWS_A; r += NW) { if (LOAD) d0[r * LANES + lane] = ga[r]; else ga[r] = d0[r * LANES + lane]; }
+  for (int r = warp; r < ST_ROWS_B; r += NW) { if (LOAD) d1[r * LANES + lane] = gb[r]; else gb[r] = d1[r * LANES + lane]; }
+  for (int r = warp; r < ST_ROWS_U; r += NW) { if (LOAD) u[r * LANES + lane] = gu[r]; else gu[r] = u[r * LANES + lane]; }
+}
+
 
 #ifdef AFS_TDS_TIMING
 #define AFS_TICK(k) do { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } while (0)
@@ -1859,10 +1947,18 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     sst.D0 = 0.0; sst.w84 = sst.e28 = sst.g28 = 0.0;
     swarp_build(P, S, lane, warp);
   }
+  // chunked synthesis: this chunk continues from the state the last one left (OPT kernels; see "state in / state out")
+  const bool resume = OPT && A.state_in != nullptr;
+  double *st_in = resume ? const_cast<double *>(A.state_in) + (size_t)tract * ST_WORDS + warp * ST_REG_WORDS : nullptr;
+  int st_parity = 0;
   if (ROLE == 3) {
 #pragma unroll
     for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; orr.x1[j] = orr.y1[j] = orr.x2[j] = orr.y2[j] = orr.xg[j] = orr.yg[j] = 0.0; }
-    if (NOISE) {
+    if (OPT) {
+#pragma unroll
+      for (int j = 0; j < 7; j++) rr.keep[0][j] = rr.keep[1][j] = 0.0;
+    }
+    if (NOISE && !resume) {
       rng_seed(S, lane, A.seeds ? A.seeds[tract] : 1u, nr.ph);
       nr.cap = nr.free = NZ_RING;
       nz_refill(S, lane, nr, NZ_RING);  // (42 sums; the ring is never emptier than that when a step begins)
@@ -1875,6 +1971,20 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
 #pragma unroll
     for (int i = 0; i < 8; i++) xr.chebS[i] = 0.0;
     xr.prevFlow = 0.0;
+  }
+  if (OPT && resume) {
+    if (ROLE == 0) st_dregs<true>(st_in, dst);
+    if (ROLE == 1) st_sregs<true>(st_in, sst, nz_live);
+    if (ROLE == 2) {
+      st_x1regs<true>(st_in, xr, st_parity);
+      emit_update(P, xr);  // (the last sample of the previous chunk: its filter states were left for the next pass A)
+    }
+    if (ROLE == 3) {
+      st_x2regs<true>(st_in, rr, orr, nr);
+      // the history parts X2 prepared for the step that is now step 0 sit in the half of the previous chunk's parity
+      const int par = (int)A.state_in[(size_t)tract * ST_WORDS + W_X1 * ST_REG_WORDS + ST_PARITY_AT];
+      if (par) { S.tvh[0][lane] = S.tvh[1][lane]; S.kenth[0][lane] = S.kenth[1][lane]; }
+    }
   }
   cta_sync();  // static boundary records / pivots visible
   if (warp == W_T0) reduced_constants(S, lane);
@@ -1901,8 +2011,13 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     }
     if (ROLE == 2) {  // glottis geometry of step 0
       double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
-      for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
-      glottis_geometry(P, ctl, xr.G, len, ar, xr.GD);
+      if (OPT && resume) {  // ... is what the last step of the previous chunk prepared (same control frame, ratio 1)
+        len[0] = S.glLen[st_parity][0][lane]; len[1] = S.glLen[st_parity][1][lane];
+        ar[0] = S.glArea[st_parity][0][lane]; ar[1] = S.glArea[st_parity][1][lane];
+      } else {
+        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++) ctl[c] = S.gctl[0][c][lane];
+        glottis_geometry(P, ctl, xr.G, len, ar, xr.GD);
+      }
       if (NOISE) {
         double fa, fc;
         nz_factors(ar[1], 1.0, fa, fc);
@@ -2118,6 +2233,17 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     A.dump[336 + blockIdx.x] = (double)all;
   }
 #endif
+  if (OPT && A.state_out && T > 0) {
+    // (shared memory: nothing is written behind the barrier the loop was left at)
+    double *blk = A.state_out + (size_t)tract * ST_WORDS, *st_out = blk + warp * ST_REG_WORDS;
+    if (active) {
+      if (ROLE == 0) st_dregs<false>(st_out, dst);
+      if (ROLE == 1) st_sregs<false>(st_out, sst, nz_live);
+      if (ROLE == 2) { st_parity = T & 1; st_x1regs<false>(st_out, xr, st_parity); }
+      if (ROLE == 3) st_x2regs<false>(st_out, rr, orr, nr);
+    }
+    st_smem<false>(S, blk, lane, warp, active);
+  }
   if (ROLE == 2 && NOISE && A.run_ctl && A.run_ctl[1]) bad |= 2u;  // the noise pre-pass ran out of record space
   if (ROLE == 2 && active && A.status) A.status[tract] = bad;
 }
@@ -2190,6 +2316,11 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
     S.tvflow[lane] = 0.0;
   }
   __syncthreads();
+  if (OPT && A.state_in) {  // chunked synthesis: the per-tract rows as the previous chunk left them
+    const int tr = blockIdx.x * P.lanes_per_cta + lane;
+    st_smem<true>(S, const_cast<double *>(A.state_in) + (size_t)(tr < P.n_tracts ? tr : P.n_tracts - 1) * ST_WORDS, lane, warp, true);
+    __syncthreads();
+  }
 
   switch (warp) {
     case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
@@ -3135,7 +3266,7 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
                        const double *d_glottis, const uint32_t *d_seeds, double *d_audio, double *d_flow,
                        uint32_t *d_status, double *d_dump, int dump_step, void *d_nzc, const void *d_runs,
                        const uint32_t *d_run_ctl, int run_items, const afs_tds_probes *probes, unsigned int *d_progress,
-                       int progress_every, cudaStream_t stream) {
+                       int progress_every, const double *d_state_in, double *d_state_out, cudaStream_t stream) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);
   P.dump_step = dump_step;
@@ -3150,7 +3281,7 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
   }
   static_assert(sizeof(TdsSmem) <= 227 * 1024, "TdsSmem exceeds the 227 KB a CTA can have on sm_100a");
   // non-default options, a flow source, taps: separate instantiations, like the noise sources
-  const bool opt = P.transvelar || P.var_loss || P.fsrc_sec >= 0 || P.n_probes > 0;
+  const bool opt = P.transvelar || P.var_loss || P.fsrc_sec >= 0 || P.n_probes > 0 || d_state_in || d_state_out;
   auto kernel = P.noise ? (opt ? tds_batch_kernel<true, true> : tds_batch_kernel<true, false>)
                         : (opt ? tds_batch_kernel<false, true> : tds_batch_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -3170,6 +3301,8 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
   A.seeds = d_seeds ? d_seeds + tract0 : nullptr;
   A.progress = progress_every > 0 ? d_progress : nullptr;
   A.progress_every = progress_every;
+  A.state_in = d_state_in ? d_state_in + (size_t)tract0 * ST_WORDS : nullptr;
+  A.state_out = d_state_out ? d_state_out + (size_t)tract0 * ST_WORDS : nullptr;
   if (P.n_probes > 0) {
     const size_t off = (size_t)tract0 * P.n_probes * (size_t)P.total_steps;
     A.tap_p = probes->pressure_dPa ? probes->pressure_dPa + off : nullptr;
@@ -3197,6 +3330,7 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
 }
 
 size_t tds_smem_bytes() { return sizeof(TdsSmem); }
+size_t tds_state_words() { return (size_t)ST_WORDS; }
 int tds_total_steps(const TdsLaunch &L) {
   TdsParams P;
   memcpy(&P, L.params.data(), sizeof P);

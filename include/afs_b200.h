@@ -436,6 +436,44 @@ int afs_tds_synthesize_probed_device(afs_ctx *ctx, const afs_tds_options *opts, 
                                      double fs_tds_hz, int sr_factor, const uint32_t *d_seeds, double *d_audio,
                                      double *d_flow, uint32_t *d_status, const afs_tds_probes *d_probes, void *stream);
 
+/*
+ * Chunked synthesis: a batch of utterances whose models live ACROSS calls, the way the reference's Synthesizer is
+ * used (Synthesizer::synthesizeSignalTds is called once per control frame and continues from the state the TdsModel,
+ * the TriangularGlottis and the driver -- prevTube, prevGlottisParams, the output filter, the last flow sample -- were
+ * left in, Synthesizer.cpp:515-639; SURVEY.md section 5 "checkpoint / resume": state in / state out per tract).
+ * The recurrent state of every tract (pressures, currents, wall currents and their rates, noise sources and the
+ * tract's random() stream, glottis displacements, filters: ~15 KB) stays in device memory between calls; utterances
+ * of any length are synthesised piece by piece in bounded memory, and the audio of a chunked utterance equals the
+ * audio of the same frames given to afs_tds_synthesize in one call.
+ *   afs_tds_stream_create      n_tracts fresh models (`new TdsModel`, `new TriangularGlottis`, Synthesizer::init);
+ *                              seeds nullable, as in afs_tds_synthesize (used by the first chunk only).
+ *   afs_tds_stream_synthesize  n_frames >= 1 further control frames per tract, tubes [n_tracts][n_frames], glottis
+ *                              [n_tracts][n_frames][6]: frame k is one reference call synthesizeSignalTds(tube_k,
+ *                              glottis_k, frame_len[k], out) -- frame_len[k] output samples interpolated from the
+ *                              PREVIOUS frame (of this call or of the last one) to frame k.  Like the reference, the
+ *                              very first frame of a fresh stream only primes (its frame_len is ignored, no samples).
+ *                              audio [n_tracts][n_out], n_out = sum of the frame_len that produced samples; flow
+ *                              (nullable) [n_tracts][n_out * sr_factor]; status (nullable) as in afs_tds_synthesize.
+ *                              A call that fails leaves the stream in the state it had before the call.
+ *   afs_tds_stream_reset       TdsModel::resetMotion + a driver that has not been primed.
+ *   afs_tds_stream_samples     output samples per tract produced so far.
+ *   afs_tds_stream_save/load   checkpoint / resume: the whole stream (state, last frames, counters) as one host blob of
+ *                              afs_tds_stream_checkpoint_bytes bytes; load accepts a blob written by a stream of the
+ *                              same batch size, rates and options (else AFS_ERR_BAD_ARGUMENT).
+ * A stream belongs to its context (same threading rule); destroy it before the context.
+ */
+typedef struct afs_tds_stream afs_tds_stream;
+int afs_tds_stream_create(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, double fs_tds_hz, int sr_factor,
+                          const uint32_t *seeds, afs_tds_stream **stream);
+int afs_tds_stream_destroy(afs_tds_stream *stream);
+int afs_tds_stream_reset(afs_tds_stream *stream);
+int64_t afs_tds_stream_samples(const afs_tds_stream *stream);
+int afs_tds_stream_synthesize(afs_tds_stream *stream, int n_frames, const int32_t *frame_len, const afs_tube_frame *tubes,
+                              const double *glottis, double *audio, double *flow, uint32_t *status);
+size_t afs_tds_stream_checkpoint_bytes(const afs_tds_stream *stream);
+int afs_tds_stream_save(afs_tds_stream *stream, void *blob, size_t bytes);
+int afs_tds_stream_load(afs_tds_stream *stream, const void *blob, size_t bytes);
+
 /* Diagnostics: the next afs_tds_synthesize* calls copy the recurrent state of
  * tract 0 right after simulation step `step` (1-based; 0 disables) into
  * host_out473: [0..92] section pressure, [93..185] pressure rate, [186..278]

@@ -237,7 +237,8 @@ inline std::vector<double> playTargetSequences(Device &dev, const afs_tds_option
 
 // Batched replacement of the Synthesizer's TDS driver: the caller queues control frames exactly like successive
 // calls of Synthesizer::synthesizeSignalTds(newTube, newGlottisParams, numNewSamples, out) (Synthesizer.cpp:515-639)
-// -- the first call primes -- and flush() runs the whole batch of utterances in one kernel launch.
+// -- the first call primes -- and flush() runs the whole batch of utterances in one kernel launch; flushAndContinue()
+// does the same and keeps the models alive for the frames that follow (utterances of any length, piece by piece).
 class TdsSynthesizer {
  public:
   afs_tds_options options;  // TdsModel::options + TriangularGlottis static parameters
@@ -250,7 +251,15 @@ class TdsSynthesizer {
   TdsSynthesizer(Device &dev, int numUtterances) : dev_(&dev), n_(numUtterances) { afs_tds_options_default(&options); }
   // the same over several devices (contiguous shards of the utterances)
   TdsSynthesizer(DeviceGroup &group, int numUtterances) : group_(&group), n_(numUtterances) { afs_tds_options_default(&options); }
-  void resetMotion() { tubes_.clear(); glottis_.clear(); frameLen_.clear(); frames_ = 0; }
+  ~TdsSynthesizer() { if (stream_) afs_tds_stream_destroy(stream_); }
+  TdsSynthesizer(const TdsSynthesizer &) = delete;
+  TdsSynthesizer &operator=(const TdsSynthesizer &) = delete;
+  // TdsModel::resetMotion + a driver that has not seen a tube yet (Synthesizer::reset)
+  void resetMotion() {
+    clearQueue();
+    continuing_ = false;
+    if (stream_) afs_tds_stream_reset(stream_);
+  }
   // TdsModel::setFlowSource(flow_cm3_s, section) (TdsModel.cpp:629-633); section -1 switches it off.
   void setFlowSource(double flow_cm3_s, int section) { options.flow_source_cm3_s = flow_cm3_s; options.flow_source_section = section; }
   // Taps for the next flush(): TdsModel::getSectionPressure / getSectionFlow (TdsModel.cpp:1715-1734) of these tube
@@ -265,23 +274,42 @@ class TdsSynthesizer {
   void synthesizeSignalTds(const Tube *newTubes, const double *newGlottisParams, int numNewSamples) {
     for (int b = 0; b < n_; b++) tubes_.push_back(newTubes[b].frame);
     glottis_.insert(glottis_.end(), newGlottisParams, newGlottisParams + (size_t)n_ * AFS_NUM_GLOTTIS_CONTROL);
-    if (frames_ > 0) frameLen_.push_back(numNewSamples < 1 ? 1 : numNewSamples);
+    if (frames_ > 0 || continuing_) frameLen_.push_back(numNewSamples < 1 ? 1 : numNewSamples);
     frames_++;
+  }
+  // Runs the queued frames and KEEPS the models: the next synthesizeSignalTds calls continue from the state and the
+  // tube these frames ended in, exactly like further calls on the reference's Synthesizer object (afs_tds_stream_*;
+  // single device; `options`, the rates and the number of utterances are fixed by the first call).  The audio of an
+  // utterance synthesised in pieces equals the audio of one flush() of all its frames.
+  void flushAndContinue(std::vector<double> *audio, std::vector<double> *flow = nullptr, std::vector<uint32_t> *status = nullptr) {
+    if (!dev_) throw Error(AFS_ERR_UNSUPPORTED, "chunked synthesis is a single-device feature");
+    if (frames_ < 1) throw Error(AFS_ERR_BAD_ARGUMENT, "no control frames queued");
+    if (!stream_) check(afs_tds_stream_create(dev_->ctx(), &options, n_, samplingRate * tdsSrFactor, tdsSrFactor, nullptr, &stream_), dev_->ctx());
+    std::vector<afs_tube_frame> t;
+    std::vector<double> g;
+    transposeQueue(&t, &g);
+    std::vector<int32_t> len;
+    if (!continuing_) len.push_back(0);  // the priming frame
+    len.insert(len.end(), frameLen_.begin(), frameLen_.end());
+    size_t n_out = 0;
+    for (int v : frameLen_) n_out += (size_t)v;
+    audio->assign((size_t)n_ * n_out, 0.0);
+    if (flow) flow->assign((size_t)n_ * n_out * tdsSrFactor, 0.0);
+    if (status) status->assign((size_t)n_, 0u);
+    check(afs_tds_stream_synthesize(stream_, frames_, len.data(), t.data(), g.data(), audio->data(), flow ? flow->data() : nullptr,
+                                    status ? status->data() : nullptr), dev_->ctx());
+    clearQueue();
+    continuing_ = true;
   }
   // Runs the queued frames; audio[n][sum(numNewSamples)] in [-1, 1]; flow (optional) per simulation step.
   void flush(std::vector<double> *audio, std::vector<double> *flow = nullptr, std::vector<uint32_t> *status = nullptr) {
     if (frames_ < 2) throw Error(AFS_ERR_BAD_ARGUMENT, "need at least two control frames");
     size_t n_out = 0;
     for (int v : frameLen_) n_out += (size_t)v;
-    // queue order is frame-major; the ABI wants [utterance][frame]
-    std::vector<afs_tube_frame> t((size_t)n_ * frames_);
-    std::vector<double> g((size_t)n_ * frames_ * AFS_NUM_GLOTTIS_CONTROL);
-    for (int k = 0; k < frames_; k++)
-      for (int b = 0; b < n_; b++) {
-        t[(size_t)b * frames_ + k] = tubes_[(size_t)k * n_ + b];
-        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
-          g[((size_t)b * frames_ + k) * AFS_NUM_GLOTTIS_CONTROL + c] = glottis_[((size_t)k * n_ + b) * AFS_NUM_GLOTTIS_CONTROL + c];
-      }
+    if (continuing_) throw Error(AFS_ERR_BAD_ARGUMENT, "models kept by flushAndContinue: go on with it, or resetMotion() first");
+    std::vector<afs_tube_frame> t;
+    std::vector<double> g;
+    transposeQueue(&t, &g);
     audio->assign((size_t)n_ * n_out, 0.0);
     if (flow) flow->assign((size_t)n_ * n_out * tdsSrFactor, 0.0);
     if (status) status->assign((size_t)n_, 0u);
@@ -303,10 +331,24 @@ class TdsSynthesizer {
                                       flow ? flow->data() : nullptr, status ? status->data() : nullptr,
                                       pr.n_probes ? &pr : nullptr), dev_->ctx());
     }
-    resetMotion();
+    clearQueue();
   }
 
  private:
+  void clearQueue() { tubes_.clear(); glottis_.clear(); frameLen_.clear(); frames_ = 0; }
+  // queue order is frame-major; the ABI wants [utterance][frame]
+  void transposeQueue(std::vector<afs_tube_frame> *t, std::vector<double> *g) const {
+    t->resize((size_t)n_ * frames_);
+    g->resize((size_t)n_ * frames_ * AFS_NUM_GLOTTIS_CONTROL);
+    for (int k = 0; k < frames_; k++)
+      for (int b = 0; b < n_; b++) {
+        (*t)[(size_t)b * frames_ + k] = tubes_[(size_t)k * n_ + b];
+        for (int c = 0; c < AFS_NUM_GLOTTIS_CONTROL; c++)
+          (*g)[((size_t)b * frames_ + k) * AFS_NUM_GLOTTIS_CONTROL + c] = glottis_[((size_t)k * n_ + b) * AFS_NUM_GLOTTIS_CONTROL + c];
+      }
+  }
+  afs_tds_stream *stream_ = nullptr;
+  bool continuing_ = false;  // the models carry state and a previous tube (flushAndContinue)
   Device *dev_ = nullptr;
   DeviceGroup *group_ = nullptr;
   std::vector<int> probeSections_;

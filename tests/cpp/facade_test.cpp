@@ -76,6 +76,20 @@ int main() {
     const std::vector<double> mf = tl.getMeanFlow(8000.0);
     const std::vector<int32_t> mc = tl.getMostConstrictedSection();
     std::printf("meanflow %.17g %d\n", mf[0], mc[0]);
+    // --- the same utterance in two pieces on models that live across calls (afs_tds_stream) ---
+    {
+      afs::TdsSynthesizer chunked(dev, 2);
+      std::vector<double> a1, a2;
+      chunked.synthesizeSignalTds(tubes, g, 0);
+      chunked.synthesizeSignalTds(tubes, g, 551);
+      chunked.flushAndContinue(&a1);
+      chunked.synthesizeSignalTds(tubes, g, 551);
+      chunked.flushAndContinue(&a2);
+      double ce = 0;
+      for (double v : a1) ce += v * v;
+      for (double v : a2) ce += v * v;
+      std::printf("stream %zu %.12e\n", a1.size() + a2.size(), ce);
+    }
     // --- the same utterances over every visible device (afs_group) ---
     afs::DeviceGroup grp;
     afs::TdsSynthesizer gsyn(grp, 2);

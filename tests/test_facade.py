@@ -70,6 +70,9 @@ def test_facade_matches_ctypes_path(ctx, shapes):
     mf, mc = ctx.tl_mean_flow(fr[:1], 8000.0)
     assert float(lines["meanflow"][0]) == mf[0] and int(lines["meanflow"][1]) == mc[0]
     a3, _, _ = ctx.tds_synthesize(np.stack([fr, fr], axis=1), gl, [1102], 44100.0, 2)  # default options, default seed
+    # two pieces of 551 samples on models kept across calls == one piece of 1102 (constant frames)
+    assert int(lines["stream"][0]) == a3.size
+    assert abs(float(lines["stream"][1]) - float((a3 ** 2).sum())) <= 1e-9 * float((a3 ** 2).sum())
     import torch
     assert int(lines["group"][0]) == torch.cuda.device_count() and int(lines["group"][1]) == a3.size
     assert abs(float(lines["group"][2]) - float((a3 ** 2).sum())) <= 1e-12 * float((a3 ** 2).sum())
