@@ -113,6 +113,10 @@ def load_library():
     lib.afs_tds_stream_checkpoint_bytes.restype = C.c_size_t
     lib.afs_tds_stream_save.argtypes = [vp, vp, C.c_size_t]
     lib.afs_tds_stream_load.argtypes = [vp, vp, C.c_size_t]
+    lib.afs_group_tds_stream_create.argtypes = [vp, vp, i32, dbl, i32, vp, C.POINTER(C.c_void_p)]
+    lib.afs_group_tds_stream_destroy.argtypes = [vp]
+    lib.afs_group_tds_stream_reset.argtypes = [vp]
+    lib.afs_group_tds_stream_synthesize.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
     lib.afs_debug_set.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.afs_group_create.argtypes = [C.POINTER(C.c_void_p), vp, i32]
@@ -323,17 +327,22 @@ class TdsStream:
     """afs_tds_stream: a batch of utterances whose models live across calls (chunked synthesis, checkpoint / resume)."""
 
     def __init__(self, ctx, n_tracts, fs_tds_hz=44100.0, sr_factor=2, opts=None, seeds=None):
+        """ctx: a Context, or a Group (afs_group_tds_stream_*: every device keeps the models of its shard)."""
         self.ctx, self.lib, self.n, self.sr_factor = ctx, ctx.lib, int(n_tracts), int(sr_factor)
         self.opts = opts or tds_options_default()
         s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32)
         self.h = C.c_void_p()
-        _check(self.lib, self.lib.afs_tds_stream_create(ctx.h, C.byref(self.opts), self.n, float(fs_tds_hz), self.sr_factor,
-                                                        _ptr(s), C.byref(self.h)), ctx.h)
+        self._group = isinstance(ctx, Group)
+        self._err = None if self._group else ctx.h
+        pre = "afs_group_tds_stream_" if self._group else "afs_tds_stream_"
+        self._f = {k: getattr(self.lib, pre + k) for k in ("create", "destroy", "reset", "synthesize")}
+        _check(self.lib, self._f["create"](ctx.h, C.byref(self.opts), self.n, float(fs_tds_hz), self.sr_factor,
+                                           _ptr(s), C.byref(self.h)), self._err)
         self._primed = False
 
     def close(self):
         if self.h:
-            self.lib.afs_tds_stream_destroy(self.h)
+            self._f["destroy"](self.h)
             self.h = None
 
     def __del__(self):
@@ -343,7 +352,7 @@ class TdsStream:
             pass
 
     def reset(self):
-        _check(self.lib, self.lib.afs_tds_stream_reset(self.h), self.ctx.h)
+        _check(self.lib, self._f["reset"](self.h), self._err)
         self._primed = False
 
     @property
@@ -363,8 +372,8 @@ class TdsStream:
         audio = np.empty((B, n_out))
         flow = np.empty((B, n_out * self.sr_factor)) if want_flow else None
         status = np.zeros(B, dtype=np.uint32)
-        _check(self.lib, self.lib.afs_tds_stream_synthesize(self.h, F, _ptr(frame_len), _ptr(frames), _ptr(glottis), _ptr(audio),
-                                                            _ptr(flow), _ptr(status)), self.ctx.h)
+        _check(self.lib, self._f["synthesize"](self.h, F, _ptr(frame_len), _ptr(frames), _ptr(glottis), _ptr(audio),
+                                               _ptr(flow), _ptr(status)), self._err)
         self._primed = True
         return audio, flow, status
 

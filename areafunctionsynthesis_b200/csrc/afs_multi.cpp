@@ -118,6 +118,63 @@ int afs_group_tl_sweep(afs_group *g, const afs_tl_options *opts, int n_tubes, co
   });
 }
 
+// ---- chunked synthesis over the group: one afs_tds_stream per device, each holding its shard's models ----------------
+struct afs_group_tds_stream {
+  afs_group *g = nullptr;
+  int n = 0, sr_factor = 1;
+  bool primed = false;
+  std::vector<afs_tds_stream *> part;  // by device; null where the shard is empty
+};
+
+int afs_group_tds_stream_create(afs_group *g, const afs_tds_options *opts, int n_tracts, double fs_tds_hz, int sr_factor,
+                                const uint32_t *seeds, afs_group_tds_stream **out) {
+  if (!g || g->ctx.empty()) return AFS_ERR_BAD_CONTEXT;
+  if (!out || !opts || n_tracts < 1 || sr_factor < 1) return AFS_ERR_BAD_ARGUMENT;
+  afs_group_tds_stream *s = new (std::nothrow) afs_group_tds_stream();
+  if (!s) return AFS_ERR_OUT_OF_MEMORY;
+  s->g = g; s->n = n_tracts; s->sr_factor = sr_factor;
+  s->part.assign(g->ctx.size(), nullptr);
+  const int rc = for_each_shard(g, n_tracts, [&](int r, int lo, int hi) {
+    return afs_tds_stream_create(g->ctx[(size_t)r], opts, hi - lo, fs_tds_hz, sr_factor, seeds ? seeds + lo : nullptr, &s->part[(size_t)r]);
+  });
+  if (rc != AFS_OK) { afs_group_tds_stream_destroy(s); return rc; }
+  *out = s;
+  return AFS_OK;
+}
+
+int afs_group_tds_stream_destroy(afs_group_tds_stream *s) {
+  if (!s) return AFS_OK;
+  for (afs_tds_stream *p : s->part) afs_tds_stream_destroy(p);
+  delete s;
+  return AFS_OK;
+}
+
+int afs_group_tds_stream_reset(afs_group_tds_stream *s) {
+  if (!s) return AFS_ERR_BAD_ARGUMENT;
+  for (afs_tds_stream *p : s->part) if (p) afs_tds_stream_reset(p);
+  s->primed = false;
+  return AFS_OK;
+}
+
+int afs_group_tds_stream_synthesize(afs_group_tds_stream *s, int n_frames, const int32_t *frame_len, const afs_tube_frame *tubes,
+                                    const double *glottis, double *audio, double *flow, uint32_t *status) {
+  if (!s) return AFS_ERR_BAD_ARGUMENT;
+  if (n_frames < 1 || !frame_len || !tubes || !glottis) return AFS_ERR_BAD_ARGUMENT;
+  size_t n_out = 0;
+  for (int k = s->primed ? 0 : 1; k < n_frames; k++) { if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT; n_out += (size_t)frame_len[k]; }
+  if (n_out > 0 && !audio) return AFS_ERR_BAD_ARGUMENT;
+  // (a device that fails leaves ITS shard where it was; the caller should reset the stream after an error)
+  const int rc = for_each_shard(s->g, s->n, [&](int r, int lo, int hi) {
+    const size_t o = (size_t)lo;
+    (void)hi;
+    return afs_tds_stream_synthesize(s->part[(size_t)r], n_frames, frame_len, tubes + o * (size_t)n_frames,
+                                     glottis + o * (size_t)n_frames * AFS_NUM_GLOTTIS_CONTROL, audio ? audio + o * n_out : nullptr,
+                                     flow ? flow + o * n_out * (size_t)s->sr_factor : nullptr, status ? status + o : nullptr);
+  });
+  if (rc == AFS_OK) s->primed = true;
+  return rc;
+}
+
 int afs_host_alloc(void **ptr, size_t bytes) {
   if (!ptr) return AFS_ERR_BAD_ARGUMENT;
   *ptr = nullptr;

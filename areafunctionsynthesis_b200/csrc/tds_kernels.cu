@@ -1757,7 +1757,7 @@ struct KArgs {
   // `progress_every` steps (nullable): lets the host copy finished time slices while the kernel runs
   unsigned int *progress;
   int progress_every;
-  // chunked synthesis (OPT kernels only): recurrent state of every tract, ST_WORDS doubles each (see "state in / state
+  // chunked synthesis (STATE kernels only): recurrent state of every tract, ST_WORDS doubles each (see "state in / state
   // out" below); state_in null = a fresh model, state_out null = the state is dropped at the end
   const double *state_in;
   double *state_out;
@@ -1910,7 +1910,7 @@ __device__ __noinline__ void stage_interval(TdsSmem &S, const int lane, const in
 
 // The time loop, one instantiation per warp role.  All roles execute the same sequence of CTA barriers.
 //   ROLE 0: dynamic chain, 1: static chain, 2: X1 (glottis + output), 3: X2 (radiation loads; noise sources)
-template <int ROLE, bool NOISE, bool OPT>
+template <int ROLE, bool NOISE, bool OPT, bool STATE>
 __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const KArgs &A, const int lane, const int warp,
                                          const bool hw_ok) {
   const int tract_raw = blockIdx.x * P.lanes_per_cta + lane;
@@ -1947,14 +1947,14 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     sst.D0 = 0.0; sst.w84 = sst.e28 = sst.g28 = 0.0;
     swarp_build(P, S, lane, warp);
   }
-  // chunked synthesis: this chunk continues from the state the last one left (OPT kernels; see "state in / state out")
-  const bool resume = OPT && A.state_in != nullptr;
+  // chunked synthesis: this chunk continues from the state the last one left (STATE kernels; see "state in / state out")
+  const bool resume = STATE && A.state_in != nullptr;
   double *st_in = resume ? const_cast<double *>(A.state_in) + (size_t)tract * ST_WORDS + warp * ST_REG_WORDS : nullptr;
   int st_parity = 0;
   if (ROLE == 3) {
 #pragma unroll
     for (int j = 0; j < 4; j++) { rr.c[j] = rr.u[j] = 0.0; orr.x1[j] = orr.y1[j] = orr.x2[j] = orr.y2[j] = orr.xg[j] = orr.yg[j] = 0.0; }
-    if (OPT) {
+    if (STATE) {
 #pragma unroll
       for (int j = 0; j < 7; j++) rr.keep[0][j] = rr.keep[1][j] = 0.0;
     }
@@ -1972,7 +1972,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     for (int i = 0; i < 8; i++) xr.chebS[i] = 0.0;
     xr.prevFlow = 0.0;
   }
-  if (OPT && resume) {
+  if (STATE && resume) {
     if (ROLE == 0) st_dregs<true>(st_in, dst);
     if (ROLE == 1) st_sregs<true>(st_in, sst, nz_live);
     if (ROLE == 2) {
@@ -2011,7 +2011,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     }
     if (ROLE == 2) {  // glottis geometry of step 0
       double ctl[AFS_NUM_GLOTTIS_CONTROL], len[2], ar[2];
-      if (OPT && resume) {  // ... is what the last step of the previous chunk prepared (same control frame, ratio 1)
+      if (STATE && resume) {  // ... is what the last step of the previous chunk prepared (same control frame, ratio 1)
         len[0] = S.glLen[st_parity][0][lane]; len[1] = S.glLen[st_parity][1][lane];
         ar[0] = S.glArea[st_parity][0][lane]; ar[1] = S.glArea[st_parity][1][lane];
       } else {
@@ -2233,7 +2233,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
     A.dump[336 + blockIdx.x] = (double)all;
   }
 #endif
-  if (OPT && A.state_out && T > 0) {
+  if (STATE && A.state_out && T > 0) {
     // (shared memory: nothing is written behind the barrier the loop was left at)
     double *blk = A.state_out + (size_t)tract * ST_WORDS, *st_out = blk + warp * ST_REG_WORDS;
     if (active) {
@@ -2250,7 +2250,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
 
 // OPT = transvelar coupling or variable entrance loss switched on; NOISE = generate_noise_sources: a separate instantiation, so that the (large) noise-source code of warp X2 does not
 // sit in the instruction stream of the noise-free kernel.
-template <bool NOISE, bool OPT>
+template <bool NOISE, bool OPT, bool STATE>
 __global__ void __launch_bounds__(TDS_THREADS, 1)
 tds_batch_kernel(const TdsParams P, const KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -2316,17 +2316,17 @@ tds_batch_kernel(const TdsParams P, const KArgs A) {
     S.tvflow[lane] = 0.0;
   }
   __syncthreads();
-  if (OPT && A.state_in) {  // chunked synthesis: the per-tract rows as the previous chunk left them
+  if (STATE && A.state_in) {  // chunked synthesis: the per-tract rows as the previous chunk left them
     const int tr = blockIdx.x * P.lanes_per_cta + lane;
     st_smem<true>(S, const_cast<double *>(A.state_in) + (size_t)(tr < P.n_tracts ? tr : P.n_tracts - 1) * ST_WORDS, lane, warp, true);
     __syncthreads();
   }
 
   switch (warp) {
-    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
-    case W_X1: run_role<2, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
-    case W_X2: run_role<3, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
-    default: run_role<0, NOISE, OPT>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_T0: case W_T1: case W_T2: case W_N1: case W_N2: case W_F: run_role<1, NOISE, OPT, STATE>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_X1: run_role<2, NOISE, OPT, STATE>(P, S, A, lane, warp, hw_lane < LANES); break;
+    case W_X2: run_role<3, NOISE, OPT, STATE>(P, S, A, lane, warp, hw_lane < LANES); break;
+    default: run_role<0, NOISE, OPT, STATE>(P, S, A, lane, warp, hw_lane < LANES); break;
   }
 }
 static_assert(NSEP == NW, "prologue zeroing assumes NSEP == NW");
@@ -3281,9 +3281,13 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
   }
   static_assert(sizeof(TdsSmem) <= 227 * 1024, "TdsSmem exceeds the 227 KB a CTA can have on sm_100a");
   // non-default options, a flow source, taps: separate instantiations, like the noise sources
-  const bool opt = P.transvelar || P.var_loss || P.fsrc_sec >= 0 || P.n_probes > 0 || d_state_in || d_state_out;
-  auto kernel = P.noise ? (opt ? tds_batch_kernel<true, true> : tds_batch_kernel<true, false>)
-                        : (opt ? tds_batch_kernel<false, true> : tds_batch_kernel<false, false>);
+  const bool opt = P.transvelar || P.var_loss || P.fsrc_sec >= 0 || P.n_probes > 0;
+  // chunked synthesis (state in / state out): its own instantiations, the one-call kernels stay as they are
+  const bool state = d_state_in || d_state_out;
+  auto kernel = state ? (P.noise ? (opt ? tds_batch_kernel<true, true, true> : tds_batch_kernel<true, false, true>)
+                                 : (opt ? tds_batch_kernel<false, true, true> : tds_batch_kernel<false, false, true>))
+                      : (P.noise ? (opt ? tds_batch_kernel<true, true, false> : tds_batch_kernel<true, false, false>)
+                                 : (opt ? tds_batch_kernel<false, true, false> : tds_batch_kernel<false, false, false>));
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(TdsSmem));  // per device; cheap
   if (e != cudaSuccess) return e;

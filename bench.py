@@ -30,6 +30,7 @@ flop per (area function, bin).  `cpu_baseline` times the compiled reference (ora
 Further objects of the same JSON line (rank 0; the small legs only at N = 1): `noise_sources_on` (the TDS batch with
 the reference's default noise sources), `gather` (NCCL all-gather of the audio after the compute),
 `tl.fast_arithmetic` (afs_tl_options.arithmetic = FAST, with its error against the bit-identical output of this run),
+`chunked` (the headline batch in five pieces through afs_tds_stream_*: models kept on the device between calls),
 `raster` (K4), `formant_optimizer`, `lf_vowels`, `target_sequences`, `dataset_sweep` (one GPU's share of BASELINE
 configs[4]) -- each with the reference's CPU figure beside it where the reference has that path.
 """
@@ -461,6 +462,53 @@ def run_ours(args):
     e2e_value = e2e_of(noisy, args.steps)
     assert torch.equal(h_audio, d_audio.cpu()), "host-path audio differs from the device-resident path"
 
+    # ---------------- chunked synthesis: the same batch in five pieces, the models kept on the device ---------
+    # (afs_tds_stream_*: what a caller of the reference's Synthesizer does -- one synthesizeSignalTds call per control
+    #  frame on a live object.  The intermediate control frames are the linear interpolation of the two end frames,
+    #  i.e. the same trajectory up to rounding; host buffers, H2D + kernels + D2H per chunk inside the timed region.)
+    N_CHUNKS = 5
+    chunked = None
+    if n_out % N_CHUNKS == 0:
+        def lerp_frames(r):
+            f = fr[:, 0].copy()
+            for name in ("area_cm2", "length_cm", "laterality", "incisor_pos_cm", "velum_area_cm2", "aspiration_dB"):
+                a, b = fr[name][:, 0], fr[name][:, 1]
+                if name in ("area_cm2", "velum_area_cm2"):  # (Tube::setPharynxMouthGeometry / setVelumOpening clamp on the way in)
+                    a, b = np.maximum(a, 1e-3), np.maximum(b, 1e-3)
+                f[name] = (1.0 - r) * a + r * b
+            return f, (1.0 - r) * gl[:, 0] + r * gl[:, 1]
+        pieces = [lerp_frames(k / N_CHUNKS) for k in range(N_CHUNKS + 1)]
+        h_cf = [torch.from_numpy(np.ascontiguousarray(f).view(np.uint8).reshape(B_TDS, -1).copy()).pin_memory() for f, _ in pieces]
+        h_cg = [torch.from_numpy(np.ascontiguousarray(g)).pin_memory() for _, g in pieces]
+        h_ca = [torch.empty(B_TDS, n_out // N_CHUNKS, dtype=torch.float64).pin_memory() for _ in range(N_CHUNKS)]
+        st_h = afs.api.C.c_void_p()
+        rc = ctx.lib.afs_tds_stream_create(ctx.h, afs.api.C.byref(noisy), B_TDS, FS, SR_FACTOR, h_seeds.data_ptr(), afs.api.C.byref(st_h))
+        assert rc == 0, rc
+        one_len = np.array([n_out // N_CHUNKS], dtype=np.int32)
+
+        def run_chunks():
+            ctx.lib.afs_tds_stream_reset(st_h)
+            for k in range(N_CHUNKS + 1):  # (piece 0 primes)
+                rc = ctx.lib.afs_tds_stream_synthesize(st_h, 1, one_len.ctypes.data, h_cf[k].data_ptr(), h_cg[k].data_ptr(),
+                                                       h_ca[k - 1].data_ptr() if k else None, None, h_status.data_ptr())
+                assert rc == 0, rc
+        run_chunks()
+        barrier()
+        t0 = time.perf_counter()
+        run_chunks()
+        barrier()
+        ch_dt = max_over_ranks(time.perf_counter() - t0)
+        ctx.lib.afs_tds_stream_destroy(st_h)
+        a_ch = torch.cat(h_ca, dim=1)
+        ch_rel = float(((a_ch - h_audio).abs().amax(dim=1) / h_audio.abs().amax(dim=1)).max().item())
+        chunked = {"workload": f"the headline batch in {N_CHUNKS} pieces of {T_SEC / N_CHUNKS:g} s through afs_tds_stream_* (models and "
+                               "state resident on the device between calls), host buffers",
+                   "value": audio_s_per_step / ch_dt, "unit": "audio-s/s", "chunks": N_CHUNKS,
+                   "vs_one_call_e2e": audio_s_per_step / ch_dt / e2e_value,
+                   "max_rel_vs_one_call": ch_rel}
+        assert ch_rel <= 1e-6, ch_rel
+        del h_cf, h_cg, h_ca, a_ch
+
     # the only collective of the path: one all-gather of the outputs, after the compute; timed separately
     digest = d_audio.abs().mean(dim=1)
     gather_ms = 0.0
@@ -761,6 +809,7 @@ def run_ours(args):
         "parity": parity,
         "strong": {"workload": "BASELINE configs[3] as written: 4096 utterances in total, contiguous shards over the ranks",
                    "scaling": "strong", "utterances_this_rank": int(n_shard), **strong},
+        "chunked": chunked,
         "oral_b1024": {"workload": "BASELINE configs[2]: 1024 oral vowel-to-vowel transitions x 1 s per GPU (velum closed)",
                        "scaling": "weak", **oral},
         "dataset_sweep": dataset,

@@ -521,6 +521,16 @@ int afs_group_tds_synthesize(afs_group *group, const afs_tds_options *opts, int 
                              uint32_t *status);
 int afs_group_tl_sweep(afs_group *group, const afs_tl_options *opts, int n_tubes, const afs_tube_frame *tubes,
                        int spectrum_type, int section, double f0_hz, int num_freq, double *re, double *im);
+/* Chunked synthesis (afs_tds_stream_*) over the devices of a group: every device keeps the models of its shard;
+ * arguments and results as for the single-device stream, bit for bit. */
+typedef struct afs_group_tds_stream afs_group_tds_stream;
+int afs_group_tds_stream_create(afs_group *group, const afs_tds_options *opts, int n_tracts, double fs_tds_hz, int sr_factor,
+                                const uint32_t *seeds, afs_group_tds_stream **stream);
+int afs_group_tds_stream_destroy(afs_group_tds_stream *stream);
+int afs_group_tds_stream_reset(afs_group_tds_stream *stream);
+int afs_group_tds_stream_synthesize(afs_group_tds_stream *stream, int n_frames, const int32_t *frame_len,
+                                    const afs_tube_frame *tubes, const double *glottis, double *audio, double *flow,
+                                    uint32_t *status);
 /* Page-locked host memory (cudaHostAlloc, portable across the devices of a group). */
 int afs_host_alloc(void **ptr, size_t bytes);
 int afs_host_free(void *ptr);

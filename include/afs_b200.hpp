@@ -251,7 +251,10 @@ class TdsSynthesizer {
   TdsSynthesizer(Device &dev, int numUtterances) : dev_(&dev), n_(numUtterances) { afs_tds_options_default(&options); }
   // the same over several devices (contiguous shards of the utterances)
   TdsSynthesizer(DeviceGroup &group, int numUtterances) : group_(&group), n_(numUtterances) { afs_tds_options_default(&options); }
-  ~TdsSynthesizer() { if (stream_) afs_tds_stream_destroy(stream_); }
+  ~TdsSynthesizer() {
+    if (stream_) afs_tds_stream_destroy(stream_);
+    if (gstream_) afs_group_tds_stream_destroy(gstream_);
+  }
   TdsSynthesizer(const TdsSynthesizer &) = delete;
   TdsSynthesizer &operator=(const TdsSynthesizer &) = delete;
   // TdsModel::resetMotion + a driver that has not seen a tube yet (Synthesizer::reset)
@@ -259,6 +262,7 @@ class TdsSynthesizer {
     clearQueue();
     continuing_ = false;
     if (stream_) afs_tds_stream_reset(stream_);
+    if (gstream_) afs_group_tds_stream_reset(gstream_);
   }
   // TdsModel::setFlowSource(flow_cm3_s, section) (TdsModel.cpp:629-633); section -1 switches it off.
   void setFlowSource(double flow_cm3_s, int section) { options.flow_source_cm3_s = flow_cm3_s; options.flow_source_section = section; }
@@ -278,13 +282,13 @@ class TdsSynthesizer {
     frames_++;
   }
   // Runs the queued frames and KEEPS the models: the next synthesizeSignalTds calls continue from the state and the
-  // tube these frames ended in, exactly like further calls on the reference's Synthesizer object (afs_tds_stream_*;
-  // single device; `options`, the rates and the number of utterances are fixed by the first call).  The audio of an
+  // tube these frames ended in, exactly like further calls on the reference's Synthesizer object (afs_tds_stream_*,
+  // afs_group_tds_stream_*; `options`, the rates and the number of utterances are fixed by the first call).  The audio of an
   // utterance synthesised in pieces equals the audio of one flush() of all its frames.
   void flushAndContinue(std::vector<double> *audio, std::vector<double> *flow = nullptr, std::vector<uint32_t> *status = nullptr) {
-    if (!dev_) throw Error(AFS_ERR_UNSUPPORTED, "chunked synthesis is a single-device feature");
     if (frames_ < 1) throw Error(AFS_ERR_BAD_ARGUMENT, "no control frames queued");
-    if (!stream_) check(afs_tds_stream_create(dev_->ctx(), &options, n_, samplingRate * tdsSrFactor, tdsSrFactor, nullptr, &stream_), dev_->ctx());
+    if (dev_ && !stream_) check(afs_tds_stream_create(dev_->ctx(), &options, n_, samplingRate * tdsSrFactor, tdsSrFactor, nullptr, &stream_), dev_->ctx());
+    if (group_ && !gstream_) check(afs_group_tds_stream_create(group_->group(), &options, n_, samplingRate * tdsSrFactor, tdsSrFactor, nullptr, &gstream_));
     std::vector<afs_tube_frame> t;
     std::vector<double> g;
     transposeQueue(&t, &g);
@@ -296,8 +300,10 @@ class TdsSynthesizer {
     audio->assign((size_t)n_ * n_out, 0.0);
     if (flow) flow->assign((size_t)n_ * n_out * tdsSrFactor, 0.0);
     if (status) status->assign((size_t)n_, 0u);
-    check(afs_tds_stream_synthesize(stream_, frames_, len.data(), t.data(), g.data(), audio->data(), flow ? flow->data() : nullptr,
-                                    status ? status->data() : nullptr), dev_->ctx());
+    if (group_) check(afs_group_tds_stream_synthesize(gstream_, frames_, len.data(), t.data(), g.data(), audio->data(),
+                                                      flow ? flow->data() : nullptr, status ? status->data() : nullptr));
+    else check(afs_tds_stream_synthesize(stream_, frames_, len.data(), t.data(), g.data(), audio->data(), flow ? flow->data() : nullptr,
+                                         status ? status->data() : nullptr), dev_->ctx());
     clearQueue();
     continuing_ = true;
   }
@@ -348,6 +354,7 @@ class TdsSynthesizer {
       }
   }
   afs_tds_stream *stream_ = nullptr;
+  afs_group_tds_stream *gstream_ = nullptr;
   bool continuing_ = false;  // the models carry state and a previous tube (flushAndContinue)
   Device *dev_ = nullptr;
   DeviceGroup *group_ = nullptr;

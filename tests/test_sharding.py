@@ -77,6 +77,7 @@ def test_device_group_equals_single_device(shapes):
     a1, f1, s1 = one.tds_synthesize(fr, gl, [120], 44100.0, 2, seeds=seeds, want_flow=True)
     re1, im1 = one.tl_sweep(fr[:, 0], 22050.0 / 2048, 512)
     one.close()
+    g_one = afs.Context(0)
     for devices in (None, [0], list(range(n_dev))[::-1]):
         g = afs.Group(devices)
         G = len(g)
@@ -86,6 +87,16 @@ def test_device_group_equals_single_device(shapes):
         assert np.array_equal(a, a1) and np.array_equal(f, f1) and np.array_equal(s, s1)
         re, im = g.tl_sweep(fr[:, 0], 22050.0 / 2048, 512)
         assert np.array_equal(re, re1) and np.array_equal(im, im1)
+        # chunked synthesis over the group: every device keeps the models of its shard between calls
+        gs = afs.TdsStream(g, B, 44100.0, 2, seeds=seeds)
+        p1, _, _ = gs.synthesize(fr, gl, [0, 120])
+        p2, _, _ = gs.synthesize(fr[:, :1], gl[:, :1], [60])
+        gs.close()
+        ss = afs.TdsStream(g_one, B, 44100.0, 2, seeds=seeds)
+        q1, _, _ = ss.synthesize(fr, gl, [0, 120])
+        q2, _, _ = ss.synthesize(fr[:, :1], gl[:, :1], [60])
+        ss.close()
+        assert np.array_equal(p1, q1) and np.array_equal(p2, q2) and np.abs(p2).max() > 0
         # fewer units than devices, empty batch, pinned output
         a, _, _ = g.tds_synthesize(fr[:1], gl[:1], [120], 44100.0, 2, seeds=seeds[:1])
         assert np.array_equal(a, a1[:1])
@@ -96,5 +107,6 @@ def test_device_group_equals_single_device(shapes):
         assert np.array_equal(pin, a1)
         afs.pinned_free(pin)
         g.close()
+    g_one.close()
     with pytest.raises(afs.AfsError):
         afs.Group([0, 0])
