@@ -287,6 +287,7 @@ class TdsSynthesizer {
   // utterance synthesised in pieces equals the audio of one flush() of all its frames.
   void flushAndContinue(std::vector<double> *audio, std::vector<double> *flow = nullptr, std::vector<uint32_t> *status = nullptr) {
     if (frames_ < 1) throw Error(AFS_ERR_BAD_ARGUMENT, "no control frames queued");
+    if (!probeSections_.empty()) throw Error(AFS_ERR_UNSUPPORTED, "taps are served by flush() only");
     if (dev_ && !stream_) check(afs_tds_stream_create(dev_->ctx(), &options, n_, samplingRate * tdsSrFactor, tdsSrFactor, nullptr, &stream_), dev_->ctx());
     if (group_ && !gstream_) check(afs_group_tds_stream_create(group_->group(), &options, n_, samplingRate * tdsSrFactor, tdsSrFactor, nullptr, &gstream_));
     std::vector<afs_tube_frame> t;
