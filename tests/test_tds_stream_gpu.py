@@ -151,3 +151,30 @@ def test_long_utterance_in_bounded_memory(ctx, shapes):
     rms = np.array(rms)
     assert (rms[1:] > 1e-3).all(), rms.min()
     st.close()
+
+
+def test_chunk_repeated_after_pool_overflow(ctx, shapes):
+    """The record pool of the noise pre-pass turns out too small in the middle of a stream: the chunk is repeated with
+    a larger pool FROM THE SAME STATE (two state buffers), the audio is that of an undisturbed stream."""
+    import areafunctionsynthesis_b200 as afs
+    n = len(shapes["names"])
+    rng = np.random.default_rng(5)
+    B = 6400
+    fr = np.tile(shapes["frames"][rng.integers(0, n, size=(40, 3))], (160, 1))
+    gl = np.tile(np.array([120.0, 8000.0, 0.01, 0.01, 0.0, -15.0]), (B, 3, 1))
+    seeds = np.tile(np.arange(1, 41, dtype=np.uint32), 160)
+    on = afs.tds_options_default(noise=True)
+    ref, _, _ = _chunked(ctx, fr, gl, [400, 400], [2], 44100.0, 2, on, seeds=seeds)
+    st = afs.TdsStream(ctx, B, 44100.0, 2, opts=on, seeds=seeds)
+    a1, _, s1 = st.synthesize(fr[:, :2], gl[:, :2], [0, 400])
+    ctx.debug_set("tds.noise_run_pool_factor", 2)   # (the chunk below needs more records than 2 per piece + 4096)
+    l0 = ctx.launch_count
+    try:
+        a2, _, s2 = st.synthesize(fr[:, 2:], gl[:, 2:], [400])
+    finally:
+        ctx.debug_set("tds.noise_run_pool_factor", 32)
+    assert ctx.launch_count - l0 >= 4, "pre-pass + time loop at least twice: the overflow must have happened"
+    st.close()
+    assert not s1.any() and not s2.any()
+    assert np.array_equal(np.concatenate([a1, a2], axis=1), ref)
+    assert np.array_equal(ref[:40], ref[-40:])
