@@ -99,7 +99,9 @@ struct TdsParams {
   int transvelar, var_loss;         // transvelarCoupling, glottisLossOption == VARIABLE_ENTRANCE_LOSS (TdsModel.h:75-87)
   int fsrc_sec;                     // TdsModel::setFlowSource (TdsModel.cpp:629-633): section of the flow source, -1 = none
   double fsrc_amp;                  // ... and its strength in cm^3/s
-  int n_probes, probe_sec[AFS_MAX_TDS_PROBES];  // taps (getSectionPressure / getSectionFlow, TdsModel.cpp:1715-1734)
+  int n_probes;                     // taps (getSectionPressure / getSectionFlow, TdsModel.cpp:1715-1734) ...
+  unsigned long long probe_pack;    // ... and their tube sections, one per byte
+  int reserved_[6];                 // (keeps the layout the plain kernels were tuned with)
   double tg_a[5], tg_b[5];          // 50 Hz Chebyshev low-pass of the transglottal pressure (TdsModel.cpp:474)
   double k_sondhi, k_bern;          // 8 rho/(3 pi^2) resp. rho/2, or 0 when the option is off
   double kalpha[3], c1[3], c2[3], c3[3];  // wall constants: 0 standard, 1 trachea, 2 sinus
@@ -375,13 +377,16 @@ struct StepCtx {
 // the section, volume velocity into and out of it.
 // (not inlined: taps are rare, and code that is not executed must stay out of the instruction stream of the time loop
 //  -- the kernel lives off its instruction cache)
-__device__ __noinline__ void tap_section(const int n_probes, const int *probe_sec, const StepCtx &X, int sec, double p, double in,
-                                         double out) {
+// (everything by value -- the probe sections packed one per byte: a pointer into the kernel parameters or to the step
+//  context handed to a function that is not inlined would move BOTH to local memory for the whole kernel; the
+//  instantiations with taps ran 1.43 x slower than the plain ones for that reason)
+__device__ __noinline__ void tap_section(const int n_probes, const unsigned long long probe_pack, double *tap_p, double *tap_in,
+                                         double *tap_out, const size_t tap_stride, int sec, double p, double in, double out) {
   for (int q = 0; q < n_probes; q++) {
-    if (probe_sec[q] != sec) continue;
-    if (X.tap_p) X.tap_p[q * X.tap_stride] = p;
-    if (X.tap_in) X.tap_in[q * X.tap_stride] = in;
-    if (X.tap_out) X.tap_out[q * X.tap_stride] = out;
+    if ((int)((probe_pack >> (8 * q)) & 255ull) != sec) continue;
+    if (tap_p) tap_p[q * tap_stride] = p;
+    if (tap_in) tap_in[q * tap_stride] = in;
+    if (tap_out) tap_out[q * tap_stride] = out;
   }
 }
 
@@ -475,7 +480,7 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
       S.wall[sec][0][lane] = wc; S.wall[sec][1][lane] = wcr; S.wall[sec][2][lane] = wcr2;
       if (k < 3 && sec <= PHAR0) S.p4[sec - TRACHEA_LAST][lane] = p_new;  // sections 23, 24, 25
-      if (OPT && P.n_probes > 0) tap_section(P.n_probes, P.probe_sec, X, sec, p_new, u, out);
+      if (OPT && P.n_probes > 0) tap_section(P.n_probes, P.probe_pack, X.tap_p, X.tap_in, X.tap_out, X.tap_stride, sec, p_new, u, out);
     }
     if (rows) {
       // Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350); the index is clamped for the other kinds
@@ -725,7 +730,7 @@ __device__ __forceinline__ void static_section(const TdsParams &P, TdsSmem &S, c
     const double ur = fma(u, P.idt, -c);
     c = fma(ur, P.th, u * P.idt);
     const double p_new = fma(E, u - out, D_old);
-    if (OPT && P.n_probes > 0) tap_section(P.n_probes, P.probe_sec, X, sec, p_new, u, out);
+    if (OPT && P.n_probes > 0) tap_section(P.n_probes, P.probe_pack, X.tap_p, X.tap_in, X.tap_out, X.tap_stride, sec, p_new, u, out);
     const double pr_new = (p_new - p) * P.idt - pr * P.th;
     const double wc_new = fma(pr_new, r.alpha, beta_old);
     const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
@@ -3276,7 +3281,7 @@ cudaError_t launch_tds(const TdsLaunch &L, int tract0, int n_wave, const int32_t
     P.n_probes = probes->n_probes;
     for (int q = 0; q < P.n_probes; q++) {
       if (probes->section[q] < 0 || probes->section[q] >= NS) return cudaErrorInvalidValue;
-      P.probe_sec[q] = probes->section[q];
+      P.probe_pack |= (unsigned long long)probes->section[q] << (8 * q);
     }
   }
   static_assert(sizeof(TdsSmem) <= 227 * 1024, "TdsSmem exceeds the 227 KB a CTA can have on sm_100a");
