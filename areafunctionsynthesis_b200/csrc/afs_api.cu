@@ -1116,6 +1116,42 @@ size_t stream_state_bytes(const afs_tds_stream *s) { return (size_t)s->n * tds_s
 size_t stream_blob_bytes(const afs_tds_stream *s) {
   return sizeof(StreamHeader) + (size_t)s->n * (sizeof(afs_tube_frame) + AFS_NUM_GLOTTIS_CONTROL * sizeof(double)) + stream_state_bytes(s);
 }
+// Device-to-host copy of a chunk's audio WHILE its kernel runs (the scheme of afs_tds_synthesize_probed: per-CTA progress
+// marks in mapped host memory, finished time slices / CTA waves copied on the second stream).  Returns what is already
+// on its way: output samples per tract (*copied) or whole tracts (*rows_copied); the caller copies the rest behind the kernel.
+cudaError_t copy_finished_audio(afs_ctx *ctx, double *audio, const double *d_audio, size_t n_tracts, size_t n_out, int sr_factor,
+                                int every, size_t slice_out, int ctas, int lpc, size_t *copied, size_t *rows_copied) {
+  *copied = 0; *rows_copied = 0;
+  const volatile unsigned int *mark = ctx->progress_h;
+  auto wait_for = [&](int c0, int c1, unsigned int need) {
+    for (int spin = 0;; spin++) {
+      bool ready = true;
+      for (int c = c0; c < c1; c++) if (mark[c] < need) { ready = false; break; }
+      if (ready) return true;
+      if ((spin & 1023) == 1023 && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) return false;
+    }
+  };
+  cudaError_t ce = cudaSuccess;
+  const size_t total_steps = n_out * (size_t)sr_factor;
+  if (every && ctas > 0 && ctas <= ctx->sm_count) {
+    while (ce == cudaSuccess && *copied + slice_out < n_out) {
+      if (!wait_for(0, ctas, (unsigned int)((*copied + slice_out) * (size_t)sr_factor))) break;
+      ce = cudaMemcpy2DAsync(audio + *copied, n_out * sizeof(double), d_audio + *copied, n_out * sizeof(double),
+                             slice_out * sizeof(double), n_tracts, cudaMemcpyDeviceToHost, ctx->copy_stream);
+      *copied += slice_out;
+    }
+  } else if (every && ctas > ctx->sm_count) {
+    for (int c0 = 0; ce == cudaSuccess && c0 + ctx->sm_count < ctas; c0 += ctx->sm_count) {
+      if (!wait_for(c0, c0 + ctx->sm_count, (unsigned int)total_steps)) break;
+      const size_t r1 = (size_t)(c0 + ctx->sm_count) * (size_t)lpc;
+      ce = cudaMemcpyAsync(audio + *rows_copied * n_out, d_audio + *rows_copied * n_out, (r1 - *rows_copied) * n_out * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->copy_stream);
+      *rows_copied = r1;
+    }
+  }
+  return ce;
+}
+
 void stream_release(afs_tds_stream *s) {
   cudaFree(s->d_state[0]); cudaFree(s->d_state[1]); cudaFree(s->d_prev_tubes); cudaFree(s->d_prev_gl); cudaFree(s->d_seeds);
   delete s;
@@ -1201,22 +1237,39 @@ int afs_tds_stream_synthesize(afs_tds_stream *s, int n_frames, const int32_t *fr
   CU(cudaMemcpy2DAsync((unsigned char *)d_gl + gsz, dp_g, glottis + (size_t)k0 * AFS_NUM_GLOTTIS_CONTROL, (size_t)n_frames * gsz,
                        (size_t)m * gsz, n, cudaMemcpyHostToDevice, ctx->stream));
   std::vector<uint32_t> st((size_t)s->n);
+  // finished time slices of the audio leave the device while the kernel runs (as in afs_tds_synthesize)
+  const size_t total_steps = n_out * (size_t)s->sr_factor;
+  int n_slices = ab >= ((size_t)8 << 20) && n_out >= 64 ? 16 : 1;
+  if (ctx->dbg_d2h_slices > 0) n_slices = ctx->dbg_d2h_slices;
+  const size_t slice_out = (n_out + (size_t)n_slices - 1) / (size_t)n_slices;
+  const int every = n_slices > 1 && total_steps < 0x7fffffffull ? (int)(slice_out * (size_t)s->sr_factor) : 0;
+  size_t copied = 0, rows_copied = 0;
   for (;;) {
+    if (every) memset(ctx->progress_h, 0, kMaxProgressCtas * sizeof(unsigned int));
+    int grid[2] = {0, 0};
     rc = tds_run_device(ctx, &s->opts, s->n, m + 1, frame_len + k0, (const afs_tube_frame *)d_tubes, (const double *)d_gl, s->fs,
                         s->sr_factor, s->d_seeds, (double *)d_audio, (double *)d_flow, (uint32_t *)d_status, nullptr, ctx->stream,
-                        nullptr, 0, nullptr, s->has_state ? s->d_state[s->cur] : nullptr, s->d_state[s->cur ^ 1]);
-    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
-    cudaError_t e = cudaMemcpyAsync(st.data(), d_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                        every ? ctx->progress_d : nullptr, every, grid, s->has_state ? s->d_state[s->cur] : nullptr,
+                        s->d_state[s->cur ^ 1]);
+    if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    cudaError_t e = copy_finished_audio(ctx, audio, (const double *)d_audio, n, n_out, s->sr_factor, every, slice_out, grid[0], grid[1],
+                                        &copied, &rows_copied);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(st.data(), d_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = e1 != cudaSuccess ? e1 : e2;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "afs_tds_stream_synthesize");
     // status bit 1: the record pool of the noise pre-pass was too small -- the chunk is repeated from the same state
+    // (whatever was copied already is overwritten by the repeat)
     if (s->opts.generate_noise_sources && (st[0] & 2u) && ctx->run_pool_factor < 4096) { ctx->run_pool_factor *= 8; continue; }
     break;
   }
   // the chunk is in: its last frame is the next prevTube, the state buffers change roles
   CU(cudaMemcpy2DAsync(s->d_prev_tubes, fsz, (unsigned char *)d_tubes + (size_t)m * fsz, dp_t, fsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpy2DAsync(s->d_prev_gl, gsz, (unsigned char *)d_gl + (size_t)m * gsz, dp_g, gsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(audio, d_audio, ab, cudaMemcpyDeviceToHost, ctx->stream));
+  if (copied == 0) CU(cudaMemcpyAsync(audio + rows_copied * n_out, (const double *)d_audio + rows_copied * n_out,
+                                      (n - rows_copied) * n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  else CU(cudaMemcpy2DAsync(audio + copied, n_out * sizeof(double), (const double *)d_audio + copied, n_out * sizeof(double),
+                            (n_out - copied) * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
   if (flow) CU(cudaMemcpyAsync(flow, d_flow, fb, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (status) memcpy(status, st.data(), n * sizeof(uint32_t));
