@@ -460,7 +460,9 @@ int afs_tds_synthesize_probed_device(afs_ctx *ctx, const afs_tds_options *opts, 
  *   afs_tds_stream_save/load   checkpoint / resume: the whole stream (state, last frames, counters) as one host blob of
  *                              afs_tds_stream_checkpoint_bytes bytes; load accepts a blob written by a stream of the
  *                              same batch size, rates and options (else AFS_ERR_BAD_ARGUMENT).
- * A stream belongs to its context (same threading rule); destroy it before the context.
+ * A stream belongs to its context (same threading rule); destroy it before the context.  Taps (afs_tds_probes) and the
+ * state dump are served by the one-call entry points only.  The audio of a chunk leaves the device while its kernel
+ * runs, like in afs_tds_synthesize; pass page-locked buffers (afs_host_alloc) for the copies to overlap.
  */
 typedef struct afs_tds_stream afs_tds_stream;
 int afs_tds_stream_create(afs_ctx *ctx, const afs_tds_options *opts, int n_tracts, double fs_tds_hz, int sr_factor,
