@@ -89,21 +89,24 @@ def test_chunked_equals_one_call_and_oracle(ctx, oracle, shapes, noise):
         assert rel_err(a2[b], ao[k]) <= 1e-6 and rel_err(u2[b], uo[k]) <= 1e-6, b
 
 
+@pytest.mark.parametrize("noise", [False, True])
 @pytest.mark.parametrize("srf", [1, 3])
-def test_chunks_with_odd_step_counts(ctx, shapes, srf):
+def test_chunks_with_odd_step_counts(ctx, shapes, srf, noise):
     """The step-parity buffers of the kernel (glottis geometry, filter histories of the non-default options) across
-    chunks of an odd number of simulation steps; transvelar coupling + variable entrance loss + fossa on."""
+    chunks of an odd number of simulation steps; transvelar coupling + variable entrance loss + fossa + a flow source on
+    (the OPT x STATE instantiations of the kernel)."""
     import areafunctionsynthesis_b200 as afs
     n, F = 5, 5
     fr, gl = _utterances(shapes, n, 77, F)
     frame_len = [7, 1, 33, 260]
-    o = afs.tds_options_default(noise=True)
+    o = afs.tds_options_default(noise=noise)
     o.transvelar_coupling = 1; o.glottis_loss_option = 2; o.piriform_fossa = 1
+    o.flow_source_section = 45; o.flow_source_cm3_s = 20.0
     fs = 22050.0 * srf
     a1, u1, _ = ctx.tds_synthesize(fr, gl, frame_len, fs, srf, opts=o, want_flow=True)
     a2, u2, _ = _chunked(ctx, fr, gl, frame_len, [2, 3, 4], fs, srf, o, want_flow=True)
     e = max(rel_err(a2, a1), rel_err(u2, u1))
-    print(f"odd chunks, sr_factor {srf}: max rel difference {e:.2e}")
+    print(f"odd chunks, sr_factor {srf}, noise {'on' if noise else 'off'}: max rel difference {e:.2e}")
     assert e <= CHUNK_TOL
 
 
