@@ -342,7 +342,8 @@ class TdsStream:
 
     def close(self):
         if self.h:
-            self._f["destroy"](self.h)
+            if getattr(self.ctx, "h", None):  # (a stream must not outlive its context: nothing to release then)
+                self._f["destroy"](self.h)
             self.h = None
 
     def __del__(self):
