@@ -1214,11 +1214,18 @@ int afs_tds_stream_synthesize(afs_tds_stream *s, int n_frames, const int32_t *fr
   for (int k = k0; k < n_frames; k++) { if (frame_len[k] < 1) return AFS_ERR_BAD_ARGUMENT; n_out += (size_t)frame_len[k]; }
   if (m > 0 && !audio) return AFS_ERR_BAD_ARGUMENT;
   const size_t n = (size_t)s->n, fsz = sizeof(afs_tube_frame), gsz = AFS_NUM_GLOTTIS_CONTROL * sizeof(double);
+  // every error path drains both streams before it returns: the caller owns its buffers again
+  auto fail = [&](cudaError_t err, const char *what) {
+    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream);
+    return cuda_fail(ctx, err, what);
+  };
+  cudaError_t e = cudaSuccess;
   if (!s->primed) {  // prevTube = the first frame, no samples (Synthesizer.cpp:522-532)
-    CU(cudaMemcpy2DAsync(s->d_prev_tubes, fsz, tubes, (size_t)n_frames * fsz, fsz, n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpy2DAsync(s->d_prev_gl, gsz, glottis, (size_t)n_frames * gsz, gsz, n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    s->primed = true;
+    e = cudaMemcpy2DAsync(s->d_prev_tubes, fsz, tubes, (size_t)n_frames * fsz, fsz, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(s->d_prev_gl, gsz, glottis, (size_t)n_frames * gsz, gsz, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(e, "afs_tds_stream_synthesize (priming frame)");
+    if (m == 0) s->primed = true;  // (with more frames in this call: once their chunk is in)
   }
   if (m == 0) return AFS_OK;
   // the chunk's frames on the device: [tract][prev, new 0 .. m-1]
@@ -1230,12 +1237,13 @@ int afs_tds_stream_synthesize(afs_tds_stream *s, int n_frames, const int32_t *fr
   if (flow && (rc = scratch(ctx, 3, fb, &d_flow))) return rc;
   if ((rc = scratch(ctx, 4, n * sizeof(uint32_t), &d_status))) return rc;
   const size_t dp_t = (size_t)(m + 1) * fsz, dp_g = (size_t)(m + 1) * gsz;
-  CU(cudaMemcpy2DAsync(d_tubes, dp_t, s->d_prev_tubes, fsz, fsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpy2DAsync(d_gl, dp_g, s->d_prev_gl, gsz, gsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpy2DAsync((unsigned char *)d_tubes + fsz, dp_t, tubes + k0, (size_t)n_frames * fsz, (size_t)m * fsz, n,
-                       cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpy2DAsync((unsigned char *)d_gl + gsz, dp_g, glottis + (size_t)k0 * AFS_NUM_GLOTTIS_CONTROL, (size_t)n_frames * gsz,
-                       (size_t)m * gsz, n, cudaMemcpyHostToDevice, ctx->stream));
+  e = cudaMemcpy2DAsync(d_tubes, dp_t, s->d_prev_tubes, fsz, fsz, n, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_gl, dp_g, s->d_prev_gl, gsz, gsz, n, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync((unsigned char *)d_tubes + fsz, dp_t, tubes + k0, (size_t)n_frames * fsz, (size_t)m * fsz, n,
+                                              cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync((unsigned char *)d_gl + gsz, dp_g, glottis + (size_t)k0 * AFS_NUM_GLOTTIS_CONTROL,
+                                              (size_t)n_frames * gsz, (size_t)m * gsz, n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return fail(e, "afs_tds_stream_synthesize (control frames)");
   std::vector<uint32_t> st((size_t)s->n);
   // finished time slices of the audio leave the device while the kernel runs (as in afs_tds_synthesize)
   const size_t total_steps = n_out * (size_t)s->sr_factor;
@@ -1252,7 +1260,7 @@ int afs_tds_stream_synthesize(afs_tds_stream *s, int n_frames, const int32_t *fr
                         every ? ctx->progress_d : nullptr, every, grid, s->has_state ? s->d_state[s->cur] : nullptr,
                         s->d_state[s->cur ^ 1]);
     if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); return rc; }
-    cudaError_t e = copy_finished_audio(ctx, audio, (const double *)d_audio, n, n_out, s->sr_factor, every, slice_out, grid[0], grid[1],
+    e = copy_finished_audio(ctx, audio, (const double *)d_audio, n, n_out, s->sr_factor, every, slice_out, grid[0], grid[1],
                                         &copied, &rows_copied);
     if (e == cudaSuccess) e = cudaMemcpyAsync(st.data(), d_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     const cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
@@ -1264,16 +1272,20 @@ int afs_tds_stream_synthesize(afs_tds_stream *s, int n_frames, const int32_t *fr
     break;
   }
   // the chunk is in: its last frame is the next prevTube, the state buffers change roles
-  CU(cudaMemcpy2DAsync(s->d_prev_tubes, fsz, (unsigned char *)d_tubes + (size_t)m * fsz, dp_t, fsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpy2DAsync(s->d_prev_gl, gsz, (unsigned char *)d_gl + (size_t)m * gsz, dp_g, gsz, n, cudaMemcpyDeviceToDevice, ctx->stream));
-  if (copied == 0) CU(cudaMemcpyAsync(audio + rows_copied * n_out, (const double *)d_audio + rows_copied * n_out,
-                                      (n - rows_copied) * n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  else CU(cudaMemcpy2DAsync(audio + copied, n_out * sizeof(double), (const double *)d_audio + copied, n_out * sizeof(double),
-                            (n_out - copied) * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (flow) CU(cudaMemcpyAsync(flow, d_flow, fb, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (copied == 0) e = cudaMemcpyAsync(audio + rows_copied * n_out, (const double *)d_audio + rows_copied * n_out,
+                                       (n - rows_copied) * n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  else e = cudaMemcpy2DAsync(audio + copied, n_out * sizeof(double), (const double *)d_audio + copied, n_out * sizeof(double),
+                             (n_out - copied) * sizeof(double), n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && flow) e = cudaMemcpyAsync(flow, d_flow, fb, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return fail(e, "afs_tds_stream_synthesize (device-to-host copies)");
+  // (the last frame becomes prevTube only now: a call that failed above leaves the stream as it was)
+  e = cudaMemcpy2DAsync(s->d_prev_tubes, fsz, (unsigned char *)d_tubes + (size_t)m * fsz, dp_t, fsz, n, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(s->d_prev_gl, gsz, (unsigned char *)d_gl + (size_t)m * gsz, dp_g, gsz, n, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return fail(e, "afs_tds_stream_synthesize (last control frame)");
   if (status) memcpy(status, st.data(), n * sizeof(uint32_t));
-  s->cur ^= 1; s->has_state = true; s->samples += (int64_t)n_out;
+  s->cur ^= 1; s->has_state = true; s->primed = true; s->samples += (int64_t)n_out;
   return AFS_OK;
 }
 
@@ -1292,13 +1304,16 @@ int afs_tds_stream_save(afs_tds_stream *s, void *blob, size_t bytes) {
   memcpy(at, &h, sizeof h); at += sizeof h;
   const size_t tb = (size_t)s->n * sizeof(afs_tube_frame), gb = (size_t)s->n * AFS_NUM_GLOTTIS_CONTROL * sizeof(double);
   memset(at, 0, tb + gb + stream_state_bytes(s));
+  cudaError_t e = cudaSuccess;
   if (s->primed) {
-    CU(cudaMemcpyAsync(at, s->d_prev_tubes, tb, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(at + tb, s->d_prev_gl, gb, cudaMemcpyDeviceToHost, ctx->stream));
+    e = cudaMemcpyAsync(at, s->d_prev_tubes, tb, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(at + tb, s->d_prev_gl, gb, cudaMemcpyDeviceToHost, ctx->stream);
   }
-  if (s->has_state) CU(cudaMemcpyAsync(at + tb + gb, s->d_state[s->cur], stream_state_bytes(s), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  return AFS_OK;
+  if (e == cudaSuccess && s->has_state)
+    e = cudaMemcpyAsync(at + tb + gb, s->d_state[s->cur], stream_state_bytes(s), cudaMemcpyDeviceToHost, ctx->stream);
+  const cudaError_t es = cudaStreamSynchronize(ctx->stream);  // (drained on every path)
+  if (e == cudaSuccess) e = es;
+  return e == cudaSuccess ? AFS_OK : cuda_fail(ctx, e, "afs_tds_stream_save");
 }
 
 int afs_tds_stream_load(afs_tds_stream *s, const void *blob, size_t bytes) {
@@ -1314,10 +1329,12 @@ int afs_tds_stream_load(afs_tds_stream *s, const void *blob, size_t bytes) {
       h.state_words != tds_state_words() || memcmp(&h.opts, &s->opts, sizeof h.opts) != 0)
     return AFS_ERR_BAD_ARGUMENT;
   const size_t tb = (size_t)s->n * sizeof(afs_tube_frame), gb = (size_t)s->n * AFS_NUM_GLOTTIS_CONTROL * sizeof(double);
-  CU(cudaMemcpyAsync(s->d_prev_tubes, at, tb, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s->d_prev_gl, at + tb, gb, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s->d_state[s->cur], at + tb + gb, stream_state_bytes(s), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  cudaError_t e = cudaMemcpyAsync(s->d_prev_tubes, at, tb, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_prev_gl, at + tb, gb, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_state[s->cur], at + tb + gb, stream_state_bytes(s), cudaMemcpyHostToDevice, ctx->stream);
+  const cudaError_t es = cudaStreamSynchronize(ctx->stream);  // (drained on every path)
+  if (e == cudaSuccess) e = es;
+  if (e != cudaSuccess) { s->primed = false; s->has_state = false; return cuda_fail(ctx, e, "afs_tds_stream_load"); }  // (half-loaded: a fresh stream)
   s->primed = h.primed != 0; s->has_state = h.has_state != 0; s->samples = h.samples;
   return AFS_OK;
 }
