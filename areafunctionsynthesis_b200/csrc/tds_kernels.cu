@@ -377,6 +377,9 @@ struct StepCtx {
 // the section, volume velocity into and out of it.
 // (not inlined: taps are rare, and code that is not executed must stay out of the instruction stream of the time loop
 //  -- the kernel lives off its instruction cache)
+// Called from run_role around pass A, for the sections of the warp's segment that are tapped (taps_of): the flows are
+// the solution of the last step, still in the registers when pass A begins; the pressure is there when it ends.  (The
+// calls used to sit in the slot code of pass A: sixteen call sites in the hottest code of the kernel.)
 // (everything by value -- the probe sections packed one per byte: a pointer into the kernel parameters or to the step
 //  context handed to a function that is not inlined would move BOTH to local memory for the whole kernel; the
 //  instantiations with taps ran 1.43 x slower than the plain ones for that reason)
@@ -480,7 +483,6 @@ __device__ __forceinline__ void dwarp_pass_a(const TdsParams &P, TdsSmem &S, con
       wc = wc_new; wcr = wcr_new; wcr2 = wcr2_new;
       S.wall[sec][0][lane] = wc; S.wall[sec][1][lane] = wcr; S.wall[sec][2][lane] = wcr2;
       if (k < 3 && sec <= PHAR0) S.p4[sec - TRACHEA_LAST][lane] = p_new;  // sections 23, 24, 25
-      if (OPT && P.n_probes > 0) tap_section(P.n_probes, P.probe_pack, X.tap_p, X.tap_in, X.tap_out, X.tap_stride, sec, p_new, u, out);
     }
     if (rows) {
       // Tube::interpolate + setPharynxMouthGeometry (Tube.cpp:449-466, 323-350); the index is clamped for the other kinds
@@ -730,7 +732,6 @@ __device__ __forceinline__ void static_section(const TdsParams &P, TdsSmem &S, c
     const double ur = fma(u, P.idt, -c);
     c = fma(ur, P.th, u * P.idt);
     const double p_new = fma(E, u - out, D_old);
-    if (OPT && P.n_probes > 0) tap_section(P.n_probes, P.probe_pack, X.tap_p, X.tap_in, X.tap_out, X.tap_stride, sec, p_new, u, out);
     const double pr_new = (p_new - p) * P.idt - pr * P.th;
     const double wc_new = fma(pr_new, r.alpha, beta_old);
     const double wcr_new = (wc_new - wc) * P.idt - wcr * P.th;
@@ -1913,6 +1914,55 @@ __device__ __noinline__ void stage_interval(TdsSmem &S, const int lane, const in
   }
 }
 
+// Taps (OPT kernels): which slots of this warp's segment hold a tapped section (bit k: slot k; bits 8, 9: sinus leaves).
+__device__ __forceinline__ unsigned taps_of(const TdsParams &P, const int role, const int warp, const SCfg &c) {
+  unsigned m = 0;
+  for (int q = 0; q < P.n_probes; q++) {
+    const int sec = (int)((P.probe_pack >> (8 * q)) & 255ull);
+    if (role == 0) { const int k = sec - (23 + KD * warp); if (k >= 0 && k < KD) m |= 1u << k; }
+    if (role == 1) {
+      const int k = sec - c.base;
+      if (k >= c.ks && k < KS) m |= 1u << k;
+      if (c.leaves && (sec == c.leaf0 || sec == c.leaf0 + 1)) m |= 1u << (8 + sec - c.leaf0);
+    }
+  }
+  return m;
+}
+// before pass A: flows of step n-1 (x still holds its solution); after it: the pressures the update produced
+template <bool AFTER>
+__device__ __forceinline__ void dwarp_taps(const TdsParams &P, TdsSmem &S, const int lane, const int w, const unsigned wc_,
+                                           const DRegs &st, const StepCtx &X, const unsigned mask) {
+  const double outLast = AFTER ? 0.0 : S.uext[wc_out0(wc_)][lane] + S.uext[wc_out1(wc_)][lane];
+#pragma unroll
+  for (int k = 0; k < KD; k++) {
+    if (!((mask >> k) & 1u)) continue;
+    const int sec = 23 + KD * w + k;
+    if (AFTER) tap_section(P.n_probes, P.probe_pack, X.tap_p, nullptr, nullptr, X.tap_stride, sec, st.p[k], 0.0, 0.0);
+    else tap_section(P.n_probes, P.probe_pack, nullptr, X.tap_in, X.tap_out, X.tap_stride, sec, 0.0, st.x[k], k < KD - 1 ? st.x[k + 1] : outLast);
+  }
+}
+template <bool AFTER>
+__device__ __forceinline__ void swarp_taps(const TdsParams &P, TdsSmem &S, const int lane, const unsigned wc_, const SCfg &c,
+                                           const SRegs &st, const StepCtx &X, const unsigned mask) {
+  const double outLast = AFTER ? 0.0 : S.uext[wc_out0(wc_)][lane];
+  const int j0 = c.n2 ? 0 : 5;
+#pragma unroll
+  for (int k = 0; k < KS; k++) {
+    if (!((mask >> k) & 1u)) continue;
+    if (AFTER) { tap_section(P.n_probes, P.probe_pack, X.tap_p, nullptr, nullptr, X.tap_stride, c.base + k, st.p[k], 0.0, 0.0); continue; }
+    double out = (k < KS - 1) ? st.x[k + 1] : outLast;
+    if (k == j0) out += st.lx[0];
+    if (k == j0 + 1) out += st.lx[1];
+    tap_section(P.n_probes, P.probe_pack, nullptr, X.tap_in, X.tap_out, X.tap_stride, c.base + k, 0.0, st.x[k], out);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    if (!((mask >> (8 + j)) & 1u)) continue;
+    if (AFTER) tap_section(P.n_probes, P.probe_pack, X.tap_p, nullptr, nullptr, X.tap_stride, c.leaf0 + j, st.lp[j], 0.0, 0.0);
+    else tap_section(P.n_probes, P.probe_pack, nullptr, X.tap_in, X.tap_out, X.tap_stride, c.leaf0 + j, 0.0, st.lx[j], 0.0);
+  }
+}
+
 // The time loop, one instantiation per warp role.  All roles execute the same sequence of CTA barriers.
 //   ROLE 0: dynamic chain, 1: static chain, 2: X1 (glottis + output), 3: X2 (radiation loads; noise sources)
 template <int ROLE, bool NOISE, bool OPT, bool STATE>
@@ -1939,6 +1989,7 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
   nr.ph = 12; nr.head = 0; nr.free = 0; nr.cap = NZ_RING; nr.lips = 0.0; nr.nm93 = nr.nm94 = 0.0; nr.asp = nan(""); nr.gain = 0.0;
   const SCfg scfg = scfg_of(warp);
   const unsigned wcfg = wcfg_make(warp);
+  const unsigned tapmask = (OPT && P.n_probes > 0 && ROLE <= 1) ? taps_of(P, ROLE, warp, scfg) : 0u;
   if (ROLE == 0) {
 #pragma unroll
     for (int k = 0; k < KD; k++) { dst.p[k] = dst.pr[k] = dst.c[k] = dst.x[k] = dst.y[k] = dst.h[k] = 0.0; }
@@ -2069,6 +2120,10 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         bar_arrive(4, NZ_BAR4);
       }
     }
+    if (OPT && tapmask && X.upd) {  // taps: flows of step n-1
+      if (ROLE == 0) dwarp_taps<false>(P, S, lane, warp, wcfg, dst, X, tapmask);
+      if (ROLE == 1) swarp_taps<false>(P, S, lane, wcfg, scfg, sst, X, tapmask);
+    }
     // (state dump requested for this step: update and rows in two separate passes, the dump in between)
     if (ROLE == 0 && X.upd && X.rows && !X.dumping) dwarp_pass_a<true, OPT>(P, S, lane, warp, wcfg, dst, X);
     else for (int half = 0; half < (X.dumping ? 2 : 1); half++) {
@@ -2081,6 +2136,10 @@ __device__ __forceinline__ void run_role(const TdsParams &P, TdsSmem &S, const K
         if (ROLE == 0) dwarp_dump(P, S, lane, warp, dst, A.dump);
         if (ROLE == 1) swarp_dump(P, S, lane, scfg, sst, A.dump);
       }
+    }
+    if (OPT && tapmask && X.upd) {  // taps: pressures of step n-1
+      if (ROLE == 0) dwarp_taps<true>(P, S, lane, warp, wcfg, dst, X, tapmask);
+      if (ROLE == 1) swarp_taps<true>(P, S, lane, wcfg, scfg, sst, X, tapmask);
     }
     if (ROLE == 2 && n > 1) emit_update(P, xr);  // (the sample emitted in iteration n-1)
     if (ROLE == 2 && NOISE && X.rows) {
