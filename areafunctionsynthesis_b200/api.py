@@ -117,6 +117,13 @@ def load_library():
     lib.afs_group_tds_stream_destroy.argtypes = [vp]
     lib.afs_group_tds_stream_reset.argtypes = [vp]
     lib.afs_group_tds_stream_synthesize.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.afs_group_tds_stream_samples.argtypes = [vp]
+    lib.afs_group_tds_stream_samples.restype = C.c_int64
+    lib.afs_group_tds_stream_checkpoint_bytes.argtypes = [vp]
+    lib.afs_group_tds_stream_checkpoint_bytes.restype = C.c_size_t
+    lib.afs_group_tds_stream_save.argtypes = [vp, vp, C.c_size_t]
+    lib.afs_group_tds_stream_load.argtypes = [vp, vp, C.c_size_t]
+    lib.afs_tds_stream_primed.argtypes = [vp]
     lib.afs_tds_set_state_dump.argtypes = [vp, i32, vp]
     lib.afs_debug_set.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.afs_group_create.argtypes = [C.POINTER(C.c_void_p), vp, i32]
@@ -335,7 +342,8 @@ class TdsStream:
         self._group = isinstance(ctx, Group)
         self._err = None if self._group else ctx.h
         pre = "afs_group_tds_stream_" if self._group else "afs_tds_stream_"
-        self._f = {k: getattr(self.lib, pre + k) for k in ("create", "destroy", "reset", "synthesize")}
+        self._f = {k: getattr(self.lib, pre + k) for k in ("create", "destroy", "reset", "synthesize", "samples", "checkpoint_bytes",
+                                                           "save", "load")}
         _check(self.lib, self._f["create"](ctx.h, C.byref(self.opts), self.n, float(fs_tds_hz), self.sr_factor,
                                            _ptr(s), C.byref(self.h)), self._err)
         self._primed = False
@@ -358,7 +366,7 @@ class TdsStream:
 
     @property
     def samples(self):
-        return int(self.lib.afs_tds_stream_samples(self.h))
+        return int(self._f["samples"](self.h))
 
     def synthesize(self, frames, glottis, frame_len, want_flow=False):
         """frames [B, F], glottis [B, F, 6], frame_len [F]: frame k yields frame_len[k] samples interpolated from the
@@ -379,14 +387,14 @@ class TdsStream:
         return audio, flow, status
 
     def save(self):
-        blob = np.empty(int(self.lib.afs_tds_stream_checkpoint_bytes(self.h)), dtype=np.uint8)
-        _check(self.lib, self.lib.afs_tds_stream_save(self.h, _ptr(blob), blob.size), self.ctx.h)
+        blob = np.empty(int(self._f["checkpoint_bytes"](self.h)), dtype=np.uint8)
+        _check(self.lib, self._f["save"](self.h, _ptr(blob), blob.size), self._err)
         return blob
 
     def load(self, blob):
         blob = np.ascontiguousarray(blob, dtype=np.uint8)
-        _check(self.lib, self.lib.afs_tds_stream_load(self.h, _ptr(blob), blob.size), self.ctx.h)
-        self._primed = bool(np.frombuffer(blob[16:20].tobytes(), dtype=np.int32)[0])  # StreamHeader.primed
+        _check(self.lib, self._f["load"](self.h, _ptr(blob), blob.size), self._err)
+        self._primed = bool(np.frombuffer(blob[16:20].tobytes(), dtype=np.int32)[0])  # StreamHeader.primed (of the first shard)
 
 
 class Context:

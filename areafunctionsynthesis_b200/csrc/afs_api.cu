@@ -1200,6 +1200,7 @@ int afs_tds_stream_reset(afs_tds_stream *s) {
 }
 
 int64_t afs_tds_stream_samples(const afs_tds_stream *s) { return s ? s->samples : -1; }
+int afs_tds_stream_primed(const afs_tds_stream *s) { return s ? (s->primed ? 1 : 0) : -1; }
 
 int afs_tds_stream_synthesize(afs_tds_stream *s, int n_frames, const int32_t *frame_len, const afs_tube_frame *tubes,
                               const double *glottis, double *audio, double *flow, uint32_t *status) {

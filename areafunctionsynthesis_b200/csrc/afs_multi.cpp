@@ -175,6 +175,46 @@ int afs_group_tds_stream_synthesize(afs_group_tds_stream *s, int n_frames, const
   return rc;
 }
 
+// checkpoint / resume of a group stream: the blobs of its per-device streams back to back, in device order
+size_t afs_group_tds_stream_checkpoint_bytes(const afs_group_tds_stream *s) {
+  size_t total = 0;
+  if (s) for (const afs_tds_stream *p : s->part) if (p) total += afs_tds_stream_checkpoint_bytes(p);
+  return total;
+}
+
+int afs_group_tds_stream_save(afs_group_tds_stream *s, void *blob, size_t bytes) {
+  if (!s || !blob || bytes < afs_group_tds_stream_checkpoint_bytes(s)) return AFS_ERR_BAD_ARGUMENT;
+  unsigned char *at = (unsigned char *)blob;
+  for (afs_tds_stream *p : s->part) {
+    if (!p) continue;
+    const size_t b = afs_tds_stream_checkpoint_bytes(p);
+    const int rc = afs_tds_stream_save(p, at, b);
+    if (rc != AFS_OK) return rc;
+    at += b;
+  }
+  return AFS_OK;
+}
+
+int afs_group_tds_stream_load(afs_group_tds_stream *s, const void *blob, size_t bytes) {
+  if (!s || !blob || bytes < afs_group_tds_stream_checkpoint_bytes(s)) return AFS_ERR_BAD_ARGUMENT;
+  const unsigned char *at = (const unsigned char *)blob;
+  for (afs_tds_stream *p : s->part) {
+    if (!p) continue;
+    const size_t b = afs_tds_stream_checkpoint_bytes(p);
+    const int rc = afs_tds_stream_load(p, at, b);  // (refuses a blob of another sharding: the batch sizes differ)
+    if (rc != AFS_OK) { afs_group_tds_stream_reset(s); return rc; }
+    at += b;
+  }
+  s->primed = false;
+  for (const afs_tds_stream *p : s->part) if (p && afs_tds_stream_primed(p) > 0) s->primed = true;
+  return AFS_OK;
+}
+
+int64_t afs_group_tds_stream_samples(const afs_group_tds_stream *s) {
+  if (s) for (const afs_tds_stream *p : s->part) if (p) return afs_tds_stream_samples(p);
+  return -1;
+}
+
 int afs_host_alloc(void **ptr, size_t bytes) {
   if (!ptr) return AFS_ERR_BAD_ARGUMENT;
   *ptr = nullptr;

@@ -471,6 +471,8 @@ int afs_tds_stream_create(afs_ctx *ctx, const afs_tds_options *opts, int n_tract
 int afs_tds_stream_destroy(afs_tds_stream *stream);
 int afs_tds_stream_reset(afs_tds_stream *stream);
 int64_t afs_tds_stream_samples(const afs_tds_stream *stream);
+/* 1 once the stream holds a previous frame (the next frame produces samples), 0 before the priming frame. */
+int afs_tds_stream_primed(const afs_tds_stream *stream);
 int afs_tds_stream_synthesize(afs_tds_stream *stream, int n_frames, const int32_t *frame_len, const afs_tube_frame *tubes,
                               const double *glottis, double *audio, double *flow, uint32_t *status);
 size_t afs_tds_stream_checkpoint_bytes(const afs_tds_stream *stream);
@@ -534,6 +536,11 @@ int afs_group_tds_stream_reset(afs_group_tds_stream *stream);
 int afs_group_tds_stream_synthesize(afs_group_tds_stream *stream, int n_frames, const int32_t *frame_len,
                                     const afs_tube_frame *tubes, const double *glottis, double *audio, double *flow,
                                     uint32_t *status);
+int64_t afs_group_tds_stream_samples(const afs_group_tds_stream *stream);
+/* checkpoint / resume: the blobs of the per-device streams back to back (a blob belongs to one sharding) */
+size_t afs_group_tds_stream_checkpoint_bytes(const afs_group_tds_stream *stream);
+int afs_group_tds_stream_save(afs_group_tds_stream *stream, void *blob, size_t bytes);
+int afs_group_tds_stream_load(afs_group_tds_stream *stream, const void *blob, size_t bytes);
 /* Page-locked host memory (cudaHostAlloc, portable across the devices of a group). */
 int afs_host_alloc(void **ptr, size_t bytes);
 int afs_host_free(void *ptr);

@@ -308,6 +308,23 @@ class TdsSynthesizer {
     clearQueue();
     continuing_ = true;
   }
+  // Checkpoint / resume of the models kept by flushAndContinue (afs_tds_stream_save / _load): restore() accepts the
+  // blob of a synthesizer with the same number of utterances, rates, options and devices.
+  std::vector<unsigned char> checkpoint() {
+    if (!stream_ && !gstream_) throw Error(AFS_ERR_BAD_ARGUMENT, "no live models: call flushAndContinue first");
+    std::vector<unsigned char> blob(stream_ ? afs_tds_stream_checkpoint_bytes(stream_) : afs_group_tds_stream_checkpoint_bytes(gstream_));
+    if (stream_) check(afs_tds_stream_save(stream_, blob.data(), blob.size()), dev_->ctx());
+    else check(afs_group_tds_stream_save(gstream_, blob.data(), blob.size()));
+    return blob;
+  }
+  void restore(const std::vector<unsigned char> &blob) {
+    clearQueue();
+    if (dev_ && !stream_) check(afs_tds_stream_create(dev_->ctx(), &options, n_, samplingRate * tdsSrFactor, tdsSrFactor, nullptr, &stream_), dev_->ctx());
+    if (group_ && !gstream_) check(afs_group_tds_stream_create(group_->group(), &options, n_, samplingRate * tdsSrFactor, tdsSrFactor, nullptr, &gstream_));
+    if (stream_) check(afs_tds_stream_load(stream_, blob.data(), blob.size()), dev_->ctx());
+    else check(afs_group_tds_stream_load(gstream_, blob.data(), blob.size()));
+    continuing_ = stream_ ? afs_tds_stream_primed(stream_) > 0 : afs_group_tds_stream_samples(gstream_) > 0;
+  }
   // Runs the queued frames; audio[n][sum(numNewSamples)] in [-1, 1]; flow (optional) per simulation step.
   void flush(std::vector<double> *audio, std::vector<double> *flow = nullptr, std::vector<uint32_t> *status = nullptr) {
     if (frames_ < 2) throw Error(AFS_ERR_BAD_ARGUMENT, "need at least two control frames");

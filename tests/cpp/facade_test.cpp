@@ -83,8 +83,15 @@ int main() {
       chunked.synthesizeSignalTds(tubes, g, 0);
       chunked.synthesizeSignalTds(tubes, g, 551);
       chunked.flushAndContinue(&a1);
+      const std::vector<unsigned char> blob = chunked.checkpoint();
       chunked.synthesizeSignalTds(tubes, g, 551);
       chunked.flushAndContinue(&a2);
+      afs::TdsSynthesizer resumed(dev, 2);   // a new object continues from the checkpoint, bit for bit
+      std::vector<double> a3;
+      resumed.restore(blob);
+      resumed.synthesizeSignalTds(tubes, g, 551);
+      resumed.flushAndContinue(&a3);
+      if (a3 != a2) { std::printf("error 99 restored stream differs\n"); return 2; }
       double ce = 0;
       for (double v : a1) ce += v * v;
       for (double v : a2) ce += v * v;

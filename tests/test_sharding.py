@@ -90,8 +90,15 @@ def test_device_group_equals_single_device(shapes):
         # chunked synthesis over the group: every device keeps the models of its shard between calls
         gs = afs.TdsStream(g, B, 44100.0, 2, seeds=seeds)
         p1, _, _ = gs.synthesize(fr, gl, [0, 120])
+        blob = gs.save()                                   # checkpoint of the group stream -> a new one continues bit for bit
         p2, _, _ = gs.synthesize(fr[:, :1], gl[:, :1], [60])
         gs.close()
+        gs = afs.TdsStream(g, B, 44100.0, 2)
+        gs.load(blob)
+        assert gs.samples == 120
+        p3, _, _ = gs.synthesize(fr[:, :1], gl[:, :1], [60])
+        gs.close()
+        assert np.array_equal(p2, p3)
         ss = afs.TdsStream(g_one, B, 44100.0, 2, seeds=seeds)
         q1, _, _ = ss.synthesize(fr, gl, [0, 120])
         q2, _, _ = ss.synthesize(fr[:, :1], gl[:, :1], [60])
